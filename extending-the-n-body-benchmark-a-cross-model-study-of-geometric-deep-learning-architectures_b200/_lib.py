@@ -1,0 +1,64 @@
+"""ctypes binding of libsegnn_b200.so (the C ABI in include/segnn_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing the import fails loudly, and every
+entry point raises on a non-zero return code with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsegnn_b200.so")
+
+MODE_FP32 = 0
+MODE_BF16_TC = 1
+
+_c = ctypes
+_ptr = _c.c_void_p
+_int = _c.c_int
+
+# name -> (restype, argtypes); must list every symbol include/segnn_b200.h declares
+PROTOTYPES = {
+    "segnn_version": (_int, []),
+    "segnn_last_error": (_c.c_char_p, []),
+    "segnn_edge_index": (_int, [_int, _int, _ptr, _ptr]),
+    "segnn_edge_attr": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_prep_fwd": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_embed_fwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
+    "segnn_node_gemm": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
+    "segnn_tp_combine": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_edge_layer_fwd": (_int, [_int, _ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                    _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_pack_w2_tc": (_c.c_int64, [_ptr, _ptr, _ptr, _ptr, _int, _ptr, _ptr]),
+    "segnn_head_fwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
+    "segnn_integrate": (_int, [_ptr, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_counter_add": (_int, [_ptr, _int, _ptr]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the sm_100a kernels first (python -c 'import __graft_entry__ as g; "
+            f"g.build()' or csrc/build.sh). There is no CPU or PyTorch fallback for the SEGNN hot path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class SegnnKernelError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.segnn_last_error()
+        raise SegnnKernelError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,478 @@
+// Node-level kernels of the SEGNN hot path: graph/geometry materialisation (tests only), K1 prep,
+// K2 embedding, the node GEMM, the attribute combine, the head and the self-feed integrator.
+#include <stdarg.h>
+
+#include "segnn_common.cuh"
+
+namespace segnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph enumeration + edge attributes (materialised for parity tests / legacy consumers only)
+// ------------------------------------------------------------------------------------------------
+
+__global__ void edge_index_kernel(int B, int N, int64_t* __restrict__ ei) {
+  const int64_t per = (int64_t)N * (N - 1);
+  const int64_t E = per * B;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g = e / per;
+    int64_t r = e - g * per;
+    int a = (int)(r / (N - 1));
+    int b = (int)(r - (int64_t)a * (N - 1));
+    b += (b >= a);
+    ei[e] = g * N + a;      // source / sender
+    ei[E + e] = g * N + b;  // target / receiver
+  }
+}
+
+__global__ void edge_attr_kernel(const float* __restrict__ pos, const float* __restrict__ mass, int B, int N,
+                                 float* __restrict__ edge_attr, float* __restrict__ add) {
+  const int64_t per = (int64_t)N * (N - 1);
+  const int64_t E = per * B;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g = e / per;
+    int64_t r = e - g * per;
+    int a = (int)(r / (N - 1));
+    int b = (int)(r - (int64_t)a * (N - 1));
+    b += (b >= a);
+    int64_t s = g * N + a, t = g * N + b;
+    float ux, uy, uz, len;
+    unit_vec(pos[s * 3 + 0] - pos[t * 3 + 0], pos[s * 3 + 1] - pos[t * 3 + 1], pos[s * 3 + 2] - pos[t * 3 + 2], ux,
+             uy, uz, len);
+    edge_attr[e * 4 + 0] = kY0;
+    edge_attr[e * 4 + 1] = kY1 * ux;
+    edge_attr[e * 4 + 2] = kY1 * uy;
+    edge_attr[e * 4 + 3] = kY1 * uz;
+    add[e * 2 + 0] = len;
+    add[e * 2 + 1] = mass[s] * mass[t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 prep: node_attr = mean_j Y(r_j - r_i) + Y(v_i) with the l=0 slot forced to 1; x = [pos - mean_xyz, vel, |vel|]
+// One thread per receiver; the graph's positions are staged in shared memory in sender tiles.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kPrepThreads = 128;
+
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(const float* __restrict__ pos,
+                                                           const float* __restrict__ vel, int B, int N,
+                                                           float* __restrict__ x_in, float* __restrict__ node_attr) {
+  // grid.y = graph, grid.x = receiver tile inside the graph
+  __shared__ float sp[kPrepThreads * 3];
+  const int g = blockIdx.y;
+  const int i = blockIdx.x * kPrepThreads + threadIdx.x;
+  const int64_t base = (int64_t)g * N;
+  const bool live = i < N;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  if (live) {
+    px = pos[(base + i) * 3 + 0];
+    py = pos[(base + i) * 3 + 1];
+    pz = pos[(base + i) * 3 + 2];
+  }
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int j0 = 0; j0 < N; j0 += kPrepThreads) {
+    int cnt = min(kPrepThreads, N - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt * 3; t += kPrepThreads) sp[t] = pos[(base + j0) * 3 + t];
+    __syncthreads();
+    if (live) {
+      for (int j = 0; j < cnt; ++j) {
+        if (j0 + j == i) continue;
+        float ux, uy, uz, len;
+        unit_vec(sp[j * 3 + 0] - px, sp[j * 3 + 1] - py, sp[j * 3 + 2] - pz, ux, uy, uz, len);
+        sx += ux;
+        sy += uy;
+        sz += uz;
+      }
+    }
+  }
+  if (!live) return;
+  const int64_t node = base + i;
+  float vx = vel[node * 3 + 0], vy = vel[node * 3 + 1], vz = vel[node * 3 + 2];
+  float ux, uy, uz, vlen;
+  unit_vec(vx, vy, vz, ux, uy, uz, vlen);
+  float inv_deg = N > 1 ? 1.0f / (float)(N - 1) : 0.0f;
+  node_attr[node * 4 + 0] = 1.0f;
+  node_attr[node * 4 + 1] = kY1 * (sx * inv_deg) + kY1 * ux;
+  node_attr[node * 4 + 2] = kY1 * (sy * inv_deg) + kY1 * uy;
+  node_attr[node * 4 + 3] = kY1 * (sz * inv_deg) + kY1 * uz;
+  float m = (px + py + pz) / 3.0f;  // reference quirk: mean over xyz of the node (o3_building_blocks.py:274)
+  float* x = x_in + node * 7;
+  x[0] = px - m;
+  x[1] = py - m;
+  x[2] = pz - m;
+  x[3] = vx;
+  x[4] = vy;
+  x[5] = vz;
+  x[6] = vlen;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 embedding: O3TensorProduct(2x1o + 1x0e -> n x0e + n x1o) steered by node_attr; K = 3, elementwise.
+// ------------------------------------------------------------------------------------------------
+
+__global__ void embed_kernel(const float* __restrict__ x_in, const float* __restrict__ node_attr,
+                             const float* __restrict__ w, const float* __restrict__ bias, int nodes, int n,
+                             float* __restrict__ h) {
+  const int64_t total = (int64_t)nodes * n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t node = idx / n;
+    const int c = (int)(idx - node * n);
+    const float* x = x_in + node * 7;
+    const float a0 = node_attr[node * 4 + 0], ax = node_attr[node * 4 + 1], ay = node_attr[node * 4 + 2],
+                az = node_attr[node * 4 + 3];
+    const float w_p1 = w[0 * n + c], w_v1 = w[1 * n + c], w_p0 = w[2 * n + c], w_v0 = w[3 * n + c],
+                w_s0 = w[4 * n + c], w_s1 = w[5 * n + c];
+    const float pdot = x[0] * ax + x[1] * ay + x[2] * az;
+    const float vdot = x[3] * ax + x[4] * ay + x[5] * az;
+    const float s = x[6];
+    float* out = h + node * 4 * n;
+    out[c] = a0 * w_s0 * s + w_p0 * pdot + w_v0 * vdot + bias[c];
+    const float t = w_s1 * s;
+    out[1 * n + c] = ax * t + a0 * (w_p1 * x[0] + w_v1 * x[3]);
+    out[2 * n + c] = ay * t + a0 * (w_p1 * x[1] + w_v1 * x[4]);
+    out[3 * n + c] = az * t + a0 * (w_p1 * x[2] + w_v1 * x[5]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Node GEMM (fp32 FFMA): y[node][c][:] = cat_K(x0[node][c], x1[node][c]) @ (c == 0 ? w_s : w_v)
+// grid.z selects the row class (0: scalar planes, 1: the three vector planes), so one launch covers both.
+// 64x64 tile, BK = 16, 256 threads, 4x4 outputs per thread.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16;
+
+__global__ void __launch_bounds__(256) node_gemm_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
+                                                      int nodes, int n_in, const float* __restrict__ w_s,
+                                                      const float* __restrict__ w_v, const float* __restrict__ bias,
+                                                      int n_bias, int n_out, float* __restrict__ y) {
+  __shared__ float As[kGemmBK][kGemmBM + 4];
+  __shared__ float Bs[kGemmBK][kGemmBN + 4];
+  const int cls = blockIdx.z;  // 0 scalar rows, 1 vector rows
+  const int64_t rows = cls == 0 ? (int64_t)nodes : (int64_t)nodes * 3;
+  const int64_t row0 = (int64_t)blockIdx.x * kGemmBM;
+  if (row0 >= rows) return;
+  const int col0 = blockIdx.y * kGemmBN;
+  const float* __restrict__ W = cls == 0 ? w_s : w_v;
+  const int K = x1 ? 2 * n_in : n_in;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  // A-tile loader: thread -> (row = tid / 4, 4 consecutive k at (tid % 4) * 4)
+  const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+  const int64_t ar = row0 + a_row;
+  int64_t a_plane = -1;  // (node * 4 + c)
+  if (ar < rows) a_plane = cls == 0 ? ar * 4 : (ar / 3) * 4 + 1 + (ar % 3);
+  // B-tile loader: thread -> (k = tid / 16, 4 consecutive cols at (tid % 16) * 4)
+  const int b_k = tid >> 4, b_c = (tid & 15) * 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += kGemmBK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int k = k0 + a_k + q;
+      float v = 0.f;
+      if (a_plane >= 0 && k < K) v = k < n_in ? x0[a_plane * n_in + k] : x1[a_plane * n_in + (k - n_in)];
+      As[a_k + q][a_row] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int k = k0 + b_k, c = col0 + b_c + q;
+      Bs[b_k][b_c + q] = (k < K && c < n_out) ? W[(int64_t)k * n_out + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kGemmBK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t r = row0 + ty * 4 + i;
+    if (r >= rows) continue;
+    int64_t plane = cls == 0 ? r * 4 : (r / 3) * 4 + 1 + (r % 3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = col0 + tx * 4 + j;
+      if (c >= n_out) continue;
+      float v = acc[i][j];
+      if (cls == 0 && bias != nullptr && c < n_bias) v += bias[c];
+      y[plane * n_out + c] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attribute combine + gate / residual / eval-BN epilogue of a node-level tensor product.
+// ------------------------------------------------------------------------------------------------
+
+template <bool GATE>
+__global__ void tp_combine_kernel(const float* __restrict__ y, const float* __restrict__ node_attr, int nodes, int n,
+                                  const float* __restrict__ bias, const float* __restrict__ residual,
+                                  const float* __restrict__ bn_mul,
+                                  const float* __restrict__ bn_add, float* __restrict__ out) {
+  const int n0 = GATE ? 2 * n : n;
+  const int n_out = n0 + n;
+  const int64_t total = (int64_t)nodes * n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t node = idx / n;
+    const int w = (int)(idx - node * n);
+    const float a0 = node_attr[node * 4 + 0], ax = node_attr[node * 4 + 1], ay = node_attr[node * 4 + 2],
+                az = node_attr[node * 4 + 3];
+    const float* y0 = y + node * 4 * n_out;
+    const float* y1 = y0 + n_out;
+    const float* y2 = y1 + n_out;
+    const float* y3 = y2 + n_out;
+    float zs = a0 * y0[w] + ax * y1[w] + ay * y2[w] + az * y3[w];
+    if (bias != nullptr) zs += bias[w];
+    const float t = y0[n0 + w];
+    float vx = ax * t + a0 * y1[n0 + w];
+    float vy = ay * t + a0 * y2[n0 + w];
+    float vz = az * t + a0 * y3[n0 + w];
+    if (GATE) {
+      float zg = a0 * y0[n + w] + ax * y1[n + w] + ay * y2[n + w] + az * y3[n + w];
+      if (bias != nullptr) zg += bias[n + w];
+      float g = sig_gate(zg);
+      zs = silu_gate(zs);
+      vx *= g;
+      vy *= g;
+      vz *= g;
+    }
+    const int64_t o = node * 4 * n;
+    if (residual != nullptr) {
+      zs += residual[o + w];
+      vx += residual[o + n + w];
+      vy += residual[o + 2 * n + w];
+      vz += residual[o + 3 * n + w];
+    }
+    if (bn_mul != nullptr) {
+      const float ms = bn_mul[w], mv = bn_mul[n + w];
+      zs = fmaf(zs, ms, bn_add[w]);
+      vx *= mv;
+      vy *= mv;
+      vz *= mv;
+    }
+    out[o + w] = zs;
+    out[o + n + w] = vx;
+    out[o + 2 * n + w] = vy;
+    out[o + 3 * n + w] = vz;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head: pre_pool2 (h -> 2x1o), one warp per node; and the self-feed integrator.
+// ------------------------------------------------------------------------------------------------
+
+__global__ void head_kernel(const float* __restrict__ h, const float* __restrict__ node_attr,
+                            const float* __restrict__ w_head, int nodes, int n, float* __restrict__ pred) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float* ws = w_head;          // [n][2]  scalar -> 1o (times a1)
+  const float* wv = w_head + 2 * n;  // [n][2]  vector -> 1o (times a0)
+  for (int64_t node = warp; node < nodes; node += nwarps) {
+    const float* hn = h + node * 4 * n;
+    float t[2] = {0.f, 0.f};
+    float d[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    for (int u = lane; u < n; u += 32) {
+      float s = hn[u], vx = hn[n + u], vy = hn[2 * n + u], vz = hn[3 * n + u];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        float a = ws[u * 2 + o], b = wv[u * 2 + o];
+        t[o] = fmaf(a, s, t[o]);
+        d[o][0] = fmaf(b, vx, d[o][0]);
+        d[o][1] = fmaf(b, vy, d[o][1]);
+        d[o][2] = fmaf(b, vz, d[o][2]);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        t[o] += __shfl_xor_sync(0xffffffffu, t[o], off);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[o][k] += __shfl_xor_sync(0xffffffffu, d[o][k], off);
+      }
+    }
+    if (lane == 0) {
+      const float a0 = node_attr[node * 4 + 0];
+      const float a1[3] = {node_attr[node * 4 + 1], node_attr[node * 4 + 2], node_attr[node * 4 + 3]};
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pred[node * 6 + o * 3 + k] = a1[k] * t[o] + a0 * d[o][k];
+    }
+  }
+}
+
+__global__ void integrate_kernel(const float* __restrict__ pred, float* __restrict__ pos, float* __restrict__ vel,
+                                 int nodes, float* __restrict__ traj_pos, float* __restrict__ traj_vel,
+                                 const int* __restrict__ frame) {
+  const int64_t total = (int64_t)nodes * 3;
+  if (frame != nullptr) {  // frame slot chosen on the device so a captured CUDA graph can be replayed
+    const int64_t off = (int64_t)(*frame) * total;
+    if (traj_pos) traj_pos += off;
+    if (traj_vel) traj_vel += off;
+  }
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t node = idx / 3;
+    const int k = (int)(idx - node * 3);
+    float p = pos[idx] + pred[node * 6 + k];
+    float v = pred[node * 6 + 3 + k];
+    pos[idx] = p;
+    vel[idx] = v;
+    if (traj_pos) traj_pos[idx] = p;
+    if (traj_vel) traj_vel[idx] = v;
+  }
+}
+
+static inline int grid_for(int64_t total, int threads) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = 148LL * 32;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace segnn
+
+using namespace segnn;
+
+extern "C" {
+
+int segnn_version(void) { return 100; }
+const char* segnn_last_error(void) { return g_err; }
+
+int segnn_edge_index(int B, int N, int64_t* edge_index, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(B >= 0 && N >= 1, "need B >= 0, N >= 1");
+  int64_t E = (int64_t)B * N * (N - 1);
+  if (E == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(edge_index != nullptr, "null edge_index");
+  edge_index_kernel<<<grid_for(E, 256), 256, 0, (cudaStream_t)stream>>>(B, N, edge_index);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_edge_attr(const float* pos, const float* mass, int B, int N, float* edge_attr, float* add,
+                    segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(B >= 0 && N >= 1, "need B >= 0, N >= 1");
+  int64_t E = (int64_t)B * N * (N - 1);
+  if (E == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pos && mass && edge_attr && add, "null pointer");
+  edge_attr_kernel<<<grid_for(E, 256), 256, 0, (cudaStream_t)stream>>>(pos, mass, B, N, edge_attr, add);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_prep_fwd(const float* pos, const float* vel, int B, int N, float* x_in, float* node_attr,
+                   segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(B >= 0 && N >= 1, "need B >= 0, N >= 1");
+  if (B == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pos && vel && x_in && node_attr, "null pointer");
+  SEGNN_CHECK_ARG(B <= 65535, "B > 65535 graphs per call: split the batch");
+  dim3 grid((N + kPrepThreads - 1) / kPrepThreads, B);
+  prep_kernel<<<grid, kPrepThreads, 0, (cudaStream_t)stream>>>(pos, vel, B, N, x_in, node_attr);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_embed_fwd(const float* x_in, const float* node_attr, const float* w_embed, const float* bias, int nodes,
+                    int n, float* h_out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n >= 1, "need nodes >= 0, n >= 1");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x_in && node_attr && w_embed && bias && h_out, "null pointer");
+  embed_kernel<<<grid_for((int64_t)nodes * n, 256), 256, 0, (cudaStream_t)stream>>>(x_in, node_attr, w_embed, bias,
+                                                                                 nodes, n, h_out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const float* w_s, const float* w_v,
+                    const float* bias, int n_bias, int n_out, float* y, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n_in >= 1 && n_out >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x0 && w_s && w_v && y, "null pointer");
+  SEGNN_CHECK_ARG(bias == nullptr || (n_bias >= 0 && n_bias <= n_out), "n_bias out of range");
+  int64_t row_tiles = ((int64_t)nodes * 3 + kGemmBM - 1) / kGemmBM;
+  SEGNN_CHECK_ARG(row_tiles < (1LL << 31), "too many rows");
+  dim3 grid((unsigned)row_tiles, (n_out + kGemmBN - 1) / kGemmBN, 2);
+  node_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, x1, nodes, n_in, w_s, w_v, bias, n_bias, n_out, y);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_tp_combine(const float* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                     const float* residual, const float* bn_mul, const float* bn_add, float* out,
+                     segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(y && node_attr && out, "null pointer");
+  SEGNN_CHECK_ARG((bn_mul == nullptr) == (bn_add == nullptr), "bn_mul and bn_add must be given together");
+  int grid = grid_for((int64_t)nodes * n, 256);
+  if (gate)
+    tp_combine_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(y, node_attr, nodes, n, bias, residual, bn_mul,
+                                                                   bn_add, out);
+  else
+    tp_combine_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(y, node_attr, nodes, n, bias, residual, bn_mul,
+                                                                    bn_add, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_head_fwd(const float* h, const float* node_attr, const float* w_head, int nodes, int n, float* pred,
+                   segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(h && node_attr && w_head && pred, "null pointer");
+  head_kernel<<<grid_for((int64_t)nodes * 32, 256), 256, 0, (cudaStream_t)stream>>>(h, node_attr, w_head, nodes, n,
+                                                                                  pred);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+__global__ void counter_add_kernel(int* ctr, int delta) { *ctr += delta; }
+
+int segnn_counter_add(int* counter, int delta, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(counter != nullptr, "null counter");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_integrate(const float* pred, float* pos, float* vel, int nodes, float* traj_pos, float* traj_vel,
+                    const int* frame, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pred && pos && vel, "null pointer");
+  integrate_kernel<<<grid_for((int64_t)nodes * 3, 256), 256, 0, (cudaStream_t)stream>>>(pred, pos, vel, nodes,
+                                                                                      traj_pos, traj_vel, frame);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+"""Host-side mirror of models/segnn/o3_building_blocks.py: same class names, constructor arguments, parameter
+names (``tp.weight``, ``biases``) and initialisation, with the arithmetic running in the sm_100a kernels."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops, packing
+from .graph import infer_graph_shape
+from .irreps import Irreps, tp_instructions
+
+
+class _TensorProductWeights(nn.Module):
+    """Stands where e3nn's FullyConnectedTensorProduct sits in the reference (attribute ``tp``): owns the flat
+    ``weight`` parameter in e3nn's instruction order."""
+
+    def __init__(self, irreps_in1, irreps_in2, irreps_out):
+        super().__init__()
+        self.irreps_in1, self.irreps_in2, self.irreps_out = Irreps(irreps_in1), Irreps(irreps_in2), Irreps(irreps_out)
+        self.instructions, self.weight_numel = tp_instructions(self.irreps_in1, self.irreps_in2, self.irreps_out)
+        self.weight = nn.Parameter(torch.empty(self.weight_numel))
+
+    def weight_views(self):
+        return [self.weight[i["offset"]: i["offset"] + math.prod(i["shape"])].view(i["shape"])
+                for i in self.instructions]
+
+
+class O3TensorProduct(nn.Module):
+    """models/segnn/o3_building_blocks.py:10-167. Parameters: ``tp.weight`` (flat), ``biases`` (one per l=0 output).
+    Initialisation follows tensor_product_init (:79-116): U(-1/sqrt(fan_in), 1/sqrt(fan_in)) per output slice."""
+
+    def __init__(self, irreps_in1, irreps_out, irreps_in2=None, tp_rescale=True) -> None:
+        super().__init__()
+        if not tp_rescale:
+            raise NotImplementedError("tp_rescale=False is never used by the SEGNN path")
+        self.irreps_in1, self.irreps_out = Irreps(str(irreps_in1)), Irreps(str(irreps_out))
+        self.irreps_in2_provided = irreps_in2 is not None
+        self.irreps_in2 = Irreps(str(irreps_in2)) if irreps_in2 is not None else Irreps("1x0e")
+        self.tp_rescale = tp_rescale
+        self.tp = _TensorProductWeights(self.irreps_in1, self.irreps_in2, self.irreps_out)
+        fan = {}
+        for ins in self.tp.instructions:
+            fan[ins["io"]] = fan.get(ins["io"], 0) + ins["shape"][0] * ins["shape"][1]
+        self.slices_fan_in = fan
+        with torch.no_grad():
+            for ins, view in zip(self.tp.instructions, self.tp.weight_views()):
+                k = 1.0 / math.sqrt(fan[ins["io"]])
+                view.uniform_(-k, k)
+            biases = []
+            for io, (mul, l, _) in enumerate(self.irreps_out):
+                if l == 0:
+                    k = 1.0 / math.sqrt(fan[io])
+                    biases.append(torch.empty(mul).uniform_(-k, k))
+        self.biases = nn.Parameter(torch.cat(biases)) if biases else None
+
+    # -- generic module-level forward (node rows, hidden irreps): used for API parity, not by SEGNN.forward ----
+    def _node_forward(self, data_in1, data_in2, gate: bool):
+        n_out = self.irreps_out[-1][0]
+        n_in = self.irreps_in1[0][0]
+        n_blocks = len(self.irreps_in1) // 2
+        hid = [(n_in, 0, 1), (n_in, 1, -1)] * n_blocks
+        n0 = self.irreps_out[0][0]
+        if list(self.irreps_in1) != hid or list(self.irreps_out) != [(n0, 0, 1), (n_out, 1, -1)] \
+                or list(self.irreps_in2) != [(1, 0, 1), (1, 1, -1)] or n_in != n_out or n_blocks > 2:
+            raise NotImplementedError(
+                f"standalone O3TensorProduct forward is built for hidden->hidden irreps only, got "
+                f"{self.irreps_in1} x {self.irreps_in2} -> {self.irreps_out}")
+        w = packing.pack_node_tp(self.tp.weight.detach().float(), self.biases.detach().float(), n_blocks, n_in, n0)
+        x = data_in1.float()
+        xs = [packing.to_planar(x[:, b * 4 * n_in:(b + 1) * 4 * n_in], n_in) for b in range(n_blocks)]
+        attr = data_in2.float().contiguous()
+        y = ops.node_gemm(xs[0], xs[1] if n_blocks == 2 else None, w["w_s"], w["w_v"], None, 0, n0 + n_out)
+        out = ops.tp_combine(y, attr, n_out, gate, bias=w["bias"])
+        return packing.from_planar(out).to(data_in1.dtype)
+
+    def forward(self, data_in1, data_in2=None) -> torch.Tensor:
+        return self._node_forward(data_in1, data_in2, gate=False)
+
+
+class O3TensorProductSwishGate(O3TensorProduct):
+    """models/segnn/o3_building_blocks.py:170-203: the TP output carries one extra scalar per gated irrep; e3nn Gate
+    (SiLU on scalars, sigmoid gates, both normalize2mom-scaled) is fused into the kernels' epilogues."""
+
+    def __init__(self, irreps_in1, irreps_out, irreps_in2=None) -> None:
+        irreps_out = Irreps(str(irreps_out))
+        scalars = Irreps([irreps_out[0]])
+        gated = irreps_out[1:]
+        gates = Irreps([(gated.num_irreps, 0, 1)])
+        irreps_g = (scalars + gates + gated).simplify()
+        super().__init__(irreps_in1, irreps_g, irreps_in2)
+        self.irreps_gated_out = irreps_out
+
+    def forward(self, data_in1, data_in2=None) -> torch.Tensor:
+        return self._node_forward(data_in1, data_in2, gate=True)
+
+
+class BatchNorm(nn.Module):
+    """Parameter/buffer holder with e3nn.nn.BatchNorm's names and shapes (models/segnn/segnn.py:233-235):
+    weight [num_irreps], bias [n_scalar], running_mean [n_scalar], running_var [num_irreps]."""
+
+    def __init__(self, irreps, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.irreps = Irreps(str(irreps))
+        self.eps, self.momentum = eps, momentum
+        n_scalar = sum(m for m, l, p in self.irreps if l == 0 and p == 1)
+        n_feat = self.irreps.num_irreps
+        self.register_buffer("running_mean", torch.zeros(n_scalar))
+        self.register_buffer("running_var", torch.ones(n_feat))
+        self.weight = nn.Parameter(torch.ones(n_feat))
+        self.bias = nn.Parameter(torch.zeros(n_scalar))
+
+
+class O3Transform:
+    """models/segnn/o3_building_blocks.py:225-278. Runs K1 (node_attr, x) and leaves the per-edge quantities
+    implicit; they are recomputed in registers inside the fused edge kernel."""
+
+    def __init__(self, lmax_attr, use_force_input=False):
+        if int(lmax_attr) != 1:
+            raise NotImplementedError("the accelerated SEGNN path is built for lmax_attr = 1")
+        if use_force_input:
+            raise NotImplementedError("use_force_input is never set on the configured path")
+        self.attr_irreps = Irreps.spherical_harmonics(int(lmax_attr))
+        self.use_force_input = use_force_input
+
+    def __call__(self, graph):
+        b, n = infer_graph_shape(graph)
+        graph.num_graphs, graph.n_nodes = b, n
+        x, attr = ops.prep(graph.pos, graph.vel, b, n)
+        graph.x = x.to(graph.pos.dtype)
+        graph.node_attr = attr.to(graph.pos.dtype)
+        return graph

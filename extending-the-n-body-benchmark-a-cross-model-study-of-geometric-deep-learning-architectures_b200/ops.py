@@ -1,0 +1,150 @@
+"""Tensor-level wrappers over the C ABI: validate, allocate outputs with torch, launch on torch's current
+stream. PyTorch is plumbing here (device memory + streams); all arithmetic happens in libsegnn_b200.so."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from ._lib import MODE_BF16_TC, MODE_FP32, check, lib
+
+__all__ = ["edge_index", "edge_attr", "prep", "embed", "node_gemm", "tp_combine", "edge_layer", "head",
+           "integrate", "counter_add", "launch_count", "MODE_FP32", "MODE_BF16_TC"]
+
+_launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _bump(k: int = 1) -> None:
+    global _launches
+    _launches += k
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the SEGNN hot path has no CPU fallback")
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()
+
+
+def edge_index(batch_size: int, num_nodes: int, device) -> torch.Tensor:
+    E = batch_size * num_nodes * (num_nodes - 1)
+    out = torch.empty((2, E), dtype=torch.int64, device=device)
+    if not out.is_cuda:
+        raise RuntimeError("edge_index needs a CUDA device")
+    with torch.cuda.device(out.device):
+        check(lib.segnn_edge_index(batch_size, num_nodes, _p(out), _stream()), "segnn_edge_index")
+    _bump()
+    return out
+
+
+def edge_attr(pos: torch.Tensor, mass: torch.Tensor, batch_size: int, num_nodes: int):
+    pos, mass = _f32(pos, "pos"), _f32(mass, "mass").reshape(-1)
+    E = batch_size * num_nodes * (num_nodes - 1)
+    ea = torch.empty((E, 4), dtype=torch.float32, device=pos.device)
+    add = torch.empty((E, 2), dtype=torch.float32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        check(lib.segnn_edge_attr(_p(pos), _p(mass), batch_size, num_nodes, _p(ea), _p(add), _stream()),
+              "segnn_edge_attr")
+    _bump()
+    return ea, add
+
+
+def prep(pos: torch.Tensor, vel: torch.Tensor, batch_size: int, num_nodes: int):
+    pos, vel = _f32(pos, "pos"), _f32(vel, "vel")
+    nodes = batch_size * num_nodes
+    assert pos.shape == (nodes, 3) and vel.shape == (nodes, 3), (pos.shape, vel.shape, nodes)
+    x_in = torch.empty((nodes, 7), dtype=torch.float32, device=pos.device)
+    attr = torch.empty((nodes, 4), dtype=torch.float32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        check(lib.segnn_prep_fwd(_p(pos), _p(vel), batch_size, num_nodes, _p(x_in), _p(attr), _stream()),
+              "segnn_prep_fwd")
+    _bump()
+    return x_in, attr
+
+
+def embed(x_in, node_attr, w_embed, bias, n: int):
+    nodes = x_in.shape[0]
+    h = torch.empty((nodes, 4, n), dtype=torch.float32, device=x_in.device)
+    with torch.cuda.device(x_in.device):
+        check(lib.segnn_embed_fwd(_p(x_in), _p(node_attr), _p(w_embed), _p(bias), nodes, n, _p(h), _stream()),
+              "segnn_embed_fwd")
+    _bump()
+    return h
+
+
+def node_gemm(x0, x1, w_s, w_v, bias, n_bias: int, n_out: int, out: Optional[torch.Tensor] = None):
+    nodes, _, n_in = x0.shape
+    y = out if out is not None else torch.empty((nodes, 4, n_out), dtype=torch.float32, device=x0.device)
+    with torch.cuda.device(x0.device):
+        check(lib.segnn_node_gemm(_p(x0), _p(x1), nodes, n_in, _p(w_s), _p(w_v), _p(bias), n_bias, n_out, _p(y),
+                                  _stream()), "segnn_node_gemm")
+    _bump()
+    return y
+
+
+def tp_combine(y, node_attr, n: int, gate: bool, bias=None, residual=None, bn_mul=None, bn_add=None,
+               out: Optional[torch.Tensor] = None):
+    nodes = y.shape[0]
+    o = out if out is not None else torch.empty((nodes, 4, n), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        check(lib.segnn_tp_combine(_p(y), _p(node_attr), nodes, n, int(gate), _p(bias), _p(residual), _p(bn_mul),
+                                   _p(bn_add), _p(o), _stream()), "segnn_tp_combine")
+    _bump()
+    return o
+
+
+def edge_layer(mode: int, pos, mass, batch_size: int, num_nodes: int, n: int, pq, w_edge1, w2, bn_mul=None,
+               bn_add=None, want_moments: bool = False):
+    """w2: dict with fp32 blocks 'ss','vs','sv','vv','b' and (tensor-core mode) 'tc' image."""
+    nodes = batch_size * num_nodes
+    agg = torch.empty((nodes, 4, n), dtype=torch.float32, device=pos.device)
+    mom = torch.empty((nodes, 2 * n), dtype=torch.float32, device=pos.device) if want_moments else None
+    with torch.cuda.device(pos.device):
+        check(lib.segnn_edge_layer_fwd(mode, _p(pos), _p(mass), batch_size, num_nodes, n, _p(pq), _p(w_edge1),
+                                       _p(w2.get("ss")), _p(w2.get("vs")), _p(w2.get("sv")), _p(w2.get("vv")),
+                                       _p(w2["b"]), _p(w2.get("tc")), _p(bn_mul), _p(bn_add), _p(agg), _p(mom),
+                                       _stream()), "segnn_edge_layer_fwd")
+    _bump()
+    return (agg, mom) if want_moments else agg
+
+
+def head(h, node_attr, w_head, n: int):
+    nodes = h.shape[0]
+    pred = torch.empty((nodes, 6), dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        check(lib.segnn_head_fwd(_p(h), _p(node_attr), _p(w_head), nodes, n, _p(pred), _stream()), "segnn_head_fwd")
+    _bump()
+    return pred
+
+
+def integrate(pred, pos, vel, traj_pos=None, traj_vel=None, frame=None):
+    nodes = pos.shape[0]
+    with torch.cuda.device(pos.device):
+        check(lib.segnn_integrate(_p(pred), _p(pos), _p(vel), nodes, _p(traj_pos), _p(traj_vel), _p(frame),
+                                  _stream()), "segnn_integrate")
+    _bump()
+
+
+def counter_add(counter: torch.Tensor, delta: int):
+    with torch.cuda.device(counter.device):
+        check(lib.segnn_counter_add(_p(counter), int(delta), _stream()), "segnn_counter_add")
+    _bump()
+
+
+def tc_available() -> bool:
+    """True when the tcgen05 (SEGNN_MODE_BF16_TC) edge kernel is compiled into the library."""
+    return lib.segnn_pack_w2_tc(None, None, None, None, 96, None, None) > 0

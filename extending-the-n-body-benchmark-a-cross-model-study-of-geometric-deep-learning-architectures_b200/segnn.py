@@ -1,0 +1,209 @@
+"""Host-side mirror of models/segnn/segnn.py: same classes, constructor signature, parameter names and
+``forward(graph) -> [nodes, 6]``; the arithmetic is the sm_100a kernel sequence K1..K6 behind the C ABI."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops, packing
+from .graph import infer_graph_shape
+from .irreps import Irreps, weight_balanced_irreps
+from .o3_building_blocks import BatchNorm, O3TensorProduct, O3TensorProductSwishGate
+
+_MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16_TC}
+
+
+class SEGNNLayer(nn.Module):
+    """models/segnn/segnn.py:192-304 (PyG MessagePassing, aggr='add'). Holds the four tensor products and the two
+    BatchNorms under the reference's names; ``forward`` runs node GEMM -> fused edge kernel -> node update."""
+
+    def __init__(self, input_irreps, hidden_irreps, output_irreps, edge_attr_irreps, node_attr_irreps, norm=None,
+                 additional_message_irreps=None):
+        super().__init__()
+        input_irreps, hidden_irreps = Irreps(str(input_irreps)), Irreps(str(hidden_irreps))
+        self.hidden_irreps = hidden_irreps
+        add = Irreps(str(additional_message_irreps)) if additional_message_irreps is not None else Irreps()
+        message_input_irreps = (2 * input_irreps + add).simplify()
+        update_input_irreps = (input_irreps + hidden_irreps).simplify()
+        self.message_layer_1 = O3TensorProductSwishGate(message_input_irreps, hidden_irreps, edge_attr_irreps)
+        self.message_layer_2 = O3TensorProductSwishGate(hidden_irreps, hidden_irreps, edge_attr_irreps)
+        self.update_layer_1 = O3TensorProductSwishGate(update_input_irreps, hidden_irreps, node_attr_irreps)
+        self.update_layer_2 = O3TensorProduct(hidden_irreps, hidden_irreps, node_attr_irreps)
+        self.norm = norm
+        self.feature_norm = None
+        self.message_norm = None
+        if norm == "batch":
+            self.feature_norm = BatchNorm(hidden_irreps)
+            self.message_norm = BatchNorm(hidden_irreps)
+        elif norm == "instance":
+            raise NotImplementedError("norm='instance' cannot be selected by the reference's create_model; not built")
+        if list(hidden_irreps) != [(hidden_irreps[0][0], 0, 1), (hidden_irreps[0][0], 1, -1)] \
+                or list(add) != [(2, 0, 1)] or list(input_irreps) != list(hidden_irreps):
+            raise NotImplementedError(
+                f"kernels are built for hidden irreps n x0e + n x1o (lmax_h = 1) with 2x0e message features; "
+                f"got hidden={hidden_irreps}, additional={add}")
+        self.n = hidden_irreps[0][0]
+
+    # -- weight packing -----------------------------------------------------------------------------------------
+    def pack(self, degree: int, eval_bn: bool = True) -> Dict[str, object]:
+        n = self.n
+        f = lambda t: t.detach().to(torch.float32)
+        out = dict(
+            msg1=packing.pack_msg1(f(self.message_layer_1.tp.weight), f(self.message_layer_1.biases), n),
+            msg2=packing.pack_msg2(f(self.message_layer_2.tp.weight), f(self.message_layer_2.biases), n),
+            upd1=packing.pack_node_tp(f(self.update_layer_1.tp.weight), f(self.update_layer_1.biases), 2, n, 2 * n),
+            upd2=packing.pack_node_tp(f(self.update_layer_2.tp.weight), f(self.update_layer_2.biases), 1, n, n),
+            bn_msg=(None, None), bn_feat=(None, None))
+        if eval_bn and self.message_norm is not None:
+            bn = self.message_norm
+            out["bn_msg"] = packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), n,
+                                                   bn.eps, float(degree))
+            bn = self.feature_norm
+            out["bn_feat"] = packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var),
+                                                    n, bn.eps, 1.0)
+        return out
+
+    def run(self, w, mode: int, h, pos, mass, node_attr, batch_size: int, num_nodes: int):
+        """One layer on planar features h [nodes,4,n] (eval-mode BatchNorm)."""
+        n = self.n
+        m1 = w["msg1"]
+        pq = ops.node_gemm(h, None, m1["w_s"], m1["w_v"], m1["bias"], 2 * n, 6 * n)
+        agg = ops.edge_layer(mode, pos, mass, batch_size, num_nodes, n, pq, m1["w_edge"], w["msg2"],
+                             w["bn_msg"][0], w["bn_msg"][1])
+        u1 = w["upd1"]
+        y1 = ops.node_gemm(h, agg, u1["w_s"], u1["w_v"], None, 0, 3 * n)
+        g1 = ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"])
+        u2 = w["upd2"]
+        y2 = ops.node_gemm(g1, None, u2["w_s"], u2["w_v"], None, 0, 2 * n)
+        return ops.tp_combine(y2, node_attr, n, False, bias=u2["bias"], residual=h, bn_mul=w["bn_feat"][0],
+                              bn_add=w["bn_feat"][1])
+
+    def forward(self, x, edge_index, edge_attr, node_attr, batch, additional_message_features=None, *, pos=None,
+                mass=None, num_graphs=None, n_nodes=None, mode="fp32"):
+        """Reference signature (segnn.py:239-247) on e3nn-layout features. The graph is implicit: ``edge_index`` /
+        ``edge_attr`` / ``additional_message_features`` are ignored and recomputed from ``pos`` / ``mass``."""
+        if pos is None or mass is None or num_graphs is None or n_nodes is None:
+            raise ValueError("SEGNNLayer.forward needs pos, mass, num_graphs, n_nodes (implicit complete graph)")
+        if self.training:
+            raise NotImplementedError("train-mode BatchNorm for the standalone layer: use SEGNN.forward")
+        w = self.pack(n_nodes - 1)
+        h = packing.to_planar(x.float(), self.n)
+        out = self.run(w, _MODES[mode], h, pos.float().contiguous(), mass.float().reshape(-1).contiguous(),
+                       node_attr.float().contiguous(), num_graphs, n_nodes)
+        return packing.from_planar(out).to(x.dtype)
+
+
+class SEGNN(nn.Module):
+    """Steerable E(3) equivariant message passing network -- models/segnn/segnn.py:14-189 (task='node').
+
+    ``compute_mode``: 'fp32' (FFMA kernels, the 1e-5 parity mode) or 'bf16' (tcgen05 tensor-core edge kernel)."""
+
+    def __init__(self, input_irreps="2x1o + 1x0e", hidden_features=64, lmax_h=1, lmax_attr=1, num_layers=4,
+                 output_irreps="2x1o", norm="batch", pool="avg", task="node", additional_message_irreps="2x0e",
+                 training_args=None, compute_mode="fp32"):
+        super().__init__()
+        if task != "node":
+            raise NotImplementedError("only task='node' is on the N-body path")
+        if int(lmax_attr) != 1 or int(lmax_h) != 1:
+            raise NotImplementedError(f"kernels are built for lmax_h = lmax_attr = 1 (got {lmax_h}, {lmax_attr})")
+        if Irreps(str(input_irreps)) != Irreps("2x1o+1x0e") or Irreps(str(output_irreps)) != Irreps("2x1o"):
+            raise NotImplementedError("kernels are built for the N-body irreps: input 2x1o+1x0e, output 2x1o")
+        self.hidden_features, self.lmax_h, self.lmax_attr, self.num_layers = hidden_features, lmax_h, lmax_attr, num_layers
+        self.node_attr_irreps = Irreps.spherical_harmonics(lmax_attr)
+        self.edge_attr_irreps = Irreps.spherical_harmonics(lmax_attr)
+        self.hidden_irreps = weight_balanced_irreps(hidden_features, self.node_attr_irreps, lmax=lmax_h)
+        self.task, self.norm, self.pool, self.training_args = task, norm, pool, training_args
+        self.additional_message_irreps = Irreps(str(additional_message_irreps))
+        self.compute_mode = compute_mode
+        h = self.hidden_irreps
+        self.n = h[0][0]
+        self.embedding_layer = O3TensorProduct(Irreps(str(input_irreps)), h, self.node_attr_irreps)
+        self.layers = nn.ModuleList([
+            SEGNNLayer(h, h, h, self.edge_attr_irreps, self.node_attr_irreps, norm=norm,
+                       additional_message_irreps=self.additional_message_irreps) for _ in range(num_layers)])
+        self.pre_pool1 = O3TensorProductSwishGate(h, h, self.node_attr_irreps)
+        self.pre_pool2 = O3TensorProduct(h, Irreps(str(output_irreps)), self.node_attr_irreps)
+        self._pack_key = None
+        self._packed = None
+
+    def get_model_size(self):
+        return self.hidden_features
+
+    def get_serializable_attributes(self):
+        return {
+            "hidden_features": self.hidden_features, "lmax_h": self.lmax_h, "lmax_attr": self.lmax_attr,
+            "node_attr_irreps": str(self.node_attr_irreps), "num_layers": self.num_layers,
+            "input_irreps": str(self.embedding_layer.irreps_in1), "hidden_irreps": str(self.hidden_irreps),
+            "output_irreps": str(self.pre_pool2.irreps_out), "edge_attr_irreps": str(self.edge_attr_irreps),
+            "norm": self.norm, "pool": None, "task": self.task,
+            "additional_message_irreps": str(self.additional_message_irreps), "training_args": self.training_args,
+            "num_params": sum(p.numel() for p in self.parameters()),
+        }
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        """Accepts reference checkpoints: e3nn-internal buffers (tp.output_mask, compiled w3j constants, empty
+        gate.mul.weight, ...) are filtered out; the learnable tensors keep the reference's names."""
+        own = set(self.state_dict().keys())
+        filtered = {k: v for k, v in state_dict.items() if k in own}
+        return super().load_state_dict(filtered, strict=strict, assign=assign)
+
+    # -- packing cache ------------------------------------------------------------------------------------------
+    def packed(self, degree: int):
+        tensors = list(self.parameters()) + list(self.buffers())
+        key = (degree, tuple((t.data_ptr(), t._version, t.device, t.dtype) for t in tensors))
+        if key != self._pack_key:
+            f = lambda t: t.detach().to(torch.float32)
+            n = self.n
+            self._packed = dict(
+                embed=packing.pack_embedding(f(self.embedding_layer.tp.weight), f(self.embedding_layer.biases), n),
+                layers=[layer.pack(degree) for layer in self.layers],
+                pool1=packing.pack_node_tp(f(self.pre_pool1.tp.weight), f(self.pre_pool1.biases), 1, n, 2 * n),
+                head=packing.pack_head(f(self.pre_pool2.tp.weight), n))
+            self._pack_key = key
+        return self._packed
+
+    # -- forward ------------------------------------------------------------------------------------------------
+    def forward_state(self, pos, vel, mass, batch_size: int, num_nodes: int, x_in=None, node_attr=None,
+                      return_layers: bool = False):
+        """pos, vel [nodes,3] fp32 CUDA, mass [nodes] -> pred [nodes,6] fp32 (eval-mode BatchNorm)."""
+        if self.training and self.norm == "batch":
+            raise NotImplementedError("train-mode BatchNorm forward is not built yet; call model.eval()")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("backward kernels are not built yet; wrap inference in torch.no_grad()")
+        w = self.packed(num_nodes - 1)
+        mode = _MODES[self.compute_mode]
+        n = self.n
+        if x_in is None or node_attr is None:
+            x_in, node_attr = ops.prep(pos, vel, batch_size, num_nodes)
+        h = ops.embed(x_in, node_attr, w["embed"]["w"], w["embed"]["bias"], n)
+        per_layer = [h]
+        for layer, lw in zip(self.layers, w["layers"]):
+            h = layer.run(lw, mode, h, pos, mass, node_attr, batch_size, num_nodes)
+            per_layer.append(h)
+        p1 = w["pool1"]
+        y = ops.node_gemm(h, None, p1["w_s"], p1["w_v"], None, 0, 3 * n)
+        hp = ops.tp_combine(y, node_attr, n, True, bias=p1["bias"])
+        pred = ops.head(hp, node_attr, w["head"], n)
+        if return_layers:
+            return pred, per_layer
+        return pred
+
+    def forward(self, graph, return_layers: bool = False):
+        """SEGNN forward pass on a batched implicit graph (reference: segnn.py:150-189)."""
+        b, n_nodes = infer_graph_shape(graph)
+        dtype = graph.pos.dtype
+        dev = graph.pos.device
+        if dev.type != "cuda":
+            raise RuntimeError("SEGNN (B200) needs CUDA tensors: there is no CPU fallback")
+        f32 = lambda t: t.to(torch.float32).contiguous()
+        pos, vel, mass = f32(graph.pos), f32(graph.vel), f32(graph.mass).reshape(-1)
+        x_in = node_attr = None
+        if getattr(graph, "x", None) is not None and getattr(graph, "node_attr", None) is not None:
+            x_in, node_attr = f32(graph.x), f32(graph.node_attr).clone()
+            node_attr[:, 0] = 1.0  # catch_isolated_nodes, segnn.py:148
+        out = self.forward_state(pos, vel, mass, b, n_nodes, x_in, node_attr, return_layers)
+        if return_layers:
+            return out[0].to(dtype), [packing.from_planar(h).to(dtype) for h in out[1]]
+        return out.to(dtype)

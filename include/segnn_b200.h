@@ -1,0 +1,145 @@
+/*
+ * segnn_b200.h -- C ABI of the B200-native SEGNN message-passing hot path.
+ *
+ * The reference (a pure-Python repository) has no FFI for this path; its boundary is the Python
+ * module contract of models/segnn (SEGNN, SEGNNLayer, O3TensorProduct, O3Transform) and
+ * utils/build_fully_connected_graph.py.  Every entry point below names the reference code it replaces
+ * (paths are into the reference repository).  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated otherwise; tensors are dense, row-major, float32
+ *     unless the name says otherwise;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated, nothing
+ *     synchronises, every launch goes to `stream` => all calls are CUDA-graph capturable and re-entrant;
+ *   - return value 0 = ok, negative = error (SEGNN_E_*); segnn_last_error() returns a thread-local message;
+ *   - "planar" hidden features: [nodes][4][n] = (scalars, v_x, v_y, v_z) per node, n = multiplicity of the
+ *     hidden irreps n x0e + n x1o.  e3nn's mul-major layout (models/segnn: [s(n) | v(u,k) at n+3u+k]) is
+ *     converted at the module boundary only;
+ *   - B graphs of N nodes each, fully connected without self loops: nodes = B*N, E = B*N*(N-1).  The edge
+ *     list is never materialised on the hot path; enumeration order (when materialised) is the reference's:
+ *     graph-major, then source ascending, then target ascending (utils/build_fully_connected_graph.py:4-20).
+ */
+#ifndef SEGNN_B200_H_
+#define SEGNN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* segnn_stream_t; /* cudaStream_t */
+
+enum {
+  SEGNN_OK = 0,
+  SEGNN_E_INVALID = -1,   /* bad argument (null pointer, unsupported size) */
+  SEGNN_E_UNSUPPORTED = -2, /* configuration not built (e.g. lmax_h != 1) */
+  SEGNN_E_CUDA = -3       /* CUDA runtime error at launch */
+};
+
+/* compute mode of the per-edge contraction (message_layer_2) */
+enum {
+  SEGNN_MODE_FP32 = 0,   /* FFMA, fp32 everywhere: the 1e-5 parity mode */
+  SEGNN_MODE_BF16_TC = 1 /* tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM): the throughput mode */
+};
+
+int segnn_version(void);
+const char* segnn_last_error(void);
+
+/* ---- graph / geometry materialisation (tests and legacy consumers only) -------------------------- */
+
+/* utils/build_fully_connected_graph.py:4-20 _build_fully_connected_edge_index.
+ * edge_index: int64 [2, B*N*(N-1)], row 0 = source (sender), row 1 = target (receiver). */
+int segnn_edge_index(int B, int N, int64_t* edge_index, segnn_stream_t stream);
+
+/* models/segnn/o3_building_blocks.py:237-245,277 (O3Transform edge part), lmax_attr = 1.
+ * edge_attr [E,4] = Y_0..1(pos[src]-pos[tgt]) ('integral', normalised); add [E,2] = (|r|, m_src*m_tgt). */
+int segnn_edge_attr(const float* pos, const float* mass, int B, int N, float* edge_attr, float* add,
+                    segnn_stream_t stream);
+
+/* ---- K1: per-step node geometry ------------------------------------------------------------------ */
+
+/* models/segnn/o3_building_blocks.py:253-276 (node_attr = mean_j Y(r_j - r_i) + Y(v_i); x = [pos -
+ * mean_xyz(pos), vel, |vel|]) plus models/segnn/segnn.py:148 (node_attr[:,0] = 1).
+ * pos, vel [nodes,3] -> x_in [nodes,7], node_attr [nodes,4]. */
+int segnn_prep_fwd(const float* pos, const float* vel, int B, int N, float* x_in, float* node_attr,
+                   segnn_stream_t stream);
+
+/* ---- K2: embedding tensor product ---------------------------------------------------------------- */
+
+/* models/segnn/segnn.py:170 embedding_layer = O3TensorProduct(2x1o+1x0e -> h, node_attr).
+ * w_embed: packed [6][n] = (W_vec0->1o, W_vec1->1o, W_vec0->0e /sqrt3, W_vec1->0e /sqrt3, W_sc->0e, W_sc->1o),
+ * bias [n].  h_out planar [nodes][4][n]. */
+int segnn_embed_fwd(const float* x_in, const float* node_attr, const float* w_embed, const float* bias,
+                    int nodes, int n, float* h_out, segnn_stream_t stream);
+
+/* ---- node-level tensor products: plain GEMM + attribute combine ------------------------------------ */
+
+/* The weight contraction of an O3TensorProduct over node rows (o3_building_blocks.py:150-162) hoisted out
+ * of the attribute coupling:  y[node][c][:] = concat_K(x0[node][c], x1[node][c]) @ (c == 0 ? w_s : w_v),
+ * c = 0 scalar plane, c = 1..3 vector planes.  x0, x1 planar [nodes][4][n_in] (x1 may be NULL);
+ * w_s, w_v [K][n_out] row-major with K = n_in * (x1 ? 2 : 1); bias (may be NULL) [n_bias] is added to
+ * columns [0, n_bias) of the c = 0 plane.  y [nodes][4][n_out]. */
+int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const float* w_s, const float* w_v,
+                    const float* bias, int n_bias, int n_out, float* y, segnn_stream_t stream);
+
+/* Attribute coupling + epilogue of a node-level tensor product.  With a = node_attr[node] = (a0, a1[3]):
+ *   z0[w]    = a0 * y[0][w]      + sum_k a1[k] * y[1+k][w] + bias[w]   w < n0 (l=0 outputs; bias may be NULL)
+ *   z1[w][k] = a1[k] * y[0][n0+w] + a0 * y[1+k][n0+w]             w < n    (l=1 outputs)
+ * gate != 0 (O3TensorProductSwishGate, o3_building_blocks.py:197-203 + e3nn Gate): n0 = 2n,
+ *   out = (c_silu*silu(z0[w]), c_sig*sigmoid(z0[n+w]) * z1[w][k]);
+ * gate == 0 (O3TensorProduct): n0 = n, out = (z0, z1).
+ * residual (may be NULL) planar [nodes][4][n] is added (models/segnn/segnn.py:303 x += update).
+ * bn_mul [2n] / bn_add [n] (may be NULL): eval-mode e3nn BatchNorm folded to out_s*mul[w]+add[w],
+ * out_v*mul[n+w] (segnn.py:257-261).  out planar [nodes][4][n]. */
+int segnn_tp_combine(const float* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                     const float* residual, const float* bn_mul, const float* bn_add, float* out,
+                     segnn_stream_t stream);
+
+/* ---- K3: fused edge layer ---------------------------------------------------------------------------- */
+
+/* SEGNNLayer.message + aggregate (models/segnn/segnn.py:264-284 + PyG scatter-add, segnn.py:205) over the
+ * implicit fully-connected graph, eval-mode message BatchNorm folded into the aggregate:
+ *   agg[i] = bn_mul * sum_{j != i} gate(msg2(gate(msg1(x_i, x_j, |r_ij|, m_i m_j; Y(r_ij))); Y(r_ij))) + bn_add
+ * message_layer_1 is linear in (x_i, x_j), so its weight contraction is hoisted to the node GEMM:
+ *   pq [nodes][4][6n] = per plane (P0[2n], P1[n], Q0[2n], Q1[n]) -- receiver (P) and sender (Q) projections
+ *   with the constant Y_0 and the bias folded in (see pack_msg1 in the host package).
+ * w_edge1 [6n] = (d->0e [2n], mm->0e [2n], d->1o [n], mm->1o [n]) (Y_0 folded into the 0e parts).
+ * msg2 weights (fp32 mode): w2_ss [n][2n] (Y_0 folded), w2_vs [n][2n] (1/sqrt3 folded), w2_sv [n][n],
+ *   w2_vv [n][n] (Y_0 folded), b2 [2n].
+ * bn_mul [2n], bn_add [n]: folded eval BatchNorm with the degree (N-1) applied to the mean/bias terms;
+ *   both NULL => raw sum.
+ * agg_out planar [nodes][4][n].
+ * moments (may be NULL): [nodes][2n] per-receiver sums needed for train-mode batch statistics:
+ *   (sum_j m_s[w]^2 , sum_j |m_v[w]|^2); the plain sums are agg itself when bn_mul == NULL. */
+int segnn_edge_layer_fwd(int mode, const float* pos, const float* mass, int B, int N, int n, const float* pq,
+                         const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
+                         const float* w2_vv, const float* b2, const void* w2_tc, const float* bn_mul,
+                         const float* bn_add, float* agg_out, float* moments, segnn_stream_t stream);
+
+/* Packs the message_layer_2 weights for SEGNN_MODE_BF16_TC into the UMMA shared-memory image the tensor-core
+ * kernel copies verbatim (bf16, K-major, 128B swizzle).  Returns the image size in bytes when out == NULL. */
+int64_t segnn_pack_w2_tc(const float* w2_ss, const float* w2_vs, const float* w2_sv, const float* w2_vv, int n,
+                         void* out, segnn_stream_t stream);
+
+/* ---- K5/K6: head + self-feed integration ------------------------------------------------------------- */
+
+/* models/segnn/segnn.py:180 pre_pool2 = O3TensorProduct(h -> 2x1o, node_attr), no bias.
+ * w_head [2][n][2]: (W_s->1o [n][2], W_v->1o [n][2]).  pred [nodes][6] = (out_0 xyz, out_1 xyz). */
+int segnn_head_fwd(const float* h, const float* node_attr, const float* w_head, int nodes, int n, float* pred,
+                   segnn_stream_t stream);
+
+/* helper_scripts/infer_self_feed.py:182-194 with target 'pos_dt+vel': pos += pred[:, :3]; vel = pred[:, 3:].
+ * traj_pos / traj_vel (may be NULL): trajectory buffers [frames][nodes][3]; the new state is also written to
+ * frame slot *frame (device int; NULL => slot 0), which replaces predicted_loc.append(...) (:188-189) and keeps
+ * the step replayable as a CUDA graph. */
+int segnn_integrate(const float* pred, float* pos, float* vel, int nodes, float* traj_pos, float* traj_vel,
+                    const int* frame, segnn_stream_t stream);
+
+/* *counter += delta on the device (the rollout's frame cursor; `for step in range(...)`, infer_self_feed.py:99). */
+int segnn_counter_add(int* counter, int delta, segnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGNN_B200_H_ */

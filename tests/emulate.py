@@ -1,0 +1,131 @@
+"""Pure-torch emulation of the kernel-side algebra on the PACKED operands (test infrastructure only).
+
+It follows the same steps as the CUDA kernels (hoisted message_layer_1 projections, split message_layer_2
+contraction, BatchNorm folded through the sender sum, GEMM + attribute combine for node-level products), so
+comparing it with the oracle on CPU validates the host-side packing and the algebraic rewrites without a GPU.
+"""
+import math
+
+import torch
+
+C_SILU = 1.6791767923989418
+C_SIG = 1.8467055342154763
+Y1 = 0.4886025119029199
+
+
+def _unit(v):
+    return v / v.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+
+
+def prep(pos, vel, B, N):
+    p = pos.reshape(B, N, 3)
+    rel = p[:, None, :, :] - p[:, :, None, :]  # [B, i, j] = pos_j - pos_i
+    u = _unit(rel)
+    mask = ~torch.eye(N, dtype=torch.bool)
+    s = (u * mask[None, :, :, None]).sum(2) / max(N - 1, 1)
+    a1 = Y1 * s.reshape(B * N, 3) + Y1 * _unit(vel)
+    attr = torch.cat([torch.ones(B * N, 1, dtype=pos.dtype), a1], dim=1)
+    x = torch.cat([pos - pos.mean(1, keepdim=True), vel, vel.norm(dim=1, keepdim=True)], dim=1)
+    return x, attr
+
+
+def embed(x, attr, w, bias):
+    a0, a1 = attr[:, 0:1], attr[:, 1:4]
+    p, v, s = x[:, 0:3], x[:, 3:6], x[:, 6:7]
+    pdot, vdot = (p * a1).sum(1, keepdim=True), (v * a1).sum(1, keepdim=True)
+    out_s = a0 * w[4] * s + w[2] * pdot + w[3] * vdot + bias
+    t = w[5] * s
+    out_v = [a1[:, k:k + 1] * t + a0 * (w[0] * p[:, k:k + 1] + w[1] * v[:, k:k + 1]) for k in range(3)]
+    return torch.stack([out_s] + out_v, dim=1)  # planar [nodes,4,n]
+
+
+def node_gemm(x0, x1, w_s, w_v, bias, n_bias):
+    x = x0 if x1 is None else torch.cat([x0, x1], dim=2)
+    y = torch.stack([x[:, 0] @ w_s] + [x[:, c] @ w_v for c in (1, 2, 3)], dim=1)
+    if bias is not None:
+        y[:, 0, :n_bias] += bias
+    return y
+
+
+def tp_combine(y, attr, n, gate, bias=None, residual=None, bn_mul=None, bn_add=None):
+    n0 = 2 * n if gate else n
+    a0, a1 = attr[:, 0:1], attr[:, 1:4]
+    z0 = a0 * y[:, 0, :n0] + sum(a1[:, k:k + 1] * y[:, 1 + k, :n0] for k in range(3))
+    if bias is not None:
+        z0 = z0 + bias
+    z1 = [a1[:, k:k + 1] * y[:, 0, n0:] + a0 * y[:, 1 + k, n0:] for k in range(3)]
+    if gate:
+        s = C_SILU * torch.nn.functional.silu(z0[:, :n])
+        g = C_SIG * torch.sigmoid(z0[:, n:])
+        out = torch.stack([s] + [g * z for z in z1], dim=1)
+    else:
+        out = torch.stack([z0] + z1, dim=1)
+    if residual is not None:
+        out = out + residual
+    if bn_mul is not None:
+        out = torch.cat([(out[:, 0] * bn_mul[:n] + bn_add).unsqueeze(1), out[:, 1:] * bn_mul[n:]], dim=1)
+    return out
+
+
+def edge_layer(pos, mass, B, N, n, pq, w_edge, w2, bn_mul=None, bn_add=None):
+    p = pos.reshape(B, N, 3)
+    rel = p[:, None, :, :] - p[:, :, None, :]  # [B,i,j,3] = pos_j - pos_i
+    dist = rel.norm(dim=-1, keepdim=True)
+    a1 = Y1 * rel / dist.clamp_min(1e-12)
+    m = mass.reshape(B, N)
+    mm = (m[:, :, None] * m[:, None, :]).unsqueeze(-1)
+    pqr = pq.reshape(B, N, 4, 6 * n)
+    P, Q = pqr[..., : 3 * n], pqr[..., 3 * n:]
+    S = P[:, :, None] + Q[:, None, :]  # [B,i,j,4,3n]
+    wd0, wm0, wd1, wm1 = w_edge[:2 * n], w_edge[2 * n:4 * n], w_edge[4 * n:5 * n], w_edge[5 * n:]
+    z0 = S[..., 0, :2 * n] + sum(a1[..., k:k + 1] * S[..., 1 + k, :2 * n] for k in range(3)) + dist * wd0 + mm * wm0
+    t = S[..., 0, 2 * n:] + dist * wd1 + mm * wm1
+    zv = [a1[..., k:k + 1] * t + S[..., 1 + k, 2 * n:] for k in range(3)]
+    s1 = C_SILU * torch.nn.functional.silu(z0[..., :n])
+    g1 = C_SIG * torch.sigmoid(z0[..., n:])
+    v1 = [g1 * z for z in zv]
+    dot = sum(a1[..., k:k + 1] * v1[k] for k in range(3))
+    y0 = s1 @ w2["ss"] + dot @ w2["vs"] + w2["b"]
+    t1 = s1 @ w2["sv"]
+    dk = [v1[k] @ w2["vv"] for k in range(3)]
+    ms = C_SILU * torch.nn.functional.silu(y0[..., :n])
+    gt = C_SIG * torch.sigmoid(y0[..., n:])
+    mv = [gt * (a1[..., k:k + 1] * t1 + dk[k]) for k in range(3)]
+    mask = (~torch.eye(N, dtype=torch.bool))[None, :, :, None].to(pos.dtype)
+    agg = torch.stack([(ms * mask).sum(2)] + [(x * mask).sum(2) for x in mv], dim=2).reshape(B * N, 4, n)
+    if bn_mul is not None:
+        agg = torch.cat([(agg[:, 0] * bn_mul[:n] + bn_add).unsqueeze(1), agg[:, 1:] * bn_mul[n:]], dim=1)
+    return agg
+
+
+def head(h, attr, w_head):
+    a0, a1 = attr[:, 0:1], attr[:, 1:4]
+    t = h[:, 0] @ w_head[0]  # [nodes,2]
+    d = [h[:, 1 + k] @ w_head[1] for k in range(3)]  # each [nodes,2]
+    cols = []
+    for o in range(2):
+        for k in range(3):
+            cols.append(a1[:, k] * t[:, o] + a0[:, 0] * d[k][:, o])
+    return torch.stack(cols, dim=1)
+
+
+def model_forward(packed, n, pos, vel, mass, B, N, return_layers=False):
+    """Same kernel sequence as SEGNN.forward_state, on CPU tensors of any float dtype."""
+    c = lambda t: None if t is None else t.to(pos.dtype)
+    x, attr = prep(pos, vel, B, N)
+    h = embed(x, attr, c(packed["embed"]["w"]), c(packed["embed"]["bias"]))
+    layers = [h]
+    for lw in packed["layers"]:
+        m1 = lw["msg1"]
+        pq = node_gemm(h, None, c(m1["w_s"]), c(m1["w_v"]), c(m1["bias"]), 2 * n)
+        w2 = {k: c(v) for k, v in lw["msg2"].items()}
+        agg = edge_layer(pos, mass, B, N, n, pq, c(m1["w_edge"]), w2, c(lw["bn_msg"][0]), c(lw["bn_msg"][1]))
+        u1, u2 = lw["upd1"], lw["upd2"]
+        g1 = tp_combine(node_gemm(h, agg, c(u1["w_s"]), c(u1["w_v"]), None, 0), attr, n, True, bias=c(u1["bias"]))
+        h = tp_combine(node_gemm(g1, None, c(u2["w_s"]), c(u2["w_v"]), None, 0), attr, n, False, bias=c(u2["bias"]),
+                       residual=h, bn_mul=c(lw["bn_feat"][0]), bn_add=c(lw["bn_feat"][1]))
+        layers.append(h)
+    p1 = packed["pool1"]
+    hp = tp_combine(node_gemm(h, None, c(p1["w_s"]), c(p1["w_v"]), None, 0), attr, n, True, bias=c(p1["bias"]))
+    pred = head(hp, attr, c(packed["head"]))
+    return (pred, layers) if return_layers else pred

@@ -1,0 +1,211 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs and weights.
+Tolerances: bit-exact for the integer graph enumeration; 1e-5 relative (max-norm) per layer in fp32 mode and 2e-2 in
+bf16 tensor-core mode (BASELINE.json north_star, check (b))."""
+import os
+
+import pytest
+import torch
+
+import segnn_b200 as S
+from oracle import segnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "segnn_small.pt")
+TOL = {"fp32": 1e-5, "bf16": 2e-2}
+
+
+def rel(a, b):
+    return float((a.double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def modes():
+    return ["fp32"] + (["bf16"] if S.ops.tc_available() else [])
+
+
+def make_pair(H, L, seed=0, dtype=torch.float32):
+    torch.manual_seed(seed)
+    om = O.SEGNN(hidden_features=H, num_layers=L).eval()
+    O.perturb_bn_buffers(om, seed=seed + 1)
+    m = S.SEGNN(hidden_features=H, num_layers=L)
+    m.load_state_dict(om.state_dict())
+    return om, m.to(dtype).cuda().eval()
+
+
+def gpu_graph(pos, vel, mass, B, N, dtype=torch.float32):
+    return S.GraphBatch(pos=pos.reshape(-1, 3).to(dtype).cuda(), vel=vel.reshape(-1, 3).to(dtype).cuda(),
+                        mass=mass.reshape(-1, 1).to(dtype).cuda(), num_graphs=B, n_nodes=N)
+
+
+@pytest.mark.parametrize("B,N", [(1, 2), (2, 3), (3, 5), (7, 100), (1, 1000)])
+def test_edge_enumeration_bit_exact(B, N):
+    got = S.build_graph_with_knn(None, B, N, "cuda", N - 1).cpu()
+    assert got.dtype == torch.int64
+    assert torch.equal(got, O.fully_connected_edge_index(B, N))
+
+
+def test_graph_builder_errors():
+    with pytest.raises(ValueError):
+        S.build_graph_with_knn(None, 2, 5, "cuda", 5)
+    with pytest.raises(NotImplementedError):
+        S.build_graph_with_knn(None, 2, 5, "cuda", 3)
+    assert S.build_graph_with_knn(None, 0, 5, "cuda", None).shape == (2, 0)
+
+
+@pytest.mark.parametrize("B,N", [(3, 5), (2, 100), (1, 300)])
+def test_o3_transform(B, N):
+    pos, vel, mass = O.synthetic_system(B, N, seed=11)
+    ref = O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N)
+    g = S.O3Transform(1)(gpu_graph(pos, vel, mass, B, N))
+    ref_attr = ref.node_attr.clone()
+    ref_attr[:, 0] = 1.0  # K1 applies segnn.py:148 directly
+    assert float((g.node_attr.double().cpu() - ref_attr).abs().max()) < 2e-6
+    assert float((g.x.double().cpu() - ref.x).abs().max()) < 2e-6 * float(ref.x.abs().max())
+    assert torch.equal(g.edge_index.cpu(), ref.edge_index)
+    assert float((g.edge_attr.double().cpu() - ref.edge_attr).abs().max()) < 2e-6
+    add = g.additional_message_features.double().cpu()
+    assert float((add - ref.additional_message_features).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("H,L,B,N", [(64, 4, 100, 5), (192, 6, 64, 5), (192, 6, 2, 100), (128, 2, 1, 37),
+                                       (50, 2, 3, 9), (64, 1, 1, 2)])
+def test_segnn_per_layer_parity(H, L, B, N):
+    om, m = make_pair(H, L, seed=H + N)
+    pos, vel, mass = O.synthetic_system(B, N, seed=5)
+    with torch.no_grad():
+        ref, ref_layers = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N),
+                             return_layers=True)
+        for mode in modes():
+            m.compute_mode = mode
+            out, layers = m(gpu_graph(pos, vel, mass, B, N), return_layers=True)
+            for i, (a, b) in enumerate(zip(layers, ref_layers)):
+                assert rel(a, b) < TOL[mode], f"{mode} layer {i}: {rel(a, b)}"
+            assert rel(out, ref) < TOL[mode], f"{mode} output: {rel(out, ref)}"
+
+
+def test_double_precision_module_and_precomputed_attributes():
+    """The reference default is float64 (.double() model, float64 graph): accept it, compute in fp32, return float64."""
+    om, m = make_pair(64, 2, dtype=torch.float64)
+    B, N = 4, 5
+    pos, vel, mass = O.synthetic_system(B, N, seed=2)
+    g = S.O3Transform(1)(gpu_graph(pos, vel, mass, B, N, dtype=torch.float64))
+    with torch.no_grad():
+        out = m(g)
+        ref = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N))
+    assert out.dtype == torch.float64 and rel(out, ref) < 1e-5
+
+
+def test_golden_fixture():
+    gold = torch.load(GOLDEN)
+    cfg = gold["config"]
+    m = S.SEGNN(hidden_features=cfg["hidden_features"], num_layers=cfg["num_layers"])
+    m.load_state_dict(gold["state_dict"])
+    m = m.float().cuda().eval()
+    B, N = cfg["B"], cfg["N"]
+    with torch.no_grad():
+        for mode in modes():
+            m.compute_mode = mode
+            out, layers = m(gpu_graph(gold["pos"], gold["vel"], gold["mass"], B, N), return_layers=True)
+            assert rel(out, gold["pred"]) < TOL[mode]
+            for a, b in zip(layers, gold["layers"]):
+                assert rel(a, b) < TOL[mode]
+    assert torch.equal(S.build_graph_with_knn(None, B, N, "cuda", None).cpu(), gold["edge_index"])
+
+
+def test_module_level_tensor_products():
+    torch.manual_seed(0)
+    n, rows = 32, 50
+    for cls_s, cls_o, in1 in [(S.O3TensorProductSwishGate, O.O3TensorProductSwishGate, f"{n}x0e+{n}x1o"),
+                              (S.O3TensorProduct, O.O3TensorProduct, f"{n}x0e+{n}x1o"),
+                              (S.O3TensorProductSwishGate, O.O3TensorProductSwishGate,
+                               f"{n}x0e+{n}x1o+{n}x0e+{n}x1o")]:
+        ot = cls_o(in1, f"{n}x0e+{n}x1o", "1x0e+1x1o")
+        st = cls_s(in1, f"{n}x0e+{n}x1o", "1x0e+1x1o")
+        st.load_state_dict(ot.state_dict())
+        st = st.cuda()
+        x = torch.randn(rows, O.Irreps(in1).dim, dtype=torch.float64)
+        a = torch.randn(rows, 4, dtype=torch.float64)
+        with torch.no_grad():
+            assert rel(st(x.float().cuda(), a.float().cuda()), ot(x, a)) < 1e-5
+
+
+def test_standalone_layer_matches_oracle():
+    torch.manual_seed(0)
+    n, B, N = 32, 3, 6
+    h = f"{n}x0e+{n}x1o"
+    ol = O.SEGNNLayer(h, h, h, "1x0e+1x1o", "1x0e+1x1o", norm="batch", additional_message_irreps="2x0e").eval()
+    O.perturb_bn_buffers(ol)
+    sl = S.SEGNNLayer(h, h, h, "1x0e+1x1o", "1x0e+1x1o", norm="batch", additional_message_irreps="2x0e")
+    sl.load_state_dict(ol.state_dict())
+    sl = sl.cuda().eval()
+    pos, vel, mass = O.synthetic_system(B, N, seed=8)
+    g = O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N)
+    g.node_attr[:, 0] = 1.0
+    x = torch.randn(B * N, 4 * n, dtype=torch.float64)
+    with torch.no_grad():
+        ref = ol(x, g.edge_index, g.edge_attr, g.node_attr, None, g.additional_message_features)
+        out = sl(x.float().cuda(), None, None, g.node_attr.float().cuda(), None, None,
+                 pos=pos.reshape(-1, 3).float().cuda(), mass=mass.reshape(-1).float().cuda(), num_graphs=B, n_nodes=N)
+    assert rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_rollout_matches_oracle(use_graph):
+    om, m = make_pair(64, 4, seed=3)
+    B, N, steps = 6, 5, 8
+    pos, vel, mass = O.synthetic_system(B, N, seed=9)
+    ref_loc, ref_vel = O.rollout(om, pos, vel, mass, steps)
+    roll = S.SelfFeedRollout(m, B, N, "cuda", max_frames=steps + 1, use_cuda_graph=use_graph)
+    roll.reset(pos, vel, mass)
+    tp, tv = roll.run(steps)
+    got_loc = tp.reshape(steps + 1, B, N, 3).permute(1, 0, 2, 3)
+    got_vel = tv.reshape(steps + 1, B, N, 3).permute(1, 0, 2, 3)
+    assert rel(got_loc, ref_loc) < 5e-5 and rel(got_vel, ref_vel) < 5e-5
+    assert int(roll.frame.item()) == steps + 1
+
+
+def test_run_inference_api(tmp_path):
+    om, m = make_pair(64, 2, seed=4)
+    B, N, T = 3, 5, 6
+    pos, vel, mass = O.synthetic_system(B, N, seed=10)
+    truth_loc, truth_vel = O.rollout(om, pos, vel, mass, T - 1)  # any [B,T,N,3] ground truth will do
+    d, loc, velc = S.run_inference("segnn", None, model=m, save_dir=str(tmp_path), print_step=False,
+                                   ground_truth=(truth_loc, truth_vel, mass))
+    assert loc.shape == (2, B, T, N, 3) and velc.shape == (2, B, T, N, 3)
+    assert sorted(os.listdir(d))[0] == "loc_actual_sim_0.npy" and len(os.listdir(d)) == 4 * B
+    assert float(abs(loc[1] - loc[0]).max()) < 1e-4 * float(abs(loc[0]).max())
+    with pytest.raises(ValueError):
+        S.run_inference("ponita", None, model=m, ground_truth=(truth_loc, truth_vel, mass))
+
+
+def _rotation(seed):
+    g = torch.Generator().manual_seed(seed)
+    q, r = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    q = q * torch.sign(torch.diagonal(r))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+def test_equivariance_and_permutation_at_scale():
+    """Size-independent properties on a workload too big for the oracle: rotating the system rotates the
+    prediction (x_in is passed rotated, which removes the reference's pos.mean(1) quirk from the test path), and
+    permuting the bodies of every graph permutes the prediction."""
+    _, m = make_pair(192, 6, seed=6)
+    B, N = 8, 100
+    pos, vel, mass = O.synthetic_system(B, N, seed=12)
+    R = _rotation(1).float().cuda()
+    p, v, ms = pos.reshape(-1, 3).float().cuda(), vel.reshape(-1, 3).float().cuda(), mass.reshape(-1).float().cuda()
+    with torch.no_grad():
+        x0, a0 = S.ops.prep(p, v, B, N)
+        x0[:, :3] = p  # centred input without the quirk
+        base = m.forward_state(p, v, ms, B, N, x_in=x0, node_attr=a0)
+        pr, vr = (p @ R.T).contiguous(), (v @ R.T).contiguous()
+        x1, a1 = S.ops.prep(pr, vr, B, N)
+        x1[:, :3] = pr
+        rot = m.forward_state(pr, vr, ms, B, N, x_in=x1, node_attr=a1)
+        expect = torch.cat([base[:, :3] @ R.T, base[:, 3:] @ R.T], dim=1)
+        assert float((rot - expect).abs().max() / expect.abs().max()) < 2e-4
+        perm = torch.stack([torch.randperm(N) + b * N for b in range(B)]).reshape(-1).cuda()
+        out_p = m.forward_state(p[perm].contiguous(), v[perm].contiguous(), ms[perm].contiguous(), B, N)
+        out = m.forward_state(p, v, ms, B, N)
+        assert float((out_p - out[perm]).abs().max() / out.abs().max()) < 2e-4

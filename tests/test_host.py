@@ -1,0 +1,140 @@
+"""CPU tests of the host side: C-ABI exports, packing + kernel algebra (emulated) against the oracle, irreps
+sizing, checkpoint key compatibility, error behaviour without a GPU, and 2-rank gloo sharding."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import emulate as E
+import segnn_b200 as S
+from oracle import segnn_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "segnn_b200.h")).read()
+    declared = set(re.findall(r"\b(segnn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"segnn_stream_t"}
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(S._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/segnn_b200.h but not exported"
+    assert declared == set(S._lib.PROTOTYPES.keys())
+    assert lib.segnn_version() >= 100
+
+
+def test_cabi_argument_errors_without_gpu():
+    lib = S._lib.lib
+    assert lib.segnn_prep_fwd(None, None, 2, 5, None, None, None) == -1
+    assert b"null" in lib.segnn_last_error()
+    assert lib.segnn_edge_index(0, 5, None, None) == 0  # empty batch is a no-op
+    assert lib.segnn_edge_layer_fwd(7, None, None, 0, 5, 8, None, None, None, None, None, None, None, None, None,
+                                    None, None, None, None) == 0
+
+
+def test_no_cpu_fallback():
+    model = S.SEGNN(hidden_features=16, num_layers=1).eval()
+    g = S.GraphBatch(pos=torch.zeros(4, 3), vel=torch.zeros(4, 3), mass=torch.ones(4, 1), num_graphs=1, n_nodes=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(g)
+
+
+def test_irreps_and_sizing():
+    assert str(S.weight_balanced_irreps(192, S.Irreps("1x0e+1x1o"), 1)) == "96x0e+96x1o"
+    assert str(S.weight_balanced_irreps(64, S.Irreps("1x0e+1x1o"), 1)) == "32x0e+32x1o"
+    assert str(S.weight_balanced_irreps(192, S.Irreps("1x0e+1x1o"), 2)) == "73x0e+73x1o+73x2e"
+    h = S.Irreps("96x0e+96x1o")
+    assert str((2 * h + S.Irreps("2x0e")).simplify()) == "96x0e+96x1o+96x0e+96x1o+2x0e"
+    assert (h + h).simplify().dim == 768
+    with pytest.raises(NotImplementedError):
+        S.SEGNN(hidden_features=64, lmax_h=2)
+
+
+def test_state_dict_interchange_with_oracle():
+    om = O.SEGNN(hidden_features=64, num_layers=4)
+    m = S.SEGNN(hidden_features=64, num_layers=4)
+    assert list(m.state_dict().keys()) == list(om.state_dict().keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(om.state_dict()[k].shape), k
+    sd = dict(om.state_dict())
+    sd["layers.0.message_layer_1.tp.output_mask"] = torch.ones(3)  # e3nn-internal buffer in reference checkpoints
+    m.load_state_dict(sd)
+    assert m.get_model_size() == 64
+    assert m.get_serializable_attributes()["num_params"] == 148256
+    assert m.get_serializable_attributes()["hidden_irreps"] == "32x0e+32x1o"
+
+
+def test_init_matches_reference_distribution():
+    torch.manual_seed(0)
+    tp = S.O3TensorProductSwishGate("96x0e+96x1o+96x0e+96x1o+2x0e", "96x0e+96x1o", "1x0e+1x1o")
+    assert tp.tp.weight.numel() == 111168 and tp.biases.numel() == 192
+    bound = 1.0 / (386 ** 0.5)
+    assert float(tp.tp.weight.abs().max()) <= bound and float(tp.tp.weight.abs().max()) > 0.95 * bound
+
+
+@pytest.mark.parametrize("H,L,B,N", [(64, 2, 3, 5), (10, 2, 2, 7)])
+def test_packing_and_kernel_algebra_vs_oracle(H, L, B, N):
+    torch.manual_seed(0)
+    om = O.SEGNN(hidden_features=H, num_layers=L).eval()
+    O.perturb_bn_buffers(om)
+    m = S.SEGNN(hidden_features=H, num_layers=L).double().eval()
+    m.load_state_dict(om.state_dict())
+    pos, vel, mass = O.synthetic_system(B, N, seed=3)
+    g = O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N)
+    with torch.no_grad():
+        ref, ref_layers = om(g, return_layers=True)
+        packed = m.packed(N - 1)  # fp32 operands, exactly what the kernels receive
+        out, layers = E.model_forward(packed, m.n, pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1), B, N,
+                                      return_layers=True)
+    for a, b in zip(layers, ref_layers):
+        assert float((S.packing.from_planar(a) - b).abs().max() / b.abs().max()) < 2e-6
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
+def test_planar_layout_roundtrip():
+    x = torch.randn(5, 4 * 6)
+    assert torch.equal(S.packing.from_planar(S.packing.to_planar(x, 6)), x)
+
+
+def test_shard_simulations_partition():
+    for total, world in [(8192, 8), (10, 4), (3, 8), (0, 2)]:
+        spans = [S.shard_simulations(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+            assert s0 + c0 == s1
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, total, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    start, count = S.shard_simulations(total, rank, world)
+    owned = torch.zeros(total, dtype=torch.int64)
+    owned[start:start + count] = 1
+    dist.all_reduce(owned)  # every simulation must be owned by exactly one rank
+    # max-over-ranks timing reduction used by bench.py
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        out.put((owned.tolist(), float(t)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 11, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    owned, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert owned == [1] * 11 and tmax == 2.0

@@ -54,10 +54,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
@@ -66,10 +66,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}

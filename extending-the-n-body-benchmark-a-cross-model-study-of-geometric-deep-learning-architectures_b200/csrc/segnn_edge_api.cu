@@ -5,6 +5,11 @@ namespace segnn {
 int edge_layer_fp32(const float* pos, const float* mass, int B, int N, int n, const float* pq, const float* w_edge1,
                     const float* w2_ss, const float* w2_vs, const float* w2_sv, const float* w2_vv, const float* b2,
                     const float* bn_mul, const float* bn_add, float* agg, float* moments, cudaStream_t stream);
+int edge_layer_tc(const float* pos, const float* mass, int B, int N, int n, const float* pq, const float* w_edge1,
+                  const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg,
+                  cudaStream_t stream);
+int64_t pack_w2_tc(const float* ss, const float* vs, const float* sv, const float* vv, int n, void* out,
+                   cudaStream_t stream);
 }  // namespace segnn
 
 using namespace segnn;
@@ -24,16 +29,19 @@ int segnn_edge_layer_fwd(int mode, const float* pos, const float* mass, int B, i
     return edge_layer_fp32(pos, mass, B, N, n, pq, w_edge1, w2_ss, w2_vs, w2_sv, w2_vv, b2, bn_mul, bn_add, agg_out,
                            moments, (cudaStream_t)stream);
   }
-  (void)w2_tc;
-  set_error("segnn_edge_layer_fwd: mode %d is not built", mode);
-  return SEGNN_E_UNSUPPORTED;
+  if (mode == SEGNN_MODE_BF16_TC) {
+    SEGNN_CHECK_ARG(w2_tc != nullptr, "tensor-core mode needs the packed weight image (segnn_pack_w2_tc)");
+    SEGNN_CHECK_ARG(moments == nullptr, "tensor-core mode does not emit train-mode moments");
+    SEGNN_CHECK_ARG(N >= 2, "tensor-core mode needs N >= 2");
+    return edge_layer_tc(pos, mass, B, N, n, pq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg_out, (cudaStream_t)stream);
+  }
+  set_error("segnn_edge_layer_fwd: unknown mode %d", mode);
+  return SEGNN_E_INVALID;
 }
 
 int64_t segnn_pack_w2_tc(const float* w2_ss, const float* w2_vs, const float* w2_sv, const float* w2_vv, int n,
                          void* out, segnn_stream_t stream) {
-  (void)w2_ss; (void)w2_vs; (void)w2_sv; (void)w2_vv; (void)n; (void)out; (void)stream;
-  set_error("segnn_pack_w2_tc: tensor-core mode is not built");
-  return SEGNN_E_UNSUPPORTED;
+  return pack_w2_tc(w2_ss, w2_vs, w2_sv, w2_vv, n, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -145,6 +145,23 @@ def counter_add(counter: torch.Tensor, delta: int):
     _bump()
 
 
+TC_MULTIPLICITIES = (32, 64, 96)
+
+
+def pack_w2_tc(w2: dict, n: int) -> torch.Tensor:
+    """message_layer_2 weight image for the tcgen05 kernel: [128 lanes][3n] bf16 pairs (segnn_pack_w2_tc)."""
+    nbytes = lib.segnn_pack_w2_tc(None, None, None, None, n, None, None)
+    if nbytes <= 0:
+        check(int(nbytes), "segnn_pack_w2_tc")
+    out = torch.empty(nbytes // 4, dtype=torch.int32, device=w2["ss"].device)
+    with torch.cuda.device(out.device):
+        rc = lib.segnn_pack_w2_tc(_p(w2["ss"]), _p(w2["vs"]), _p(w2["sv"]), _p(w2["vv"]), n, _p(out), _stream())
+    if rc < 0:
+        check(int(rc), "segnn_pack_w2_tc")
+    _bump()
+    return out
+
+
 def tc_available() -> bool:
     """True when the tcgen05 (SEGNN_MODE_BF16_TC) edge kernel is compiled into the library."""
     return lib.segnn_pack_w2_tc(None, None, None, None, 96, None, None) > 0

@@ -56,6 +56,8 @@ class SEGNNLayer(nn.Module):
             upd1=packing.pack_node_tp(f(self.update_layer_1.tp.weight), f(self.update_layer_1.biases), 2, n, 2 * n),
             upd2=packing.pack_node_tp(f(self.update_layer_2.tp.weight), f(self.update_layer_2.biases), 1, n, n),
             bn_msg=(None, None), bn_feat=(None, None))
+        if out["msg2"]["ss"].is_cuda and n in ops.TC_MULTIPLICITIES and ops.tc_available():
+            out["msg2"]["tc"] = ops.pack_w2_tc(out["msg2"], n)
         if eval_bn and self.message_norm is not None:
             bn = self.message_norm
             out["bn_msg"] = packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), n,
@@ -175,6 +177,9 @@ class SEGNN(nn.Module):
         w = self.packed(num_nodes - 1)
         mode = _MODES[self.compute_mode]
         n = self.n
+        if mode == ops.MODE_BF16_TC and "tc" not in w["layers"][0]["msg2"]:
+            raise RuntimeError(f"compute_mode='bf16' needs hidden multiplicity in {ops.TC_MULTIPLICITIES} "
+                               f"(hidden_features 64/128/192); this model has n={n}")
         if x_in is None or node_attr is None:
             x_in, node_attr = ops.prep(pos, vel, batch_size, num_nodes)
         h = ops.embed(x_in, node_attr, w["embed"]["w"], w["embed"]["bias"], n)

@@ -26,10 +26,12 @@ PROTOTYPES = {
     "segnn_edge_attr": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_prep_fwd": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_embed_fwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
-    "segnn_node_gemm": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
+    "segnn_node_gemm": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr]),
+    "segnn_node_gemm_tc": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr]),
+    "segnn_pack_node_weight_tc": (_int, [_ptr, _int, _int, _ptr, _ptr]),
     "segnn_tp_combine": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "segnn_edge_layer_fwd": (_int, [_int, _ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
-                                    _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+                                    _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "segnn_pack_w2_tc": (_c.c_int64, [_ptr, _ptr, _ptr, _ptr, _int, _ptr, _ptr]),
     "segnn_head_fwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_integrate": (_int, [_ptr, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _ptr]),

@@ -20,7 +20,8 @@ __device__ __forceinline__ void group_barrier(int id, int count) {
 template <int NT>
 __global__ void __launch_bounds__(NT* kRB)
     edge_layer_fp32_kernel(const float* __restrict__ pos, const float* __restrict__ mass, int nodes, int N, int n,
-                           const float* __restrict__ pq, const float* __restrict__ w_edge1,
+                           const float* __restrict__ pp, const float* __restrict__ qq,
+                           const float* __restrict__ w_edge1,
                            const float* __restrict__ w2_ss, const float* __restrict__ w2_vs,
                            const float* __restrict__ w2_sv, const float* __restrict__ w2_vv,
                            const float* __restrict__ b2, const float* __restrict__ bn_mul,
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(NT* kRB)
   const int i = (int)(r - g * N);
   const int64_t base = g * N;
   const bool act = w < n;
-  const int n6 = 6 * n;
+  const int n3 = 3 * n;
 
   if (w >= n && w < NP) {
     for (int t = 0; t < kEB * 5; ++t) hb[t * NP + w] = 0.f;
@@ -50,13 +51,13 @@ __global__ void __launch_bounds__(NT* kRB)
   float p0s = 0.f, p0g = 0.f, p1 = 0.f, p0sk[3] = {0.f, 0.f, 0.f}, p0gk[3] = {0.f, 0.f, 0.f}, p1k[3] = {0.f, 0.f, 0.f};
   float wd0s = 0.f, wd0g = 0.f, wm0s = 0.f, wm0g = 0.f, wd1 = 0.f, wm1 = 0.f, b2s = 0.f, b2g = 0.f;
   if (act) {
-    const float* pr = pq + r * 4 * n6;
+    const float* pr = pp + r * 4 * n3;
     p0s = pr[w];
     p0g = pr[n + w];
     p1 = pr[2 * n + w];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float* prk = pr + (1 + k) * n6;
+      const float* prk = pr + (1 + k) * n3;
       p0sk[k] = prk[w];
       p0gk[k] = prk[n + w];
       p1k[k] = prk[2 * n + w];
@@ -85,10 +86,10 @@ __global__ void __launch_bounds__(NT* kRB)
       const float ax = kY1 * ux, ay = kY1 * uy, az = kY1 * uz;
       const float mm = mass[s] * mi;
       if (act) {
-        const float* qr = pq + s * 4 * n6 + 3 * n;
-        const float* q1 = qr + n6;
-        const float* q2 = q1 + n6;
-        const float* q3 = q2 + n6;
+        const float* qr = qq + s * 4 * n3;
+        const float* q1 = qr + n3;
+        const float* q2 = q1 + n3;
+        const float* q3 = q2 + n3;
         float zs = p0s + qr[w] + ax * (p0sk[0] + q1[w]) + ay * (p0sk[1] + q2[w]) + az * (p0sk[2] + q3[w]) +
                    len * wd0s + mm * wm0s;
         float zg = p0g + qr[n + w] + ax * (p0gk[0] + q1[n + w]) + ay * (p0gk[1] + q2[n + w]) +
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(NT* kRB)
 }
 
 template <int NT>
-static int launch_fp32(const float* pos, const float* mass, int nodes, int N, int n, const float* pq,
+static int launch_fp32(const float* pos, const float* mass, int nodes, int N, int n, const float* pp, const float* qq,
                        const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
                        const float* w2_vv, const float* b2, const float* bn_mul, const float* bn_add, float* agg,
                        float* moments, cudaStream_t stream) {
@@ -221,7 +222,7 @@ static int launch_fp32(const float* pos, const float* mass, int nodes, int N, in
   }
   dim3 block(NT, kRB);
   unsigned grid = (unsigned)(((int64_t)nodes + kRB - 1) / kRB);
-  kern<<<grid, block, smem, stream>>>(pos, mass, nodes, N, n, pq, w_edge1, w2_ss, w2_vs, w2_sv, w2_vv, b2, bn_mul,
+  kern<<<grid, block, smem, stream>>>(pos, mass, nodes, N, n, pp, qq, w_edge1, w2_ss, w2_vs, w2_sv, w2_vv, b2, bn_mul,
                                       bn_add, agg, moments);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
@@ -231,7 +232,8 @@ static int launch_fp32(const float* pos, const float* mass, int nodes, int N, in
   return SEGNN_OK;
 }
 
-int edge_layer_fp32(const float* pos, const float* mass, int B, int N, int n, const float* pq, const float* w_edge1,
+int edge_layer_fp32(const float* pos, const float* mass, int B, int N, int n, const float* pp, const float* qq,
+                    const float* w_edge1,
                     const float* w2_ss, const float* w2_vs, const float* w2_sv, const float* w2_vv, const float* b2,
                     const float* bn_mul, const float* bn_add, float* agg, float* moments, cudaStream_t stream) {
   const int64_t nodes64 = (int64_t)B * N;
@@ -241,7 +243,7 @@ int edge_layer_fp32(const float* pos, const float* mass, int B, int N, int n, co
   }
   const int nodes = (int)nodes64;
 #define SEGNN_FP32_CASE(NT_)                                                                                   \
-  return launch_fp32<NT_>(pos, mass, nodes, N, n, pq, w_edge1, w2_ss, w2_vs, w2_sv, w2_vv, b2, bn_mul, bn_add, \
+  return launch_fp32<NT_>(pos, mass, nodes, N, n, pp, qq, w_edge1, w2_ss, w2_vs, w2_sv, w2_vv, b2, bn_mul, bn_add, \
                           agg, moments, stream)
   if (n <= 32) SEGNN_FP32_CASE(32);
   if (n <= 64) SEGNN_FP32_CASE(64);

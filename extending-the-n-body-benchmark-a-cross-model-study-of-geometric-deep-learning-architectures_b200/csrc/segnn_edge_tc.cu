@@ -123,10 +123,17 @@ __device__ __forceinline__ float sig_gate_fast(float x) {
   return fmaf(0.5f * kCSig, t, 0.5f * kCSig);
 }
 
+// Warp layout (NW = n / 32): producers [0, 4 NW); epilogue group e at [4 NW + 4 e, 4 NW + 4 e + NW) so that
+// warp % 4 (the TMEM lane quadrant a warp may access) equals the channel block; the MMA warp sits in the unused
+// quadrant slot of epilogue group 0.
 template <int NMUL>
-__global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
+constexpr int tc_num_warps() { return 4 * (NMUL / 32) + 4 + (NMUL / 32 < 4 ? NMUL / 32 : 5); }
+
+template <int NMUL>
+__global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
     edge_layer_tc_kernel(const float* __restrict__ pos, const float* __restrict__ mass, int B, int N,
-                         const float* __restrict__ pq, const float* __restrict__ w_edge1,
+                         const float* __restrict__ pp, const float* __restrict__ qq,
+                         const float* __restrict__ w_edge1,
                          const float* __restrict__ b2, const uint32_t* __restrict__ w2_tc,
                          const float* __restrict__ bn_mul, const float* __restrict__ bn_add,
                          float* __restrict__ agg, int* __restrict__ err_flag) {
@@ -134,13 +141,14 @@ __global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
   constexpr int NW = n / 32;            // warps per producer group
   constexpr int kProdWarps = 4 * NW;
   constexpr int kEpiWarp0 = kProdWarps;
-  constexpr int kMmaWarp = kProdWarps + 8;
+  constexpr int kMmaWarp = NW < 4 ? kEpiWarp0 + NW : kEpiWarp0 + 8;
+  constexpr int kEpiThreads = 2 * NW * 32;
   constexpr int kWeightCols = 3 * n;    // TMEM columns of the weight image
   constexpr int kDBase = kWeightCols;   // accumulator tiles start here (6 x 32 columns)
-  constexpr int n6 = 6 * n;
+  constexpr int n3 = 3 * n;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sB = smem;                                                  // 5n * 128 bytes
   float4* geoA = reinterpret_cast<float4*>(smem + 5 * n * 128);        // [slots][32] (ax, ay, az, valid)
   float2* geoB = reinterpret_cast<float2*>(geoA + kGeoSlots * kCols);  // [slots][32] (dist, m_i m_j)
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
     mbar_init(&empty[0], 1);
     mbar_init(&empty[1], 1);
     mbar_init(dfull, 1);
-    mbar_init(dempty, 256);
+    mbar_init(dempty, kEpiThreads);
     for (int i = 0; i < kGeoSlots; ++i) mbar_init(&gfull[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
   const uint32_t tmem = *tmem_slot;
 
   // ---- message_layer_2 weights -> TMEM (lane = output channel, 2 bf16 of K per column) ------------------------
-  if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+  if (warp >= kEpiWarp0 && warp < kEpiWarp0 + NW) {  // lanes >= n are never read back
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t* src = w2_tc + (size_t)row * kWeightCols;
@@ -215,13 +223,13 @@ __global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
 #pragma unroll
       for (int r = 0; r < kRecv; ++r) {
         const long long node = base + min(i0 + r, N - 1);
-        const float* pr = pq + node * 4 * n6;
+        const float* pr = pp + node * 4 * n3;
         p0s[r] = pr[w];
         p0g[r] = pr[n + w];
         p1[r] = pr[2 * n + w];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const float* prk = pr + (1 + k) * n6;
+          const float* prk = pr + (1 + k) * n3;
           p0sk[r][k] = prk[w];
           p0gk[r][k] = prk[n + w];
           p1k[r][k] = prk[2 * n + w];
@@ -245,16 +253,17 @@ __global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
         }
         named_barrier(1 + q, n);
         if (w == 0) mbar_arrive(&gfull[slot]);  // publishes the group's 8 geometry entries to the epilogue
+        uint2 packed[2][5];
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {
           const int sl = 2 * q + s2;
           const long long sn = base + min(sb * kSend + sl, N - 1);
-          const float* qr = pq + sn * 4 * n6 + 3 * n;
+          const float* qr = qq + sn * 4 * n3;
           const float q0s = qr[w], q0g = qr[n + w], q1 = qr[2 * n + w];
           float q0sk[3], q0gk[3], q1k[3];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const float* qk = qr + (1 + k) * n6;
+            const float* qk = qr + (1 + k) * n3;
             q0sk[k] = qk[w];
             q0gk[k] = qk[n + w];
             q1k[k] = qk[2 * n + w];
@@ -279,17 +288,21 @@ __global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
             o_y[r] = vy;
             o_z[r] = vz;
           }
-          // 4 receivers of this sender = 4 consecutive columns = 8 bytes per plane row
+          packed[s2][0] = make_uint2(pack_bf16x2(o_s[0], o_s[1]), pack_bf16x2(o_s[2], o_s[3]));
+          packed[s2][1] = make_uint2(pack_bf16x2(o_d[0], o_d[1]), pack_bf16x2(o_d[2], o_d[3]));
+          packed[s2][2] = make_uint2(pack_bf16x2(o_x[0], o_x[1]), pack_bf16x2(o_x[2], o_x[3]));
+          packed[s2][3] = make_uint2(pack_bf16x2(o_y[0], o_y[1]), pack_bf16x2(o_y[2], o_y[3]));
+          packed[s2][4] = make_uint2(pack_bf16x2(o_z[0], o_z[1]), pack_bf16x2(o_z[2], o_z[3]));
+        }
+        // 2 senders x 4 receivers = 8 consecutive columns = one 16-byte chunk per plane row (conflict-free with
+        // the 128B swizzle: 8 consecutive rows hit 8 distinct chunks)
+        {
           const int chunk = st * 4 + q;
-          const int byte_in_chunk = s2 * 8;
 #pragma unroll
           for (int p = 0; p < 5; ++p) {
-            const float* o = p == 0 ? o_s : p == 1 ? o_d : p == 2 ? o_x : p == 3 ? o_y : o_z;
             const int row = p * n + w;
-            uint2 v;
-            v.x = pack_bf16x2(o[0], o[1]);
-            v.y = pack_bf16x2(o[2], o[3]);
-            *reinterpret_cast<uint2*>(sB + row * 128 + ((chunk ^ (row & 7)) << 4) + byte_in_chunk) = v;
+            *reinterpret_cast<uint4*>(sB + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+                make_uint4(packed[0][p].x, packed[0][p].y, packed[1][p].x, packed[1][p].y);
           }
         }
         proxy_fence();
@@ -332,6 +345,7 @@ __global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
     }
   } else {
     // ============================ epilogue: gate + aggregation ================================================
+    if (warp >= kEpiWarp0 + 4 + NW || (warp >= kEpiWarp0 + NW && warp < kEpiWarp0 + 4)) goto done;  // spare slots
     const int eg = (warp - kEpiWarp0) >> 2;   // column half
     const int quad = warp & 3;
     const int w = quad * 32 + lane;           // channel = TMEM lane
@@ -393,7 +407,7 @@ __global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
 #pragma unroll
           for (int c = 0; c < 4; ++c) xch[(r * 4 + c) * n + w] = acc[r][c];
       }
-      named_barrier(6, 256);
+      named_barrier(6, kEpiThreads);
       if (eg == 0 && act) {
 #pragma unroll
         for (int r = 0; r < kRecv; ++r) {
@@ -406,10 +420,11 @@ __global__ void __launch_bounds__((4 * (NMUL / 32) + 9) * 32, 1)
           }
         }
       }
-      named_barrier(6, 256);
+      named_barrier(6, kEpiThreads);
     }
   }
 
+done:
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -447,10 +462,11 @@ __global__ void pack_w2_kernel(const float* __restrict__ ss, const float* __rest
 }
 
 template <int NMUL>
-static int launch_tc(const float* pos, const float* mass, int B, int N, const float* pq, const float* w_edge1,
+static int launch_tc(const float* pos, const float* mass, int B, int N, const float* pp, const float* qq,
+                     const float* w_edge1,
                      const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg,
                      int* err_flag, cudaStream_t stream) {
-  constexpr int threads = (4 * (NMUL / 32) + 9) * 32;
+  constexpr int threads = tc_num_warps<NMUL>() * 32;
   const size_t smem = 1024 + (size_t)5 * NMUL * 128 + kGeoSlots * kCols * (sizeof(float4) + sizeof(float2)) +
                       (size_t)kRecv * 4 * NMUL * sizeof(float) + 16 * sizeof(uint64_t) + 16;
   auto kern = edge_layer_tc_kernel<NMUL>;
@@ -466,7 +482,7 @@ static int launch_tc(const float* pos, const float* mass, int B, int N, const fl
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long items = (long long)B * ((N + kRecv - 1) / kRecv);
   const unsigned grid = (unsigned)(items < sms ? items : sms);
-  kern<<<grid, threads, smem, stream>>>(pos, mass, B, N, pq, w_edge1, b2, (const uint32_t*)w2_tc, bn_mul, bn_add, agg,
+  kern<<<grid, threads, smem, stream>>>(pos, mass, B, N, pp, qq, w_edge1, b2, (const uint32_t*)w2_tc, bn_mul, bn_add, agg,
                                         err_flag);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
@@ -478,12 +494,13 @@ static int launch_tc(const float* pos, const float* mass, int B, int N, const fl
 
 }  // namespace tc
 
-int edge_layer_tc(const float* pos, const float* mass, int B, int N, int n, const float* pq, const float* w_edge1,
+int edge_layer_tc(const float* pos, const float* mass, int B, int N, int n, const float* pp, const float* qq,
+                  const float* w_edge1,
                   const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg,
                   cudaStream_t stream) {
-  if (n == 32) return tc::launch_tc<32>(pos, mass, B, N, pq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
-  if (n == 64) return tc::launch_tc<64>(pos, mass, B, N, pq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
-  if (n == 96) return tc::launch_tc<96>(pos, mass, B, N, pq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
+  if (n == 32) return tc::launch_tc<32>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
+  if (n == 64) return tc::launch_tc<64>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
+  if (n == 96) return tc::launch_tc<96>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
   set_error("edge_layer_tc: tensor-core mode is built for hidden multiplicity n in {32, 64, 96} (hidden_features "
             "64/128/192), got n=%d", n);
   return SEGNN_E_UNSUPPORTED;

@@ -156,7 +156,8 @@ constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16;
 __global__ void __launch_bounds__(256) node_gemm_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                                                       int nodes, int n_in, const float* __restrict__ w_s,
                                                       const float* __restrict__ w_v, const float* __restrict__ bias,
-                                                      int n_bias, int n_out, float* __restrict__ y) {
+                                                      int n_bias, int n_out, float* __restrict__ y0,
+                                                      float* __restrict__ y1, int split) {
   __shared__ float As[kGemmBK][kGemmBM + 4];
   __shared__ float Bs[kGemmBK][kGemmBN + 4];
   const int cls = blockIdx.z;  // 0 scalar rows, 1 vector rows
@@ -222,7 +223,8 @@ __global__ void __launch_bounds__(256) node_gemm_kernel(const float* __restrict_
       if (c >= n_out) continue;
       float v = acc[i][j];
       if (cls == 0 && bias != nullptr && c < n_bias) v += bias[c];
-      y[plane * n_out + c] = v;
+      if (c < split) y0[plane * split + c] = v;
+      else y1[plane * (n_out - split) + (c - split)] = v;
     }
   }
 }
@@ -413,15 +415,19 @@ int segnn_embed_fwd(const float* x_in, const float* node_attr, const float* w_em
 }
 
 int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const float* w_s, const float* w_v,
-                    const float* bias, int n_bias, int n_out, float* y, segnn_stream_t stream) {
+                    const float* bias, int n_bias, int n_out, float* y0, float* y1, int split,
+                    segnn_stream_t stream) {
   SEGNN_CHECK_ARG(nodes >= 0 && n_in >= 1 && n_out >= 1, "bad sizes");
   if (nodes == 0) return SEGNN_OK;
-  SEGNN_CHECK_ARG(x0 && w_s && w_v && y, "null pointer");
+  SEGNN_CHECK_ARG(x0 && w_s && w_v && y0, "null pointer");
   SEGNN_CHECK_ARG(bias == nullptr || (n_bias >= 0 && n_bias <= n_out), "n_bias out of range");
+  if (y1 == nullptr) split = n_out;
+  SEGNN_CHECK_ARG(split > 0 && split <= n_out, "split out of range");
   int64_t row_tiles = ((int64_t)nodes * 3 + kGemmBM - 1) / kGemmBM;
   SEGNN_CHECK_ARG(row_tiles < (1LL << 31), "too many rows");
   dim3 grid((unsigned)row_tiles, (n_out + kGemmBN - 1) / kGemmBN, 2);
-  node_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, x1, nodes, n_in, w_s, w_v, bias, n_bias, n_out, y);
+  node_gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, x1, nodes, n_in, w_s, w_v, bias, n_bias, n_out, y0, y1,
+                                                           split);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

@@ -1,0 +1,315 @@
+// Node GEMM on tcgen05 (bf16 mode): y[node][c][:] = cat_K(x0[node][c], x1[node][c]) @ (c == 0 ? W_s : W_v).
+//
+// Rows (node, plane) are the MMA M dimension: a CTA owns 128-row tiles of ONE row class (scalar planes or vector
+// planes; blockIdx.y) so that a single weight matrix stays resident in shared memory for the whole kernel.
+//   A tile  [128 rows][K]   fp32 in HBM -> bf16, K-major, 128B swizzle, in shared memory (double buffered)
+//   B       [n_out][K]      bf16 (pre-transposed weights), K-major, 128B swizzle, loaded once per CTA
+//   D       [128][NC]       fp32 in TMEM, NC = output-column chunk (<= 192), double buffered
+// Warp roles: 4 loader warps, 4 epilogue warps (TMEM lane quadrant = warp % 4), 1 MMA warp.
+// The kernel is HBM-bound (writes 4*n_out bytes per row against 2*K*n_out flops): the roofline is the copy rate.
+#include <cuda_bf16.h>
+
+#include "segnn_common.cuh"
+
+namespace segnn {
+namespace ngemm {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int it = 0; it < (1 << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();  // protocol bug: fail loudly instead of hanging the GPU
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B: 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;   // D = f32
+  d |= 1u << 7;   // A = bf16
+  d |= 1u << 10;  // B = bf16
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(128 >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+#define SEGNN_NG_LD8(taddr, r)                                                                                     \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                            \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])     \
+               : "r"(taddr))
+
+constexpr int kThreads = 288;  // 4 loader + 4 epilogue + 1 MMA warps
+
+// rows of class 0: node r -> plane (r*4); class 1: row r -> node r/3, plane 1 + r%3
+__device__ __forceinline__ long long plane_of(int cls, long long r) {
+  return cls == 0 ? r * 4 : (r / 3) * 4 + 1 + (r % 3);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    node_gemm_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int nodes, int n_in,
+                        const __nv_bfloat16* __restrict__ wt_s, const __nv_bfloat16* __restrict__ wt_v,
+                        const float* __restrict__ bias, int n_bias, int n_out, int nc, float* __restrict__ y0,
+                        float* __restrict__ y1, int split, int ctas_cls0) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int K = x1 ? 2 * n_in : n_in;
+  const int katoms = (K + 63) / 64;
+  const int a_bytes = katoms * 128 * 128;       // one A stage
+  const int b_atom_bytes = n_out * 128;         // one K-atom of B
+  uint8_t* sA = smem;                           // 2 stages
+  uint8_t* sB = smem + 2 * a_bytes;             // katoms * n_out * 128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + katoms * b_atom_bytes);
+  uint64_t* afull = bars;       // [2] loaders -> MMA
+  uint64_t* aempty = bars + 2;  // [2] MMA -> loaders
+  uint64_t* dfull = bars + 4;   // [2] MMA -> epilogue
+  uint64_t* dempty = bars + 6;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the first ctas_cls0 CTAs own the scalar-plane rows, the rest the vector-plane rows (3x as many)
+  const int cls = (int)blockIdx.x < ctas_cls0 ? 0 : 1;
+  const int cta = cls == 0 ? blockIdx.x : blockIdx.x - ctas_cls0;
+  const int cta_stride = cls == 0 ? ctas_cls0 : gridDim.x - ctas_cls0;
+  const long long rows = cls == 0 ? (long long)nodes : (long long)nodes * 3;
+  const long long tiles = (rows + 127) / 128;
+  const __nv_bfloat16* __restrict__ wt = cls == 0 ? wt_s : wt_v;
+  const int nchunks = n_out / nc;
+
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&afull[i], 128);
+      mbar_init(&aempty[i], 1);
+      mbar_init(&dfull[i], 1);
+      mbar_init(&dempty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // weights -> smem (bf16 [n_out][K] K-major in HBM): 16-byte pieces of 8 k
+  {
+    const int k8n = K / 8;
+    for (int idx = tid; idx < n_out * k8n; idx += kThreads) {
+      const int row = idx / k8n, k8 = idx - row * k8n;
+      const uint4 v = *reinterpret_cast<const uint4*>(wt + (size_t)row * K + k8 * 8);
+      *reinterpret_cast<uint4*>(sB + (k8 >> 3) * b_atom_bytes + row * 128 + (((k8 & 7) ^ (row & 7)) << 4)) = v;
+    }
+    proxy_fence();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== loaders: fp32 rows -> bf16 swizzled A tile =====================
+    const int k4n = K / 4;  // float4 pieces per row
+    uint32_t t = 0;
+    for (long long tile = cta; tile < tiles; tile += cta_stride, ++t) {
+      const int ab = t & 1;
+      mbar_wait(&aempty[ab], ((t >> 1) & 1) ^ 1);
+      uint8_t* dst = sA + ab * a_bytes;
+      const long long r0 = tile * 128;
+      for (int idx = tid; idx < 128 * k4n; idx += 128) {
+        const int r = idx / k4n, k4 = idx - r * k4n;
+        const long long gr = r0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < rows) {
+          const long long pl = plane_of(cls, gr);
+          const int k = k4 * 4;
+          v = k < n_in ? *reinterpret_cast<const float4*>(x0 + pl * n_in + k)
+                       : *reinterpret_cast<const float4*>(x1 + pl * n_in + (k - n_in));
+        }
+        const int k = k4 * 4;
+        uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        *reinterpret_cast<uint2*>(dst + (k >> 6) * (128 * 128) + r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) +
+                                  (k & 7) * 2) = o;
+      }
+      proxy_fence();
+      mbar_arrive(&afull[ab]);
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(nc);
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    uint32_t t = 0, dcount = 0;
+    for (long long tile = cta; tile < tiles; tile += cta_stride, ++t) {
+      const int ab = t & 1;
+      mbar_wait(&afull[ab], (t >> 1) & 1);
+      for (int c = 0; c < nchunks; ++c, ++dcount) {
+        const int db = dcount & 1;
+        mbar_wait(&dempty[db], ((dcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          for (int s = 0; s < K / 16; ++s) {
+            const uint32_t koff = (s >> 2) * (128 * 128) + (s & 3) * 32;
+            const uint32_t boff = (s >> 2) * b_atom_bytes + (c * nc) * 128 + (s & 3) * 32;
+            mma_ss(tmem + db * 256, make_desc(sA_addr + ab * a_bytes + koff), make_desc(sB_addr + boff), idesc, s > 0);
+          }
+          tc_commit(&dfull[db]);
+          if (c == nchunks - 1) tc_commit(&aempty[ab]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> HBM =====================
+    const int quad = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const int r = quad * 32 + lane;
+    const int n_out1 = n_out - split;
+    uint32_t dcount = 0;
+    for (long long tile = cta; tile < tiles; tile += cta_stride) {
+      const long long gr = tile * 128 + r;
+      const bool live = gr < rows;
+      const long long pl = live ? plane_of(cls, gr) : 0;
+      for (int c = 0; c < nchunks; ++c, ++dcount) {
+        const int db = dcount & 1;
+        mbar_wait(&dfull[db], (dcount >> 1) & 1);
+        tc_fence_after();
+        for (int j = 0; j < nc; j += 16) {
+          uint32_t a[8], b[8];
+          SEGNN_NG_LD8(tmem + lane_base + db * 256 + j, a);
+          SEGNN_NG_LD8(tmem + lane_base + db * 256 + j + 8, b);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (j + 16 >= nc) {  // last columns of this accumulator are in registers
+            tc_fence_before();
+            mbar_arrive(&dempty[db]);
+          }
+          if (live) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t* v = h == 0 ? a : b;
+              const int col = c * nc + j + h * 8;
+              float f[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                f[q] = __uint_as_float(v[q]);
+                if (cls == 0 && bias != nullptr && col + q < n_bias) f[q] += bias[col + q];
+              }
+              float* dst = col < split ? y0 + pl * split + col : y1 + pl * n_out1 + (col - split);
+              *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+__global__ void transpose_bf16_kernel(const float* __restrict__ w, int K, int n_out, __nv_bfloat16* __restrict__ wt) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < K * n_out; idx += gridDim.x * blockDim.x) {
+    const int o = idx / K, k = idx - o * K;
+    wt[idx] = __float2bfloat16(w[(size_t)k * n_out + o]);
+  }
+}
+
+}  // namespace ngemm
+}  // namespace segnn
+
+using namespace segnn;
+
+extern "C" {
+
+int segnn_pack_node_weight_tc(const float* w, int K, int n_out, void* wt_bf16, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(w && wt_bf16 && K > 0 && n_out > 0, "bad arguments");
+  ngemm::transpose_bf16_kernel<<<(K * n_out + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      w, K, n_out, (__nv_bfloat16*)wt_bf16);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                       const float* bias, int n_bias, int n_out, float* y0, float* y1, int split,
+                       segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n_in >= 1 && n_out >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x0 && wt_s && wt_v && y0, "null pointer");
+  const int K = x1 ? 2 * n_in : n_in;
+  SEGNN_CHECK_ARG(n_in % 16 == 0 && K <= 192, "tensor-core node GEMM needs n_in % 16 == 0 and K <= 192");
+  SEGNN_CHECK_ARG(n_out % 16 == 0, "tensor-core node GEMM needs n_out % 16 == 0");
+  if (y1 == nullptr) split = n_out;
+  SEGNN_CHECK_ARG(split % 8 == 0 && split > 0 && split <= n_out, "split must be a positive multiple of 8");
+  SEGNN_CHECK_ARG(bias == nullptr || (n_bias >= 0 && n_bias <= n_out), "n_bias out of range");
+  int nc = 0;
+  for (int c = 192; c >= 16; c -= 16)
+    if (n_out % c == 0) { nc = c; break; }
+  const int katoms = (K + 63) / 64;
+  const size_t smem = 1024 + (size_t)2 * katoms * 128 * 128 + (size_t)katoms * n_out * 128 + 8 * 8 + 16;
+  if (smem > 227 * 1024) {
+    set_error("segnn_node_gemm_tc: K=%d, n_out=%d needs %zu bytes of shared memory", K, n_out, smem);
+    return SEGNN_E_UNSUPPORTED;
+  }
+  cudaError_t err = cudaFuncSetAttribute(ngemm::node_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+  if (err != cudaSuccess) {
+    set_error("segnn_node_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    return SEGNN_E_CUDA;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // one persistent CTA per SM: a quarter of them on the scalar-plane rows (1/4 of all rows), the rest on the
+  // vector-plane rows
+  const long long tiles0 = ((long long)nodes + 127) / 128, tiles1 = ((long long)nodes * 3 + 127) / 128;
+  long long c0 = sms / 4 > 0 ? sms / 4 : 1;
+  if (c0 > tiles0) c0 = tiles0;
+  long long c1 = sms - c0;
+  if (c1 > tiles1) c1 = tiles1;
+  ngemm::node_gemm_tc_kernel<<<(unsigned)(c0 + c1), ngemm::kThreads, smem, (cudaStream_t)stream>>>(
+      x0, x1, nodes, n_in, (const __nv_bfloat16*)wt_s, (const __nv_bfloat16*)wt_v, bias, n_bias, n_out, nc, y0, y1,
+      split, (int)c0);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+}  // extern "C"

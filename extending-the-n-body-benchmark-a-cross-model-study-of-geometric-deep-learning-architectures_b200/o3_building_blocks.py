@@ -71,7 +71,7 @@ class O3TensorProduct(nn.Module):
         x = data_in1.float()
         xs = [packing.to_planar(x[:, b * 4 * n_in:(b + 1) * 4 * n_in], n_in) for b in range(n_blocks)]
         attr = data_in2.float().contiguous()
-        y = ops.node_gemm(xs[0], xs[1] if n_blocks == 2 else None, w["w_s"], w["w_v"], None, 0, n0 + n_out)
+        y = ops.node_gemm(xs[0], xs[1] if n_blocks == 2 else None, w, n0 + n_out)
         out = ops.tp_combine(y, attr, n_out, gate, bias=w["bias"])
         return packing.from_planar(out).to(data_in1.dtype)
 

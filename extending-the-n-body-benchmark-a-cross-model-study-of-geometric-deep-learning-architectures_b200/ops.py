@@ -9,7 +9,7 @@ import torch
 
 from ._lib import MODE_BF16_TC, MODE_FP32, check, lib
 
-__all__ = ["edge_index", "edge_attr", "prep", "embed", "node_gemm", "tp_combine", "edge_layer", "head",
+__all__ = ["edge_index", "edge_attr", "prep", "embed", "node_gemm", "pack_node_weight_tc", "tp_combine", "edge_layer", "head",
            "integrate", "counter_add", "launch_count", "MODE_FP32", "MODE_BF16_TC"]
 
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -86,14 +86,35 @@ def embed(x_in, node_attr, w_embed, bias, n: int):
     return h
 
 
-def node_gemm(x0, x1, w_s, w_v, bias, n_bias: int, n_out: int, out: Optional[torch.Tensor] = None):
+def node_gemm(x0, x1, w, n_out: int, bias=None, n_bias: int = 0, split: int = 0, tc: bool = False):
+    """w: dict with fp32 'w_s','w_v' [K][n_out] (and bf16 'wt_s','wt_v' [n_out][K] when tc). With split > 0 returns
+    (y0 [nodes,4,split], y1 [nodes,4,n_out-split]), else one tensor [nodes,4,n_out]."""
     nodes, _, n_in = x0.shape
-    y = out if out is not None else torch.empty((nodes, 4, n_out), dtype=torch.float32, device=x0.device)
-    with torch.cuda.device(x0.device):
-        check(lib.segnn_node_gemm(_p(x0), _p(x1), nodes, n_in, _p(w_s), _p(w_v), _p(bias), n_bias, n_out, _p(y),
-                                  _stream()), "segnn_node_gemm")
+    dev = x0.device
+    if split:
+        y0 = torch.empty((nodes, 4, split), dtype=torch.float32, device=dev)
+        y1 = torch.empty((nodes, 4, n_out - split), dtype=torch.float32, device=dev)
+    else:
+        y0, y1 = torch.empty((nodes, 4, n_out), dtype=torch.float32, device=dev), None
+    with torch.cuda.device(dev):
+        if tc:
+            check(lib.segnn_node_gemm_tc(_p(x0), _p(x1), nodes, n_in, _p(w["wt_s"]), _p(w["wt_v"]), _p(bias), n_bias,
+                                         n_out, _p(y0), _p(y1), split, _stream()), "segnn_node_gemm_tc")
+        else:
+            check(lib.segnn_node_gemm(_p(x0), _p(x1), nodes, n_in, _p(w["w_s"]), _p(w["w_v"]), _p(bias), n_bias,
+                                      n_out, _p(y0), _p(y1), split, _stream()), "segnn_node_gemm")
     _bump()
-    return y
+    return (y0, y1) if split else y0
+
+
+def pack_node_weight_tc(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [K][n_out] -> bf16 [n_out][K] (segnn_pack_node_weight_tc)."""
+    K, n_out = w.shape
+    out = torch.empty((n_out, K), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib.segnn_pack_node_weight_tc(_p(w), K, n_out, _p(out), _stream()), "segnn_pack_node_weight_tc")
+    _bump()
+    return out
 
 
 def tp_combine(y, node_attr, n: int, gate: bool, bias=None, residual=None, bn_mul=None, bn_add=None,
@@ -107,14 +128,14 @@ def tp_combine(y, node_attr, n: int, gate: bool, bias=None, residual=None, bn_mu
     return o
 
 
-def edge_layer(mode: int, pos, mass, batch_size: int, num_nodes: int, n: int, pq, w_edge1, w2, bn_mul=None,
+def edge_layer(mode: int, pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_mul=None,
                bn_add=None, want_moments: bool = False):
     """w2: dict with fp32 blocks 'ss','vs','sv','vv','b' and (tensor-core mode) 'tc' image."""
     nodes = batch_size * num_nodes
     agg = torch.empty((nodes, 4, n), dtype=torch.float32, device=pos.device)
     mom = torch.empty((nodes, 2 * n), dtype=torch.float32, device=pos.device) if want_moments else None
     with torch.cuda.device(pos.device):
-        check(lib.segnn_edge_layer_fwd(mode, _p(pos), _p(mass), batch_size, num_nodes, n, _p(pq), _p(w_edge1),
+        check(lib.segnn_edge_layer_fwd(mode, _p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1),
                                        _p(w2.get("ss")), _p(w2.get("vs")), _p(w2.get("sv")), _p(w2.get("vv")),
                                        _p(w2["b"]), _p(w2.get("tc")), _p(bn_mul), _p(bn_add), _p(agg), _p(mom),
                                        _stream()), "segnn_edge_layer_fwd")

@@ -58,6 +58,9 @@ class SEGNNLayer(nn.Module):
             bn_msg=(None, None), bn_feat=(None, None))
         if out["msg2"]["ss"].is_cuda and n in ops.TC_MULTIPLICITIES and ops.tc_available():
             out["msg2"]["tc"] = ops.pack_w2_tc(out["msg2"], n)
+            for key in ("msg1", "upd1", "upd2"):
+                out[key]["wt_s"] = ops.pack_node_weight_tc(out[key]["w_s"])
+                out[key]["wt_v"] = ops.pack_node_weight_tc(out[key]["w_v"])
         if eval_bn and self.message_norm is not None:
             bn = self.message_norm
             out["bn_msg"] = packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), n,
@@ -70,15 +73,16 @@ class SEGNNLayer(nn.Module):
     def run(self, w, mode: int, h, pos, mass, node_attr, batch_size: int, num_nodes: int):
         """One layer on planar features h [nodes,4,n] (eval-mode BatchNorm)."""
         n = self.n
+        tc = mode == ops.MODE_BF16_TC
         m1 = w["msg1"]
-        pq = ops.node_gemm(h, None, m1["w_s"], m1["w_v"], m1["bias"], 2 * n, 6 * n)
-        agg = ops.edge_layer(mode, pos, mass, batch_size, num_nodes, n, pq, m1["w_edge"], w["msg2"],
+        p, q = ops.node_gemm(h, None, m1, 6 * n, bias=m1["bias"], n_bias=2 * n, split=3 * n, tc=tc)
+        agg = ops.edge_layer(mode, pos, mass, batch_size, num_nodes, n, p, q, m1["w_edge"], w["msg2"],
                              w["bn_msg"][0], w["bn_msg"][1])
         u1 = w["upd1"]
-        y1 = ops.node_gemm(h, agg, u1["w_s"], u1["w_v"], None, 0, 3 * n)
+        y1 = ops.node_gemm(h, agg, u1, 3 * n, tc=tc)
         g1 = ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"])
         u2 = w["upd2"]
-        y2 = ops.node_gemm(g1, None, u2["w_s"], u2["w_v"], None, 0, 2 * n)
+        y2 = ops.node_gemm(g1, None, u2, 2 * n, tc=tc)
         return ops.tp_combine(y2, node_attr, n, False, bias=u2["bias"], residual=h, bn_mul=w["bn_feat"][0],
                               bn_add=w["bn_feat"][1])
 
@@ -163,6 +167,9 @@ class SEGNN(nn.Module):
                 layers=[layer.pack(degree) for layer in self.layers],
                 pool1=packing.pack_node_tp(f(self.pre_pool1.tp.weight), f(self.pre_pool1.biases), 1, n, 2 * n),
                 head=packing.pack_head(f(self.pre_pool2.tp.weight), n))
+            if "tc" in self._packed["layers"][0]["msg2"]:
+                for key in ("w_s", "w_v"):
+                    self._packed["pool1"]["wt" + key[1:]] = ops.pack_node_weight_tc(self._packed["pool1"][key])
             self._pack_key = key
         return self._packed
 
@@ -188,7 +195,7 @@ class SEGNN(nn.Module):
             h = layer.run(lw, mode, h, pos, mass, node_attr, batch_size, num_nodes)
             per_layer.append(h)
         p1 = w["pool1"]
-        y = ops.node_gemm(h, None, p1["w_s"], p1["w_v"], None, 0, 3 * n)
+        y = ops.node_gemm(h, None, p1, 3 * n, tc=(mode == ops.MODE_BF16_TC))
         hp = ops.tp_combine(y, node_attr, n, True, bias=p1["bias"])
         pred = ops.head(hp, node_attr, w["head"], n)
         if return_layers:

@@ -79,9 +79,22 @@ int segnn_embed_fwd(const float* x_in, const float* node_attr, const float* w_em
  * of the attribute coupling:  y[node][c][:] = concat_K(x0[node][c], x1[node][c]) @ (c == 0 ? w_s : w_v),
  * c = 0 scalar plane, c = 1..3 vector planes.  x0, x1 planar [nodes][4][n_in] (x1 may be NULL);
  * w_s, w_v [K][n_out] row-major with K = n_in * (x1 ? 2 : 1); bias (may be NULL) [n_bias] is added to
- * columns [0, n_bias) of the c = 0 plane.  y [nodes][4][n_out]. */
+ * columns [0, n_bias) of the c = 0 plane.  Output columns [0, split) go to y0 [nodes][4][split] and columns
+ * [split, n_out) to y1 [nodes][4][n_out - split]; y1 == NULL => everything goes to y0 [nodes][4][n_out].
+ * fp32 FFMA kernel (the 1e-5 parity mode). */
 int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const float* w_s, const float* w_v,
-                    const float* bias, int n_bias, int n_out, float* y, segnn_stream_t stream);
+                    const float* bias, int n_bias, int n_out, float* y0, float* y1, int split,
+                    segnn_stream_t stream);
+
+/* Same contraction on tcgen05 (bf16 operands, fp32 accumulate in TMEM, fp32 output): wt_s, wt_v are the
+ * weights pre-transposed to bf16 [n_out][K] by segnn_pack_node_weight_tc.  Needs n_in % 16 == 0, K <= 192,
+ * n_out % 16 == 0, split % 8 == 0. */
+int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                       const float* bias, int n_bias, int n_out, float* y0, float* y1, int split,
+                       segnn_stream_t stream);
+
+/* w [K][n_out] fp32 -> wt [n_out][K] bf16 (the B operand image of segnn_node_gemm_tc). */
+int segnn_pack_node_weight_tc(const float* w, int K, int n_out, void* wt_bf16, segnn_stream_t stream);
 
 /* Attribute coupling + epilogue of a node-level tensor product.  With a = node_attr[node] = (a0, a1[3]):
  *   z0[w]    = a0 * y[0][w]      + sum_k a1[k] * y[1+k][w] + bias[w]   w < n0 (l=0 outputs; bias may be NULL)
@@ -102,8 +115,9 @@ int segnn_tp_combine(const float* y, const float* node_attr, int nodes, int n, i
  * implicit fully-connected graph, eval-mode message BatchNorm folded into the aggregate:
  *   agg[i] = bn_mul * sum_{j != i} gate(msg2(gate(msg1(x_i, x_j, |r_ij|, m_i m_j; Y(r_ij))); Y(r_ij))) + bn_add
  * message_layer_1 is linear in (x_i, x_j), so its weight contraction is hoisted to the node GEMM:
- *   pq [nodes][4][6n] = per plane (P0[2n], P1[n], Q0[2n], Q1[n]) -- receiver (P) and sender (Q) projections
- *   with the constant Y_0 and the bias folded in (see pack_msg1 in the host package).
+ *   p, q [nodes][4][3n] = per plane (X0[2n], X1[n]) -- receiver (P) and sender (Q) projections with the
+ *   constant Y_0 and the bias folded in (see pack_msg1 in the host package; the node GEMM writes both with
+ *   split = 3n).
  * w_edge1 [6n] = (d->0e [2n], mm->0e [2n], d->1o [n], mm->1o [n]) (Y_0 folded into the 0e parts).
  * msg2 weights (fp32 mode): w2_ss [n][2n] (Y_0 folded), w2_vs [n][2n] (1/sqrt3 folded), w2_sv [n][n],
  *   w2_vv [n][n] (Y_0 folded), b2 [2n].
@@ -112,8 +126,8 @@ int segnn_tp_combine(const float* y, const float* node_attr, int nodes, int n, i
  * agg_out planar [nodes][4][n].
  * moments (may be NULL): [nodes][2n] per-receiver sums needed for train-mode batch statistics:
  *   (sum_j m_s[w]^2 , sum_j |m_v[w]|^2); the plain sums are agg itself when bn_mul == NULL. */
-int segnn_edge_layer_fwd(int mode, const float* pos, const float* mass, int B, int N, int n, const float* pq,
-                         const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
+int segnn_edge_layer_fwd(int mode, const float* pos, const float* mass, int B, int N, int n, const float* p,
+                         const float* q, const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
                          const float* w2_vv, const float* b2, const void* w2_tc, const float* bn_mul,
                          const float* bn_add, float* agg_out, float* moments, segnn_stream_t stream);
 

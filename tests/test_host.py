@@ -32,7 +32,7 @@ def test_cabi_argument_errors_without_gpu():
     assert b"null" in lib.segnn_last_error()
     assert lib.segnn_edge_index(0, 5, None, None) == 0  # empty batch is a no-op
     assert lib.segnn_edge_layer_fwd(7, None, None, 0, 5, 8, None, None, None, None, None, None, None, None, None,
-                                    None, None, None, None) == 0
+                                    None, None, None, None, None) == 0
 
 
 def test_no_cpu_fallback():

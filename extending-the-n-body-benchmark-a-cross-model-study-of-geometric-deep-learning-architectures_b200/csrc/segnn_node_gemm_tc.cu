@@ -5,7 +5,8 @@
 //   A tile  [128 rows][K]   fp32 in HBM -> bf16, K-major, 128B swizzle, in shared memory (double buffered)
 //   B       [n_out][K]      bf16 (pre-transposed weights), K-major, 128B swizzle, loaded once per CTA
 //   D       [128][NC]       fp32 in TMEM, NC = output-column chunk (<= 192), double buffered
-// Warp roles: 4 loader warps, 4 epilogue warps (TMEM lane quadrant = warp % 4), 1 MMA warp.
+// Warp roles: 8 loader warps (2 threads per row, 12 independent 16-byte loads in flight each), 4 epilogue warps
+// (TMEM lane quadrant = warp % 4), 1 MMA warp.
 // The kernel is HBM-bound (writes 4*n_out bytes per row against 2*K*n_out flops): the roofline is the copy rate.
 #include <cuda_bf16.h>
 
@@ -80,7 +81,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])     \
                : "r"(taddr))
 
-constexpr int kThreads = 288;  // 4 loader + 4 epilogue + 1 MMA warps
+constexpr int kLoadWarps = 8;
+constexpr int kThreads = (kLoadWarps + 5) * 32;  // 8 loader + 4 epilogue + 1 MMA warps
+constexpr int kMmaWarp = kLoadWarps + 4;
 
 // rows of class 0: node r -> plane (r*4); class 1: row r -> node r/3, plane 1 + r%3
 __device__ __forceinline__ long long plane_of(int cls, long long r) {
@@ -117,14 +120,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   const __nv_bfloat16* __restrict__ wt = cls == 0 ? wt_s : wt_v;
   const int nchunks = n_out / nc;
 
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&afull[i], 128);
+      mbar_init(&afull[i], kLoadWarps * 32);
       mbar_init(&aempty[i], 1);
       mbar_init(&dfull[i], 1);
       mbar_init(&dempty[i], 128);
@@ -146,34 +149,44 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kLoadWarps) {
     // ===================== loaders: fp32 rows -> bf16 swizzled A tile =====================
-    const int k4n = K / 4;  // float4 pieces per row
+    // thread -> (row = tid / 2, half = tid & 1); each half-row is k4h consecutive float4 pieces, fetched in
+    // batches of up to 12 independent loads so a whole tile is in flight per SM
+    const int r = tid >> 1, half = tid & 1;
+    const int k4h = K / 8;  // float4 pieces per half row
     uint32_t t = 0;
     for (long long tile = cta; tile < tiles; tile += cta_stride, ++t) {
       const int ab = t & 1;
+      const long long gr = tile * 128 + r;
+      const bool live = gr < rows;
+      const long long pl = live ? plane_of(cls, gr) : 0;
       mbar_wait(&aempty[ab], ((t >> 1) & 1) ^ 1);
-      uint8_t* dst = sA + ab * a_bytes;
-      const long long r0 = tile * 128;
-      for (int idx = tid; idx < 128 * k4n; idx += 128) {
-        const int r = idx / k4n, k4 = idx - r * k4n;
-        const long long gr = r0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < rows) {
-          const long long pl = plane_of(cls, gr);
-          const int k = k4 * 4;
-          v = k < n_in ? *reinterpret_cast<const float4*>(x0 + pl * n_in + k)
-                       : *reinterpret_cast<const float4*>(x1 + pl * n_in + (k - n_in));
+      uint8_t* dst = sA + ab * a_bytes + r * 128;
+      for (int b0 = 0; b0 < k4h; b0 += 12) {
+        float4 v[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int k = (half * k4h + b0 + i) * 4;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && b0 + i < k4h)
+            v[i] = k < n_in ? *reinterpret_cast<const float4*>(x0 + pl * n_in + k)
+                            : *reinterpret_cast<const float4*>(x1 + pl * n_in + (k - n_in));
         }
-        const int k = k4 * 4;
-        uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-        *reinterpret_cast<uint2*>(dst + (k >> 6) * (128 * 128) + r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) +
-                                  (k & 7) * 2) = o;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          if (b0 + i < k4h) {
+            const int k = (half * k4h + b0 + i) * 4;
+            const uint2 o = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+            *reinterpret_cast<uint2*>(dst + (k >> 6) * (128 * 128) + ((((k & 63) >> 3) ^ (r & 7)) << 4) +
+                                      (k & 7) * 2) = o;
+          }
+        }
       }
       proxy_fence();
       mbar_arrive(&afull[ab]);
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc(nc);
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
@@ -243,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 __global__ void transpose_bf16_kernel(const float* __restrict__ w, int K, int n_out, __nv_bfloat16* __restrict__ wt) {

@@ -17,7 +17,9 @@
 // Warp roles (one CTA per SM, persistent over work items = (graph, block of 4 receivers)):
 //   4 producer groups (n threads each): group q owns senders 2q, 2q+1 of the 8-sender block and all 4 receivers;
 //   2 epilogue groups (128 threads each, lane quadrant = warp % 4): group e owns tile columns [16e, 16e+16);
-//   1 MMA warp (lane 0 issues; the warp also owns the TMEM allocation).
+//   1 MMA warp (lane 0 issues; the warp also owns the TMEM allocation);
+//   1 loader warp (lane 0 issues one cp.async.bulk per tile: the 8 consecutive sender rows of the Q projection,
+//   36 KB at n = 96, double buffered behind mbarriers).
 // Tile column c = sender_local * 4 + receiver_local.
 #include <cuda_bf16.h>
 
@@ -29,7 +31,8 @@ namespace tc {
 constexpr int kRecv = 4;      // receivers per work item
 constexpr int kSend = 8;      // senders per tile
 constexpr int kCols = 32;     // edges (columns) per tile
-constexpr int kGeoSlots = 4;  // geometry ring depth (see the reuse argument in DESIGN.md)
+constexpr int kGeoSlots = 8;  // geometry ring depth (tile t+1 is written while tile t computes)
+constexpr int kMaxNodesPerGraph = 2048;  // positions of one graph are staged in shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -127,7 +130,7 @@ __device__ __forceinline__ float sig_gate_fast(float x) {
 // warp % 4 (the TMEM lane quadrant a warp may access) equals the channel block; the MMA warp sits in the unused
 // quadrant slot of epilogue group 0.
 template <int NMUL>
-constexpr int tc_num_warps() { return 4 * (NMUL / 32) + 4 + (NMUL / 32 < 4 ? NMUL / 32 : 5); }
+constexpr int tc_num_warps() { return 4 * (NMUL / 32) + 4 + NMUL / 32 + 1; }
 
 template <int NMUL>
 __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
@@ -141,7 +144,10 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
   constexpr int NW = n / 32;            // warps per producer group
   constexpr int kProdWarps = 4 * NW;
   constexpr int kEpiWarp0 = kProdWarps;
-  constexpr int kMmaWarp = NW < 4 ? kEpiWarp0 + NW : kEpiWarp0 + 8;
+  static_assert(NW < 4, "the MMA warp sits in the unused quadrant slot of epilogue group 0");
+  constexpr int kMmaWarp = kEpiWarp0 + NW;
+  constexpr int kLoadWarp = kEpiWarp0 + 4 + NW;
+  constexpr int kQStageBytes = kSend * 4 * 3 * n * (int)sizeof(float);
   constexpr int kEpiThreads = 2 * NW * 32;
   constexpr int kWeightCols = 3 * n;    // TMEM columns of the weight image
   constexpr int kDBase = kWeightCols;   // accumulator tiles start here (6 x 32 columns)
@@ -150,16 +156,20 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sB = smem;                                                  // 5n * 128 bytes
-  float4* geoA = reinterpret_cast<float4*>(smem + 5 * n * 128);        // [slots][32] (ax, ay, az, valid)
+  float* sQ = reinterpret_cast<float*>(smem + 5 * n * 128);            // [2][8 senders][4 planes][3n]
+  float4* sPos = reinterpret_cast<float4*>(smem + 5 * n * 128 + 2 * kQStageBytes);  // [N] (x, y, z, mass)
+  float4* geoA = sPos + N;                                             // [slots][32] (ax, ay, az, valid)
   float2* geoB = reinterpret_cast<float2*>(geoA + kGeoSlots * kCols);  // [slots][32] (dist, m_i m_j)
   float* xch = reinterpret_cast<float*>(geoB + kGeoSlots * kCols);     // [4 recv][4 planes][n]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kRecv * 4 * n);   // full[2], empty[2], dfull, dempty, gfull[4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kRecv * 4 * n);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   uint64_t* full = bars;
   uint64_t* empty = bars + 2;
   uint64_t* dfull = bars + 4;
   uint64_t* dempty = bars + 5;
-  uint64_t* gfull = bars + 6;  // geometry ring: one barrier per slot, one arrival per producer group
+  uint64_t* qfull = bars + 6;   // [2] bulk copy landed (expect_tx)
+  uint64_t* qempty = bars + 8;  // [2] producers done reading the Q stage
+  uint64_t* gfull = bars + 10;  // [8] geometry ring: one barrier per slot, one arrival per producer group
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -176,6 +186,10 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
     mbar_init(&empty[1], 1);
     mbar_init(dfull, 1);
     mbar_init(dempty, kEpiThreads);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qfull[i], 1);
+      mbar_init(&qempty[i], 4 * n);
+    }
     for (int i = 0; i < kGeoSlots; ++i) mbar_init(&gfull[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -213,11 +227,34 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
     const int w = (warp % NW) * 32 + lane;    // channel
     const float wd0s = w_edge1[w], wd0g = w_edge1[n + w], wm0s = w_edge1[2 * n + w], wm0g = w_edge1[3 * n + w],
                 wd1 = w_edge1[4 * n + w], wm1 = w_edge1[5 * n + w];
+    // geometry of this group's 8 columns (2 senders x 4 receivers) of sender block sb, one thread per column
+    auto write_geometry = [&](int sb, int i0, int slot) {
+      if (w < 8) {
+        const int sl = 2 * q + (w >> 2), r = w & 3;
+        const int jj = sb * kSend + sl, ii = i0 + r;
+        const float4 ps = sPos[min(jj, N - 1)], pr = sPos[min(ii, N - 1)];
+        float ux, uy, uz, len;
+        unit_vec(ps.x - pr.x, ps.y - pr.y, ps.z - pr.z, ux, uy, uz, len);
+        const bool valid = (jj < N) && (ii < N) && (jj != ii);
+        const int c = sl * 4 + r;
+        geoA[slot * kCols + c] = make_float4(kY1 * ux, kY1 * uy, kY1 * uz, valid ? 1.0f : 0.0f);
+        geoB[slot * kCols + c] = make_float2(len, ps.w * pr.w);
+      }
+      named_barrier(1 + q, n);
+      if (w == 0) mbar_arrive(&gfull[slot]);  // publishes the group's 8 geometry entries to the epilogue
+    };
     uint32_t t = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       const long long g = item / recv_blocks;
       const int i0 = (int)(item - g * recv_blocks) * kRecv;
       const long long base = g * N;
+      // stage the graph's positions and masses (all producer groups together)
+      named_barrier(5, 4 * n);
+      for (int i = q * n + w; i < N; i += 4 * n) {
+        const long long node = base + i;
+        sPos[i] = make_float4(pos[node * 3 + 0], pos[node * 3 + 1], pos[node * 3 + 2], mass[node]);
+      }
+      named_barrier(5, 4 * n);
       // receiver-side projections of the 4 receivers (clamped: invalid receivers are masked by the epilogue)
       float p0s[kRecv], p0g[kRecv], p1[kRecv], p0sk[kRecv][3], p0gk[kRecv][3], p1k[kRecv][3];
 #pragma unroll
@@ -235,30 +272,18 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
           p1k[r][k] = prk[2 * n + w];
         }
       }
+      write_geometry(0, i0, t & (kGeoSlots - 1));
       for (int sb = 0; sb < send_blocks; ++sb, ++t) {
         const int st = t & 1, slot = t & (kGeoSlots - 1);
+        const int nvalid = min(kSend, N - sb * kSend);
         mbar_wait(&empty[st], ((t >> 1) & 1) ^ 1, err_flag);
-        // geometry of this group's 8 columns (2 senders x 4 receivers), one thread per column
-        if (w < 8) {
-          const int sl = 2 * q + (w >> 2), r = w & 3;
-          const int jj = sb * kSend + sl, ii = i0 + r;
-          const long long sn = base + min(jj, N - 1), rn = base + min(ii, N - 1);
-          float ux, uy, uz, len;
-          unit_vec(pos[sn * 3 + 0] - pos[rn * 3 + 0], pos[sn * 3 + 1] - pos[rn * 3 + 1],
-                   pos[sn * 3 + 2] - pos[rn * 3 + 2], ux, uy, uz, len);
-          const bool valid = (jj < N) && (ii < N) && (jj != ii);
-          const int c = sl * 4 + r;
-          geoA[slot * kCols + c] = make_float4(kY1 * ux, kY1 * uy, kY1 * uz, valid ? 1.0f : 0.0f);
-          geoB[slot * kCols + c] = make_float2(len, mass[sn] * mass[rn]);
-        }
-        named_barrier(1 + q, n);
-        if (w == 0) mbar_arrive(&gfull[slot]);  // publishes the group's 8 geometry entries to the epilogue
+        mbar_wait(&qfull[st], (t >> 1) & 1, err_flag);
+        const float* qs = sQ + st * (kQStageBytes / 4);
         uint2 packed[2][5];
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {
           const int sl = 2 * q + s2;
-          const long long sn = base + min(sb * kSend + sl, N - 1);
-          const float* qr = qq + sn * 4 * n3;
+          const float* qr = qs + min(sl, nvalid - 1) * 4 * n3;  // senders past the graph end reuse a valid row
           const float q0s = qr[w], q0g = qr[n + w], q1 = qr[2 * n + w];
           float q0sk[3], q0gk[3], q1k[3];
 #pragma unroll
@@ -294,6 +319,7 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
           packed[s2][3] = make_uint2(pack_bf16x2(o_y[0], o_y[1]), pack_bf16x2(o_y[2], o_y[3]));
           packed[s2][4] = make_uint2(pack_bf16x2(o_z[0], o_z[1]), pack_bf16x2(o_z[2], o_z[3]));
         }
+        mbar_arrive(&qempty[st]);  // this thread is done with the staged sender rows
         // 2 senders x 4 receivers = 8 consecutive columns = one 16-byte chunk per plane row (conflict-free with
         // the 128B swizzle: 8 consecutive rows hit 8 distinct chunks)
         {
@@ -307,6 +333,29 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
         }
         proxy_fence();
         mbar_arrive(&full[st]);
+        if (sb + 1 < send_blocks) write_geometry(sb + 1, i0, (t + 1) & (kGeoSlots - 1));
+      }
+    }
+  } else if (warp == kLoadWarp) {
+    // ============================ loader: one bulk copy of the tile's sender rows per tile ======================
+    if (lane == 0) {
+      uint32_t t = 0;
+      for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long g = item / recv_blocks;
+        for (int sb = 0; sb < send_blocks; ++sb, ++t) {
+          const int st = t & 1;
+          mbar_wait(&qempty[st], ((t >> 1) & 1) ^ 1, err_flag);
+          const int nvalid = min(kSend, N - sb * kSend);
+          const uint32_t bytes = (uint32_t)nvalid * 4 * n3 * (uint32_t)sizeof(float);
+          const float* src = qq + (g * N + (long long)sb * kSend) * 4 * n3;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&qfull[st])), "r"(bytes)
+                       : "memory");
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  smem_u32(sQ + st * (kQStageBytes / 4))),
+              "l"(src), "r"(bytes), "r"(smem_u32(&qfull[st]))
+              : "memory");
+        }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -345,7 +394,7 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
     }
   } else {
     // ============================ epilogue: gate + aggregation ================================================
-    if (warp >= kEpiWarp0 + 4 + NW || (warp >= kEpiWarp0 + NW && warp < kEpiWarp0 + 4)) goto done;  // spare slots
+    if (warp >= kEpiWarp0 + NW && warp < kEpiWarp0 + 4) goto done;  // unused quadrant slots of group 0
     const int eg = (warp - kEpiWarp0) >> 2;   // column half
     const int quad = warp & 3;
     const int w = quad * 32 + lane;           // channel = TMEM lane
@@ -370,7 +419,7 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
 
       for (int sb = 0; sb < send_blocks; ++sb, ++t) {
         const int slot = t & (kGeoSlots - 1);
-        mbar_wait(&gfull[slot], (t >> 2) & 1, err_flag);  // acquires the producers' geometry writes
+        mbar_wait(&gfull[slot], (t >> 3) & 1, err_flag);  // acquires the producers' geometry writes
         mbar_wait(dfull, t & 1, err_flag);
         tc_fence_after();
 #pragma unroll
@@ -467,8 +516,9 @@ static int launch_tc(const float* pos, const float* mass, int B, int N, const fl
                      const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg,
                      int* err_flag, cudaStream_t stream) {
   constexpr int threads = tc_num_warps<NMUL>() * 32;
-  const size_t smem = 1024 + (size_t)5 * NMUL * 128 + kGeoSlots * kCols * (sizeof(float4) + sizeof(float2)) +
-                      (size_t)kRecv * 4 * NMUL * sizeof(float) + 16 * sizeof(uint64_t) + 16;
+  const size_t smem = 1024 + (size_t)5 * NMUL * 128 + (size_t)2 * kSend * 4 * 3 * NMUL * sizeof(float) +
+                      (size_t)N * sizeof(float4) + kGeoSlots * kCols * (sizeof(float4) + sizeof(float2)) +
+                      (size_t)kRecv * 4 * NMUL * sizeof(float) + 24 * sizeof(uint64_t) + 16;
   auto kern = edge_layer_tc_kernel<NMUL>;
   {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -498,6 +548,11 @@ int edge_layer_tc(const float* pos, const float* mass, int B, int N, int n, cons
                   const float* w_edge1,
                   const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg,
                   cudaStream_t stream) {
+  if (N > tc::kMaxNodesPerGraph) {
+    set_error("edge_layer_tc: N=%d nodes per graph exceeds the tensor-core kernel's staging limit (%d)", N,
+              tc::kMaxNodesPerGraph);
+    return SEGNN_E_UNSUPPORTED;
+  }
   if (n == 32) return tc::launch_tc<32>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
   if (n == 64) return tc::launch_tc<64>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
   if (n == 96) return tc::launch_tc<96>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);

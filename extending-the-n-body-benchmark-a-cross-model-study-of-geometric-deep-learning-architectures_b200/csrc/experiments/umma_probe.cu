@@ -217,6 +217,197 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int N, int ts, int iters,
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+
+// MMA rate v2: fully unrolled issue (descriptors precomputed in registers), rotating over NACC accumulators of
+// N columns each, so issue overhead, dependent-accumulate latency and tensor throughput can be told apart.
+template <int NACC, int UNROLL>
+__global__ void __launch_bounds__(128) mma_rate2_kernel(int N, int ts, int iters, long long* cycles, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) mbar_init(&bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, N, 0, 1);
+    uint64_t bdesc[UNROLL], adesc[UNROLL];
+    uint32_t atm[UNROLL], dtm[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      bdesc[u] = make_desc(smem_u32(smem) + (u & 7) * 2048, 16, 1024);
+      adesc[u] = make_desc(smem_u32(smem) + 16384 + (u & 3) * 32, 16, 1024);
+      atm[u] = tmem + (u & 7) * 8;
+      dtm[u] = tmem + 128 + (u % NACC) * N;
+    }
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i += UNROLL) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (ts) mma_ts(dtm[u], atm[u], bdesc[u], idesc, 1);
+        else    mma_ss(dtm[u], adesc[u], bdesc[u], idesc, 1);
+      }
+    }
+    tc_commit(&bar);
+    bool ok = mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    *cycles = t1 - t0;
+    if (!ok) *status = -2;
+  }
+  __syncthreads();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+template <int NACC>
+static void run_rate2(int N, int ts, long long* d_cyc, int* d_status) {
+  const int iters = 4096;
+  if (128 + NACC * N > 512) return;
+  CK(cudaFuncSetAttribute(mma_rate2_kernel<NACC, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaMemset(d_status, 0, 4));
+  mma_rate2_kernel<NACC, 24><<<1, 128, 64 * 1024>>>(N, ts, iters - iters % 24, d_cyc, d_status);
+  CK(cudaDeviceSynchronize());
+  long long cyc; int status;
+  CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost));
+  const int done = iters - iters % 24;
+  printf("mma_rate2 %s N=%3d NACC=%d unrolled: %.1f clk/MMA (%.0f MAC/clk) status=%d\n", ts ? "TS" : "SS", N, NACC,
+         (double)cyc / done, 128.0 * N * 16 * done / (double)cyc, status);
+}
+
+
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+
+// MMA rate v3: the whole warp runs the (warp-uniform) issue loop, only the tcgen05.mma is under elect.sync, so the
+// compiler can keep descriptors in uniform registers.
+template <int NACC>
+__global__ void __launch_bounds__(128) mma_rate3_kernel(int N, int ts, int iters, long long* cycles, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) mbar_init(&bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(128, N, 0, 1);
+    const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const uint64_t b0 = make_desc(sbase, 16, 1024);
+    const uint64_t a0 = make_desc(sbase + 16384, 16, 1024);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i += 8 * NACC) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          if (elect_one()) {
+            if (ts) mma_ts(tmem + 128 + a * N, tmem + s * 8, b0 + (uint64_t)(s * 128), idesc, 1);
+            else    mma_ss(tmem + 128 + a * N, a0 + (uint64_t)((s & 3) * 2), b0 + (uint64_t)(s * 128), idesc, 1);
+          }
+        }
+      }
+    }
+    if (elect_one()) tc_commit(&bar);
+    __syncwarp();
+    bool ok = mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (tid == 0) { *cycles = t1 - t0; if (!ok) *status = -2; }
+  }
+  __syncthreads();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+template <int NACC>
+static void run_rate3(int N, int ts, long long* d_cyc, int* d_status) {
+  if (128 + NACC * N > 512) return;
+  const int iters = 8 * NACC * 64;
+  CK(cudaFuncSetAttribute(mma_rate3_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaMemset(d_status, 0, 4));
+  mma_rate3_kernel<NACC><<<1, 128, 64 * 1024>>>(N, ts, iters, d_cyc, d_status);
+  CK(cudaDeviceSynchronize());
+  long long cyc; int status;
+  CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost));
+  printf("mma_rate3 %s N=%3d NACC=%d uniform-issue: %.1f clk/MMA (%.0f MAC/clk) status=%d\n", ts ? "TS" : "SS", N, NACC,
+         (double)cyc / iters, 128.0 * N * 16 * iters / (double)cyc, status);
+}
+
+
+// MMA rate v4: NWARPS warps issue concurrently (each its own accumulator), to tell a tensor-pipe floor from a
+// single-warp issue limit.
+__global__ void __launch_bounds__(256) mma_rate4_kernel(int N, int nwarps, int iters, long long* cycles, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar[8];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ long long tstart[8], tend[8];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 1024 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid < 8) mbar_init(&bar[tid], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp < nwarps) {
+    const uint32_t idesc = make_idesc(128, N, 0, 1);
+    const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const uint64_t b0 = make_desc(sbase, 16, 1024);
+    const uint32_t dacc = tmem + 128 + warp * N;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        if (elect_one()) mma_ts(dacc, tmem + s * 8, b0 + (uint64_t)(s * 128), idesc, 1);
+      }
+    }
+    if (elect_one()) tc_commit(&bar[warp]);
+    __syncwarp();
+    bool ok = mbar_wait(&bar[warp], 0);
+    long long t1 = clock64();
+    if ((tid & 31) == 0) { tstart[warp] = t0; tend[warp] = t1; if (!ok) *status = -2; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long a = tstart[0], b = tend[0];
+    for (int w = 1; w < nwarps; ++w) { a = min(a, tstart[w]); b = max(b, tend[w]); }
+    *cycles = b - a;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 // tcgen05.ld bandwidth: every warp streams x16 loads over 256 columns of its lane quadrant
 __global__ void __launch_bounds__(256) tmem_ld_kernel(int iters, long long* cycles, float* sink) {
   __shared__ uint32_t tmem_base_s;
@@ -349,6 +540,32 @@ int main() {
       CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost));
       printf("mma_rate %s M=128 N=%3d K=16: %.1f clk/MMA (%.0f MAC/clk) status=%d\n", ts ? "TS" : "SS", N,
              (double)cyc / iters, 128.0 * N * 16 * iters / (double)cyc, status);
+    }
+  for (int ts = 1; ts >= 0; --ts)
+    for (int N : {16, 32, 64, 128}) {
+      run_rate2<1>(N, ts, d_cyc, d_status);
+      run_rate2<2>(N, ts, d_cyc, d_status);
+      run_rate2<3>(N, ts, d_cyc, d_status);
+      run_rate2<6>(N, ts, d_cyc, d_status);
+    }
+  for (int ts = 1; ts >= 0; --ts)
+    for (int N : {16, 32, 64, 128}) {
+      run_rate3<1>(N, ts, d_cyc, d_status);
+      run_rate3<2>(N, ts, d_cyc, d_status);
+      run_rate3<6>(N, ts, d_cyc, d_status);
+    }
+  CK(cudaFuncSetAttribute(mma_rate4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  for (int N : {16, 32, 64})
+    for (int nw : {1, 2, 4, 6}) {
+      if (128 + nw * N > 512) continue;
+      const int iters = 2048;
+      CK(cudaMemset(d_status, 0, 4));
+      mma_rate4_kernel<<<1, 256, 64 * 1024>>>(N, nw, iters, d_cyc, d_status);
+      CK(cudaDeviceSynchronize());
+      long long cyc; int status;
+      CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost));
+      printf("mma_rate4 TS N=%3d issuing warps=%d: %.1f clk per MMA overall (%.0f MAC/clk) status=%d\n", N, nw,
+             (double)cyc / (iters * nw), 128.0 * N * 16 * iters * nw / (double)cyc, status);
     }
   for (int threads : {128, 256}) {
     const int iters = 4096;

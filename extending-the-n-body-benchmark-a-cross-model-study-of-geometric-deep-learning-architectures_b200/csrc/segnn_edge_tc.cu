@@ -17,9 +17,9 @@
 // Warp roles (one CTA per SM, persistent over work items = (graph, block of 4 receivers)):
 //   4 producer groups (n threads each): group q owns senders 2q, 2q+1 of the 8-sender block and all 4 receivers;
 //   2 epilogue groups (128 threads each, lane quadrant = warp % 4): group e owns tile columns [16e, 16e+16);
-//   1 MMA warp (lane 0 issues; the warp also owns the TMEM allocation);
-//   1 loader warp (lane 0 issues one cp.async.bulk per tile: the 8 consecutive sender rows of the Q projection,
-//   36 KB at n = 96, double buffered behind mbarriers).
+//   1 MMA warp (warp-uniform loop, one elected lane issues; it also owns the TMEM allocation and issues one
+//   cp.async.bulk per tile: the 8 consecutive sender rows of the Q projection, 36 KB at n = 96, double buffered;
+//   the copy for tile t+2 is issued when the producers have signalled tile t complete).
 // Tile column c = sender_local * 4 + receiver_local.
 #include <cuda_bf16.h>
 
@@ -45,13 +45,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded spin: a protocol bug must never hang the GPU. On timeout the flag is raised and the kernel traps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
   uint32_t done = 0;
-  for (int it = 0; it < (1 << 26); ++it) {
+  for (int it = 0; it < (1 << 22); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint: fewer polls steal issue slots
         : "memory");
     if (done) return;
   }
@@ -110,6 +110,14 @@ __device__ __forceinline__ uint32_t make_idesc() {
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])                          \
                : "memory")
 
+// one elected lane of a converged warp (the tcgen05.mma / commit instructions are issued by a single thread, but the
+// surrounding code stays warp-uniform so descriptors live in uniform registers: profiles/r1_umma_probe.log)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -130,7 +138,7 @@ __device__ __forceinline__ float sig_gate_fast(float x) {
 // warp % 4 (the TMEM lane quadrant a warp may access) equals the channel block; the MMA warp sits in the unused
 // quadrant slot of epilogue group 0.
 template <int NMUL>
-constexpr int tc_num_warps() { return 4 * (NMUL / 32) + 4 + NMUL / 32 + 1; }
+constexpr int tc_num_warps() { return 4 * (NMUL / 32) + 4 + NMUL / 32; }
 
 template <int NMUL>
 __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
@@ -146,7 +154,6 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
   constexpr int kEpiWarp0 = kProdWarps;
   static_assert(NW < 4, "the MMA warp sits in the unused quadrant slot of epilogue group 0");
   constexpr int kMmaWarp = kEpiWarp0 + NW;
-  constexpr int kLoadWarp = kEpiWarp0 + 4 + NW;
   constexpr int kQStageBytes = kSend * 4 * 3 * n * (int)sizeof(float);
   constexpr int kEpiThreads = 2 * NW * 32;
   constexpr int kWeightCols = 3 * n;    // TMEM columns of the weight image
@@ -168,7 +175,6 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
   uint64_t* dfull = bars + 4;
   uint64_t* dempty = bars + 5;
   uint64_t* qfull = bars + 6;   // [2] bulk copy landed (expect_tx)
-  uint64_t* qempty = bars + 8;  // [2] producers done reading the Q stage
   uint64_t* gfull = bars + 10;  // [8] geometry ring: one barrier per slot, one arrival per producer group
 
   const int tid = threadIdx.x;
@@ -188,7 +194,6 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
     mbar_init(dempty, kEpiThreads);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qfull[i], 1);
-      mbar_init(&qempty[i], 4 * n);
     }
     for (int i = 0; i < kGeoSlots; ++i) mbar_init(&gfull[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -319,7 +324,6 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
           packed[s2][3] = make_uint2(pack_bf16x2(o_y[0], o_y[1]), pack_bf16x2(o_y[2], o_y[3]));
           packed[s2][4] = make_uint2(pack_bf16x2(o_z[0], o_z[1]), pack_bf16x2(o_z[2], o_z[3]));
         }
-        mbar_arrive(&qempty[st]);  // this thread is done with the staged sender rows
         // 2 senders x 4 receivers = 8 consecutive columns = one 16-byte chunk per plane row (conflict-free with
         // the 128B swizzle: 8 consecutive rows hit 8 distinct chunks)
         {
@@ -336,56 +340,72 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
         if (sb + 1 < send_blocks) write_geometry(sb + 1, i0, (t + 1) & (kGeoSlots - 1));
       }
     }
-  } else if (warp == kLoadWarp) {
-    // ============================ loader: one bulk copy of the tile's sender rows per tile ======================
-    if (lane == 0) {
-      uint32_t t = 0;
-      for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-        const long long g = item / recv_blocks;
-        for (int sb = 0; sb < send_blocks; ++sb, ++t) {
-          const int st = t & 1;
-          mbar_wait(&qempty[st], ((t >> 1) & 1) ^ 1, err_flag);
-          const int nvalid = min(kSend, N - sb * kSend);
-          const uint32_t bytes = (uint32_t)nvalid * 4 * n3 * (uint32_t)sizeof(float);
-          const float* src = qq + (g * N + (long long)sb * kSend) * 4 * n3;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&qfull[st])), "r"(bytes)
-                       : "memory");
-          asm volatile(
-              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                  smem_u32(sQ + st * (kQStageBytes / 4))),
-              "l"(src), "r"(bytes), "r"(smem_u32(&qfull[st]))
-              : "memory");
-        }
-      }
-    }
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ==================================================================
+    // The whole warp runs this warp-uniform loop; only the tcgen05 instructions sit under elect.sync. A lean issue
+    // sequence matters: one warp sustains ~1 MMA / 24 clk, the tensor pipe needs one 128x32x16 MMA / 16 clk.
     const uint32_t idesc = make_idesc();
-    const uint32_t sB_addr = smem_u32(sB);
+    const uint32_t sB_addr = __shfl_sync(0xffffffffu, smem_u32(sB), 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint64_t bdesc0 = make_b_desc(sB_addr);
+    const uint32_t d0 = tm + kDBase;
+    // bulk copy of the 8 sender rows of tile (item, sb) into Q stage st (one elected lane)
+    auto load_q = [&](long long item, int sb, int st) {
+      if (item < items && elect_one()) {
+        const long long g = item / recv_blocks;
+        const int nvalid = min(kSend, N - sb * kSend);
+        const uint32_t bytes = (uint32_t)nvalid * 4 * n3 * (uint32_t)sizeof(float);
+        const float* src = qq + (g * N + (long long)sb * kSend) * 4 * n3;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&qfull[st])), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sQ + st * (kQStageBytes / 4))),
+                     "l"(src), "r"(bytes), "r"(smem_u32(&qfull[st]))
+                     : "memory");
+      }
+      __syncwarp();
+    };
+    // (item, sb) of the tile two ahead of the current one
+    long long pf_item = blockIdx.x;
+    int pf_sb = 0;
+    auto advance_pf = [&]() {
+      if (++pf_sb == send_blocks) {
+        pf_sb = 0;
+        pf_item += gridDim.x;
+      }
+    };
+    load_q(pf_item, pf_sb, 0);
+    advance_pf();
+    load_q(pf_item, pf_sb, 1);
+    advance_pf();
     uint32_t t = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       for (int sb = 0; sb < send_blocks; ++sb, ++t) {
         const int st = t & 1;
         mbar_wait(&full[st], (t >> 1) & 1, err_flag);
+        load_q(pf_item, pf_sb, st);  // producers are done with Q stage st: refill it for tile t + 2
+        advance_pf();
         mbar_wait(dempty, (t & 1) ^ 1, err_flag);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t bcol = sB_addr + st * 64;
-          const uint32_t d0 = tmem + kDBase;
-#pragma unroll 1
-          for (int s = 0; s < 2 * n / 16; ++s) {
-            const uint64_t b_sd = make_b_desc(bcol + s * 2048);  // rows [16 s, 16 s + 16) of the (s', dot) planes
-            mma_ts(d0 + 0 * kCols, tmem + 0 * n + s * 8, b_sd, idesc, s > 0);
-            mma_ts(d0 + 1 * kCols, tmem + 1 * n + s * 8, b_sd, idesc, s > 0);
+        const uint64_t bst = bdesc0 + (uint64_t)(st * (64 >> 4));  // column half of the swizzled rows
+#pragma unroll
+        for (int s = 0; s < 2 * n / 16; ++s) {
+          // rows [16 s, 16 s + 16) of the (s', dot) planes; 16 rows = 2048 bytes
+          const uint64_t b_sd = bst + (uint64_t)(s * (2048 >> 4));
+          if (elect_one()) {
+            mma_ts(d0 + 0 * kCols, tm + 0 * n + s * 8, b_sd, idesc, s > 0);
+            mma_ts(d0 + 1 * kCols, tm + 1 * n + s * 8, b_sd, idesc, s > 0);
             if (s < n / 16) {
-              mma_ts(d0 + 2 * kCols, tmem + 2 * n + s * 8, b_sd, idesc, s > 0);
+              mma_ts(d0 + 2 * kCols, tm + 2 * n + s * 8, b_sd, idesc, s > 0);
 #pragma unroll
               for (int k = 0; k < 3; ++k) {
-                const uint64_t b_v = make_b_desc(bcol + ((2 + k) * n + 16 * s) * 128);
-                mma_ts(d0 + (3 + k) * kCols, tmem + 2 * n + n / 2 + s * 8, b_v, idesc, s > 0);
+                const uint64_t b_v = bst + (uint64_t)((((2 + k) * n + 16 * s) * 128) >> 4);
+                mma_ts(d0 + (3 + k) * kCols, tm + 2 * n + n / 2 + s * 8, b_v, idesc, s > 0);
               }
             }
           }
+        }
+        if (elect_one()) {
           tc_commit(&empty[st]);
           tc_commit(dfull);
         }

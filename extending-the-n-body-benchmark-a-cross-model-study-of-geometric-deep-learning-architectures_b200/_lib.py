@@ -36,6 +36,15 @@ PROTOTYPES = {
     "segnn_head_fwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_integrate": (_int, [_ptr, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _ptr]),
     "segnn_counter_add": (_int, [_ptr, _int, _ptr]),
+    "segnn_colsum_workspace": (_c.c_int64, [_c.c_int64, _int]),
+    "segnn_colsum": (_int, [_ptr, _ptr, _c.c_int64, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_lincomb": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c.c_int64, _int, _ptr, _ptr]),
+    "segnn_tp_combine_bwd": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_node_gemm_wgrad_workspace": (_c.c_int64, [_int, _int, _int]),
+    "segnn_node_gemm_wgrad": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_edge_layer_bwd": (_int, [_int, _ptr, _ptr, _int, _int, _int] + [_ptr] * 24),
+    "segnn_embed_bwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
+    "segnn_head_bwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
 }
 
 

@@ -1,0 +1,367 @@
+// Training-side node-level kernels (fp32): deterministic column reductions (BatchNorm statistics, bias and weight
+// gradients), per-column affine / linear combination (train-mode BatchNorm forward and backward), backward of the
+// attribute combine + gate, the weight-gradient GEMM, and the backward of the embedding and the head.
+// Reference semantics: e3nn BatchNorm as used at models/segnn/segnn.py:233-235,257-261,282-283; autograd of
+// o3_building_blocks.py:150-203; training/losses.py:22-45.
+#include "segnn_common.cuh"
+
+namespace segnn {
+
+// ------------------------------------------------------------------------------------------------
+// colsum: out[c] = sum_r f(x[r][c], y[r][c]);  mode 0: x, 1: x*x, 2: x*y.  Two deterministic stages.
+// ------------------------------------------------------------------------------------------------
+constexpr int kColsumRowsPerBlock = 256;
+
+__global__ void colsum_stage1(const float* __restrict__ x, const float* __restrict__ y, int64_t rows, int cols,
+                              int mode, float* __restrict__ partial) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int64_t r0 = (int64_t)blockIdx.y * kColsumRowsPerBlock;
+  const int64_t r1 = min(rows, r0 + kColsumRowsPerBlock);
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float v = x[r * cols + c];
+    acc += mode == 0 ? v : (mode == 1 ? v * v : v * y[r * cols + c]);
+  }
+  partial[(int64_t)blockIdx.y * cols + c] = acc;
+}
+
+__global__ void colsum_stage2(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float acc = 0.f;
+  for (int p = 0; p < nparts; ++p) acc += partial[(int64_t)p * cols + c];
+  out[c] = acc;
+}
+
+// out[r][c] = A[c] * dy[r][c] + B[c] * x[r][c] + C[c]   (x / B / C may be NULL)
+__global__ void lincomb_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ A,
+                               const float* __restrict__ B, const float* __restrict__ C, int64_t rows, int cols,
+                               float* __restrict__ out) {
+  const int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cols);
+    float v = A[c] * dy[idx];
+    if (x != nullptr) v = fmaf(B[c], x[idx], v);
+    if (C != nullptr) v += C[c];
+    out[idx] = v;
+  }
+}
+
+// d/dx of c*silu(x) and c*sigmoid(x)
+__device__ __forceinline__ float silu_gate_grad(float x) {
+  const float s = sigmoid_acc(x);
+  return kCSilu * s * (1.0f + x * (1.0f - s));
+}
+__device__ __forceinline__ float sig_gate_grad(float x) {
+  const float s = sigmoid_acc(x);
+  return kCSig * s * (1.0f - s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of tp_combine (without residual / BN: those are handled by the caller)
+//   dy [nodes][4][n0+n], dz0 [nodes][n0] (gradient w.r.t. the l=0 pre-activations = bias gradient rows)
+// ------------------------------------------------------------------------------------------------
+template <bool GATE>
+__global__ void tp_combine_bwd_kernel(const float* __restrict__ y, const float* __restrict__ node_attr, int nodes,
+                                      int n, const float* __restrict__ bias, const float* __restrict__ dout,
+                                      float* __restrict__ dy, float* __restrict__ dz0) {
+  const int n0 = GATE ? 2 * n : n;
+  const int n_out = n0 + n;
+  const int64_t total = (int64_t)nodes * n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t node = idx / n;
+    const int w = (int)(idx - node * n);
+    const float a0 = node_attr[node * 4 + 0], ax = node_attr[node * 4 + 1], ay = node_attr[node * 4 + 2],
+                az = node_attr[node * 4 + 3];
+    const float* y0 = y + node * 4 * n_out;
+    const float* y1 = y0 + n_out;
+    const float* y2 = y1 + n_out;
+    const float* y3 = y2 + n_out;
+    const float* d = dout + node * 4 * n;
+    const float ds = d[w], dvx = d[n + w], dvy = d[2 * n + w], dvz = d[3 * n + w];
+    float dzs, dzg = 0.f, dzx, dzy, dzz;
+    if (GATE) {
+      float zs = a0 * y0[w] + ax * y1[w] + ay * y2[w] + az * y3[w];
+      float zg = a0 * y0[n + w] + ax * y1[n + w] + ay * y2[n + w] + az * y3[n + w];
+      if (bias != nullptr) {
+        zs += bias[w];
+        zg += bias[n + w];
+      }
+      const float t = y0[n0 + w];
+      const float zx = ax * t + a0 * y1[n0 + w], zy = ay * t + a0 * y2[n0 + w], zz = az * t + a0 * y3[n0 + w];
+      const float g = sig_gate(zg);
+      dzs = ds * silu_gate_grad(zs);
+      dzg = sig_gate_grad(zg) * (dvx * zx + dvy * zy + dvz * zz);
+      dzx = g * dvx;
+      dzy = g * dvy;
+      dzz = g * dvz;
+    } else {
+      dzs = ds;
+      dzx = dvx;
+      dzy = dvy;
+      dzz = dvz;
+    }
+    float* e0 = dy + node * 4 * n_out;
+    float* e1 = e0 + n_out;
+    float* e2 = e1 + n_out;
+    float* e3 = e2 + n_out;
+    e0[w] = a0 * dzs;
+    e1[w] = ax * dzs;
+    e2[w] = ay * dzs;
+    e3[w] = az * dzs;
+    if (GATE) {
+      e0[n + w] = a0 * dzg;
+      e1[n + w] = ax * dzg;
+      e2[n + w] = ay * dzg;
+      e3[n + w] = az * dzg;
+    }
+    e0[n0 + w] = ax * dzx + ay * dzy + az * dzz;
+    e1[n0 + w] = a0 * dzx;
+    e2[n0 + w] = a0 * dzy;
+    e3[n0 + w] = a0 * dzz;
+    if (dz0 != nullptr) {
+      dz0[node * n0 + w] = dzs;
+      if (GATE) dz0[node * n0 + n + w] = dzg;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient of the node GEMM: dw_s[k][c] = sum_nodes x[node][0][k] * dy[node][0][c],
+//                                   dw_v[k][c] = sum_nodes sum_{p=1..3} x[node][p][k] * dy[node][p][c]
+// x = cat_K(x0, x1); dy = cat_cols(dy0 [.. split], dy1). 32x32 output tile per block, rows streamed through smem;
+// grid.z splits the rows into slabs whose partial results are reduced by colsum_stage2 (deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgTile = 32, kWgRows = 32;
+
+__global__ void __launch_bounds__(256) node_wgrad_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
+                                                       const float* __restrict__ dy0, const float* __restrict__ dy1,
+                                                       int split, int nodes, int n_in, int n_out, int cls,
+                                                       int64_t rows_per_slab, float* __restrict__ partial) {
+  __shared__ float sx[kWgRows][kWgTile + 1];
+  __shared__ float sd[kWgRows][kWgTile + 1];
+  const int K = x1 ? 2 * n_in : n_in;
+  const int k0 = blockIdx.x * kWgTile, c0 = blockIdx.y * kWgTile;
+  const int64_t rows = cls == 0 ? (int64_t)nodes : (int64_t)nodes * 3;
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_slab;
+  const int64_t r_end = min(rows, r_begin + rows_per_slab);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};                       // output (k0 + ty*4 + i, c0 + tx)
+  const int n_out1 = n_out - split;
+  for (int64_t rb = r_begin; rb < r_end; rb += kWgRows) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = ty * 4 + i;
+      const int64_t r = rb + rr;
+      float vx = 0.f, vd = 0.f;
+      if (r < r_end) {
+        const int64_t plane = cls == 0 ? r * 4 : (r / 3) * 4 + 1 + (r % 3);
+        const int k = k0 + tx, c = c0 + tx;
+        if (k < K) vx = k < n_in ? x0[plane * n_in + k] : x1[plane * n_in + (k - n_in)];
+        if (c < n_out) vd = c < split ? dy0[plane * split + c] : dy1[plane * n_out1 + (c - split)];
+      }
+      sx[rr][tx] = vx;
+      sd[rr][tx] = vd;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < kWgRows; ++rr) {
+      const float dv = sd[rr][tx];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(sx[rr][ty * 4 + i], dv, acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i, c = c0 + tx;
+    if (k < K && c < n_out) partial[((int64_t)blockIdx.z * K + k) * n_out + c] = acc[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding backward (inputs carry no gradient): per-node contributions to (w_embed [6][n], bias [n]) -> [nodes][7][n]
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_bwd_kernel(const float* __restrict__ x_in, const float* __restrict__ node_attr,
+                                 const float* __restrict__ dh, int nodes, int n, float* __restrict__ contrib) {
+  const int64_t total = (int64_t)nodes * n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t node = idx / n;
+    const int c = (int)(idx - node * n);
+    const float* x = x_in + node * 7;
+    const float a0 = node_attr[node * 4 + 0], ax = node_attr[node * 4 + 1], ay = node_attr[node * 4 + 2],
+                az = node_attr[node * 4 + 3];
+    const float* d = dh + node * 4 * n;
+    const float ds = d[c], dx = d[n + c], dy = d[2 * n + c], dz = d[3 * n + c];
+    const float pdot = x[0] * ax + x[1] * ay + x[2] * az;
+    const float vdot = x[3] * ax + x[4] * ay + x[5] * az;
+    float* o = contrib + node * 7 * n;
+    o[0 * n + c] = a0 * (x[0] * dx + x[1] * dy + x[2] * dz);  // W_vec0 -> 1o
+    o[1 * n + c] = a0 * (x[3] * dx + x[4] * dy + x[5] * dz);  // W_vec1 -> 1o
+    o[2 * n + c] = pdot * ds;                                 // W_vec0 -> 0e (/sqrt3 folded)
+    o[3 * n + c] = vdot * ds;                                 // W_vec1 -> 0e
+    o[4 * n + c] = a0 * x[6] * ds;                            // W_sc -> 0e
+    o[5 * n + c] = x[6] * (ax * dx + ay * dy + az * dz);      // W_sc -> 1o
+    o[6 * n + c] = ds;                                        // bias
+  }
+}
+
+// head backward: dh [nodes][4][n] and per-node contributions to w_head [2][n][2] -> [nodes][4][n] (ws0, ws1, wv0, wv1)
+__global__ void head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ node_attr,
+                                const float* __restrict__ w_head, const float* __restrict__ dpred, int nodes, int n,
+                                float* __restrict__ dh, float* __restrict__ contrib) {
+  const int64_t total = (int64_t)nodes * n;
+  const float* ws = w_head;
+  const float* wv = w_head + 2 * n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t node = idx / n;
+    const int u = (int)(idx - node * n);
+    const float a0 = node_attr[node * 4 + 0];
+    const float a1[3] = {node_attr[node * 4 + 1], node_attr[node * 4 + 2], node_attr[node * 4 + 3]};
+    const float* dp = dpred + node * 6;
+    const float* hn = h + node * 4 * n;
+    const float s = hn[u], v[3] = {hn[n + u], hn[2 * n + u], hn[3 * n + u]};
+    float dt[2], dd[2][3];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      dt[o] = a1[0] * dp[o * 3 + 0] + a1[1] * dp[o * 3 + 1] + a1[2] * dp[o * 3 + 2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dd[o][k] = a0 * dp[o * 3 + k];
+    }
+    float* dhn = dh + node * 4 * n;
+    dhn[u] = ws[u * 2 + 0] * dt[0] + ws[u * 2 + 1] * dt[1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dhn[(1 + k) * n + u] = wv[u * 2 + 0] * dd[0][k] + wv[u * 2 + 1] * dd[1][k];
+    float* c = contrib + node * 4 * n;
+    c[0 * n + u] = s * dt[0];
+    c[1 * n + u] = s * dt[1];
+    c[2 * n + u] = v[0] * dd[0][0] + v[1] * dd[0][1] + v[2] * dd[0][2];
+    c[3 * n + u] = v[0] * dd[1][0] + v[1] * dd[1][1] + v[2] * dd[1][2];
+  }
+}
+
+static inline int grid_for_train(int64_t total, int threads) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = 148LL * 32;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace segnn
+
+using namespace segnn;
+
+extern "C" {
+
+int64_t segnn_colsum_workspace(int64_t rows, int cols) {
+  const int64_t parts = (rows + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock;
+  return parts * cols * (int64_t)sizeof(float);
+}
+
+int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mode, float* workspace, float* out,
+                 segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(rows >= 0 && cols >= 1 && mode >= 0 && mode <= 2, "bad arguments");
+  SEGNN_CHECK_ARG(out != nullptr, "null out");
+  if (rows == 0) {
+    cudaMemsetAsync(out, 0, sizeof(float) * cols, (cudaStream_t)stream);
+    return SEGNN_OK;
+  }
+  SEGNN_CHECK_ARG(x && workspace && (mode != 2 || y), "null pointer");
+  const int64_t parts = (rows + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock;
+  SEGNN_CHECK_ARG(parts <= 65535, "too many rows for one colsum call");
+  dim3 grid((cols + 127) / 128, (unsigned)parts);
+  colsum_stage1<<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, rows, cols, mode, workspace);
+  colsum_stage2<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, (int)parts, cols, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_lincomb(const float* dy, const float* x, const float* A, const float* B, const float* C, int64_t rows,
+                  int cols, float* out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(rows >= 0 && cols >= 1, "bad sizes");
+  if (rows == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(dy && A && out && (x == nullptr || B != nullptr), "null pointer");
+  lincomb_kernel<<<grid_for_train(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, A, B, C, rows, cols, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_tp_combine_bwd(const float* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                         const float* dout, float* dy, float* dz0, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(y && node_attr && dout && dy, "null pointer");
+  const int grid = grid_for_train((int64_t)nodes * n, 256);
+  if (gate)
+    tp_combine_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(y, node_attr, nodes, n, bias, dout, dy, dz0);
+  else
+    tp_combine_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(y, node_attr, nodes, n, bias, dout, dy, dz0);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int64_t segnn_node_gemm_wgrad_workspace(int nodes, int K, int n_out) {
+  const int64_t rows = (int64_t)nodes * 3;
+  int64_t slabs = (rows + 4095) / 4096;
+  if (slabs > 64) slabs = 64;
+  if (slabs < 1) slabs = 1;
+  return slabs * (int64_t)K * n_out * (int64_t)sizeof(float);
+}
+
+int segnn_node_gemm_wgrad(const float* x0, const float* x1, const float* dy0, const float* dy1, int split, int nodes,
+                          int n_in, int n_out, float* workspace, float* dw_s, float* dw_v, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n_in >= 1 && n_out >= 1, "bad sizes");
+  const int K = x1 ? 2 * n_in : n_in;
+  SEGNN_CHECK_ARG(dw_s && dw_v, "null output");
+  if (nodes == 0) {
+    cudaMemsetAsync(dw_s, 0, sizeof(float) * K * n_out, (cudaStream_t)stream);
+    cudaMemsetAsync(dw_v, 0, sizeof(float) * K * n_out, (cudaStream_t)stream);
+    return SEGNN_OK;
+  }
+  SEGNN_CHECK_ARG(x0 && dy0 && workspace, "null pointer");
+  if (dy1 == nullptr) split = n_out;
+  SEGNN_CHECK_ARG(split > 0 && split <= n_out, "split out of range");
+  for (int cls = 0; cls < 2; ++cls) {
+    const int64_t rows = cls == 0 ? (int64_t)nodes : (int64_t)nodes * 3;
+    int64_t slabs = ((int64_t)nodes * 3 + 4095) / 4096;  // same count as the workspace query
+    if (slabs > 64) slabs = 64;
+    if (slabs < 1) slabs = 1;
+    const int64_t per = ((rows + slabs - 1) / slabs + kWgRows - 1) / kWgRows * kWgRows;
+    dim3 grid((K + kWgTile - 1) / kWgTile, (n_out + kWgTile - 1) / kWgTile, (unsigned)slabs);
+    node_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, x1, dy0, dy1, split, nodes, n_in, n_out, cls, per,
+                                                             workspace);
+    colsum_stage2<<<(K * n_out + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, (int)slabs, K * n_out,
+                                                                           cls == 0 ? dw_s : dw_v);
+  }
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_embed_bwd(const float* x_in, const float* node_attr, const float* dh, int nodes, int n, float* contrib,
+                    segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x_in && node_attr && dh && contrib, "null pointer");
+  embed_bwd_kernel<<<grid_for_train((int64_t)nodes * n, 256), 256, 0, (cudaStream_t)stream>>>(x_in, node_attr, dh,
+                                                                                            nodes, n, contrib);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_head_bwd(const float* h, const float* node_attr, const float* w_head, const float* dpred, int nodes, int n,
+                   float* dh, float* contrib, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(h && node_attr && w_head && dpred && dh && contrib, "null pointer");
+  head_bwd_kernel<<<grid_for_train((int64_t)nodes * n, 256), 256, 0, (cudaStream_t)stream>>>(h, node_attr, w_head,
+                                                                                           dpred, nodes, n, dh,
+                                                                                           contrib);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+}  // extern "C"

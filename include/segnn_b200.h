@@ -153,6 +153,56 @@ int segnn_integrate(const float* pred, float* pos, float* vel, int nodes, float*
 /* *counter += delta on the device (the rollout's frame cursor; `for step in range(...)`, infer_self_feed.py:99). */
 int segnn_counter_add(int* counter, int delta, segnn_stream_t stream);
 
+
+/* ---- training: train-mode BatchNorm statistics and the backward pass (fp32) ---------------------------- */
+
+/* Deterministic column reduction out[c] = sum_r f(x[r][c], y[r][c]); mode 0: x, 1: x*x, 2: x*y.  Used for e3nn
+ * BatchNorm batch statistics (models/segnn/segnn.py:233-235) and for bias / BatchNorm-parameter gradients.
+ * workspace: segnn_colsum_workspace(rows, cols) bytes. */
+int64_t segnn_colsum_workspace(int64_t rows, int cols);
+int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mode, float* workspace, float* out,
+                 segnn_stream_t stream);
+
+/* out[r][c] = A[c]*dy[r][c] + B[c]*x[r][c] + C[c] (x/B and C may be NULL): train-mode BatchNorm forward
+ * (dy := pre-norm features) and backward with the batch-statistics terms folded into per-column coefficients. */
+int segnn_lincomb(const float* dy, const float* x, const float* A, const float* B, const float* C, int64_t rows,
+                  int cols, float* out, segnn_stream_t stream);
+
+/* Backward of segnn_tp_combine without residual / BatchNorm: dout [nodes][4][n] -> dy [nodes][4][n0+n] and
+ * dz0 [nodes][n0] (rows of the bias gradient; may be NULL). */
+int segnn_tp_combine_bwd(const float* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                         const float* dout, float* dy, float* dz0, segnn_stream_t stream);
+
+/* Weight gradient of the node GEMM: dw_s[k][c] = sum over scalar-plane rows x*dy, dw_v likewise over the three
+ * vector planes; x = cat_K(x0, x1), dy = cat_cols(dy0 [split], dy1).  Deterministic (slab partials + reduction).
+ * (The input gradient is segnn_node_gemm itself with transposed weights.) */
+int64_t segnn_node_gemm_wgrad_workspace(int nodes, int K, int n_out);
+int segnn_node_gemm_wgrad(const float* x0, const float* x1, const float* dy0, const float* dy1, int split, int nodes,
+                          int n_in, int n_out, float* workspace, float* dw_s, float* dw_v, segnn_stream_t stream);
+
+/* Backward of the fused edge layer (autograd of models/segnn/segnn.py:264-284 + the scatter-add): messages are
+ * recomputed, nothing per-edge is stored.  pass 0: dout = dP [nodes][4][3n], message_layer_2 weight/bias gradients
+ * (accumulated into caller-zeroed dw2_*, db2) and per-receiver w_edge1 gradient rows dwe_partial [nodes][6n];
+ * pass 1: dout = dQ.  The gradient reaching every message of receiver i is bn_a*dagg_i + bn_b*m + bn_c
+ * (bn_a, bn_b [2n], bn_c [n]): plain sum, eval BatchNorm or train-mode BatchNorm.  w2t_* are the transposes
+ * ([out][in]) of the w2_* blocks. */
+int segnn_edge_layer_bwd(int pass, const float* pos, const float* mass, int B, int N, int n, const float* p,
+                         const float* q, const float* w_edge1, const float* w2_ss, const float* w2_vs,
+                         const float* w2_sv, const float* w2_vv, const float* b2, const float* w2t_ss,
+                         const float* w2t_vs, const float* w2t_sv, const float* w2t_vv, const float* bn_a,
+                         const float* bn_b, const float* bn_c, const float* dagg, float* dout, float* dw2_ss,
+                         float* dw2_vs, float* dw2_sv, float* dw2_vv, float* db2, float* dwe_partial,
+                         segnn_stream_t stream);
+
+/* Backward of the embedding (inputs carry no gradient): per-node contribution rows [nodes][7][n] to
+ * (w_embed [6][n], bias [n]); reduce with segnn_colsum. */
+int segnn_embed_bwd(const float* x_in, const float* node_attr, const float* dh, int nodes, int n, float* contrib,
+                    segnn_stream_t stream);
+
+/* Backward of the head: dh [nodes][4][n] and per-node contribution rows [nodes][4][n] to w_head. */
+int segnn_head_bwd(const float* h, const float* node_attr, const float* w_head, const float* dpred, int nodes, int n,
+                   float* dh, float* contrib, segnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,6 +245,17 @@ __global__ void head_bwd_kernel(const float* __restrict__ h, const float* __rest
   }
 }
 
+// out = a + b + c (c may be NULL): the three gradient streams that meet at a layer input
+__global__ void add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                            int64_t count, float* __restrict__ out) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < count;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    float v = a[idx] + b[idx];
+    if (c != nullptr) v += c[idx];
+    out[idx] = v;
+  }
+}
+
 static inline int grid_for_train(int64_t total, int threads) {
   int64_t b = (total + threads - 1) / threads;
   const int64_t cap = 148LL * 32;
@@ -286,6 +297,15 @@ int segnn_lincomb(const float* dy, const float* x, const float* A, const float* 
   if (rows == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(dy && A && out && (x == nullptr || B != nullptr), "null pointer");
   lincomb_kernel<<<grid_for_train(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, A, B, C, rows, cols, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_add3(const float* a, const float* b, const float* c, int64_t count, float* out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(count >= 0, "bad size");
+  if (count == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(a && b && out, "null pointer");
+  add3_kernel<<<grid_for_train(count, 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, count, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

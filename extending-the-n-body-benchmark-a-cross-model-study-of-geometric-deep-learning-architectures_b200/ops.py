@@ -186,3 +186,110 @@ def pack_w2_tc(w2: dict, n: int) -> torch.Tensor:
 def tc_available() -> bool:
     """True when the tcgen05 (SEGNN_MODE_BF16_TC) edge kernel is compiled into the library."""
     return lib.segnn_pack_w2_tc(None, None, None, None, 96, None, None) > 0
+
+
+# ---- training-side wrappers (fp32) --------------------------------------------------------------------------------
+def colsum(x: torch.Tensor, y: Optional[torch.Tensor] = None, mode: int = 0) -> torch.Tensor:
+    """Deterministic column reduction of a dense [rows, cols] view: sum x (0), sum x^2 (1), sum x*y (2)."""
+    rows, cols = x.shape
+    assert x.is_contiguous() and (y is None or (y.is_contiguous() and y.shape == x.shape))
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    ws = torch.empty(max(1, lib.segnn_colsum_workspace(rows, cols) // 4), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.segnn_colsum(_p(x), _p(y), rows, cols, mode, _p(ws), _p(out), _stream()), "segnn_colsum")
+    _bump(2)
+    return out
+
+
+def lincomb(dy, x, A, B=None, C=None):
+    """out[r][c] = A[c]*dy[r][c] + B[c]*x[r][c] + C[c] on dense [rows, cols] views."""
+    rows, cols = dy.shape
+    assert dy.is_contiguous() and A.numel() == cols
+    out = torch.empty_like(dy)
+    with torch.cuda.device(dy.device):
+        check(lib.segnn_lincomb(_p(dy), _p(x), _p(A), _p(B), _p(C), rows, cols, _p(out), _stream()), "segnn_lincomb")
+    _bump()
+    return out
+
+
+def add3(a, b, c=None):
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        check(lib.segnn_add3(_p(a), _p(b), _p(c), a.numel(), _p(out), _stream()), "segnn_add3")
+    _bump()
+    return out
+
+
+def tp_combine_bwd(y, node_attr, n: int, gate: bool, bias, dout):
+    nodes = y.shape[0]
+    n0 = 2 * n if gate else n
+    dy = torch.empty((nodes, 4, n0 + n), dtype=torch.float32, device=y.device)
+    dz0 = torch.empty((nodes, n0), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        check(lib.segnn_tp_combine_bwd(_p(y), _p(node_attr), nodes, n, int(gate), _p(bias), _p(dout.contiguous()),
+                                       _p(dy), _p(dz0), _stream()), "segnn_tp_combine_bwd")
+    _bump()
+    return dy, dz0
+
+
+def node_gemm_wgrad(x0, x1, dy0, dy1, split: int):
+    """dw_s, dw_v [K][n_out] of node_gemm(x0 | x1) -> (dy0 | dy1)."""
+    nodes, _, n_in = x0.shape
+    K = n_in * (2 if x1 is not None else 1)
+    n_out = dy0.shape[2] + (dy1.shape[2] if dy1 is not None else 0)
+    dev = x0.device
+    dw_s = torch.empty((K, n_out), dtype=torch.float32, device=dev)
+    dw_v = torch.empty((K, n_out), dtype=torch.float32, device=dev)
+    ws = torch.empty(max(1, lib.segnn_node_gemm_wgrad_workspace(nodes, K, n_out) // 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.segnn_node_gemm_wgrad(_p(x0), _p(x1), _p(dy0), _p(dy1), split, nodes, n_in, n_out, _p(ws),
+                                        _p(dw_s), _p(dw_v), _stream()), "segnn_node_gemm_wgrad")
+    _bump(4)
+    return dw_s, dw_v
+
+
+def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg):
+    """Backward of the fused edge layer with recompute. Returns dP, dQ [nodes,4,3n], the message_layer_2 gradient
+    blocks {ss, vs, sv, vv, b} and dw_edge1 [6n]."""
+    nodes = batch_size * num_nodes
+    dev = pos.device
+    f = dict(dtype=torch.float32, device=dev)
+    dP, dQ = torch.empty((nodes, 4, 3 * n), **f), torch.empty((nodes, 4, 3 * n), **f)
+    g = dict(ss=torch.zeros((n, 2 * n), **f), vs=torch.zeros((n, 2 * n), **f), sv=torch.zeros((n, n), **f),
+             vv=torch.zeros((n, n), **f), b=torch.zeros((2 * n,), **f))
+    dwe_partial = torch.empty((nodes, 6 * n), **f)
+    w2t = {k: w2[k].t().contiguous() for k in ("ss", "vs", "sv", "vv")}
+    with torch.cuda.device(dev):
+        for pas, dout in ((0, dP), (1, dQ)):
+            check(lib.segnn_edge_layer_bwd(pas, _p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1),
+                                           _p(w2["ss"]), _p(w2["vs"]), _p(w2["sv"]), _p(w2["vv"]), _p(w2["b"]),
+                                           _p(w2t["ss"]), _p(w2t["vs"]), _p(w2t["sv"]), _p(w2t["vv"]), _p(bn_a),
+                                           _p(bn_b), _p(bn_c), _p(dagg.contiguous()), _p(dout), _p(g["ss"]),
+                                           _p(g["vs"]), _p(g["sv"]), _p(g["vv"]), _p(g["b"]), _p(dwe_partial),
+                                           _stream()), "segnn_edge_layer_bwd")
+            _bump()
+    return dP, dQ, g, colsum(dwe_partial)
+
+
+def embed_bwd(x_in, node_attr, dh, n: int):
+    nodes = x_in.shape[0]
+    contrib = torch.empty((nodes, 7 * n), dtype=torch.float32, device=x_in.device)
+    with torch.cuda.device(x_in.device):
+        check(lib.segnn_embed_bwd(_p(x_in), _p(node_attr), _p(dh.contiguous()), nodes, n, _p(contrib), _stream()),
+              "segnn_embed_bwd")
+    _bump()
+    s = colsum(contrib)
+    return s[: 6 * n].view(6, n), s[6 * n:]
+
+
+def head_bwd(h, node_attr, w_head, dpred, n: int):
+    """dh [nodes,4,n] and dw_head [2][n][2]."""
+    nodes = h.shape[0]
+    dh = torch.empty((nodes, 4, n), dtype=torch.float32, device=h.device)
+    contrib = torch.empty((nodes, 4 * n), dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        check(lib.segnn_head_bwd(_p(h), _p(node_attr), _p(w_head), _p(dpred), nodes, n, _p(dh), _p(contrib), _stream()),
+              "segnn_head_bwd")
+    _bump()
+    s = colsum(contrib).view(2, 2, n)  # (ws0, ws1), (wv0, wv1)
+    return dh, s.permute(0, 2, 1).contiguous()

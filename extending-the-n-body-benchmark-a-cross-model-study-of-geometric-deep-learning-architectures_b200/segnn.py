@@ -7,7 +7,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-from . import ops, packing
+from . import ops, packing, training
 from .graph import infer_graph_shape
 from .irreps import Irreps, weight_balanced_irreps
 from .o3_building_blocks import BatchNorm, O3TensorProduct, O3TensorProductSwishGate
@@ -177,10 +177,10 @@ class SEGNN(nn.Module):
     def forward_state(self, pos, vel, mass, batch_size: int, num_nodes: int, x_in=None, node_attr=None,
                       return_layers: bool = False):
         """pos, vel [nodes,3] fp32 CUDA, mass [nodes] -> pred [nodes,6] fp32 (eval-mode BatchNorm)."""
-        if self.training and self.norm == "batch":
-            raise NotImplementedError("train-mode BatchNorm forward is not built yet; call model.eval()")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("backward kernels are not built yet; wrap inference in torch.no_grad()")
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        bn_training = self.training and self.norm == "batch"
+        if needs_grad or bn_training:
+            return self._forward_train(pos, vel, mass, batch_size, num_nodes, bn_training, needs_grad, return_layers)
         w = self.packed(num_nodes - 1)
         mode = _MODES[self.compute_mode]
         n = self.n
@@ -200,6 +200,51 @@ class SEGNN(nn.Module):
         pred = ops.head(hp, node_attr, w["head"], n)
         if return_layers:
             return pred, per_layer
+        return pred
+
+    # -- training path: train-mode BatchNorm + hand-written backward (fp32 kernels) -----------------------------
+    def packed_train(self, dtype=torch.float32):
+        """Differentiable re-layout of the parameters into kernel operand blocks (no caching: the parameters
+        change every optimizer step) + the BatchNorm buffers that ride along outside autograd."""
+        n = self.n
+        f = lambda t: t.to(dtype)
+        layers, bufs = [], []
+        for layer in self.layers:
+            lw = dict(
+                msg1=packing.pack_msg1(f(layer.message_layer_1.tp.weight), f(layer.message_layer_1.biases), n),
+                msg2=packing.pack_msg2(f(layer.message_layer_2.tp.weight), f(layer.message_layer_2.biases), n),
+                upd1=packing.pack_node_tp(f(layer.update_layer_1.tp.weight), f(layer.update_layer_1.biases), 2, n, 2 * n),
+                upd2=packing.pack_node_tp(f(layer.update_layer_2.tp.weight), f(layer.update_layer_2.biases), 1, n, n),
+                bn_msg=None, bn_feat=None)
+            lb = dict(bn_msg=None, bn_feat=None)
+            for key, bn in (("bn_msg", layer.message_norm), ("bn_feat", layer.feature_norm)):
+                if bn is not None:
+                    lw[key] = dict(weight=f(bn.weight), bias=f(bn.bias))
+                    lb[key] = dict(running_mean=bn.running_mean, running_var=bn.running_var, eps=bn.eps,
+                                   momentum=bn.momentum)
+            layers.append(lw)
+            bufs.append(lb)
+        tree = dict(embed=packing.pack_embedding(f(self.embedding_layer.tp.weight), f(self.embedding_layer.biases), n),
+                    layers=layers,
+                    pool1=packing.pack_node_tp(f(self.pre_pool1.tp.weight), f(self.pre_pool1.biases), 1, n, 2 * n),
+                    head=packing.pack_head(f(self.pre_pool2.tp.weight), n))
+        return tree, bufs
+
+    def _forward_train(self, pos, vel, mass, batch_size, num_nodes, bn_training, needs_grad, return_layers=False,
+                       backend=None, dtype=torch.float32):
+        tree, bufs = self.packed_train(dtype)
+        leaves, spec = training.flatten_packed(tree)
+        cfg = dict(spec=spec, bn_buffers=bufs, n=self.n, B=batch_size, N=num_nodes, bn_training=bn_training,
+                   backend=backend)
+        if needs_grad and not return_layers:
+            return training.SegnnTrainFunction.apply(cfg, pos, vel, mass, *leaves)
+        with torch.no_grad():
+            W = training.unflatten_packed([t.detach() for t in leaves], spec)
+            training.attach_bn_buffers(W, bufs)
+            pred, saved = training.forward_train(W, self.n, pos, vel, mass, batch_size, num_nodes, bn_training,
+                                                 backend=backend)
+        if return_layers:
+            return pred, [rec["h"] for rec in saved["layers"]] + [saved["h_last"]]
         return pred
 
     def forward(self, graph, return_layers: bool = False):

@@ -1,0 +1,304 @@
+"""Forward with train-mode BatchNorm and the hand-written backward of the SEGNN kernel sequence
+(trainer.py:233-358 `train_one_step`: forward -> loss -> backward; models/segnn/segnn.py:150-304).
+
+Nothing per-edge is saved by the forward: the edge-layer backward (K3^T) recomputes the messages from the saved
+node-level projections. Per layer the saved tensors are all [nodes, .]: the layer input, the hoisted projections
+P/Q, the raw aggregate (sum over senders of the un-normalised messages), the two node GEMM outputs and the
+pre-BatchNorm features.
+
+e3nn BatchNorm (segnn.py:233-235) in train mode is an affine map given its batch statistics; for the message
+BatchNorm those statistics are sums over all E edges, which the edge kernel delivers as per-receiver partial sums
+(sum_j m, sum_j m^2) reduced here by a deterministic column sum. With G_i = dL/d agg_i, the gradient that reaches
+every message of receiver i is dm_ij = A * G_i + B * m_ij + C with per-channel A, B, C computed from node-level
+reductions (sum_i G_i, sum_i G_i * agg_raw_i): see `_bn_backward_coeffs`.
+
+`backend` is the kernel namespace (``ops``: the C ABI). Tests substitute a torch emulation to check this
+orchestration and the BatchNorm algebra on CPU; the product path always uses ``ops``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops as _ops
+
+__all__ = ["forward_train", "backward_train", "SegnnTrainFunction", "flatten_packed", "unflatten_packed",
+           "attach_bn_buffers"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# packed-weight tree <-> flat tuple (autograd.Function inputs must be a flat list of tensors)
+# ---------------------------------------------------------------------------------------------------------------
+def flatten_packed(tree):
+    """Deterministic depth-first flattening (dict keys sorted). Returns (leaves, spec)."""
+    leaves: List[torch.Tensor] = []
+
+    def rec(node):
+        if isinstance(node, dict):
+            return {"d": [(k, rec(node[k])) for k in sorted(node.keys())]}
+        if isinstance(node, (list, tuple)):
+            return {"l": [rec(v) for v in node]}
+        if node is None:
+            return {"n": None}
+        leaves.append(node)
+        return {"t": len(leaves) - 1}
+
+    spec = rec(tree)
+    return leaves, spec
+
+
+def unflatten_packed(leaves, spec):
+    if "d" in spec:
+        return {k: unflatten_packed(leaves, s) for k, s in spec["d"]}
+    if "l" in spec:
+        return [unflatten_packed(leaves, s) for s in spec["l"]]
+    if "n" in spec:
+        return None
+    return leaves[spec["t"]]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BatchNorm helpers (per-channel vectors of length n; tiny, kept in torch on the device)
+# ---------------------------------------------------------------------------------------------------------------
+def _planar_cols(s, v):
+    """per-channel scalar-plane and vector-plane coefficients -> one value per planar column [4n]."""
+    return torch.cat([s, v, v, v]).contiguous()
+
+
+def _bn_forward_coeffs(bn, n, rows, deg, sum_x, sumsq_s, sumsq_v, training):
+    """Statistics + folded affine of one e3nn BatchNorm over `rows` rows (rows = E for messages, nodes for
+    features). sum_x [n]: sum of the scalar channel over rows; sumsq_s [n]: sum of squares; sumsq_v [n]: sum of
+    |v|^2. Returns dict(mean, rs_s, rs_v, mul_s, mul_v, add) where out_s = mul_s * x + add / deg (per row)."""
+    w_s, w_v = bn["weight"][:n], bn["weight"][n:]
+    if training:
+        mean = sum_x / rows
+        var_s = (sumsq_s / rows - mean * mean).clamp_min(0.0)
+        var_v = sumsq_v / (3.0 * rows)
+    else:
+        f = lambda b: b.to(w_s.dtype)
+        mean, var_s, var_v = f(bn["running_mean"]), f(bn["running_var"][:n]), f(bn["running_var"][n:])
+    rs_s = (var_s + bn["eps"]).rsqrt()
+    rs_v = (var_v + bn["eps"]).rsqrt()
+    mul_s, mul_v = w_s * rs_s, w_v * rs_v
+    add = deg * (bn["bias"] - mean * mul_s)
+    return dict(mean=mean, var_s=var_s, var_v=var_v, rs_s=rs_s, rs_v=rs_v, mul_s=mul_s, mul_v=mul_v, add=add)
+
+
+def _bn_backward_coeffs(bn, st, n, rows, deg, sum_g, sum_gx, training):
+    """sum_g [4n] = sum_i G_i, sum_gx [4n] = sum_i G_i * x_i (planar columns; x_i = raw aggregate or pre-norm
+    feature). Returns A_s, A_v, B_s, B_v, C_s and the parameter gradients (dweight [2n], dbias [n])."""
+    w_s, w_v = bn["weight"][:n], bn["weight"][n:]
+    sg_s = deg * sum_g[:n]                                   # sum over rows of dL/dy (scalars)
+    sgx_s = sum_gx[:n]                                       # sum over rows of dL/dy * x
+    sgx_v = sum_gx[n:2 * n] + sum_gx[2 * n:3 * n] + sum_gx[3 * n:]
+    mean, rs_s, rs_v = st["mean"], st["rs_s"], st["rs_v"]
+    dgamma_s = rs_s * (sgx_s - mean * sg_s)
+    dgamma_v = rs_v * sgx_v
+    dbeta = sg_s
+    A_s, A_v = w_s * rs_s, w_v * rs_v
+    if training:
+        c1 = sg_s / rows
+        c2 = dgamma_s / rows                                 # mean over rows of dL/dy * x_hat
+        B_s = -w_s * rs_s * rs_s * c2
+        C_s = -w_s * rs_s * c1 - B_s * mean
+        B_v = -w_v * rs_v * rs_v * rs_v * sgx_v / (3.0 * rows)
+    else:
+        B_s, C_s, B_v = torch.zeros_like(A_s), torch.zeros_like(A_s), torch.zeros_like(A_v)
+    return A_s, A_v, B_s, B_v, C_s, torch.cat([dgamma_s, dgamma_v]), dbeta
+
+
+def _update_running(bn, st):
+    mom = bn["momentum"]
+    bn["running_mean"].mul_(1 - mom).add_(mom * st["mean"])
+    bn["running_var"].mul_(1 - mom).add_(mom * torch.cat([st["var_s"], st["var_v"]]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# forward (fp32 kernels), saving node-level tensors only
+# ---------------------------------------------------------------------------------------------------------------
+def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: bool, backend=None,
+                  update_running_stats: bool = True):
+    """W: packed weights (see SEGNN.packed_train). Returns (pred [nodes,6], saved)."""
+    be = backend or _ops
+    nodes, deg = B * N, N - 1
+    E = nodes * deg
+    x_in, attr = be.prep(pos, vel, B, N)
+    h = be.embed(x_in, attr, W["embed"]["w"], W["embed"]["bias"], n)
+    saved = dict(x_in=x_in, attr=attr, layers=[], n=n, B=B, N=N, pos=pos, mass=mass, bn_training=bn_training)
+    for lw in W["layers"]:
+        m1, m2, u1, u2 = lw["msg1"], lw["msg2"], lw["upd1"], lw["upd2"]
+        p, q = be.node_gemm(h, None, m1, 6 * n, bias=m1["bias"], n_bias=2 * n, split=3 * n)
+        agg_raw, mom = be.edge_layer(be.MODE_FP32, pos, mass, B, N, n, p, q, m1["w_edge"], m2, None, None,
+                                     want_moments=True)
+        rec = dict(h=h, p=p, q=q, agg_raw=agg_raw)
+        if lw["bn_msg"] is not None:
+            sums = be.colsum(agg_raw.view(nodes, 4 * n))
+            sq = be.colsum(mom)
+            st = _bn_forward_coeffs(lw["bn_msg"], n, float(E), float(deg), sums[:n], sq[:n], sq[n:], bn_training)
+            agg = be.lincomb(agg_raw.view(nodes, 4 * n), None, _planar_cols(st["mul_s"], st["mul_v"]), None,
+                             _planar_cols(st["add"], torch.zeros_like(st["add"]))).view(nodes, 4, n)
+            if bn_training and update_running_stats:
+                _update_running(lw["bn_msg"], st)
+            rec["bn_msg"] = st
+        else:
+            agg = agg_raw
+        y1 = be.node_gemm(h, agg, u1, 3 * n)
+        g1 = be.tp_combine(y1, attr, n, True, bias=u1["bias"])
+        y2 = be.node_gemm(g1, None, u2, 2 * n)
+        pre = be.tp_combine(y2, attr, n, False, bias=u2["bias"], residual=h)
+        rec.update(agg=agg, y1=y1, g1=g1, y2=y2, pre=pre)
+        if lw["bn_feat"] is not None:
+            flat = pre.view(nodes, 4 * n)
+            sums = be.colsum(flat)
+            sq = be.colsum(flat, None, 1)
+            st = _bn_forward_coeffs(lw["bn_feat"], n, float(nodes), 1.0, sums[:n], sq[:n],
+                                    sq[n:2 * n] + sq[2 * n:3 * n] + sq[3 * n:], bn_training)
+            h = be.lincomb(flat, None, _planar_cols(st["mul_s"], st["mul_v"]), None,
+                           _planar_cols(st["add"], torch.zeros_like(st["add"]))).view(nodes, 4, n)
+            if bn_training and update_running_stats:
+                _update_running(lw["bn_feat"], st)
+            rec["bn_feat"] = st
+        else:
+            h = pre
+        saved["layers"].append(rec)
+    p1 = W["pool1"]
+    yp = be.node_gemm(h, None, p1, 3 * n)
+    hp = be.tp_combine(yp, attr, n, True, bias=p1["bias"])
+    pred = be.head(hp, attr, W["head"], n)
+    saved.update(h_last=h, yp=yp, hp=hp)
+    return pred, saved
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------------------------------
+def _transposed(w):
+    return dict(w_s=w["w_s"].t().contiguous(), w_v=w["w_v"].t().contiguous())
+
+
+def _node_tp_backward(be, w, x0, x1, y, attr, n, gate, dout, split_out: Optional[int] = None):
+    """Backward of node_gemm(x0|x1; w) -> tp_combine(gate, bias). Returns (dx (tensor or pair), grads dict)."""
+    nodes = y.shape[0]
+    n0 = 2 * n if gate else n
+    dy, dz0 = be.tp_combine_bwd(y, attr, n, gate, w["bias"], dout)
+    dbias = be.colsum(dz0.view(nodes, n0))
+    dw_s, dw_v = be.node_gemm_wgrad(x0, x1, dy, None, 0)
+    k = w["w_s"].shape[0]
+    dx = be.node_gemm(dy, None, _transposed(w), k, split=split_out or 0)
+    return dx, dict(w_s=dw_s, w_v=dw_v, bias=dbias)
+
+
+def backward_train(W: Dict, saved: Dict, dpred, backend=None):
+    """Returns the gradient tree matching W (None where a leaf has no gradient, e.g. BatchNorm buffers)."""
+    be = backend or _ops
+    n, B, N = saved["n"], saved["B"], saved["N"]
+    nodes, deg = B * N, N - 1
+    E = nodes * deg
+    attr, pos, mass = saved["attr"], saved["pos"], saved["mass"]
+    bn_training = saved["bn_training"]
+    grads = dict(layers=[])
+    # head + pre_pool1
+    dhp, dw_head = be.head_bwd(saved["hp"], attr, W["head"], dpred.contiguous(), n)
+    grads["head"] = dw_head
+    dh, grads["pool1"] = _node_tp_backward(be, W["pool1"], saved["h_last"], None, saved["yp"], attr, n, True, dhp)
+    for lw, rec in zip(reversed(W["layers"]), reversed(saved["layers"])):
+        g = dict(bn_msg=None, bn_feat=None)
+        m1, m2, u1, u2 = lw["msg1"], lw["msg2"], lw["upd1"], lw["upd2"]
+        # feature BatchNorm
+        if lw["bn_feat"] is not None:
+            flat_pre, flat_dh = rec["pre"].view(nodes, 4 * n), dh.view(nodes, 4 * n)
+            sum_g = be.colsum(flat_dh)
+            sum_gx = be.colsum(flat_dh, flat_pre, 2)
+            A_s, A_v, B_s, B_v, C_s, dweight, dbias = _bn_backward_coeffs(lw["bn_feat"], rec["bn_feat"], n,
+                                                                          float(nodes), 1.0, sum_g, sum_gx, bn_training)
+            dpre = be.lincomb(flat_dh, flat_pre, _planar_cols(A_s, A_v), _planar_cols(B_s, B_v),
+                              _planar_cols(C_s, torch.zeros_like(C_s))).view(nodes, 4, n)
+            g["bn_feat"] = dict(weight=dweight, bias=dbias)
+        else:
+            dpre = dh
+        # update_layer_2 (+ residual), update_layer_1
+        dg1, g["upd2"] = _node_tp_backward(be, u2, rec["g1"], None, rec["y2"], attr, n, False, dpre)
+        (dh_u, dagg), g["upd1"] = _node_tp_backward(be, u1, rec["h"], rec["agg"], rec["y1"], attr, n, True, dg1,
+                                                    split_out=n)
+        # message BatchNorm folded through the sum over senders
+        if lw["bn_msg"] is not None:
+            flat_g, flat_raw = dagg.view(nodes, 4 * n), rec["agg_raw"].view(nodes, 4 * n)
+            sum_g = be.colsum(flat_g)
+            sum_gx = be.colsum(flat_g, flat_raw, 2)
+            A_s, A_v, B_s, B_v, C_s, dweight, dbias = _bn_backward_coeffs(lw["bn_msg"], rec["bn_msg"], n, float(E),
+                                                                          float(deg), sum_g, sum_gx, bn_training)
+            g["bn_msg"] = dict(weight=dweight, bias=dbias)
+        else:
+            A_s = torch.ones(n, dtype=dagg.dtype, device=dagg.device)
+            A_v, B_s, B_v, C_s = A_s.clone(), torch.zeros_like(A_s), torch.zeros_like(A_s), torch.zeros_like(A_s)
+        # fused edge layer backward (recompute) -> dP, dQ, message_layer_2 and w_edge gradients
+        dP, dQ, g["msg2"], dwe = be.edge_layer_bwd(pos, mass, B, N, n, rec["p"], rec["q"], m1["w_edge"], m2,
+                                                   torch.cat([A_s, A_v]).contiguous(),
+                                                   torch.cat([B_s, B_v]).contiguous(), C_s.contiguous(), dagg)
+        # message_layer_1 projections: [P | Q] = h @ W (+ bias on P's l=0 columns)
+        dw_s, dw_v = be.node_gemm_wgrad(rec["h"], None, dP, dQ, 3 * n)
+        dbias1 = be.colsum(dP.view(nodes, 12 * n))[:2 * n]
+        dh_m = be.node_gemm(dP, dQ, _transposed(m1), n)
+        g["msg1"] = dict(w_s=dw_s, w_v=dw_v, bias=dbias1.contiguous(), w_edge=dwe)
+        dh = be.add3(dpre, dh_u, dh_m)
+        grads["layers"].append(g)
+    grads["layers"].reverse()
+    dw_e, db_e = be.embed_bwd(saved["x_in"], attr, dh, n)
+    grads["embed"] = dict(w=dw_e, bias=db_e)
+    return grads
+
+
+def attach_bn_buffers(W, bufs):
+    """BatchNorm running statistics / eps / momentum ride next to the differentiable leaves."""
+    for lw, lb in zip(W["layers"], bufs):
+        for key in ("bn_msg", "bn_feat"):
+            if lw[key] is not None:
+                lw[key].update(lb[key])
+
+
+class SegnnTrainFunction(torch.autograd.Function):
+    """pred = SEGNN(pos, vel, mass; packed weights) with the hand-written backward. The packed weights are
+    differentiable torch re-layouts of the reference-named parameters (packing.py), so autograd carries the packed
+    gradients back to ``tp.weight`` / ``biases`` / BatchNorm ``weight`` / ``bias``."""
+
+    @staticmethod
+    def forward(ctx, cfg, pos, vel, mass, *leaves):
+        W = unflatten_packed([t.detach() for t in leaves], cfg["spec"])
+        attach_bn_buffers(W, cfg["bn_buffers"])
+        pred, saved = forward_train(W, cfg["n"], pos, vel, mass, cfg["B"], cfg["N"], cfg["bn_training"],
+                                    backend=cfg.get("backend"))
+        ctx.cfg, ctx.W, ctx.saved, ctx.n_leaves = cfg, W, saved, len(leaves)
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        grads = backward_train(ctx.W, ctx.saved, dpred, backend=ctx.cfg.get("backend"))
+        gl, gspec = flatten_packed(_align(grads, ctx.cfg["spec"]))
+        out = [None] * ctx.n_leaves
+        _scatter_leaves(gspec, ctx.cfg["spec"], gl, out)
+        ctx.saved = None
+        return (None, None, None, None, *out)
+
+
+def _align(grads, spec):
+    """Shape the gradient tree like the weight tree (missing entries -> None)."""
+    if "d" in spec:
+        return {k: _align(grads.get(k) if isinstance(grads, dict) else None, s) for k, s in spec["d"]}
+    if "l" in spec:
+        return [_align(grads[i] if grads is not None else None, s) for i, s in enumerate(spec["l"])]
+    return grads
+
+
+def _scatter_leaves(gspec, wspec, gleaves, out):
+    if "d" in wspec:
+        gd = dict(gspec["d"]) if "d" in gspec else {}
+        for k, s in wspec["d"]:
+            if k in gd:
+                _scatter_leaves(gd[k], s, gleaves, out)
+    elif "l" in wspec:
+        if "l" in gspec:
+            for gs, s in zip(gspec["l"], wspec["l"]):
+                _scatter_leaves(gs, s, gleaves, out)
+    elif "t" in wspec and "t" in gspec:
+        out[wspec["t"]] = gleaves[gspec["t"]]

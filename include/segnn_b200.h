@@ -168,6 +168,10 @@ int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mod
 int segnn_lincomb(const float* dy, const float* x, const float* A, const float* B, const float* C, int64_t rows,
                   int cols, float* out, segnn_stream_t stream);
 
+/* out = a + b + c elementwise (c may be NULL): sums the gradient streams meeting at a layer input (residual,
+ * update_layer_1 and message_layer_1 branches of models/segnn/segnn.py:249-304). */
+int segnn_add3(const float* a, const float* b, const float* c, int64_t count, float* out, segnn_stream_t stream);
+
 /* Backward of segnn_tp_combine without residual / BatchNorm: dout [nodes][4][n] -> dy [nodes][4][n0+n] and
  * dz0 [nodes][n0] (rows of the bias gradient; may be NULL). */
 int segnn_tp_combine_bwd(const float* y, const float* node_attr, int nodes, int n, int gate, const float* bias,

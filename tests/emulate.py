@@ -129,3 +129,128 @@ def model_forward(packed, n, pos, vel, mass, B, N, return_layers=False):
     hp = tp_combine(node_gemm(h, None, c(p1["w_s"]), c(p1["w_v"]), None, 0), attr, n, True, bias=c(p1["bias"]))
     pred = head(hp, attr, c(packed["head"]))
     return (pred, layers) if return_layers else pred
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Torch stand-in for the kernel namespace `ops` (test infrastructure): lets tests drive training.forward_train /
+# backward_train on CPU in float64. Backward "kernels" are autograd of the forward emulations above, so this checks
+# the orchestration and the BatchNorm algebra of training.py, not the CUDA kernels (those are checked on the GPU).
+# ----------------------------------------------------------------------------------------------------------------
+def edge_messages(pos, mass, B, N, n, p, q, w_edge, w2):
+    """Per-edge messages (ms [B,i,j,n], mv 3 x [B,i,j,n]) and the validity mask, as in edge_layer above."""
+    pp = pos.reshape(B, N, 3)
+    rel = pp[:, None, :, :] - pp[:, :, None, :]
+    dist = rel.norm(dim=-1, keepdim=True)
+    a1 = Y1 * rel / dist.clamp_min(1e-12)
+    m = mass.reshape(B, N)
+    mm = (m[:, :, None] * m[:, None, :]).unsqueeze(-1)
+    P, Q = p.reshape(B, N, 4, 3 * n), q.reshape(B, N, 4, 3 * n)
+    S = P[:, :, None] + Q[:, None, :]
+    wd0, wm0, wd1, wm1 = w_edge[:2 * n], w_edge[2 * n:4 * n], w_edge[4 * n:5 * n], w_edge[5 * n:]
+    z0 = S[..., 0, :2 * n] + sum(a1[..., k:k + 1] * S[..., 1 + k, :2 * n] for k in range(3)) + dist * wd0 + mm * wm0
+    t = S[..., 0, 2 * n:] + dist * wd1 + mm * wm1
+    zv = [a1[..., k:k + 1] * t + S[..., 1 + k, 2 * n:] for k in range(3)]
+    s1 = C_SILU * torch.nn.functional.silu(z0[..., :n])
+    g1 = C_SIG * torch.sigmoid(z0[..., n:])
+    v1 = [g1 * z for z in zv]
+    dot = sum(a1[..., k:k + 1] * v1[k] for k in range(3))
+    y0 = s1 @ w2["ss"] + dot @ w2["vs"] + w2["b"]
+    t1 = s1 @ w2["sv"]
+    dk = [v1[k] @ w2["vv"] for k in range(3)]
+    ms = C_SILU * torch.nn.functional.silu(y0[..., :n])
+    gt = C_SIG * torch.sigmoid(y0[..., n:])
+    mv = [gt * (a1[..., k:k + 1] * t1 + dk[k]) for k in range(3)]
+    mask = (~torch.eye(N, dtype=torch.bool))[None, :, :, None].to(pos.dtype)
+    return ms, mv, mask
+
+
+class TorchBackend:
+    MODE_FP32 = 0
+
+    prep = staticmethod(prep)
+    head = staticmethod(lambda h, attr, w_head, n: head(h, attr, w_head))
+    embed = staticmethod(lambda x, attr, w, bias, n: embed(x, attr, w, bias))
+
+    @staticmethod
+    def node_gemm(x0, x1, w, n_out, bias=None, n_bias=0, split=0, tc=False):
+        y = node_gemm(x0, x1, w["w_s"], w["w_v"], bias, n_bias)
+        return (y[..., :split].contiguous(), y[..., split:].contiguous()) if split else y
+
+    @staticmethod
+    def tp_combine(y, attr, n, gate, bias=None, residual=None, bn_mul=None, bn_add=None):
+        return tp_combine(y, attr, n, gate, bias, residual, bn_mul, bn_add)
+
+    @staticmethod
+    def edge_layer(mode, pos, mass, B, N, n, p, q, w_edge, w2, bn_mul=None, bn_add=None, want_moments=False):
+        ms, mv, mask = edge_messages(pos, mass, B, N, n, p, q, w_edge, w2)
+        agg = torch.stack([(ms * mask).sum(2)] + [(x * mask).sum(2) for x in mv], dim=2).reshape(B * N, 4, n)
+        mom = torch.cat([(ms * ms * mask).sum(2), (sum(x * x for x in mv) * mask).sum(2)], dim=-1).reshape(B * N, 2 * n)
+        assert bn_mul is None
+        return (agg, mom) if want_moments else agg
+
+    @staticmethod
+    def colsum(x, y=None, mode=0):
+        return (x if mode == 0 else (x * x if mode == 1 else x * y)).sum(0)
+
+    @staticmethod
+    def lincomb(dy, x, A, B=None, C=None):
+        out = A * dy
+        if x is not None:
+            out = out + B * x
+        if C is not None:
+            out = out + C
+        return out
+
+    @staticmethod
+    def add3(a, b, c=None):
+        return a + b + (c if c is not None else 0)
+
+    @staticmethod
+    def tp_combine_bwd(y, attr, n, gate, bias, dout):
+        n0 = 2 * n if gate else n
+        with torch.enable_grad():
+            yy = y.detach().clone().requires_grad_(True)
+            bb = bias.detach().expand(y.shape[0], n0).clone().requires_grad_(True)
+            out = tp_combine(yy, attr, n, gate, bias=bb)
+            dy, dz0 = torch.autograd.grad(out, [yy, bb], dout)
+        return dy, dz0
+
+    @staticmethod
+    def node_gemm_wgrad(x0, x1, dy0, dy1, split):
+        dy = dy0 if dy1 is None else torch.cat([dy0, dy1], dim=2)
+        x = x0 if x1 is None else torch.cat([x0, x1], dim=2)
+        dw_s = x[:, 0].t() @ dy[:, 0]
+        dw_v = sum(x[:, c].t() @ dy[:, c] for c in (1, 2, 3))
+        return dw_s, dw_v
+
+    @staticmethod
+    def edge_layer_bwd(pos, mass, B, N, n, p, q, w_edge, w2, bn_a, bn_b, bn_c, dagg):
+        with torch.enable_grad():
+            leaves = [t.detach().clone().requires_grad_(True) for t in
+                      (p, q, w_edge, w2["ss"], w2["vs"], w2["sv"], w2["vv"], w2["b"])]
+            pp, qq, we, ss, vs, sv, vv, b = leaves
+            ms, mv, mask = edge_messages(pos, mass, B, N, n, pp, qq, we, dict(ss=ss, vs=vs, sv=sv, vv=vv, b=b))
+            G = dagg.reshape(B, N, 1, 4, n)
+            dms = (bn_a[:n] * G[..., 0, :] + bn_b[:n] * ms + bn_c).detach() * mask
+            obj = (dms * ms).sum()
+            for k in range(3):
+                dmk = (bn_a[n:] * G[..., 1 + k, :] + bn_b[n:] * mv[k]).detach() * mask
+                obj = obj + (dmk * mv[k]).sum()
+            g = torch.autograd.grad(obj, leaves)
+        return g[0], g[1], dict(ss=g[3], vs=g[4], sv=g[5], vv=g[6], b=g[7]), g[2]
+
+    @staticmethod
+    def embed_bwd(x_in, attr, dh, n):
+        with torch.enable_grad():
+            w = torch.zeros(6, n, dtype=dh.dtype, requires_grad=True)
+            b = torch.zeros(n, dtype=dh.dtype, requires_grad=True)
+            gw, gb = torch.autograd.grad(embed(x_in, attr, w, b), [w, b], dh)
+        return gw, gb
+
+    @staticmethod
+    def head_bwd(h, attr, w_head, dpred, n):
+        with torch.enable_grad():
+            hh = h.detach().clone().requires_grad_(True)
+            ww = w_head.detach().clone().requires_grad_(True)
+            gh, gw = torch.autograd.grad(head(hh, attr, ww), [hh, ww], dpred)
+        return gh, gw

@@ -212,3 +212,63 @@ def test_equivariance_and_permutation_at_scale():
         out_p = m.forward_state(p[perm].contiguous(), v[perm].contiguous(), ms[perm].contiguous(), B, N)
         out = m.forward_state(p, v, ms, B, N)
         assert float((out_p - out[perm]).abs().max() / out.abs().max()) < 2e-4
+
+
+# ---- training: train-mode BatchNorm forward + hand-written backward vs autograd through the oracle ----------------
+def _grad_case(H, L, B, N, bn_train, seed=0):
+    torch.manual_seed(seed)
+    om = O.SEGNN(hidden_features=H, num_layers=L)
+    O.perturb_bn_buffers(om, seed=seed + 1)
+    om.train(bn_train)
+    m = S.SEGNN(hidden_features=H, num_layers=L)
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().train(bn_train)
+    pos, vel, mass = O.synthetic_system(B, N, seed=seed + 2)
+    y = torch.randn(B * N, 6, dtype=torch.float64)
+    ref = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N))
+    loss_ref = O.target_common_loss(ref, y)
+    loss_ref.backward()
+    pred = m(gpu_graph(pos, vel, mass, B, N))
+    loss = O.target_common_loss(pred, y.float().cuda())
+    loss.backward()
+    return om, m, ref.detach(), pred.detach(), float(loss_ref), float(loss)
+
+
+@pytest.mark.parametrize("H,L,B,N,bn_train", [(64, 2, 4, 5, True), (64, 2, 4, 5, False), (192, 1, 2, 20, True),
+                                                (128, 2, 1, 33, True), (50, 1, 3, 6, True)])
+def test_training_gradients_match_oracle(H, L, B, N, bn_train):
+    """fp32 kernels vs float64 autograd: prediction 1e-5 (north_star fp32 tolerance); gradients 1e-4 of each
+    parameter's max-norm (they accumulate over all edges in fp32; message_layer_2's use fp32 atomics)."""
+    om, m, ref, pred, loss_ref, loss = _grad_case(H, L, B, N, bn_train)
+    assert rel(pred, ref) < 1e-5
+    assert abs(loss - loss_ref) < 1e-5 * abs(loss_ref)
+    worst = 0.0
+    for (k, a), (k2, b) in zip(om.named_parameters(), m.named_parameters()):
+        assert k == k2 and b.grad is not None, k
+        scale = float(a.grad.abs().max())
+        err = float((a.grad - b.grad.double().cpu()).abs().max())
+        if scale > 1e-9:
+            worst = max(worst, err / scale)
+        assert err <= 1e-4 * scale + 1e-9, f"{k}: {err} vs scale {scale}"
+    print(f"H={H} N={N} bn_train={bn_train}: worst gradient rel err {worst:.2e}")
+    sd = om.state_dict()
+    for k, b in m.state_dict().items():
+        if "running" in k:
+            assert float((sd[k] - b.double().cpu()).abs().max()) < 1e-5 * (1 + float(sd[k].abs().max())), k
+
+
+def test_train_mode_forward_without_grad_matches_oracle():
+    """trainer.py never calls model.eval() before its in-training rollout (SURVEY note 6): train-mode BatchNorm must
+    also work under no_grad, and must update the running statistics."""
+    torch.manual_seed(1)
+    om = O.SEGNN(hidden_features=64, num_layers=2).train()
+    m = S.SEGNN(hidden_features=64, num_layers=2)
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().train()
+    B, N = 5, 5
+    pos, vel, mass = O.synthetic_system(B, N, seed=4)
+    with torch.no_grad():
+        ref = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N))
+        out = m(gpu_graph(pos, vel, mass, B, N))
+    assert rel(out, ref) < 1e-5
+    assert rel(m.layers[0].message_norm.running_var, om.layers[0].message_norm.running_var) < 1e-5

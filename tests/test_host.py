@@ -138,3 +138,33 @@ def test_two_rank_gloo_sharding():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert owned == [1] * 11 and tmax == 2.0
+
+
+@pytest.mark.parametrize("bn_train", [True, False])
+def test_training_orchestration_and_batchnorm_algebra_vs_oracle(bn_train):
+    """training.forward_train/backward_train driven by the torch stand-in for the kernels (float64, CPU): predictions,
+    every parameter gradient and the BatchNorm running statistics must match autograd through the oracle."""
+    torch.manual_seed(0)
+    H, L, B, N = 16, 2, 3, 5
+    om = O.SEGNN(hidden_features=H, num_layers=L)
+    O.perturb_bn_buffers(om)
+    om.train(bn_train)
+    m = S.SEGNN(hidden_features=H, num_layers=L).double()
+    m.load_state_dict(om.state_dict())
+    m.train(bn_train)
+    pos, vel, mass = O.synthetic_system(B, N, seed=3)
+    y = torch.randn(B * N, 6, dtype=torch.float64)
+    ref = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N))
+    O.target_common_loss(ref, y).backward()
+    pred = m._forward_train(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1), B, N, bn_train, True,
+                            backend=E.TorchBackend, dtype=torch.float64)
+    O.target_common_loss(pred, y).backward()
+    assert float((pred.detach() - ref.detach()).abs().max() / ref.detach().abs().max()) < 1e-11
+    for (k, a), (k2, b) in zip(om.named_parameters(), m.named_parameters()):
+        assert k == k2 and b.grad is not None, k
+        scale = float(a.grad.abs().max())
+        assert float((a.grad - b.grad).abs().max()) <= 1e-8 * scale + 1e-14, k
+    sd = om.state_dict()
+    for k, b in m.state_dict().items():
+        if "running" in k:
+            assert float((sd[k] - b).abs().max()) < 1e-10, k

@@ -13,25 +13,27 @@ namespace segnn {
 constexpr int kColsumRowsPerBlock = 256;
 
 __global__ void colsum_stage1(const float* __restrict__ x, const float* __restrict__ y, int64_t rows, int cols,
-                              int mode, float* __restrict__ partial) {
+                              int mode, double* __restrict__ partial) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   const int64_t r0 = (int64_t)blockIdx.y * kColsumRowsPerBlock;
   const int64_t r1 = min(rows, r0 + kColsumRowsPerBlock);
-  float acc = 0.f;
+  // float64 accumulation: BatchNorm statistics feed var = E[x^2] - mean^2 and cancellation-prone gradient sums
+  double acc = 0.0;
   for (int64_t r = r0; r < r1; ++r) {
-    const float v = x[r * cols + c];
-    acc += mode == 0 ? v : (mode == 1 ? v * v : v * y[r * cols + c]);
+    const double v = (double)x[r * cols + c];
+    acc += mode == 0 ? v : (mode == 1 ? v * v : v * (double)y[r * cols + c]);
   }
   partial[(int64_t)blockIdx.y * cols + c] = acc;
 }
 
-__global__ void colsum_stage2(const float* __restrict__ partial, int nparts, int cols, float* __restrict__ out) {
+template <typename T>
+__global__ void colsum_stage2(const T* __restrict__ partial, int nparts, int cols, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  float acc = 0.f;
+  T acc = 0;
   for (int p = 0; p < nparts; ++p) acc += partial[(int64_t)p * cols + c];
-  out[c] = acc;
+  out[c] = (float)acc;
 }
 
 // out[r][c] = A[c] * dy[r][c] + B[c] * x[r][c] + C[c]   (x / B / C may be NULL)
@@ -270,7 +272,7 @@ extern "C" {
 
 int64_t segnn_colsum_workspace(int64_t rows, int cols) {
   const int64_t parts = (rows + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock;
-  return parts * cols * (int64_t)sizeof(float);
+  return parts * cols * (int64_t)sizeof(double);
 }
 
 int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mode, float* workspace, float* out,
@@ -285,8 +287,9 @@ int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mod
   const int64_t parts = (rows + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock;
   SEGNN_CHECK_ARG(parts <= 65535, "too many rows for one colsum call");
   dim3 grid((cols + 127) / 128, (unsigned)parts);
-  colsum_stage1<<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, rows, cols, mode, workspace);
-  colsum_stage2<<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, (int)parts, cols, out);
+  double* partial = reinterpret_cast<double*>(workspace);
+  colsum_stage1<<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, rows, cols, mode, partial);
+  colsum_stage2<double><<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, (int)parts, cols, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }
@@ -354,7 +357,7 @@ int segnn_node_gemm_wgrad(const float* x0, const float* x1, const float* dy0, co
     dim3 grid((K + kWgTile - 1) / kWgTile, (n_out + kWgTile - 1) / kWgTile, (unsigned)slabs);
     node_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, x1, dy0, dy1, split, nodes, n_in, n_out, cls, per,
                                                              workspace);
-    colsum_stage2<<<(K * n_out + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, (int)slabs, K * n_out,
+    colsum_stage2<float><<<(K * n_out + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, (int)slabs, K * n_out,
                                                                            cls == 0 ? dw_s : dw_v);
   }
   SEGNN_CHECK_LAUNCH();

@@ -194,7 +194,7 @@ def colsum(x: torch.Tensor, y: Optional[torch.Tensor] = None, mode: int = 0) -> 
     rows, cols = x.shape
     assert x.is_contiguous() and (y is None or (y.is_contiguous() and y.shape == x.shape))
     out = torch.empty(cols, dtype=torch.float32, device=x.device)
-    ws = torch.empty(max(1, lib.segnn_colsum_workspace(rows, cols) // 4), dtype=torch.float32, device=x.device)
+    ws = torch.empty(max(1, lib.segnn_colsum_workspace(rows, cols) // 8), dtype=torch.float64, device=x.device)
     with torch.cuda.device(x.device):
         check(lib.segnn_colsum(_p(x), _p(y), rows, cols, mode, _p(ws), _p(out), _stream()), "segnn_colsum")
     _bump(2)

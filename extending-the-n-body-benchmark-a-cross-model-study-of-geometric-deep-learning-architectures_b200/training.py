@@ -72,8 +72,9 @@ def _bn_forward_coeffs(bn, n, rows, deg, sum_x, sumsq_s, sumsq_v, training):
     |v|^2. Returns dict(mean, rs_s, rs_v, mul_s, mul_v, add) where out_s = mul_s * x + add / deg (per row)."""
     w_s, w_v = bn["weight"][:n], bn["weight"][n:]
     if training:
-        mean = sum_x / rows
-        var_s = (sumsq_s / rows - mean * mean).clamp_min(0.0)
+        mean64 = sum_x.double() / rows
+        var_s = (sumsq_s.double() / rows - mean64 * mean64).clamp_min(0.0).to(w_s.dtype)
+        mean = mean64.to(w_s.dtype)
         var_v = sumsq_v / (3.0 * rows)
     else:
         f = lambda b: b.to(w_s.dtype)

@@ -237,19 +237,23 @@ def _grad_case(H, L, B, N, bn_train, seed=0):
 @pytest.mark.parametrize("H,L,B,N,bn_train", [(64, 2, 4, 5, True), (64, 2, 4, 5, False), (192, 1, 2, 20, True),
                                                 (128, 2, 1, 33, True), (50, 1, 3, 6, True)])
 def test_training_gradients_match_oracle(H, L, B, N, bn_train):
-    """fp32 kernels vs float64 autograd: prediction 1e-5 (north_star fp32 tolerance); gradients 1e-4 of each
-    parameter's max-norm (they accumulate over all edges in fp32; message_layer_2's use fp32 atomics)."""
+    """fp32 kernels vs float64 autograd: prediction 1e-5 (north_star fp32 tolerance); gradients within 1e-4 of each
+    parameter's max-norm plus 1e-5 of the largest gradient in the model. The second term covers parameters that sit
+    upstream of a train-mode BatchNorm (message_layer_2 / update_layer_2 biases): their gradient is a sum over all
+    rows of terms that cancel almost exactly (the BatchNorm backward removes the mean), so its fp32 rounding error is
+    set by the size of the terms, not of the result."""
     om, m, ref, pred, loss_ref, loss = _grad_case(H, L, B, N, bn_train)
     assert rel(pred, ref) < 1e-5
     assert abs(loss - loss_ref) < 1e-5 * abs(loss_ref)
     worst = 0.0
+    top = max(float(a.grad.abs().max()) for a in om.parameters())
     for (k, a), (k2, b) in zip(om.named_parameters(), m.named_parameters()):
         assert k == k2 and b.grad is not None, k
         scale = float(a.grad.abs().max())
         err = float((a.grad - b.grad.double().cpu()).abs().max())
         if scale > 1e-9:
             worst = max(worst, err / scale)
-        assert err <= 1e-4 * scale + 1e-9, f"{k}: {err} vs scale {scale}"
+        assert err <= 1e-4 * scale + 1e-5 * top, f"{k}: {err} vs scale {scale} (top {top})"
     print(f"H={H} N={N} bn_train={bn_train}: worst gradient rel err {worst:.2e}")
     sd = om.state_dict()
     for k, b in m.state_dict().items():

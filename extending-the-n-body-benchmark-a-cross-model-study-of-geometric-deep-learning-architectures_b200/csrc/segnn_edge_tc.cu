@@ -4,23 +4,30 @@
 //   D_tile[128 lanes = channel w][32 cols = edges] += A_tile[128 x K] (message_layer_2 weights, resident in TMEM,
 //   tcgen05.mma "TS" form) x B[K x 32] (per-edge features: gate(message_layer_1) output, bf16 in shared memory,
 //   MN-major, 128B swizzle).
-// With channels on the lanes, the producer (thread = channel), the tensor core output and the epilogue (thread =
-// lane = channel) all agree on the mapping: node projections are read coalesced, the B tile is written with one
-// 8-byte store per plane and sender, the gate needs no cross-lane traffic and the sum over senders is a plain
-// in-register accumulation (no atomics, no shuffles).
-//
 // Six accumulator tiles per 32-edge tile: s (K = 2n: [s' | v'.a1]), g (same K), T1 = W_sv^T s' (K = n),
 // D_k = W_vv^T v'_k (K = n, k = x,y,z); message = (silu(s), sigmoid(g) * (a1_k * T1 + D_k)).
-// The six dependent-accumulate chains are interleaved because a tcgen05.mma that accumulates into the tile of
-// its predecessor waits ~67 clk (measured, profiles/r1_umma_probe.log).
 //
-// Warp roles (one CTA per SM, persistent over work items = (graph, block of 4 receivers)):
-//   4 producer groups (n threads each): group q owns senders 2q, 2q+1 of the 8-sender block and all 4 receivers;
-//   2 epilogue groups (128 threads each, lane quadrant = warp % 4): group e owns tile columns [16e, 16e+16);
-//   1 MMA warp (warp-uniform loop, one elected lane issues; it also owns the TMEM allocation and issues one
-//   cp.async.bulk per tile: the 8 consecutive sender rows of the Q projection, 36 KB at n = 96, double buffered;
-//   the copy for tile t+2 is issued when the producers have signalled tile t complete).
-// Tile column c = sender_local * 4 + receiver_local.
+// Work item = (graph, 4 receivers); tile = 4 receivers x 8 senders = 32 edge columns, column c = sender_local * 4 +
+// receiver_local.  One persistent CTA of 16 warps per SM:
+//   compute warps (warp % 4 < n / 32; warp % 4 = channel block = TMEM lane quadrant, warp / 4 = group g):
+//     every thread is one channel.  Group g owns columns [8g, 8g + 8) = senders (2g, 2g + 1) x 4 receivers of every
+//     tile, in BOTH roles, software-pipelined:   produce(t + 1)  ->  epilogue(t)  ->  produce(t + 2)  -> ...
+//       produce:  message_layer_1 combine (hoisted projections P_i + Q_j, geometry) + gate -> bf16 B tile (one
+//                 conflict-free 16-byte store per plane);
+//       epilogue: tcgen05.ld of the six accumulators, gate, in-register accumulation over senders (no atomics, no
+//                 shuffles: channels sit on lanes, so the sum over senders is a per-thread sum).
+//     Merging the two roles removes the spinning consumer warps of the previous design (12% of the issue slots)
+//     and the tensor pipe works on tile t + 1 while the CUDA cores run epilogue(t) / produce(t + 2).
+//     All fp32 math is packed (FFMA2 / FADD2 / FMUL2 over receiver pairs; scalar operands ride as broadcast
+//     operands), which halves the issue slots of the fp32 work; the gates use one MUFU.TANH each and their
+//     constants are folded: pre-activations are carried as z/2 (the 1/2 is folded into the weights), the gate
+//     outputs as z/2 * (1 + tanh(z/2)) and (1 + tanh(z/2)), and c_silu, c_sig/2 are folded into the
+//     message_layer_2 weight image / the final per-receiver scale.
+//   warp 3:  MMA issuer A (tiles s, g) + TMEM allocation + cp.async.bulk of the sender rows of Q (36 KB per tile at
+//            n = 96, double buffered, issued two tiles ahead);
+//   warp 7:  MMA issuer B (tiles T1, D_x, D_y, D_z)   [one warp sustains ~1 MMA / 24 clk, the pipe needs 1 / 16 clk];
+//   warp 11: geometry (lane = column): unit vectors, distances, mass products, validity of tile t + 1.. into a ring.
+// Synchronisation is mbarrier-only between roles; every wait is bounded and traps instead of hanging.
 #include <cuda_bf16.h>
 
 #include "segnn_common.cuh"
@@ -31,8 +38,8 @@ namespace tc {
 constexpr int kRecv = 4;      // receivers per work item
 constexpr int kSend = 8;      // senders per tile
 constexpr int kCols = 32;     // edges (columns) per tile
-constexpr int kGeoSlots = 8;  // geometry ring depth (tile t+1 is written while tile t computes)
-constexpr int kMaxNodesPerGraph = 2048;  // positions of one graph are staged in shared memory
+constexpr int kGeoSlots = 4;  // geometry ring depth
+constexpr int kWarps = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -45,6 +52,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded spin: a protocol bug must never hang the GPU. On timeout the flag is raised and the kernel traps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
   uint32_t done = 0;
+#pragma unroll 1
   for (int it = 0; it < (1 << 22); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -134,14 +142,26 @@ __device__ __forceinline__ float sig_gate_fast(float x) {
   return fmaf(0.5f * kCSig, t, 0.5f * kCSig);
 }
 
-// Warp layout (NW = n / 32): producers [0, 4 NW); epilogue group e at [4 NW + 4 e, 4 NW + 4 e + NW) so that
-// warp % 4 (the TMEM lane quadrant a warp may access) equals the channel block; the MMA warp sits in the unused
-// quadrant slot of epilogue group 0.
-template <int NMUL>
-constexpr int tc_num_warps() { return 4 * (NMUL / 32) + 4 + NMUL / 32; }
+
+#define SEGNN_TMEM_LD4(taddr, r)                                                          \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"               \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])                           \
+               : "r"(taddr))
+
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 tanh2(float2 x) { return make_float2(tanh_fast(x.x), tanh_fast(x.y)); }
+__device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float2 u2f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+
+struct TileCursor {
+  long long item;
+  int sb;
+  uint32_t t;
+};
 
 template <int NMUL>
-__global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
+__global__ void __launch_bounds__(kWarps * 32, 1)
     edge_layer_tc_kernel(const float* __restrict__ pos, const float* __restrict__ mass, int B, int N,
                          const float* __restrict__ pp, const float* __restrict__ qq,
                          const float* __restrict__ w_edge1,
@@ -149,53 +169,55 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
                          const float* __restrict__ bn_mul, const float* __restrict__ bn_add,
                          float* __restrict__ agg, int* __restrict__ err_flag) {
   constexpr int n = NMUL;
-  constexpr int NW = n / 32;            // warps per producer group
-  constexpr int kProdWarps = 4 * NW;
-  constexpr int kEpiWarp0 = kProdWarps;
-  static_assert(NW < 4, "the MMA warp sits in the unused quadrant slot of epilogue group 0");
-  constexpr int kMmaWarp = kEpiWarp0 + NW;
-  constexpr int kQStageBytes = kSend * 4 * 3 * n * (int)sizeof(float);
-  constexpr int kEpiThreads = 2 * NW * 32;
+  constexpr int NW = n / 32;            // channel blocks (compute warps per group)
+  static_assert(NW >= 1 && NW <= 3, "warp % 4 == 3 hosts the MMA / geometry warps");
+  constexpr int kComputeThreads = 4 * NW * 32;
+  constexpr int kComputeWarps = 4 * NW;
+  constexpr int kMmaWarpA = 3, kMmaWarpB = 7, kGeoWarp = 11;
+  constexpr int n3 = 3 * n;
+  constexpr int kQStageFloats = kSend * 4 * n3;
+  constexpr int kQStageBytes = kQStageFloats * (int)sizeof(float);
   constexpr int kWeightCols = 3 * n;    // TMEM columns of the weight image
   constexpr int kDBase = kWeightCols;   // accumulator tiles start here (6 x 32 columns)
-  constexpr int n3 = 3 * n;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
-  uint8_t* sB = smem;                                                  // 5n * 128 bytes
+  uint8_t* sB = smem;                                                  // 5n rows x 128 bytes (two 64-byte stages)
   float* sQ = reinterpret_cast<float*>(smem + 5 * n * 128);            // [2][8 senders][4 planes][3n]
-  float4* sPos = reinterpret_cast<float4*>(smem + 5 * n * 128 + 2 * kQStageBytes);  // [N] (x, y, z, mass)
-  float4* geoA = sPos + N;                                             // [slots][32] (ax, ay, az, valid)
-  float2* geoB = reinterpret_cast<float2*>(geoA + kGeoSlots * kCols);  // [slots][32] (dist, m_i m_j)
-  float* xch = reinterpret_cast<float*>(geoB + kGeoSlots * kCols);     // [4 recv][4 planes][n]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kRecv * 4 * n);
+  float* geo = sQ + 2 * kQStageFloats;                                 // [slots][6][32]: ax, ay, az, len, mm, valid
+  float* xch = geo + kGeoSlots * 6 * kCols;                            // [2][4 recv][4 src group][4 comp][n]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 16 * 4 * n);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 2;
-  uint64_t* dfull = bars + 4;
-  uint64_t* dempty = bars + 5;
-  uint64_t* qfull = bars + 6;   // [2] bulk copy landed (expect_tx)
-  uint64_t* gfull = bars + 10;  // [8] geometry ring: one barrier per slot, one arrival per producer group
+  uint64_t* full = bars;         // [2] B stage written (all compute threads)
+  uint64_t* empty = bars + 2;    // [2] B stage consumed (both MMA issuers commit)
+  uint64_t* dfull = bars + 4;    // accumulators complete (both issuers commit)
+  uint64_t* dempty = bars + 5;   // accumulators read out (all compute threads)
+  uint64_t* qfull = bars + 6;    // [2] bulk copy landed (expect_tx)
+  uint64_t* gfull = bars + 8;    // [kGeoSlots] geometry written
+  uint64_t* gempty = bars + 12;  // [kGeoSlots] geometry consumed (one arrival per compute warp)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const int cb = warp & 3, grp = warp >> 2;
+  const bool is_compute = cb < NW;
 
-  if (warp == kMmaWarp) {
+  if (warp == kMmaWarpA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    mbar_init(&full[0], 4 * n);
-    mbar_init(&full[1], 4 * n);
-    mbar_init(&empty[0], 1);
-    mbar_init(&empty[1], 1);
-    mbar_init(dfull, 1);
-    mbar_init(dempty, kEpiThreads);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], kComputeThreads);
+      mbar_init(&empty[i], 2);
       mbar_init(&qfull[i], 1);
     }
-    for (int i = 0; i < kGeoSlots; ++i) mbar_init(&gfull[i], 4);
+    mbar_init(dfull, 2);
+    mbar_init(dempty, kComputeThreads);
+    for (int i = 0; i < kGeoSlots; ++i) {
+      mbar_init(&gfull[i], 1);
+      mbar_init(&gempty[i], kComputeWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -204,9 +226,9 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
   const uint32_t tmem = *tmem_slot;
 
   // ---- message_layer_2 weights -> TMEM (lane = output channel, 2 bf16 of K per column) ------------------------
-  if (warp >= kEpiWarp0 && warp < kEpiWarp0 + NW) {  // lanes >= n are never read back
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  if (is_compute && grp == 0) {  // lanes >= n are never read back
+    const int row = cb * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(cb * 32) << 16;
     const uint32_t* src = w2_tc + (size_t)row * kWeightCols;
     for (int c = 0; c < kWeightCols; c += 8) {
       uint32_t r[8];
@@ -225,169 +247,262 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
   const int recv_blocks = (N + kRecv - 1) / kRecv;
   const int send_blocks = (N + kSend - 1) / kSend;
   const long long items = (long long)B * recv_blocks;
+  auto advance = [&](TileCursor& c) {
+    ++c.t;
+    if (++c.sb == send_blocks) {
+      c.sb = 0;
+      c.item += gridDim.x;
+    }
+  };
 
-  if (warp < kProdWarps) {
-    // ============================ producers: message_layer_1 (hoisted) + gate -> B tile ========================
-    const int q = warp / NW;                  // group = sender pair
-    const int w = (warp % NW) * 32 + lane;    // channel
-    const float wd0s = w_edge1[w], wd0g = w_edge1[n + w], wm0s = w_edge1[2 * n + w], wm0g = w_edge1[3 * n + w],
-                wd1 = w_edge1[4 * n + w], wm1 = w_edge1[5 * n + w];
-    // geometry of this group's 8 columns (2 senders x 4 receivers) of sender block sb, one thread per column
-    auto write_geometry = [&](int sb, int i0, int slot) {
-      if (w < 8) {
-        const int sl = 2 * q + (w >> 2), r = w & 3;
-        const int jj = sb * kSend + sl, ii = i0 + r;
-        const float4 ps = sPos[min(jj, N - 1)], pr = sPos[min(ii, N - 1)];
-        float ux, uy, uz, len;
-        unit_vec(ps.x - pr.x, ps.y - pr.y, ps.z - pr.z, ux, uy, uz, len);
-        const bool valid = (jj < N) && (ii < N) && (jj != ii);
-        const int c = sl * 4 + r;
-        geoA[slot * kCols + c] = make_float4(kY1 * ux, kY1 * uy, kY1 * uz, valid ? 1.0f : 0.0f);
-        geoB[slot * kCols + c] = make_float2(len, ps.w * pr.w);
-      }
-      named_barrier(1 + q, n);
-      if (w == 0) mbar_arrive(&gfull[slot]);  // publishes the group's 8 geometry entries to the epilogue
-    };
-    uint32_t t = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+  if (is_compute) {
+    // ============================ compute warps: produce(t + 1) / epilogue(t) ==================================
+    const int w = cb * 32 + lane;  // channel = B-tile row (producer role) = TMEM lane (epilogue role)
+    const uint32_t lane_base = (uint32_t)(cb * 32) << 16;
+    const float2 wd0s = bc2(0.5f * w_edge1[w]), wd0g = bc2(0.5f * w_edge1[n + w]), wm0s = bc2(0.5f * w_edge1[2 * n + w]),
+                 wm0g = bc2(0.5f * w_edge1[3 * n + w]), wd1 = bc2(w_edge1[4 * n + w]), wm1 = bc2(w_edge1[5 * n + w]);
+    const float2 b2s = bc2(0.5f * b2[w]), b2g = bc2(0.5f * b2[n + w]);
+    const float2 half2v = bc2(0.5f);
+    float sc_s = kCSilu, sc_v = 0.5f * kCSig, add_s = 0.f;
+    if (bn_mul != nullptr) {
+      sc_s *= bn_mul[w];
+      sc_v *= bn_mul[n + w];
+      add_s = bn_add[w];
+    }
+    // receiver-side projections, as receiver pairs: P[plane * 3 + part][pair]; parts (0s, 0g) carry the factor 1/2
+    float2 P[12][2];
+    float2 acc[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = make_float2(0.f, 0.f);
+
+    auto load_p = [&](long long item) {
       const long long g = item / recv_blocks;
       const int i0 = (int)(item - g * recv_blocks) * kRecv;
       const long long base = g * N;
-      // stage the graph's positions and masses (all producer groups together)
-      named_barrier(5, 4 * n);
-      for (int i = q * n + w; i < N; i += 4 * n) {
-        const long long node = base + i;
-        sPos[i] = make_float4(pos[node * 3 + 0], pos[node * 3 + 1], pos[node * 3 + 2], mass[node]);
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        const float* r0 = pp + (base + min(i0 + 2 * pr, N - 1)) * 4 * n3;
+        const float* r1 = pp + (base + min(i0 + 2 * pr + 1, N - 1)) * 4 * n3;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int part = 0; part < 3; ++part) {
+            const float sc = part < 2 ? 0.5f : 1.0f;
+            P[c * 3 + part][pr] = make_float2(sc * r0[c * n3 + part * n + w], sc * r1[c * n3 + part * n + w]);
+          }
       }
-      named_barrier(5, 4 * n);
-      // receiver-side projections of the 4 receivers (clamped: invalid receivers are masked by the epilogue)
-      float p0s[kRecv], p0g[kRecv], p1[kRecv], p0sk[kRecv][3], p0gk[kRecv][3], p1k[kRecv][3];
+    };
+
+    auto produce = [&](const TileCursor& cur) {
+      const uint32_t t = cur.t;
+      const int st = t & 1, slot = t & (kGeoSlots - 1);
+      const int nvalid = min(kSend, N - cur.sb * kSend);
+      mbar_wait(&gfull[slot], (t / kGeoSlots) & 1, err_flag);
+      mbar_wait(&empty[st], ((t >> 1) & 1) ^ 1, err_flag);
+      mbar_wait(&qfull[st], (t >> 1) & 1, err_flag);
+      const float* qs = sQ + st * kQStageFloats;
+      const float* gs = geo + slot * 6 * kCols;
+      uint32_t packed[2][5][2];
 #pragma unroll
-      for (int r = 0; r < kRecv; ++r) {
-        const long long node = base + min(i0 + r, N - 1);
-        const float* pr = pp + node * 4 * n3;
-        p0s[r] = pr[w];
-        p0g[r] = pr[n + w];
-        p1[r] = pr[2 * n + w];
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int sl = 2 * grp + s2;
+        const float* qr = qs + min(sl, nvalid - 1) * 4 * n3;  // senders past the graph end reuse a valid row
+        float q[12];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float* prk = pr + (1 + k) * n3;
-          p0sk[r][k] = prk[w];
-          p0gk[r][k] = prk[n + w];
-          p1k[r][k] = prk[2 * n + w];
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int part = 0; part < 3; ++part) q[c * 3 + part] = qr[c * n3 + part * n + w];
+        const float4 AX = *reinterpret_cast<const float4*>(gs + 0 * kCols + sl * 4);
+        const float4 AY = *reinterpret_cast<const float4*>(gs + 1 * kCols + sl * 4);
+        const float4 AZ = *reinterpret_cast<const float4*>(gs + 2 * kCols + sl * 4);
+        const float4 LE = *reinterpret_cast<const float4*>(gs + 3 * kCols + sl * 4);
+        const float4 MM = *reinterpret_cast<const float4*>(gs + 4 * kCols + sl * 4);
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const float2 ax = pr ? hi2(AX) : lo2(AX), ay = pr ? hi2(AY) : lo2(AY), az = pr ? hi2(AZ) : lo2(AZ);
+          const float2 le = pr ? hi2(LE) : lo2(LE), mm = pr ? hi2(MM) : lo2(MM);
+          // half pre-activations of the scalar / gate channels: (P0 + Q0)/2 + a.(P0k + Q0k)/2 + |r| wd/2 + m_i m_j wm/2
+          float2 hs = __ffma2_rn(bc2(q[0]), half2v, P[0][pr]);
+          float2 hg = __ffma2_rn(bc2(q[1]), half2v, P[1][pr]);
+          hs = __ffma2_rn(ax, __ffma2_rn(bc2(q[3]), half2v, P[3][pr]), hs);
+          hg = __ffma2_rn(ax, __ffma2_rn(bc2(q[4]), half2v, P[4][pr]), hg);
+          hs = __ffma2_rn(ay, __ffma2_rn(bc2(q[6]), half2v, P[6][pr]), hs);
+          hg = __ffma2_rn(ay, __ffma2_rn(bc2(q[7]), half2v, P[7][pr]), hg);
+          hs = __ffma2_rn(az, __ffma2_rn(bc2(q[9]), half2v, P[9][pr]), hs);
+          hg = __ffma2_rn(az, __ffma2_rn(bc2(q[10]), half2v, P[10][pr]), hg);
+          hs = __ffma2_rn(le, wd0s, hs);
+          hg = __ffma2_rn(le, wd0g, hg);
+          hs = __ffma2_rn(mm, wm0s, hs);
+          hg = __ffma2_rn(mm, wm0g, hg);
+          float2 tt = __fadd2_rn(P[2][pr], bc2(q[2]));
+          tt = __ffma2_rn(le, wd1, tt);
+          tt = __ffma2_rn(mm, wm1, tt);
+          const float2 zx = __ffma2_rn(ax, tt, __fadd2_rn(P[5][pr], bc2(q[5])));
+          const float2 zy = __ffma2_rn(ay, tt, __fadd2_rn(P[8][pr], bc2(q[8])));
+          const float2 zz = __ffma2_rn(az, tt, __fadd2_rn(P[11][pr], bc2(q[11])));
+          const float2 ts = tanh2(hs), tg = tanh2(hg);
+          const float2 so = __ffma2_rn(hs, ts, hs);   // silu(z) / c = z/2 (1 + tanh(z/2))
+          const float2 vx = __ffma2_rn(tg, zx, zx);   // 2 sigmoid(z_g) z_v
+          const float2 vy = __ffma2_rn(tg, zy, zy);
+          const float2 vz = __ffma2_rn(tg, zz, zz);
+          float2 dt = __fmul2_rn(ax, vx);
+          dt = __ffma2_rn(ay, vy, dt);
+          dt = __ffma2_rn(az, vz, dt);
+          packed[s2][0][pr] = pack_bf16x2(so.x, so.y);
+          packed[s2][1][pr] = pack_bf16x2(dt.x, dt.y);
+          packed[s2][2][pr] = pack_bf16x2(vx.x, vx.y);
+          packed[s2][3][pr] = pack_bf16x2(vy.x, vy.y);
+          packed[s2][4][pr] = pack_bf16x2(vz.x, vz.y);
         }
       }
-      write_geometry(0, i0, t & (kGeoSlots - 1));
-      for (int sb = 0; sb < send_blocks; ++sb, ++t) {
-        const int st = t & 1, slot = t & (kGeoSlots - 1);
-        const int nvalid = min(kSend, N - sb * kSend);
-        mbar_wait(&empty[st], ((t >> 1) & 1) ^ 1, err_flag);
-        mbar_wait(&qfull[st], (t >> 1) & 1, err_flag);
-        const float* qs = sQ + st * (kQStageBytes / 4);
-        uint2 packed[2][5];
+      // 2 senders x 4 receivers = 8 consecutive columns = one 16-byte chunk per plane row (conflict-free with the
+      // 128B swizzle: 8 consecutive rows hit 8 distinct chunks)
+      const int chunk = st * 4 + grp;
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          const int sl = 2 * q + s2;
-          const float* qr = qs + min(sl, nvalid - 1) * 4 * n3;  // senders past the graph end reuse a valid row
-          const float q0s = qr[w], q0g = qr[n + w], q1 = qr[2 * n + w];
-          float q0sk[3], q0gk[3], q1k[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float* qk = qr + (1 + k) * n3;
-            q0sk[k] = qk[w];
-            q0gk[k] = qk[n + w];
-            q1k[k] = qk[2 * n + w];
-          }
-          float o_s[kRecv], o_d[kRecv], o_x[kRecv], o_y[kRecv], o_z[kRecv];
-#pragma unroll
-          for (int r = 0; r < kRecv; ++r) {
-            const float4 ga = geoA[slot * kCols + sl * 4 + r];
-            const float2 gb = geoB[slot * kCols + sl * 4 + r];
-            float zs = (p0s[r] + q0s) + ga.x * (p0sk[r][0] + q0sk[0]) + ga.y * (p0sk[r][1] + q0sk[1]) +
-                       ga.z * (p0sk[r][2] + q0sk[2]) + gb.x * wd0s + gb.y * wm0s;
-            float zg = (p0g[r] + q0g) + ga.x * (p0gk[r][0] + q0gk[0]) + ga.y * (p0gk[r][1] + q0gk[1]) +
-                       ga.z * (p0gk[r][2] + q0gk[2]) + gb.x * wd0g + gb.y * wm0g;
-            const float tt = (p1[r] + q1) + gb.x * wd1 + gb.y * wm1;
-            const float gg = sig_gate_fast(zg);
-            const float vx = gg * (ga.x * tt + (p1k[r][0] + q1k[0]));
-            const float vy = gg * (ga.y * tt + (p1k[r][1] + q1k[1]));
-            const float vz = gg * (ga.z * tt + (p1k[r][2] + q1k[2]));
-            o_s[r] = silu_gate_fast(zs);
-            o_d[r] = ga.x * vx + ga.y * vy + ga.z * vz;
-            o_x[r] = vx;
-            o_y[r] = vy;
-            o_z[r] = vz;
-          }
-          packed[s2][0] = make_uint2(pack_bf16x2(o_s[0], o_s[1]), pack_bf16x2(o_s[2], o_s[3]));
-          packed[s2][1] = make_uint2(pack_bf16x2(o_d[0], o_d[1]), pack_bf16x2(o_d[2], o_d[3]));
-          packed[s2][2] = make_uint2(pack_bf16x2(o_x[0], o_x[1]), pack_bf16x2(o_x[2], o_x[3]));
-          packed[s2][3] = make_uint2(pack_bf16x2(o_y[0], o_y[1]), pack_bf16x2(o_y[2], o_y[3]));
-          packed[s2][4] = make_uint2(pack_bf16x2(o_z[0], o_z[1]), pack_bf16x2(o_z[2], o_z[3]));
-        }
-        // 2 senders x 4 receivers = 8 consecutive columns = one 16-byte chunk per plane row (conflict-free with
-        // the 128B swizzle: 8 consecutive rows hit 8 distinct chunks)
-        {
-          const int chunk = st * 4 + q;
-#pragma unroll
-          for (int p = 0; p < 5; ++p) {
-            const int row = p * n + w;
-            *reinterpret_cast<uint4*>(sB + row * 128 + ((chunk ^ (row & 7)) << 4)) =
-                make_uint4(packed[0][p].x, packed[0][p].y, packed[1][p].x, packed[1][p].y);
-          }
-        }
-        proxy_fence();
-        mbar_arrive(&full[st]);
-        if (sb + 1 < send_blocks) write_geometry(sb + 1, i0, (t + 1) & (kGeoSlots - 1));
+      for (int p = 0; p < 5; ++p) {
+        const int row = p * n + w;
+        *reinterpret_cast<uint4*>(sB + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+            make_uint4(packed[0][p][0], packed[0][p][1], packed[1][p][0], packed[1][p][1]);
       }
+      proxy_fence();
+      mbar_arrive(&full[st]);
+    };
+
+    uint32_t items_done = 0;
+    auto epilogue = [&](const TileCursor& cur) {
+      const uint32_t t = cur.t;
+      const int slot = t & (kGeoSlots - 1);
+      const float* gs = geo + slot * 6 * kCols;
+      mbar_wait(dfull, t & 1, err_flag);
+      tc_fence_after();
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int c0 = 8 * grp + 4 * s2;
+        uint32_t d[6][4];
+#pragma unroll
+        for (int tile = 0; tile < 6; ++tile) SEGNN_TMEM_LD4(tmem + lane_base + kDBase + tile * kCols + c0, d[tile]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (s2 == 1) {  // accumulators are in registers: hand the TMEM tiles back to the MMA warps
+          tc_fence_before();
+          mbar_arrive(dempty);
+        }
+        const float4 AX = *reinterpret_cast<const float4*>(gs + 0 * kCols + c0);
+        const float4 AY = *reinterpret_cast<const float4*>(gs + 1 * kCols + c0);
+        const float4 AZ = *reinterpret_cast<const float4*>(gs + 2 * kCols + c0);
+        const float4 VA = *reinterpret_cast<const float4*>(gs + 5 * kCols + c0);
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const float2 ax = pr ? hi2(AX) : lo2(AX), ay = pr ? hi2(AY) : lo2(AY), az = pr ? hi2(AZ) : lo2(AZ);
+          const float2 va = pr ? hi2(VA) : lo2(VA);
+          const float2 ys = __fadd2_rn(u2f2(d[0][2 * pr], d[0][2 * pr + 1]), b2s);
+          const float2 yg = __fadd2_rn(u2f2(d[1][2 * pr], d[1][2 * pr + 1]), b2g);
+          const float2 ts = tanh2(ys), tg = tanh2(yg);
+          const float2 ms = __ffma2_rn(ys, ts, ys);
+          const float2 g1 = __ffma2_rn(va, tg, va);  // valid * (1 + tanh): masks self edges and padding
+          const float2 t1 = u2f2(d[2][2 * pr], d[2][2 * pr + 1]);
+          acc[0][pr] = __ffma2_rn(va, ms, acc[0][pr]);
+          acc[1][pr] = __ffma2_rn(g1, __ffma2_rn(ax, t1, u2f2(d[3][2 * pr], d[3][2 * pr + 1])), acc[1][pr]);
+          acc[2][pr] = __ffma2_rn(g1, __ffma2_rn(ay, t1, u2f2(d[4][2 * pr], d[4][2 * pr + 1])), acc[2][pr]);
+          acc[3][pr] = __ffma2_rn(g1, __ffma2_rn(az, t1, u2f2(d[5][2 * pr], d[5][2 * pr + 1])), acc[3][pr]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gempty[slot]);
+      if (cur.sb == send_blocks - 1) {
+        // item complete: each group holds the partial sums of its 2 senders per tile for all 4 receivers; group r
+        // collects receiver r.  xch is double buffered by item parity, one named barrier per item.
+        const long long g = cur.item / recv_blocks;
+        const int i0 = (int)(cur.item - g * recv_blocks) * kRecv;
+        float* xb = xch + (items_done & 1) * (16 * 4 * n);
+        float own[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float v = (r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x;
+            if (r == grp) own[c] = v;
+            else xb[((r * 4 + grp) * 4 + c) * n + w] = v;
+          }
+        named_barrier(1, kComputeThreads);
+#pragma unroll
+        for (int src = 0; src < 4; ++src)
+          if (src != grp) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) own[c] += xb[((grp * 4 + src) * 4 + c) * n + w];
+          }
+        if (i0 + grp < N) {
+          float* o = agg + (g * N + i0 + grp) * 4 * n;
+          o[w] = fmaf(own[0], sc_s, add_s);
+          o[n + w] = own[1] * sc_v;
+          o[2 * n + w] = own[2] * sc_v;
+          o[3 * n + w] = own[3] * sc_v;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = make_float2(0.f, 0.f);
+        ++items_done;
+      }
+    };
+
+    // iteration i: produce(tile i), then epilogue(tile i - 1)
+    TileCursor pc{(long long)blockIdx.x, 0, 0u}, ec{(long long)blockIdx.x, 0, 0u};
+    bool primed = false;
+#pragma unroll 1
+    while (ec.item < items) {
+      if (pc.item < items) {
+        if (pc.sb == 0) load_p(pc.item);
+        produce(pc);
+        advance(pc);
+      }
+      if (primed) {
+        epilogue(ec);
+        advance(ec);
+      }
+      primed = true;
     }
-  } else if (warp == kMmaWarp) {
-    // ============================ MMA issuer ==================================================================
-    // The whole warp runs this warp-uniform loop; only the tcgen05 instructions sit under elect.sync. A lean issue
-    // sequence matters: one warp sustains ~1 MMA / 24 clk, the tensor pipe needs one 128x32x16 MMA / 16 clk.
+  } else if (warp == kMmaWarpA || warp == kMmaWarpB) {
+    // ============================ MMA issuers ================================================================
+    // Warp-uniform loops; only the tcgen05 instructions sit under elect.sync so descriptors stay in uniform registers.
+    const bool is_a = warp == kMmaWarpA;
     const uint32_t idesc = make_idesc();
     const uint32_t sB_addr = __shfl_sync(0xffffffffu, smem_u32(sB), 0);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint64_t bdesc0 = make_b_desc(sB_addr);
     const uint32_t d0 = tm + kDBase;
-    // bulk copy of the 8 sender rows of tile (item, sb) into Q stage st (one elected lane)
-    auto load_q = [&](long long item, int sb, int st) {
-      if (item < items && elect_one()) {
-        const long long g = item / recv_blocks;
-        const int nvalid = min(kSend, N - sb * kSend);
+    // bulk copy of the 8 sender rows of tile (item, sb) into Q stage st (issuer A, one elected lane)
+    auto load_q = [&](const TileCursor& c, int st) {
+      if (c.item < items && elect_one()) {
+        const long long g = c.item / recv_blocks;
+        const int nvalid = min(kSend, N - c.sb * kSend);
         const uint32_t bytes = (uint32_t)nvalid * 4 * n3 * (uint32_t)sizeof(float);
-        const float* src = qq + (g * N + (long long)sb * kSend) * 4 * n3;
+        const float* src = qq + (g * N + (long long)c.sb * kSend) * 4 * n3;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&qfull[st])), "r"(bytes)
                      : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(sQ + st * (kQStageBytes / 4))),
+                         smem_u32(sQ + st * kQStageFloats)),
                      "l"(src), "r"(bytes), "r"(smem_u32(&qfull[st]))
                      : "memory");
       }
       __syncwarp();
     };
-    // (item, sb) of the tile two ahead of the current one
-    long long pf_item = blockIdx.x;
-    int pf_sb = 0;
-    auto advance_pf = [&]() {
-      if (++pf_sb == send_blocks) {
-        pf_sb = 0;
-        pf_item += gridDim.x;
+    TileCursor pf{(long long)blockIdx.x, 0, 0u};  // tile two ahead of the current one
+    if (is_a) {
+      load_q(pf, 0);
+      advance(pf);
+      load_q(pf, 1);
+      advance(pf);
+    }
+    for (TileCursor c{(long long)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
+      const uint32_t t = c.t;
+      const int st = t & 1;
+      mbar_wait(&full[st], (t >> 1) & 1, err_flag);
+      if (is_a) {  // producers are done with Q stage st: refill it for tile t + 2
+        load_q(pf, st);
+        advance(pf);
       }
-    };
-    load_q(pf_item, pf_sb, 0);
-    advance_pf();
-    load_q(pf_item, pf_sb, 1);
-    advance_pf();
-    uint32_t t = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-      for (int sb = 0; sb < send_blocks; ++sb, ++t) {
-        const int st = t & 1;
-        mbar_wait(&full[st], (t >> 1) & 1, err_flag);
-        load_q(pf_item, pf_sb, st);  // producers are done with Q stage st: refill it for tile t + 2
-        advance_pf();
-        mbar_wait(dempty, (t & 1) ^ 1, err_flag);
-        tc_fence_after();
-        const uint64_t bst = bdesc0 + (uint64_t)(st * (64 >> 4));  // column half of the swizzled rows
+      mbar_wait(dempty, (t & 1) ^ 1, err_flag);
+      tc_fence_after();
+      const uint64_t bst = bdesc0 + (uint64_t)(st * (64 >> 4));  // column half of the swizzled rows
+      if (is_a) {
 #pragma unroll
         for (int s = 0; s < 2 * n / 16; ++s) {
           // rows [16 s, 16 s + 16) of the (s', dot) planes; 16 rows = 2048 bytes
@@ -395,108 +510,59 @@ __global__ void __launch_bounds__(tc_num_warps<NMUL>() * 32, 1)
           if (elect_one()) {
             mma_ts(d0 + 0 * kCols, tm + 0 * n + s * 8, b_sd, idesc, s > 0);
             mma_ts(d0 + 1 * kCols, tm + 1 * n + s * 8, b_sd, idesc, s > 0);
-            if (s < n / 16) {
-              mma_ts(d0 + 2 * kCols, tm + 2 * n + s * 8, b_sd, idesc, s > 0);
-#pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                const uint64_t b_v = bst + (uint64_t)((((2 + k) * n + 16 * s) * 128) >> 4);
-                mma_ts(d0 + (3 + k) * kCols, tm + 2 * n + n / 2 + s * 8, b_v, idesc, s > 0);
-              }
-            }
           }
         }
-        if (elect_one()) {
-          tc_commit(&empty[st]);
-          tc_commit(dfull);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ============================ epilogue: gate + aggregation ================================================
-    if (warp >= kEpiWarp0 + NW && warp < kEpiWarp0 + 4) goto done;  // unused quadrant slots of group 0
-    const int eg = (warp - kEpiWarp0) >> 2;   // column half
-    const int quad = warp & 3;
-    const int w = quad * 32 + lane;           // channel = TMEM lane
-    const bool act = w < n;
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const float b2s = act ? b2[w] : 0.f, b2g = act ? b2[n + w] : 0.f;
-    float bm_s = 1.f, bm_v = 1.f, ba_s = 0.f;
-    if (act && bn_mul != nullptr) {
-      bm_s = bn_mul[w];
-      bm_v = bn_mul[n + w];
-      ba_s = bn_add[w];
-    }
-    uint32_t t = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-      const long long g = item / recv_blocks;
-      const int i0 = (int)(item - g * recv_blocks) * kRecv;
-      float acc[kRecv][4];
+      } else {
 #pragma unroll
-      for (int r = 0; r < kRecv; ++r)
+        for (int s = 0; s < n / 16; ++s) {
+          const uint64_t b_sd = bst + (uint64_t)(s * (2048 >> 4));
+          if (elect_one()) {
+            mma_ts(d0 + 2 * kCols, tm + 2 * n + s * 8, b_sd, idesc, s > 0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-
-      for (int sb = 0; sb < send_blocks; ++sb, ++t) {
-        const int slot = t & (kGeoSlots - 1);
-        mbar_wait(&gfull[slot], (t >> 3) & 1, err_flag);  // acquires the producers' geometry writes
-        mbar_wait(dfull, t & 1, err_flag);
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c0 = eg * 16 + h * 8;
-          uint32_t d[6][8];
-#pragma unroll
-          for (int tile = 0; tile < 6; ++tile) SEGNN_TMEM_LD8(tmem + lane_base + kDBase + tile * kCols + c0, d[tile]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (h == 1) {  // accumulators are in registers: hand the TMEM tiles back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(dempty);
-          }
-          if (act) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 ga = geoA[slot * kCols + c0 + j];
-              const int r = j & 3;
-              const float ms = silu_gate_fast(__uint_as_float(d[0][j]) + b2s);
-              const float gt = sig_gate_fast(__uint_as_float(d[1][j]) + b2g) * ga.w;
-              const float t1 = __uint_as_float(d[2][j]);
-              acc[r][0] = fmaf(ga.w, ms, acc[r][0]);
-              acc[r][1] = fmaf(gt, fmaf(ga.x, t1, __uint_as_float(d[3][j])), acc[r][1]);
-              acc[r][2] = fmaf(gt, fmaf(ga.y, t1, __uint_as_float(d[4][j])), acc[r][2]);
-              acc[r][3] = fmaf(gt, fmaf(ga.z, t1, __uint_as_float(d[5][j])), acc[r][3]);
+            for (int k = 0; k < 3; ++k) {
+              const uint64_t b_v = bst + (uint64_t)((((2 + k) * n + 16 * s) * 128) >> 4);
+              mma_ts(d0 + (3 + k) * kCols, tm + 2 * n + n / 2 + s * 8, b_v, idesc, s > 0);
             }
           }
         }
       }
-      // combine the two column halves and write the receivers' aggregates (eval BatchNorm folded)
-      if (eg == 1 && act) {
-#pragma unroll
-        for (int r = 0; r < kRecv; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) xch[(r * 4 + c) * n + w] = acc[r][c];
+      if (elect_one()) {
+        tc_commit(&empty[st]);
+        tc_commit(dfull);
       }
-      named_barrier(6, kEpiThreads);
-      if (eg == 0 && act) {
-#pragma unroll
-        for (int r = 0; r < kRecv; ++r) {
-          if (i0 + r < N) {
-            float* o = agg + (g * N + i0 + r) * 4 * n;
-            o[w] = fmaf(acc[r][0] + xch[(r * 4 + 0) * n + w], bm_s, ba_s);
-            o[n + w] = (acc[r][1] + xch[(r * 4 + 1) * n + w]) * bm_v;
-            o[2 * n + w] = (acc[r][2] + xch[(r * 4 + 2) * n + w]) * bm_v;
-            o[3 * n + w] = (acc[r][3] + xch[(r * 4 + 3) * n + w]) * bm_v;
-          }
-        }
-      }
-      named_barrier(6, kEpiThreads);
+      __syncwarp();
+    }
+  } else if (warp == kGeoWarp) {
+    // ============================ geometry: lane = tile column ==================================================
+    const int sl = lane >> 2, r = lane & 3;
+    for (TileCursor c{(long long)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
+      const uint32_t t = c.t;
+      const int slot = t & (kGeoSlots - 1);
+      const long long g = c.item / recv_blocks;
+      const int i0 = (int)(c.item - g * recv_blocks) * kRecv;
+      const int jj = c.sb * kSend + sl, ii = i0 + r;
+      const long long js = g * N + min(jj, N - 1), is = g * N + min(ii, N - 1);
+      float ux, uy, uz, len;
+      unit_vec(pos[js * 3 + 0] - pos[is * 3 + 0], pos[js * 3 + 1] - pos[is * 3 + 1], pos[js * 3 + 2] - pos[is * 3 + 2],
+               ux, uy, uz, len);
+      const float mm = mass[js] * mass[is];
+      const bool valid = (jj < N) && (ii < N) && (jj != ii);
+      mbar_wait(&gempty[slot], ((t / kGeoSlots) & 1) ^ 1, err_flag);
+      float* gs = geo + slot * 6 * kCols;
+      gs[0 * kCols + lane] = kY1 * ux;
+      gs[1 * kCols + lane] = kY1 * uy;
+      gs[2 * kCols + lane] = kY1 * uz;
+      gs[3 * kCols + lane] = len;
+      gs[4 * kCols + lane] = mm;
+      gs[5 * kCols + lane] = valid ? 1.0f : 0.0f;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gfull[slot]);
     }
   }
 
-done:
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kMmaWarpA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
 }
@@ -515,13 +581,14 @@ __global__ void pack_w2_kernel(const float* __restrict__ ss, const float* __rest
         if (c < 2 * n) {  // s tile (c < n) / g tile: K = [s' (n) | dot (n)], output column w or n + w
           const int oc = c < n ? w : n + w;
           const int k = 2 * (c < n ? c : c - n) + h;
-          v[h] = k < n ? ss[(size_t)k * 2 * n + oc] : vs[(size_t)(k - n) * 2 * n + oc];
+          // output carried as z/2; inputs arrive as silu/c_silu and 2 sigmoid/c_sig * v (see the kernel header)
+          v[h] = k < n ? 0.5f * kCSilu * ss[(size_t)k * 2 * n + oc] : 0.25f * kCSig * vs[(size_t)(k - n) * 2 * n + oc];
         } else if (c < 2 * n + n / 2) {  // T1 tile: K = s'
           const int k = 2 * (c - 2 * n) + h;
-          v[h] = sv[(size_t)k * n + w];
+          v[h] = kCSilu * sv[(size_t)k * n + w];
         } else {  // D_k tiles: K = v'_k
           const int k = 2 * (c - 2 * n - n / 2) + h;
-          v[h] = vv[(size_t)k * n + w];
+          v[h] = 0.5f * kCSig * vv[(size_t)k * n + w];
         }
       }
     }
@@ -535,10 +602,10 @@ static int launch_tc(const float* pos, const float* mass, int B, int N, const fl
                      const float* w_edge1,
                      const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg,
                      int* err_flag, cudaStream_t stream) {
-  constexpr int threads = tc_num_warps<NMUL>() * 32;
+  constexpr int threads = kWarps * 32;
   const size_t smem = 1024 + (size_t)5 * NMUL * 128 + (size_t)2 * kSend * 4 * 3 * NMUL * sizeof(float) +
-                      (size_t)N * sizeof(float4) + kGeoSlots * kCols * (sizeof(float4) + sizeof(float2)) +
-                      (size_t)kRecv * 4 * NMUL * sizeof(float) + 24 * sizeof(uint64_t) + 16;
+                      (size_t)kGeoSlots * 6 * kCols * sizeof(float) + (size_t)2 * 16 * 4 * NMUL * sizeof(float) +
+                      24 * sizeof(uint64_t) + 16;
   auto kern = edge_layer_tc_kernel<NMUL>;
   {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -568,11 +635,6 @@ int edge_layer_tc(const float* pos, const float* mass, int B, int N, int n, cons
                   const float* w_edge1,
                   const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg,
                   cudaStream_t stream) {
-  if (N > tc::kMaxNodesPerGraph) {
-    set_error("edge_layer_tc: N=%d nodes per graph exceeds the tensor-core kernel's staging limit (%d)", N,
-              tc::kMaxNodesPerGraph);
-    return SEGNN_E_UNSUPPORTED;
-  }
   if (n == 32) return tc::launch_tc<32>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
   if (n == 64) return tc::launch_tc<64>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
   if (n == 96) return tc::launch_tc<96>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);

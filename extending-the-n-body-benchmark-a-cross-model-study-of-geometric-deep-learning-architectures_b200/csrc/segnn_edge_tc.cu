@@ -66,6 +66,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   if (err_flag) atomicExch(err_flag, 1);
   __trap();
 }
+// Same wait on a precomputed shared-memory address, as one PTX loop: the fast path (phase already complete) is
+// mov + try_wait + branch; still bounded (traps after ~4M polls instead of hanging the GPU).
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+      "mov.u32 c, 0;\n"
+      "SEGNN_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra SEGNN_DONE_%=;\n\t"
+      "add.u32 c, c, 1;\n\t"
+      "setp.lt.u32 p, c, 4194304;\n\t"
+      "@p bra SEGNN_WAIT_%=;\n\t"
+      "trap;\n"
+      "SEGNN_DONE_%=:\n\t}" ::"r"(bar_addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -155,7 +175,7 @@ __device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); 
 __device__ __forceinline__ float2 u2f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 struct TileCursor {
-  long long item;
+  int item;
   int sb;
   uint32_t t;
 };
@@ -184,9 +204,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sB = smem;                                                  // 5n rows x 128 bytes (two 64-byte stages)
   float* sQ = reinterpret_cast<float*>(smem + 5 * n * 128);            // [2][8 senders][4 planes][3n]
-  float* geo = sQ + 2 * kQStageFloats;                                 // [slots][6][32]: ax, ay, az, len, mm, valid
-  float* xch = geo + kGeoSlots * 6 * kCols;                            // [2][4 recv][4 src group][4 comp][n]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 16 * 4 * n);
+  float* sP = sQ + 2 * kQStageFloats;                                  // [4 receivers][4 planes][3n]
+  float* geo = sP + kRecv * 4 * n3;                                // [slots][6][32]: ax, ay, az, len, mm, valid
+  float* xch = geo + kGeoSlots * 6 * kCols;                            // [2][4 recv][3 other groups][4 comp][n]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 12 * 4 * n);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   uint64_t* full = bars;         // [2] B stage written (all compute threads)
   uint64_t* empty = bars + 2;    // [2] B stage consumed (both MMA issuers commit)
@@ -195,6 +216,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   uint64_t* qfull = bars + 6;    // [2] bulk copy landed (expect_tx)
   uint64_t* gfull = bars + 8;    // [kGeoSlots] geometry written
   uint64_t* gempty = bars + 12;  // [kGeoSlots] geometry consumed (one arrival per compute warp)
+  uint64_t* pfull = bars + 16;   // receiver rows of P landed (expect_tx)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -213,6 +235,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       mbar_init(&qfull[i], 1);
     }
     mbar_init(dfull, 2);
+    mbar_init(pfull, 1);
     mbar_init(dempty, kComputeThreads);
     for (int i = 0; i < kGeoSlots; ++i) {
       mbar_init(&gfull[i], 1);
@@ -246,7 +269,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 
   const int recv_blocks = (N + kRecv - 1) / kRecv;
   const int send_blocks = (N + kSend - 1) / kSend;
-  const long long items = (long long)B * recv_blocks;
+  const int items = B * recv_blocks;  // launch_tc checks that this fits an int
   auto advance = [&](TileCursor& c) {
     ++c.t;
     if (++c.sb == send_blocks) {
@@ -259,6 +282,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     // ============================ compute warps: produce(t + 1) / epilogue(t) ==================================
     const int w = cb * 32 + lane;  // channel = B-tile row (producer role) = TMEM lane (epilogue role)
     const uint32_t lane_base = (uint32_t)(cb * 32) << 16;
+    const uint32_t bar0 = smem_u32(bars);  // barrier addresses: bar0 + 8 * index
     const float2 wd0s = bc2(0.5f * w_edge1[w]), wd0g = bc2(0.5f * w_edge1[n + w]), wm0s = bc2(0.5f * w_edge1[2 * n + w]),
                  wm0g = bc2(0.5f * w_edge1[3 * n + w]), wd1 = bc2(w_edge1[4 * n + w]), wm1 = bc2(w_edge1[5 * n + w]);
     const float2 b2s = bc2(0.5f * b2[w]), b2g = bc2(0.5f * b2[n + w]);
@@ -275,14 +299,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = make_float2(0.f, 0.f);
 
-    auto load_p = [&](long long item) {
-      const long long g = item / recv_blocks;
+    uint32_t p_items = 0;  // items whose P rows this thread has loaded
+    auto load_p = [&](int item) {
+      const int g = item / recv_blocks;
       const int i0 = (int)(item - g * recv_blocks) * kRecv;
-      const long long base = g * N;
+      const int nrecv = min(kRecv, N - i0);
+      mbar_wait_a(bar0 + 8 * 16, p_items & 1);  // pfull: this item's rows have landed
+      const float* pb = sP;
+      ++p_items;
 #pragma unroll
       for (int pr = 0; pr < 2; ++pr) {
-        const float* r0 = pp + (base + min(i0 + 2 * pr, N - 1)) * 4 * n3;
-        const float* r1 = pp + (base + min(i0 + 2 * pr + 1, N - 1)) * 4 * n3;
+        const float* r0 = pb + min(2 * pr, nrecv - 1) * 4 * n3;  // receivers past the graph end reuse a valid row
+        const float* r1 = pb + min(2 * pr + 1, nrecv - 1) * 4 * n3;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -297,9 +325,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       const uint32_t t = cur.t;
       const int st = t & 1, slot = t & (kGeoSlots - 1);
       const int nvalid = min(kSend, N - cur.sb * kSend);
-      mbar_wait(&gfull[slot], (t / kGeoSlots) & 1, err_flag);
-      mbar_wait(&empty[st], ((t >> 1) & 1) ^ 1, err_flag);
-      mbar_wait(&qfull[st], (t >> 1) & 1, err_flag);
+      mbar_wait_a(bar0 + 8 * (8 + slot), (t / kGeoSlots) & 1);     // gfull[slot]
+      mbar_wait_a(bar0 + 8 * (2 + st), ((t >> 1) & 1) ^ 1);         // empty[st]
+      mbar_wait_a(bar0 + 8 * (6 + st), (t >> 1) & 1);               // qfull[st]
       const float* qs = sQ + st * kQStageFloats;
       const float* gs = geo + slot * 6 * kCols;
       uint32_t packed[2][5][2];
@@ -365,7 +393,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
             make_uint4(packed[0][p][0], packed[0][p][1], packed[1][p][0], packed[1][p][1]);
       }
       proxy_fence();
-      mbar_arrive(&full[st]);
+      mbar_arrive_a(bar0 + 8 * st);  // full[st]
     };
 
     uint32_t items_done = 0;
@@ -373,7 +401,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       const uint32_t t = cur.t;
       const int slot = t & (kGeoSlots - 1);
       const float* gs = geo + slot * 6 * kCols;
-      mbar_wait(dfull, t & 1, err_flag);
+      mbar_wait_a(bar0 + 8 * 4, t & 1);  // dfull
       tc_fence_after();
 #pragma unroll
       for (int s2 = 0; s2 < 2; ++s2) {
@@ -384,7 +412,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (s2 == 1) {  // accumulators are in registers: hand the TMEM tiles back to the MMA warps
           tc_fence_before();
-          mbar_arrive(dempty);
+          mbar_arrive_a(bar0 + 8 * 5);  // dempty
         }
         const float4 AX = *reinterpret_cast<const float4*>(gs + 0 * kCols + c0);
         const float4 AY = *reinterpret_cast<const float4*>(gs + 1 * kCols + c0);
@@ -407,13 +435,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&gempty[slot]);
+      if (lane == 0) mbar_arrive_a(bar0 + 8 * (12 + slot));  // gempty[slot]
       if (cur.sb == send_blocks - 1) {
         // item complete: each group holds the partial sums of its 2 senders per tile for all 4 receivers; group r
         // collects receiver r.  xch is double buffered by item parity, one named barrier per item.
         const long long g = cur.item / recv_blocks;
         const int i0 = (int)(cur.item - g * recv_blocks) * kRecv;
-        float* xb = xch + (items_done & 1) * (16 * 4 * n);
+        float* xb = xch + (items_done & 1) * (12 * 4 * n);
         float own[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -421,15 +449,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
           for (int c = 0; c < 4; ++c) {
             const float v = (r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x;
             if (r == grp) own[c] = v;
-            else xb[((r * 4 + grp) * 4 + c) * n + w] = v;
+            else xb[((r * 3 + (grp - (grp > r))) * 4 + c) * n + w] = v;  // slot = source group, skipping r
           }
         named_barrier(1, kComputeThreads);
 #pragma unroll
-        for (int src = 0; src < 4; ++src)
-          if (src != grp) {
+        for (int src = 0; src < 3; ++src)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) own[c] += xb[((grp * 4 + src) * 4 + c) * n + w];
-          }
+          for (int c = 0; c < 4; ++c) own[c] += xb[((grp * 3 + src) * 4 + c) * n + w];
         if (i0 + grp < N) {
           float* o = agg + (g * N + i0 + grp) * 4 * n;
           o[w] = fmaf(own[0], sc_s, add_s);
@@ -444,7 +470,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     };
 
     // iteration i: produce(tile i), then epilogue(tile i - 1)
-    TileCursor pc{(long long)blockIdx.x, 0, 0u}, ec{(long long)blockIdx.x, 0, 0u};
+    TileCursor pc{(int)blockIdx.x, 0, 0u}, ec{(int)blockIdx.x, 0, 0u};
     bool primed = false;
 #pragma unroll 1
     while (ec.item < items) {
@@ -484,20 +510,39 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       }
       __syncwarp();
     };
-    TileCursor pf{(long long)blockIdx.x, 0, 0u};  // tile two ahead of the current one
+    // bulk copy of the (up to) 4 receiver rows of P of an item into P buffer `buf` (issuer A, one elected lane)
+    auto load_prow = [&](int item) {
+      if (item < items && elect_one()) {
+        const long long g = item / recv_blocks;
+        const int i0 = (int)(item - g * recv_blocks) * kRecv;
+        const uint32_t bytes = (uint32_t)min(kRecv, N - i0) * 4 * n3 * (uint32_t)sizeof(float);
+        const float* src = pp + (g * N + i0) * 4 * n3;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(pfull)), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sP)),
+                     "l"(src), "r"(bytes), "r"(smem_u32(pfull))
+                     : "memory");
+      }
+      __syncwarp();
+    };
+    TileCursor pf{(int)blockIdx.x, 0, 0u};  // tile two ahead of the current one
     if (is_a) {
+      load_prow(blockIdx.x);
       load_q(pf, 0);
       advance(pf);
       load_q(pf, 1);
       advance(pf);
     }
-    for (TileCursor c{(long long)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
+    for (TileCursor c{(int)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
       const uint32_t t = c.t;
       const int st = t & 1;
       mbar_wait(&full[st], (t >> 1) & 1, err_flag);
       if (is_a) {  // producers are done with Q stage st: refill it for tile t + 2
         load_q(pf, st);
         advance(pf);
+        // every compute thread now holds this item's P rows in registers: fetch the next item's (single buffer)
+        if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
       }
       mbar_wait(dempty, (t & 1) ^ 1, err_flag);
       tc_fence_after();
@@ -535,7 +580,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   } else if (warp == kGeoWarp) {
     // ============================ geometry: lane = tile column ==================================================
     const int sl = lane >> 2, r = lane & 3;
-    for (TileCursor c{(long long)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
+    for (TileCursor c{(int)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
       const uint32_t t = c.t;
       const int slot = t & (kGeoSlots - 1);
       const long long g = c.item / recv_blocks;
@@ -604,7 +649,8 @@ static int launch_tc(const float* pos, const float* mass, int B, int N, const fl
                      int* err_flag, cudaStream_t stream) {
   constexpr int threads = kWarps * 32;
   const size_t smem = 1024 + (size_t)5 * NMUL * 128 + (size_t)2 * kSend * 4 * 3 * NMUL * sizeof(float) +
-                      (size_t)kGeoSlots * 6 * kCols * sizeof(float) + (size_t)2 * 16 * 4 * NMUL * sizeof(float) +
+                      (size_t)kRecv * 4 * 3 * NMUL * sizeof(float) + (size_t)kGeoSlots * 6 * kCols * sizeof(float) +
+                      (size_t)2 * 12 * 4 * NMUL * sizeof(float) +
                       24 * sizeof(uint64_t) + 16;
   auto kern = edge_layer_tc_kernel<NMUL>;
   {
@@ -618,6 +664,10 @@ static int launch_tc(const float* pos, const float* mass, int B, int N, const fl
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long items = (long long)B * ((N + kRecv - 1) / kRecv);
+  if (items > 0x7fffffffLL) {
+    set_error("edge_layer_tc: too many work items");
+    return SEGNN_E_UNSUPPORTED;
+  }
   const unsigned grid = (unsigned)(items < sms ? items : sms);
   kern<<<grid, threads, smem, stream>>>(pos, mass, B, N, pp, qq, w_edge1, b2, (const uint32_t*)w2_tc, bn_mul, bn_add, agg,
                                         err_flag);

@@ -7,11 +7,12 @@
 // Six accumulator tiles per 32-edge tile: s (K = 2n: [s' | v'.a1]), g (same K), T1 = W_sv^T s' (K = n),
 // D_k = W_vv^T v'_k (K = n, k = x,y,z); message = (silu(s), sigmoid(g) * (a1_k * T1 + D_k)).
 //
-// Work item = (graph, 4 receivers); tile = 4 receivers x 8 senders = 32 edge columns, column c = sender_local * 4 +
-// receiver_local.  One persistent CTA of 16 warps per SM:
+// Work item = (graph, 4 receivers); tile = 4 receivers x 8 senders = 32 edge columns, column c = (r / 2) * 16 +
+// sender_local * 2 + (r % 2).  One persistent CTA of 16 warps per SM:
 //   compute warps (warp % 4 < n / 32; warp % 4 = channel block = TMEM lane quadrant, warp / 4 = group g):
-//     every thread is one channel.  Group g owns columns [8g, 8g + 8) = senders (2g, 2g + 1) x 4 receivers of every
-//     tile, in BOTH roles, software-pipelined:   produce(t + 1)  ->  epilogue(t)  ->  produce(t + 2)  -> ...
+//     every thread is one channel.  Group g owns 8 consecutive columns = 2 receivers x 4 senders of every tile
+//     (12 receiver-side projection pairs live in registers), in BOTH roles, software-pipelined:
+//     produce(t + 1)  ->  epilogue(t)  ->  produce(t + 2)  -> ...
 //       produce:  message_layer_1 combine (hoisted projections P_i + Q_j, geometry) + gate -> bf16 B tile (one
 //                 conflict-free 16-byte store per plane);
 //       epilogue: tcgen05.ld of the six accumulators, gate, in-register accumulation over senders (no atomics, no
@@ -206,8 +207,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   float* sQ = reinterpret_cast<float*>(smem + 5 * n * 128);            // [2][8 senders][4 planes][3n]
   float* sP = sQ + 2 * kQStageFloats;                                  // [4 receivers][4 planes][3n]
   float* geo = sP + kRecv * 4 * n3;                                // [slots][6][32]: ax, ay, az, len, mm, valid
-  float* xch = geo + kGeoSlots * 6 * kCols;                            // [2][4 recv][3 other groups][4 comp][n]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 12 * 4 * n);
+  float* xch = geo + kGeoSlots * 6 * kCols;                            // [2][4 groups][4 comp][n]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 4 * 4 * n);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   uint64_t* full = bars;         // [2] B stage written (all compute threads)
   uint64_t* empty = bars + 2;    // [2] B stage consumed (both MMA issuers commit)
@@ -293,11 +294,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       sc_v *= bn_mul[n + w];
       add_s = bn_add[w];
     }
-    // receiver-side projections, as receiver pairs: P[plane * 3 + part][pair]; parts (0s, 0g) carry the factor 1/2
-    float2 P[12][2];
-    float2 acc[4][2];
+    // group shape: 2 receivers (pair rp) x 4 senders (quad sq); tile column c = rp * 16 + sender_local * 2 + (r & 1),
+    // so the group's 8 columns [8 gi, 8 gi + 8), gi = rp * 2 + sq, are one 16-byte chunk of every B row and one
+    // contiguous TMEM column range.  Every packed operation handles the receiver pair of one sender.
+    const int rp = grp & 1, sq = grp >> 1, gi = rp * 2 + sq;
+    // receiver-side projections of the pair: P[plane * 3 + part]; parts (0s, 0g) carry the factor 1/2
+    float2 P[12];
+    float2 acc[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = make_float2(0.f, 0.f);
+    for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
 
     uint32_t p_items = 0;  // items whose P rows this thread has loaded
     auto load_p = [&](int item) {
@@ -305,20 +310,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       const int i0 = (int)(item - g * recv_blocks) * kRecv;
       const int nrecv = min(kRecv, N - i0);
       mbar_wait_a(bar0 + 8 * 16, p_items & 1);  // pfull: this item's rows have landed
-      const float* pb = sP;
       ++p_items;
+      const float* r0 = sP + min(2 * rp, nrecv - 1) * 4 * n3;  // receivers past the graph end reuse a valid row
+      const float* r1 = sP + min(2 * rp + 1, nrecv - 1) * 4 * n3;
 #pragma unroll
-      for (int pr = 0; pr < 2; ++pr) {
-        const float* r0 = pb + min(2 * pr, nrecv - 1) * 4 * n3;  // receivers past the graph end reuse a valid row
-        const float* r1 = pb + min(2 * pr + 1, nrecv - 1) * 4 * n3;
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int part = 0; part < 3; ++part) {
-            const float sc = part < 2 ? 0.5f : 1.0f;
-            P[c * 3 + part][pr] = make_float2(sc * r0[c * n3 + part * n + w], sc * r1[c * n3 + part * n + w]);
-          }
-      }
+        for (int part = 0; part < 3; ++part) {
+          const float sc = part < 2 ? 0.5f : 1.0f;
+          P[c * 3 + part] = make_float2(sc * r0[c * n3 + part * n + w], sc * r1[c * n3 + part * n + w]);
+        }
     };
 
     auto produce = [&](const TileCursor& cur) {
@@ -329,45 +330,46 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       mbar_wait_a(bar0 + 8 * (2 + st), ((t >> 1) & 1) ^ 1);         // empty[st]
       mbar_wait_a(bar0 + 8 * (6 + st), (t >> 1) & 1);               // qfull[st]
       const float* qs = sQ + st * kQStageFloats;
-      const float* gs = geo + slot * 6 * kCols;
-      uint32_t packed[2][5][2];
+      const float* gs = geo + slot * 6 * kCols + 8 * gi;
+      uint32_t packed[4][5];
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        const int sl = 2 * grp + s2;
-        const float* qr = qs + min(sl, nvalid - 1) * 4 * n3;  // senders past the graph end reuse a valid row
-        float q[12];
+      for (int h = 0; h < 2; ++h) {
+        const float4 AX = *reinterpret_cast<const float4*>(gs + 0 * kCols + 4 * h);
+        const float4 AY = *reinterpret_cast<const float4*>(gs + 1 * kCols + 4 * h);
+        const float4 AZ = *reinterpret_cast<const float4*>(gs + 2 * kCols + 4 * h);
+        const float4 LE = *reinterpret_cast<const float4*>(gs + 3 * kCols + 4 * h);
+        const float4 MM = *reinterpret_cast<const float4*>(gs + 4 * kCols + 4 * h);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int e = 0; e < 2; ++e) {
+          const int s4 = 2 * h + e;
+          const int sl = 4 * sq + s4;
+          const float* qr = qs + min(sl, nvalid - 1) * 4 * n3;  // senders past the graph end reuse a valid row
+          float q[12];
 #pragma unroll
-          for (int part = 0; part < 3; ++part) q[c * 3 + part] = qr[c * n3 + part * n + w];
-        const float4 AX = *reinterpret_cast<const float4*>(gs + 0 * kCols + sl * 4);
-        const float4 AY = *reinterpret_cast<const float4*>(gs + 1 * kCols + sl * 4);
-        const float4 AZ = *reinterpret_cast<const float4*>(gs + 2 * kCols + sl * 4);
-        const float4 LE = *reinterpret_cast<const float4*>(gs + 3 * kCols + sl * 4);
-        const float4 MM = *reinterpret_cast<const float4*>(gs + 4 * kCols + sl * 4);
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int pr = 0; pr < 2; ++pr) {
-          const float2 ax = pr ? hi2(AX) : lo2(AX), ay = pr ? hi2(AY) : lo2(AY), az = pr ? hi2(AZ) : lo2(AZ);
-          const float2 le = pr ? hi2(LE) : lo2(LE), mm = pr ? hi2(MM) : lo2(MM);
+            for (int part = 0; part < 3; ++part) q[c * 3 + part] = qr[c * n3 + part * n + w];
+          const float2 ax = e ? hi2(AX) : lo2(AX), ay = e ? hi2(AY) : lo2(AY), az = e ? hi2(AZ) : lo2(AZ);
+          const float2 le = e ? hi2(LE) : lo2(LE), mm = e ? hi2(MM) : lo2(MM);
           // half pre-activations of the scalar / gate channels: (P0 + Q0)/2 + a.(P0k + Q0k)/2 + |r| wd/2 + m_i m_j wm/2
-          float2 hs = __ffma2_rn(bc2(q[0]), half2v, P[0][pr]);
-          float2 hg = __ffma2_rn(bc2(q[1]), half2v, P[1][pr]);
-          hs = __ffma2_rn(ax, __ffma2_rn(bc2(q[3]), half2v, P[3][pr]), hs);
-          hg = __ffma2_rn(ax, __ffma2_rn(bc2(q[4]), half2v, P[4][pr]), hg);
-          hs = __ffma2_rn(ay, __ffma2_rn(bc2(q[6]), half2v, P[6][pr]), hs);
-          hg = __ffma2_rn(ay, __ffma2_rn(bc2(q[7]), half2v, P[7][pr]), hg);
-          hs = __ffma2_rn(az, __ffma2_rn(bc2(q[9]), half2v, P[9][pr]), hs);
-          hg = __ffma2_rn(az, __ffma2_rn(bc2(q[10]), half2v, P[10][pr]), hg);
+          float2 hs = __ffma2_rn(bc2(q[0]), half2v, P[0]);
+          float2 hg = __ffma2_rn(bc2(q[1]), half2v, P[1]);
+          hs = __ffma2_rn(ax, __ffma2_rn(bc2(q[3]), half2v, P[3]), hs);
+          hg = __ffma2_rn(ax, __ffma2_rn(bc2(q[4]), half2v, P[4]), hg);
+          hs = __ffma2_rn(ay, __ffma2_rn(bc2(q[6]), half2v, P[6]), hs);
+          hg = __ffma2_rn(ay, __ffma2_rn(bc2(q[7]), half2v, P[7]), hg);
+          hs = __ffma2_rn(az, __ffma2_rn(bc2(q[9]), half2v, P[9]), hs);
+          hg = __ffma2_rn(az, __ffma2_rn(bc2(q[10]), half2v, P[10]), hg);
           hs = __ffma2_rn(le, wd0s, hs);
           hg = __ffma2_rn(le, wd0g, hg);
           hs = __ffma2_rn(mm, wm0s, hs);
           hg = __ffma2_rn(mm, wm0g, hg);
-          float2 tt = __fadd2_rn(P[2][pr], bc2(q[2]));
+          float2 tt = __fadd2_rn(P[2], bc2(q[2]));
           tt = __ffma2_rn(le, wd1, tt);
           tt = __ffma2_rn(mm, wm1, tt);
-          const float2 zx = __ffma2_rn(ax, tt, __fadd2_rn(P[5][pr], bc2(q[5])));
-          const float2 zy = __ffma2_rn(ay, tt, __fadd2_rn(P[8][pr], bc2(q[8])));
-          const float2 zz = __ffma2_rn(az, tt, __fadd2_rn(P[11][pr], bc2(q[11])));
+          const float2 zx = __ffma2_rn(ax, tt, __fadd2_rn(P[5], bc2(q[5])));
+          const float2 zy = __ffma2_rn(ay, tt, __fadd2_rn(P[8], bc2(q[8])));
+          const float2 zz = __ffma2_rn(az, tt, __fadd2_rn(P[11], bc2(q[11])));
           const float2 ts = tanh2(hs), tg = tanh2(hg);
           const float2 so = __ffma2_rn(hs, ts, hs);   // silu(z) / c = z/2 (1 + tanh(z/2))
           const float2 vx = __ffma2_rn(tg, zx, zx);   // 2 sigmoid(z_g) z_v
@@ -376,21 +378,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
           float2 dt = __fmul2_rn(ax, vx);
           dt = __ffma2_rn(ay, vy, dt);
           dt = __ffma2_rn(az, vz, dt);
-          packed[s2][0][pr] = pack_bf16x2(so.x, so.y);
-          packed[s2][1][pr] = pack_bf16x2(dt.x, dt.y);
-          packed[s2][2][pr] = pack_bf16x2(vx.x, vx.y);
-          packed[s2][3][pr] = pack_bf16x2(vy.x, vy.y);
-          packed[s2][4][pr] = pack_bf16x2(vz.x, vz.y);
+          packed[s4][0] = pack_bf16x2(so.x, so.y);
+          packed[s4][1] = pack_bf16x2(dt.x, dt.y);
+          packed[s4][2] = pack_bf16x2(vx.x, vx.y);
+          packed[s4][3] = pack_bf16x2(vy.x, vy.y);
+          packed[s4][4] = pack_bf16x2(vz.x, vz.y);
         }
       }
-      // 2 senders x 4 receivers = 8 consecutive columns = one 16-byte chunk per plane row (conflict-free with the
+      // 4 senders x 2 receivers = 8 consecutive columns = one 16-byte chunk per plane row (conflict-free with the
       // 128B swizzle: 8 consecutive rows hit 8 distinct chunks)
-      const int chunk = st * 4 + grp;
+      const int chunk = st * 4 + gi;
 #pragma unroll
       for (int p = 0; p < 5; ++p) {
         const int row = p * n + w;
         *reinterpret_cast<uint4*>(sB + row * 128 + ((chunk ^ (row & 7)) << 4)) =
-            make_uint4(packed[0][p][0], packed[0][p][1], packed[1][p][0], packed[1][p][1]);
+            make_uint4(packed[0][p], packed[1][p], packed[2][p], packed[3][p]);
       }
       proxy_fence();
       mbar_arrive_a(bar0 + 8 * st);  // full[st]
@@ -400,71 +402,68 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     auto epilogue = [&](const TileCursor& cur) {
       const uint32_t t = cur.t;
       const int slot = t & (kGeoSlots - 1);
-      const float* gs = geo + slot * 6 * kCols;
+      const float* gs = geo + slot * 6 * kCols + 8 * gi;
       mbar_wait_a(bar0 + 8 * 4, t & 1);  // dfull
       tc_fence_after();
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        const int c0 = 8 * grp + 4 * s2;
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = 8 * gi + 4 * h;
         uint32_t d[6][4];
 #pragma unroll
         for (int tile = 0; tile < 6; ++tile) SEGNN_TMEM_LD4(tmem + lane_base + kDBase + tile * kCols + c0, d[tile]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (s2 == 1) {  // accumulators are in registers: hand the TMEM tiles back to the MMA warps
+        if (h == 1) {  // accumulators are in registers: hand the TMEM tiles back to the MMA warps
           tc_fence_before();
           mbar_arrive_a(bar0 + 8 * 5);  // dempty
         }
-        const float4 AX = *reinterpret_cast<const float4*>(gs + 0 * kCols + c0);
-        const float4 AY = *reinterpret_cast<const float4*>(gs + 1 * kCols + c0);
-        const float4 AZ = *reinterpret_cast<const float4*>(gs + 2 * kCols + c0);
-        const float4 VA = *reinterpret_cast<const float4*>(gs + 5 * kCols + c0);
+        const float4 AX = *reinterpret_cast<const float4*>(gs + 0 * kCols + 4 * h);
+        const float4 AY = *reinterpret_cast<const float4*>(gs + 1 * kCols + 4 * h);
+        const float4 AZ = *reinterpret_cast<const float4*>(gs + 2 * kCols + 4 * h);
+        const float4 VA = *reinterpret_cast<const float4*>(gs + 5 * kCols + 4 * h);
 #pragma unroll
-        for (int pr = 0; pr < 2; ++pr) {
-          const float2 ax = pr ? hi2(AX) : lo2(AX), ay = pr ? hi2(AY) : lo2(AY), az = pr ? hi2(AZ) : lo2(AZ);
-          const float2 va = pr ? hi2(VA) : lo2(VA);
-          const float2 ys = __fadd2_rn(u2f2(d[0][2 * pr], d[0][2 * pr + 1]), b2s);
-          const float2 yg = __fadd2_rn(u2f2(d[1][2 * pr], d[1][2 * pr + 1]), b2g);
+        for (int e = 0; e < 2; ++e) {
+          const float2 ax = e ? hi2(AX) : lo2(AX), ay = e ? hi2(AY) : lo2(AY), az = e ? hi2(AZ) : lo2(AZ);
+          const float2 va = e ? hi2(VA) : lo2(VA);
+          const float2 ys = __fadd2_rn(u2f2(d[0][2 * e], d[0][2 * e + 1]), b2s);
+          const float2 yg = __fadd2_rn(u2f2(d[1][2 * e], d[1][2 * e + 1]), b2g);
           const float2 ts = tanh2(ys), tg = tanh2(yg);
           const float2 ms = __ffma2_rn(ys, ts, ys);
           const float2 g1 = __ffma2_rn(va, tg, va);  // valid * (1 + tanh): masks self edges and padding
-          const float2 t1 = u2f2(d[2][2 * pr], d[2][2 * pr + 1]);
-          acc[0][pr] = __ffma2_rn(va, ms, acc[0][pr]);
-          acc[1][pr] = __ffma2_rn(g1, __ffma2_rn(ax, t1, u2f2(d[3][2 * pr], d[3][2 * pr + 1])), acc[1][pr]);
-          acc[2][pr] = __ffma2_rn(g1, __ffma2_rn(ay, t1, u2f2(d[4][2 * pr], d[4][2 * pr + 1])), acc[2][pr]);
-          acc[3][pr] = __ffma2_rn(g1, __ffma2_rn(az, t1, u2f2(d[5][2 * pr], d[5][2 * pr + 1])), acc[3][pr]);
+          const float2 t1 = u2f2(d[2][2 * e], d[2][2 * e + 1]);
+          acc[0] = __ffma2_rn(va, ms, acc[0]);
+          acc[1] = __ffma2_rn(g1, __ffma2_rn(ax, t1, u2f2(d[3][2 * e], d[3][2 * e + 1])), acc[1]);
+          acc[2] = __ffma2_rn(g1, __ffma2_rn(ay, t1, u2f2(d[4][2 * e], d[4][2 * e + 1])), acc[2]);
+          acc[3] = __ffma2_rn(g1, __ffma2_rn(az, t1, u2f2(d[5][2 * e], d[5][2 * e + 1])), acc[3]);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_a(bar0 + 8 * (12 + slot));  // gempty[slot]
       if (cur.sb == send_blocks - 1) {
-        // item complete: each group holds the partial sums of its 2 senders per tile for all 4 receivers; group r
-        // collects receiver r.  xch is double buffered by item parity, one named barrier per item.
+        // item complete: the two groups of a receiver pair (sender quads 0 / 1) each hold half of the senders for both
+        // receivers; quad sq keeps receiver 2 rp + sq and hands the other one to its partner.  xch is double
+        // buffered by item parity, one named barrier per item.
         const long long g = cur.item / recv_blocks;
         const int i0 = (int)(cur.item - g * recv_blocks) * kRecv;
-        float* xb = xch + (items_done & 1) * (12 * 4 * n);
-        float own[4] = {0.f, 0.f, 0.f, 0.f};
+        float* xb = xch + (items_done & 1) * (4 * 4 * n);
+        float own[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float v = (r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x;
-            if (r == grp) own[c] = v;
-            else xb[((r * 3 + (grp - (grp > r))) * 4 + c) * n + w] = v;  // slot = source group, skipping r
-          }
+        for (int c = 0; c < 4; ++c) {
+          own[c] = sq ? acc[c].y : acc[c].x;
+          xb[((rp * 2 + (sq ^ 1)) * 4 + c) * n + w] = sq ? acc[c].x : acc[c].y;  // partner's slot
+        }
         named_barrier(1, kComputeThreads);
 #pragma unroll
-        for (int src = 0; src < 3; ++src)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) own[c] += xb[((grp * 3 + src) * 4 + c) * n + w];
-        if (i0 + grp < N) {
-          float* o = agg + (g * N + i0 + grp) * 4 * n;
+        for (int c = 0; c < 4; ++c) own[c] += xb[((rp * 2 + sq) * 4 + c) * n + w];
+        const int r = 2 * rp + sq;
+        if (i0 + r < N) {
+          float* o = agg + (g * N + i0 + r) * 4 * n;
           o[w] = fmaf(own[0], sc_s, add_s);
           o[n + w] = own[1] * sc_v;
           o[2 * n + w] = own[2] * sc_v;
           o[3 * n + w] = own[3] * sc_v;
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = make_float2(0.f, 0.f);
+        for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
         ++items_done;
       }
     };
@@ -579,7 +578,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     }
   } else if (warp == kGeoWarp) {
     // ============================ geometry: lane = tile column ==================================================
-    const int sl = lane >> 2, r = lane & 3;
+    const int sl = (lane >> 1) & 7, r = 2 * (lane >> 4) + (lane & 1);  // column = rp * 16 + sender * 2 + (r & 1)
     for (TileCursor c{(int)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
       const uint32_t t = c.t;
       const int slot = t & (kGeoSlots - 1);
@@ -650,7 +649,7 @@ static int launch_tc(const float* pos, const float* mass, int B, int N, const fl
   constexpr int threads = kWarps * 32;
   const size_t smem = 1024 + (size_t)5 * NMUL * 128 + (size_t)2 * kSend * 4 * 3 * NMUL * sizeof(float) +
                       (size_t)kRecv * 4 * 3 * NMUL * sizeof(float) + (size_t)kGeoSlots * 6 * kCols * sizeof(float) +
-                      (size_t)2 * 12 * 4 * NMUL * sizeof(float) +
+                      (size_t)2 * 4 * 4 * NMUL * sizeof(float) +
                       24 * sizeof(uint64_t) + 16;
   auto kern = edge_layer_tc_kernel<NMUL>;
   {

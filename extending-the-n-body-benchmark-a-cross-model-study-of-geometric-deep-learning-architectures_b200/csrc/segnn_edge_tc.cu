@@ -197,7 +197,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   constexpr int kMmaWarpA = 3, kMmaWarpB = 7, kGeoWarp = 11;
   constexpr int n3 = 3 * n;
   constexpr int kQStageFloats = kSend * 4 * n3;
-  constexpr int kQStageBytes = kQStageFloats * (int)sizeof(float);
   constexpr int kWeightCols = 3 * n;    // TMEM columns of the weight image
   constexpr int kDBase = kWeightCols;   // accumulator tiles start here (6 x 32 columns)
 
@@ -211,7 +210,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 4 * 4 * n);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   uint64_t* full = bars;         // [2] B stage written (all compute threads)
-  uint64_t* empty = bars + 2;    // [2] B stage consumed (both MMA issuers commit)
   uint64_t* dfull = bars + 4;    // accumulators complete (both issuers commit)
   uint64_t* dempty = bars + 5;   // accumulators read out (all compute threads)
   uint64_t* qfull = bars + 6;    // [2] bulk copy landed (expect_tx)
@@ -232,7 +230,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full[i], kComputeThreads);
-      mbar_init(&empty[i], 2);
       mbar_init(&qfull[i], 1);
     }
     mbar_init(dfull, 2);
@@ -264,6 +261,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
+  // staging buffers start as zeros so that rows never written by a (partial) bulk copy are finite
+  for (int i = tid; i < 2 * kQStageFloats + kRecv * 4 * n3; i += kWarps * 32) sQ[i] = 0.f;
+  proxy_fence();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -305,14 +305,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
 
     uint32_t p_items = 0;  // items whose P rows this thread has loaded
-    auto load_p = [&](int item) {
-      const int g = item / recv_blocks;
-      const int i0 = (int)(item - g * recv_blocks) * kRecv;
-      const int nrecv = min(kRecv, N - i0);
+    auto load_p = [&]() {
       mbar_wait_a(bar0 + 8 * 16, p_items & 1);  // pfull: this item's rows have landed
       ++p_items;
-      const float* r0 = sP + min(2 * rp, nrecv - 1) * 4 * n3;  // receivers past the graph end reuse a valid row
-      const float* r1 = sP + min(2 * rp + 1, nrecv - 1) * 4 * n3;
+      const float* r0 = sP + (2 * rp) * 4 * n3;  // rows past the graph end: stale but finite, masked by valid = 0
+      const float* r1 = sP + (2 * rp + 1) * 4 * n3;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -325,9 +322,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     auto produce = [&](const TileCursor& cur) {
       const uint32_t t = cur.t;
       const int st = t & 1, slot = t & (kGeoSlots - 1);
-      const int nvalid = min(kSend, N - cur.sb * kSend);
       mbar_wait_a(bar0 + 8 * (8 + slot), (t / kGeoSlots) & 1);     // gfull[slot]
-      mbar_wait_a(bar0 + 8 * (2 + st), ((t >> 1) & 1) ^ 1);         // empty[st]
+      // B stage st was last read by the MMAs of tile t - 2, whose completion (dfull) this thread observed in
+      // epilogue(t - 2), which precedes produce(t) in program order: no separate "stage empty" barrier is needed.
       mbar_wait_a(bar0 + 8 * (6 + st), (t >> 1) & 1);               // qfull[st]
       const float* qs = sQ + st * kQStageFloats;
       const float* gs = geo + slot * 6 * kCols + 8 * gi;
@@ -343,7 +340,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         for (int e = 0; e < 2; ++e) {
           const int s4 = 2 * h + e;
           const int sl = 4 * sq + s4;
-          const float* qr = qs + min(sl, nvalid - 1) * 4 * n3;  // senders past the graph end reuse a valid row
+          // rows past the graph end hold stale (finite: the buffers are zero-initialised) data, masked by valid = 0
+          const float* qr = qs + sl * 4 * n3;
           float q[12];
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -405,35 +403,34 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       const float* gs = geo + slot * 6 * kCols + 8 * gi;
       mbar_wait_a(bar0 + 8 * 4, t & 1);  // dfull
       tc_fence_after();
+      uint32_t d[6][8];
+#pragma unroll
+      for (int tile = 0; tile < 6; ++tile) SEGNN_TMEM_LD8(tmem + lane_base + kDBase + tile * kCols + 8 * gi, d[tile]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // accumulators are in registers: hand the TMEM tiles back to the MMA warps
+      tc_fence_before();
+      mbar_arrive_a(bar0 + 8 * 5);  // dempty
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int c0 = 8 * gi + 4 * h;
-        uint32_t d[6][4];
-#pragma unroll
-        for (int tile = 0; tile < 6; ++tile) SEGNN_TMEM_LD4(tmem + lane_base + kDBase + tile * kCols + c0, d[tile]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (h == 1) {  // accumulators are in registers: hand the TMEM tiles back to the MMA warps
-          tc_fence_before();
-          mbar_arrive_a(bar0 + 8 * 5);  // dempty
-        }
         const float4 AX = *reinterpret_cast<const float4*>(gs + 0 * kCols + 4 * h);
         const float4 AY = *reinterpret_cast<const float4*>(gs + 1 * kCols + 4 * h);
         const float4 AZ = *reinterpret_cast<const float4*>(gs + 2 * kCols + 4 * h);
         const float4 VA = *reinterpret_cast<const float4*>(gs + 5 * kCols + 4 * h);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
+          const int j = 4 * h + 2 * e;
           const float2 ax = e ? hi2(AX) : lo2(AX), ay = e ? hi2(AY) : lo2(AY), az = e ? hi2(AZ) : lo2(AZ);
           const float2 va = e ? hi2(VA) : lo2(VA);
-          const float2 ys = __fadd2_rn(u2f2(d[0][2 * e], d[0][2 * e + 1]), b2s);
-          const float2 yg = __fadd2_rn(u2f2(d[1][2 * e], d[1][2 * e + 1]), b2g);
+          const float2 ys = __fadd2_rn(u2f2(d[0][j], d[0][j + 1]), b2s);
+          const float2 yg = __fadd2_rn(u2f2(d[1][j], d[1][j + 1]), b2g);
           const float2 ts = tanh2(ys), tg = tanh2(yg);
           const float2 ms = __ffma2_rn(ys, ts, ys);
           const float2 g1 = __ffma2_rn(va, tg, va);  // valid * (1 + tanh): masks self edges and padding
-          const float2 t1 = u2f2(d[2][2 * e], d[2][2 * e + 1]);
+          const float2 t1 = u2f2(d[2][j], d[2][j + 1]);
           acc[0] = __ffma2_rn(va, ms, acc[0]);
-          acc[1] = __ffma2_rn(g1, __ffma2_rn(ax, t1, u2f2(d[3][2 * e], d[3][2 * e + 1])), acc[1]);
-          acc[2] = __ffma2_rn(g1, __ffma2_rn(ay, t1, u2f2(d[4][2 * e], d[4][2 * e + 1])), acc[2]);
-          acc[3] = __ffma2_rn(g1, __ffma2_rn(az, t1, u2f2(d[5][2 * e], d[5][2 * e + 1])), acc[3]);
+          acc[1] = __ffma2_rn(g1, __ffma2_rn(ax, t1, u2f2(d[3][j], d[3][j + 1])), acc[1]);
+          acc[2] = __ffma2_rn(g1, __ffma2_rn(ay, t1, u2f2(d[4][j], d[4][j + 1])), acc[2]);
+          acc[3] = __ffma2_rn(g1, __ffma2_rn(az, t1, u2f2(d[5][j], d[5][j + 1])), acc[3]);
         }
       }
       __syncwarp();
@@ -474,7 +471,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 #pragma unroll 1
     while (ec.item < items) {
       if (pc.item < items) {
-        if (pc.sb == 0) load_p(pc.item);
+        if (pc.sb == 0) load_p();
         produce(pc);
         advance(pc);
       }
@@ -570,10 +567,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
           }
         }
       }
-      if (elect_one()) {
-        tc_commit(&empty[st]);
-        tc_commit(dfull);
-      }
+      if (elect_one()) tc_commit(dfull);
       __syncwarp();
     }
   } else if (warp == kGeoWarp) {

@@ -138,6 +138,85 @@ def workload_config(args, sims_per_gpu):
             "l2_policy": "per-step working set (>1 GB of node projections per layer) exceeds the 126 MB L2"}
 
 
+def measure_training(S, dev, world, rank, dist, cpu_baseline):
+    """Secondary numbers (not the headline metric): BASELINE config 2 -- the README training configuration (SEGNN 6
+    layers / hidden 192 / lmax_h 1, 64 graphs x 5 bodies, fp32 kernels, train-mode BatchNorm, hand-written backward,
+    AdamW + Noam schedule; forward + backward replayed as a CUDA graph; one flat-bucket NCCL all-reduce per step when
+    N > 1) -- and BASELINE config 4 -- one N=1000 graph, hidden 128, forward + backward."""
+    out = {}
+    torch.manual_seed(0)
+    B, N = 64, 5
+    model = S.SEGNN(hidden_features=HIDDEN, num_layers=LAYERS, lmax_h=1).to(dev).train()
+    ts = S.TrainStep(model, B, N, learning_rate_factor=1.0, process_group=None, distributed=world > 1,
+                     use_cuda_graph=True)
+    pos, vel, charge = synthetic_system(B, N, seed=77 + rank)
+    y = torch.randn(B * N, 6)
+    hp, hv, hm, hy = [t.pin_memory() for t in (pos, vel, charge, y)]
+    for _ in range(5):
+        ts.step(hp, hv, hm, hy)
+    steps = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = S.ops.launch_count()
+    e0.record()
+    for _ in range(steps):
+        loss = ts.step(hp, hv, hm, hy)       # H2D of the batch from pinned memory every step
+    loss_host = float(loss)                  # D2H of the loss
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.cpu()) / steps
+    out["cfg2_readme_training"] = {
+        "config": "SEGNN 6 layers hidden 192 lmax_h 1, batch 64 x N=5 per GPU, fp32 kernels, train-mode BatchNorm, "
+                  "AdamW + Noam, fwd+bwd as CUDA graph" + (", DDP flat-bucket all-reduce (NCCL)" if world > 1 else ""),
+        "ms_per_step": ms, "train_steps_per_s": 1e3 / ms, "particle_steps_per_s": world * B * N * 1e3 / ms,
+        "n_gpus": world, "steps": steps, "loss": loss_host,
+        "reference_published": "<= 7.6 train steps/s (BASELINE.md, unrecorded hardware, fp64)"}
+    if rank == 0 and world == 1:
+        torch.manual_seed(0)
+        N4, H4 = 1000, 128
+        m4 = S.SEGNN(hidden_features=H4, num_layers=LAYERS, lmax_h=1).to(dev).train()
+        p4, v4, c4 = synthetic_system(1, N4, seed=5)
+        g = S.GraphBatch(pos=p4.reshape(-1, 3).to(dev), vel=v4.reshape(-1, 3).to(dev), mass=c4.reshape(-1, 1).to(dev),
+                         num_graphs=1, n_nodes=N4)
+        y4 = torch.randn(N4, 6, device=dev)
+        times = []
+        for i in range(3):
+            m4.zero_grad(set_to_none=True)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            S.target_common_loss(m4(g), y4).backward()
+            a1.record()
+            torch.cuda.synchronize()
+            times.append(a0.elapsed_time(a1))
+        out["cfg4_n1000_fwd_bwd"] = {
+            "config": "SEGNN 6 layers hidden 128 lmax_h 1, one N=1000 fully-connected graph (999,000 edges), fp32 "
+                      "kernels, forward + backward with recompute (no per-edge tensor stored)",
+            "ms_fwd_bwd": min(times[1:]), "edge_msgs_fwd_bwd_per_s": 999000 * LAYERS / (min(times[1:]) * 1e-3),
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+        if cpu_baseline:
+            from oracle import segnn_oracle as O
+            torch.set_num_threads(os.cpu_count() or 1)
+            om = O.SEGNN(hidden_features=HIDDEN, num_layers=LAYERS, dtype=torch.float32).train()
+            og = O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), charge.reshape(-1, 1), B, N)
+            opt = torch.optim.AdamW(om.parameters(), weight_decay=1e-8, lr=1e-4, betas=(0.9, 0.98), eps=1e-9)
+            ct = []
+            for i in range(4):
+                t0 = time.perf_counter()
+                opt.zero_grad()
+                O.target_common_loss(om(og), y).backward()
+                opt.step()
+                ct.append(time.perf_counter() - t0)
+            out["cfg2_readme_training"]["cpu_baseline"] = {
+                "train_steps_per_s": 1.0 / min(ct[1:]), "cores": os.cpu_count() or 1, "kind": "port",
+                "sample": "3 timed steps after 1 warm-up, float32, oracle port (explicit edges, autograd)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -148,6 +227,7 @@ def main():
     ap.add_argument("--cpu-sims", type=int, default=4, help="bounded CPU sample: simulations per CPU step")
     ap.add_argument("--mode", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-training", action="store_true", help="skip the secondary training measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -249,6 +329,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms, k3_ms = [float(x) for x in t.cpu()]
+    del roll, roll2
+    training = None
+    if not args.no_training:
+        training = measure_training(S, dev, world, rank, dist if world > 1 else None,
+                                    cpu_baseline=(world == 1 and not args.no_cpu_baseline))
 
     if rank == 0:
         tensor_peak, hbm_peak, peak_src = measured_peaks()
@@ -289,6 +374,8 @@ def main():
                 "value": sims * N / sec, "unit": "particle-steps/s", "cores": cores, "kind": "port",
                 "sample": f"{sims} sims x N={N} x 1 rollout step, 2 timed steps after 1 warm-up, float32, "
                           f"{cores} threads (oracle port of the reference's e3nn/PyG formulation)"}
+        if training is not None:
+            line["training"] = training
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -276,3 +276,39 @@ def test_train_mode_forward_without_grad_matches_oracle():
         out = m(gpu_graph(pos, vel, mass, B, N))
     assert rel(out, ref) < 1e-5
     assert rel(m.layers[0].message_norm.running_var, om.layers[0].message_norm.running_var) < 1e-5
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_loss_trajectory_matches_oracle(use_graph):
+    """Five optimisation steps (AdamW + Noam schedule, trainer.py:170-195) on a fixed batch: the loss trajectory of the
+    CUDA path must follow float64 training of the oracle. (Parameters themselves are not compared: biases in front of
+    a train-mode BatchNorm have exactly-zero true gradients, and Adam turns their fp32 rounding noise into +-lr steps
+    that do not change the function.)"""
+    torch.manual_seed(3)
+    H, L, B, N = 64, 2, 8, 5
+    om = O.SEGNN(hidden_features=H, num_layers=L).train()
+    m = S.SEGNN(hidden_features=H, num_layers=L)
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().train()
+    pos, vel, mass = O.synthetic_system(B, N, seed=7)
+    y = torch.randn(B * N, 6, dtype=torch.float64)
+    hp = dict(learning_rate=1.0, learning_rate_factor=4000.0, learning_rate_warmup_steps=4000)
+    ts = S.TrainStep(m, B, N, use_cuda_graph=use_graph, clip_gradients_norm=10.0, **hp)
+    opt = torch.optim.AdamW(om.parameters(), weight_decay=1e-8, lr=1.0, betas=(0.9, 0.98), eps=1e-9)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: S.noam_rate(s, H, 4000.0, 4000))
+    g = O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N)
+    ref_losses, losses = [], []
+    for _ in range(5):
+        opt.zero_grad()
+        loss = O.target_common_loss(om(g), y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(om.parameters(), 10.0)
+        opt.step()
+        sched.step()
+        ref_losses.append(float(loss))
+        losses.append(float(ts.step(pos, vel, mass, y)))
+    print("loss trajectory", losses, ref_losses)
+    assert ref_losses[-1] < ref_losses[0]
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-4 * abs(b)
+    assert rel(m.layers[0].feature_norm.running_var, om.layers[0].feature_norm.running_var) < 1e-4

@@ -168,3 +168,51 @@ def test_training_orchestration_and_batchnorm_algebra_vs_oracle(bn_train):
     for k, b in m.state_dict().items():
         if "running" in k:
             assert float((sd[k] - b).abs().max()) < 1e-10, k
+
+
+def test_noam_rate_matches_reference_formula():
+    # trainer.py:188-195: factor * size^-0.5 * min(step^-0.5, step * warmup^-1.5); step 0 is treated as step 1
+    assert S.noam_rate(0, 192.0, 1.0, 4000) == S.noam_rate(1, 192.0, 1.0, 4000)
+    assert abs(S.noam_rate(4000, 192.0, 2.0, 4000) - 2.0 * 192 ** -0.5 * 4000 ** -0.5) < 1e-15
+    assert abs(S.noam_rate(10, 64.0, 1.0, 4000) - 64 ** -0.5 * 10 * 4000 ** -1.5) < 1e-18
+    assert S.noam_rate(8000, 64.0) < S.noam_rate(4000, 64.0)
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)  # ranks start from different weights and buffers
+    model = S.SEGNN(hidden_features=16, num_layers=1)
+    S.trainer.broadcast_module_state(model, 0)
+    ref = [p.detach().clone() for p in model.parameters()]
+    for i, p in enumerate(model.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1)) if i != 2 else None  # one parameter without a gradient
+    S.allreduce_gradients(model.parameters())
+    grads = [float(p.grad.reshape(-1)[0]) for p in model.parameters()]
+    gathered = [torch.zeros_like(ref[0]) for _ in range(world)]
+    dist.all_gather(gathered, ref[0])
+    same = all(torch.equal(g, gathered[0]) for g in gathered)
+    if rank == 0:
+        out.put((grads, same))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce():
+    """world_size-2 data-parallel plumbing on CPU: parameters are broadcast from rank 0, gradients are averaged with one
+    flat-bucket all-reduce, a parameter without gradient contributes zeros."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    grads, same = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same
+    for i, g in enumerate(grads):
+        assert g == (0.0 if i == 2 else 1.5 * (i + 1))

@@ -10,21 +10,34 @@ namespace segnn {
 // ------------------------------------------------------------------------------------------------
 // colsum: out[c] = sum_r f(x[r][c], y[r][c]);  mode 0: x, 1: x*x, 2: x*y.  Two deterministic stages.
 // ------------------------------------------------------------------------------------------------
-constexpr int kColsumRowsPerBlock = 256;
+constexpr int kColsumRowsPerBlock = 64;  // rows per partial sum (fixed => the reduction order is deterministic)
+constexpr int kColsumRowLanes = 8;       // threads that share one column inside a block
 
-__global__ void colsum_stage1(const float* __restrict__ x, const float* __restrict__ y, int64_t rows, int cols,
-                              int mode, double* __restrict__ partial) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// block = 32 columns x 8 row lanes; lane ry sums rows r0 + ry, r0 + ry + 8, ...; the 8 lane sums are combined in
+// shared memory in a fixed order.
+__global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ x, const float* __restrict__ y,
+                                                   int64_t rows, int cols, int mode, double* __restrict__ partial) {
+  __shared__ double red[kColsumRowLanes][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   const int64_t r0 = (int64_t)blockIdx.y * kColsumRowsPerBlock;
   const int64_t r1 = min(rows, r0 + kColsumRowsPerBlock);
   // float64 accumulation: BatchNorm statistics feed var = E[x^2] - mean^2 and cancellation-prone gradient sums
   double acc = 0.0;
-  for (int64_t r = r0; r < r1; ++r) {
-    const double v = (double)x[r * cols + c];
-    acc += mode == 0 ? v : (mode == 1 ? v * v : v * (double)y[r * cols + c]);
+  if (c < cols) {
+    for (int64_t r = r0 + ry; r < r1; r += kColsumRowLanes) {
+      const double v = (double)x[r * cols + c];
+      acc += mode == 0 ? v : (mode == 1 ? v * v : v * (double)y[r * cols + c]);
+    }
   }
-  partial[(int64_t)blockIdx.y * cols + c] = acc;
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    double s = red[0][cx];
+#pragma unroll
+    for (int i = 1; i < kColsumRowLanes; ++i) s += red[i][cx];
+    partial[(int64_t)blockIdx.y * cols + c] = s;
+  }
 }
 
 template <typename T>
@@ -286,9 +299,9 @@ int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mod
   SEGNN_CHECK_ARG(x && workspace && (mode != 2 || y), "null pointer");
   const int64_t parts = (rows + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock;
   SEGNN_CHECK_ARG(parts <= 65535, "too many rows for one colsum call");
-  dim3 grid((cols + 127) / 128, (unsigned)parts);
+  dim3 grid((cols + 31) / 32, (unsigned)parts);
   double* partial = reinterpret_cast<double*>(workspace);
-  colsum_stage1<<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, rows, cols, mode, partial);
+  colsum_stage1<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, rows, cols, mode, partial);
   colsum_stage2<double><<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, (int)parts, cols, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
@@ -327,12 +340,23 @@ int segnn_tp_combine_bwd(const float* y, const float* node_attr, int nodes, int 
   return SEGNN_OK;
 }
 
-int64_t segnn_node_gemm_wgrad_workspace(int nodes, int K, int n_out) {
+// Row slabs of the weight-gradient GEMM: enough CTAs to fill the GPU even for a few hundred nodes (the README training
+// batch has 320), at least 32 rows per slab, at most 64 slabs. Depends on the sizes only => deterministic.
+static int64_t wgrad_slabs(int nodes, int K, int n_out) {
   const int64_t rows = (int64_t)nodes * 3;
-  int64_t slabs = (rows + 4095) / 4096;
+  const int64_t tiles = (int64_t)((K + kWgTile - 1) / kWgTile) * ((n_out + kWgTile - 1) / kWgTile);
+  int64_t slabs = (2 * 148 + tiles - 1) / tiles;
+  const int64_t by_rows = (rows + 4095) / 4096;
+  if (slabs < by_rows) slabs = by_rows;
+  const int64_t max_by_rows = (nodes + kWgRows - 1) / kWgRows;  // the scalar class has `nodes` rows
+  if (slabs > max_by_rows) slabs = max_by_rows;
   if (slabs > 64) slabs = 64;
   if (slabs < 1) slabs = 1;
-  return slabs * (int64_t)K * n_out * (int64_t)sizeof(float);
+  return slabs;
+}
+
+int64_t segnn_node_gemm_wgrad_workspace(int nodes, int K, int n_out) {
+  return wgrad_slabs(nodes, K, n_out) * (int64_t)K * n_out * (int64_t)sizeof(float);
 }
 
 int segnn_node_gemm_wgrad(const float* x0, const float* x1, const float* dy0, const float* dy1, int split, int nodes,
@@ -350,9 +374,7 @@ int segnn_node_gemm_wgrad(const float* x0, const float* x1, const float* dy0, co
   SEGNN_CHECK_ARG(split > 0 && split <= n_out, "split out of range");
   for (int cls = 0; cls < 2; ++cls) {
     const int64_t rows = cls == 0 ? (int64_t)nodes : (int64_t)nodes * 3;
-    int64_t slabs = ((int64_t)nodes * 3 + 4095) / 4096;  // same count as the workspace query
-    if (slabs > 64) slabs = 64;
-    if (slabs < 1) slabs = 1;
+    const int64_t slabs = wgrad_slabs(nodes, K, n_out);  // same count as the workspace query
     const int64_t per = ((rows + slabs - 1) / slabs + kWgRows - 1) / kWgRows * kWgRows;
     dim3 grid((K + kWgTile - 1) / kWgTile, (n_out + kWgTile - 1) / kWgTile, (unsigned)slabs);
     node_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, x1, dy0, dy1, split, nodes, n_in, n_out, cls, per,

@@ -245,6 +245,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout for the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     mode = args.mode
     if mode == "auto":

@@ -24,10 +24,13 @@
 //     constants are folded: pre-activations are carried as z/2 (the 1/2 is folded into the weights), the gate
 //     outputs as z/2 * (1 + tanh(z/2)) and (1 + tanh(z/2)), and c_silu, c_sig/2 are folded into the
 //     message_layer_2 weight image / the final per-receiver scale.
-//   warp 3:  MMA issuer A (tiles s, g) + TMEM allocation + cp.async.bulk of the sender rows of Q (36 KB per tile at
-//            n = 96, double buffered, issued two tiles ahead);
-//   warp 7:  MMA issuer B (tiles T1, D_x, D_y, D_z)   [one warp sustains ~1 MMA / 24 clk, the pipe needs 1 / 16 clk];
-//   warp 11: geometry (lane = column): unit vectors, distances, mass products, validity of tile t + 1.. into a ring.
+//   The fourth SM sub-partition (warp % 4 == 3) owns no TMEM lane quadrant at n <= 96; it hosts
+//   warp 3:  MMA issuer + TMEM allocation + cp.async.bulk of the sender rows of Q (36 KB per tile at n = 96, double
+//            buffered, two tiles ahead) and of the item's 4 receiver rows of P + the tile geometry (lane = column:
+//            unit vectors, distances, mass products, validity; 4-slot ring, two tiles ahead);
+//   warps 7, 11, 15: scalar-channel producers (channel blocks 0, 1, 2): the s' plane of the B tile needs only the
+//            (0s) parts of P and Q, so it is produced here for all 32 columns, which moves 22% of the producer
+//            instructions off the three compute sub-partitions.
 // Synchronisation is mbarrier-only between roles; every wait is bounded and traps instead of hanging.
 #include <cuda_bf16.h>
 
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   static_assert(NW >= 1 && NW <= 3, "warp % 4 == 3 hosts the MMA / geometry warps");
   constexpr int kComputeThreads = 4 * NW * 32;
   constexpr int kComputeWarps = 4 * NW;
-  constexpr int kMmaWarpA = 3, kMmaWarpB = 7, kGeoWarp = 11;
+  constexpr int kScalarWarps = NW;      // warps 7, 11, 15: scalar-channel producers of channel blocks 0, 1, 2
+  constexpr int kMmaWarp = 3;           // MMA issuer + bulk copies + tile geometry (lane = column)
   constexpr int n3 = 3 * n;
   constexpr int kQStageFloats = kSend * 4 * n3;
   constexpr int kWeightCols = 3 * n;    // TMEM columns of the weight image
@@ -209,35 +213,38 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   float* xch = geo + kGeoSlots * 6 * kCols;                            // [2][4 groups][4 comp][n]
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 4 * 4 * n);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  uint64_t* full = bars;         // [2] B stage written (all compute threads)
-  uint64_t* dfull = bars + 4;    // accumulators complete (both issuers commit)
+  uint64_t* full = bars;         // [2] B stage written (all compute + scalar-producer threads)
+  uint64_t* empty = bars + 2;    // [2] B stage consumed (tcgen05.commit; only the scalar producers need it)
+  uint64_t* dfull = bars + 4;    // accumulators complete (tcgen05.commit)
   uint64_t* dempty = bars + 5;   // accumulators read out (all compute threads)
   uint64_t* qfull = bars + 6;    // [2] bulk copy landed (expect_tx)
   uint64_t* gfull = bars + 8;    // [kGeoSlots] geometry written
-  uint64_t* gempty = bars + 12;  // [kGeoSlots] geometry consumed (one arrival per compute warp)
+  uint64_t* gempty = bars + 12;  // [kGeoSlots] geometry consumed (one arrival per compute / scalar-producer warp)
   uint64_t* pfull = bars + 16;   // receiver rows of P landed (expect_tx)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int cb = warp & 3, grp = warp >> 2;
   const bool is_compute = cb < NW;
+  const bool is_scalar = cb == 3 && grp >= 1 && grp - 1 < NW;
 
-  if (warp == kMmaWarpA) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], kComputeThreads);
+      mbar_init(&full[i], kComputeThreads + kScalarWarps * 32);
+      mbar_init(&empty[i], 1);
       mbar_init(&qfull[i], 1);
     }
-    mbar_init(dfull, 2);
+    mbar_init(dfull, 1);
     mbar_init(pfull, 1);
     mbar_init(dempty, kComputeThreads);
     for (int i = 0; i < kGeoSlots; ++i) {
       mbar_init(&gfull[i], 1);
-      mbar_init(&gempty[i], kComputeWarps);
+      mbar_init(&gempty[i], kComputeWarps + kScalarWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -245,6 +252,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // The CTA owns all 512 TMEM columns, so the allocation starts at lane 0 / column 0.  The MMA issuer relies on it
+  // (compile-time TMEM addresses keep every tcgen05.mma operand in uniform registers); fail loudly otherwise.
+  if (tmem != 0u) {
+    if (err_flag) atomicExch(err_flag, 2);
+    __trap();
+  }
 
   // ---- message_layer_2 weights -> TMEM (lane = output channel, 2 bf16 of K per column) ------------------------
   if (is_compute && grp == 0) {  // lanes >= n are never read back
@@ -284,8 +297,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     const int w = cb * 32 + lane;  // channel = B-tile row (producer role) = TMEM lane (epilogue role)
     const uint32_t lane_base = (uint32_t)(cb * 32) << 16;
     const uint32_t bar0 = smem_u32(bars);  // barrier addresses: bar0 + 8 * index
-    const float2 wd0s = bc2(0.5f * w_edge1[w]), wd0g = bc2(0.5f * w_edge1[n + w]), wm0s = bc2(0.5f * w_edge1[2 * n + w]),
-                 wm0g = bc2(0.5f * w_edge1[3 * n + w]), wd1 = bc2(w_edge1[4 * n + w]), wm1 = bc2(w_edge1[5 * n + w]);
+    const float2 wd0g = bc2(0.5f * w_edge1[n + w]), wm0g = bc2(0.5f * w_edge1[3 * n + w]), wd1 = bc2(w_edge1[4 * n + w]),
+                 wm1 = bc2(w_edge1[5 * n + w]);
     const float2 b2s = bc2(0.5f * b2[w]), b2g = bc2(0.5f * b2[n + w]);
     const float2 half2v = bc2(0.5f);
     float sc_s = kCSilu, sc_v = 0.5f * kCSig, add_s = 0.f;
@@ -313,7 +326,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int part = 0; part < 3; ++part) {
+        for (int part = 1; part < 3; ++part) {
           const float sc = part < 2 ? 0.5f : 1.0f;
           P[c * 3 + part] = make_float2(sc * r0[c * n3 + part * n + w], sc * r1[c * n3 + part * n + w]);
         }
@@ -346,21 +359,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int part = 0; part < 3; ++part) q[c * 3 + part] = qr[c * n3 + part * n + w];
+            for (int part = 1; part < 3; ++part) q[c * 3 + part] = qr[c * n3 + part * n + w];
           const float2 ax = e ? hi2(AX) : lo2(AX), ay = e ? hi2(AY) : lo2(AY), az = e ? hi2(AZ) : lo2(AZ);
           const float2 le = e ? hi2(LE) : lo2(LE), mm = e ? hi2(MM) : lo2(MM);
           // half pre-activations of the scalar / gate channels: (P0 + Q0)/2 + a.(P0k + Q0k)/2 + |r| wd/2 + m_i m_j wm/2
-          float2 hs = __ffma2_rn(bc2(q[0]), half2v, P[0]);
+          // (the scalar channel s' is produced by the scalar-producer warps on the fourth SM sub-partition)
           float2 hg = __ffma2_rn(bc2(q[1]), half2v, P[1]);
-          hs = __ffma2_rn(ax, __ffma2_rn(bc2(q[3]), half2v, P[3]), hs);
           hg = __ffma2_rn(ax, __ffma2_rn(bc2(q[4]), half2v, P[4]), hg);
-          hs = __ffma2_rn(ay, __ffma2_rn(bc2(q[6]), half2v, P[6]), hs);
           hg = __ffma2_rn(ay, __ffma2_rn(bc2(q[7]), half2v, P[7]), hg);
-          hs = __ffma2_rn(az, __ffma2_rn(bc2(q[9]), half2v, P[9]), hs);
           hg = __ffma2_rn(az, __ffma2_rn(bc2(q[10]), half2v, P[10]), hg);
-          hs = __ffma2_rn(le, wd0s, hs);
           hg = __ffma2_rn(le, wd0g, hg);
-          hs = __ffma2_rn(mm, wm0s, hs);
           hg = __ffma2_rn(mm, wm0g, hg);
           float2 tt = __fadd2_rn(P[2], bc2(q[2]));
           tt = __ffma2_rn(le, wd1, tt);
@@ -368,15 +376,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
           const float2 zx = __ffma2_rn(ax, tt, __fadd2_rn(P[5], bc2(q[5])));
           const float2 zy = __ffma2_rn(ay, tt, __fadd2_rn(P[8], bc2(q[8])));
           const float2 zz = __ffma2_rn(az, tt, __fadd2_rn(P[11], bc2(q[11])));
-          const float2 ts = tanh2(hs), tg = tanh2(hg);
-          const float2 so = __ffma2_rn(hs, ts, hs);   // silu(z) / c = z/2 (1 + tanh(z/2))
+          const float2 tg = tanh2(hg);
           const float2 vx = __ffma2_rn(tg, zx, zx);   // 2 sigmoid(z_g) z_v
           const float2 vy = __ffma2_rn(tg, zy, zy);
           const float2 vz = __ffma2_rn(tg, zz, zz);
           float2 dt = __fmul2_rn(ax, vx);
           dt = __ffma2_rn(ay, vy, dt);
           dt = __ffma2_rn(az, vz, dt);
-          packed[s4][0] = pack_bf16x2(so.x, so.y);
           packed[s4][1] = pack_bf16x2(dt.x, dt.y);
           packed[s4][2] = pack_bf16x2(vx.x, vx.y);
           packed[s4][3] = pack_bf16x2(vy.x, vy.y);
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       // 128B swizzle: 8 consecutive rows hit 8 distinct chunks)
       const int chunk = st * 4 + gi;
 #pragma unroll
-      for (int p = 0; p < 5; ++p) {
+      for (int p = 1; p < 5; ++p) {
         const int row = p * n + w;
         *reinterpret_cast<uint4*>(sB + row * 128 + ((chunk ^ (row & 7)) << 4)) =
             make_uint4(packed[0][p], packed[1][p], packed[2][p], packed[3][p]);
@@ -481,16 +487,86 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       }
       primed = true;
     }
-  } else if (warp == kMmaWarpA || warp == kMmaWarpB) {
-    // ============================ MMA issuers ================================================================
-    // Warp-uniform loops; only the tcgen05 instructions sit under elect.sync so descriptors stay in uniform registers.
-    const bool is_a = warp == kMmaWarpA;
+  } else if (is_scalar) {
+    // ============================ scalar-channel producers (4th SM sub-partition) ===============================
+    // s' = silu-gate of the l=0 "scalar" pre-activation needs only the (0s) parts of P and Q; it is independent of
+    // the gate / vector pipeline, so three warps on the sub-partition that owns no TMEM lane quadrant produce plane 0
+    // of the B tile for all 32 columns: 22% of the producer instructions leave the three compute sub-partitions.
+    const int w = (grp - 1) * 32 + lane;
+    const uint32_t bar0 = smem_u32(bars);
+    const float2 wd0s = bc2(0.5f * w_edge1[w]), wm0s = bc2(0.5f * w_edge1[2 * n + w]);
+    const float2 half2v = bc2(0.5f);
+    float2 Ps[4][2];  // [plane][receiver pair], factor 1/2 folded
+    uint32_t p_items = 0;
+    for (TileCursor c{(int)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
+      const uint32_t t = c.t;
+      const int st = t & 1, slot = t & (kGeoSlots - 1);
+      if (c.sb == 0) {
+        mbar_wait_a(bar0 + 8 * 16, p_items & 1);  // pfull
+        ++p_items;
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl)
+#pragma unroll
+          for (int rp = 0; rp < 2; ++rp)
+            Ps[pl][rp] = make_float2(0.5f * sP[(2 * rp) * 4 * n3 + pl * n3 + w], 0.5f * sP[(2 * rp + 1) * 4 * n3 + pl * n3 + w]);
+      }
+      mbar_wait_a(bar0 + 8 * (8 + slot), (t / kGeoSlots) & 1);  // gfull[slot]
+      mbar_wait_a(bar0 + 8 * (6 + st), (t >> 1) & 1);            // qfull[st]
+      mbar_wait_a(bar0 + 8 * (2 + st), ((t >> 1) & 1) ^ 1);      // empty[st]: MMAs of tile t - 2 have read the stage
+      const float* qs = sQ + st * kQStageFloats;
+      const float* gs = geo + slot * 6 * kCols;
+#pragma unroll
+      for (int sq = 0; sq < 2; ++sq) {
+        uint32_t packed[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 G[2][5];
+#pragma unroll
+          for (int rp = 0; rp < 2; ++rp)
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+              G[rp][a] = *reinterpret_cast<const float4*>(gs + a * kCols + 8 * (rp * 2 + sq) + 4 * h);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int s4 = 2 * h + e;
+            const float* qr = qs + (4 * sq + s4) * 4 * n3;
+            const float q0 = qr[w], qx = qr[n3 + w], qy = qr[2 * n3 + w], qz = qr[3 * n3 + w];
+#pragma unroll
+            for (int rp = 0; rp < 2; ++rp) {
+              const float2 ax = e ? hi2(G[rp][0]) : lo2(G[rp][0]), ay = e ? hi2(G[rp][1]) : lo2(G[rp][1]);
+              const float2 az = e ? hi2(G[rp][2]) : lo2(G[rp][2]), le = e ? hi2(G[rp][3]) : lo2(G[rp][3]);
+              const float2 mm = e ? hi2(G[rp][4]) : lo2(G[rp][4]);
+              float2 hs = __ffma2_rn(bc2(q0), half2v, Ps[0][rp]);
+              hs = __ffma2_rn(ax, __ffma2_rn(bc2(qx), half2v, Ps[1][rp]), hs);
+              hs = __ffma2_rn(ay, __ffma2_rn(bc2(qy), half2v, Ps[2][rp]), hs);
+              hs = __ffma2_rn(az, __ffma2_rn(bc2(qz), half2v, Ps[3][rp]), hs);
+              hs = __ffma2_rn(le, wd0s, hs);
+              hs = __ffma2_rn(mm, wm0s, hs);
+              const float2 so = __ffma2_rn(hs, tanh2(hs), hs);  // silu(z) / c = z/2 (1 + tanh(z/2))
+              packed[rp][s4] = pack_bf16x2(so.x, so.y);
+            }
+          }
+        }
+#pragma unroll
+        for (int rp = 0; rp < 2; ++rp) {
+          const int chunk = st * 4 + rp * 2 + sq;
+          *reinterpret_cast<uint4*>(sB + w * 128 + ((chunk ^ (w & 7)) << 4)) =
+              make_uint4(packed[rp][0], packed[rp][1], packed[rp][2], packed[rp][3]);
+        }
+      }
+      proxy_fence();
+      mbar_arrive_a(bar0 + 8 * st);  // full[st]
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(bar0 + 8 * (12 + slot));  // gempty[slot]
+    }
+  } else if (warp == kMmaWarp) {
+    // ============================ MMA issuer ==================================================================
+    // Warp-uniform loop; only the tcgen05 instructions sit under elect.sync so descriptors stay in uniform registers.
     const uint32_t idesc = make_idesc();
-    const uint32_t sB_addr = __shfl_sync(0xffffffffu, smem_u32(sB), 0);
-    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint64_t bdesc0 = make_b_desc(sB_addr);
+    const uint32_t tm = 0u;  // checked above
+    const uint64_t bdesc0 = make_b_desc(smem_u32(sB));
     const uint32_t d0 = tm + kDBase;
-    // bulk copy of the 8 sender rows of tile (item, sb) into Q stage st (issuer A, one elected lane)
+    // bulk copy of the 8 sender rows of tile (item, sb) into Q stage st (one elected lane)
     auto load_q = [&](const TileCursor& c, int st) {
       if (c.item < items && elect_one()) {
         const long long g = c.item / recv_blocks;
@@ -506,7 +582,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       }
       __syncwarp();
     };
-    // bulk copy of the (up to) 4 receiver rows of P of an item into P buffer `buf` (issuer A, one elected lane)
+    // bulk copy of the (up to) 4 receiver rows of P of an item (one elected lane)
     auto load_prow = [&](int item) {
       if (item < items && elect_one()) {
         const long long g = item / recv_blocks;
@@ -522,42 +598,75 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       }
       __syncwarp();
     };
+    // geometry of a tile (lane = column = rp * 16 + sender * 2 + (r & 1)): loads first, ring write later, so the
+    // global-load latency hides behind the MMA issue block
+    const int gsl = (lane >> 1) & 7, gr = 2 * (lane >> 4) + (lane & 1);
+    float gx = 0.f, gy = 0.f, gz = 0.f, gmm = 0.f;
+    bool gvalid = false;
+    auto geo_load = [&](const TileCursor& c) {
+      if (c.item < items) {
+        const long long g = c.item / recv_blocks;
+        const int i0 = (int)(c.item - g * recv_blocks) * kRecv;
+        const int jj = c.sb * kSend + gsl, ii = i0 + gr;
+        const long long js = g * N + min(jj, N - 1), is = g * N + min(ii, N - 1);
+        gx = pos[js * 3 + 0] - pos[is * 3 + 0];
+        gy = pos[js * 3 + 1] - pos[is * 3 + 1];
+        gz = pos[js * 3 + 2] - pos[is * 3 + 2];
+        gmm = mass[js] * mass[is];
+        gvalid = (jj < N) && (ii < N) && (jj != ii);
+      }
+    };
+    auto geo_store = [&](const TileCursor& c) {
+      if (c.item < items) {
+        const uint32_t t = c.t;
+        const int slot = t & (kGeoSlots - 1);
+        float ux, uy, uz, len;
+        unit_vec(gx, gy, gz, ux, uy, uz, len);
+        mbar_wait(&gempty[slot], ((t / kGeoSlots) & 1) ^ 1, err_flag);
+        float* gs = geo + slot * 6 * kCols;
+        gs[0 * kCols + lane] = kY1 * ux;
+        gs[1 * kCols + lane] = kY1 * uy;
+        gs[2 * kCols + lane] = kY1 * uz;
+        gs[3 * kCols + lane] = len;
+        gs[4 * kCols + lane] = gmm;
+        gs[5 * kCols + lane] = gvalid ? 1.0f : 0.0f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gfull[slot]);
+      }
+    };
     TileCursor pf{(int)blockIdx.x, 0, 0u};  // tile two ahead of the current one
-    if (is_a) {
-      load_prow(blockIdx.x);
-      load_q(pf, 0);
-      advance(pf);
-      load_q(pf, 1);
-      advance(pf);
+    TileCursor gc{(int)blockIdx.x, 0, 0u};  // geometry cursor, two tiles ahead as well
+    load_prow(blockIdx.x);
+    load_q(pf, 0);
+    advance(pf);
+    load_q(pf, 1);
+    advance(pf);
+    for (int i = 0; i < 2; ++i) {
+      geo_load(gc);
+      geo_store(gc);
+      advance(gc);
     }
     for (TileCursor c{(int)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
       const uint32_t t = c.t;
       const int st = t & 1;
+      geo_load(gc);  // positions of tile t + 2
       mbar_wait(&full[st], (t >> 1) & 1, err_flag);
-      if (is_a) {  // producers are done with Q stage st: refill it for tile t + 2
-        load_q(pf, st);
-        advance(pf);
-        // every compute thread now holds this item's P rows in registers: fetch the next item's (single buffer)
-        if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
-      }
+      // producers are done with Q stage st: refill it for tile t + 2; every producer thread now holds this item's P
+      // rows in registers: fetch the next item's (single buffer)
+      load_q(pf, st);
+      advance(pf);
+      if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
       mbar_wait(dempty, (t & 1) ^ 1, err_flag);
       tc_fence_after();
       const uint64_t bst = bdesc0 + (uint64_t)(st * (64 >> 4));  // column half of the swizzled rows
-      if (is_a) {
+      if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < 2 * n / 16; ++s) {
           // rows [16 s, 16 s + 16) of the (s', dot) planes; 16 rows = 2048 bytes
           const uint64_t b_sd = bst + (uint64_t)(s * (2048 >> 4));
-          if (elect_one()) {
-            mma_ts(d0 + 0 * kCols, tm + 0 * n + s * 8, b_sd, idesc, s > 0);
-            mma_ts(d0 + 1 * kCols, tm + 1 * n + s * 8, b_sd, idesc, s > 0);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int s = 0; s < n / 16; ++s) {
-          const uint64_t b_sd = bst + (uint64_t)(s * (2048 >> 4));
-          if (elect_one()) {
+          mma_ts(d0 + 0 * kCols, tm + 0 * n + s * 8, b_sd, idesc, s > 0);
+          mma_ts(d0 + 1 * kCols, tm + 1 * n + s * 8, b_sd, idesc, s > 0);
+          if (s < n / 16) {
             mma_ts(d0 + 2 * kCols, tm + 2 * n + s * 8, b_sd, idesc, s > 0);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -566,41 +675,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
             }
           }
         }
+        tc_commit(&empty[st]);
+        tc_commit(dfull);
       }
-      if (elect_one()) tc_commit(dfull);
       __syncwarp();
-    }
-  } else if (warp == kGeoWarp) {
-    // ============================ geometry: lane = tile column ==================================================
-    const int sl = (lane >> 1) & 7, r = 2 * (lane >> 4) + (lane & 1);  // column = rp * 16 + sender * 2 + (r & 1)
-    for (TileCursor c{(int)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
-      const uint32_t t = c.t;
-      const int slot = t & (kGeoSlots - 1);
-      const long long g = c.item / recv_blocks;
-      const int i0 = (int)(c.item - g * recv_blocks) * kRecv;
-      const int jj = c.sb * kSend + sl, ii = i0 + r;
-      const long long js = g * N + min(jj, N - 1), is = g * N + min(ii, N - 1);
-      float ux, uy, uz, len;
-      unit_vec(pos[js * 3 + 0] - pos[is * 3 + 0], pos[js * 3 + 1] - pos[is * 3 + 1], pos[js * 3 + 2] - pos[is * 3 + 2],
-               ux, uy, uz, len);
-      const float mm = mass[js] * mass[is];
-      const bool valid = (jj < N) && (ii < N) && (jj != ii);
-      mbar_wait(&gempty[slot], ((t / kGeoSlots) & 1) ^ 1, err_flag);
-      float* gs = geo + slot * 6 * kCols;
-      gs[0 * kCols + lane] = kY1 * ux;
-      gs[1 * kCols + lane] = kY1 * uy;
-      gs[2 * kCols + lane] = kY1 * uz;
-      gs[3 * kCols + lane] = len;
-      gs[4 * kCols + lane] = mm;
-      gs[5 * kCols + lane] = valid ? 1.0f : 0.0f;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gfull[slot]);
+      geo_store(gc);  // tile t + 2
+      advance(gc);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarpA) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
 }

@@ -178,6 +178,20 @@ __device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); 
 __device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
 __device__ __forceinline__ float2 u2f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
+// ---- optional timeline tracing (compile with -DSEGNN_K3_TRACE; csrc/experiments/k3_trace.py reads the buffer) --------
+#ifdef SEGNN_K3_TRACE
+__device__ long long* g_k3_trace = nullptr;  // [16 warps][64 tiles][8 events]
+#define K3_TRACE(ev, t)                                                                           \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) < 64u && g_k3_trace != nullptr)        \
+      g_k3_trace[((threadIdx.x >> 5) * 64 + (t)) * 8 + (ev)] = clock64();                          \
+  } while (0)
+#else
+#define K3_TRACE(ev, t) \
+  do {                  \
+  } while (0)
+#endif
+
 struct TileCursor {
   int item;
   int sb;
@@ -335,10 +349,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     auto produce = [&](const TileCursor& cur) {
       const uint32_t t = cur.t;
       const int st = t & 1, slot = t & (kGeoSlots - 1);
+      K3_TRACE(0, t);
       mbar_wait_a(bar0 + 8 * (8 + slot), (t / kGeoSlots) & 1);     // gfull[slot]
       // B stage st was last read by the MMAs of tile t - 2, whose completion (dfull) this thread observed in
       // epilogue(t - 2), which precedes produce(t) in program order: no separate "stage empty" barrier is needed.
       mbar_wait_a(bar0 + 8 * (6 + st), (t >> 1) & 1);               // qfull[st]
+      K3_TRACE(1, t);
       const float* qs = sQ + st * kQStageFloats;
       const float* gs = geo + slot * 6 * kCols + 8 * gi;
       uint32_t packed[4][5];
@@ -400,6 +416,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       }
       proxy_fence();
       mbar_arrive_a(bar0 + 8 * st);  // full[st]
+      K3_TRACE(2, t);
     };
 
     uint32_t items_done = 0;
@@ -408,6 +425,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       const int slot = t & (kGeoSlots - 1);
       const float* gs = geo + slot * 6 * kCols + 8 * gi;
       mbar_wait_a(bar0 + 8 * 4, t & 1);  // dfull
+      K3_TRACE(3, t);
       tc_fence_after();
       uint32_t d[6][8];
 #pragma unroll
@@ -416,6 +434,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       // accumulators are in registers: hand the TMEM tiles back to the MMA warps
       tc_fence_before();
       mbar_arrive_a(bar0 + 8 * 5);  // dempty
+      K3_TRACE(4, t);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float4 AX = *reinterpret_cast<const float4*>(gs + 0 * kCols + 4 * h);
@@ -441,6 +460,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_a(bar0 + 8 * (12 + slot));  // gempty[slot]
+      K3_TRACE(5, t);
       if (cur.sb == send_blocks - 1) {
         // item complete: the two groups of a receiver pair (sender quads 0 / 1) each hold half of the senders for both
         // receivers; quad sq keeps receiver 2 rp + sq and hands the other one to its partner.  xch is double
@@ -510,9 +530,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
           for (int rp = 0; rp < 2; ++rp)
             Ps[pl][rp] = make_float2(0.5f * sP[(2 * rp) * 4 * n3 + pl * n3 + w], 0.5f * sP[(2 * rp + 1) * 4 * n3 + pl * n3 + w]);
       }
+      K3_TRACE(0, t);
       mbar_wait_a(bar0 + 8 * (8 + slot), (t / kGeoSlots) & 1);  // gfull[slot]
       mbar_wait_a(bar0 + 8 * (6 + st), (t >> 1) & 1);            // qfull[st]
       mbar_wait_a(bar0 + 8 * (2 + st), ((t >> 1) & 1) ^ 1);      // empty[st]: MMAs of tile t - 2 have read the stage
+      K3_TRACE(1, t);
       const float* qs = sQ + st * kQStageFloats;
       const float* gs = geo + slot * 6 * kCols;
 #pragma unroll
@@ -556,6 +578,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       }
       proxy_fence();
       mbar_arrive_a(bar0 + 8 * st);  // full[st]
+      K3_TRACE(2, t);
       __syncwarp();
       if (lane == 0) mbar_arrive_a(bar0 + 8 * (12 + slot));  // gempty[slot]
     }
@@ -601,18 +624,22 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     // geometry of a tile (lane = column = rp * 16 + sender * 2 + (r & 1)): loads first, ring write later, so the
     // global-load latency hides behind the MMA issue block
     const int gsl = (lane >> 1) & 7, gr = 2 * (lane >> 4) + (lane & 1);
-    float gx = 0.f, gy = 0.f, gz = 0.f, gmm = 0.f;
+    float gsx = 0.f, gsy = 0.f, gsz = 0.f, gsm = 0.f, grx = 0.f, gry = 0.f, grz = 0.f, grm = 0.f;  // raw loads
     bool gvalid = false;
-    auto geo_load = [&](const TileCursor& c) {
+    auto geo_load = [&](const TileCursor& c) {  // issues the loads only: nothing here waits for them
       if (c.item < items) {
         const long long g = c.item / recv_blocks;
         const int i0 = (int)(c.item - g * recv_blocks) * kRecv;
         const int jj = c.sb * kSend + gsl, ii = i0 + gr;
         const long long js = g * N + min(jj, N - 1), is = g * N + min(ii, N - 1);
-        gx = pos[js * 3 + 0] - pos[is * 3 + 0];
-        gy = pos[js * 3 + 1] - pos[is * 3 + 1];
-        gz = pos[js * 3 + 2] - pos[is * 3 + 2];
-        gmm = mass[js] * mass[is];
+        gsx = pos[js * 3 + 0];
+        gsy = pos[js * 3 + 1];
+        gsz = pos[js * 3 + 2];
+        gsm = mass[js];
+        grx = pos[is * 3 + 0];
+        gry = pos[is * 3 + 1];
+        grz = pos[is * 3 + 2];
+        grm = mass[is];
         gvalid = (jj < N) && (ii < N) && (jj != ii);
       }
     };
@@ -621,7 +648,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         const uint32_t t = c.t;
         const int slot = t & (kGeoSlots - 1);
         float ux, uy, uz, len;
-        unit_vec(gx, gy, gz, ux, uy, uz, len);
+        unit_vec(gsx - grx, gsy - gry, gsz - grz, ux, uy, uz, len);
+        const float gmm = gsm * grm;
         mbar_wait(&gempty[slot], ((t / kGeoSlots) & 1) ^ 1, err_flag);
         float* gs = geo + slot * 6 * kCols;
         gs[0 * kCols + lane] = kY1 * ux;
@@ -646,17 +674,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       geo_store(gc);
       advance(gc);
     }
+    geo_load(gc);  // tile 2: stored at the end of iteration 0
     for (TileCursor c{(int)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
       const uint32_t t = c.t;
       const int st = t & 1;
-      geo_load(gc);  // positions of tile t + 2
+      K3_TRACE(0, t);
+      // critical path first: the tile's 48 MMAs as soon as its B stage is written and the accumulators are free
       mbar_wait(&full[st], (t >> 1) & 1, err_flag);
-      // producers are done with Q stage st: refill it for tile t + 2; every producer thread now holds this item's P
-      // rows in registers: fetch the next item's (single buffer)
-      load_q(pf, st);
-      advance(pf);
-      if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
+      K3_TRACE(1, t);
       mbar_wait(dempty, (t & 1) ^ 1, err_flag);
+      K3_TRACE(2, t);
       tc_fence_after();
       const uint64_t bst = bdesc0 + (uint64_t)(st * (64 >> 4));  // column half of the swizzled rows
       if (elect_one()) {
@@ -679,8 +706,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         tc_commit(dfull);
       }
       __syncwarp();
-      geo_store(gc);  // tile t + 2
+      K3_TRACE(3, t);
+      // housekeeping off the critical path: producers are done with Q stage st (full[st] observed): refill it for tile
+      // t + 2; every producer thread holds this item's P rows in registers: fetch the next item's (single buffer);
+      // geometry of tile t + 2 into the ring, loads of tile t + 3 in flight until the next iteration
+      load_q(pf, st);
+      advance(pf);
+      if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
+      geo_store(gc);
       advance(gc);
+      geo_load(gc);
+      K3_TRACE(4, t);
     }
   }
 
@@ -771,6 +807,14 @@ int edge_layer_tc(const float* pos, const float* mass, int B, int N, int n, cons
             "64/128/192), got n=%d", n);
   return SEGNN_E_UNSUPPORTED;
 }
+
+#ifdef SEGNN_K3_TRACE
+}  // namespace segnn
+extern "C" int segnn_debug_set_k3_trace(long long* buf) {
+  return (int)cudaMemcpyToSymbol(segnn::tc::g_k3_trace, &buf, sizeof(buf));
+}
+namespace segnn {
+#endif
 
 int64_t pack_w2_tc(const float* ss, const float* vs, const float* sv, const float* vv, int n, void* out,
                    cudaStream_t stream) {

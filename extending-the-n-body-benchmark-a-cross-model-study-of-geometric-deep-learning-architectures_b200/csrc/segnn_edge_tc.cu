@@ -196,6 +196,7 @@ struct TileCursor {
   int item;
   int sb;
   uint32_t t;
+  int g, i0;  // graph and first receiver of the item (MMA warp only; recomputed once per item)
 };
 
 template <int NMUL>
@@ -210,7 +211,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   constexpr int NW = n / 32;            // channel blocks (compute warps per group)
   static_assert(NW >= 1 && NW <= 3, "warp % 4 == 3 hosts the MMA / geometry warps");
   constexpr int kComputeThreads = 4 * NW * 32;
-  constexpr int kComputeWarps = 4 * NW;
   constexpr int kScalarWarps = NW;      // warps 7, 11, 15: scalar-channel producers of channel blocks 0, 1, 2
   constexpr int kMmaWarp = 3;           // MMA issuer + bulk copies + tile geometry (lane = column)
   constexpr int n3 = 3 * n;
@@ -231,9 +231,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   uint64_t* empty = bars + 2;    // [2] B stage consumed (tcgen05.commit; only the scalar producers need it)
   uint64_t* dfull = bars + 4;    // accumulators complete (tcgen05.commit)
   uint64_t* dempty = bars + 5;   // accumulators read out (all compute threads)
-  uint64_t* qfull = bars + 6;    // [2] bulk copy landed (expect_tx)
-  uint64_t* gfull = bars + 8;    // [kGeoSlots] geometry written
-  uint64_t* gempty = bars + 12;  // [kGeoSlots] geometry consumed (one arrival per compute / scalar-producer warp)
+  uint64_t* qfull = bars + 6;    // [2] sender rows landed (expect_tx) and tile geometry written
   uint64_t* pfull = bars + 16;   // receiver rows of P landed (expect_tx)
 
   const int tid = threadIdx.x;
@@ -256,10 +254,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     mbar_init(dfull, 1);
     mbar_init(pfull, 1);
     mbar_init(dempty, kComputeThreads);
-    for (int i = 0; i < kGeoSlots; ++i) {
-      mbar_init(&gfull[i], 1);
-      mbar_init(&gempty[i], kComputeWarps + kScalarWarps);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -303,6 +297,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     if (++c.sb == send_blocks) {
       c.sb = 0;
       c.item += gridDim.x;
+    }
+  };
+  auto locate = [&](TileCursor& c) {  // (g, i0) of c.item
+    c.g = c.item / recv_blocks;
+    c.i0 = (c.item - c.g * recv_blocks) * kRecv;
+  };
+  auto advance_located = [&](TileCursor& c) {
+    ++c.t;
+    if (++c.sb == send_blocks) {
+      c.sb = 0;
+      c.item += gridDim.x;
+      locate(c);
     }
   };
 
@@ -350,9 +356,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       const uint32_t t = cur.t;
       const int st = t & 1, slot = t & (kGeoSlots - 1);
       K3_TRACE(0, t);
-      mbar_wait_a(bar0 + 8 * (8 + slot), (t / kGeoSlots) & 1);     // gfull[slot]
-      // B stage st was last read by the MMAs of tile t - 2, whose completion (dfull) this thread observed in
-      // epilogue(t - 2), which precedes produce(t) in program order: no separate "stage empty" barrier is needed.
+      // One wait: qfull[st] = the tile's sender rows have landed AND its geometry is in the ring (the MMA warp writes
+      // the geometry before it arms the barrier for the bulk copy).  B stage st was last read by the MMAs of tile
+      // t - 2, whose completion (dfull) this thread observed in epilogue(t - 2), which precedes produce(t) in program
+      // order: no "stage empty" barrier.  Geometry slot t % 4 was last read in epilogue(t - 4): no "slot empty" one.
       mbar_wait_a(bar0 + 8 * (6 + st), (t >> 1) & 1);               // qfull[st]
       K3_TRACE(1, t);
       const float* qs = sQ + st * kQStageFloats;
@@ -458,8 +465,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
           acc[3] = __ffma2_rn(g1, __ffma2_rn(az, t1, u2f2(d[5][j], d[5][j + 1])), acc[3]);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(bar0 + 8 * (12 + slot));  // gempty[slot]
       K3_TRACE(5, t);
       if (cur.sb == send_blocks - 1) {
         // item complete: the two groups of a receiver pair (sender quads 0 / 1) each hold half of the senders for both
@@ -492,7 +497,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     };
 
     // iteration i: produce(tile i), then epilogue(tile i - 1)
-    TileCursor pc{(int)blockIdx.x, 0, 0u}, ec{(int)blockIdx.x, 0, 0u};
+    TileCursor pc{(int)blockIdx.x, 0, 0u, 0, 0}, ec{(int)blockIdx.x, 0, 0u, 0, 0};
     bool primed = false;
 #pragma unroll 1
     while (ec.item < items) {
@@ -518,7 +523,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     const float2 half2v = bc2(0.5f);
     float2 Ps[4][2];  // [plane][receiver pair], factor 1/2 folded
     uint32_t p_items = 0;
-    for (TileCursor c{(int)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
+    for (TileCursor c{(int)blockIdx.x, 0, 0u, 0, 0}; c.item < items; advance(c)) {
       const uint32_t t = c.t;
       const int st = t & 1, slot = t & (kGeoSlots - 1);
       if (c.sb == 0) {
@@ -531,8 +536,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
             Ps[pl][rp] = make_float2(0.5f * sP[(2 * rp) * 4 * n3 + pl * n3 + w], 0.5f * sP[(2 * rp + 1) * 4 * n3 + pl * n3 + w]);
       }
       K3_TRACE(0, t);
-      mbar_wait_a(bar0 + 8 * (8 + slot), (t / kGeoSlots) & 1);  // gfull[slot]
-      mbar_wait_a(bar0 + 8 * (6 + st), (t >> 1) & 1);            // qfull[st]
+      mbar_wait_a(bar0 + 8 * (6 + st), (t >> 1) & 1);            // qfull[st]: sender rows + geometry
       mbar_wait_a(bar0 + 8 * (2 + st), ((t >> 1) & 1) ^ 1);      // empty[st]: MMAs of tile t - 2 have read the stage
       K3_TRACE(1, t);
       const float* qs = sQ + st * kQStageFloats;
@@ -579,8 +583,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       proxy_fence();
       mbar_arrive_a(bar0 + 8 * st);  // full[st]
       K3_TRACE(2, t);
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(bar0 + 8 * (12 + slot));  // gempty[slot]
     }
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ==================================================================
@@ -589,22 +591,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     const uint32_t tm = 0u;  // checked above
     const uint64_t bdesc0 = make_b_desc(smem_u32(sB));
     const uint32_t d0 = tm + kDBase;
-    // bulk copy of the 8 sender rows of tile (item, sb) into Q stage st (one elected lane)
-    auto load_q = [&](const TileCursor& c, int st) {
-      if (c.item < items && elect_one()) {
-        const long long g = c.item / recv_blocks;
-        const int nvalid = min(kSend, N - c.sb * kSend);
-        const uint32_t bytes = (uint32_t)nvalid * 4 * n3 * (uint32_t)sizeof(float);
-        const float* src = qq + (g * N + (long long)c.sb * kSend) * 4 * n3;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&qfull[st])), "r"(bytes)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(sQ + st * kQStageFloats)),
-                     "l"(src), "r"(bytes), "r"(smem_u32(&qfull[st]))
-                     : "memory");
-      }
-      __syncwarp();
-    };
     // bulk copy of the (up to) 4 receiver rows of P of an item (one elected lane)
     auto load_prow = [&](int item) {
       if (item < items && elect_one()) {
@@ -621,17 +607,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       }
       __syncwarp();
     };
-    // geometry of a tile (lane = column = rp * 16 + sender * 2 + (r & 1)): loads first, ring write later, so the
-    // global-load latency hides behind the MMA issue block
+    // Inputs of a tile = its geometry (lane = column = rp * 16 + sender * 2 + (r & 1)) + the 8 sender rows of Q.
+    // tile_load issues the position loads only (nothing waits for them); tile_publish, one iteration later, writes
+    // the geometry into ring slot t % 4, then arms qfull[st] and issues the bulk copy: one barrier covers both.
     const int gsl = (lane >> 1) & 7, gr = 2 * (lane >> 4) + (lane & 1);
     float gsx = 0.f, gsy = 0.f, gsz = 0.f, gsm = 0.f, grx = 0.f, gry = 0.f, grz = 0.f, grm = 0.f;  // raw loads
     bool gvalid = false;
-    auto geo_load = [&](const TileCursor& c) {  // issues the loads only: nothing here waits for them
+    auto tile_load = [&](const TileCursor& c) {
       if (c.item < items) {
-        const long long g = c.item / recv_blocks;
-        const int i0 = (int)(c.item - g * recv_blocks) * kRecv;
-        const int jj = c.sb * kSend + gsl, ii = i0 + gr;
-        const long long js = g * N + min(jj, N - 1), is = g * N + min(ii, N - 1);
+        const int jj = c.sb * kSend + gsl, ii = c.i0 + gr;
+        const long long js = (long long)c.g * N + min(jj, N - 1), is = (long long)c.g * N + min(ii, N - 1);
         gsx = pos[js * 3 + 0];
         gsy = pos[js * 3 + 1];
         gsz = pos[js * 3 + 2];
@@ -643,39 +628,44 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         gvalid = (jj < N) && (ii < N) && (jj != ii);
       }
     };
-    auto geo_store = [&](const TileCursor& c) {
+    auto tile_publish = [&](const TileCursor& c) {
       if (c.item < items) {
         const uint32_t t = c.t;
-        const int slot = t & (kGeoSlots - 1);
+        const int slot = t & (kGeoSlots - 1), st = t & 1;
         float ux, uy, uz, len;
         unit_vec(gsx - grx, gsy - gry, gsz - grz, ux, uy, uz, len);
-        const float gmm = gsm * grm;
-        mbar_wait(&gempty[slot], ((t / kGeoSlots) & 1) ^ 1, err_flag);
-        float* gs = geo + slot * 6 * kCols;
+        float* gs = geo + slot * 6 * kCols;  // slot last read in epilogue(t - 4), long complete (see produce)
         gs[0 * kCols + lane] = kY1 * ux;
         gs[1 * kCols + lane] = kY1 * uy;
         gs[2 * kCols + lane] = kY1 * uz;
         gs[3 * kCols + lane] = len;
-        gs[4 * kCols + lane] = gmm;
+        gs[4 * kCols + lane] = gsm * grm;
         gs[5 * kCols + lane] = gvalid ? 1.0f : 0.0f;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&gfull[slot]);
+        if (elect_one()) {
+          const int nvalid = min(kSend, N - c.sb * kSend);
+          const uint32_t bytes = (uint32_t)nvalid * 4 * n3 * (uint32_t)sizeof(float);
+          const float* src = qq + ((long long)c.g * N + (long long)c.sb * kSend) * 4 * n3;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&qfull[st])), "r"(bytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_u32(sQ + st * kQStageFloats)),
+                       "l"(src), "r"(bytes), "r"(smem_u32(&qfull[st]))
+                       : "memory");
+        }
+        __syncwarp();
       }
     };
-    TileCursor pf{(int)blockIdx.x, 0, 0u};  // tile two ahead of the current one
-    TileCursor gc{(int)blockIdx.x, 0, 0u};  // geometry cursor, two tiles ahead as well
+    TileCursor pf{(int)blockIdx.x, 0, 0u, 0, 0};  // runs two tiles ahead of the MMA issue
+    locate(pf);
     load_prow(blockIdx.x);
-    load_q(pf, 0);
-    advance(pf);
-    load_q(pf, 1);
-    advance(pf);
     for (int i = 0; i < 2; ++i) {
-      geo_load(gc);
-      geo_store(gc);
-      advance(gc);
+      tile_load(pf);
+      tile_publish(pf);
+      advance_located(pf);
     }
-    geo_load(gc);  // tile 2: stored at the end of iteration 0
-    for (TileCursor c{(int)blockIdx.x, 0, 0u}; c.item < items; advance(c)) {
+    tile_load(pf);  // tile 2: published at the end of iteration 0
+    for (TileCursor c{(int)blockIdx.x, 0, 0u, 0, 0}; c.item < items; advance(c)) {
       const uint32_t t = c.t;
       const int st = t & 1;
       K3_TRACE(0, t);
@@ -710,12 +700,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       // housekeeping off the critical path: producers are done with Q stage st (full[st] observed): refill it for tile
       // t + 2; every producer thread holds this item's P rows in registers: fetch the next item's (single buffer);
       // geometry of tile t + 2 into the ring, loads of tile t + 3 in flight until the next iteration
-      load_q(pf, st);
-      advance(pf);
+      tile_publish(pf);
+      advance_located(pf);
+      tile_load(pf);
       if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
-      geo_store(gc);
-      advance(gc);
-      geo_load(gc);
       K3_TRACE(4, t);
     }
   }

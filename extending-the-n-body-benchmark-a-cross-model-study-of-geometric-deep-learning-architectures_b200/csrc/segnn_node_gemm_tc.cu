@@ -163,23 +163,31 @@ __global__ void __launch_bounds__(kThreads, 1)
       const long long pl = live ? plane_of(cls, gr) : 0;
       mbar_wait(&aempty[ab], ((t >> 1) & 1) ^ 1);
       uint8_t* dst = sA + ab * a_bytes + r * 128;
-      for (int b0 = 0; b0 < k4h; b0 += 12) {
-        float4 v[12];
+      // 256-bit loads: lanes own different rows, so the load rate is bound by memory transactions (32 bytes = one full
+      // sector per transaction); up to 6 independent loads (192 bytes) in flight per thread
+      const int k8h = k4h / 2;  // 8-float pieces per half row
+      for (int b0 = 0; b0 < k8h; b0 += 6) {
+        float v[6][8];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
-          const int k = (half * k4h + b0 + i) * 4;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live && b0 + i < k4h)
-            v[i] = k < n_in ? *reinterpret_cast<const float4*>(x0 + pl * n_in + k)
-                            : *reinterpret_cast<const float4*>(x1 + pl * n_in + (k - n_in));
+        for (int i = 0; i < 6; ++i) {
+          const int k = (half * k8h + b0 + i) * 8;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[i][q] = 0.f;
+          if (live && b0 + i < k8h) {
+            const float* src = k < n_in ? x0 + pl * n_in + k : x1 + pl * n_in + (k - n_in);
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(v[i][0]), "=f"(v[i][1]), "=f"(v[i][2]), "=f"(v[i][3]), "=f"(v[i][4]), "=f"(v[i][5]),
+                           "=f"(v[i][6]), "=f"(v[i][7])
+                         : "l"(src));
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
-          if (b0 + i < k4h) {
-            const int k = (half * k4h + b0 + i) * 4;
-            const uint2 o = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
-            *reinterpret_cast<uint2*>(dst + (k >> 6) * (128 * 128) + ((((k & 63) >> 3) ^ (r & 7)) << 4) +
-                                      (k & 7) * 2) = o;
+        for (int i = 0; i < 6; ++i) {
+          if (b0 + i < k8h) {
+            const int k = (half * k8h + b0 + i) * 8;  // 8 k = one 16-byte chunk of the swizzled row
+            const uint4 o = make_uint4(pack_bf16x2(v[i][0], v[i][1]), pack_bf16x2(v[i][2], v[i][3]),
+                                       pack_bf16x2(v[i][4], v[i][5]), pack_bf16x2(v[i][6], v[i][7]));
+            *reinterpret_cast<uint4*>(dst + (k >> 6) * (128 * 128) + ((((k & 63) >> 3) ^ (r & 7)) << 4)) = o;
           }
         }
       }
@@ -246,8 +254,11 @@ __global__ void __launch_bounds__(kThreads, 1)
                 if (cls == 0 && bias != nullptr && col + q < n_bias) f[q] += bias[col + q];
               }
               float* dst = col < split ? y0 + pl * split + col : y1 + pl * n_out1 + (col - split);
-              *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              // one 256-bit store = one full 32-byte sector per lane (lanes own different rows, so the store rate is
+              // bound by memory transactions: two 16-byte stores per sector halve it)
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(f[0]), "f"(f[1]),
+                           "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
+                           : "memory");
             }
           }
         }
@@ -293,6 +304,9 @@ int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, co
   if (y1 == nullptr) split = n_out;
   SEGNN_CHECK_ARG(split % 8 == 0 && split > 0 && split <= n_out, "split must be a positive multiple of 8");
   SEGNN_CHECK_ARG(bias == nullptr || (n_bias >= 0 && n_bias <= n_out), "n_bias out of range");
+  SEGNN_CHECK_ARG(((uintptr_t)y0 & 31) == 0 && ((uintptr_t)y1 & 31) == 0 && ((uintptr_t)x0 & 31) == 0 &&
+                      ((uintptr_t)x1 & 31) == 0,
+                  "inputs and outputs must be 32-byte aligned (256-bit loads and stores)");
   int nc = 0;
   for (int c = 192; c >= 16; c -= 16)
     if (n_out % c == 0) { nc = c; break; }

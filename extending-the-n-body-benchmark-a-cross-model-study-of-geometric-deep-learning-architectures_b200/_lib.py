@@ -46,6 +46,7 @@ PROTOTYPES = {
     "segnn_edge_layer_bwd": (_int, [_int, _ptr, _ptr, _int, _int, _int] + [_ptr] * 24),
     "segnn_embed_bwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_head_bwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_macros_energy_momentum": (_int, [_ptr, _ptr, _int, _int, _int, _c.c_float, _c.c_float, _ptr, _ptr]),
 }
 
 

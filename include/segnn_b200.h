@@ -207,6 +207,15 @@ int segnn_embed_bwd(const float* x_in, const float* node_attr, const float* dh, 
 int segnn_head_bwd(const float* h, const float* node_attr, const float* w_head, const float* dpred, int nodes, int n,
                    float* dh, float* contrib, segnn_stream_t stream);
 
+/* ---- rollout macros (evaluation of rollouts) ------------------------------------------- */
+
+/* trainer.py:888-927 `_compute_nbody_energies` and datasets/nbody/visualization_utils.py:959-960 (momentum), per
+ * (frame, simulation) instead of per Python loop iteration: traj_pos, traj_vel [frames][B*N][3] (the rollout's
+ * trajectory buffers) -> out [frames][B][3] = (kinetic = 0.5 sum v^2, potential = -G sum_{i<j} (r_ij^2 +
+ * softening^2)^-1/2, |sum_i v_i|), unit masses as in the reference. */
+int segnn_macros_energy_momentum(const float* traj_pos, const float* traj_vel, int frames, int B, int N, float G,
+                                 float softening, float* out, segnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

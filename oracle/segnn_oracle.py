@@ -643,3 +643,58 @@ def perturb_bn_buffers(model: nn.Module, seed: int = 1):
                 mod.running_var.copy_(0.5 + torch.rand(mod.running_var.shape, generator=gen, dtype=torch.float64))
                 mod.weight.copy_(0.75 + 0.5 * torch.rand(mod.weight.shape, generator=gen, dtype=torch.float64))
                 mod.bias.copy_(0.1 * torch.randn(mod.bias.shape, generator=gen, dtype=torch.float64))
+
+
+# ----------------------------------------------------------------------------------------------
+# Rollout macros (acceptance statistics) -- restated with the reference's own loops / libraries
+# ----------------------------------------------------------------------------------------------
+def nbody_energies(loc, vel, G: float, softening: float):
+    """trainer.py:888-927 `_compute_nbody_energies`. loc, vel [B, T, N, 3] -> per-simulation arrays [B, T] and the
+    batch-averaged series dict (unit masses)."""
+    import numpy as np
+    loc, vel = np.asarray(loc, dtype=np.float64), np.asarray(vel, dtype=np.float64)
+    batch, steps, n, _ = loc.shape
+    kinetic, potential = np.zeros((batch, steps)), np.zeros((batch, steps))
+    iu = np.triu_indices(n, 1)
+    for b in range(batch):
+        L, V = loc[b], vel[b]
+        kinetic[b] = 0.5 * np.sum(V * V, axis=(1, 2))
+        d = L[:, None, :, :] - L[:, :, None, :]
+        inv_r = np.sqrt((d * d).sum(-1) + softening * softening)
+        inv_r[inv_r > 0] = 1.0 / inv_r[inv_r > 0]
+        potential[b] = -G * np.sum(inv_r[:, iu[0], iu[1]], axis=1)
+    series = {"potential": potential.mean(0), "kinetic": kinetic.mean(0)}
+    series["total"] = series["potential"] + series["kinetic"]
+    return kinetic, potential, series
+
+
+def momentum_magnitude(vel):
+    """datasets/nbody/visualization_utils.py:959-960: |sum_i v_i| per (simulation, frame). vel [B, T, N, 3]."""
+    import numpy as np
+    v = np.asarray(vel, dtype=np.float64).sum(axis=2)
+    return np.sqrt((v ** 2).sum(axis=-1))
+
+
+def ks_p(a, b) -> float:
+    """utils/ks_utils.py:7-19."""
+    import numpy as np
+    from scipy import stats
+    a, b = np.asarray(a).ravel(), np.asarray(b).ravel()
+    if a.size == 0 or b.size == 0 or np.all(np.isnan(a)) or np.all(np.isnan(b)):
+        return float("nan")
+    a, b = a[~np.isnan(a)], b[~np.isnan(b)]
+    if a.size == 0 or b.size == 0:
+        return float("nan")
+    return float(stats.ks_2samp(a, b)[1])
+
+
+def combine_pvalues_fisher(p_values) -> float:
+    """utils/ks_utils.py:22-29 (mpmath 200-digit sum + scipy chi2.sf, floored at 1e-300)."""
+    from mpmath import log, mp
+    from scipy.stats import chi2
+    vals = [p for p in p_values if p == p and p > 0.0]
+    if not vals:
+        return float("nan")
+    mp.dps = 200
+    chi_stat = float(-2 * mp.fsum([log(mp.mpf(p)) for p in vals]))
+    return float(max(chi2.sf(chi_stat, 2 * len(vals)), 1e-300))

@@ -312,3 +312,57 @@ def test_train_step_loss_trajectory_matches_oracle(use_graph):
     for a, b in zip(losses, ref_losses):
         assert abs(a - b) < 2e-4 * abs(b)
     assert rel(m.layers[0].feature_norm.running_var, om.layers[0].feature_norm.running_var) < 1e-4
+
+
+# ---- rollout macros ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,T", [(3, 5, 7), (2, 100, 4), (1, 300, 2)])
+def test_macro_kernel_matches_reference_definitions(B, N, T):
+    import numpy as np
+    gen = torch.Generator().manual_seed(B * N + T)
+    loc = torch.randn(B, T, N, 3, generator=gen, dtype=torch.float64) * 2.0
+    vel = torch.randn(B, T, N, 3, generator=gen, dtype=torch.float64)
+    G, soft = 2.0, 0.2
+    kin_ref, pot_ref, series = O.nbody_energies(loc.numpy(), vel.numpy(), G, soft)
+    mom_ref = O.momentum_magnitude(vel.numpy())
+    tp = loc.permute(1, 0, 2, 3).reshape(T, B * N, 3).float().cuda()
+    tv = vel.permute(1, 0, 2, 3).reshape(T, B * N, 3).float().cuda()
+    kin, pot, mom = S.macros.energy_momentum(tp, tv, B, N, G, soft)
+    assert np.abs(kin.cpu().numpy().T - kin_ref).max() < 1e-5 * np.abs(kin_ref).max()
+    assert np.abs(pot.cpu().numpy().T - pot_ref).max() < 1e-5 * np.abs(pot_ref).max()
+    assert np.abs(mom.cpu().numpy().T - mom_ref).max() < 1e-5 * max(np.abs(mom_ref).max(), 1.0)
+    got = S.macros.nbody_energies(tp, tv, B, N, G, soft)
+    for k in ("potential", "kinetic", "total"):
+        assert np.abs(got[k] - series[k]).max() < 1e-5 * np.abs(series[k]).max()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_rollout_macros_within_reference_statistical_tolerance(mode):
+    """BASELINE north_star check (c): energy / momentum macros of the CUDA rollout against the oracle rollout on the same
+    initial conditions and weights: two-sample KS p >= 0.05 per macro and Fisher-combined (the reference's acceptance
+    threshold, figures/combined_pvalues_summary.csv `time_to_p_ge_0.05`), and the total-energy ratio stays within
+    [1/2.5, 2.5] for every step (trainer.py:27,692-701)."""
+    import numpy as np
+    if mode == "bf16" and not (S.ops.tc_available()):
+        pytest.skip("tensor-core mode not built")
+    om, m = make_pair(64, 3, seed=21)
+    m.compute_mode = mode
+    B, N, steps = 24, 5, 30
+    pos, vel, mass = O.synthetic_system(B, N, seed=31, charged=False)
+    ref_loc, ref_vel = O.rollout(om, pos, vel, mass, steps)
+    roll = S.SelfFeedRollout(m, B, N, "cuda", max_frames=steps + 1)
+    roll.reset(pos, vel, mass)
+    tp, tv = roll.run(steps)
+    G, soft = 2.0, 0.2
+    kin, pot, mom = S.macros.energy_momentum(tp, tv, B, N, G, soft)
+    kin_ref, pot_ref, series_ref = O.nbody_energies(ref_loc.numpy(), ref_vel.numpy(), G, soft)
+    mom_ref = O.momentum_magnitude(ref_vel.numpy())
+    ps = [S.macros.ks_p(kin.cpu().numpy().T[:, -1], kin_ref[:, -1]),
+          S.macros.ks_p(pot.cpu().numpy().T[:, -1], pot_ref[:, -1]),
+          S.macros.ks_p(mom.cpu().numpy().T[:, -1], mom_ref[:, -1]),
+          S.macros.ks_p(kin.cpu().numpy().T.ravel(), kin_ref.ravel()),
+          S.macros.ks_p(pot.cpu().numpy().T.ravel(), pot_ref.ravel())]
+    combined = S.macros.combine_pvalues_fisher(ps)
+    print(f"[{mode}] KS p-values {ps} combined {combined}")
+    assert min(ps) >= 0.05 and combined >= 0.05
+    got = S.macros.nbody_energies(tp, tv, B, N, G, soft)
+    assert S.macros.energy_ratio_steps(got["total"], series_ref["total"]) == steps + 1

@@ -216,3 +216,23 @@ def test_two_rank_gloo_gradient_allreduce():
     assert same
     for i, g in enumerate(grads):
         assert g == (0.0 if i == 2 else 1.5 * (i + 1))
+
+
+def test_fisher_and_ks_match_reference_libraries():
+    """macros.combine_pvalues_fisher (closed form, log space) and macros.ks_p against the oracle's restatement of
+    utils/ks_utils.py (scipy + mpmath), including the 1e-300 floor and the NaN / non-positive filtering."""
+    import numpy as np
+    M = S.macros
+    rng = np.random.default_rng(0)
+    for ps in ([0.5], [0.01, 0.2, 0.9], [1e-5, 1e-7, 0.3, float("nan"), 0.0], list(rng.uniform(1e-6, 1, 40)),
+               [1e-120] * 5, [1.0, 1.0]):
+        ref, got = O.combine_pvalues_fisher(ps), M.combine_pvalues_fisher(ps)
+        assert abs(got - ref) <= 1e-9 * ref + 1e-300, (ps, ref, got)
+    assert M.combine_pvalues_fisher([float("nan"), -1.0]) != M.combine_pvalues_fisher([float("nan"), -1.0])  # NaN
+    a, b = rng.normal(size=300), rng.normal(0.3, 1.0, size=250)
+    assert abs(M.ks_p(a, b) - O.ks_p(a, b)) < 1e-12
+    assert abs(M.ks_statistic(a, b) - __import__("scipy").stats.ks_2samp(a, b)[0]) < 1e-12
+    assert M.ks_p([], b) != M.ks_p([], b)
+    assert M.energy_ratio_steps(np.array([1.0, 1.2, 3.0, 1.0]), np.ones(4)) == 2
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        M.energy_momentum(torch.zeros(2, 10, 3), torch.zeros(2, 10, 3), 2, 5)

@@ -1,0 +1,167 @@
+// Generic-irreps SEGNN path (fp32, inference): the reference's formulation -- materialised edge list order, gathered
+// message inputs, one FullyConnectedTensorProduct per call, e3nn Gate, scatter-sum -- as plain CUDA kernels that work
+// for ANY hidden irreps (e.g. lmax_h = 2, BASELINE config 3).  It exists for parity coverage of configurations the
+// fused kernels are not specialised for; it is not tuned (per-edge tensors live in HBM like in the reference).
+//   models/segnn/o3_building_blocks.py:150-162 (tensor product + rescale + bias), :197-203 (gate),
+//   models/segnn/segnn.py:264-304 (message / aggregate / update).
+#include "segnn_common.cuh"
+
+namespace segnn {
+
+constexpr int kInstrInts = 9;    // off1, mul1, dim1, off2, dim2, offo, mulo, dimo, woff
+constexpr int kCgFloats = 75;    // [5][3][5] coupling (net coefficient folded), row-major (i, j, k)
+
+// out[row][c] = bias[c] + sum_{instructions writing c} sum_u W[u][w] * sum_{i,j} C[i][j][k] x1[row][u, i] x2[row][j]
+__global__ void generic_tp_kernel(const float* __restrict__ x1, int d1, const float* __restrict__ x2, int d2,
+                                  long long rows, const float* __restrict__ weights, const int* __restrict__ instr,
+                                  int n_instr, const float* __restrict__ cg, const float* __restrict__ bias, int dout,
+                                  float* __restrict__ out) {
+  const long long total = rows * dout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / dout;
+    const int c = (int)(idx - row * dout);
+    const float* a = x1 + row * d1;
+    const float* b = x2 + row * d2;
+    float acc = bias != nullptr ? bias[c] : 0.f;
+    for (int q = 0; q < n_instr; ++q) {
+      const int* in = instr + q * kInstrInts;
+      const int offo = in[5], mulo = in[6], dimo = in[7];
+      if (c < offo || c >= offo + mulo * dimo) continue;
+      const int w = (c - offo) / dimo, k = (c - offo) - w * dimo;
+      const int off1 = in[0], mul1 = in[1], dim1 = in[2], off2 = in[3], dim2 = in[4], woff = in[8];
+      const float* C = cg + q * kCgFloats;
+      float m[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        float s = 0.f;
+        if (i < dim1)
+          for (int j = 0; j < dim2; ++j) s = fmaf(C[(i * 3 + j) * 5 + k], b[off2 + j], s);
+        m[i] = s;
+      }
+      const float* W = weights + woff + w;
+      const float* xa = a + off1;
+      for (int u = 0; u < mul1; ++u) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          if (i < dim1) t = fmaf(m[i], xa[u * dim1 + i], t);
+        acc = fmaf(W[(long long)u * mulo], t, acc);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// e3nn Gate: x = [n_s scalars | n_g gates | gated]; out = [c_silu silu(scalars) | gated * c_sig sigmoid(gate)]
+__global__ void generic_gate_kernel(const float* __restrict__ x, long long rows, int n_s, int n_g, int d_gated,
+                                    const int* __restrict__ gate_index, float* __restrict__ out) {
+  const int din = n_s + n_g + d_gated, dout = n_s + d_gated;
+  const long long total = rows * dout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / dout;
+    const int c = (int)(idx - row * dout);
+    const float* r = x + row * din;
+    out[idx] = c < n_s ? silu_gate(r[c]) : r[n_s + n_g + (c - n_s)] * sig_gate(r[n_s + gate_index[c - n_s]]);
+  }
+}
+
+// message input cat(x_i, x_j, add) in the reference edge order (graph-major, source ascending, target ascending):
+// edge (g, a -> b): x_i = x[target b], x_j = x[source a]   (models/segnn/segnn.py:264-277)
+__global__ void generic_message_input_kernel(const float* __restrict__ x, const float* __restrict__ add, int B, int N,
+                                             int D, int d_add, float* __restrict__ out) {
+  const int dout = 2 * D + d_add;
+  const long long E = (long long)B * N * (N - 1);
+  const long long total = E * dout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx / dout;
+    const int c = (int)(idx - e * dout);
+    const long long g = e / ((long long)N * (N - 1));
+    const int le = (int)(e - g * N * (N - 1));
+    const int a = le / (N - 1), bb = le - a * (N - 1);
+    const int b = bb < a ? bb : bb + 1;
+    float v;
+    if (c < D) v = x[(g * N + b) * D + c];
+    else if (c < 2 * D) v = x[(g * N + a) * D + (c - D)];
+    else v = add[e * d_add + (c - 2 * D)];
+    out[idx] = v;
+  }
+}
+
+// agg[target] = sum over sources (ascending) of m[edge(source -> target)]: deterministic scatter-sum (segnn.py:205)
+__global__ void generic_aggregate_kernel(const float* __restrict__ m, int B, int N, int D, float* __restrict__ agg) {
+  const long long total = (long long)B * N * D;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long node = idx / D;
+    const int c = (int)(idx - node * D);
+    const long long g = node / N;
+    const int b = (int)(node - g * N);
+    float s = 0.f;
+    for (int a = 0; a < N; ++a) {
+      if (a == b) continue;
+      const long long e = g * N * (N - 1) + (long long)a * (N - 1) + (b < a ? b : b - 1);
+      s += m[e * D + c];
+    }
+    agg[idx] = s;
+  }
+}
+
+static inline int generic_grid(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = 148LL * 64;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace segnn
+
+using namespace segnn;
+
+extern "C" {
+
+int segnn_generic_tp(const float* x1, int d1, const float* x2, int d2, int64_t rows, const float* weights,
+                     const int* instr, int n_instr, const float* cg, const float* bias, int dout, float* out,
+                     segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(rows >= 0 && d1 >= 1 && d2 >= 1 && dout >= 1 && n_instr >= 1, "bad sizes");
+  if (rows == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x1 && x2 && weights && instr && cg && out, "null pointer");
+  generic_tp_kernel<<<generic_grid(rows * dout), 256, 0, (cudaStream_t)stream>>>(x1, d1, x2, d2, rows, weights, instr,
+                                                                               n_instr, cg, bias, dout, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_generic_gate(const float* x, int64_t rows, int n_scalars, int n_gates, int d_gated, const int* gate_index,
+                       float* out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(rows >= 0 && n_scalars >= 0 && n_gates >= 0 && d_gated >= 0, "bad sizes");
+  if (rows == 0 || n_scalars + d_gated == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x && out && (d_gated == 0 || gate_index), "null pointer");
+  generic_gate_kernel<<<generic_grid(rows * (n_scalars + d_gated)), 256, 0, (cudaStream_t)stream>>>(
+      x, rows, n_scalars, n_gates, d_gated, gate_index, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_generic_message_input(const float* x, const float* add, int B, int N, int D, int d_add, float* out,
+                                segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(B >= 0 && N >= 2 && D >= 1 && d_add >= 0, "bad sizes");
+  if (B == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x && out && (d_add == 0 || add), "null pointer");
+  generic_message_input_kernel<<<generic_grid((long long)B * N * (N - 1) * (2 * D + d_add)), 256, 0,
+                                 (cudaStream_t)stream>>>(x, add, B, N, D, d_add, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_generic_aggregate(const float* m, int B, int N, int D, float* agg, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(B >= 0 && N >= 2 && D >= 1, "bad sizes");
+  if (B == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(m && agg, "null pointer");
+  generic_aggregate_kernel<<<generic_grid((long long)B * N * D), 256, 0, (cudaStream_t)stream>>>(m, B, N, D, agg);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+}  // extern "C"

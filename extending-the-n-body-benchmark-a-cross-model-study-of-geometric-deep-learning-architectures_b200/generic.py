@@ -1,0 +1,172 @@
+"""Generic-irreps forward of the SEGNN modules (fp32, inference): the reference's own formulation -- gathered message
+inputs, one tensor product per call, e3nn Gate, BatchNorm (eval), scatter-sum -- on plain CUDA kernels
+(csrc/segnn_generic.cu) that accept any hidden irreps with lmax_attr = 1. It gives parity coverage for configurations
+the fused kernels are not specialised for (lmax_h = 2, BASELINE config 3); per-edge tensors live in HBM here, as in the
+reference, so it is a correctness path, not the throughput path.
+
+models/segnn/segnn.py:150-189 (SEGNN.forward), :239-304 (SEGNNLayer), o3_building_blocks.py:150-203.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import check, lib
+from .cg import real_wigner_3j
+from .irreps import Irreps
+
+_p = ops._p
+
+
+def _slices(irreps: Irreps):
+    out, off = [], 0
+    for m, l, _ in irreps:
+        out.append((off, m, 2 * l + 1))
+        off += m * (2 * l + 1)
+    return out
+
+
+class TensorProductPlan:
+    """Device-side description of one O3TensorProduct: instruction table, scaled couplings, dense bias."""
+
+    def __init__(self, module, device):
+        tp = module.tp
+        s1, s2, so = _slices(tp.irreps_in1), _slices(tp.irreps_in2), _slices(tp.irreps_out)
+        instr, cgs = [], []
+        for ins in tp.instructions:
+            l1, l2, lo = ins["ls"]
+            if max(l1, lo) > 2 or l2 > 1 or ins["shape"][1] != 1:
+                raise NotImplementedError("generic tensor product: l <= 2 for features, lmax_attr = 1, attribute "
+                                          "multiplicity 1")
+            o1, m1, d1 = s1[ins["i1"]]
+            o2, _, d2 = s2[ins["i2"]]
+            oo, mo, do = so[ins["io"]]
+            instr.append([o1, m1, d1, o2, d2, oo, mo, do, ins["offset"]])
+            c = np.zeros((5, 3, 5), dtype=np.float64)
+            # net path coefficient: e3nn 'component'/'element' path weight x the reference's sqrt_k_correction
+            c[:d1, :d2, :do] = math.sqrt(2 * lo + 1) * real_wigner_3j(l1, l2, lo)
+            cgs.append(c)
+        self.n_instr = len(instr)
+        self.instr = torch.tensor(instr, dtype=torch.int32, device=device).contiguous()
+        self.cg = torch.tensor(np.stack(cgs), dtype=torch.float32, device=device).contiguous()
+        self.d1, self.d2, self.dout = tp.irreps_in1.dim, tp.irreps_in2.dim, tp.irreps_out.dim
+        cols = [c for (off, m, d), (_, l, _) in zip(so, tp.irreps_out) if l == 0 for c in range(off, off + m)]
+        self.bias_idx = torch.tensor(cols, dtype=torch.int64, device=device) if cols else None
+        self.module = module
+
+    def run(self, x1, x2):
+        rows = x1.shape[0]
+        m = self.module
+        w = m.tp.weight.detach().to(torch.float32).contiguous()
+        bias = None
+        if m.biases is not None:
+            bias = torch.zeros(self.dout, dtype=torch.float32, device=x1.device)
+            bias[self.bias_idx] = m.biases.detach().to(torch.float32)
+        out = torch.empty((rows, self.dout), dtype=torch.float32, device=x1.device)
+        with torch.cuda.device(x1.device):
+            check(lib.segnn_generic_tp(_p(x1), self.d1, _p(x2), self.d2, rows, _p(w), _p(self.instr), self.n_instr,
+                                       _p(self.cg), _p(bias), self.dout, _p(out), ops._stream()), "segnn_generic_tp")
+        ops._bump()
+        return out
+
+
+class GatePlan:
+    """e3nn Gate layout of an O3TensorProductSwishGate output (o3_building_blocks.py:175-193)."""
+
+    def __init__(self, module, device):
+        out = module.irreps_gated_out
+        self.n_s = out[0][0] if out[0][1] == 0 else 0
+        gated = out[1:] if self.n_s else out
+        idx, g = [], 0
+        for m, l, _ in gated:
+            for u in range(m):
+                idx += [g] * (2 * l + 1)
+                g += 1
+        self.n_g, self.d_gated = g, len(idx)
+        self.gate_index = torch.tensor(idx, dtype=torch.int32, device=device) if idx else None
+
+    def run(self, x):
+        rows = x.shape[0]
+        out = torch.empty((rows, self.n_s + self.d_gated), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.segnn_generic_gate(_p(x), rows, self.n_s, self.n_g, self.d_gated, _p(self.gate_index), _p(out),
+                                         ops._stream()), "segnn_generic_gate")
+        ops._bump()
+        return out
+
+
+def _bn_eval_columns(bn, irreps: Irreps):
+    """Eval-mode e3nn BatchNorm (segnn.py:233-235) as a per-column affine (mul, add)."""
+    f = lambda t: t.detach().to(torch.float32)
+    mul_irrep = f(bn.weight) * (f(bn.running_var) + bn.eps).rsqrt()
+    mul, add, ii, isc = [], [], 0, 0
+    for m, l, p in irreps:
+        d = 2 * l + 1
+        mi = mul_irrep[ii: ii + m]
+        mul.append(mi.repeat_interleave(d))
+        if l == 0 and p == 1:
+            add.append(f(bn.bias)[isc: isc + m] - f(bn.running_mean)[isc: isc + m] * mi)
+            isc += m
+        else:
+            add.append(torch.zeros(m * d, dtype=torch.float32, device=mi.device))
+        ii += m
+    return torch.cat(mul).contiguous(), torch.cat(add).contiguous()
+
+
+class GenericRunner:
+    """Plans for every tensor product / gate of one SEGNN; ``forward`` mirrors SEGNN.forward (eval mode)."""
+
+    def __init__(self, model, device):
+        self.model = model
+        tp = lambda m: TensorProductPlan(m, device)
+        self.embed = tp(model.embedding_layer)
+        self.layers = []
+        for layer in model.layers:
+            self.layers.append(dict(
+                msg1=tp(layer.message_layer_1), g_msg1=GatePlan(layer.message_layer_1, device),
+                msg2=tp(layer.message_layer_2), g_msg2=GatePlan(layer.message_layer_2, device),
+                upd1=tp(layer.update_layer_1), g_upd1=GatePlan(layer.update_layer_1, device),
+                upd2=tp(layer.update_layer_2)))
+        self.pool1, self.g_pool1 = tp(model.pre_pool1), GatePlan(model.pre_pool1, device)
+        self.pool2 = tp(model.pre_pool2)
+
+    @torch.no_grad()
+    def forward(self, pos, vel, mass, B: int, N: int, return_layers: bool = False):
+        model = self.model
+        if model.training and model.norm == "batch":
+            raise NotImplementedError("the generic-irreps path implements eval-mode BatchNorm only")
+        D = model.hidden_irreps.dim
+        x_in, attr = ops.prep(pos, vel, B, N)
+        ea, add = ops.edge_attr(pos, mass, B, N)
+        E = ea.shape[0]
+        x = self.embed.run(x_in, attr)
+        per_layer = [x]
+        for layer, pl in zip(model.layers, self.layers):
+            inp = torch.empty((E, 2 * D + 2), dtype=torch.float32, device=pos.device)
+            with torch.cuda.device(pos.device):
+                check(lib.segnn_generic_message_input(_p(x), _p(add), B, N, D, 2, _p(inp), ops._stream()),
+                      "segnn_generic_message_input")
+            m = pl["g_msg1"].run(pl["msg1"].run(inp, ea))
+            m = pl["g_msg2"].run(pl["msg2"].run(m, ea))
+            if layer.message_norm is not None:
+                mul, addc = _bn_eval_columns(layer.message_norm, layer.hidden_irreps)
+                m = ops.lincomb(m, None, mul, None, addc)
+            agg = torch.empty((B * N, D), dtype=torch.float32, device=pos.device)
+            with torch.cuda.device(pos.device):
+                check(lib.segnn_generic_aggregate(_p(m), B, N, D, _p(agg), ops._stream()), "segnn_generic_aggregate")
+            ops._bump(2)
+            u = pl["g_upd1"].run(pl["upd1"].run(torch.cat([x, agg], dim=1).contiguous(), attr))
+            u = pl["upd2"].run(u, attr)
+            x = ops.add3(x, u)
+            if layer.feature_norm is not None:
+                mul, addc = _bn_eval_columns(layer.feature_norm, layer.hidden_irreps)
+                x = ops.lincomb(x, None, mul, None, addc)
+            per_layer.append(x)
+        h = self.g_pool1.run(self.pool1.run(x, attr))
+        pred = self.pool2.run(h, attr)
+        return (pred, per_layer) if return_layers else pred

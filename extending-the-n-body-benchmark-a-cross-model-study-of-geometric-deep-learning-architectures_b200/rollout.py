@@ -65,7 +65,8 @@ class SelfFeedRollout:
     @torch.no_grad()
     def capture(self):
         """Warm up (packs weights, sets kernel attributes), then capture one step as a CUDA graph."""
-        self.model.packed(self.N - 1)
+        if getattr(self.model, "fused", True) and self.model.compute_mode != "generic":
+            self.model.packed(self.N - 1)
         state = (self.pos.clone(), self.vel.clone(), self.frame.clone())
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))

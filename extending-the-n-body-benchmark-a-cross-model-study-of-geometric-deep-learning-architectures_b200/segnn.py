@@ -39,11 +39,11 @@ class SEGNNLayer(nn.Module):
             self.message_norm = BatchNorm(hidden_irreps)
         elif norm == "instance":
             raise NotImplementedError("norm='instance' cannot be selected by the reference's create_model; not built")
-        if list(hidden_irreps) != [(hidden_irreps[0][0], 0, 1), (hidden_irreps[0][0], 1, -1)] \
-                or list(add) != [(2, 0, 1)] or list(input_irreps) != list(hidden_irreps):
-            raise NotImplementedError(
-                f"kernels are built for hidden irreps n x0e + n x1o (lmax_h = 1) with 2x0e message features; "
-                f"got hidden={hidden_irreps}, additional={add}")
+        if list(add) != [(2, 0, 1)] or list(input_irreps) != list(hidden_irreps):
+            raise NotImplementedError(f"SEGNN layers take hidden -> hidden irreps with 2x0e message features; got "
+                                      f"input={input_irreps}, hidden={hidden_irreps}, additional={add}")
+        # the fused kernels are specialised for n x0e + n x1o (lmax_h = 1); anything else runs the generic path
+        self.fused = list(hidden_irreps) == [(hidden_irreps[0][0], 0, 1), (hidden_irreps[0][0], 1, -1)]
         self.n = hidden_irreps[0][0]
 
     # -- weight packing -----------------------------------------------------------------------------------------
@@ -92,6 +92,8 @@ class SEGNNLayer(nn.Module):
         ``edge_attr`` / ``additional_message_features`` are ignored and recomputed from ``pos`` / ``mass``."""
         if pos is None or mass is None or num_graphs is None or n_nodes is None:
             raise ValueError("SEGNNLayer.forward needs pos, mass, num_graphs, n_nodes (implicit complete graph)")
+        if not self.fused:
+            raise NotImplementedError("standalone SEGNNLayer.forward is built for lmax_h = 1; use SEGNN.forward")
         if self.training:
             raise NotImplementedError("train-mode BatchNorm for the standalone layer: use SEGNN.forward")
         w = self.pack(n_nodes - 1)
@@ -112,8 +114,8 @@ class SEGNN(nn.Module):
         super().__init__()
         if task != "node":
             raise NotImplementedError("only task='node' is on the N-body path")
-        if int(lmax_attr) != 1 or int(lmax_h) != 1:
-            raise NotImplementedError(f"kernels are built for lmax_h = lmax_attr = 1 (got {lmax_h}, {lmax_attr})")
+        if int(lmax_attr) != 1 or int(lmax_h) not in (1, 2):
+            raise NotImplementedError(f"built for lmax_attr = 1 and lmax_h in (1, 2) (got {lmax_h}, {lmax_attr})")
         if Irreps(str(input_irreps)) != Irreps("2x1o+1x0e") or Irreps(str(output_irreps)) != Irreps("2x1o"):
             raise NotImplementedError("kernels are built for the N-body irreps: input 2x1o+1x0e, output 2x1o")
         self.hidden_features, self.lmax_h, self.lmax_attr, self.num_layers = hidden_features, lmax_h, lmax_attr, num_layers
@@ -133,6 +135,10 @@ class SEGNN(nn.Module):
         self.pre_pool2 = O3TensorProduct(h, Irreps(str(output_irreps)), self.node_attr_irreps)
         self._pack_key = None
         self._packed = None
+        # lmax_h = 1 runs the fused kernels (compute_mode 'fp32' / 'bf16'); other hidden irreps (lmax_h = 2, BASELINE
+        # config 3) run the generic-irreps fp32 path (generic.py), which is also selectable with compute_mode='generic'
+        self.fused = all(layer.fused for layer in self.layers)
+        self._generic = None
 
     def get_model_size(self):
         return self.hidden_features
@@ -179,6 +185,14 @@ class SEGNN(nn.Module):
         """pos, vel [nodes,3] fp32 CUDA, mass [nodes] -> pred [nodes,6] fp32 (eval-mode BatchNorm)."""
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         bn_training = self.training and self.norm == "batch"
+        if not self.fused or self.compute_mode == "generic":
+            if needs_grad or bn_training:
+                raise NotImplementedError("the generic-irreps path (lmax_h != 1 or compute_mode='generic') is inference "
+                                          "only: call model.eval() under torch.no_grad()")
+            from .generic import GenericRunner
+            if self._generic is None or self._generic.embed.instr.device != pos.device:
+                self._generic = GenericRunner(self, pos.device)
+            return self._generic.forward(pos, vel, mass, batch_size, num_nodes, return_layers)
         if needs_grad or bn_training:
             return self._forward_train(pos, vel, mass, batch_size, num_nodes, bn_training, needs_grad, return_layers)
         w = self.packed(num_nodes - 1)
@@ -262,5 +276,6 @@ class SEGNN(nn.Module):
             node_attr[:, 0] = 1.0  # catch_isolated_nodes, segnn.py:148
         out = self.forward_state(pos, vel, mass, b, n_nodes, x_in, node_attr, return_layers)
         if return_layers:
-            return out[0].to(dtype), [packing.from_planar(h).to(dtype) for h in out[1]]
+            unpack = packing.from_planar if (self.fused and self.compute_mode != "generic") else (lambda h: h)
+            return out[0].to(dtype), [unpack(h).to(dtype) for h in out[1]]
         return out.to(dtype)

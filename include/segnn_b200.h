@@ -207,6 +207,30 @@ int segnn_embed_bwd(const float* x_in, const float* node_attr, const float* dh, 
 int segnn_head_bwd(const float* h, const float* node_attr, const float* w_head, const float* dpred, int nodes, int n,
                    float* dh, float* contrib, segnn_stream_t stream);
 
+/* ---- generic-irreps path (fp32 inference for hidden irreps the fused kernels are not specialised for, e.g. lmax_h = 2) */
+
+/* O3TensorProduct.forward_tp_rescale_bias (models/segnn/o3_building_blocks.py:150-162) for arbitrary irreps:
+ * out[row] = FullyConnectedTensorProduct(x1[row], x2[row]) with e3nn path normalisation x the reference's
+ * sqrt_k_correction, + bias.  instr [n_instr][9] = (offset, mul, 2l+1 of in1; offset, 2l+1 of in2; offset, mul, 2l+1
+ * of out; flat weight offset) in e3nn instruction order; cg [n_instr][5][3][5] = real Wigner 3j scaled by the net path
+ * coefficient; bias: dense [dout] (zeros on l > 0 columns) or NULL. */
+int segnn_generic_tp(const float* x1, int d1, const float* x2, int d2, int64_t rows, const float* weights,
+                     const int* instr, int n_instr, const float* cg, const float* bias, int dout, float* out,
+                     segnn_stream_t stream);
+
+/* e3nn Gate as used by O3TensorProductSwishGate (:186-203): x [rows][n_scalars + n_gates + d_gated] ->
+ * out [rows][n_scalars + d_gated]; gate_index [d_gated] = gate of every gated column. */
+int segnn_generic_gate(const float* x, int64_t rows, int n_scalars, int n_gates, int d_gated, const int* gate_index,
+                       float* out, segnn_stream_t stream);
+
+/* cat(x_i, x_j, additional_message_features) in the reference edge order (models/segnn/segnn.py:264-277):
+ * x [nodes][D], add [E][d_add] -> out [E][2D + d_add]. */
+int segnn_generic_message_input(const float* x, const float* add, int B, int N, int D, int d_add, float* out,
+                                segnn_stream_t stream);
+
+/* Deterministic scatter-sum over the implicit complete graph (segnn.py:205): m [E][D] -> agg [nodes][D]. */
+int segnn_generic_aggregate(const float* m, int B, int N, int D, float* agg, segnn_stream_t stream);
+
 /* ---- rollout macros (evaluation of rollouts) ------------------------------------------- */
 
 /* trainer.py:888-927 `_compute_nbody_energies` and datasets/nbody/visualization_utils.py:959-960 (momentum), per

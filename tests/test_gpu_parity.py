@@ -366,3 +366,48 @@ def test_rollout_macros_within_reference_statistical_tolerance(mode):
     assert min(ps) >= 0.05 and combined >= 0.05
     got = S.macros.nbody_energies(tp, tv, B, N, G, soft)
     assert S.macros.energy_ratio_steps(got["total"], series_ref["total"]) == steps + 1
+
+
+# ---- generic-irreps path (lmax_h = 2, BASELINE config 3) -------------------------------------------------------------
+@pytest.mark.parametrize("H,lmax_h,L,B,N", [(32, 2, 2, 2, 6), (192, 2, 1, 1, 10), (64, 2, 3, 3, 5), (64, 1, 2, 3, 5)])
+def test_generic_irreps_path_matches_oracle(H, lmax_h, L, B, N):
+    """Per-layer parity of the generic fp32 kernels (any hidden irreps; lmax_h = 2 is BASELINE config 3) at the fp32
+    tolerance 1e-5; for lmax_h = 1 the same path is selected with compute_mode='generic' and must also agree with the
+    fused kernels."""
+    torch.manual_seed(H + lmax_h)
+    om = O.SEGNN(hidden_features=H, num_layers=L, lmax_h=lmax_h).eval()
+    O.perturb_bn_buffers(om, seed=5)
+    m = S.SEGNN(hidden_features=H, num_layers=L, lmax_h=lmax_h, compute_mode="generic")
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().eval()
+    pos, vel, mass = O.synthetic_system(B, N, seed=6)
+    with torch.no_grad():
+        ref, ref_layers = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N),
+                             return_layers=True)
+        out, layers = m(gpu_graph(pos, vel, mass, B, N), return_layers=True)
+        print(f"generic H={H} lmax_h={lmax_h}: per-layer", [f"{rel(a, b):.2e}" for a, b in zip(layers, ref_layers)],
+              f"out {rel(out, ref):.2e}")
+        for a, b in zip(layers, ref_layers):
+            assert rel(a, b) < 1e-5
+        assert rel(out, ref) < 1e-5
+        if lmax_h == 1:
+            m.compute_mode = "fp32"
+            fused = m(gpu_graph(pos, vel, mass, B, N))
+            assert float((fused - out).abs().max() / out.abs().max()) < 1e-5
+
+
+def test_generic_rollout_lmax2_matches_oracle():
+    torch.manual_seed(9)
+    om = O.SEGNN(hidden_features=32, num_layers=2, lmax_h=2).eval()
+    O.perturb_bn_buffers(om, seed=2)
+    m = S.SEGNN(hidden_features=32, num_layers=2, lmax_h=2)
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().eval()
+    B, N, steps = 3, 5, 6
+    pos, vel, mass = O.synthetic_system(B, N, seed=4)
+    ref_loc, ref_vel = O.rollout(om, pos, vel, mass, steps)
+    roll = S.SelfFeedRollout(m, B, N, "cuda", max_frames=steps + 1)
+    roll.reset(pos, vel, mass)
+    tp, tv = roll.run(steps)
+    got_loc = tp.reshape(steps + 1, B, N, 3).permute(1, 0, 2, 3)
+    assert rel(got_loc, ref_loc) < 5e-5

@@ -50,7 +50,10 @@ def test_irreps_and_sizing():
     assert str((2 * h + S.Irreps("2x0e")).simplify()) == "96x0e+96x1o+96x0e+96x1o+2x0e"
     assert (h + h).simplify().dim == 768
     with pytest.raises(NotImplementedError):
-        S.SEGNN(hidden_features=64, lmax_h=2)
+        S.SEGNN(hidden_features=64, lmax_h=3)
+    m2 = S.SEGNN(hidden_features=192, lmax_h=2, num_layers=6)  # BASELINE config 3: generic-irreps path
+    assert str(m2.hidden_irreps) == "73x0e+73x1o+73x2e" and not m2.fused
+    assert sum(p.numel() for p in m2.parameters()) == 2053709
 
 
 def test_state_dict_interchange_with_oracle():
@@ -168,6 +171,18 @@ def test_training_orchestration_and_batchnorm_algebra_vs_oracle(bn_train):
     for k, b in m.state_dict().items():
         if "running" in k:
             assert float((sd[k] - b).abs().max()) < 1e-10, k
+
+
+def test_real_wigner_3j_matches_oracle_and_closed_forms():
+    import numpy as np
+    from segnn_b200 import cg
+    for ls in [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0), (1, 1, 2), (2, 0, 2), (2, 1, 1)]:
+        assert np.abs(cg.real_wigner_3j(*ls) - O.wigner_3j(*ls).numpy()).max() < 1e-14
+        assert abs(np.linalg.norm(cg.real_wigner_3j(*ls)) - 1.0) < 1e-14
+    c110 = cg.real_wigner_3j(1, 1, 0)[:, :, 0]
+    assert np.abs(c110 - np.eye(3) / np.sqrt(3)).max() < 1e-14          # (1,1,0) = x.y / sqrt(3)
+    c112 = cg.real_wigner_3j(1, 1, 2)
+    assert abs(c112[0, 2, 0] - 1 / np.sqrt(10)) < 1e-14 and abs(c112[1, 1, 2] - 2 / np.sqrt(30)) < 1e-14
 
 
 def test_noam_rate_matches_reference_formula():

@@ -39,6 +39,9 @@ PROTOTYPES = {
     "segnn_colsum_workspace": (_c.c_int64, [_c.c_int64, _int]),
     "segnn_colsum": (_int, [_ptr, _ptr, _c.c_int64, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_lincomb": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c.c_int64, _int, _ptr, _ptr]),
+    "segnn_bn_coeffs_fwd": (_int, [_ptr, _ptr, _int, _int, _c.c_double, _c.c_double, _ptr, _ptr, _ptr, _ptr, _c.c_double,
+                                   _c.c_double, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_bn_coeffs_bwd": (_int, [_ptr, _ptr, _int, _c.c_double, _c.c_double, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _ptr]),
     "segnn_add3": (_int, [_ptr, _ptr, _ptr, _c.c_int64, _ptr, _ptr]),
     "segnn_tp_combine_bwd": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "segnn_node_gemm_wgrad_workspace": (_c.c_int64, [_int, _int, _int]),

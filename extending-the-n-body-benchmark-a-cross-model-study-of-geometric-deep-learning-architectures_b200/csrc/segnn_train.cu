@@ -271,6 +271,92 @@ __global__ void add3_kernel(const float* __restrict__ a, const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// e3nn BatchNorm coefficients (models/segnn/segnn.py:233-235): one thread per channel turns the column sums into the
+// folded affine of the forward pass (+ running-statistics update) or into the (A, B, C) coefficients of the backward
+// pass and the parameter gradients.  Replaces ~60 tiny elementwise launches per BatchNorm and step.
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_coeffs_fwd_kernel(const float* __restrict__ sums, const float* __restrict__ sq, int v_planes, int n,
+                                     double rows, double deg, const float* __restrict__ weight,
+                                     const float* __restrict__ bias, float* __restrict__ running_mean,
+                                     float* __restrict__ running_var, double eps, double momentum, int training,
+                                     int update, float* __restrict__ cols, float* __restrict__ stats) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  double mean, var_s, var_v;
+  if (training) {
+    mean = (double)sums[w] / rows;
+    var_s = fmax((double)sq[w] / rows - mean * mean, 0.0);
+    double sv = 0.0;
+    for (int p = 0; p < v_planes; ++p) sv += (double)sq[n + p * n + w];
+    var_v = sv / (3.0 * rows);
+  } else {
+    mean = running_mean[w];
+    var_s = running_var[w];
+    var_v = running_var[n + w];
+  }
+  const double rs_s = rsqrt(var_s + eps), rs_v = rsqrt(var_v + eps);
+  const double mul_s = weight[w] * rs_s, mul_v = weight[n + w] * rs_v;
+  float* mulc = cols;
+  float* addc = cols + 4 * n;
+  mulc[w] = (float)mul_s;
+  mulc[n + w] = mulc[2 * n + w] = mulc[3 * n + w] = (float)mul_v;
+  addc[w] = (float)(deg * ((double)bias[w] - mean * mul_s));
+  addc[n + w] = addc[2 * n + w] = addc[3 * n + w] = 0.f;
+  stats[w] = (float)mean;
+  stats[n + w] = (float)var_s;
+  stats[2 * n + w] = (float)var_v;
+  stats[3 * n + w] = (float)rs_s;
+  stats[4 * n + w] = (float)rs_v;
+  if (training && update) {
+    running_mean[w] = (float)((1.0 - momentum) * running_mean[w] + momentum * mean);
+    running_var[w] = (float)((1.0 - momentum) * running_var[w] + momentum * var_s);
+    running_var[n + w] = (float)((1.0 - momentum) * running_var[n + w] + momentum * var_v);
+  }
+}
+
+__global__ void bn_coeffs_bwd_kernel(const float* __restrict__ sum_g, const float* __restrict__ sum_gx, int n,
+                                     double rows, double deg, const float* __restrict__ weight,
+                                     const float* __restrict__ stats, int training, float* __restrict__ cols,
+                                     float* __restrict__ edge, float* __restrict__ dparam) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  const double mean = stats[w], rs_s = stats[3 * n + w], rs_v = stats[4 * n + w];
+  const double w_s = weight[w], w_v = weight[n + w];
+  const double sg_s = deg * (double)sum_g[w];
+  const double sgx_s = sum_gx[w];
+  const double sgx_v = (double)sum_gx[n + w] + (double)sum_gx[2 * n + w] + (double)sum_gx[3 * n + w];
+  const double dgamma_s = rs_s * (sgx_s - mean * sg_s), dgamma_v = rs_v * sgx_v;
+  const double A_s = w_s * rs_s, A_v = w_v * rs_v;
+  double B_s = 0.0, B_v = 0.0, C_s = 0.0;
+  if (training) {
+    const double c1 = sg_s / rows, c2 = dgamma_s / rows;
+    B_s = -w_s * rs_s * rs_s * c2;
+    C_s = -w_s * rs_s * c1 - B_s * mean;
+    B_v = -w_v * rs_v * rs_v * rs_v * sgx_v / (3.0 * rows);
+  }
+  float* A4 = cols;
+  float* B4 = cols + 4 * n;
+  float* C4 = cols + 8 * n;
+  A4[w] = (float)A_s;
+  B4[w] = (float)B_s;
+  C4[w] = (float)C_s;
+#pragma unroll
+  for (int p = 1; p < 4; ++p) {
+    A4[p * n + w] = (float)A_v;
+    B4[p * n + w] = (float)B_v;
+    C4[p * n + w] = 0.f;
+  }
+  edge[w] = (float)A_s;
+  edge[n + w] = (float)A_v;
+  edge[2 * n + w] = (float)B_s;
+  edge[3 * n + w] = (float)B_v;
+  edge[4 * n + w] = (float)C_s;
+  dparam[w] = (float)dgamma_s;
+  dparam[n + w] = (float)dgamma_v;
+  dparam[2 * n + w] = (float)sg_s;
+}
+
 static inline int grid_for_train(int64_t total, int threads) {
   int64_t b = (total + threads - 1) / threads;
   const int64_t cap = 148LL * 32;
@@ -313,6 +399,30 @@ int segnn_lincomb(const float* dy, const float* x, const float* A, const float* 
   if (rows == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(dy && A && out && (x == nullptr || B != nullptr), "null pointer");
   lincomb_kernel<<<grid_for_train(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, A, B, C, rows, cols, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_bn_coeffs_fwd(const float* sums, const float* sq, int v_planes, int n, double rows, double deg,
+                        const float* weight, const float* bias, float* running_mean, float* running_var, double eps,
+                        double momentum, int training, int update, float* cols, float* stats, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(n >= 1 && rows > 0 && v_planes >= 1 && v_planes <= 3, "bad arguments");
+  SEGNN_CHECK_ARG(weight && bias && running_mean && running_var && cols && stats && (!training || (sums && sq)),
+                  "null pointer");
+  bn_coeffs_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, sq, v_planes, n, rows, deg, weight, bias,
+                                                                         running_mean, running_var, eps, momentum,
+                                                                         training, update, cols, stats);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_bn_coeffs_bwd(const float* sum_g, const float* sum_gx, int n, double rows, double deg, const float* weight,
+                        const float* stats, int training, float* cols, float* edge, float* dparam,
+                        segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(n >= 1 && rows > 0, "bad arguments");
+  SEGNN_CHECK_ARG(sum_g && sum_gx && weight && stats && cols && edge && dparam, "null pointer");
+  bn_coeffs_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum_g, sum_gx, n, rows, deg, weight, stats,
+                                                                         training, cols, edge, dparam);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

@@ -255,8 +255,9 @@ def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_e
     dev = pos.device
     f = dict(dtype=torch.float32, device=dev)
     dP, dQ = torch.empty((nodes, 4, 3 * n), **f), torch.empty((nodes, 4, 3 * n), **f)
-    g = dict(ss=torch.zeros((n, 2 * n), **f), vs=torch.zeros((n, 2 * n), **f), sv=torch.zeros((n, n), **f),
-             vv=torch.zeros((n, n), **f), b=torch.zeros((2 * n,), **f))
+    gz = torch.zeros(6 * n * n + 2 * n, **f)  # one fill for all atomically-accumulated gradient blocks
+    g = dict(ss=gz[: 2 * n * n].view(n, 2 * n), vs=gz[2 * n * n: 4 * n * n].view(n, 2 * n),
+             sv=gz[4 * n * n: 5 * n * n].view(n, n), vv=gz[5 * n * n: 6 * n * n].view(n, n), b=gz[6 * n * n:])
     dwe_partial = torch.empty((nodes, 6 * n), **f)
     w2t = {k: w2[k].t().contiguous() for k in ("ss", "vs", "sv", "vv")}
     with torch.cuda.device(dev):
@@ -293,3 +294,40 @@ def head_bwd(h, node_attr, w_head, dpred, n: int):
     _bump()
     s = colsum(contrib).view(2, 2, n)  # (ws0, ws1), (wv0, wv1)
     return dh, s.permute(0, 2, 1).contiguous()
+
+
+def bn_forward_coeffs(bn, n: int, rows: float, deg: float, sums, sq, v_planes: int, training: bool, update: bool):
+    """e3nn BatchNorm statistics -> folded affine (one launch). bn: dict(weight, bias, running_mean, running_var, eps,
+    momentum). Returns dict(mulcols [4n], addcols [4n], stats [5, n])."""
+    dev = bn["weight"].device
+    cols = torch.empty((2, 4 * n), dtype=torch.float32, device=dev)
+    stats = torch.empty((5, n), dtype=torch.float32, device=dev)
+    rm, rv = bn["running_mean"], bn["running_var"]
+    native = rm.dtype == torch.float32 and rv.dtype == torch.float32 and rm.is_contiguous() and rv.is_contiguous()
+    rm32, rv32 = (rm, rv) if native else (rm.to(torch.float32).contiguous(), rv.to(torch.float32).contiguous())
+    with torch.cuda.device(dev):
+        check(lib.segnn_bn_coeffs_fwd(_p(sums), _p(sq), v_planes, n, float(rows), float(deg), _p(bn["weight"].contiguous()),
+                                      _p(bn["bias"].contiguous()), _p(rm32), _p(rv32), float(bn["eps"]),
+                                      float(bn["momentum"]), int(training), int(update), _p(cols), _p(stats), _stream()),
+              "segnn_bn_coeffs_fwd")
+    _bump()
+    if not native and training and update:  # e.g. a .double() module: write the updated statistics back
+        rm.copy_(rm32)
+        rv.copy_(rv32)
+    return dict(mulcols=cols[0], addcols=cols[1], stats=stats)
+
+
+def bn_backward_coeffs(bn, st, n: int, rows: float, deg: float, sum_g, sum_gx, training: bool):
+    """Returns dict(A4, B4, C4 [4n] planar-column coefficients; edge = (bn_a [2n], bn_b [2n], bn_c [n]); dweight [2n],
+    dbias [n])."""
+    dev = sum_g.device
+    cols = torch.empty((3, 4 * n), dtype=torch.float32, device=dev)
+    edge = torch.empty(5 * n, dtype=torch.float32, device=dev)
+    dparam = torch.empty(3 * n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.segnn_bn_coeffs_bwd(_p(sum_g), _p(sum_gx), n, float(rows), float(deg), _p(bn["weight"].contiguous()),
+                                      _p(st["stats"]), int(training), _p(cols), _p(edge), _p(dparam), _stream()),
+              "segnn_bn_coeffs_bwd")
+    _bump()
+    return dict(A4=cols[0], B4=cols[1], C4=cols[2], bn_a=edge[: 2 * n], bn_b=edge[2 * n: 4 * n], bn_c=edge[4 * n:],
+                dweight=dparam[: 2 * n], dbias=dparam[2 * n:])

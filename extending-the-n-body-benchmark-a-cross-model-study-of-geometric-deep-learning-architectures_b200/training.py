@@ -10,7 +10,8 @@ e3nn BatchNorm (segnn.py:233-235) in train mode is an affine map given its batch
 BatchNorm those statistics are sums over all E edges, which the edge kernel delivers as per-receiver partial sums
 (sum_j m, sum_j m^2) reduced here by a deterministic column sum. With G_i = dL/d agg_i, the gradient that reaches
 every message of receiver i is dm_ij = A * G_i + B * m_ij + C with per-channel A, B, C computed from node-level
-reductions (sum_i G_i, sum_i G_i * agg_raw_i): see `_bn_backward_coeffs`.
+reductions (sum_i G_i, sum_i G_i * agg_raw_i): `segnn_bn_coeffs_bwd` (the algebra is restated in torch in
+tests/emulate.py and checked against autograd through the oracle).
 
 `backend` is the kernel namespace (``ops``: the C ABI). Tests substitute a torch emulation to check this
 orchestration and the BatchNorm algebra on CPU; the product path always uses ``ops``.
@@ -59,63 +60,6 @@ def unflatten_packed(leaves, spec):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# BatchNorm helpers (per-channel vectors of length n; tiny, kept in torch on the device)
-# ---------------------------------------------------------------------------------------------------------------
-def _planar_cols(s, v):
-    """per-channel scalar-plane and vector-plane coefficients -> one value per planar column [4n]."""
-    return torch.cat([s, v, v, v]).contiguous()
-
-
-def _bn_forward_coeffs(bn, n, rows, deg, sum_x, sumsq_s, sumsq_v, training):
-    """Statistics + folded affine of one e3nn BatchNorm over `rows` rows (rows = E for messages, nodes for
-    features). sum_x [n]: sum of the scalar channel over rows; sumsq_s [n]: sum of squares; sumsq_v [n]: sum of
-    |v|^2. Returns dict(mean, rs_s, rs_v, mul_s, mul_v, add) where out_s = mul_s * x + add / deg (per row)."""
-    w_s, w_v = bn["weight"][:n], bn["weight"][n:]
-    if training:
-        mean64 = sum_x.double() / rows
-        var_s = (sumsq_s.double() / rows - mean64 * mean64).clamp_min(0.0).to(w_s.dtype)
-        mean = mean64.to(w_s.dtype)
-        var_v = sumsq_v / (3.0 * rows)
-    else:
-        f = lambda b: b.to(w_s.dtype)
-        mean, var_s, var_v = f(bn["running_mean"]), f(bn["running_var"][:n]), f(bn["running_var"][n:])
-    rs_s = (var_s + bn["eps"]).rsqrt()
-    rs_v = (var_v + bn["eps"]).rsqrt()
-    mul_s, mul_v = w_s * rs_s, w_v * rs_v
-    add = deg * (bn["bias"] - mean * mul_s)
-    return dict(mean=mean, var_s=var_s, var_v=var_v, rs_s=rs_s, rs_v=rs_v, mul_s=mul_s, mul_v=mul_v, add=add)
-
-
-def _bn_backward_coeffs(bn, st, n, rows, deg, sum_g, sum_gx, training):
-    """sum_g [4n] = sum_i G_i, sum_gx [4n] = sum_i G_i * x_i (planar columns; x_i = raw aggregate or pre-norm
-    feature). Returns A_s, A_v, B_s, B_v, C_s and the parameter gradients (dweight [2n], dbias [n])."""
-    w_s, w_v = bn["weight"][:n], bn["weight"][n:]
-    sg_s = deg * sum_g[:n]                                   # sum over rows of dL/dy (scalars)
-    sgx_s = sum_gx[:n]                                       # sum over rows of dL/dy * x
-    sgx_v = sum_gx[n:2 * n] + sum_gx[2 * n:3 * n] + sum_gx[3 * n:]
-    mean, rs_s, rs_v = st["mean"], st["rs_s"], st["rs_v"]
-    dgamma_s = rs_s * (sgx_s - mean * sg_s)
-    dgamma_v = rs_v * sgx_v
-    dbeta = sg_s
-    A_s, A_v = w_s * rs_s, w_v * rs_v
-    if training:
-        c1 = sg_s / rows
-        c2 = dgamma_s / rows                                 # mean over rows of dL/dy * x_hat
-        B_s = -w_s * rs_s * rs_s * c2
-        C_s = -w_s * rs_s * c1 - B_s * mean
-        B_v = -w_v * rs_v * rs_v * rs_v * sgx_v / (3.0 * rows)
-    else:
-        B_s, C_s, B_v = torch.zeros_like(A_s), torch.zeros_like(A_s), torch.zeros_like(A_v)
-    return A_s, A_v, B_s, B_v, C_s, torch.cat([dgamma_s, dgamma_v]), dbeta
-
-
-def _update_running(bn, st):
-    mom = bn["momentum"]
-    bn["running_mean"].mul_(1 - mom).add_(mom * st["mean"])
-    bn["running_var"].mul_(1 - mom).add_(mom * torch.cat([st["var_s"], st["var_v"]]))
-
-
-# ---------------------------------------------------------------------------------------------------------------
 # forward (fp32 kernels), saving node-level tensors only
 # ---------------------------------------------------------------------------------------------------------------
 def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: bool, backend=None,
@@ -136,11 +80,9 @@ def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: 
         if lw["bn_msg"] is not None:
             sums = be.colsum(agg_raw.view(nodes, 4 * n))
             sq = be.colsum(mom)
-            st = _bn_forward_coeffs(lw["bn_msg"], n, float(E), float(deg), sums[:n], sq[:n], sq[n:], bn_training)
-            agg = be.lincomb(agg_raw.view(nodes, 4 * n), None, _planar_cols(st["mul_s"], st["mul_v"]), None,
-                             _planar_cols(st["add"], torch.zeros_like(st["add"]))).view(nodes, 4, n)
-            if bn_training and update_running_stats:
-                _update_running(lw["bn_msg"], st)
+            st = be.bn_forward_coeffs(lw["bn_msg"], n, float(E), float(deg), sums, sq, 1, bn_training,
+                                      update_running_stats)
+            agg = be.lincomb(agg_raw.view(nodes, 4 * n), None, st["mulcols"], None, st["addcols"]).view(nodes, 4, n)
             rec["bn_msg"] = st
         else:
             agg = agg_raw
@@ -153,12 +95,9 @@ def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: 
             flat = pre.view(nodes, 4 * n)
             sums = be.colsum(flat)
             sq = be.colsum(flat, None, 1)
-            st = _bn_forward_coeffs(lw["bn_feat"], n, float(nodes), 1.0, sums[:n], sq[:n],
-                                    sq[n:2 * n] + sq[2 * n:3 * n] + sq[3 * n:], bn_training)
-            h = be.lincomb(flat, None, _planar_cols(st["mul_s"], st["mul_v"]), None,
-                           _planar_cols(st["add"], torch.zeros_like(st["add"]))).view(nodes, 4, n)
-            if bn_training and update_running_stats:
-                _update_running(lw["bn_feat"], st)
+            st = be.bn_forward_coeffs(lw["bn_feat"], n, float(nodes), 1.0, sums, sq, 3, bn_training,
+                                      update_running_stats)
+            h = be.lincomb(flat, None, st["mulcols"], None, st["addcols"]).view(nodes, 4, n)
             rec["bn_feat"] = st
         else:
             h = pre
@@ -211,11 +150,9 @@ def backward_train(W: Dict, saved: Dict, dpred, backend=None):
             flat_pre, flat_dh = rec["pre"].view(nodes, 4 * n), dh.view(nodes, 4 * n)
             sum_g = be.colsum(flat_dh)
             sum_gx = be.colsum(flat_dh, flat_pre, 2)
-            A_s, A_v, B_s, B_v, C_s, dweight, dbias = _bn_backward_coeffs(lw["bn_feat"], rec["bn_feat"], n,
-                                                                          float(nodes), 1.0, sum_g, sum_gx, bn_training)
-            dpre = be.lincomb(flat_dh, flat_pre, _planar_cols(A_s, A_v), _planar_cols(B_s, B_v),
-                              _planar_cols(C_s, torch.zeros_like(C_s))).view(nodes, 4, n)
-            g["bn_feat"] = dict(weight=dweight, bias=dbias)
+            c = be.bn_backward_coeffs(lw["bn_feat"], rec["bn_feat"], n, float(nodes), 1.0, sum_g, sum_gx, bn_training)
+            dpre = be.lincomb(flat_dh, flat_pre, c["A4"], c["B4"], c["C4"]).view(nodes, 4, n)
+            g["bn_feat"] = dict(weight=c["dweight"], bias=c["dbias"])
         else:
             dpre = dh
         # update_layer_2 (+ residual), update_layer_1
@@ -227,16 +164,15 @@ def backward_train(W: Dict, saved: Dict, dpred, backend=None):
             flat_g, flat_raw = dagg.view(nodes, 4 * n), rec["agg_raw"].view(nodes, 4 * n)
             sum_g = be.colsum(flat_g)
             sum_gx = be.colsum(flat_g, flat_raw, 2)
-            A_s, A_v, B_s, B_v, C_s, dweight, dbias = _bn_backward_coeffs(lw["bn_msg"], rec["bn_msg"], n, float(E),
-                                                                          float(deg), sum_g, sum_gx, bn_training)
-            g["bn_msg"] = dict(weight=dweight, bias=dbias)
+            c = be.bn_backward_coeffs(lw["bn_msg"], rec["bn_msg"], n, float(E), float(deg), sum_g, sum_gx, bn_training)
+            g["bn_msg"] = dict(weight=c["dweight"], bias=c["dbias"])
+            bn_a, bn_b, bn_c = c["bn_a"], c["bn_b"], c["bn_c"]
         else:
-            A_s = torch.ones(n, dtype=dagg.dtype, device=dagg.device)
-            A_v, B_s, B_v, C_s = A_s.clone(), torch.zeros_like(A_s), torch.zeros_like(A_s), torch.zeros_like(A_s)
+            bn_a = torch.ones(2 * n, dtype=dagg.dtype, device=dagg.device)
+            bn_b, bn_c = torch.zeros_like(bn_a), torch.zeros(n, dtype=dagg.dtype, device=dagg.device)
         # fused edge layer backward (recompute) -> dP, dQ, message_layer_2 and w_edge gradients
-        dP, dQ, g["msg2"], dwe = be.edge_layer_bwd(pos, mass, B, N, n, rec["p"], rec["q"], m1["w_edge"], m2,
-                                                   torch.cat([A_s, A_v]).contiguous(),
-                                                   torch.cat([B_s, B_v]).contiguous(), C_s.contiguous(), dagg)
+        dP, dQ, g["msg2"], dwe = be.edge_layer_bwd(pos, mass, B, N, n, rec["p"], rec["q"], m1["w_edge"], m2, bn_a, bn_b,
+                                                   bn_c, dagg)
         # message_layer_1 projections: [P | Q] = h @ W (+ bias on P's l=0 columns)
         dw_s, dw_v = be.node_gemm_wgrad(rec["h"], None, dP, dQ, 3 * n)
         dbias1 = be.colsum(dP.view(nodes, 12 * n))[:2 * n]

@@ -168,6 +168,24 @@ int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mod
 int segnn_lincomb(const float* dy, const float* x, const float* A, const float* B, const float* C, int64_t rows,
                   int cols, float* out, segnn_stream_t stream);
 
+/* e3nn BatchNorm (models/segnn/segnn.py:233-235) for hidden irreps n x0e + n x1o from column sums over `rows` rows
+ * (rows = E for the message norm with deg = N-1 messages per receiver folded through the sender sum, rows = nodes and
+ * deg = 1 for the feature norm).  sums [>= n]: sum of the scalar channels; sq [n + v_planes*n]: sums of squares of the
+ * scalar channels, then of the vector planes (v_planes = 1 when already summed over xyz).  weight [2n], bias [n],
+ * running_mean [n], running_var [2n] (updated in place with `momentum` when training && update, e3nn semantics).
+ * Outputs: cols [2][4n] = per planar column (mul, add) of the folded affine; stats [5][n] = (mean, var_s, var_v,
+ * rsqrt(var_s + eps), rsqrt(var_v + eps)) kept for the backward pass.  training == 0 uses the running statistics. */
+int segnn_bn_coeffs_fwd(const float* sums, const float* sq, int v_planes, int n, double rows, double deg,
+                        const float* weight, const float* bias, float* running_mean, float* running_var, double eps,
+                        double momentum, int training, int update, float* cols, float* stats, segnn_stream_t stream);
+
+/* Backward of the same: sum_g [4n] = sum over nodes of dL/d(output) per planar column, sum_gx [4n] = sum of
+ * dL/d(output) * (raw aggregate or pre-norm feature).  cols [3][4n] = (A, B, C) with dL/dx = A*g + B*x + C per planar
+ * column; edge [5n] = (A_s, A_v, B_s, B_v, C_s) for segnn_edge_layer_bwd; dparam [3n] = (dweight [2n], dbias [n]). */
+int segnn_bn_coeffs_bwd(const float* sum_g, const float* sum_gx, int n, double rows, double deg, const float* weight,
+                        const float* stats, int training, float* cols, float* edge, float* dparam,
+                        segnn_stream_t stream);
+
 /* out = a + b + c elementwise (c may be NULL): sums the gradient streams meeting at a layer input (residual,
  * update_layer_1 and message_layer_1 branches of models/segnn/segnn.py:249-304). */
 int segnn_add3(const float* a, const float* b, const float* c, int64_t count, float* out, segnn_stream_t stream);

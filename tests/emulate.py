@@ -164,6 +164,62 @@ def edge_messages(pos, mass, B, N, n, p, q, w_edge, w2):
     return ms, mv, mask
 
 
+# e3nn BatchNorm algebra in torch (what segnn_bn_coeffs_fwd / _bwd compute on the device)
+def _planar_cols(s, v):
+    """per-channel scalar-plane and vector-plane coefficients -> one value per planar column [4n]."""
+    return torch.cat([s, v, v, v]).contiguous()
+
+
+def _bn_forward_coeffs(bn, n, rows, deg, sum_x, sumsq_s, sumsq_v, training):
+    """Statistics + folded affine of one e3nn BatchNorm over `rows` rows (rows = E for messages, nodes for
+    features). sum_x [n]: sum of the scalar channel over rows; sumsq_s [n]: sum of squares; sumsq_v [n]: sum of
+    |v|^2. Returns dict(mean, rs_s, rs_v, mul_s, mul_v, add) where out_s = mul_s * x + add / deg (per row)."""
+    w_s, w_v = bn["weight"][:n], bn["weight"][n:]
+    if training:
+        mean64 = sum_x.double() / rows
+        var_s = (sumsq_s.double() / rows - mean64 * mean64).clamp_min(0.0).to(w_s.dtype)
+        mean = mean64.to(w_s.dtype)
+        var_v = sumsq_v / (3.0 * rows)
+    else:
+        f = lambda b: b.to(w_s.dtype)
+        mean, var_s, var_v = f(bn["running_mean"]), f(bn["running_var"][:n]), f(bn["running_var"][n:])
+    rs_s = (var_s + bn["eps"]).rsqrt()
+    rs_v = (var_v + bn["eps"]).rsqrt()
+    mul_s, mul_v = w_s * rs_s, w_v * rs_v
+    add = deg * (bn["bias"] - mean * mul_s)
+    return dict(mean=mean, var_s=var_s, var_v=var_v, rs_s=rs_s, rs_v=rs_v, mul_s=mul_s, mul_v=mul_v, add=add)
+
+
+def _bn_backward_coeffs(bn, st, n, rows, deg, sum_g, sum_gx, training):
+    """sum_g [4n] = sum_i G_i, sum_gx [4n] = sum_i G_i * x_i (planar columns; x_i = raw aggregate or pre-norm
+    feature). Returns A_s, A_v, B_s, B_v, C_s and the parameter gradients (dweight [2n], dbias [n])."""
+    w_s, w_v = bn["weight"][:n], bn["weight"][n:]
+    sg_s = deg * sum_g[:n]                                   # sum over rows of dL/dy (scalars)
+    sgx_s = sum_gx[:n]                                       # sum over rows of dL/dy * x
+    sgx_v = sum_gx[n:2 * n] + sum_gx[2 * n:3 * n] + sum_gx[3 * n:]
+    mean, rs_s, rs_v = st["mean"], st["rs_s"], st["rs_v"]
+    dgamma_s = rs_s * (sgx_s - mean * sg_s)
+    dgamma_v = rs_v * sgx_v
+    dbeta = sg_s
+    A_s, A_v = w_s * rs_s, w_v * rs_v
+    if training:
+        c1 = sg_s / rows
+        c2 = dgamma_s / rows                                 # mean over rows of dL/dy * x_hat
+        B_s = -w_s * rs_s * rs_s * c2
+        C_s = -w_s * rs_s * c1 - B_s * mean
+        B_v = -w_v * rs_v * rs_v * rs_v * sgx_v / (3.0 * rows)
+    else:
+        B_s, C_s, B_v = torch.zeros_like(A_s), torch.zeros_like(A_s), torch.zeros_like(A_v)
+    return A_s, A_v, B_s, B_v, C_s, torch.cat([dgamma_s, dgamma_v]), dbeta
+
+
+def _update_running(bn, st):
+    mom = bn["momentum"]
+    bn["running_mean"].mul_(1 - mom).add_(mom * st["mean"])
+    bn["running_var"].mul_(1 - mom).add_(mom * torch.cat([st["var_s"], st["var_v"]]))
+
+
+
 class TorchBackend:
     MODE_FP32 = 0
 
@@ -254,3 +310,20 @@ class TorchBackend:
             ww = w_head.detach().clone().requires_grad_(True)
             gh, gw = torch.autograd.grad(head(hh, attr, ww), [hh, ww], dpred)
         return gh, gw
+
+    @staticmethod
+    def bn_forward_coeffs(bn, n, rows, deg, sums, sq, v_planes, training, update):
+        sq_v = sq[n:2 * n] if v_planes == 1 else sq[n:2 * n] + sq[2 * n:3 * n] + sq[3 * n:4 * n]
+        st = _bn_forward_coeffs(bn, n, rows, deg, sums[:n], sq[:n], sq_v, training)
+        if training and update:
+            _update_running(bn, st)
+        st["mulcols"] = _planar_cols(st["mul_s"], st["mul_v"])
+        st["addcols"] = _planar_cols(st["add"], torch.zeros_like(st["add"]))
+        return st
+
+    @staticmethod
+    def bn_backward_coeffs(bn, st, n, rows, deg, sum_g, sum_gx, training):
+        A_s, A_v, B_s, B_v, C_s, dweight, dbias = _bn_backward_coeffs(bn, st, n, rows, deg, sum_g, sum_gx, training)
+        z = torch.zeros_like(C_s)
+        return dict(A4=_planar_cols(A_s, A_v), B4=_planar_cols(B_s, B_v), C4=_planar_cols(C_s, z),
+                    bn_a=torch.cat([A_s, A_v]), bn_b=torch.cat([B_s, B_v]), bn_c=C_s, dweight=dweight, dbias=dbias)

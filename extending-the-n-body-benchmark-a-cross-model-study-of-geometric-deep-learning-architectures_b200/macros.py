@@ -18,7 +18,7 @@ import torch
 from ._lib import check, lib
 from . import ops
 
-__all__ = ["energy_momentum", "nbody_energies", "momentum_statistics", "ks_statistic", "ks_p",
+__all__ = ["event_counters", "energy_momentum", "nbody_energies", "momentum_statistics", "ks_statistic", "ks_p",
            "combine_pvalues_fisher", "energy_ratio_steps"]
 
 
@@ -40,6 +40,32 @@ def energy_momentum(traj_pos: torch.Tensor, traj_vel: torch.Tensor, batch_size: 
               "segnn_macros_energy_momentum")
     ops._bump()
     return out[..., 0], out[..., 1], out[..., 2]
+
+
+def event_counters(traj_pos: torch.Tensor, traj_vel: torch.Tensor, batch_size: int, num_nodes: int,
+                   time_threshold: int = 3, contact_distance: float = 0.5, leave_distance: float = 15.0,
+                   turn_angle_degrees: float = 30.0) -> Dict[str, np.ndarray]:
+    """visualization_utils.py:1093-1222 per simulation: {'stickings', 'collisions', 'bodies_left', 'sharp_turns'}
+    (int64 [B]) and 'max_com_distance' (float64 [B]), from the device trajectory buffers [frames, B*N, 3]."""
+    if not traj_pos.is_cuda:
+        raise RuntimeError("macros run on the device trajectory buffers: there is no CPU fallback")
+    traj_pos = traj_pos.to(torch.float32).contiguous()
+    traj_vel = traj_vel.to(torch.float32).contiguous()
+    frames = traj_pos.shape[0]
+    assert traj_pos.shape == (frames, batch_size * num_nodes, 3) and traj_vel.shape == traj_pos.shape
+    counts = torch.empty((batch_size, 4), dtype=torch.int32, device=traj_pos.device)
+    com = torch.empty((batch_size,), dtype=torch.float32, device=traj_pos.device)
+    with torch.cuda.device(traj_pos.device):
+        check(lib.segnn_macros_counters(ctypes.c_void_p(traj_pos.data_ptr()), ctypes.c_void_p(traj_vel.data_ptr()),
+                                        frames, batch_size, num_nodes, int(time_threshold), float(contact_distance),
+                                        float(leave_distance), float(turn_angle_degrees),
+                                        ctypes.c_void_p(counts.data_ptr()), ctypes.c_void_p(com.data_ptr()),
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              "segnn_macros_counters")
+    ops._bump()
+    c = counts.cpu().numpy().astype(np.int64)
+    return {"stickings": c[:, 0], "collisions": c[:, 1], "bodies_left": c[:, 2], "sharp_turns": c[:, 3],
+            "max_com_distance": com.double().cpu().numpy()}
 
 
 def nbody_energies(traj_pos, traj_vel, batch_size: int, num_nodes: int, G: float, softening: float) -> Dict[str, np.ndarray]:

@@ -258,6 +258,15 @@ int segnn_generic_aggregate(const float* m, int B, int N, int D, float* agg, seg
 int segnn_macros_energy_momentum(const float* traj_pos, const float* traj_vel, int frames, int B, int N, float G,
                                  float softening, float* out, segnn_stream_t stream);
 
+/* datasets/nbody/visualization_utils.py:1093-1124 (count_stickings_and_collisions), :1145-1167
+ * (count_balls_leaving_defined_area), :1170-1187 (get_max_distance_of_com_from_starting_position), :1201-1222
+ * (count_sharp_turns) on the device trajectory buffers [frames][B*N][3]: out_counts [B][4] int32 = (stickings,
+ * collisions, bodies_left, sharp_turns), out_com [B] = max distance of the centre of mass from its start.
+ * Reference defaults: time_threshold 3, contact_distance 0.5, leave_distance 15, turn_angle_degrees 30. */
+int segnn_macros_counters(const float* traj_pos, const float* traj_vel, int frames, int B, int N, int time_threshold,
+                          float contact_distance, float leave_distance, float turn_angle_degrees, int* out_counts,
+                          float* out_com, segnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -698,3 +698,44 @@ def combine_pvalues_fisher(p_values) -> float:
     mp.dps = 200
     chi_stat = float(-2 * mp.fsum([log(mp.mpf(p)) for p in vals]))
     return float(max(chi2.sf(chi_stat, 2 * len(vals)), 1e-300))
+
+
+def event_counters(loc, vel, time_threshold=3, contact_distance=0.5, leave_distance=15.0, turn_angle=30.0):
+    """datasets/nbody/visualization_utils.py:1093-1124 (stickings / collisions), :1145-1167 (bodies leaving),
+    :1170-1187 (max centre-of-mass drift), :1201-1222 (sharp turns), with the reference's own loop structure.
+    loc, vel [B, T, N, 3] -> dict of per-simulation arrays."""
+    import numpy as np
+    loc, vel = np.asarray(loc), np.asarray(vel)
+    sims, steps, n = loc.shape[:3]
+    stick, coll, left, turns, drift = (np.zeros(sims) for _ in range(5))
+    for s in range(sims):
+        ongoing = np.zeros((n, n))
+        outside = np.zeros(n)
+        com0 = loc[s, 0].mean(axis=0)
+        for t in range(1, steps):
+            for i in range(n):
+                for j in range(i + 1, n):
+                    if np.linalg.norm(loc[s, t, i] - loc[s, t, j]) <= contact_distance:
+                        ongoing[i, j] += 1
+                        if ongoing[i, j] == 1:
+                            coll[s] += 1
+                        if ongoing[i, j] == time_threshold:
+                            stick[s] += 1
+                            coll[s] -= 1
+                    else:
+                        ongoing[i, j] = 0
+            com = loc[s, t].mean(axis=0)
+            drift[s] = max(drift[s], np.sqrt(((com - com0) ** 2).sum()))
+            for b in range(n):
+                if np.sqrt(((loc[s, t, b] - com) ** 2).sum()) > leave_distance:
+                    outside[b] += 1
+                else:
+                    outside[b] = 0
+                a, c = vel[s, t, b], vel[s, t - 1, b]
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    cosang = np.clip(np.dot(a, c) / (np.linalg.norm(a) * np.linalg.norm(c)), -1, 1)
+                    if np.degrees(np.arccos(cosang)) > turn_angle:
+                        turns[s] += 1
+        left[s] = len([i for i in outside if i > 10])
+    return {"stickings": stick, "collisions": coll, "bodies_left": left, "sharp_turns": turns,
+            "max_com_distance": drift}

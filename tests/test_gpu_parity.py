@@ -411,3 +411,27 @@ def test_generic_rollout_lmax2_matches_oracle():
     tp, tv = roll.run(steps)
     got_loc = tp.reshape(steps + 1, B, N, 3).permute(1, 0, 2, 3)
     assert rel(got_loc, ref_loc) < 5e-5
+
+
+@pytest.mark.parametrize("B,N,T", [(4, 5, 40), (2, 30, 25)])
+def test_event_counter_macros_bit_exact(B, N, T):
+    """Collision / sticking / leaving / sharp-turn counters (visualization_utils.py:1093-1222) are integer statistics:
+    bit-exact against the reference's loop structure on float32-representable trajectories built to exercise every
+    branch (contacts of different run lengths, bodies that leave and return, reversals, a zero velocity)."""
+    import numpy as np
+    gen = torch.Generator().manual_seed(B + N + T)
+    vel = torch.randn(B, T, N, 3, generator=gen) * 0.4
+    vel[:, ::7] = -vel[:, ::7]                       # sharp turns
+    vel[0, 3, 0] = 0.0                               # zero velocity -> NaN angle, counts as no turn
+    loc = torch.cumsum(vel * 0.3, dim=1) + torch.randn(B, 1, N, 3, generator=gen) * 0.6
+    loc[:, T // 2:, 1] += 40.0                       # body 1 leaves for the second half (run > 10 when T/2 > 10)
+    loc[:, 5:9, 2] = loc[:, 5:9, 3] + 0.01           # a 4-step contact: collision upgraded to sticking
+    loc[:, 12:14, 2] = loc[:, 12:14, 3] + 0.01       # a 2-step contact: plain collision
+    ref = O.event_counters(loc.double().numpy(), vel.double().numpy())
+    tp = loc.permute(1, 0, 2, 3).reshape(T, B * N, 3).contiguous().cuda()
+    tv = vel.permute(1, 0, 2, 3).reshape(T, B * N, 3).contiguous().cuda()
+    got = S.macros.event_counters(tp, tv, B, N)
+    for k in ("stickings", "collisions", "bodies_left", "sharp_turns"):
+        assert np.array_equal(got[k], ref[k].astype(np.int64)), (k, got[k], ref[k])
+    assert ref["stickings"].sum() > 0 and ref["collisions"].sum() > 0 and ref["sharp_turns"].sum() > 0
+    assert np.abs(got["max_com_distance"] - ref["max_com_distance"]).max() < 1e-5 * max(ref["max_com_distance"].max(), 1)

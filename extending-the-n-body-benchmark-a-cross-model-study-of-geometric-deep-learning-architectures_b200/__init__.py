@@ -3,7 +3,7 @@
 Importing this package loads ``libsegnn_b200.so`` (hand-written sm_100a CUDA behind the C ABI in
 include/segnn_b200.h) and fails loudly if it is missing: there is no CPU, PyTorch or Triton fallback."""
 from . import _lib, ops, packing  # noqa: F401
-from . import macros  # noqa: F401,E402
+from . import macros, simulator  # noqa: F401,E402
 from .graph import GraphBatch, build_graph_with_knn  # noqa: F401
 from .irreps import Irreps, weight_balanced_irreps  # noqa: F401
 from .o3_building_blocks import BatchNorm, O3TensorProduct, O3TensorProductSwishGate, O3Transform  # noqa: F401

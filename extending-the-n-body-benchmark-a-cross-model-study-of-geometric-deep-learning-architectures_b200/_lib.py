@@ -53,6 +53,8 @@ PROTOTYPES = {
     "segnn_generic_gate": (_int, [_ptr, _c.c_int64, _int, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_generic_message_input": (_int, [_ptr, _ptr, _int, _int, _int, _int, _ptr, _ptr]),
     "segnn_generic_aggregate": (_int, [_ptr, _int, _int, _int, _ptr, _ptr]),
+    "segnn_sim_gravity": (_int, [_ptr, _ptr, _ptr, _int, _int, _c.c_double, _c.c_double, _c.c_double, _int, _int, _ptr,
+                                 _ptr, _ptr, _ptr]),
     "segnn_macros_counters": (_int, [_ptr, _ptr, _int, _int, _int, _int, _c.c_float, _c.c_float, _c.c_float, _ptr, _ptr,
                                      _ptr]),
     "segnn_macros_energy_momentum": (_int, [_ptr, _ptr, _int, _int, _int, _c.c_float, _c.c_float, _ptr, _ptr]),

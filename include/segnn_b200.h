@@ -267,6 +267,17 @@ int segnn_macros_counters(const float* traj_pos, const float* traj_vel, int fram
                           float contact_distance, float leave_distance, float turn_angle_degrees, int* out_counts,
                           float* out_com, segnn_stream_t stream);
 
+/* ---- ground-truth simulator ------------------------------------------------------------- */
+
+/* GravitySim.sample_trajectory (datasets/nbody/dataset/synthetic_sim.py:305-420; the OTF dataset's generator,
+ * datasets/nbody/dataset_gravity_otf.py:91-107): softened gravity, kick-drift-kick leapfrog in float64, one CTA per
+ * simulation, the whole trajectory in one launch.  pos, vel [B*N][3] (in: initial state, out: final state), mass [B*N];
+ * traj_* [steps / sample_freq][B*N][3]: frame k = state after k * sample_freq steps (frame 0 = initial state);
+ * traj_force may be NULL.  Observation noise (noise_var, 0 by default) is left to the caller. */
+int segnn_sim_gravity(double* pos, double* vel, const double* mass, int B, int N, double G, double softening, double dt,
+                      int steps, int sample_freq, double* traj_pos, double* traj_vel, double* traj_force,
+                      segnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -739,3 +739,31 @@ def event_counters(loc, vel, time_threshold=3, contact_distance=0.5, leave_dista
         left[s] = len([i for i in outside if i > 10])
     return {"stickings": stick, "collisions": coll, "bodies_left": left, "sharp_turns": turns,
             "max_com_distance": drift}
+
+
+def gravity_trajectory(pos, vel, mass, G, softening, dt, T, sample_freq):
+    """datasets/nbody/dataset/synthetic_sim.py:319-358,360-418 (GravitySim) for given initial conditions, NumPy
+    float64, one simulation: pos, vel [N,3], mass [N,1] -> loc, vel, force [T / sample_freq, N, 3]."""
+    import numpy as np
+
+    def acceleration(p):
+        x, y, z = p[:, 0:1], p[:, 1:2], p[:, 2:3]
+        dx, dy, dz = x.T - x, y.T - y, z.T - z
+        inv_r3 = dx ** 2 + dy ** 2 + dz ** 2 + softening ** 2
+        inv_r3[inv_r3 > 0] = inv_r3[inv_r3 > 0] ** (-1.5)
+        return np.hstack((G * (dx * inv_r3) @ mass, G * (dy * inv_r3) @ mass, G * (dz * inv_r3) @ mass))
+
+    pos, vel, mass = np.array(pos, dtype=np.float64), np.array(vel, dtype=np.float64), np.array(mass, dtype=np.float64)
+    frames = T // sample_freq
+    ps, vs, fs = (np.zeros((frames,) + pos.shape) for _ in range(3))
+    acc = acceleration(pos)
+    k = 0
+    for i in range(T):
+        if i % sample_freq == 0:
+            ps[k], vs[k], fs[k] = pos, vel, acc * mass
+            k += 1
+        vel = vel + acc * dt / 2.0
+        pos = pos + vel * dt
+        acc = acceleration(pos)
+        vel = vel + acc * dt / 2.0
+    return ps, vs, fs

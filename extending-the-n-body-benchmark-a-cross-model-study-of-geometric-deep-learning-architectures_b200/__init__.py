@@ -11,4 +11,5 @@ from .segnn import SEGNN, SEGNNLayer  # noqa: F401
 
 WeightBalancedIrreps = weight_balanced_irreps
 from .rollout import SelfFeedRollout, run_inference, shard_simulations  # noqa: F401,E402
+from .dataloader import GravityDatasetOtf, SegnnNBodyDataLoader  # noqa: F401,E402
 from .trainer import TrainStep, allreduce_gradients, noam_rate, target_common_loss  # noqa: F401,E402

@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 HIDDEN, LAYERS, NBODY = 192, 6, 100
 FLOP_PER_EDGE_MSG2 = 20 * (HIDDEN // 2) ** 2       # 184,320: irreducible per-edge contraction
 FLOP_PER_EDGE_REFERENCE = 554_880                   # msg1 + msg2 in the reference's formulation
+K3_DRAM_BYTES_PER_LAUNCH = 947_169_280 + 151_965_952  # measured with ncu on this workload (1024 sims x 100 bodies)
 
 
 def synthetic_system(batch, n, seed):
@@ -359,7 +360,11 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "edge_layer (K3, message_layer_1 combine + gate + message_layer_2 + gate + "
                                    "aggregation)", "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
-                         "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                         "traffic": K3_DRAM_BYTES_PER_LAUNCH if (mode == "bf16" and B == 1024) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                           "(profiles/r1_v8_ncu_full_summary.json); algorithmic P + Q + agg bytes = "
+                                           "1.10e9",
                          "peak_source": peak_src + ", bf16 dense sustained",
                          "flop_per_edge": FLOP_PER_EDGE_MSG2, "edges_per_launch": edges,
                          "avg_launch_ms": k3_ms, "launches_timed": len(k3_events),

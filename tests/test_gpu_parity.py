@@ -536,4 +536,4 @@ def test_large_graph_tensor_core_mode_agrees_with_fp32_mode():
         assert err < 6e-2
         perm = torch.randperm(N).cuda()
         out_p = m.forward_state(p[perm].contiguous(), v[perm].contiguous(), ms[perm].contiguous(), B, N)
-        assert float((out_p - out[perm]).abs().max() / out.abs().max()) < 5e-3
+        assert float((out_p - out[perm]).abs().max() / out.abs().max()) < 2e-2  # bf16 operands, different tile grouping

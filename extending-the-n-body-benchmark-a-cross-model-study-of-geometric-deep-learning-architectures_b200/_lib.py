@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libsegnn_b200.so")
 
 MODE_FP32 = 0
 MODE_BF16_TC = 1
+MODE_FP16_TC = 2
+OPERAND_BF16, OPERAND_FP16 = 0, 1
 
 _c = ctypes
 _ptr = _c.c_void_p
@@ -27,12 +29,12 @@ PROTOTYPES = {
     "segnn_prep_fwd": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_embed_fwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_node_gemm": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr]),
-    "segnn_node_gemm_tc": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr]),
-    "segnn_pack_node_weight_tc": (_int, [_ptr, _int, _int, _ptr, _ptr]),
+    "segnn_node_gemm_tc": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _int, _ptr]),
+    "segnn_pack_node_weight_tc": (_int, [_ptr, _int, _int, _int, _ptr, _ptr]),
     "segnn_tp_combine": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "segnn_edge_layer_fwd": (_int, [_int, _ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                                     _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
-    "segnn_pack_w2_tc": (_c.c_int64, [_ptr, _ptr, _ptr, _ptr, _int, _ptr, _ptr]),
+    "segnn_pack_w2_tc": (_c.c_int64, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_head_fwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_integrate": (_int, [_ptr, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _ptr]),
     "segnn_counter_add": (_int, [_ptr, _int, _ptr]),

@@ -33,6 +33,7 @@
 //            instructions off the three compute sub-partitions.
 // Synchronisation is mbarrier-only between roles; every wait is bounded and traps instead of hanging.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "segnn_common.cuh"
 
@@ -121,12 +122,14 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D = f32, A = B = bf16, A K-major (TMEM), B MN-major, M = 128, N = 32
-__device__ __forceinline__ uint32_t make_idesc() {
+// instruction descriptor: D = f32, A = B = bf16 or f16, A K-major (TMEM), B MN-major, M = 128, N = 32
+__device__ __forceinline__ uint32_t make_idesc(bool half) {
   uint32_t d = 0;
   d |= 1u << 4;
-  d |= 1u << 7;
-  d |= 1u << 10;
+  if (!half) {
+    d |= 1u << 7;   // A format: 0 = f16, 1 = bf16
+    d |= 1u << 10;  // B format
+  }
   d |= 1u << 16;
   d |= (uint32_t)(kCols >> 3) << 17;
   d |= (uint32_t)(128 >> 4) << 24;
@@ -150,9 +153,14 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// two fp32 -> one 32-bit pair of 16-bit operands (bf16, or fp16 in SEGNN_MODE_FP16_TC)
+template <bool HALF>
+__device__ __forceinline__ uint32_t pack_pair(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (HALF)
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 
@@ -199,7 +207,7 @@ struct TileCursor {
   int g, i0;  // graph and first receiver of the item (MMA warp only; recomputed once per item)
 };
 
-template <int NMUL>
+template <int NMUL, bool HALF>
 __global__ void __launch_bounds__(kWarps * 32, 1)
     edge_layer_tc_kernel(const float* __restrict__ pos, const float* __restrict__ mass, int B, int N,
                          const float* __restrict__ pp, const float* __restrict__ qq,
@@ -406,10 +414,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
           float2 dt = __fmul2_rn(ax, vx);
           dt = __ffma2_rn(ay, vy, dt);
           dt = __ffma2_rn(az, vz, dt);
-          packed[s4][1] = pack_bf16x2(dt.x, dt.y);
-          packed[s4][2] = pack_bf16x2(vx.x, vx.y);
-          packed[s4][3] = pack_bf16x2(vy.x, vy.y);
-          packed[s4][4] = pack_bf16x2(vz.x, vz.y);
+          packed[s4][1] = pack_pair<HALF>(dt.x, dt.y);
+          packed[s4][2] = pack_pair<HALF>(vx.x, vx.y);
+          packed[s4][3] = pack_pair<HALF>(vy.x, vy.y);
+          packed[s4][4] = pack_pair<HALF>(vz.x, vz.y);
         }
       }
       // 4 senders x 2 receivers = 8 consecutive columns = one 16-byte chunk per plane row (conflict-free with the
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
               hs = __ffma2_rn(le, wd0s, hs);
               hs = __ffma2_rn(mm, wm0s, hs);
               const float2 so = __ffma2_rn(hs, tanh2(hs), hs);  // silu(z) / c = z/2 (1 + tanh(z/2))
-              packed[rp][s4] = pack_bf16x2(so.x, so.y);
+              packed[rp][s4] = pack_pair<HALF>(so.x, so.y);
             }
           }
         }
@@ -587,7 +595,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ==================================================================
     // Warp-uniform loop; only the tcgen05 instructions sit under elect.sync so descriptors stay in uniform registers.
-    const uint32_t idesc = make_idesc();
+    const uint32_t idesc = make_idesc(HALF);
     const uint32_t tm = 0u;  // checked above
     const uint64_t bdesc0 = make_b_desc(smem_u32(sB));
     const uint32_t d0 = tm + kDBase;
@@ -717,7 +725,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 
 // ---- weight image: [128 lanes][3n columns] of bf16 pairs ------------------------------------------------------
 __global__ void pack_w2_kernel(const float* __restrict__ ss, const float* __restrict__ vs,
-                               const float* __restrict__ sv, const float* __restrict__ vv, int n,
+                               const float* __restrict__ sv, const float* __restrict__ vv, int n, int half,
                                uint32_t* __restrict__ out) {
   const int cols = 3 * n;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * cols; idx += gridDim.x * blockDim.x) {
@@ -740,12 +748,16 @@ __global__ void pack_w2_kernel(const float* __restrict__ ss, const float* __rest
         }
       }
     }
-    const __nv_bfloat16 lo = __float2bfloat16(v[0]), hi = __float2bfloat16(v[1]);
-    out[idx] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+    if (half) {
+      out[idx] = (uint32_t)__half_as_ushort(__float2half_rn(v[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(v[1])) << 16);
+    } else {
+      const __nv_bfloat16 lo = __float2bfloat16(v[0]), hi = __float2bfloat16(v[1]);
+      out[idx] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+    }
   }
 }
 
-template <int NMUL>
+template <int NMUL, bool HALF>
 static int launch_tc(const float* pos, const float* mass, int B, int N, const float* pp, const float* qq,
                      const float* w_edge1,
                      const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg,
@@ -755,7 +767,7 @@ static int launch_tc(const float* pos, const float* mass, int B, int N, const fl
                       (size_t)kRecv * 4 * 3 * NMUL * sizeof(float) + (size_t)kGeoSlots * 6 * kCols * sizeof(float) +
                       (size_t)2 * 4 * 4 * NMUL * sizeof(float) +
                       24 * sizeof(uint64_t) + 16;
-  auto kern = edge_layer_tc_kernel<NMUL>;
+  auto kern = edge_layer_tc_kernel<NMUL, HALF>;
   {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) {
@@ -786,11 +798,17 @@ static int launch_tc(const float* pos, const float* mass, int B, int N, const fl
 
 int edge_layer_tc(const float* pos, const float* mass, int B, int N, int n, const float* pp, const float* qq,
                   const float* w_edge1,
-                  const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg,
+                  const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add, float* agg, int half,
                   cudaStream_t stream) {
-  if (n == 32) return tc::launch_tc<32>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
-  if (n == 64) return tc::launch_tc<64>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
-  if (n == 96) return tc::launch_tc<96>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
+  if (n == 32)
+    return half ? tc::launch_tc<32, true>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream)
+                : tc::launch_tc<32, false>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
+  if (n == 64)
+    return half ? tc::launch_tc<64, true>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream)
+                : tc::launch_tc<64, false>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
+  if (n == 96)
+    return half ? tc::launch_tc<96, true>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream)
+                : tc::launch_tc<96, false>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, nullptr, stream);
   set_error("edge_layer_tc: tensor-core mode is built for hidden multiplicity n in {32, 64, 96} (hidden_features "
             "64/128/192), got n=%d", n);
   return SEGNN_E_UNSUPPORTED;
@@ -804,7 +822,7 @@ extern "C" int segnn_debug_set_k3_trace(long long* buf) {
 namespace segnn {
 #endif
 
-int64_t pack_w2_tc(const float* ss, const float* vs, const float* sv, const float* vv, int n, void* out,
+int64_t pack_w2_tc(const float* ss, const float* vs, const float* sv, const float* vv, int n, int half, void* out,
                    cudaStream_t stream) {
   if (n != 32 && n != 64 && n != 96) {
     set_error("segnn_pack_w2_tc: n must be 32, 64 or 96 (got %d)", n);
@@ -816,7 +834,7 @@ int64_t pack_w2_tc(const float* ss, const float* vs, const float* sv, const floa
     set_error("segnn_pack_w2_tc: null weight block");
     return SEGNN_E_INVALID;
   }
-  tc::pack_w2_kernel<<<(128 * 3 * n + 255) / 256, 256, 0, stream>>>(ss, vs, sv, vv, n, (uint32_t*)out);
+  tc::pack_w2_kernel<<<(128 * 3 * n + 255) / 256, 256, 0, stream>>>(ss, vs, sv, vv, n, half, (uint32_t*)out);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     set_error("segnn_pack_w2_tc: launch: %s", cudaGetErrorString(err));

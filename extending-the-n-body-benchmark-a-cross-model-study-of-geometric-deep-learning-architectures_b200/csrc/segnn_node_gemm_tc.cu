@@ -9,6 +9,7 @@
 // (TMEM lane quadrant = warp % 4), 1 MMA warp.
 // The kernel is HBM-bound (writes 4*n_out bytes per row against 2*K*n_out flops): the roofline is the copy rate.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "segnn_common.cuh"
 
@@ -62,18 +63,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ uint32_t make_idesc(int N) {
+__device__ __forceinline__ uint32_t make_idesc(int N, int half) {
   uint32_t d = 0;
   d |= 1u << 4;   // D = f32
-  d |= 1u << 7;   // A = bf16
-  d |= 1u << 10;  // B = bf16
+  if (!half) {
+    d |= 1u << 7;   // A format: 0 = f16, 1 = bf16
+    d |= 1u << 10;  // B format
+  }
   d |= (uint32_t)(N >> 3) << 17;
   d |= (uint32_t)(128 >> 4) << 24;
   return d;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+__device__ __forceinline__ uint32_t pack_pair(float lo, float hi, int half) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (half)
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 #define SEGNN_NG_LD8(taddr, r)                                                                                     \
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     node_gemm_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int nodes, int n_in,
                         const __nv_bfloat16* __restrict__ wt_s, const __nv_bfloat16* __restrict__ wt_v,
                         const float* __restrict__ bias, int n_bias, int n_out, int nc, float* __restrict__ y0,
-                        float* __restrict__ y1, int split, int ctas_cls0) {
+                        float* __restrict__ y1, int split, int ctas_cls0, int fp16_operands) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int K = x1 ? 2 * n_in : n_in;
@@ -185,8 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int i = 0; i < 6; ++i) {
           if (b0 + i < k8h) {
             const int k = (half * k8h + b0 + i) * 8;  // 8 k = one 16-byte chunk of the swizzled row
-            const uint4 o = make_uint4(pack_bf16x2(v[i][0], v[i][1]), pack_bf16x2(v[i][2], v[i][3]),
-                                       pack_bf16x2(v[i][4], v[i][5]), pack_bf16x2(v[i][6], v[i][7]));
+            const uint4 o = make_uint4(pack_pair(v[i][0], v[i][1], fp16_operands), pack_pair(v[i][2], v[i][3], fp16_operands),
+                                       pack_pair(v[i][4], v[i][5], fp16_operands), pack_pair(v[i][6], v[i][7], fp16_operands));
             *reinterpret_cast<uint4*>(dst + (k >> 6) * (128 * 128) + ((((k & 63) >> 3) ^ (r & 7)) << 4)) = o;
           }
         }
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc(nc);
+    const uint32_t idesc = make_idesc(nc, fp16_operands);
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     uint32_t t = 0, dcount = 0;
     for (long long tile = cta; tile < tiles; tile += cta_stride, ++t) {
@@ -270,10 +276,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-__global__ void transpose_bf16_kernel(const float* __restrict__ w, int K, int n_out, __nv_bfloat16* __restrict__ wt) {
+__global__ void transpose_bf16_kernel(const float* __restrict__ w, int K, int n_out, int half,
+                                      __nv_bfloat16* __restrict__ wt) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < K * n_out; idx += gridDim.x * blockDim.x) {
     const int o = idx / K, k = idx - o * K;
-    wt[idx] = __float2bfloat16(w[(size_t)k * n_out + o]);
+    if (half)
+      reinterpret_cast<__half*>(wt)[idx] = __float2half_rn(w[(size_t)k * n_out + o]);
+    else
+      wt[idx] = __float2bfloat16(w[(size_t)k * n_out + o]);
   }
 }
 
@@ -284,18 +294,20 @@ using namespace segnn;
 
 extern "C" {
 
-int segnn_pack_node_weight_tc(const float* w, int K, int n_out, void* wt_bf16, segnn_stream_t stream) {
+int segnn_pack_node_weight_tc(const float* w, int K, int n_out, int operand, void* wt_bf16, segnn_stream_t stream) {
   SEGNN_CHECK_ARG(w && wt_bf16 && K > 0 && n_out > 0, "bad arguments");
+  SEGNN_CHECK_ARG(operand == SEGNN_OPERAND_BF16 || operand == SEGNN_OPERAND_FP16, "unknown operand format");
   ngemm::transpose_bf16_kernel<<<(K * n_out + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      w, K, n_out, (__nv_bfloat16*)wt_bf16);
+      w, K, n_out, operand == SEGNN_OPERAND_FP16 ? 1 : 0, (__nv_bfloat16*)wt_bf16);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }
 
 int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
-                       const float* bias, int n_bias, int n_out, float* y0, float* y1, int split,
+                       const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, int operand,
                        segnn_stream_t stream) {
   SEGNN_CHECK_ARG(nodes >= 0 && n_in >= 1 && n_out >= 1, "bad sizes");
+  SEGNN_CHECK_ARG(operand == SEGNN_OPERAND_BF16 || operand == SEGNN_OPERAND_FP16, "unknown operand format");
   if (nodes == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(x0 && wt_s && wt_v && y0, "null pointer");
   const int K = x1 ? 2 * n_in : n_in;
@@ -334,7 +346,7 @@ int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, co
   if (c1 > tiles1) c1 = tiles1;
   ngemm::node_gemm_tc_kernel<<<(unsigned)(c0 + c1), ngemm::kThreads, smem, (cudaStream_t)stream>>>(
       x0, x1, nodes, n_in, (const __nv_bfloat16*)wt_s, (const __nv_bfloat16*)wt_v, bias, n_bias, n_out, nc, y0, y1,
-      split, (int)c0);
+      split, (int)c0, operand == SEGNN_OPERAND_FP16 ? 1 : 0);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

@@ -7,10 +7,10 @@ from typing import Optional
 
 import torch
 
-from ._lib import MODE_BF16_TC, MODE_FP32, check, lib
+from ._lib import MODE_BF16_TC, MODE_FP16_TC, MODE_FP32, OPERAND_BF16, OPERAND_FP16, check, lib
 
 __all__ = ["edge_index", "edge_attr", "prep", "embed", "node_gemm", "pack_node_weight_tc", "tp_combine", "edge_layer", "head",
-           "integrate", "counter_add", "launch_count", "MODE_FP32", "MODE_BF16_TC"]
+           "integrate", "counter_add", "launch_count", "MODE_FP32", "MODE_BF16_TC", "MODE_FP16_TC"]
 
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -86,8 +86,9 @@ def embed(x_in, node_attr, w_embed, bias, n: int):
     return h
 
 
-def node_gemm(x0, x1, w, n_out: int, bias=None, n_bias: int = 0, split: int = 0, tc: bool = False):
-    """w: dict with fp32 'w_s','w_v' [K][n_out] (and bf16 'wt_s','wt_v' [n_out][K] when tc). With split > 0 returns
+def node_gemm(x0, x1, w, n_out: int, bias=None, n_bias: int = 0, split: int = 0, tc=False):
+    """w: dict with fp32 'w_s','w_v' [K][n_out] and, for the tensor-core kernel, 16-bit 'wt_s','wt_v' [n_out][K] packed
+    with the operand format w['operand']. ``tc``: False (FFMA) or True (tcgen05). With split > 0 returns
     (y0 [nodes,4,split], y1 [nodes,4,n_out-split]), else one tensor [nodes,4,n_out]."""
     nodes, _, n_in = x0.shape
     dev = x0.device
@@ -99,7 +100,8 @@ def node_gemm(x0, x1, w, n_out: int, bias=None, n_bias: int = 0, split: int = 0,
     with torch.cuda.device(dev):
         if tc:
             check(lib.segnn_node_gemm_tc(_p(x0), _p(x1), nodes, n_in, _p(w["wt_s"]), _p(w["wt_v"]), _p(bias), n_bias,
-                                         n_out, _p(y0), _p(y1), split, _stream()), "segnn_node_gemm_tc")
+                                         n_out, _p(y0), _p(y1), split, int(w.get("operand", OPERAND_BF16)), _stream()),
+                  "segnn_node_gemm_tc")
         else:
             check(lib.segnn_node_gemm(_p(x0), _p(x1), nodes, n_in, _p(w["w_s"]), _p(w["w_v"]), _p(bias), n_bias,
                                       n_out, _p(y0), _p(y1), split, _stream()), "segnn_node_gemm")
@@ -107,12 +109,13 @@ def node_gemm(x0, x1, w, n_out: int, bias=None, n_bias: int = 0, split: int = 0,
     return (y0, y1) if split else y0
 
 
-def pack_node_weight_tc(w: torch.Tensor) -> torch.Tensor:
-    """fp32 [K][n_out] -> bf16 [n_out][K] (segnn_pack_node_weight_tc)."""
+def pack_node_weight_tc(w: torch.Tensor, operand: int = OPERAND_BF16) -> torch.Tensor:
+    """fp32 [K][n_out] -> bf16 / fp16 [n_out][K] (segnn_pack_node_weight_tc)."""
     K, n_out = w.shape
-    out = torch.empty((n_out, K), dtype=torch.bfloat16, device=w.device)
+    out = torch.empty((n_out, K), dtype=torch.float16 if operand == OPERAND_FP16 else torch.bfloat16, device=w.device)
     with torch.cuda.device(w.device):
-        check(lib.segnn_pack_node_weight_tc(_p(w), K, n_out, _p(out), _stream()), "segnn_pack_node_weight_tc")
+        check(lib.segnn_pack_node_weight_tc(_p(w), K, n_out, int(operand), _p(out), _stream()),
+              "segnn_pack_node_weight_tc")
     _bump()
     return out
 
@@ -169,14 +172,15 @@ def counter_add(counter: torch.Tensor, delta: int):
 TC_MULTIPLICITIES = (32, 64, 96)
 
 
-def pack_w2_tc(w2: dict, n: int) -> torch.Tensor:
-    """message_layer_2 weight image for the tcgen05 kernel: [128 lanes][3n] bf16 pairs (segnn_pack_w2_tc)."""
-    nbytes = lib.segnn_pack_w2_tc(None, None, None, None, n, None, None)
+def pack_w2_tc(w2: dict, n: int, operand: int = OPERAND_BF16) -> torch.Tensor:
+    """message_layer_2 weight image for the tcgen05 kernel: [128 lanes][3n] 16-bit pairs (segnn_pack_w2_tc)."""
+    nbytes = lib.segnn_pack_w2_tc(None, None, None, None, n, int(operand), None, None)
     if nbytes <= 0:
         check(int(nbytes), "segnn_pack_w2_tc")
     out = torch.empty(nbytes // 4, dtype=torch.int32, device=w2["ss"].device)
     with torch.cuda.device(out.device):
-        rc = lib.segnn_pack_w2_tc(_p(w2["ss"]), _p(w2["vs"]), _p(w2["sv"]), _p(w2["vv"]), n, _p(out), _stream())
+        rc = lib.segnn_pack_w2_tc(_p(w2["ss"]), _p(w2["vs"]), _p(w2["sv"]), _p(w2["vv"]), n, int(operand), _p(out),
+                                  _stream())
     if rc < 0:
         check(int(rc), "segnn_pack_w2_tc")
     _bump()
@@ -185,7 +189,7 @@ def pack_w2_tc(w2: dict, n: int) -> torch.Tensor:
 
 def tc_available() -> bool:
     """True when the tcgen05 (SEGNN_MODE_BF16_TC) edge kernel is compiled into the library."""
-    return lib.segnn_pack_w2_tc(None, None, None, None, 96, None, None) > 0
+    return lib.segnn_pack_w2_tc(None, None, None, None, 96, OPERAND_BF16, None, None) > 0
 
 
 # ---- training-side wrappers (fp32) --------------------------------------------------------------------------------

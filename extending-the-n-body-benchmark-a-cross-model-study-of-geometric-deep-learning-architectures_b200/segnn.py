@@ -12,7 +12,8 @@ from .graph import infer_graph_shape
 from .irreps import Irreps, weight_balanced_irreps
 from .o3_building_blocks import BatchNorm, O3TensorProduct, O3TensorProductSwishGate
 
-_MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16_TC}
+_MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16_TC, "fp16": ops.MODE_FP16_TC}
+_TC_MODES = (ops.MODE_BF16_TC, ops.MODE_FP16_TC)
 
 
 class SEGNNLayer(nn.Module):
@@ -47,7 +48,7 @@ class SEGNNLayer(nn.Module):
         self.n = hidden_irreps[0][0]
 
     # -- weight packing -----------------------------------------------------------------------------------------
-    def pack(self, degree: int, eval_bn: bool = True) -> Dict[str, object]:
+    def pack(self, degree: int, eval_bn: bool = True, operand: int = 0) -> Dict[str, object]:
         n = self.n
         f = lambda t: t.detach().to(torch.float32)
         out = dict(
@@ -57,10 +58,11 @@ class SEGNNLayer(nn.Module):
             upd2=packing.pack_node_tp(f(self.update_layer_2.tp.weight), f(self.update_layer_2.biases), 1, n, n),
             bn_msg=(None, None), bn_feat=(None, None))
         if out["msg2"]["ss"].is_cuda and n in ops.TC_MULTIPLICITIES and ops.tc_available():
-            out["msg2"]["tc"] = ops.pack_w2_tc(out["msg2"], n)
+            out["msg2"]["tc"] = ops.pack_w2_tc(out["msg2"], n, operand)
             for key in ("msg1", "upd1", "upd2"):
-                out[key]["wt_s"] = ops.pack_node_weight_tc(out[key]["w_s"])
-                out[key]["wt_v"] = ops.pack_node_weight_tc(out[key]["w_v"])
+                out[key]["wt_s"] = ops.pack_node_weight_tc(out[key]["w_s"], operand)
+                out[key]["wt_v"] = ops.pack_node_weight_tc(out[key]["w_v"], operand)
+                out[key]["operand"] = operand
         if eval_bn and self.message_norm is not None:
             bn = self.message_norm
             out["bn_msg"] = packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), n,
@@ -73,7 +75,7 @@ class SEGNNLayer(nn.Module):
     def run(self, w, mode: int, h, pos, mass, node_attr, batch_size: int, num_nodes: int):
         """One layer on planar features h [nodes,4,n] (eval-mode BatchNorm)."""
         n = self.n
-        tc = mode == ops.MODE_BF16_TC
+        tc = mode in _TC_MODES
         m1 = w["msg1"]
         p, q = ops.node_gemm(h, None, m1, 6 * n, bias=m1["bias"], n_bias=2 * n, split=3 * n, tc=tc)
         agg = ops.edge_layer(mode, pos, mass, batch_size, num_nodes, n, p, q, m1["w_edge"], w["msg2"],
@@ -96,7 +98,7 @@ class SEGNNLayer(nn.Module):
             raise NotImplementedError("standalone SEGNNLayer.forward is built for lmax_h = 1; use SEGNN.forward")
         if self.training:
             raise NotImplementedError("train-mode BatchNorm for the standalone layer: use SEGNN.forward")
-        w = self.pack(n_nodes - 1)
+        w = self.pack(n_nodes - 1, operand=1 if mode == "fp16" else 0)
         h = packing.to_planar(x.float(), self.n)
         out = self.run(w, _MODES[mode], h, pos.float().contiguous(), mass.float().reshape(-1).contiguous(),
                        node_attr.float().contiguous(), num_graphs, n_nodes)
@@ -106,7 +108,8 @@ class SEGNNLayer(nn.Module):
 class SEGNN(nn.Module):
     """Steerable E(3) equivariant message passing network -- models/segnn/segnn.py:14-189 (task='node').
 
-    ``compute_mode``: 'fp32' (FFMA kernels, the 1e-5 parity mode) or 'bf16' (tcgen05 tensor-core edge kernel)."""
+    ``compute_mode``: 'fp32' (FFMA kernels, the 1e-5 parity mode), 'bf16' (tcgen05 tensor-core kernels, the mode the
+    benchmark reports) or 'fp16' (the same kernels with fp16 operands: 8x smaller operand rounding at the same speed)."""
 
     def __init__(self, input_irreps="2x1o + 1x0e", hidden_features=64, lmax_h=1, lmax_attr=1, num_layers=4,
                  output_irreps="2x1o", norm="batch", pool="avg", task="node", additional_message_irreps="2x0e",
@@ -163,19 +166,21 @@ class SEGNN(nn.Module):
 
     # -- packing cache ------------------------------------------------------------------------------------------
     def packed(self, degree: int):
+        operand = 1 if self.compute_mode == "fp16" else 0  # 16-bit operand format of the tensor-core images
         tensors = list(self.parameters()) + list(self.buffers())
-        key = (degree, tuple((t.data_ptr(), t._version, t.device, t.dtype) for t in tensors))
+        key = (degree, operand, tuple((t.data_ptr(), t._version, t.device, t.dtype) for t in tensors))
         if key != self._pack_key:
             f = lambda t: t.detach().to(torch.float32)
             n = self.n
             self._packed = dict(
                 embed=packing.pack_embedding(f(self.embedding_layer.tp.weight), f(self.embedding_layer.biases), n),
-                layers=[layer.pack(degree) for layer in self.layers],
+                layers=[layer.pack(degree, operand=operand) for layer in self.layers],
                 pool1=packing.pack_node_tp(f(self.pre_pool1.tp.weight), f(self.pre_pool1.biases), 1, n, 2 * n),
                 head=packing.pack_head(f(self.pre_pool2.tp.weight), n))
             if "tc" in self._packed["layers"][0]["msg2"]:
-                for key in ("w_s", "w_v"):
-                    self._packed["pool1"]["wt" + key[1:]] = ops.pack_node_weight_tc(self._packed["pool1"][key])
+                for name in ("w_s", "w_v"):  # (must not reuse `key`: it is stored as the cache key below)
+                    self._packed["pool1"]["wt" + name[1:]] = ops.pack_node_weight_tc(self._packed["pool1"][name], operand)
+                self._packed["pool1"]["operand"] = operand
             self._pack_key = key
         return self._packed
 
@@ -198,8 +203,8 @@ class SEGNN(nn.Module):
         w = self.packed(num_nodes - 1)
         mode = _MODES[self.compute_mode]
         n = self.n
-        if mode == ops.MODE_BF16_TC and "tc" not in w["layers"][0]["msg2"]:
-            raise RuntimeError(f"compute_mode='bf16' needs hidden multiplicity in {ops.TC_MULTIPLICITIES} "
+        if mode in _TC_MODES and "tc" not in w["layers"][0]["msg2"]:
+            raise RuntimeError(f"compute_mode='bf16'/'fp16' needs hidden multiplicity in {ops.TC_MULTIPLICITIES} "
                                f"(hidden_features 64/128/192); this model has n={n}")
         if x_in is None or node_attr is None:
             x_in, node_attr = ops.prep(pos, vel, batch_size, num_nodes)
@@ -209,7 +214,7 @@ class SEGNN(nn.Module):
             h = layer.run(lw, mode, h, pos, mass, node_attr, batch_size, num_nodes)
             per_layer.append(h)
         p1 = w["pool1"]
-        y = ops.node_gemm(h, None, p1, 3 * n, tc=(mode == ops.MODE_BF16_TC))
+        y = ops.node_gemm(h, None, p1, 3 * n, tc=(mode in _TC_MODES))
         hp = ops.tp_combine(y, node_attr, n, True, bias=p1["bias"])
         pred = ops.head(hp, node_attr, w["head"], n)
         if return_layers:

@@ -40,8 +40,13 @@ enum {
 /* compute mode of the per-edge contraction (message_layer_2) */
 enum {
   SEGNN_MODE_FP32 = 0,   /* FFMA, fp32 everywhere: the 1e-5 parity mode */
-  SEGNN_MODE_BF16_TC = 1 /* tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM): the throughput mode */
+  SEGNN_MODE_BF16_TC = 1, /* tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM): the throughput mode */
+  SEGNN_MODE_FP16_TC = 2  /* same kernels with fp16 operands (11-bit mantissa): 8x smaller operand rounding at the same
+                             speed; operands must stay below 65504 (true for normalised features) */
 };
+
+/* 16-bit operand format of the tensor-core kernels and of their packed weight images */
+enum { SEGNN_OPERAND_BF16 = 0, SEGNN_OPERAND_FP16 = 1 };
 
 int segnn_version(void);
 const char* segnn_last_error(void);
@@ -86,15 +91,15 @@ int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const
                     const float* bias, int n_bias, int n_out, float* y0, float* y1, int split,
                     segnn_stream_t stream);
 
-/* Same contraction on tcgen05 (bf16 operands, fp32 accumulate in TMEM, fp32 output): wt_s, wt_v are the
- * weights pre-transposed to bf16 [n_out][K] by segnn_pack_node_weight_tc.  Needs n_in % 16 == 0, K <= 192,
- * n_out % 16 == 0, split % 8 == 0. */
+/* Same contraction on tcgen05 (bf16 or fp16 operands, fp32 accumulate in TMEM, fp32 output): wt_s, wt_v are the
+ * weights pre-transposed to 16-bit [n_out][K] by segnn_pack_node_weight_tc with the same `operand` format.  Needs
+ * n_in % 16 == 0, K <= 192, n_out % 16 == 0, split % 8 == 0, 32-byte aligned tensors. */
 int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
-                       const float* bias, int n_bias, int n_out, float* y0, float* y1, int split,
+                       const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, int operand,
                        segnn_stream_t stream);
 
-/* w [K][n_out] fp32 -> wt [n_out][K] bf16 (the B operand image of segnn_node_gemm_tc). */
-int segnn_pack_node_weight_tc(const float* w, int K, int n_out, void* wt_bf16, segnn_stream_t stream);
+/* w [K][n_out] fp32 -> wt [n_out][K] bf16 / fp16 (the B operand image of segnn_node_gemm_tc). */
+int segnn_pack_node_weight_tc(const float* w, int K, int n_out, int operand, void* wt, segnn_stream_t stream);
 
 /* Attribute coupling + epilogue of a node-level tensor product.  With a = node_attr[node] = (a0, a1[3]):
  *   z0[w]    = a0 * y[0][w]      + sum_k a1[k] * y[1+k][w] + bias[w]   w < n0 (l=0 outputs; bias may be NULL)
@@ -131,10 +136,11 @@ int segnn_edge_layer_fwd(int mode, const float* pos, const float* mass, int B, i
                          const float* w2_vv, const float* b2, const void* w2_tc, const float* bn_mul,
                          const float* bn_add, float* agg_out, float* moments, segnn_stream_t stream);
 
-/* Packs the message_layer_2 weights for SEGNN_MODE_BF16_TC into the UMMA shared-memory image the tensor-core
- * kernel copies verbatim (bf16, K-major, 128B swizzle).  Returns the image size in bytes when out == NULL. */
+/* Packs the message_layer_2 weights for SEGNN_MODE_BF16_TC / SEGNN_MODE_FP16_TC (operand = SEGNN_OPERAND_*) into the
+ * [128 lanes][3n] image of 16-bit pairs the tensor-core kernel copies verbatim into TMEM (gate constants folded).
+ * Returns the image size in bytes (also when out == NULL). */
 int64_t segnn_pack_w2_tc(const float* w2_ss, const float* w2_vs, const float* w2_sv, const float* w2_vv, int n,
-                         void* out, segnn_stream_t stream);
+                         int operand, void* out, segnn_stream_t stream);
 
 /* ---- K5/K6: head + self-feed integration ------------------------------------------------------------- */
 

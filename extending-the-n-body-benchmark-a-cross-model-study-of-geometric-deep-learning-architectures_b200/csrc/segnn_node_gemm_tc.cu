@@ -5,8 +5,8 @@
 //   A tile  [128 rows][K]   fp32 in HBM -> bf16, K-major, 128B swizzle, in shared memory (double buffered)
 //   B       [n_out][K]      bf16 (pre-transposed weights), K-major, 128B swizzle, loaded once per CTA
 //   D       [128][NC]       fp32 in TMEM, NC = output-column chunk (<= 192), double buffered
-// Warp roles: 8 loader warps (2 threads per row, 12 independent 16-byte loads in flight each), 4 epilogue warps
-// (TMEM lane quadrant = warp % 4), 1 MMA warp.
+// Warp roles: 8 loader warps (consecutive lanes read consecutive 32-byte pieces of a row, 6 independent loads in flight
+// each), 8 epilogue warps (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns), 1 MMA warp.
 // The kernel is HBM-bound (writes 4*n_out bytes per row against 2*K*n_out flops): the roofline is the copy rate.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -87,9 +87,17 @@ __device__ __forceinline__ uint32_t pack_pair(float lo, float hi, int half) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])     \
                : "r"(taddr))
 
+#define SEGNN_NG_LD16(taddr, r)                                                                                    \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]),   \
+                 "=r"((r)[7]), "=r"((r)[8]), "=r"((r)[9]), "=r"((r)[10]), "=r"((r)[11]), "=r"((r)[12]),              \
+                 "=r"((r)[13]), "=r"((r)[14]), "=r"((r)[15])                                                         \
+               : "r"(taddr))
+
 constexpr int kLoadWarps = 8;
-constexpr int kThreads = (kLoadWarps + 5) * 32;  // 8 loader + 4 epilogue + 1 MMA warps
-constexpr int kMmaWarp = kLoadWarps + 4;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kLoadWarps + kEpiWarps + 1) * 32;  // 8 loader + 8 epilogue + 1 MMA warps
+constexpr int kMmaWarp = kLoadWarps + kEpiWarps;
 
 // rows of class 0: node r -> plane (r*4); class 1: row r -> node r/3, plane 1 + r%3
 __device__ __forceinline__ long long plane_of(int cls, long long r) {
@@ -109,7 +117,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int b_atom_bytes = n_out * 128;         // one K-atom of B
   uint8_t* sA = smem;                           // 2 stages
   uint8_t* sB = smem + 2 * a_bytes;             // katoms * n_out * 128
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + katoms * b_atom_bytes);
+  float* sBias = reinterpret_cast<float*>(sB + katoms * b_atom_bytes);  // [n_out] (zeros past n_bias)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + n_out);
   uint64_t* afull = bars;       // [2] loaders -> MMA
   uint64_t* aempty = bars + 2;  // [2] MMA -> loaders
   uint64_t* dfull = bars + 4;   // [2] MMA -> epilogue
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&afull[i], kLoadWarps * 32);
       mbar_init(&aempty[i], 1);
       mbar_init(&dfull[i], 1);
-      mbar_init(&dempty[i], 128);
+      mbar_init(&dempty[i], kEpiWarps * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -148,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint4 v = *reinterpret_cast<const uint4*>(wt + (size_t)row * K + k8 * 8);
       *reinterpret_cast<uint4*>(sB + (k8 >> 3) * b_atom_bytes + row * 128 + (((k8 & 7) ^ (row & 7)) << 4)) = v;
     }
+    for (int i = tid; i < n_out; i += kThreads) sBias[i] = (bias != nullptr && i < n_bias) ? bias[i] : 0.f;
     proxy_fence();
   }
   tc_fence_before();
@@ -157,29 +167,37 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp < kLoadWarps) {
     // ===================== loaders: fp32 rows -> bf16 swizzled A tile =====================
-    // thread -> (row = tid / 2, half = tid & 1); each half-row is k4h consecutive float4 pieces, fetched in
-    // batches of up to 12 independent loads so a whole tile is in flight per SM
-    const int r = tid >> 1, half = tid & 1;
-    const int k4h = K / 8;  // float4 pieces per half row
+    // The tile is a list of 32-byte pieces (8 consecutive k of one row); piece p = tid + 256 i, so consecutive lanes
+    // read consecutive sectors of a row and the memory system sees full 128-byte requests (one row per lane made every
+    // lane its own request).  (row, piece-in-row) advance incrementally: no division in the loop.
+    const int k8 = K / 8;                       // pieces per row
+    const int per_thread = (128 * k8) / 256;    // K % 16 == 0 -> exact
+    const int row_step = 256 / k8, kp_step = 256 % k8;
     uint32_t t = 0;
     for (long long tile = cta; tile < tiles; tile += cta_stride, ++t) {
       const int ab = t & 1;
-      const long long gr = tile * 128 + r;
-      const bool live = gr < rows;
-      const long long pl = live ? plane_of(cls, gr) : 0;
       mbar_wait(&aempty[ab], ((t >> 1) & 1) ^ 1);
-      uint8_t* dst = sA + ab * a_bytes + r * 128;
-      // 256-bit loads: lanes own different rows, so the load rate is bound by memory transactions (32 bytes = one full
-      // sector per transaction); up to 6 independent loads (192 bytes) in flight per thread
-      const int k8h = k4h / 2;  // 8-float pieces per half row
-      for (int b0 = 0; b0 < k8h; b0 += 6) {
+      uint8_t* dst = sA + ab * a_bytes;
+      int row = tid / k8, kp = tid - row * k8;
+      for (int b0 = 0; b0 < per_thread; b0 += 6) {
         float v[6][8];
+        int rr[6], kk[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          const int k = (half * k8h + b0 + i) * 8;
+          rr[i] = row;
+          kk[i] = kp * 8;
+          row += row_step;
+          kp += kp_step;
+          if (kp >= k8) {
+            kp -= k8;
+            ++row;
+          }
 #pragma unroll
           for (int q = 0; q < 8; ++q) v[i][q] = 0.f;
-          if (live && b0 + i < k8h) {
+          const long long gr = tile * 128 + rr[i];
+          if (b0 + i < per_thread && gr < rows) {
+            const long long pl = plane_of(cls, gr);
+            const int k = kk[i];
             const float* src = k < n_in ? x0 + pl * n_in + k : x1 + pl * n_in + (k - n_in);
             asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=f"(v[i][0]), "=f"(v[i][1]), "=f"(v[i][2]), "=f"(v[i][3]), "=f"(v[i][4]), "=f"(v[i][5]),
@@ -189,11 +207,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          if (b0 + i < k8h) {
-            const int k = (half * k8h + b0 + i) * 8;  // 8 k = one 16-byte chunk of the swizzled row
+          if (b0 + i < per_thread) {
+            const int k = kk[i], r = rr[i];  // 8 k = one 16-byte chunk of the swizzled row
             const uint4 o = make_uint4(pack_pair(v[i][0], v[i][1], fp16_operands), pack_pair(v[i][2], v[i][3], fp16_operands),
                                        pack_pair(v[i][4], v[i][5], fp16_operands), pack_pair(v[i][6], v[i][7], fp16_operands));
-            *reinterpret_cast<uint4*>(dst + (k >> 6) * (128 * 128) + ((((k & 63) >> 3) ^ (r & 7)) << 4)) = o;
+            *reinterpret_cast<uint4*>(dst + (k >> 6) * (128 * 128) + r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4)) = o;
           }
         }
       }
@@ -226,10 +244,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ===================== epilogue: TMEM -> HBM =====================
-    const int quad = warp & 3;
+    // 8 warps: two per TMEM lane quadrant, each owning half of the columns of every accumulator chunk.  The profile of
+    // the 4-warp version showed the epilogue warps busy 100% of the time at ~9 clk per instruction (one warp per SM
+    // sub-partition, every step dependent on a tcgen05.ld or a bias load): twice the warps, 16-column TMEM loads that
+    // are issued one step ahead of the stores, and the bias read from shared memory.
+    const int e = warp - kLoadWarps;
+    const int quad = e & 3, chalf = e >> 2;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const int r = quad * 32 + lane;
     const int n_out1 = n_out - split;
+    const int hc = nc / 2;  // columns of a chunk owned by this warp (multiple of 16)
     uint32_t dcount = 0;
     for (long long tile = cta; tile < tiles; tile += cta_stride) {
       const long long gr = tile * 128 + r;
@@ -239,34 +263,43 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int db = dcount & 1;
         mbar_wait(&dfull[db], (dcount >> 1) & 1);
         tc_fence_after();
-        for (int j = 0; j < nc; j += 16) {
-          uint32_t a[8], b[8];
-          SEGNN_NG_LD8(tmem + lane_base + db * 256 + j, a);
-          SEGNN_NG_LD8(tmem + lane_base + db * 256 + j + 8, b);
+        const uint32_t tbase = tmem + lane_base + db * 256 + chalf * hc;
+        uint32_t cur[16], nxt[16];
+        SEGNN_NG_LD16(tbase, cur);
+        for (int j = 0; j < hc; j += 16) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (j + 16 >= nc) {  // last columns of this accumulator are in registers
+          if (j + 16 < hc) {
+            SEGNN_NG_LD16(tbase + j + 16, nxt);  // in flight while this step's stores are issued
+          } else {  // last columns of this accumulator are in registers
             tc_fence_before();
             mbar_arrive(&dempty[db]);
           }
-          if (live) {
+          const int col = c * nc + chalf * hc + j;
+          float f[16];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t* v = h == 0 ? a : b;
-              const int col = c * nc + j + h * 8;
-              float f[8];
+          for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(cur[q]);
+          if (cls == 0 && col < n_bias) {  // warp-uniform; n_bias is a multiple of 16
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                f[q] = __uint_as_float(v[q]);
-                if (cls == 0 && bias != nullptr && col + q < n_bias) f[q] += bias[col + q];
-              }
-              float* dst = col < split ? y0 + pl * split + col : y1 + pl * n_out1 + (col - split);
-              // one 256-bit store = one full 32-byte sector per lane (lanes own different rows, so the store rate is
-              // bound by memory transactions: two 16-byte stores per sector halve it)
-              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(f[0]), "f"(f[1]),
-                           "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
-                           : "memory");
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 bv = *reinterpret_cast<const float4*>(sBias + col + 4 * q4);
+              f[4 * q4 + 0] += bv.x;
+              f[4 * q4 + 1] += bv.y;
+              f[4 * q4 + 2] += bv.z;
+              f[4 * q4 + 3] += bv.w;
             }
           }
+          if (live) {
+            // one 256-bit store = one full 32-byte sector per lane (split is a multiple of 16)
+            float* dst = col < split ? y0 + pl * split + col : y1 + pl * n_out1 + (col - split);
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(f[0]), "f"(f[1]),
+                         "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
+                         : "memory");
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8), "f"(f[8]), "f"(f[9]),
+                         "f"(f[10]), "f"(f[11]), "f"(f[12]), "f"(f[13]), "f"(f[14]), "f"(f[15])
+                         : "memory");
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) cur[q] = nxt[q];
         }
       }
     }
@@ -319,11 +352,14 @@ int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, co
   SEGNN_CHECK_ARG(((uintptr_t)y0 & 31) == 0 && ((uintptr_t)y1 & 31) == 0 && ((uintptr_t)x0 & 31) == 0 &&
                       ((uintptr_t)x1 & 31) == 0,
                   "inputs and outputs must be 32-byte aligned (256-bit loads and stores)");
-  int nc = 0;
-  for (int c = 192; c >= 16; c -= 16)
+  SEGNN_CHECK_ARG(n_out % 32 == 0 && split % 16 == 0 && n_bias % 16 == 0,
+                  "tensor-core node GEMM needs n_out % 32 == 0, split % 16 == 0, n_bias % 16 == 0");
+  int nc = 0;  // accumulator chunk: two epilogue warps per TMEM lane quadrant own nc / 2 columns each
+  for (int c = 192; c >= 32; c -= 32)
     if (n_out % c == 0) { nc = c; break; }
   const int katoms = (K + 63) / 64;
-  const size_t smem = 1024 + (size_t)2 * katoms * 128 * 128 + (size_t)katoms * n_out * 128 + 8 * 8 + 16;
+  const size_t smem = 1024 + (size_t)2 * katoms * 128 * 128 + (size_t)katoms * n_out * 128 +
+                      (size_t)n_out * sizeof(float) + 8 * 8 + 16;
   if (smem > 227 * 1024) {
     set_error("segnn_node_gemm_tc: K=%d, n_out=%d needs %zu bytes of shared memory", K, n_out, smem);
     return SEGNN_E_UNSUPPORTED;

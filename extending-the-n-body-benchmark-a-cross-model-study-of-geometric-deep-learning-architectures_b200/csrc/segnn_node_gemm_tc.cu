@@ -244,63 +244,88 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ===================== epilogue: TMEM -> HBM =====================
-    // 8 warps: two per TMEM lane quadrant, each owning half of the columns of every accumulator chunk.  The profile of
-    // the 4-warp version showed the epilogue warps busy 100% of the time at ~9 clk per instruction (one warp per SM
-    // sub-partition, every step dependent on a tcgen05.ld or a bias load): twice the warps, 16-column TMEM loads that
-    // are issued one step ahead of the stores, and the bias read from shared memory.
+    // 8 warps, two per TMEM lane quadrant; the 32-column blocks of the accumulator chunks alternate between the two.
+    // tcgen05.ld hands every thread one ROW, and storing from that layout makes every lane its own L2 request of one
+    // 32-byte sector: the profile showed the L2 tag pipeline (one lookup per request) as the busiest unit and the
+    // epilogue warps stalled behind their own stores.  Each quad of lanes therefore transposes its 4 rows x 4 sectors
+    // with two rounds of xor-shuffles, after which lanes 4g..4g+3 hold the four consecutive sectors of ONE row: a
+    // 256-bit store per lane then makes full 128-byte lines (4x fewer L2 requests), with no shared memory.
     const int e = warp - kLoadWarps;
     const int quad = e & 3, chalf = e >> 2;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const int r = quad * 32 + lane;
+    const int q = lane & 3;
+    const bool up2 = (q & 2) != 0, up1 = (q & 1) != 0;
     const int n_out1 = n_out - split;
-    const int hc = nc / 2;  // columns of a chunk owned by this warp (multiple of 16)
+    const int nb = nc / 32;  // 32-column blocks per chunk
     uint32_t dcount = 0;
     for (long long tile = cta; tile < tiles; tile += cta_stride) {
-      const long long gr = tile * 128 + r;
-      const bool live = gr < rows;
-      const long long pl = live ? plane_of(cls, gr) : 0;
+      // plane index of this lane's own row, then of the 4 rows of its quad (row base + m), -1 past the end
+      const long long gr = tile * 128 + quad * 32 + lane;
+      const long long pl_own = gr < rows ? plane_of(cls, gr) : -1;
+      long long plm[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) plm[m] = __shfl_sync(0xffffffffu, pl_own, (lane & ~3) + m);
       for (int c = 0; c < nchunks; ++c, ++dcount) {
         const int db = dcount & 1;
         mbar_wait(&dfull[db], (dcount >> 1) & 1);
         tc_fence_after();
-        const uint32_t tbase = tmem + lane_base + db * 256 + chalf * hc;
-        uint32_t cur[16], nxt[16];
-        SEGNN_NG_LD16(tbase, cur);
-        for (int j = 0; j < hc; j += 16) {
+        bool arrived = false;
+        for (int bk = 0; bk < nb; ++bk) {
+          if (((c * nb + bk) & 1) != chalf) continue;
+          uint32_t u[32];  // u[8 k + i]: sector k (columns 8k .. 8k+7 of the block) of this lane's row
+          SEGNN_NG_LD16(tmem + lane_base + db * 256 + bk * 32, u);
+          SEGNN_NG_LD16(tmem + lane_base + db * 256 + bk * 32 + 16, (u + 16));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (j + 16 < hc) {
-            SEGNN_NG_LD16(tbase + j + 16, nxt);  // in flight while this step's stores are issued
-          } else {  // last columns of this accumulator are in registers
+          if (bk + 2 >= nb) {  // this warp's last block of the accumulator is in registers
             tc_fence_before();
             mbar_arrive(&dempty[db]);
+            arrived = true;
           }
-          const int col = c * nc + chalf * hc + j;
-          float f[16];
+          const int col0 = c * nc + bk * 32;
+          if (cls == 0 && col0 < n_bias) {  // warp-uniform; n_bias is a multiple of 32 here (checked by the launcher)
 #pragma unroll
-          for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(cur[q]);
-          if (cls == 0 && col < n_bias) {  // warp-uniform; n_bias is a multiple of 16
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const float4 bv = *reinterpret_cast<const float4*>(sBias + col + 4 * q4);
-              f[4 * q4 + 0] += bv.x;
-              f[4 * q4 + 1] += bv.y;
-              f[4 * q4 + 2] += bv.z;
-              f[4 * q4 + 3] += bv.w;
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 bv = *reinterpret_cast<const float4*>(sBias + col0 + 4 * q4);
+              u[4 * q4 + 0] = __float_as_uint(__uint_as_float(u[4 * q4 + 0]) + bv.x);
+              u[4 * q4 + 1] = __float_as_uint(__uint_as_float(u[4 * q4 + 1]) + bv.y);
+              u[4 * q4 + 2] = __float_as_uint(__uint_as_float(u[4 * q4 + 2]) + bv.z);
+              u[4 * q4 + 3] = __float_as_uint(__uint_as_float(u[4 * q4 + 3]) + bv.w);
             }
           }
-          if (live) {
-            // one 256-bit store = one full 32-byte sector per lane (split is a multiple of 16)
-            float* dst = col < split ? y0 + pl * split + col : y1 + pl * n_out1 + (col - split);
-            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(f[0]), "f"(f[1]),
-                         "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
-                         : "memory");
-            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8), "f"(f[8]), "f"(f[9]),
-                         "f"(f[10]), "f"(f[11]), "f"(f[12]), "f"(f[13]), "f"(f[14]), "f"(f[15])
-                         : "memory");
-          }
+          // round 1 (lane ^ 2): slots {k, k + 2} -> slot = 2 * (row bit 1) + (sector bit 0), sector bit 1 = lane bit 1
 #pragma unroll
-          for (int q = 0; q < 16; ++q) cur[q] = nxt[q];
+          for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t lo = u[8 * k + i], hi = u[8 * (k + 2) + i];
+              const uint32_t rcv = __shfl_xor_sync(0xffffffffu, up2 ? lo : hi, 2);
+              u[8 * k + i] = up2 ? rcv : lo;
+              u[8 * (k + 2) + i] = up2 ? hi : rcv;
+            }
+          // round 2 (lane ^ 1): slots {2 rb, 2 rb + 1} -> slot = row offset m, sector = lane & 3
+#pragma unroll
+          for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t lo = u[8 * (2 * rb) + i], hi = u[8 * (2 * rb + 1) + i];
+              const uint32_t rcv = __shfl_xor_sync(0xffffffffu, up1 ? lo : hi, 1);
+              u[8 * (2 * rb) + i] = up1 ? rcv : lo;
+              u[8 * (2 * rb + 1) + i] = up1 ? hi : rcv;
+            }
+          // u[8 m + i]: columns col0 + 8 q + i of row (quad base + m): lanes 4g..4g+3 write one 128-byte line
+          const int col = col0 + 8 * q;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (plm[m] >= 0) {
+              float* dst = col < split ? y0 + plm[m] * split + col : y1 + plm[m] * n_out1 + (col - split);
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(u[8 * m + 0]),
+                           "r"(u[8 * m + 1]), "r"(u[8 * m + 2]), "r"(u[8 * m + 3]), "r"(u[8 * m + 4]), "r"(u[8 * m + 5]),
+                           "r"(u[8 * m + 6]), "r"(u[8 * m + 7])
+                           : "memory");
+            }
+          }
         }
+        if (!arrived) mbar_arrive(&dempty[db]);
       }
     }
   }
@@ -345,16 +370,16 @@ int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, co
   SEGNN_CHECK_ARG(x0 && wt_s && wt_v && y0, "null pointer");
   const int K = x1 ? 2 * n_in : n_in;
   SEGNN_CHECK_ARG(n_in % 16 == 0 && K <= 192, "tensor-core node GEMM needs n_in % 16 == 0 and K <= 192");
-  SEGNN_CHECK_ARG(n_out % 16 == 0, "tensor-core node GEMM needs n_out % 16 == 0");
+  SEGNN_CHECK_ARG(n_out % 32 == 0, "tensor-core node GEMM needs n_out % 32 == 0");
   if (y1 == nullptr) split = n_out;
   SEGNN_CHECK_ARG(split % 8 == 0 && split > 0 && split <= n_out, "split must be a positive multiple of 8");
   SEGNN_CHECK_ARG(bias == nullptr || (n_bias >= 0 && n_bias <= n_out), "n_bias out of range");
   SEGNN_CHECK_ARG(((uintptr_t)y0 & 31) == 0 && ((uintptr_t)y1 & 31) == 0 && ((uintptr_t)x0 & 31) == 0 &&
                       ((uintptr_t)x1 & 31) == 0,
                   "inputs and outputs must be 32-byte aligned (256-bit loads and stores)");
-  SEGNN_CHECK_ARG(n_out % 32 == 0 && split % 16 == 0 && n_bias % 16 == 0,
-                  "tensor-core node GEMM needs n_out % 32 == 0, split % 16 == 0, n_bias % 16 == 0");
-  int nc = 0;  // accumulator chunk: two epilogue warps per TMEM lane quadrant own nc / 2 columns each
+  SEGNN_CHECK_ARG(n_out % 32 == 0 && split % 32 == 0 && n_bias % 32 == 0,
+                  "tensor-core node GEMM needs n_out, split and n_bias to be multiples of 32");
+  int nc = 0;  // accumulator chunk: its 32-column blocks alternate between the two epilogue warps of a lane quadrant
   for (int c = 192; c >= 32; c -= 32)
     if (n_out % c == 0) { nc = c; break; }
   const int katoms = (K + 63) / 64;

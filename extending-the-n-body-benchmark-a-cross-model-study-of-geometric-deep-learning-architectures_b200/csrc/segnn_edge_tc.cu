@@ -28,6 +28,9 @@
 //   warp 3:  MMA issuer + TMEM allocation + cp.async.bulk of the sender rows of Q (36 KB per tile at n = 96, double
 //            buffered, two tiles ahead) and of the item's 4 receiver rows of P + the tile geometry (lane = column:
 //            unit vectors, distances, mass products, validity; 4-slot ring, two tiles ahead);
+// Projection rows P, Q [node][plane][3n] arrive as (scalar part [n] | (gate, vector) pairs [n][2]): the node GEMM
+// writes that column order (its weight image is permuted at pack time), so a thread fetches both parts of a plane
+// with one 64-bit shared-memory load.
 //   warps 7, 11, 15: scalar-channel producers (channel blocks 0, 1, 2): the s' plane of the B tile needs only the
 //            (0s) parts of P and Q, so it is produced here for all 32 columns, which moves 22% of the producer
 //            instructions off the three compute sub-partitions.
@@ -355,12 +358,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       const float* r0 = sP + (2 * rp) * 4 * n3;  // rows past the graph end: stale but finite, masked by valid = 0
       const float* r1 = sP + (2 * rp + 1) * 4 * n3;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int part = 1; part < 3; ++part) {
-          const float sc = part < 2 ? 0.5f : 1.0f;
-          P[c * 3 + part] = make_float2(sc * r0[c * n3 + part * n + w], sc * r1[c * n3 + part * n + w]);
-        }
+      for (int c = 0; c < 4; ++c) {  // (gate, vector) parts of a channel are adjacent: one 64-bit load per plane
+        const float2 a = *reinterpret_cast<const float2*>(r0 + c * n3 + n + 2 * w);
+        const float2 b = *reinterpret_cast<const float2*>(r1 + c * n3 + n + 2 * w);
+        P[c * 3 + 1] = make_float2(0.5f * a.x, 0.5f * b.x);
+        P[c * 3 + 2] = make_float2(a.y, b.y);
+      }
     };
 
     auto produce = [&](const TileCursor& cur) {
@@ -391,9 +394,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
           const float* qr = qs + sl * 4 * n3;
           float q[12];
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int part = 1; part < 3; ++part) q[c * 3 + part] = qr[c * n3 + part * n + w];
+          for (int c = 0; c < 4; ++c) {
+            const float2 gv = *reinterpret_cast<const float2*>(qr + c * n3 + n + 2 * w);
+            q[c * 3 + 1] = gv.x;
+            q[c * 3 + 2] = gv.y;
+          }
           const float2 ax = e ? hi2(AX) : lo2(AX), ay = e ? hi2(AY) : lo2(AY), az = e ? hi2(AZ) : lo2(AZ);
           const float2 le = e ? hi2(LE) : lo2(LE), mm = e ? hi2(MM) : lo2(MM);
           // half pre-activations of the scalar / gate channels: (P0 + Q0)/2 + a.(P0k + Q0k)/2 + |r| wd/2 + m_i m_j wm/2

@@ -59,10 +59,21 @@ class SEGNNLayer(nn.Module):
             bn_msg=(None, None), bn_feat=(None, None))
         if out["msg2"]["ss"].is_cuda and n in ops.TC_MULTIPLICITIES and ops.tc_available():
             out["msg2"]["tc"] = ops.pack_w2_tc(out["msg2"], n, operand)
-            for key in ("msg1", "upd1", "upd2"):
+            for key in ("upd1", "upd2"):
                 out[key]["wt_s"] = ops.pack_node_weight_tc(out[key]["w_s"], operand)
                 out[key]["wt_v"] = ops.pack_node_weight_tc(out[key]["w_v"], operand)
                 out[key]["operand"] = operand
+            # message_layer_1 projections for the tensor-core edge kernel: columns of each 3n block reordered to
+            # (scalar part [n] | (gate, vector) pairs [n][2]) so the kernel reads both parts with one 64-bit load
+            m1 = out["msg1"]
+            j = torch.arange(2 * n, device=m1["w_s"].device)
+            perm = torch.cat([torch.arange(n, device=j.device), n + (j % 2) * n + j // 2])
+            perm6 = torch.cat([perm, 3 * n + perm])
+            m1["wt_s"] = ops.pack_node_weight_tc(m1["w_s"][:, perm6].contiguous(), operand)
+            m1["wt_v"] = ops.pack_node_weight_tc(m1["w_v"][:, perm6].contiguous(), operand)
+            m1["operand"] = operand
+            bias3 = torch.cat([m1["bias"], m1["bias"].new_zeros(n)])  # bias on the (0s, 0g) parts of P only
+            m1["bias_tc"] = bias3[perm].contiguous()
         if eval_bn and self.message_norm is not None:
             bn = self.message_norm
             out["bn_msg"] = packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), n,
@@ -77,7 +88,10 @@ class SEGNNLayer(nn.Module):
         n = self.n
         tc = mode in _TC_MODES
         m1 = w["msg1"]
-        p, q = ops.node_gemm(h, None, m1, 6 * n, bias=m1["bias"], n_bias=2 * n, split=3 * n, tc=tc)
+        if tc:  # permuted column order + bias (see pack)
+            p, q = ops.node_gemm(h, None, m1, 6 * n, bias=m1["bias_tc"], n_bias=3 * n, split=3 * n, tc=True)
+        else:
+            p, q = ops.node_gemm(h, None, m1, 6 * n, bias=m1["bias"], n_bias=2 * n, split=3 * n, tc=False)
         agg = ops.edge_layer(mode, pos, mass, batch_size, num_nodes, n, p, q, m1["w_edge"], w["msg2"],
                              w["bn_msg"][0], w["bn_msg"][1])
         u1 = w["upd1"]

@@ -93,7 +93,7 @@ int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const
 
 /* Same contraction on tcgen05 (bf16 or fp16 operands, fp32 accumulate in TMEM, fp32 output): wt_s, wt_v are the
  * weights pre-transposed to 16-bit [n_out][K] by segnn_pack_node_weight_tc with the same `operand` format.  Needs
- * n_in % 16 == 0, K <= 192, n_out % 16 == 0, split % 8 == 0, 32-byte aligned tensors. */
+ * n_in % 16 == 0, K <= 192, n_out / split / n_bias multiples of 32, 32-byte aligned tensors. */
 int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
                        const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, int operand,
                        segnn_stream_t stream);
@@ -122,7 +122,9 @@ int segnn_tp_combine(const float* y, const float* node_attr, int nodes, int n, i
  * message_layer_1 is linear in (x_i, x_j), so its weight contraction is hoisted to the node GEMM:
  *   p, q [nodes][4][3n] = per plane (X0[2n], X1[n]) -- receiver (P) and sender (Q) projections with the
  *   constant Y_0 and the bias folded in (see pack_msg1 in the host package; the node GEMM writes both with
- *   split = 3n).
+ *   split = 3n).  Column order inside each plane row: SEGNN_MODE_FP32 reads (0s [n] | 0g [n] | 1o [n]); the
+ *   tensor-core modes read (0s [n] | (0g, 1o) pairs [n][2]) so that one 64-bit load fetches both parts of a channel
+ *   (the host package permutes the columns of the node-GEMM weight image accordingly).
  * w_edge1 [6n] = (d->0e [2n], mm->0e [2n], d->1o [n], mm->1o [n]) (Y_0 folded into the 0e parts).
  * msg2 weights (fp32 mode): w2_ss [n][2n] (Y_0 folded), w2_vs [n][2n] (1/sqrt3 folded), w2_sv [n][n],
  *   w2_vv [n][n] (Y_0 folded), b2 [2n].

@@ -49,14 +49,15 @@ with torch.no_grad():
     x_in, node_attr = ops.prep(p, v, B, N)
     h = ops.embed(x_in, node_attr, w["embed"]["w"], w["embed"]["bias"], n)
     m1, u1, u2 = lw["msg1"], lw["upd1"], lw["upd2"]
-    pq = ops.node_gemm(h, None, m1, 6 * n, bias=m1["bias"], n_bias=2 * n, split=3 * n, tc=tc)
+    pq_bias, pq_nb = (m1["bias_tc"], 3 * n) if tc else (m1["bias"], 2 * n)
+    pq = ops.node_gemm(h, None, m1, 6 * n, bias=pq_bias, n_bias=pq_nb, split=3 * n, tc=tc)
     agg = ops.edge_layer(mode, p, m, B, N, n, pq[0], pq[1], m1["w_edge"], lw["msg2"], lw["bn_msg"][0], lw["bn_msg"][1])
     y1 = ops.node_gemm(h, agg, u1, 3 * n, tc=tc)
     g1 = ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"])
     y2 = ops.node_gemm(g1, None, u2, 2 * n, tc=tc)
     rows = nodes * 4
     cases = [
-        ("node_gemm P/Q  (K=n,  out 6n)", lambda: ops.node_gemm(h, None, m1, 6 * n, bias=m1["bias"], n_bias=2 * n, split=3 * n, tc=tc),
+        ("node_gemm P/Q  (K=n,  out 6n)", lambda: ops.node_gemm(h, None, m1, 6 * n, bias=pq_bias, n_bias=pq_nb, split=3 * n, tc=tc),
          rows * 4 * (n + 6 * n)),
         ("edge_layer K3", lambda: ops.edge_layer(mode, p, m, B, N, n, pq[0], pq[1], m1["w_edge"], lw["msg2"], lw["bn_msg"][0],
                                                  lw["bn_msg"][1]), rows * 4 * (6 * n + n)),

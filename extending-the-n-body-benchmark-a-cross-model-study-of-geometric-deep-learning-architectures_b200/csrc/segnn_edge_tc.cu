@@ -686,9 +686,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       const int st = t & 1;
       K3_TRACE(0, t);
       // critical path first: the tile's 48 MMAs as soon as its B stage is written and the accumulators are free
-      mbar_wait(&full[st], (t >> 1) & 1, err_flag);
+      mbar_wait_a(smem_u32(&full[st]), (t >> 1) & 1);
       K3_TRACE(1, t);
-      mbar_wait(dempty, (t & 1) ^ 1, err_flag);
+      mbar_wait_a(smem_u32(dempty), (t & 1) ^ 1);
       K3_TRACE(2, t);
       tc_fence_after();
       const uint64_t bst = bdesc0 + (uint64_t)(st * (64 >> 4));  // column half of the swizzled rows

@@ -46,7 +46,7 @@ namespace tc {
 constexpr int kRecv = 4;      // receivers per work item
 constexpr int kSend = 8;      // senders per tile
 constexpr int kCols = 32;     // edges (columns) per tile
-constexpr int kGeoSlots = 4;  // geometry ring depth
+constexpr int kGeoSlots = 8;  // geometry ring depth (geometry is written three tiles ahead, read until epilogue(t))
 constexpr int kWarps = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -644,50 +644,66 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         gvalid = (jj < N) && (ii < N) && (jj != ii);
       }
     };
-    auto tile_publish = [&](const TileCursor& c) {
+    // geometry of tile c into ring slot t % 8 (last read in epilogue(t - 8), long complete)
+    auto tile_geometry = [&](const TileCursor& c) {
       if (c.item < items) {
-        const uint32_t t = c.t;
-        const int slot = t & (kGeoSlots - 1), st = t & 1;
+        const int slot = c.t & (kGeoSlots - 1);
         float ux, uy, uz, len;
         unit_vec(gsx - grx, gsy - gry, gsz - grz, ux, uy, uz, len);
-        float* gs = geo + slot * 6 * kCols;  // slot last read in epilogue(t - 4), long complete (see produce)
+        float* gs = geo + slot * 6 * kCols;
         gs[0 * kCols + lane] = kY1 * ux;
         gs[1 * kCols + lane] = kY1 * uy;
         gs[2 * kCols + lane] = kY1 * uz;
         gs[3 * kCols + lane] = len;
         gs[4 * kCols + lane] = gsm * grm;
         gs[5 * kCols + lane] = gvalid ? 1.0f : 0.0f;
-        __syncwarp();
-        if (elect_one()) {
-          const int nvalid = min(kSend, N - c.sb * kSend);
-          const uint32_t bytes = (uint32_t)nvalid * 4 * n3 * (uint32_t)sizeof(float);
-          const float* src = qq + ((long long)c.g * N + (long long)c.sb * kSend) * 4 * n3;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&qfull[st])), "r"(bytes)
-                       : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           smem_u32(sQ + st * kQStageFloats)),
-                       "l"(src), "r"(bytes), "r"(smem_u32(&qfull[st]))
-                       : "memory");
-        }
-        __syncwarp();
       }
+      __syncwarp();
     };
-    TileCursor pf{(int)blockIdx.x, 0, 0u, 0, 0};  // runs two tiles ahead of the MMA issue
-    locate(pf);
+    // sender rows of tile c into Q stage t & 1: arms qfull[st], which also publishes the tile's geometry (written by this
+    // warp at least one loop iteration earlier)
+    auto tile_copy = [&](const TileCursor& c) {
+      if (c.item < items && elect_one()) {
+        const int st = c.t & 1;
+        const int nvalid = min(kSend, N - c.sb * kSend);
+        const uint32_t bytes = (uint32_t)nvalid * 4 * n3 * (uint32_t)sizeof(float);
+        const float* src = qq + ((long long)c.g * N + (long long)c.sb * kSend) * 4 * n3;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&qfull[st])), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sQ + st * kQStageFloats)),
+                     "l"(src), "r"(bytes), "r"(smem_u32(&qfull[st]))
+                     : "memory");
+      }
+      __syncwarp();
+    };
+    // cp: next tile whose rows are copied (t + 2 in the loop); gp: next tile whose geometry is written (t + 3)
+    TileCursor cp{(int)blockIdx.x, 0, 0u, 0, 0}, gp{(int)blockIdx.x, 0, 0u, 0, 0};
+    locate(cp);
+    locate(gp);
     load_prow(blockIdx.x);
-    for (int i = 0; i < 2; ++i) {
-      tile_load(pf);
-      tile_publish(pf);
-      advance_located(pf);
+    for (int i = 0; i < 3; ++i) {  // geometry of tiles 0, 1, 2; rows of tiles 0, 1
+      tile_load(gp);
+      tile_geometry(gp);
+      advance_located(gp);
+      if (i < 2) {
+        tile_copy(cp);
+        advance_located(cp);
+      }
     }
-    tile_load(pf);  // tile 2: published at the end of iteration 0
+    tile_load(gp);  // positions of tile 3 in flight
     for (TileCursor c{(int)blockIdx.x, 0, 0u, 0, 0}; c.item < items; advance(c)) {
       const uint32_t t = c.t;
       const int st = t & 1;
       K3_TRACE(0, t);
-      // critical path first: the tile's 48 MMAs as soon as its B stage is written and the accumulators are free
       mbar_wait_a(smem_u32(&full[st]), (t >> 1) & 1);
       K3_TRACE(1, t);
+      // first thing after full[st]: every producer is done with Q stage st, so the rows of tile t + 2 start their trip
+      // from L2 now (issued after the MMAs they landed only just in time: the copy latency was the tile period's
+      // critical path); every producer thread holds this item's P rows in registers: fetch the next item's
+      tile_copy(cp);
+      advance_located(cp);
+      if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
       mbar_wait_a(smem_u32(dempty), (t & 1) ^ 1);
       K3_TRACE(2, t);
       tc_fence_after();
@@ -713,13 +729,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       }
       __syncwarp();
       K3_TRACE(3, t);
-      // housekeeping off the critical path: producers are done with Q stage st (full[st] observed): refill it for tile
-      // t + 2; every producer thread holds this item's P rows in registers: fetch the next item's (single buffer);
-      // geometry of tile t + 2 into the ring, loads of tile t + 3 in flight until the next iteration
-      tile_publish(pf);
-      advance_located(pf);
-      tile_load(pf);
-      if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
+      // off the critical path: geometry of tile t + 3 into the ring, positions of tile t + 4 in flight
+      tile_geometry(gp);
+      advance_located(gp);
+      tile_load(gp);
       K3_TRACE(4, t);
     }
   }

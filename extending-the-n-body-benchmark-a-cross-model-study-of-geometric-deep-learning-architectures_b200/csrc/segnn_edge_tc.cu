@@ -624,23 +624,33 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       __syncwarp();
     };
     // Inputs of a tile = its geometry (lane = column = rp * 16 + sender * 2 + (r & 1)) + the 8 sender rows of Q.
-    // tile_load issues the position loads only (nothing waits for them); tile_publish, one iteration later, writes
-    // the geometry into ring slot t % 4, then arms qfull[st] and issues the bulk copy: one barrier covers both.
+    // This warp's loop is a serial instruction chain that has to fit the tile period, so its index arithmetic is kept
+    // to per-item base pointers (set when a cursor enters an item) plus 32-bit offsets.
     const int gsl = (lane >> 1) & 7, gr = 2 * (lane >> 4) + (lane & 1);
     float gsx = 0.f, gsy = 0.f, gsz = 0.f, gsm = 0.f, grx = 0.f, gry = 0.f, grz = 0.f, grm = 0.f;  // raw loads
     bool gvalid = false;
+    const float* pos_g = pos;    // positions / masses of the geometry cursor's graph
+    const float* mass_g = mass;
+    const float* q_g = qq;       // sender rows of the copy cursor's graph
+    const uint32_t row_bytes = 4u * n3 * (uint32_t)sizeof(float);
+    const uint32_t last_block_bytes = (uint32_t)(N - (send_blocks - 1) * kSend) * row_bytes;
+    auto enter_geo = [&](const TileCursor& c) {
+      pos_g = pos + (long long)c.g * N * 3;
+      mass_g = mass + (long long)c.g * N;
+    };
+    auto enter_copy = [&](const TileCursor& c) { q_g = qq + (long long)c.g * N * 4 * n3; };
     auto tile_load = [&](const TileCursor& c) {
       if (c.item < items) {
         const int jj = c.sb * kSend + gsl, ii = c.i0 + gr;
-        const long long js = (long long)c.g * N + min(jj, N - 1), is = (long long)c.g * N + min(ii, N - 1);
-        gsx = pos[js * 3 + 0];
-        gsy = pos[js * 3 + 1];
-        gsz = pos[js * 3 + 2];
-        gsm = mass[js];
-        grx = pos[is * 3 + 0];
-        gry = pos[is * 3 + 1];
-        grz = pos[is * 3 + 2];
-        grm = mass[is];
+        const int js = min(jj, N - 1), is = min(ii, N - 1);
+        gsx = pos_g[js * 3 + 0];
+        gsy = pos_g[js * 3 + 1];
+        gsz = pos_g[js * 3 + 2];
+        gsm = mass_g[js];
+        grx = pos_g[is * 3 + 0];
+        gry = pos_g[is * 3 + 1];
+        grz = pos_g[is * 3 + 2];
+        grm = mass_g[is];
         gvalid = (jj < N) && (ii < N) && (jj != ii);
       }
     };
@@ -648,13 +658,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     auto tile_geometry = [&](const TileCursor& c) {
       if (c.item < items) {
         const int slot = c.t & (kGeoSlots - 1);
-        float ux, uy, uz, len;
-        unit_vec(gsx - grx, gsy - gry, gsz - grz, ux, uy, uz, len);
+        const float dx = gsx - grx, dy = gsy - gry, dz = gsz - grz;
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        const float inv = rsqrtf(fmaxf(d2, 1e-24f));  // r / max(|r|, 1e-12) with the approximate reciprocal root
+        const float sc = kY1 * inv;
         float* gs = geo + slot * 6 * kCols;
-        gs[0 * kCols + lane] = kY1 * ux;
-        gs[1 * kCols + lane] = kY1 * uy;
-        gs[2 * kCols + lane] = kY1 * uz;
-        gs[3 * kCols + lane] = len;
+        gs[0 * kCols + lane] = sc * dx;
+        gs[1 * kCols + lane] = sc * dy;
+        gs[2 * kCols + lane] = sc * dz;
+        gs[3 * kCols + lane] = d2 * inv;
         gs[4 * kCols + lane] = gsm * grm;
         gs[5 * kCols + lane] = gvalid ? 1.0f : 0.0f;
       }
@@ -665,30 +677,49 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     auto tile_copy = [&](const TileCursor& c) {
       if (c.item < items && elect_one()) {
         const int st = c.t & 1;
-        const int nvalid = min(kSend, N - c.sb * kSend);
-        const uint32_t bytes = (uint32_t)nvalid * 4 * n3 * (uint32_t)sizeof(float);
-        const float* src = qq + ((long long)c.g * N + (long long)c.sb * kSend) * 4 * n3;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&qfull[st])), "r"(bytes)
-                     : "memory");
+        const uint32_t bytes = c.sb == send_blocks - 1 ? last_block_bytes : (uint32_t)kSend * row_bytes;
+        const float* src = q_g + c.sb * (kSend * 4 * n3);
+        const uint32_t bar = smem_u32(&qfull[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          smem_u32(sQ + st * kQStageFloats)),
-                     "l"(src), "r"(bytes), "r"(smem_u32(&qfull[st]))
+                     "l"(src), "r"(bytes), "r"(bar)
                      : "memory");
       }
       __syncwarp();
+    };
+    auto advance_geo = [&](TileCursor& c) {
+      ++c.t;
+      if (++c.sb == send_blocks) {
+        c.sb = 0;
+        c.item += gridDim.x;
+        locate(c);
+        enter_geo(c);
+      }
+    };
+    auto advance_copy = [&](TileCursor& c) {
+      ++c.t;
+      if (++c.sb == send_blocks) {
+        c.sb = 0;
+        c.item += gridDim.x;
+        locate(c);
+        enter_copy(c);
+      }
     };
     // cp: next tile whose rows are copied (t + 2 in the loop); gp: next tile whose geometry is written (t + 3)
     TileCursor cp{(int)blockIdx.x, 0, 0u, 0, 0}, gp{(int)blockIdx.x, 0, 0u, 0, 0};
     locate(cp);
     locate(gp);
+    enter_copy(cp);
+    enter_geo(gp);
     load_prow(blockIdx.x);
     for (int i = 0; i < 3; ++i) {  // geometry of tiles 0, 1, 2; rows of tiles 0, 1
       tile_load(gp);
       tile_geometry(gp);
-      advance_located(gp);
+      advance_geo(gp);
       if (i < 2) {
         tile_copy(cp);
-        advance_located(cp);
+        advance_copy(cp);
       }
     }
     tile_load(gp);  // positions of tile 3 in flight
@@ -702,7 +733,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       // from L2 now (issued after the MMAs they landed only just in time: the copy latency was the tile period's
       // critical path); every producer thread holds this item's P rows in registers: fetch the next item's
       tile_copy(cp);
-      advance_located(cp);
+      advance_copy(cp);
       if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
       mbar_wait_a(smem_u32(dempty), (t & 1) ^ 1);
       K3_TRACE(2, t);
@@ -731,7 +762,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       K3_TRACE(3, t);
       // off the critical path: geometry of tile t + 3 into the ring, positions of tile t + 4 in flight
       tile_geometry(gp);
-      advance_located(gp);
+      advance_geo(gp);
       tile_load(gp);
       K3_TRACE(4, t);
     }

@@ -261,13 +261,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], kComputeThreads + kScalarWarps * 32);
+      mbar_init(&full[i], 4 * NW + kScalarWarps);  // one arrival per producer warp
       mbar_init(&empty[i], 1);
       mbar_init(&qfull[i], 1);
     }
     mbar_init(dfull, 1);
     mbar_init(pfull, 1);
-    mbar_init(dempty, kComputeThreads);
+    mbar_init(dempty, 4 * NW);  // one arrival per compute warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -437,8 +437,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         *reinterpret_cast<uint4*>(sB + row * 128 + ((chunk ^ (row & 7)) << 4)) =
             make_uint4(packed[0][p], packed[1][p], packed[2][p], packed[3][p]);
       }
+      // one arrival per warp (480 per-thread arrivals on one mbarrier serialise: the phase completed several hundred
+      // clk after the last store): every lane fences its own stores, the warp syncs, lane 0 arrives
       proxy_fence();
-      mbar_arrive_a(bar0 + 8 * st);  // full[st]
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(bar0 + 8 * st);  // full[st]
       K3_TRACE(2, t);
     };
 
@@ -456,7 +459,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       // accumulators are in registers: hand the TMEM tiles back to the MMA warps
       tc_fence_before();
-      mbar_arrive_a(bar0 + 8 * 5);  // dempty
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(bar0 + 8 * 5);  // dempty
       K3_TRACE(4, t);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -597,7 +601,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         }
       }
       proxy_fence();
-      mbar_arrive_a(bar0 + 8 * st);  // full[st]
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(bar0 + 8 * st);  // full[st]
       K3_TRACE(2, t);
     }
   } else if (warp == kMmaWarp) {

@@ -27,4 +27,4 @@ for tile in range(20, 34):
     print(f"--- tile {tile}")
     for wp in (0, 5, 10, 7, 11, 3):
         ev = [int(x) - t0 if x > 0 else -1 for x in t[wp, tile]]
-        print(f"  warp {wp:2d}: {ev[:6]}")
+        print(f"  warp {wp:2d}: {ev[:7]}")

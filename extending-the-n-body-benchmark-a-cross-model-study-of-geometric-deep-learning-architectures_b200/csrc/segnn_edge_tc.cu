@@ -639,24 +639,29 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
     const float* q_g = qq;       // sender rows of the copy cursor's graph
     const uint32_t row_bytes = 4u * n3 * (uint32_t)sizeof(float);
     const uint32_t last_block_bytes = (uint32_t)(N - (send_blocks - 1) * kSend) * row_bytes;
-    auto enter_geo = [&](const TileCursor& c) {
+    bool rvalid = false;
+    auto enter_geo = [&](const TileCursor& c) {  // per item: graph base pointers + this lane's receiver
       pos_g = pos + (long long)c.g * N * 3;
       mass_g = mass + (long long)c.g * N;
-    };
-    auto enter_copy = [&](const TileCursor& c) { q_g = qq + (long long)c.g * N * 4 * n3; };
-    auto tile_load = [&](const TileCursor& c) {
       if (c.item < items) {
-        const int jj = c.sb * kSend + gsl, ii = c.i0 + gr;
-        const int js = min(jj, N - 1), is = min(ii, N - 1);
-        gsx = pos_g[js * 3 + 0];
-        gsy = pos_g[js * 3 + 1];
-        gsz = pos_g[js * 3 + 2];
-        gsm = mass_g[js];
+        const int ii = c.i0 + gr, is = min(ii, N - 1);
         grx = pos_g[is * 3 + 0];
         gry = pos_g[is * 3 + 1];
         grz = pos_g[is * 3 + 2];
         grm = mass_g[is];
-        gvalid = (jj < N) && (ii < N) && (jj != ii);
+        rvalid = ii < N;
+      }
+    };
+    auto enter_copy = [&](const TileCursor& c) { q_g = qq + (long long)c.g * N * 4 * n3; };
+    auto tile_load = [&](const TileCursor& c) {
+      if (c.item < items) {
+        const int jj = c.sb * kSend + gsl;
+        const int js = min(jj, N - 1);
+        gsx = pos_g[js * 3 + 0];
+        gsy = pos_g[js * 3 + 1];
+        gsz = pos_g[js * 3 + 2];
+        gsm = mass_g[js];
+        gvalid = rvalid && (jj < N) && (jj != c.i0 + gr);
       }
     };
     // geometry of tile c into ring slot t % 8 (last read in epilogue(t - 8), long complete)
@@ -740,6 +745,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       tile_copy(cp);
       advance_copy(cp);
       if (c.sb == 0) load_prow(c.item + (int)gridDim.x);
+      K3_TRACE(5, t);
       mbar_wait_a(smem_u32(dempty), (t & 1) ^ 1);
       K3_TRACE(2, t);
       tc_fence_after();
@@ -767,6 +773,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       K3_TRACE(3, t);
       // off the critical path: geometry of tile t + 3 into the ring, positions of tile t + 4 in flight
       tile_geometry(gp);
+      K3_TRACE(6, t);
       advance_geo(gp);
       tile_load(gp);
       K3_TRACE(4, t);

@@ -226,7 +226,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sims-per-gpu", type=int, default=1024)
     ap.add_argument("--cpu-sims", type=int, default=4, help="bounded CPU sample: simulations per CPU step")
-    ap.add_argument("--mode", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "fp32", "bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training", action="store_true", help="skip the secondary training measurements")
     args = ap.parse_args()
@@ -349,7 +349,7 @@ def main():
             "metric": "SEGNN self-feed particle-steps/s", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if mode == "bf16" else "f32", "data": "synthetic",
+            "dtype": {"bf16": "bf16", "fp16": "f16"}.get(mode, "f32"), "data": "synthetic",
             "config": workload_config(args, B),
             "edge_msgs_per_s": world * edges * LAYERS * args.steps / (ms * 1e-3),
             "fused_edge_kernel_edge_msgs_per_s": world * edges / (k3_ms * 1e-3),
@@ -361,9 +361,9 @@ def main():
             "roofline": {"kernel": "edge_layer (K3, message_layer_1 combine + gate + message_layer_2 + gate + "
                                    "aggregation)", "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
                          "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                         "traffic": K3_DRAM_BYTES_PER_LAUNCH if (mode == "bf16" and B == 1024) else None,
+                         "traffic": K3_DRAM_BYTES_PER_LAUNCH if (mode in ("bf16", "fp16") and B == 1024) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                           "(profiles/r1_v8_ncu_full_summary.json); algorithmic P + Q + agg bytes = "
+                                           "(profiles/r1_v13_ncu_full_summary.json); algorithmic P + Q + agg bytes = "
                                            "1.10e9",
                          "peak_source": peak_src + ", bf16 dense sustained",
                          "flop_per_edge": FLOP_PER_EDGE_MSG2, "edges_per_launch": edges,
@@ -371,7 +371,7 @@ def main():
                          "share_of_step": k3_ms * LAYERS / (ms / args.steps),
                          "reference_equivalent_tflops": edges * FLOP_PER_EDGE_REFERENCE / (k3_ms * 1e-3) / 1e12,
                          "note": ("fp32 FFMA mode: the tensor pipe is idle, fraction shown against the bf16 tensor "
-                                  "roofline for continuity" if mode != "bf16" else "bf16 tcgen05 mode")},
+                                  "roofline for continuity" if mode not in ("bf16", "fp16") else f"{mode} tcgen05 mode")},
         }
         if world == 1 and not args.no_cpu_baseline:
             sims = args.cpu_sims

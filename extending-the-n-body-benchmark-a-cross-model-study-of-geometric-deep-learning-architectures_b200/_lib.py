@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsegnn_b200.so")
 MODE_FP32 = 0
 MODE_BF16_TC = 1
 MODE_FP16_TC = 2
+MODE_FP16_PACKED = 3
 OPERAND_BF16, OPERAND_FP16 = 0, 1
 
 _c = ctypes
@@ -30,6 +31,7 @@ PROTOTYPES = {
     "segnn_embed_fwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_node_gemm": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr]),
     "segnn_node_gemm_tc": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _int, _ptr]),
+    "segnn_node_gemm_tc_pair16": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _int, _ptr]),
     "segnn_pack_node_weight_tc": (_int, [_ptr, _int, _int, _int, _ptr, _ptr]),
     "segnn_tp_combine": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "segnn_edge_layer_fwd": (_int, [_int, _ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,

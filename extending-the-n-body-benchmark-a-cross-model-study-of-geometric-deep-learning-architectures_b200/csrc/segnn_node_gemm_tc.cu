@@ -103,12 +103,14 @@ constexpr int kMmaWarp = kLoadWarps + kEpiWarps;
 __device__ __forceinline__ long long plane_of(int cls, long long r) {
   return cls == 0 ? r * 4 : (r / 3) * 4 + 1 + (r % 3);
 }
+// pair16 output mode: four row classes (one per plane), row r of class c = node r, plane c
+__device__ __forceinline__ long long plane_of4(int cls, long long r) { return r * 4 + cls; }
 
 __global__ void __launch_bounds__(kThreads, 1)
     node_gemm_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int nodes, int n_in,
                         const __nv_bfloat16* __restrict__ wt_s, const __nv_bfloat16* __restrict__ wt_v,
                         const float* __restrict__ bias, int n_bias, int n_out, int nc, float* __restrict__ y0,
-                        float* __restrict__ y1, int split, int ctas_cls0, int fp16_operands) {
+                        float* __restrict__ y1, int split, int ctas_cls0, int fp16_operands, int pair16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int K = x1 ? 2 * n_in : n_in;
@@ -127,10 +129,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // the first ctas_cls0 CTAs own the scalar-plane rows, the rest the vector-plane rows (3x as many)
-  const int cls = (int)blockIdx.x < ctas_cls0 ? 0 : 1;
-  const int cta = cls == 0 ? blockIdx.x : blockIdx.x - ctas_cls0;
-  const int cta_stride = cls == 0 ? ctas_cls0 : gridDim.x - ctas_cls0;
-  const long long rows = cls == 0 ? (long long)nodes : (long long)nodes * 3;
+  // pair16: four row classes (class = plane, rows = nodes), CTAs dealt round-robin (the grid is a multiple of 4)
+  const int cls = pair16 ? (int)(blockIdx.x & 3) : ((int)blockIdx.x < ctas_cls0 ? 0 : 1);
+  const int cta = pair16 ? (int)(blockIdx.x >> 2) : (cls == 0 ? blockIdx.x : blockIdx.x - ctas_cls0);
+  const int cta_stride = pair16 ? (int)(gridDim.x >> 2) : (cls == 0 ? ctas_cls0 : gridDim.x - ctas_cls0);
+  const long long rows = (pair16 || cls == 0) ? (long long)nodes : (long long)nodes * 3;
   const long long tiles = (rows + 127) / 128;
   const __nv_bfloat16* __restrict__ wt = cls == 0 ? wt_s : wt_v;
   const int nchunks = n_out / nc;
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int q = 0; q < 8; ++q) v[i][q] = 0.f;
           const long long gr = tile * 128 + rr[i];
           if (b0 + i < per_thread && gr < rows) {
-            const long long pl = plane_of(cls, gr);
+            const long long pl = pair16 ? plane_of4(cls, gr) : plane_of(cls, gr);
             const int k = kk[i];
             const float* src = k < n_in ? x0 + pl * n_in + k : x1 + pl * n_in + (k - n_in);
             asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (long long tile = cta; tile < tiles; tile += cta_stride) {
       // plane index of this lane's own row, then of the 4 rows of its quad (row base + m), -1 past the end
       const long long gr = tile * 128 + quad * 32 + lane;
-      const long long pl_own = gr < rows ? plane_of(cls, gr) : -1;
+      const long long pl_own = gr < rows ? (pair16 ? plane_of4(cls, gr) : plane_of(cls, gr)) : -1;
       long long plm[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) plm[m] = __shfl_sync(0xffffffffu, pl_own, (lane & ~3) + m);
@@ -291,6 +294,34 @@ __global__ void __launch_bounds__(kThreads, 1)
               u[4 * q4 + 2] = __float_as_uint(__uint_as_float(u[4 * q4 + 2]) + bv.z);
               u[4 * q4 + 3] = __float_as_uint(__uint_as_float(u[4 * q4 + 3]) + bv.w);
             }
+          }
+          if (pair16) {
+            // fp16 output, nodes interleaved in pairs: y[node / 2][plane][col][node & 1] (the layout the packed-half
+            // edge kernel reads).  Lanes 2g, 2g+1 hold the two nodes of a pair (rows of a class are consecutive nodes,
+            // tiles start at even rows): the even lane packs columns [0, 16) of both, the odd lane columns [16, 32),
+            // 64 contiguous bytes each = one 128-byte line per pair of lanes.
+            const bool odd = (lane & 1) != 0;
+            uint32_t w16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t rcv = __shfl_xor_sync(0xffffffffu, odd ? u[i] : u[16 + i], 1);
+              const float lo = __uint_as_float(odd ? rcv : u[i]), hi = __uint_as_float(odd ? u[16 + i] : rcv);
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w16[i]) : "f"(hi), "f"(lo));
+            }
+            if (pl_own >= 0) {
+              const int col = col0 + (odd ? 16 : 0);
+              const long long prow = (pl_own >> 3) * 4 + cls;  // (node / 2) * 4 + plane
+              uint32_t* dst = col < split
+                                  ? reinterpret_cast<uint32_t*>(y0) + prow * split + col
+                                  : reinterpret_cast<uint32_t*>(y1) + prow * n_out1 + (col - split);
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w16[0]), "r"(w16[1]),
+                           "r"(w16[2]), "r"(w16[3]), "r"(w16[4]), "r"(w16[5]), "r"(w16[6]), "r"(w16[7])
+                           : "memory");
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8), "r"(w16[8]), "r"(w16[9]),
+                           "r"(w16[10]), "r"(w16[11]), "r"(w16[12]), "r"(w16[13]), "r"(w16[14]), "r"(w16[15])
+                           : "memory");
+            }
+            continue;
           }
           // round 1 (lane ^ 2): slots {k, k + 2} -> slot = 2 * (row bit 1) + (sector bit 0), sector bit 1 = lane bit 1
 #pragma unroll
@@ -361,9 +392,11 @@ int segnn_pack_node_weight_tc(const float* w, int K, int n_out, int operand, voi
   return SEGNN_OK;
 }
 
-int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
-                       const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, int operand,
-                       segnn_stream_t stream) {
+}  // extern "C"
+
+static int node_gemm_tc_launch(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                               const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, int operand,
+                               int pair16, segnn_stream_t stream) {
   SEGNN_CHECK_ARG(nodes >= 0 && n_in >= 1 && n_out >= 1, "bad sizes");
   SEGNN_CHECK_ARG(operand == SEGNN_OPERAND_BF16 || operand == SEGNN_OPERAND_FP16, "unknown operand format");
   if (nodes == 0) return SEGNN_OK;
@@ -405,11 +438,33 @@ int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, co
   if (c0 > tiles0) c0 = tiles0;
   long long c1 = sms - c0;
   if (c1 > tiles1) c1 = tiles1;
-  ngemm::node_gemm_tc_kernel<<<(unsigned)(c0 + c1), ngemm::kThreads, smem, (cudaStream_t)stream>>>(
+  unsigned grid = (unsigned)(c0 + c1);
+  if (pair16) {  // four row classes of `nodes` rows each, CTAs dealt round-robin
+    SEGNN_CHECK_ARG(nodes % 2 == 0, "pair-interleaved output needs an even node count (even graph size)");
+    long long per_cls = sms / 4 > 0 ? sms / 4 : 1;
+    if (per_cls > tiles0) per_cls = tiles0;
+    grid = (unsigned)(4 * per_cls);
+  }
+  ngemm::node_gemm_tc_kernel<<<grid, ngemm::kThreads, smem, (cudaStream_t)stream>>>(
       x0, x1, nodes, n_in, (const __nv_bfloat16*)wt_s, (const __nv_bfloat16*)wt_v, bias, n_bias, n_out, nc, y0, y1,
-      split, (int)c0, operand == SEGNN_OPERAND_FP16 ? 1 : 0);
+      split, (int)c0, operand == SEGNN_OPERAND_FP16 ? 1 : 0, pair16);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
+}
+
+extern "C" {
+
+int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                       const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, int operand,
+                       segnn_stream_t stream) {
+  return node_gemm_tc_launch(x0, x1, nodes, n_in, wt_s, wt_v, bias, n_bias, n_out, y0, y1, split, operand, 0, stream);
+}
+
+int segnn_node_gemm_tc_pair16(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                              const float* bias, int n_bias, int n_out, void* y0, void* y1, int split, int operand,
+                              segnn_stream_t stream) {
+  return node_gemm_tc_launch(x0, x1, nodes, n_in, wt_s, wt_v, bias, n_bias, n_out, (float*)y0, (float*)y1, split, operand,
+                             1, stream);
 }
 
 }  // extern "C"

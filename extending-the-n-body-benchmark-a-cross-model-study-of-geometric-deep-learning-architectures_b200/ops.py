@@ -7,10 +7,11 @@ from typing import Optional
 
 import torch
 
-from ._lib import MODE_BF16_TC, MODE_FP16_TC, MODE_FP32, OPERAND_BF16, OPERAND_FP16, check, lib
+from ._lib import (MODE_BF16_TC, MODE_FP16_PACKED, MODE_FP16_TC, MODE_FP32, OPERAND_BF16, OPERAND_FP16, check,
+                   lib)
 
 __all__ = ["edge_index", "edge_attr", "prep", "embed", "node_gemm", "pack_node_weight_tc", "tp_combine", "edge_layer", "head",
-           "integrate", "counter_add", "launch_count", "MODE_FP32", "MODE_BF16_TC", "MODE_FP16_TC"]
+           "integrate", "counter_add", "launch_count", "MODE_FP32", "MODE_BF16_TC", "MODE_FP16_TC", "MODE_FP16_PACKED"]
 
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -107,6 +108,23 @@ def node_gemm(x0, x1, w, n_out: int, bias=None, n_bias: int = 0, split: int = 0,
                                       n_out, _p(y0), _p(y1), split, _stream()), "segnn_node_gemm")
     _bump()
     return (y0, y1) if split else y0
+
+
+def node_gemm_pair16(x0, w, n_out: int, bias, n_bias: int, split: int):
+    """Tensor-core node GEMM with fp16 output, nodes interleaved in pairs (segnn_node_gemm_tc_pair16): returns
+    (y0 [nodes/2, 4, split, 2], y1 [nodes/2, 4, n_out - split, 2]) float16."""
+    nodes, _, n_in = x0.shape
+    dev = x0.device
+    if nodes % 2:
+        raise ValueError("pair-interleaved projections need an even node count")
+    y0 = torch.empty((nodes // 2, 4, split, 2), dtype=torch.float16, device=dev)
+    y1 = torch.empty((nodes // 2, 4, n_out - split, 2), dtype=torch.float16, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.segnn_node_gemm_tc_pair16(_p(x0), None, nodes, n_in, _p(w["wt_s"]), _p(w["wt_v"]), _p(bias), n_bias,
+                                            n_out, _p(y0), _p(y1), split, int(w.get("operand", OPERAND_FP16)),
+                                            _stream()), "segnn_node_gemm_tc_pair16")
+    _bump()
+    return y0, y1
 
 
 def pack_node_weight_tc(w: torch.Tensor, operand: int = OPERAND_BF16) -> torch.Tensor:

@@ -12,8 +12,9 @@ from .graph import infer_graph_shape
 from .irreps import Irreps, weight_balanced_irreps
 from .o3_building_blocks import BatchNorm, O3TensorProduct, O3TensorProductSwishGate
 
-_MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16_TC, "fp16": ops.MODE_FP16_TC}
-_TC_MODES = (ops.MODE_BF16_TC, ops.MODE_FP16_TC)
+_MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16_TC, "fp16": ops.MODE_FP16_TC, "fp16p": ops.MODE_FP16_PACKED}
+_TC_MODES = (ops.MODE_BF16_TC, ops.MODE_FP16_TC, ops.MODE_FP16_PACKED)
+_FP16_OPERAND_MODES = ("fp16", "fp16p")
 
 
 class SEGNNLayer(nn.Module):
@@ -74,6 +75,16 @@ class SEGNNLayer(nn.Module):
             m1["operand"] = operand
             bias3 = torch.cat([m1["bias"], m1["bias"].new_zeros(n)])  # bias on the (0s, 0g) parts of P only
             m1["bias_tc"] = bias3[perm].contiguous()
+            if operand == 1:
+                # packed-half edge kernel (compute_mode 'fp16p'): the factor 1/2 of the (0s, 0g) pre-activations is
+                # folded into the projections (the fp32-math kernels apply it on load)
+                half = torch.ones(3 * n, device=j.device)
+                half[:n] = 0.5
+                half[n::2] = 0.5
+                half6 = torch.cat([half, half])
+                m1["wt_s_h"] = ops.pack_node_weight_tc((m1["w_s"][:, perm6] * half6).contiguous(), operand)
+                m1["wt_v_h"] = ops.pack_node_weight_tc((m1["w_v"][:, perm6] * half6).contiguous(), operand)
+                m1["bias_tc_h"] = (m1["bias_tc"] * half).contiguous()
         if eval_bn and self.message_norm is not None:
             bn = self.message_norm
             out["bn_msg"] = packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), n,
@@ -88,7 +99,13 @@ class SEGNNLayer(nn.Module):
         n = self.n
         tc = mode in _TC_MODES
         m1 = w["msg1"]
-        if tc:  # permuted column order + bias (see pack)
+        if mode == ops.MODE_FP16_PACKED:  # fp16 projections, nodes interleaved in pairs
+            if num_nodes % 2:
+                raise RuntimeError("compute_mode='fp16p' needs an even number of bodies per graph (sender pairs); "
+                                   "use 'fp16' or 'bf16'")
+            p, q = ops.node_gemm_pair16(h, dict(wt_s=m1["wt_s_h"], wt_v=m1["wt_v_h"], operand=1), 6 * n,
+                                        m1["bias_tc_h"], 3 * n, 3 * n)
+        elif tc:  # permuted column order + bias (see pack)
             p, q = ops.node_gemm(h, None, m1, 6 * n, bias=m1["bias_tc"], n_bias=3 * n, split=3 * n, tc=True)
         else:
             p, q = ops.node_gemm(h, None, m1, 6 * n, bias=m1["bias"], n_bias=2 * n, split=3 * n, tc=False)
@@ -112,7 +129,7 @@ class SEGNNLayer(nn.Module):
             raise NotImplementedError("standalone SEGNNLayer.forward is built for lmax_h = 1; use SEGNN.forward")
         if self.training:
             raise NotImplementedError("train-mode BatchNorm for the standalone layer: use SEGNN.forward")
-        w = self.pack(n_nodes - 1, operand=1 if mode == "fp16" else 0)
+        w = self.pack(n_nodes - 1, operand=1 if mode in _FP16_OPERAND_MODES else 0)
         h = packing.to_planar(x.float(), self.n)
         out = self.run(w, _MODES[mode], h, pos.float().contiguous(), mass.float().reshape(-1).contiguous(),
                        node_attr.float().contiguous(), num_graphs, n_nodes)
@@ -123,7 +140,8 @@ class SEGNN(nn.Module):
     """Steerable E(3) equivariant message passing network -- models/segnn/segnn.py:14-189 (task='node').
 
     ``compute_mode``: 'fp32' (FFMA kernels, the 1e-5 parity mode), 'bf16' (tcgen05 tensor-core kernels, the mode the
-    benchmark reports) or 'fp16' (the same kernels with fp16 operands: 8x smaller operand rounding at the same speed)."""
+    benchmark reports), 'fp16' (the same kernels with fp16 operands: 8x smaller operand rounding at the same speed) or
+    'fp16p' (fp16 operands and the message_layer_1 combine in packed fp16 on fp16 projections; even N only)."""
 
     def __init__(self, input_irreps="2x1o + 1x0e", hidden_features=64, lmax_h=1, lmax_attr=1, num_layers=4,
                  output_irreps="2x1o", norm="batch", pool="avg", task="node", additional_message_irreps="2x0e",
@@ -180,7 +198,7 @@ class SEGNN(nn.Module):
 
     # -- packing cache ------------------------------------------------------------------------------------------
     def packed(self, degree: int):
-        operand = 1 if self.compute_mode == "fp16" else 0  # 16-bit operand format of the tensor-core images
+        operand = 1 if self.compute_mode in _FP16_OPERAND_MODES else 0  # 16-bit operand format of the tensor-core images
         tensors = list(self.parameters()) + list(self.buffers())
         key = (degree, operand, tuple((t.data_ptr(), t._version, t.device, t.dtype) for t in tensors))
         if key != self._pack_key:

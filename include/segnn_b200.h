@@ -41,8 +41,13 @@ enum {
 enum {
   SEGNN_MODE_FP32 = 0,   /* FFMA, fp32 everywhere: the 1e-5 parity mode */
   SEGNN_MODE_BF16_TC = 1, /* tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM): the throughput mode */
-  SEGNN_MODE_FP16_TC = 2  /* same kernels with fp16 operands (11-bit mantissa): 8x smaller operand rounding at the same
+  SEGNN_MODE_FP16_TC = 2, /* same kernels with fp16 operands (11-bit mantissa): 8x smaller operand rounding at the same
                              speed; operands must stay below 65504 (true for normalised features) */
+  SEGNN_MODE_FP16_PACKED = 3 /* fp16 operands AND the message_layer_1 combine in packed fp16 (HFMA2 over sender pairs)
+                                on fp16 projections written by segnn_node_gemm_tc_pair16: p, q are then
+                                [nodes / 2][4][3n][2] fp16 arrays (passed through the float pointers), the column
+                                order is that of the tensor-core modes and the (0s, 0g) parts carry a factor 1/2
+                                (folded into the node-GEMM weight image).  Needs an even graph size N. */
 };
 
 /* 16-bit operand format of the tensor-core kernels and of their packed weight images */
@@ -97,6 +102,14 @@ int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const
 int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
                        const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, int operand,
                        segnn_stream_t stream);
+
+/* Same GEMM with 16-bit output, nodes interleaved in pairs: y [nodes / 2][4][cols][2] fp16 (element (node, plane, col)
+ * at ((node / 2) * 4 + plane) * cols * 2 + col * 2 + (node & 1)); cols = split for y0, n_out - split for y1.  This is
+ * the layout SEGNN_MODE_FP16_PACKED reads: one 32-bit word holds the same projection of two consecutive senders.
+ * `nodes` must be even (graphs of even size, so pairs never straddle two graphs). */
+int segnn_node_gemm_tc_pair16(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                              const float* bias, int n_bias, int n_out, void* y0, void* y1, int split, int operand,
+                              segnn_stream_t stream);
 
 /* w [K][n_out] fp32 -> wt [n_out][K] bf16 / fp16 (the B operand image of segnn_node_gemm_tc). */
 int segnn_pack_node_weight_tc(const float* w, int K, int n_out, int operand, void* wt, segnn_stream_t stream);

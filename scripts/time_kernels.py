@@ -50,17 +50,22 @@ with torch.no_grad():
     h = ops.embed(x_in, node_attr, w["embed"]["w"], w["embed"]["bias"], n)
     m1, u1, u2 = lw["msg1"], lw["upd1"], lw["upd2"]
     pq_bias, pq_nb = (m1["bias_tc"], 3 * n) if tc else (m1["bias"], 2 * n)
-    pq = ops.node_gemm(h, None, m1, 6 * n, bias=pq_bias, n_bias=pq_nb, split=3 * n, tc=tc)
+    packed = mode == ops.MODE_FP16_PACKED
+    m1h = dict(wt_s=m1.get("wt_s_h"), wt_v=m1.get("wt_v_h"), operand=1)
+    if packed:
+        pq_fn = lambda: ops.node_gemm_pair16(h, m1h, 6 * n, m1["bias_tc_h"], 3 * n, 3 * n)
+    else:
+        pq_fn = lambda: ops.node_gemm(h, None, m1, 6 * n, bias=pq_bias, n_bias=pq_nb, split=3 * n, tc=tc)
+    pq = pq_fn()
     agg = ops.edge_layer(mode, p, m, B, N, n, pq[0], pq[1], m1["w_edge"], lw["msg2"], lw["bn_msg"][0], lw["bn_msg"][1])
     y1 = ops.node_gemm(h, agg, u1, 3 * n, tc=tc)
     g1 = ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"])
     y2 = ops.node_gemm(g1, None, u2, 2 * n, tc=tc)
     rows = nodes * 4
     cases = [
-        ("node_gemm P/Q  (K=n,  out 6n)", lambda: ops.node_gemm(h, None, m1, 6 * n, bias=pq_bias, n_bias=pq_nb, split=3 * n, tc=tc),
-         rows * 4 * (n + 6 * n)),
+        ("node_gemm P/Q  (K=n,  out 6n)", pq_fn, rows * 4 * n + rows * 6 * n * (2 if packed else 4)),
         ("edge_layer K3", lambda: ops.edge_layer(mode, p, m, B, N, n, pq[0], pq[1], m1["w_edge"], lw["msg2"], lw["bn_msg"][0],
-                                                 lw["bn_msg"][1]), rows * 4 * (6 * n + n)),
+                                                 lw["bn_msg"][1]), rows * 6 * n * (2 if packed else 4) + rows * 4 * n),
         ("node_gemm upd1 (K=2n, out 3n)", lambda: ops.node_gemm(h, agg, u1, 3 * n, tc=tc), rows * 4 * (2 * n + 3 * n)),
         ("tp_combine gate", lambda: ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"]), rows * 4 * (3 * n + n)),
         ("node_gemm upd2 (K=n,  out 2n)", lambda: ops.node_gemm(g1, None, u2, 2 * n, tc=tc), rows * 4 * (n + 2 * n)),

@@ -11,16 +11,17 @@ from oracle import segnn_oracle as O
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "segnn_small.pt")
-TOL = {"fp32": 1e-5, "bf16": 2e-2, "fp16": 2.5e-3}
+TOL = {"fp32": 1e-5, "bf16": 2e-2, "fp16": 2.5e-3, "fp16p": 2.5e-3}
 
 
 def rel(a, b):
     return float((a.double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def modes(n=32):
+def modes(n=32, num_nodes=1):
+    """Compute modes that apply: tensor-core modes need n in {32, 64, 96}; the packed-half mode also an even N."""
     tc = S.ops.tc_available() and n in S.ops.TC_MULTIPLICITIES
-    return ["fp32"] + (["bf16", "fp16"] if tc else [])
+    return ["fp32"] + (["bf16", "fp16"] if tc else []) + (["fp16p"] if tc and num_nodes % 2 == 0 else [])
 
 
 def make_pair(H, L, seed=0, dtype=torch.float32):
@@ -68,14 +69,14 @@ def test_o3_transform(B, N):
 
 
 @pytest.mark.parametrize("H,L,B,N", [(64, 4, 100, 5), (192, 6, 64, 5), (192, 6, 2, 100), (128, 2, 1, 37),
-                                       (50, 2, 3, 9), (64, 1, 1, 2)])
+                                       (50, 2, 3, 9), (64, 1, 1, 2), (192, 6, 3, 6), (128, 3, 2, 38), (64, 2, 5, 12)])
 def test_segnn_per_layer_parity(H, L, B, N):
     om, m = make_pair(H, L, seed=H + N)
     pos, vel, mass = O.synthetic_system(B, N, seed=5)
     with torch.no_grad():
         ref, ref_layers = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N),
                              return_layers=True)
-        for mode in modes(m.n):
+        for mode in modes(m.n, N):
             m.compute_mode = mode
             out, layers = m(gpu_graph(pos, vel, mass, B, N), return_layers=True)
             print(f"[{mode}] H={H} N={N}: per-layer rel err", [f"{rel(a, b):.2e}" for a, b in zip(layers, ref_layers)],
@@ -83,6 +84,16 @@ def test_segnn_per_layer_parity(H, L, B, N):
             for i, (a, b) in enumerate(zip(layers, ref_layers)):
                 assert rel(a, b) < TOL[mode], f"{mode} layer {i}: {rel(a, b)}"
             assert rel(out, ref) < TOL[mode], f"{mode} output: {rel(out, ref)}"
+
+
+def test_packed_half_mode_refuses_odd_graph_size():
+    if not S.ops.tc_available():
+        pytest.skip("tensor-core kernels not built")
+    _, m = make_pair(64, 1)
+    m.compute_mode = "fp16p"
+    pos, vel, mass = O.synthetic_system(2, 5, seed=1)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="even number of bodies"):
+        m(gpu_graph(pos, vel, mass, 2, 5))
 
 
 def test_double_precision_module_and_precomputed_attributes():
@@ -532,11 +543,15 @@ def test_large_graph_tensor_core_mode_agrees_with_fp32_mode():
         m.compute_mode = "fp16"  # same kernels, fp16 operands: 8x smaller rounding keeps N = 1000 inside the 2e-2 budget
         out16 = m.forward_state(p, v, ms, B, N)
         err16 = float((out16 - ref).abs().max() / ref.abs().max())
+        m.compute_mode = "fp16p"  # packed-half producers on fp16 projections
+        out16p = m.forward_state(p, v, ms, B, N)
+        err16p = float((out16p - ref).abs().max() / ref.abs().max())
         m.compute_mode = "bf16"
         out = m.forward_state(p, v, ms, B, N)
         err = float((out - ref).abs().max() / ref.abs().max())
         print(f"N=1000 vs fp32 mode: bf16 {err:.2e}, fp16 {err16:.2e} (output max {float(ref.abs().max()):.2f})")
-        assert err < 6e-2 and err16 < 2e-2
+        print(f"N=1000 fp16p vs fp32 mode: {err16p:.2e}")
+        assert err < 6e-2 and err16 < 2e-2 and err16p < 2e-2
         perm = torch.randperm(N).cuda()
         out_p = m.forward_state(p[perm].contiguous(), v[perm].contiguous(), ms[perm].contiguous(), B, N)
         assert float((out_p - out[perm]).abs().max() / out.abs().max()) < 2e-2  # bf16 operands, different tile grouping

@@ -31,6 +31,8 @@ PROTOTYPES = {
     "segnn_embed_fwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_node_gemm": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr]),
     "segnn_node_gemm_tc": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _int, _ptr]),
+    "segnn_node_gemm_tc_out16": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr, _int, _ptr]),
+    "segnn_tp_combine_y16": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "segnn_node_gemm_tc_pair16": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _int, _ptr]),
     "segnn_pack_node_weight_tc": (_int, [_ptr, _int, _int, _int, _ptr, _ptr]),
     "segnn_tp_combine": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),

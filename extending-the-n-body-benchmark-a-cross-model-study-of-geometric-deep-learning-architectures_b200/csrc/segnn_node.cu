@@ -2,6 +2,8 @@
 // K2 embedding, the node GEMM, the attribute combine, the head and the self-feed integrator.
 #include <stdarg.h>
 
+#include <cuda_fp16.h>
+
 #include "segnn_common.cuh"
 
 namespace segnn {
@@ -233,8 +235,11 @@ __global__ void __launch_bounds__(256) node_gemm_kernel(const float* __restrict_
 // Attribute combine + gate / residual / eval-BN epilogue of a node-level tensor product.
 // ------------------------------------------------------------------------------------------------
 
-template <bool GATE>
-__global__ void tp_combine_kernel(const float* __restrict__ y, const float* __restrict__ node_attr, int nodes, int n,
+__device__ __forceinline__ float ldy(const float* p) { return *p; }
+__device__ __forceinline__ float ldy(const __half* p) { return __half2float(*p); }
+
+template <bool GATE, typename YT>
+__global__ void tp_combine_kernel(const YT* __restrict__ y, const float* __restrict__ node_attr, int nodes, int n,
                                   const float* __restrict__ bias, const float* __restrict__ residual,
                                   const float* __restrict__ bn_mul,
                                   const float* __restrict__ bn_add, float* __restrict__ out) {
@@ -247,18 +252,18 @@ __global__ void tp_combine_kernel(const float* __restrict__ y, const float* __re
     const int w = (int)(idx - node * n);
     const float a0 = node_attr[node * 4 + 0], ax = node_attr[node * 4 + 1], ay = node_attr[node * 4 + 2],
                 az = node_attr[node * 4 + 3];
-    const float* y0 = y + node * 4 * n_out;
-    const float* y1 = y0 + n_out;
-    const float* y2 = y1 + n_out;
-    const float* y3 = y2 + n_out;
-    float zs = a0 * y0[w] + ax * y1[w] + ay * y2[w] + az * y3[w];
+    const YT* y0 = y + node * 4 * n_out;
+    const YT* y1 = y0 + n_out;
+    const YT* y2 = y1 + n_out;
+    const YT* y3 = y2 + n_out;
+    float zs = a0 * ldy(y0 + w) + ax * ldy(y1 + w) + ay * ldy(y2 + w) + az * ldy(y3 + w);
     if (bias != nullptr) zs += bias[w];
-    const float t = y0[n0 + w];
-    float vx = ax * t + a0 * y1[n0 + w];
-    float vy = ay * t + a0 * y2[n0 + w];
-    float vz = az * t + a0 * y3[n0 + w];
+    const float t = ldy(y0 + n0 + w);
+    float vx = ax * t + a0 * ldy(y1 + n0 + w);
+    float vy = ay * t + a0 * ldy(y2 + n0 + w);
+    float vz = az * t + a0 * ldy(y3 + n0 + w);
     if (GATE) {
-      float zg = a0 * y0[n + w] + ax * y1[n + w] + ay * y2[n + w] + az * y3[n + w];
+      float zg = a0 * ldy(y0 + n + w) + ax * ldy(y1 + n + w) + ay * ldy(y2 + n + w) + az * ldy(y3 + n + w);
       if (bias != nullptr) zg += bias[n + w];
       float g = sig_gate(zg);
       zs = silu_gate(zs);
@@ -284,6 +289,79 @@ __global__ void tp_combine_kernel(const float* __restrict__ y, const float* __re
     out[o + n + w] = vx;
     out[o + 2 * n + w] = vy;
     out[o + 3 * n + w] = vz;
+  }
+}
+
+// Same pass on fp16 rows, two channels per thread (half2 loads, float2 stores): the scalar version is bound by its
+// load instructions once the rows are half as wide.
+template <bool GATE>
+__global__ void tp_combine_y16_kernel(const __half* __restrict__ y, const float* __restrict__ node_attr, int nodes, int n,
+                                      const float* __restrict__ bias, const float* __restrict__ residual,
+                                      const float* __restrict__ bn_mul, const float* __restrict__ bn_add,
+                                      float* __restrict__ out) {
+  const int n0 = GATE ? 2 * n : n;
+  const int n_out = n0 + n;
+  const int nh = n / 2;
+  const int64_t total = (int64_t)nodes * nh;
+  auto ld2 = [](const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); };
+  auto ldf2 = [](const float* p) { return *reinterpret_cast<const float2*>(p); };
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t node = idx / nh;
+    const int w = 2 * (int)(idx - node * nh);
+    const float4 a = *reinterpret_cast<const float4*>(node_attr + node * 4);
+    const __half* y0 = y + node * 4 * n_out;
+    const __half* y1 = y0 + n_out;
+    const __half* y2 = y1 + n_out;
+    const __half* y3 = y2 + n_out;
+    auto mix = [&](int off) {  // a0 y0 + a1 . (y1, y2, y3) at column offset `off`
+      const float2 p0 = ld2(y0 + off), p1 = ld2(y1 + off), p2 = ld2(y2 + off), p3 = ld2(y3 + off);
+      return make_float2(a.x * p0.x + a.y * p1.x + a.z * p2.x + a.w * p3.x,
+                         a.x * p0.y + a.y * p1.y + a.z * p2.y + a.w * p3.y);
+    };
+    float2 zs = mix(w);
+    if (bias != nullptr) {
+      const float2 b = ldf2(bias + w);
+      zs.x += b.x;
+      zs.y += b.y;
+    }
+    const float2 t = ld2(y0 + n0 + w), q1 = ld2(y1 + n0 + w), q2 = ld2(y2 + n0 + w), q3 = ld2(y3 + n0 + w);
+    float2 vx = make_float2(a.y * t.x + a.x * q1.x, a.y * t.y + a.x * q1.y);
+    float2 vy = make_float2(a.z * t.x + a.x * q2.x, a.z * t.y + a.x * q2.y);
+    float2 vz = make_float2(a.w * t.x + a.x * q3.x, a.w * t.y + a.x * q3.y);
+    if (GATE) {
+      float2 zg = mix(n + w);
+      if (bias != nullptr) {
+        const float2 b = ldf2(bias + n + w);
+        zg.x += b.x;
+        zg.y += b.y;
+      }
+      const float gx = sig_gate(zg.x), gy = sig_gate(zg.y);
+      zs.x = silu_gate(zs.x);
+      zs.y = silu_gate(zs.y);
+      vx.x *= gx; vy.x *= gx; vz.x *= gx;
+      vx.y *= gy; vy.y *= gy; vz.y *= gy;
+    }
+    const int64_t o = node * 4 * n;
+    if (residual != nullptr) {
+      const float2 r0 = ldf2(residual + o + w), r1 = ldf2(residual + o + n + w), r2 = ldf2(residual + o + 2 * n + w),
+                   r3 = ldf2(residual + o + 3 * n + w);
+      zs.x += r0.x; zs.y += r0.y;
+      vx.x += r1.x; vx.y += r1.y;
+      vy.x += r2.x; vy.y += r2.y;
+      vz.x += r3.x; vz.y += r3.y;
+    }
+    if (bn_mul != nullptr) {
+      const float2 ms = ldf2(bn_mul + w), mv = ldf2(bn_mul + n + w), ad = ldf2(bn_add + w);
+      zs.x = fmaf(zs.x, ms.x, ad.x);
+      zs.y = fmaf(zs.y, ms.y, ad.y);
+      vx.x *= mv.x; vy.x *= mv.x; vz.x *= mv.x;
+      vx.y *= mv.y; vy.y *= mv.y; vz.y *= mv.y;
+    }
+    *reinterpret_cast<float2*>(out + o + w) = zs;
+    *reinterpret_cast<float2*>(out + o + n + w) = vx;
+    *reinterpret_cast<float2*>(out + o + 2 * n + w) = vy;
+    *reinterpret_cast<float2*>(out + o + 3 * n + w) = vz;
   }
 }
 
@@ -441,11 +519,41 @@ int segnn_tp_combine(const float* y, const float* node_attr, int nodes, int n, i
   SEGNN_CHECK_ARG((bn_mul == nullptr) == (bn_add == nullptr), "bn_mul and bn_add must be given together");
   int grid = grid_for((int64_t)nodes * n, 256);
   if (gate)
-    tp_combine_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(y, node_attr, nodes, n, bias, residual, bn_mul,
-                                                                   bn_add, out);
+    tp_combine_kernel<true, float><<<grid, 256, 0, (cudaStream_t)stream>>>(y, node_attr, nodes, n, bias, residual,
+                                                                          bn_mul, bn_add, out);
   else
-    tp_combine_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(y, node_attr, nodes, n, bias, residual, bn_mul,
-                                                                    bn_add, out);
+    tp_combine_kernel<false, float><<<grid, 256, 0, (cudaStream_t)stream>>>(y, node_attr, nodes, n, bias, residual,
+                                                                           bn_mul, bn_add, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_tp_combine_y16(const void* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                         const float* residual, const float* bn_mul, const float* bn_add, float* out,
+                         segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(y && node_attr && out, "null pointer");
+  SEGNN_CHECK_ARG((bn_mul == nullptr) == (bn_add == nullptr), "bn_mul and bn_add must be given together");
+  const __half* yh = reinterpret_cast<const __half*>(y);
+  if (n % 2 == 0) {  // every row offset is then a multiple of 2 elements: half2 / float2 accesses are aligned
+    int grid = grid_for((int64_t)nodes * (n / 2), 256);
+    if (gate)
+      tp_combine_y16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(yh, node_attr, nodes, n, bias, residual,
+                                                                         bn_mul, bn_add, out);
+    else
+      tp_combine_y16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(yh, node_attr, nodes, n, bias, residual,
+                                                                          bn_mul, bn_add, out);
+    SEGNN_CHECK_LAUNCH();
+    return SEGNN_OK;
+  }
+  int grid = grid_for((int64_t)nodes * n, 256);
+  if (gate)
+    tp_combine_kernel<true, __half><<<grid, 256, 0, (cudaStream_t)stream>>>(yh, node_attr, nodes, n, bias, residual,
+                                                                           bn_mul, bn_add, out);
+  else
+    tp_combine_kernel<false, __half><<<grid, 256, 0, (cudaStream_t)stream>>>(yh, node_attr, nodes, n, bias, residual,
+                                                                            bn_mul, bn_add, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

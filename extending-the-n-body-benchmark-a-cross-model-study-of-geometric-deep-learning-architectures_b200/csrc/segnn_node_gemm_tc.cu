@@ -130,10 +130,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // the first ctas_cls0 CTAs own the scalar-plane rows, the rest the vector-plane rows (3x as many)
   // pair16: four row classes (class = plane, rows = nodes), CTAs dealt round-robin (the grid is a multiple of 4)
-  const int cls = pair16 ? (int)(blockIdx.x & 3) : ((int)blockIdx.x < ctas_cls0 ? 0 : 1);
-  const int cta = pair16 ? (int)(blockIdx.x >> 2) : (cls == 0 ? blockIdx.x : blockIdx.x - ctas_cls0);
-  const int cta_stride = pair16 ? (int)(gridDim.x >> 2) : (cls == 0 ? ctas_cls0 : gridDim.x - ctas_cls0);
-  const long long rows = (pair16 || cls == 0) ? (long long)nodes : (long long)nodes * 3;
+  const bool four = pair16 == 1;
+  const int cls = four ? (int)(blockIdx.x & 3) : ((int)blockIdx.x < ctas_cls0 ? 0 : 1);
+  const int cta = four ? (int)(blockIdx.x >> 2) : (cls == 0 ? blockIdx.x : blockIdx.x - ctas_cls0);
+  const int cta_stride = four ? (int)(gridDim.x >> 2) : (cls == 0 ? ctas_cls0 : gridDim.x - ctas_cls0);
+  const long long rows = (four || cls == 0) ? (long long)nodes : (long long)nodes * 3;
   const long long tiles = (rows + 127) / 128;
   const __nv_bfloat16* __restrict__ wt = cls == 0 ? wt_s : wt_v;
   const int nchunks = n_out / nc;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int q = 0; q < 8; ++q) v[i][q] = 0.f;
           const long long gr = tile * 128 + rr[i];
           if (b0 + i < per_thread && gr < rows) {
-            const long long pl = pair16 ? plane_of4(cls, gr) : plane_of(cls, gr);
+            const long long pl = four ? plane_of4(cls, gr) : plane_of(cls, gr);
             const int k = kk[i];
             const float* src = k < n_in ? x0 + pl * n_in + k : x1 + pl * n_in + (k - n_in);
             asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (long long tile = cta; tile < tiles; tile += cta_stride) {
       // plane index of this lane's own row, then of the 4 rows of its quad (row base + m), -1 past the end
       const long long gr = tile * 128 + quad * 32 + lane;
-      const long long pl_own = gr < rows ? (pair16 ? plane_of4(cls, gr) : plane_of(cls, gr)) : -1;
+      const long long pl_own = gr < rows ? (four ? plane_of4(cls, gr) : plane_of(cls, gr)) : -1;
       long long plm[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) plm[m] = __shfl_sync(0xffffffffu, pl_own, (lane & ~3) + m);
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               u[4 * q4 + 3] = __float_as_uint(__uint_as_float(u[4 * q4 + 3]) + bv.w);
             }
           }
-          if (pair16) {
+          if (pair16 == 1) {
             // fp16 output, nodes interleaved in pairs: y[node / 2][plane][col][node & 1] (the layout the packed-half
             // edge kernel reads).  Lanes 2g, 2g+1 hold the two nodes of a pair (rows of a class are consecutive nodes,
             // tiles start at even rows): the even lane packs columns [0, 16) of both, the odd lane columns [16, 32),
@@ -345,6 +346,23 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           // u[8 m + i]: columns col0 + 8 q + i of row (quad base + m): lanes 4g..4g+3 write one 128-byte line
           const int col = col0 + 8 * q;
+          if (pair16 == 2) {  // plain fp16 rows [plane][n_out] (outputs that only feed an attribute-combine pass)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              if (plm[m] >= 0) {
+                uint32_t h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  asm("cvt.rn.f16x2.f32 %0, %1, %2;"
+                      : "=r"(h[i])
+                      : "f"(__uint_as_float(u[8 * m + 2 * i + 1])), "f"(__uint_as_float(u[8 * m + 2 * i])));
+                __half* dst = reinterpret_cast<__half*>(y0) + plm[m] * n_out + col;
+                asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
+                             : "memory");
+              }
+            }
+            continue;
+          }
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             if (plm[m] >= 0) {
@@ -439,7 +457,8 @@ static int node_gemm_tc_launch(const float* x0, const float* x1, int nodes, int 
   long long c1 = sms - c0;
   if (c1 > tiles1) c1 = tiles1;
   unsigned grid = (unsigned)(c0 + c1);
-  if (pair16) {  // four row classes of `nodes` rows each, CTAs dealt round-robin
+  if (pair16 == 2) SEGNN_CHECK_ARG(y1 == nullptr, "fp16 row output has no split");
+  if (pair16 == 1) {  // four row classes of `nodes` rows each, CTAs dealt round-robin
     SEGNN_CHECK_ARG(nodes % 2 == 0, "pair-interleaved output needs an even node count (even graph size)");
     long long per_cls = sms / 4 > 0 ? sms / 4 : 1;
     if (per_cls > tiles0) per_cls = tiles0;
@@ -458,6 +477,12 @@ int segnn_node_gemm_tc(const float* x0, const float* x1, int nodes, int n_in, co
                        const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, int operand,
                        segnn_stream_t stream) {
   return node_gemm_tc_launch(x0, x1, nodes, n_in, wt_s, wt_v, bias, n_bias, n_out, y0, y1, split, operand, 0, stream);
+}
+
+int segnn_node_gemm_tc_out16(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                             int n_out, void* y, int operand, segnn_stream_t stream) {
+  return node_gemm_tc_launch(x0, x1, nodes, n_in, wt_s, wt_v, nullptr, 0, n_out, (float*)y, nullptr, n_out, operand, 2,
+                             stream);
 }
 
 int segnn_node_gemm_tc_pair16(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,

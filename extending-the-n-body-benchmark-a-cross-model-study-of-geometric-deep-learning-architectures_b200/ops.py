@@ -10,7 +10,7 @@ import torch
 from ._lib import (MODE_BF16_TC, MODE_FP16_PACKED, MODE_FP16_TC, MODE_FP32, OPERAND_BF16, OPERAND_FP16, check,
                    lib)
 
-__all__ = ["edge_index", "edge_attr", "prep", "embed", "node_gemm", "pack_node_weight_tc", "tp_combine", "edge_layer", "head",
+__all__ = ["edge_index", "edge_attr", "prep", "embed", "node_gemm", "node_gemm_out16", "node_gemm_pair16", "pack_node_weight_tc", "tp_combine", "edge_layer", "head",
            "integrate", "counter_add", "launch_count", "MODE_FP32", "MODE_BF16_TC", "MODE_FP16_TC", "MODE_FP16_PACKED"]
 
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -110,6 +110,18 @@ def node_gemm(x0, x1, w, n_out: int, bias=None, n_bias: int = 0, split: int = 0,
     return (y0, y1) if split else y0
 
 
+def node_gemm_out16(x0, x1, w, n_out: int):
+    """Tensor-core node GEMM with plain fp16 rows [nodes, 4, n_out] (segnn_node_gemm_tc_out16): for outputs that only
+    feed tp_combine, which reads them through segnn_tp_combine_y16."""
+    nodes, _, n_in = x0.shape
+    y = torch.empty((nodes, 4, n_out), dtype=torch.float16, device=x0.device)
+    with torch.cuda.device(x0.device):
+        check(lib.segnn_node_gemm_tc_out16(_p(x0), _p(x1), nodes, n_in, _p(w["wt_s"]), _p(w["wt_v"]), n_out, _p(y),
+                                           int(w.get("operand", OPERAND_BF16)), _stream()), "segnn_node_gemm_tc_out16")
+    _bump()
+    return y
+
+
 def node_gemm_pair16(x0, w, n_out: int, bias, n_bias: int, split: int):
     """Tensor-core node GEMM with fp16 output, nodes interleaved in pairs (segnn_node_gemm_tc_pair16): returns
     (y0 [nodes/2, 4, split, 2], y1 [nodes/2, 4, n_out - split, 2]) float16."""
@@ -142,9 +154,10 @@ def tp_combine(y, node_attr, n: int, gate: bool, bias=None, residual=None, bn_mu
                out: Optional[torch.Tensor] = None):
     nodes = y.shape[0]
     o = out if out is not None else torch.empty((nodes, 4, n), dtype=torch.float32, device=y.device)
+    fn = lib.segnn_tp_combine_y16 if y.dtype == torch.float16 else lib.segnn_tp_combine
     with torch.cuda.device(y.device):
-        check(lib.segnn_tp_combine(_p(y), _p(node_attr), nodes, n, int(gate), _p(bias), _p(residual), _p(bn_mul),
-                                   _p(bn_add), _p(o), _stream()), "segnn_tp_combine")
+        check(fn(_p(y), _p(node_attr), nodes, n, int(gate), _p(bias), _p(residual), _p(bn_mul), _p(bn_add), _p(o),
+                 _stream()), "segnn_tp_combine")
     _bump()
     return o
 

@@ -112,10 +112,11 @@ class SEGNNLayer(nn.Module):
         agg = ops.edge_layer(mode, pos, mass, batch_size, num_nodes, n, p, q, m1["w_edge"], w["msg2"],
                              w["bn_msg"][0], w["bn_msg"][1])
         u1 = w["upd1"]
-        y1 = ops.node_gemm(h, agg, u1, 3 * n, tc=tc)
+        # tensor-core modes: the GEMM outputs that only feed an attribute-combine pass travel as fp16 rows
+        y1 = ops.node_gemm_out16(h, agg, u1, 3 * n) if tc else ops.node_gemm(h, agg, u1, 3 * n)
         g1 = ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"])
         u2 = w["upd2"]
-        y2 = ops.node_gemm(g1, None, u2, 2 * n, tc=tc)
+        y2 = ops.node_gemm_out16(g1, None, u2, 2 * n) if tc else ops.node_gemm(g1, None, u2, 2 * n)
         return ops.tp_combine(y2, node_attr, n, False, bias=u2["bias"], residual=h, bn_mul=w["bn_feat"][0],
                               bn_add=w["bn_feat"][1])
 
@@ -246,7 +247,7 @@ class SEGNN(nn.Module):
             h = layer.run(lw, mode, h, pos, mass, node_attr, batch_size, num_nodes)
             per_layer.append(h)
         p1 = w["pool1"]
-        y = ops.node_gemm(h, None, p1, 3 * n, tc=(mode in _TC_MODES))
+        y = ops.node_gemm_out16(h, None, p1, 3 * n) if mode in _TC_MODES else ops.node_gemm(h, None, p1, 3 * n)
         hp = ops.tp_combine(y, node_attr, n, True, bias=p1["bias"])
         pred = ops.head(hp, node_attr, w["head"], n)
         if return_layers:

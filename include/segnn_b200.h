@@ -111,6 +111,11 @@ int segnn_node_gemm_tc_pair16(const float* x0, const float* x1, int nodes, int n
                               const float* bias, int n_bias, int n_out, void* y0, void* y1, int split, int operand,
                               segnn_stream_t stream);
 
+/* Same GEMM with plain fp16 rows y [nodes][4][n_out] (no split, no bias): for outputs that only feed an
+ * attribute-combine pass (segnn_tp_combine_y16), which halves the bytes of both kernels. */
+int segnn_node_gemm_tc_out16(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                             int n_out, void* y, int operand, segnn_stream_t stream);
+
 /* w [K][n_out] fp32 -> wt [n_out][K] bf16 / fp16 (the B operand image of segnn_node_gemm_tc). */
 int segnn_pack_node_weight_tc(const float* w, int K, int n_out, int operand, void* wt, segnn_stream_t stream);
 
@@ -126,6 +131,11 @@ int segnn_pack_node_weight_tc(const float* w, int K, int n_out, int operand, voi
 int segnn_tp_combine(const float* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
                      const float* residual, const float* bn_mul, const float* bn_add, float* out,
                      segnn_stream_t stream);
+
+/* Same pass reading y as fp16 rows [nodes][4][n0+n] (written by segnn_node_gemm_tc_out16). */
+int segnn_tp_combine_y16(const void* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                         const float* residual, const float* bn_mul, const float* bn_add, float* out,
+                         segnn_stream_t stream);
 
 /* ---- K3: fused edge layer ---------------------------------------------------------------------------- */
 

@@ -58,20 +58,22 @@ with torch.no_grad():
         pq_fn = lambda: ops.node_gemm(h, None, m1, 6 * n, bias=pq_bias, n_bias=pq_nb, split=3 * n, tc=tc)
     pq = pq_fn()
     agg = ops.edge_layer(mode, p, m, B, N, n, pq[0], pq[1], m1["w_edge"], lw["msg2"], lw["bn_msg"][0], lw["bn_msg"][1])
-    y1 = ops.node_gemm(h, agg, u1, 3 * n, tc=tc)
+    g16 = (lambda a, b, w_, no: ops.node_gemm_out16(a, b, w_, no)) if tc else (lambda a, b, w_, no: ops.node_gemm(a, b, w_, no))
+    ob = 2 if tc else 4  # bytes per element of the node-GEMM outputs that feed the combine passes
+    y1 = g16(h, agg, u1, 3 * n)
     g1 = ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"])
-    y2 = ops.node_gemm(g1, None, u2, 2 * n, tc=tc)
+    y2 = g16(g1, None, u2, 2 * n)
     rows = nodes * 4
     cases = [
         ("node_gemm P/Q  (K=n,  out 6n)", pq_fn, rows * 4 * n + rows * 6 * n * (2 if packed else 4)),
         ("edge_layer K3", lambda: ops.edge_layer(mode, p, m, B, N, n, pq[0], pq[1], m1["w_edge"], lw["msg2"], lw["bn_msg"][0],
                                                  lw["bn_msg"][1]), rows * 6 * n * (2 if packed else 4) + rows * 4 * n),
-        ("node_gemm upd1 (K=2n, out 3n)", lambda: ops.node_gemm(h, agg, u1, 3 * n, tc=tc), rows * 4 * (2 * n + 3 * n)),
-        ("tp_combine gate", lambda: ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"]), rows * 4 * (3 * n + n)),
-        ("node_gemm upd2 (K=n,  out 2n)", lambda: ops.node_gemm(g1, None, u2, 2 * n, tc=tc), rows * 4 * (n + 2 * n)),
+        ("node_gemm upd1 (K=2n, out 3n)", lambda: g16(h, agg, u1, 3 * n), rows * (4 * 2 * n + ob * 3 * n)),
+        ("tp_combine gate", lambda: ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"]), rows * (ob * 3 * n + 4 * n)),
+        ("node_gemm upd2 (K=n,  out 2n)", lambda: g16(g1, None, u2, 2 * n), rows * (4 * n + ob * 2 * n)),
         ("tp_combine residual+BN", lambda: ops.tp_combine(y2, node_attr, n, False, bias=u2["bias"], residual=h,
                                                           bn_mul=lw["bn_feat"][0], bn_add=lw["bn_feat"][1]),
-         rows * 4 * (2 * n + n + n)),
+         rows * (ob * 2 * n + 4 * n + 4 * n)),
     ]
     total = 0.0
     for name, fn, nbytes in cases:

@@ -95,8 +95,8 @@ __device__ __forceinline__ uint32_t pack_pair(float lo, float hi, int half) {
                : "r"(taddr))
 
 constexpr int kLoadWarps = 8;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (kLoadWarps + kEpiWarps + 1) * 32;  // 8 loader + 8 epilogue + 1 MMA warps
+constexpr int kEpiWarps = 16;  // four per TMEM lane quadrant: the 32-column blocks of a chunk are dealt round-robin
+constexpr int kThreads = (kLoadWarps + kEpiWarps + 1) * 32;  // 8 loader + 16 epilogue + 1 MMA warps
 constexpr int kMmaWarp = kLoadWarps + kEpiWarps;
 
 // rows of class 0: node r -> plane (r*4); class 1: row r -> node r/3, plane 1 + r%3
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&afull[i], kLoadWarps * 32);
       mbar_init(&aempty[i], 1);
       mbar_init(&dfull[i], 1);
-      mbar_init(&dempty[i], kEpiWarps * 32);
+      mbar_init(&dempty[i], kEpiWarps);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -275,14 +275,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_after();
         bool arrived = false;
         for (int bk = 0; bk < nb; ++bk) {
-          if (((c * nb + bk) & 1) != chalf) continue;
+          if (((c * nb + bk) & (kEpiWarps / 4 - 1)) != chalf) continue;
           uint32_t u[32];  // u[8 k + i]: sector k (columns 8k .. 8k+7 of the block) of this lane's row
           SEGNN_NG_LD16(tmem + lane_base + db * 256 + bk * 32, u);
           SEGNN_NG_LD16(tmem + lane_base + db * 256 + bk * 32 + 16, (u + 16));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (bk + 2 >= nb) {  // this warp's last block of the accumulator is in registers
+          if (bk + kEpiWarps / 4 >= nb) {  // this warp's last block of the accumulator is in registers
             tc_fence_before();
-            mbar_arrive(&dempty[db]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dempty[db]);
             arrived = true;
           }
           const int col0 = c * nc + bk * 32;
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
         }
-        if (!arrived) mbar_arrive(&dempty[db]);
+        if (!arrived && lane == 0) mbar_arrive(&dempty[db]);
       }
     }
   }

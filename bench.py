@@ -367,7 +367,7 @@ def main():
                          "traffic": (K3_DRAM_BYTES_PER_LAUNCH_PACKED if mode == "fp16p" else K3_DRAM_BYTES_PER_LAUNCH)
                          if (mode in ("bf16", "fp16", "fp16p") and B == 1024) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                           "(profiles/r1_v14_ncu_full_summary.json); algorithmic P + Q + agg bytes = "
+                                           "(profiles/r1_v15_ncu_full_summary.json); algorithmic P + Q + agg bytes = "
                                            + ("6.3e8 (fp16 projections)" if mode == "fp16p" else "1.10e9"),
                          "peak_source": peak_src + ", bf16 dense sustained",
                          "flop_per_edge": FLOP_PER_EDGE_MSG2, "edges_per_launch": edges,

@@ -1,4 +1,5 @@
-// K3 (bf16 tensor-core mode): fused SEGNN edge layer on tcgen05.
+// K3 (tensor-core modes with bf16 / fp16 operands and fp32 producers; the packed-half variant is segnn_edge_tc_h2.cu):
+// fused SEGNN edge layer on tcgen05.
 //
 // Orientation: OUTPUT CHANNELS are the MMA M dimension (TMEM lanes), EDGES are the MMA N dimension (TMEM columns).
 //   D_tile[128 lanes = channel w][32 cols = edges] += A_tile[128 x K] (message_layer_2 weights, resident in TMEM,
@@ -25,9 +26,12 @@
 //     outputs as z/2 * (1 + tanh(z/2)) and (1 + tanh(z/2)), and c_silu, c_sig/2 are folded into the
 //     message_layer_2 weight image / the final per-receiver scale.
 //   The fourth SM sub-partition (warp % 4 == 3) owns no TMEM lane quadrant at n <= 96; it hosts
-//   warp 3:  MMA issuer + TMEM allocation + cp.async.bulk of the sender rows of Q (36 KB per tile at n = 96, double
-//            buffered, two tiles ahead) and of the item's 4 receiver rows of P + the tile geometry (lane = column:
-//            unit vectors, distances, mass products, validity; 4-slot ring, two tiles ahead);
+//   warp 3:  per tile, in this order: wait full[st]; cp.async.bulk of the sender rows of Q of tile t + 2 (36 KB at
+//            n = 96) into the stage the producers just released (issued after the MMAs it used to land only just in
+//            time) and, once per item, of the 4 receiver rows of P; wait dempty; the tile's 48 MMAs; then the geometry
+//            of tile t + 3 (lane = column: unit vectors, distances, mass products, validity; 8-slot ring) and the
+//            position loads of tile t + 4.  This warp's serial loop has to fit the tile period: its index arithmetic
+//            runs on per-item base pointers.
 // Projection rows P, Q [node][plane][3n] arrive as (scalar part [n] | (gate, vector) pairs [n][2]): the node GEMM
 // writes that column order (its weight image is permuted at pack time), so a thread fetches both parts of a plane
 // with one 64-bit shared-memory load.

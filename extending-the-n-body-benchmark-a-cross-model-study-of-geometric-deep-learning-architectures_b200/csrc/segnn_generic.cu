@@ -142,6 +142,61 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- "expand + GEMM" form for large row counts (per-edge tensor products) -----------------------------------------
+// For one output irrep block (mulo x dimo) the contraction is a plain GEMM once the coupling with the second operand
+// has been applied:  out[row][w][k] = sum_{(p,u)} Wcat[(p,u)][w] * A[row * dimo + k][(p,u)],
+//   A[row * dimo + k][koff_p + u] = sum_{i,j} C_p[i][j][k] x1[row][off1_p + u * dim1_p + i] x2[row][off2_p + j]
+// over the paths p that write the block.  generic_tp_expand_kernel builds A, a library SGEMM (plain GEMM, fp32) does
+// the weight contraction, generic_tp_scatter_kernel puts the result back into the e3nn column order (+ bias).
+constexpr int kPathInts = 6;  // off1, mul1, dim1, off2, dim2, koff
+
+__global__ void generic_tp_expand_kernel(const float* __restrict__ x1, int d1, const float* __restrict__ x2, int d2,
+                                         long long rows, const int* __restrict__ paths, int n_paths,
+                                         const float* __restrict__ cg, int dimo, int K, float* __restrict__ A) {
+  const long long total = rows * K;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / K;
+    const int kc = (int)(idx - row * K);
+    int p = 0;
+    while (p + 1 < n_paths && kc >= paths[(p + 1) * kPathInts + 5]) ++p;
+    const int* pa = paths + p * kPathInts;
+    const int off1 = pa[0], dim1 = pa[2], off2 = pa[3], dim2 = pa[4], u = kc - pa[5];
+    const float* C = cg + p * kCgFloats;
+    const float* xa = x1 + row * d1 + off1 + u * dim1;
+    const float* b = x2 + row * d2 + off2;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < dim1; ++i) {
+      const float xv = xa[i];
+      for (int j = 0; j < dim2; ++j) {
+        const float xb = xv * b[j];
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          if (k < dimo) acc[k] = fmaf(C[(i * 3 + j) * 5 + k], xb, acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (k < dimo) A[(row * dimo + k) * K + kc] = acc[k];
+  }
+}
+
+// out[row][offo + w * dimo + k] = Y[row * dimo + k][w] + bias[offo + w * dimo + k]
+__global__ void generic_tp_scatter_kernel(const float* __restrict__ Y, long long rows, int dimo, int mulo, int offo,
+                                          int dout, const float* __restrict__ bias, float* __restrict__ out) {
+  const int blk = mulo * dimo;
+  const long long total = rows * blk;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / blk;
+    const int c = (int)(idx - row * blk);
+    const int w = c / dimo, k = c - w * dimo;
+    float v = Y[(row * dimo + k) * mulo + w];
+    if (bias != nullptr) v += bias[offo + c];
+    out[row * dout + offo + c] = v;
+  }
+}
+
 // e3nn Gate: x = [n_s scalars | n_g gates | gated]; out = [c_silu silu(scalars) | gated * c_sig sigmoid(gate)]
 __global__ void generic_gate_kernel(const float* __restrict__ x, long long rows, int n_s, int n_g, int d_gated,
                                     const int* __restrict__ gate_index, float* __restrict__ out) {
@@ -233,6 +288,28 @@ int segnn_generic_tp(const float* x1, int d1, const float* x2, int d2, int64_t r
     generic_tp_kernel<<<generic_grid(rows * dout), 256, 0, (cudaStream_t)stream>>>(x1, d1, x2, d2, rows, weights,
                                                                                  instr, n_instr, cg, bias, dout, out);
   }
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_generic_tp_expand(const float* x1, int d1, const float* x2, int d2, int64_t rows, const int* paths,
+                            int n_paths, const float* cg, int dimo, int K, float* A, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(rows >= 0 && d1 >= 1 && d2 >= 1 && n_paths >= 1 && dimo >= 1 && dimo <= 5 && K >= 1, "bad sizes");
+  if (rows == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x1 && x2 && paths && cg && A, "null pointer");
+  generic_tp_expand_kernel<<<generic_grid(rows * K), 256, 0, (cudaStream_t)stream>>>(x1, d1, x2, d2, rows, paths,
+                                                                                   n_paths, cg, dimo, K, A);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_generic_tp_scatter(const float* Y, int64_t rows, int dimo, int mulo, int offo, int dout, const float* bias,
+                             float* out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(rows >= 0 && dimo >= 1 && mulo >= 1 && offo >= 0 && dout >= offo + mulo * dimo, "bad sizes");
+  if (rows == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(Y && out, "null pointer");
+  generic_tp_scatter_kernel<<<generic_grid(rows * mulo * dimo), 256, 0, (cudaStream_t)stream>>>(Y, rows, dimo, mulo,
+                                                                                              offo, dout, bias, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

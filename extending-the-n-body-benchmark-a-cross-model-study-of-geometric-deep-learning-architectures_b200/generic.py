@@ -2,7 +2,8 @@
 inputs, one tensor product per call, e3nn Gate, BatchNorm (eval), scatter-sum -- on plain CUDA kernels
 (csrc/segnn_generic.cu) that accept any hidden irreps with lmax_attr = 1. It gives parity coverage for configurations
 the fused kernels are not specialised for (lmax_h = 2, BASELINE config 3); per-edge tensors live in HBM here, as in the
-reference, so it is a correctness path, not the throughput path.
+reference. Per-edge tensor products run as expansion kernel + plain fp32 library GEMM + scatter kernel (the weight
+contraction is a plain GEMM once the coupling with the edge attribute is applied); node-level ones as one kernel.
 
 models/segnn/segnn.py:150-189 (SEGNN.forward), :239-304 (SEGNNLayer), o3_building_blocks.py:150-203.
 """
@@ -51,6 +52,25 @@ class TensorProductPlan:
             # net path coefficient: e3nn 'component'/'element' path weight x the reference's sqrt_k_correction
             c[:d1, :d2, :do] = math.sqrt(2 * lo + 1) * real_wigner_3j(l1, l2, lo)
             cgs.append(c)
+        # "expand + GEMM" form (large row counts): per output irrep block the paths that write it, with the column
+        # offset of each path inside the stacked weight matrix [K][mulo]
+        self.blocks = []
+        for io, (oo, mo, do) in enumerate(so):
+            paths, cg_io, wviews, koff = [], [], [], 0
+            for q, ins in enumerate(tp.instructions):
+                if ins["io"] != io:
+                    continue
+                o1, m1, d1 = s1[ins["i1"]]
+                o2, _, d2 = s2[ins["i2"]]
+                paths.append([o1, m1, d1, o2, d2, koff])
+                cg_io.append(cgs[q])
+                wviews.append((ins["offset"], m1))
+                koff += m1
+            if paths:
+                self.blocks.append(dict(
+                    paths=torch.tensor(paths, dtype=torch.int32, device=device).contiguous(),
+                    cg=torch.tensor(np.stack(cg_io), dtype=torch.float32, device=device).contiguous(),
+                    n_paths=len(paths), wviews=wviews, K=koff, offo=oo, mulo=mo, dimo=do))
         self.n_instr = len(instr)
         self.instr = torch.tensor(instr, dtype=torch.int32, device=device).contiguous()
         self.cg = torch.tensor(np.stack(cgs), dtype=torch.float32, device=device).contiguous()
@@ -68,10 +88,42 @@ class TensorProductPlan:
             bias = torch.zeros(self.dout, dtype=torch.float32, device=x1.device)
             bias[self.bias_idx] = m.biases.detach().to(torch.float32)
         out = torch.empty((rows, self.dout), dtype=torch.float32, device=x1.device)
+        if rows >= self.GEMM_MIN_ROWS:
+            return self._run_gemm(x1, x2, w, bias, out)
         with torch.cuda.device(x1.device):
             check(lib.segnn_generic_tp(_p(x1), self.d1, _p(x2), self.d2, rows, _p(w), _p(self.instr), self.n_instr,
                                        _p(self.cg), _p(bias), self.dout, _p(out), ops._stream()), "segnn_generic_tp")
         ops._bump()
+        return out
+
+    GEMM_MIN_ROWS = 2048      # per-edge tensor products; node-level ones stay on the single kernel
+    GEMM_CHUNK_BYTES = 2 << 30  # bound on the expanded operand A per chunk of rows
+
+    def _run_gemm(self, x1, x2, w, bias, out):
+        """Per output irrep block: expansion kernel (coupling with x2 applied) -> plain fp32 library GEMM against the
+        stacked path weights -> scatter kernel into the e3nn column order. Same arithmetic as segnn_generic_tp, with
+        the weight contraction at GEMM speed instead of one thread per output."""
+        rows = x1.shape[0]
+        if sum(b["mulo"] * b["dimo"] for b in self.blocks) != self.dout:
+            out.zero_()  # output columns no path writes (none for the reference's products) are bias / 0
+            if bias is not None:
+                out += bias
+        for b in self.blocks:
+            wcat = torch.cat([w[off: off + m1 * b["mulo"]].view(m1, b["mulo"]) for off, m1 in b["wviews"]], dim=0)
+            per_row = b["dimo"] * b["K"] * 4
+            chunk = max(1, min(rows, self.GEMM_CHUNK_BYTES // per_row))
+            for r0 in range(0, rows, chunk):
+                r1 = min(rows, r0 + chunk)
+                n = r1 - r0
+                A = torch.empty((n * b["dimo"], b["K"]), dtype=torch.float32, device=x1.device)
+                with torch.cuda.device(x1.device):
+                    check(lib.segnn_generic_tp_expand(_p(x1[r0:r1]), self.d1, _p(x2[r0:r1]), self.d2, n, _p(b["paths"]),
+                                                      b["n_paths"], _p(b["cg"]), b["dimo"], b["K"], _p(A),
+                                                      ops._stream()), "segnn_generic_tp_expand")
+                    Y = torch.matmul(A, wcat)  # plain library SGEMM (fp32; TF32 stays off)
+                    check(lib.segnn_generic_tp_scatter(_p(Y), n, b["dimo"], b["mulo"], b["offo"], self.dout, _p(bias),
+                                                       _p(out[r0:r1]), ops._stream()), "segnn_generic_tp_scatter")
+                ops._bump(2)
         return out
 
 

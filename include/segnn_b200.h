@@ -267,6 +267,17 @@ int segnn_generic_tp(const float* x1, int d1, const float* x2, int d2, int64_t r
                      const int* instr, int n_instr, const float* cg, const float* bias, int dout, float* out,
                      segnn_stream_t stream);
 
+/* "Expand + GEMM" form of segnn_generic_tp for large row counts, one output irrep block (mulo x dimo) at a time:
+ * segnn_generic_tp_expand writes A [rows * dimo][K] with the coupling to x2 applied
+ *   A[row * dimo + k][koff_p + u] = sum_{i,j} C_p[i][j][k] x1[row][off1_p + u * dim1_p + i] x2[row][off2_p + j]
+ * for the paths p of the block (paths [n_paths][6] = off1, mul1, dim1, off2, dim2, koff; cg [n_paths][75]); the caller
+ * multiplies A by the stacked path weights [K][mulo] with a library SGEMM; segnn_generic_tp_scatter stores
+ * Y [rows * dimo][mulo] into out[row][offo + w * dimo + k] (+ bias [dout], may be NULL). */
+int segnn_generic_tp_expand(const float* x1, int d1, const float* x2, int d2, int64_t rows, const int* paths,
+                            int n_paths, const float* cg, int dimo, int K, float* A, segnn_stream_t stream);
+int segnn_generic_tp_scatter(const float* Y, int64_t rows, int dimo, int mulo, int offo, int dout, const float* bias,
+                             float* out, segnn_stream_t stream);
+
 /* e3nn Gate as used by O3TensorProductSwishGate (:186-203): x [rows][n_scalars + n_gates + d_gated] ->
  * out [rows][n_scalars + d_gated]; gate_index [d_gated] = gate of every gated column. */
 int segnn_generic_gate(const float* x, int64_t rows, int n_scalars, int n_gates, int d_gated, const int* gate_index,

@@ -381,7 +381,8 @@ def test_rollout_macros_within_reference_statistical_tolerance(mode, N):
 
 
 # ---- generic-irreps path (lmax_h = 2, BASELINE config 3) -------------------------------------------------------------
-@pytest.mark.parametrize("H,lmax_h,L,B,N", [(32, 2, 2, 2, 6), (192, 2, 1, 1, 10), (64, 2, 3, 3, 5), (64, 1, 2, 3, 5)])
+@pytest.mark.parametrize("H,lmax_h,L,B,N", [(32, 2, 2, 2, 6), (192, 2, 1, 1, 10), (64, 2, 3, 3, 5), (64, 1, 2, 3, 5),
+                                             (32, 2, 2, 8, 17), (192, 2, 1, 1, 50)])  # the last two: expand + GEMM form
 def test_generic_irreps_path_matches_oracle(H, lmax_h, L, B, N):
     """Per-layer parity of the generic fp32 kernels (any hidden irreps; lmax_h = 2 is BASELINE config 3) at the fp32
     tolerance 1e-5; for lmax_h = 1 the same path is selected with compute_mode='generic' and must also agree with the

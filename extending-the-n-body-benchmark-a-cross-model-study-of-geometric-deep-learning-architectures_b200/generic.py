@@ -96,7 +96,7 @@ class TensorProductPlan:
         ops._bump()
         return out
 
-    GEMM_MIN_ROWS = 2048      # per-edge tensor products; node-level ones stay on the single kernel
+    GEMM_MIN_ROWS = 128       # below this the single tiled kernel is used (too few rows to fill a GEMM)
     GEMM_CHUNK_BYTES = 2 << 30  # bound on the expanded operand A per chunk of rows
 
     def _run_gemm(self, x1, x2, w, bias, out):

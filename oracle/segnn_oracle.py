@@ -12,7 +12,9 @@ for this path (/root/reference/pytest.ini:1-11 -- there is no tests/ directory).
 This file therefore *restates* the published algorithm of those packages as used
 by the reference call sites cited below, explicit-``edge_index`` / gather /
 tensor-product / scatter, in plain PyTorch (float64 by default, like the
-reference: /root/reference/config.yaml:177).
+reference: /root/reference/config.yaml:177).  Third-party anchors that ARE checked
+(tests/test_oracle.py): ``spherical_harmonics`` against SymPy's real harmonics ``Znm``
+and ``wigner_3j`` against SymPy's real Gaunt coefficients (basis order, signs, values).
 
 What is restated, with the reference call site each piece follows:
 

@@ -48,6 +48,77 @@ def test_wigner_identities():
     assert torch.allclose(O.wigner_3j(2, 1, 1), c.permute(2, 1, 0), atol=1e-12)
 
 
+# ---- third-party anchors (SymPy): the oracle cannot be pinned against e3nn itself (not installable here), but the two
+# conventions everything else hangs on -- the real spherical-harmonic basis and the coupling tensors in that basis -- can
+# be pinned against an independent implementation of the published definitions. -------------------------------------
+COUPLINGS = [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0), (1, 1, 2), (2, 0, 2), (2, 1, 1), (2, 2, 0), (2, 2, 2)]
+
+
+def test_wigner_3j_equals_sympy_real_gaunt_coefficients():
+    """Every coupling the SEGNN tensor products use (l <= 2 features, l <= 1 attributes; l1 + l2 + l3 even) equals the
+    normalised real Gaunt coefficient  int Z_{l1 m1} Z_{l2 m2} Z_{l3 m3} dOmega  of SymPy -- same basis order m = -l..l,
+    same sign, unit Frobenius norm -- for the oracle's table and for the package's own (cg.py)."""
+    sympy_wigner = pytest.importorskip("sympy.physics.wigner")
+    import numpy as np
+    import segnn_b200.cg as cg
+    for l1, l2, l3 in COUPLINGS:
+        g = np.zeros((2 * l1 + 1, 2 * l2 + 1, 2 * l3 + 1))
+        for m1 in range(-l1, l1 + 1):
+            for m2 in range(-l2, l2 + 1):
+                for m3 in range(-l3, l3 + 1):
+                    g[l1 + m1, l2 + m2, l3 + m3] = float(sympy_wigner.real_gaunt(l1, l2, l3, m1, m2, m3))
+        g /= np.linalg.norm(g)
+        assert np.abs(O.wigner_3j(l1, l2, l3).numpy() - g).max() < 1e-12, (l1, l2, l3)
+        assert np.abs(cg.real_wigner_3j(l1, l2, l3) - g).max() < 1e-12, (l1, l2, l3)
+
+
+def _sympy_real_harmonics(point):
+    """Real spherical harmonics l <= 2 of SymPy (Znm) at a unit vector given in the oracle's axis convention: e3nn's
+    l = 1 basis is (x, y, z) where the textbook one (m = -1, 0, 1) is (y, z, x), i.e. the frames differ by a cyclic
+    relabelling of the axes; SymPy's Znm carries the Condon-Shortley sign (-1)^m for m > 0 and -1 for m < 0."""
+    import sympy
+    xs, ys, zs = point[2], point[0], point[1]
+    theta, phi = math.acos(max(-1.0, min(1.0, zs))), math.atan2(ys, xs)
+    out = []
+    for l in range(3):
+        for m in range(-l, l + 1):
+            sign = 1.0 if m == 0 else ((-1.0) ** m if m > 0 else -1.0)
+            out.append(sign * float(sympy.re(sympy.N(sympy.Znm(l, m, theta, phi).expand(func=True)))))
+    return out
+
+
+def test_spherical_harmonics_equal_sympy_real_harmonics():
+    pytest.importorskip("sympy")
+    gen = torch.Generator().manual_seed(3)
+    pts = torch.randn(5, 3, generator=gen, dtype=torch.float64)
+    pts = pts / pts.norm(dim=1, keepdim=True)
+    sh = O.spherical_harmonics(2, pts, normalize=True)
+    for k in range(pts.shape[0]):
+        ref = torch.tensor(_sympy_real_harmonics([float(v) for v in pts[k]]), dtype=torch.float64)
+        assert float((sh[k] - ref).abs().max()) < 1e-12
+
+
+def test_wigner_3j_is_the_gaunt_integral_of_the_oracle_harmonics():
+    """Basis consistency without any third party: integrating the product of three oracle harmonics over the sphere
+    (Gauss-Legendre in cos(theta) x uniform in phi: exact for these polynomials) reproduces the oracle's coupling tensor
+    up to its normalisation, so the harmonics (edge / node attributes) and the couplings live in the same basis."""
+    import numpy as np
+    nodes, weights = np.polynomial.legendre.leggauss(8)
+    phis = (np.arange(16) + 0.5) * (2 * math.pi / 16)
+    ct, ph = np.meshgrid(nodes, phis, indexing="ij")
+    st = np.sqrt(1 - ct ** 2)
+    # the oracle's axes: z_e = std y, ... any right-handed frame works for the integral; use x = st cos, y = st sin, z = ct
+    vec = torch.tensor(np.stack([st * np.cos(ph), st * np.sin(ph), ct], axis=-1).reshape(-1, 3))
+    wq = torch.tensor((weights[:, None] * np.ones_like(ph) * (2 * math.pi / 16)).reshape(-1))
+    sh = O.spherical_harmonics(2, vec, normalize=True)
+    off = {0: 0, 1: 1, 2: 4}
+    for l1, l2, l3 in COUPLINGS:
+        a, b, c = (sh[:, off[l]: off[l] + 2 * l + 1] for l in (l1, l2, l3))
+        g = torch.einsum("p,pi,pj,pk->ijk", wq, a, b, c)
+        g = g / g.norm()
+        assert float((g - O.wigner_3j(l1, l2, l3)).abs().max()) < 1e-12, (l1, l2, l3)
+
+
 def test_tensor_product_closed_forms():
     # net coefficient of every path is sqrt(2 lo + 1) * C: identities and dot/sqrt(3) (SURVEY appendix B)
     torch.manual_seed(0)

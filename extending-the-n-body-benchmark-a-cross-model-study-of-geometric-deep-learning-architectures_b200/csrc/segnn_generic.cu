@@ -197,6 +197,67 @@ __global__ void generic_tp_scatter_kernel(const float* __restrict__ Y, long long
   }
 }
 
+// ---- message_layer_1 hoisted to node level (any irreps) ---------------------------------------------------------------
+// The tensor product is linear in its first operand cat(x_i, x_j, add), so the weight contraction of the x_i / x_j
+// parts is done per NODE (Y = segnn_generic_tp with an identity coupling: Y[node][yoff + w * dim1 + i] =
+// sum_u W[u][w] x[node][u, i]) and per edge only the coupling with the edge attribute remains:
+//   out[e][offo + w * dimo + k] = bias + sum_pairs sum_{i,j} C[i][j][k] (Yi[b][yi + w dim1 + i] + Yj[a][yj + w dim1 + i]) attr[e][off2 + j]
+//                                + sum_add sum_u W[u][w] add[e][u] sum_j C[0][j][k] attr[e][off2 + j]
+// for edge e = (source a -> target b) in the reference order.  ~15 fused multiply-adds per output instead of ~350.
+constexpr int kPairInts = 8;  // offo, mulo, dimo, dim1, off2, dim2, yoff_i, yoff_j  (coupling cg[pair])
+constexpr int kAddInts = 7;   // offo, mulo, dimo, off2, dim2, woff, mul1              (coupling cg[n_pairs + index])
+
+__global__ void generic_hoisted_msg1_kernel(const float* __restrict__ Y, int ydim, const float* __restrict__ attr,
+                                            int d2, const float* __restrict__ add, int d_add, int B, int N,
+                                            const int* __restrict__ pairs, int n_pairs, const int* __restrict__ adds,
+                                            int n_adds, const float* __restrict__ cg, const float* __restrict__ weights,
+                                            const float* __restrict__ bias, int dout, float* __restrict__ out) {
+  const long long E = (long long)B * N * (N - 1);
+  const long long total = E * dout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx / dout;
+    const int c = (int)(idx - e * dout);
+    const long long g = e / ((long long)N * (N - 1));
+    const int le = (int)(e - g * N * (N - 1));
+    const int a = le / (N - 1), bb = le - a * (N - 1);
+    const int b = bb < a ? bb : bb + 1;
+    const float* yi = Y + (g * N + b) * ydim;  // receiver (x_i) side
+    const float* yj = Y + (g * N + a) * ydim;  // sender (x_j) side
+    const float* at = attr + e * d2;
+    float acc = bias != nullptr ? bias[c] : 0.f;
+    for (int q = 0; q < n_pairs; ++q) {
+      const int* in = pairs + q * kPairInts;
+      const int offo = in[0], mulo = in[1], dimo = in[2];
+      if (c < offo || c >= offo + mulo * dimo) continue;
+      const int w = (c - offo) / dimo, k = (c - offo) - w * dimo;
+      const int dim1 = in[3], off2 = in[4], dim2 = in[5];
+      const float* C = cg + q * kCgFloats;
+      const float* pi = yi + in[6] + w * dim1;
+      const float* pj = yj + in[7] + w * dim1;
+      for (int i = 0; i < dim1; ++i) {
+        float m = 0.f;
+        for (int j = 0; j < dim2; ++j) m = fmaf(C[(i * 3 + j) * 5 + k], at[off2 + j], m);
+        acc = fmaf(m, pi[i] + pj[i], acc);
+      }
+    }
+    for (int q = 0; q < n_adds; ++q) {
+      const int* in = adds + q * kAddInts;
+      const int offo = in[0], mulo = in[1], dimo = in[2];
+      if (c < offo || c >= offo + mulo * dimo) continue;
+      const int w = (c - offo) / dimo, k = (c - offo) - w * dimo;
+      const int off2 = in[3], dim2 = in[4], woff = in[5], mul1 = in[6];
+      const float* C = cg + (n_pairs + q) * kCgFloats;
+      float m = 0.f;
+      for (int j = 0; j < dim2; ++j) m = fmaf(C[j * 5 + k], at[off2 + j], m);
+      float t = 0.f;
+      for (int u = 0; u < mul1; ++u) t = fmaf(weights[woff + (long long)u * mulo + w], add[e * d_add + u], t);
+      acc = fmaf(m, t, acc);
+    }
+    out[idx] = acc;
+  }
+}
+
 // e3nn Gate: x = [n_s scalars | n_g gates | gated]; out = [c_silu silu(scalars) | gated * c_sig sigmoid(gate)]
 __global__ void generic_gate_kernel(const float* __restrict__ x, long long rows, int n_s, int n_g, int d_gated,
                                     const int* __restrict__ gate_index, float* __restrict__ out) {
@@ -310,6 +371,19 @@ int segnn_generic_tp_scatter(const float* Y, int64_t rows, int dimo, int mulo, i
   SEGNN_CHECK_ARG(Y && out, "null pointer");
   generic_tp_scatter_kernel<<<generic_grid(rows * mulo * dimo), 256, 0, (cudaStream_t)stream>>>(Y, rows, dimo, mulo,
                                                                                               offo, dout, bias, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_generic_hoisted_msg1(const float* Y, int ydim, const float* attr, int d2, const float* add, int d_add, int B,
+                               int N, const int* pairs, int n_pairs, const int* adds, int n_adds, const float* cg,
+                               const float* weights, const float* bias, int dout, float* out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(B >= 0 && N >= 2 && ydim >= 1 && d2 >= 1 && dout >= 1 && n_pairs >= 0 && n_adds >= 0, "bad sizes");
+  if (B == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(Y && attr && cg && out && (n_pairs == 0 || pairs) && (n_adds == 0 || (adds && add && weights)),
+                  "null pointer");
+  generic_hoisted_msg1_kernel<<<generic_grid((long long)B * N * (N - 1) * dout), 256, 0, (cudaStream_t)stream>>>(
+      Y, ydim, attr, d2, add, d_add, B, N, pairs, n_pairs, adds, n_adds, cg, weights, bias, dout, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

@@ -278,6 +278,16 @@ int segnn_generic_tp_expand(const float* x1, int d1, const float* x2, int d2, in
 int segnn_generic_tp_scatter(const float* Y, int64_t rows, int dimo, int mulo, int offo, int dout, const float* bias,
                              float* out, segnn_stream_t stream);
 
+/* message_layer_1 (models/segnn/segnn.py:264-279) with its weight contraction hoisted to node level, for any hidden
+ * irreps: Y [nodes][ydim] holds, for every (x_i or x_j) instruction, sum_u W[u][w] x[node][u, i] at yoff + w * dim1 + i
+ * (computed with segnn_generic_tp and an identity coupling); this kernel applies the coupling with the edge attribute
+ * per edge of the reference enumeration, adds the `additional_message_features` instructions (weights = the flat
+ * tp.weight) and the bias.  pairs [n_pairs][8] = offo, mulo, dimo, dim1, off2, dim2, yoff_i, yoff_j; adds [n_adds][7] =
+ * offo, mulo, dimo, off2, dim2, woff, mul1; cg [n_pairs + n_adds][75]. */
+int segnn_generic_hoisted_msg1(const float* Y, int ydim, const float* attr, int d2, const float* add, int d_add, int B,
+                               int N, const int* pairs, int n_pairs, const int* adds, int n_adds, const float* cg,
+                               const float* weights, const float* bias, int dout, float* out, segnn_stream_t stream);
+
 /* e3nn Gate as used by O3TensorProductSwishGate (:186-203): x [rows][n_scalars + n_gates + d_gated] ->
  * out [rows][n_scalars + d_gated]; gate_index [d_gated] = gate of every gated column. */
 int segnn_generic_gate(const float* x, int64_t rows, int n_scalars, int n_gates, int d_gated, const int* gate_index,

@@ -58,8 +58,8 @@ PROTOTYPES = {
     "segnn_generic_tp": (_int, [_ptr, _int, _ptr, _int, _c.c_int64, _ptr, _ptr, _int, _ptr, _ptr, _int, _ptr, _ptr]),
     "segnn_generic_tp_expand": (_int, [_ptr, _int, _ptr, _int, _c.c_int64, _ptr, _int, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_generic_tp_scatter": (_int, [_ptr, _c.c_int64, _int, _int, _int, _int, _ptr, _ptr, _ptr]),
-    "segnn_generic_hoisted_msg1": (_int, [_ptr, _int, _ptr, _int, _ptr, _int, _int, _int, _ptr, _int, _ptr, _int, _ptr, _ptr,
-                                          _ptr, _int, _ptr, _ptr]),
+    "segnn_generic_hoisted_msg1": (_int, [_ptr, _int, _ptr, _int, _ptr, _int, _int, _int, _ptr, _int, _ptr, _int, _ptr, _int,
+                                          _int, _ptr, _ptr, _ptr, _int, _ptr, _ptr]),
     "segnn_generic_gate": (_int, [_ptr, _c.c_int64, _int, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_generic_message_input": (_int, [_ptr, _ptr, _int, _int, _int, _int, _ptr, _ptr]),
     "segnn_generic_aggregate": (_int, [_ptr, _int, _int, _int, _ptr, _ptr]),

@@ -207,17 +207,23 @@ __global__ void generic_tp_scatter_kernel(const float* __restrict__ Y, long long
 constexpr int kPairInts = 8;  // offo, mulo, dimo, dim1, off2, dim2, yoff_i, yoff_j  (coupling cg[pair])
 constexpr int kAddInts = 7;   // offo, mulo, dimo, off2, dim2, woff, mul1              (coupling cg[n_pairs + index])
 
-__global__ void generic_hoisted_msg1_kernel(const float* __restrict__ Y, int ydim, const float* __restrict__ attr,
-                                            int d2, const float* __restrict__ add, int d_add, int B, int N,
-                                            const int* __restrict__ pairs, int n_pairs, const int* __restrict__ adds,
-                                            int n_adds, const float* __restrict__ cg, const float* __restrict__ weights,
-                                            const float* __restrict__ bias, int dout, float* __restrict__ out) {
+// One block per edge: the coupling of every pair with the edge attribute (M[q][i][k] = sum_j C[i][j][k] attr[j]) is
+// computed once per edge into shared memory; every thread then owns (output block, channel w) items and produces all
+// dimo components of them (one thread per output redid the coupling and walked the whole pair table for each).
+constexpr int kMaxPairs = 12, kMaxAdds = 4;
+
+__global__ void __launch_bounds__(128)
+    generic_hoisted_msg1_kernel(const float* __restrict__ Y, int ydim, const float* __restrict__ attr, int d2,
+                                const float* __restrict__ add, int d_add, int B, int N, const int* __restrict__ pairs,
+                                int n_pairs, const int* __restrict__ adds, int n_adds, const int* __restrict__ blocks,
+                                int n_blocks, int n_items, const float* __restrict__ cg,
+                                const float* __restrict__ weights, const float* __restrict__ bias, int dout,
+                                float* __restrict__ out) {
+  __shared__ float M[kMaxPairs][25];
+  __shared__ float Ma[kMaxAdds][5];
+  __shared__ float av[8];
   const long long E = (long long)B * N * (N - 1);
-  const long long total = E * dout;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long e = idx / dout;
-    const int c = (int)(idx - e * dout);
+  for (long long e = blockIdx.x; e < E; e += gridDim.x) {
     const long long g = e / ((long long)N * (N - 1));
     const int le = (int)(e - g * N * (N - 1));
     const int a = le / (N - 1), bb = le - a * (N - 1);
@@ -225,36 +231,60 @@ __global__ void generic_hoisted_msg1_kernel(const float* __restrict__ Y, int ydi
     const float* yi = Y + (g * N + b) * ydim;  // receiver (x_i) side
     const float* yj = Y + (g * N + a) * ydim;  // sender (x_j) side
     const float* at = attr + e * d2;
-    float acc = bias != nullptr ? bias[c] : 0.f;
-    for (int q = 0; q < n_pairs; ++q) {
+    __syncthreads();  // previous edge fully consumed
+    for (int t = threadIdx.x; t < n_pairs * 25; t += blockDim.x) {
+      const int q = t / 25, i = (t - q * 25) / 5, k = t % 5;
       const int* in = pairs + q * kPairInts;
-      const int offo = in[0], mulo = in[1], dimo = in[2];
-      if (c < offo || c >= offo + mulo * dimo) continue;
-      const int w = (c - offo) / dimo, k = (c - offo) - w * dimo;
-      const int dim1 = in[3], off2 = in[4], dim2 = in[5];
-      const float* C = cg + q * kCgFloats;
-      const float* pi = yi + in[6] + w * dim1;
-      const float* pj = yj + in[7] + w * dim1;
-      for (int i = 0; i < dim1; ++i) {
-        float m = 0.f;
-        for (int j = 0; j < dim2; ++j) m = fmaf(C[(i * 3 + j) * 5 + k], at[off2 + j], m);
-        acc = fmaf(m, pi[i] + pj[i], acc);
-      }
-    }
-    for (int q = 0; q < n_adds; ++q) {
-      const int* in = adds + q * kAddInts;
-      const int offo = in[0], mulo = in[1], dimo = in[2];
-      if (c < offo || c >= offo + mulo * dimo) continue;
-      const int w = (c - offo) / dimo, k = (c - offo) - w * dimo;
-      const int off2 = in[3], dim2 = in[4], woff = in[5], mul1 = in[6];
-      const float* C = cg + (n_pairs + q) * kCgFloats;
       float m = 0.f;
-      for (int j = 0; j < dim2; ++j) m = fmaf(C[j * 5 + k], at[off2 + j], m);
-      float t = 0.f;
-      for (int u = 0; u < mul1; ++u) t = fmaf(weights[woff + (long long)u * mulo + w], add[e * d_add + u], t);
-      acc = fmaf(m, t, acc);
+      if (i < in[3] && k < in[2])
+        for (int j = 0; j < in[5]; ++j) m = fmaf(cg[q * kCgFloats + (i * 3 + j) * 5 + k], at[in[4] + j], m);
+      M[q][i * 5 + k] = m;
     }
-    out[idx] = acc;
+    for (int t = threadIdx.x; t < n_adds * 5; t += blockDim.x) {
+      const int q = t / 5, k = t % 5;
+      const int* in = adds + q * kAddInts;
+      float m = 0.f;
+      if (k < in[2])
+        for (int j = 0; j < in[4]; ++j) m = fmaf(cg[(n_pairs + q) * kCgFloats + j * 5 + k], at[in[3] + j], m);
+      Ma[q][k] = m;
+    }
+    if (threadIdx.x < d_add && threadIdx.x < 8) av[threadIdx.x] = add[e * d_add + threadIdx.x];
+    __syncthreads();
+    for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
+      int blk = 0, w = item;
+      while (w >= blocks[blk * 3 + 1]) {
+        w -= blocks[blk * 3 + 1];
+        ++blk;
+      }
+      const int offo = blocks[blk * 3], mulo = blocks[blk * 3 + 1], dimo = blocks[blk * 3 + 2];
+      float acc[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc[k] = (bias != nullptr && k < dimo) ? bias[offo + w * dimo + k] : 0.f;
+      for (int q = 0; q < n_pairs; ++q) {
+        const int* in = pairs + q * kPairInts;
+        if (in[0] != offo) continue;
+        const int dim1 = in[3];
+        const float* pi = yi + in[6] + w * dim1;
+        const float* pj = yj + in[7] + w * dim1;
+        for (int i = 0; i < dim1; ++i) {
+          const float sv = pi[i] + pj[i];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) acc[k] = fmaf(M[q][i * 5 + k], sv, acc[k]);
+        }
+      }
+      for (int q = 0; q < n_adds; ++q) {
+        const int* in = adds + q * kAddInts;
+        if (in[0] != offo) continue;
+        float t = 0.f;
+        for (int u = 0; u < in[6]; ++u) t = fmaf(weights[in[5] + (long long)u * mulo + w], av[u], t);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc[k] = fmaf(Ma[q][k], t, acc[k]);
+      }
+      float* o = out + e * dout + offo + w * dimo;
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        if (k < dimo) o[k] = acc[k];
+    }
   }
 }
 
@@ -376,14 +406,21 @@ int segnn_generic_tp_scatter(const float* Y, int64_t rows, int dimo, int mulo, i
 }
 
 int segnn_generic_hoisted_msg1(const float* Y, int ydim, const float* attr, int d2, const float* add, int d_add, int B,
-                               int N, const int* pairs, int n_pairs, const int* adds, int n_adds, const float* cg,
-                               const float* weights, const float* bias, int dout, float* out, segnn_stream_t stream) {
+                               int N, const int* pairs, int n_pairs, const int* adds, int n_adds, const int* blocks,
+                               int n_blocks, int n_items, const float* cg, const float* weights, const float* bias,
+                               int dout, float* out, segnn_stream_t stream) {
   SEGNN_CHECK_ARG(B >= 0 && N >= 2 && ydim >= 1 && d2 >= 1 && dout >= 1 && n_pairs >= 0 && n_adds >= 0, "bad sizes");
+  SEGNN_CHECK_ARG(n_pairs <= kMaxPairs && n_adds <= kMaxAdds && d_add <= 8 && n_blocks >= 1 && n_items >= 1,
+                  "too many instruction pairs / additional features for the per-edge tables");
   if (B == 0) return SEGNN_OK;
-  SEGNN_CHECK_ARG(Y && attr && cg && out && (n_pairs == 0 || pairs) && (n_adds == 0 || (adds && add && weights)),
+  SEGNN_CHECK_ARG(Y && attr && cg && out && blocks && (n_pairs == 0 || pairs) &&
+                      (n_adds == 0 || (adds && add && weights)),
                   "null pointer");
-  generic_hoisted_msg1_kernel<<<generic_grid((long long)B * N * (N - 1) * dout), 256, 0, (cudaStream_t)stream>>>(
-      Y, ydim, attr, d2, add, d_add, B, N, pairs, n_pairs, adds, n_adds, cg, weights, bias, dout, out);
+  long long nblk = (long long)B * N * (N - 1);
+  if (nblk > 148LL * 256) nblk = 148LL * 256;
+  generic_hoisted_msg1_kernel<<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(
+      Y, ydim, attr, d2, add, d_add, B, N, pairs, n_pairs, adds, n_adds, blocks, n_blocks, n_items, cg, weights, bias,
+      dout, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

@@ -178,6 +178,8 @@ class HoistedMessage1Plan:
         self.pairs = t32(pairs)
         self.adds = t32(adds) if adds else None
         self.cg = torch.tensor(np.stack(cgs + cgs_add), dtype=torch.float32, device=device).contiguous()
+        self.blocks = t32([[oo, mo, do] for oo, mo, do in so])
+        self.n_blocks, self.n_items = len(so), sum(mo for _, mo, _ in so)
         self.D, self.d2, self.dout = D, tp.irreps_in2.dim, tp.irreps_out.dim
         cols = [c for (off, m, d), (_, l, _) in zip(so, tp.irreps_out) if l == 0 for c in range(off, off + m)]
         self.bias_idx = torch.tensor(cols, dtype=torch.int64, device=device) if cols else None
@@ -198,8 +200,9 @@ class HoistedMessage1Plan:
             check(lib.segnn_generic_tp(_p(x), self.D, _p(ones), 1, nodes, _p(w), _p(self.yinstr), self.n_y, _p(self.ycg),
                                        None, self.ydim, _p(Y), ops._stream()), "segnn_generic_tp")
             check(lib.segnn_generic_hoisted_msg1(_p(Y), self.ydim, _p(edge_attr), self.d2, _p(add), add.shape[1], B, N,
-                                                 _p(self.pairs), self.n_pairs, _p(self.adds), self.n_adds, _p(self.cg),
-                                                 _p(w), _p(bias), self.dout, _p(out), ops._stream()),
+                                                 _p(self.pairs), self.n_pairs, _p(self.adds), self.n_adds,
+                                                 _p(self.blocks), self.n_blocks, self.n_items, _p(self.cg), _p(w),
+                                                 _p(bias), self.dout, _p(out), ops._stream()),
                   "segnn_generic_hoisted_msg1")
         ops._bump(2)
         return out

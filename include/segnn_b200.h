@@ -283,10 +283,12 @@ int segnn_generic_tp_scatter(const float* Y, int64_t rows, int dimo, int mulo, i
  * (computed with segnn_generic_tp and an identity coupling); this kernel applies the coupling with the edge attribute
  * per edge of the reference enumeration, adds the `additional_message_features` instructions (weights = the flat
  * tp.weight) and the bias.  pairs [n_pairs][8] = offo, mulo, dimo, dim1, off2, dim2, yoff_i, yoff_j; adds [n_adds][7] =
- * offo, mulo, dimo, off2, dim2, woff, mul1; cg [n_pairs + n_adds][75]. */
+ * offo, mulo, dimo, off2, dim2, woff, mul1; blocks [n_blocks][3] = offo, mulo, dimo of every output irrep block,
+ * n_items = sum of their mulo; cg [n_pairs + n_adds][75]. */
 int segnn_generic_hoisted_msg1(const float* Y, int ydim, const float* attr, int d2, const float* add, int d_add, int B,
-                               int N, const int* pairs, int n_pairs, const int* adds, int n_adds, const float* cg,
-                               const float* weights, const float* bias, int dout, float* out, segnn_stream_t stream);
+                               int N, const int* pairs, int n_pairs, const int* adds, int n_adds, const int* blocks,
+                               int n_blocks, int n_items, const float* cg, const float* weights, const float* bias,
+                               int dout, float* out, segnn_stream_t stream);
 
 /* e3nn Gate as used by O3TensorProductSwishGate (:186-203): x [rows][n_scalars + n_gates + d_gated] ->
  * out [rows][n_scalars + d_gated]; gate_index [d_gated] = gate of every gated column. */

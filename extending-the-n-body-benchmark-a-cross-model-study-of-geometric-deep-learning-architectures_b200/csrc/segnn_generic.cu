@@ -362,10 +362,12 @@ int segnn_generic_tp(const float* x1, int d1, const float* x2, int d2, int64_t r
   SEGNN_CHECK_ARG(rows >= 0 && d1 >= 1 && d2 >= 1 && dout >= 1 && n_instr >= 1, "bad sizes");
   if (rows == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(x1 && x2 && weights && instr && cg && out, "null pointer");
-  constexpr int R = 8;
+  // rows per block: 8 when there are enough rows to fill the GPU with 8-row tiles, else 2 (node-level products on a
+  // few hundred rows would otherwise run on a third of the SMs)
+  const int R = rows >= 8LL * 2 * 148 ? 8 : 2;
   const size_t smem = (size_t)R * (d1 + d2) * sizeof(float);
   if (rows >= 4 * R && smem <= 200 * 1024) {
-    auto kern = generic_tp_tiled_kernel<R>;
+    auto kern = R == 8 ? generic_tp_tiled_kernel<8> : generic_tp_tiled_kernel<2>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) {
       set_error("segnn_generic_tp: cudaFuncSetAttribute: %s", cudaGetErrorString(err));

@@ -161,6 +161,7 @@ class SEGNN(nn.Module):
         self.task, self.norm, self.pool, self.training_args = task, norm, pool, training_args
         self.additional_message_irreps = Irreps(str(additional_message_irreps))
         self.compute_mode = compute_mode
+        self._pack_map = None  # (key, gather tables) of the parameter -> operand-block re-layout (training path)
         h = self.hidden_irreps
         self.n = h[0][0]
         self.embedding_layer = O3TensorProduct(Irreps(str(input_irreps)), h, self.node_attr_irreps)
@@ -284,12 +285,17 @@ class SEGNN(nn.Module):
 
     def _forward_train(self, pos, vel, mass, batch_size, num_nodes, bn_training, needs_grad, return_layers=False,
                        backend=None, dtype=torch.float32):
+        if needs_grad and not return_layers:
+            # parameters go in as they are: packing is one gather inside the function (training.build_pack_map)
+            params = list(self.parameters())
+            key = tuple((tuple(p.shape), p.device) for p in params)
+            if self._pack_map is None or self._pack_map[0] != key:
+                self._pack_map = (key, training.build_pack_map(self))
+            cfg = dict(pack_map=self._pack_map[1], dtype=dtype, n=self.n, B=batch_size, N=num_nodes,
+                       bn_training=bn_training, backend=backend)
+            return training.SegnnTrainFunctionFlat.apply(cfg, pos, vel, mass, *params)
         tree, bufs = self.packed_train(dtype)
         leaves, spec = training.flatten_packed(tree)
-        cfg = dict(spec=spec, bn_buffers=bufs, n=self.n, B=batch_size, N=num_nodes, bn_training=bn_training,
-                   backend=backend)
-        if needs_grad and not return_layers:
-            return training.SegnnTrainFunction.apply(cfg, pos, vel, mass, *leaves)
         with torch.no_grad():
             W = training.unflatten_packed([t.detach() for t in leaves], spec)
             training.attach_bn_buffers(W, bufs)

@@ -24,8 +24,8 @@ import torch
 
 from . import ops as _ops
 
-__all__ = ["forward_train", "backward_train", "SegnnTrainFunction", "flatten_packed", "unflatten_packed",
-           "attach_bn_buffers"]
+__all__ = ["forward_train", "backward_train", "SegnnTrainFunction", "SegnnTrainFunctionFlat", "build_pack_map",
+           "flatten_packed", "unflatten_packed", "attach_bn_buffers"]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -192,6 +192,90 @@ def attach_bn_buffers(W, bufs):
         for key in ("bn_msg", "bn_feat"):
             if lw[key] is not None:
                 lw[key].update(lb[key])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameters -> packed operand blocks as ONE gather
+# ---------------------------------------------------------------------------------------------------------------
+def build_pack_map(model):
+    """The re-layout of the reference-named parameters into the kernels' operand blocks (packing.py) is a fixed linear
+    map in which every packed element is one parameter element times a constant. Run through autograd it costs ~1500
+    tiny launches per training step (a zero-fill, a copy and an add per view in the backward): more than the arithmetic
+    of the README configuration. This derives the map once as gather tables by probing ``model.packed_train`` in
+    float64 with two parameter settings (all ones -> the constants; distinct integer ids -> the source elements), so
+    that packing is ``cat(params)[IDX] * SCALE`` and its transpose one ``index_add_``.
+    Returns dict(idx, scale, spec, shapes, sizes, param_sizes, bufs)."""
+    params = list(model.parameters())
+    sizes = [p.numel() for p in params]
+    total = sum(sizes)
+    if total >= 2 ** 24:
+        raise NotImplementedError("pack map probing needs fewer than 2^24 parameters (fp32-exact integer ids)")
+    with torch.no_grad():
+        saved = [p.detach().clone() for p in params]
+        try:
+            for p in params:
+                p.fill_(1.0)
+            ones_leaves, spec = flatten_packed(model.packed_train(torch.float64)[0])
+            ones_leaves = [t.clone() for t in ones_leaves]  # pass-through leaves alias the parameters themselves
+            off = 0
+            for p, n in zip(params, sizes):
+                p.copy_(torch.arange(off + 1, off + n + 1, device=p.device, dtype=torch.float64).reshape(p.shape))
+                off += n
+            id_leaves, _ = flatten_packed(model.packed_train(torch.float64)[0])
+            id_leaves = [t.clone() for t in id_leaves]
+        finally:
+            for p, v in zip(params, saved):
+                p.copy_(v)
+        _, bufs = model.packed_train(torch.float32)
+        scale = torch.cat([t.reshape(-1) for t in ones_leaves])
+        ids = torch.cat([t.reshape(-1) for t in id_leaves])
+        safe = torch.where(scale != 0, scale, torch.ones_like(scale))
+        idx = torch.where(scale != 0, torch.round(ids / safe) - 1, torch.zeros_like(ids)).to(torch.int64)
+        if int(idx.min()) < 0 or int(idx.max()) >= total:
+            raise AssertionError("pack map probe produced an out-of-range source index")
+        # every packed element must be exactly scale * parameter[idx]
+        if float((ids - scale * (idx + 1).to(torch.float64)).abs().max()) > 1e-6:
+            raise AssertionError("packing is not a gather with constants: pack map unusable")
+    return dict(idx=idx, scale=scale, spec=spec, shapes=[tuple(t.shape) for t in ones_leaves],
+                sizes=[t.numel() for t in ones_leaves], param_sizes=sizes, bufs=bufs)
+
+
+class SegnnTrainFunctionFlat(torch.autograd.Function):
+    """pred = SEGNN(pos, vel, mass; parameters) with the hand-written backward, taking the reference-named parameters
+    themselves: packing is one gather (build_pack_map) inside the function, its transpose one index_add_ in backward."""
+
+    @staticmethod
+    def forward(ctx, cfg, pos, vel, mass, *params):
+        pm, dtype = cfg["pack_map"], cfg["dtype"]
+        flat = torch.cat([p.detach().reshape(-1) for p in params]).to(dtype)
+        scale = pm["scale"].to(dtype)
+        packed = flat.index_select(0, pm["idx"]) * scale
+        leaves = [t.view(shape) for t, shape in zip(packed.split(pm["sizes"]), pm["shapes"])]
+        W = unflatten_packed(leaves, pm["spec"])
+        attach_bn_buffers(W, pm["bufs"])
+        pred, saved = forward_train(W, cfg["n"], pos, vel, mass, cfg["B"], cfg["N"], cfg["bn_training"],
+                                    backend=cfg.get("backend"))
+        ctx.cfg, ctx.W, ctx.saved, ctx.scale = cfg, W, saved, scale
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        ctx.param_dtypes = [p.dtype for p in params]
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        pm = ctx.cfg["pack_map"]
+        grads = backward_train(ctx.W, ctx.saved, dpred, backend=ctx.cfg.get("backend"))
+        gl, gspec = flatten_packed(_align(grads, pm["spec"]))
+        out = [None] * len(pm["sizes"])
+        _scatter_leaves(gspec, pm["spec"], gl, out)
+        dev, dt = ctx.scale.device, ctx.scale.dtype
+        pieces = [g.reshape(-1).to(dt) if g is not None else torch.zeros(n, dtype=dt, device=dev)
+                  for g, n in zip(out, pm["sizes"])]
+        gflat = torch.zeros(sum(pm["param_sizes"]), dtype=dt, device=dev)
+        gflat.index_add_(0, pm["idx"], torch.cat(pieces) * ctx.scale)
+        gparams = [g.view(shape).to(pdt) for g, shape, pdt in
+                   zip(gflat.split(pm["param_sizes"]), ctx.param_shapes, ctx.param_dtypes)]
+        ctx.saved = None
+        return (None, None, None, None, *gparams)
 
 
 class SegnnTrainFunction(torch.autograd.Function):

@@ -294,7 +294,7 @@ def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_e
     g = dict(ss=gz[: 2 * n * n].view(n, 2 * n), vs=gz[2 * n * n: 4 * n * n].view(n, 2 * n),
              sv=gz[4 * n * n: 5 * n * n].view(n, n), vv=gz[5 * n * n: 6 * n * n].view(n, n), b=gz[6 * n * n:])
     dwe_partial = torch.empty((nodes, 6 * n), **f)
-    w2t = {k: w2[k].t().contiguous() for k in ("ss", "vs", "sv", "vv")}
+    w2t = {k: (w2[k + "_t"] if k + "_t" in w2 else w2[k].t().contiguous()) for k in ("ss", "vs", "sv", "vv")}
     with torch.cuda.device(dev):
         for pas, dout in ((0, dP), (1, dQ)):
             check(lib.segnn_edge_layer_bwd(pas, _p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1),

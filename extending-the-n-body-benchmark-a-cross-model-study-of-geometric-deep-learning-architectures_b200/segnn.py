@@ -256,18 +256,29 @@ class SEGNN(nn.Module):
         return pred
 
     # -- training path: train-mode BatchNorm + hand-written backward (fp32 kernels) -----------------------------
-    def packed_train(self, dtype=torch.float32):
+    def packed_train(self, dtype=torch.float32, transposed: bool = False):
         """Differentiable re-layout of the parameters into kernel operand blocks (no caching: the parameters
-        change every optimizer step) + the BatchNorm buffers that ride along outside autograd."""
+        change every optimizer step) + the BatchNorm buffers that ride along outside autograd. ``transposed`` adds
+        the transposed weight blocks the backward kernels read (keys ``*_t``: derived leaves without gradient)."""
         n = self.n
         f = lambda t: t.to(dtype)
+
+        def with_t(d, keys):
+            if transposed:
+                for k in keys:
+                    d[k + "_t"] = d[k].t().contiguous()
+            return d
         layers, bufs = [], []
         for layer in self.layers:
             lw = dict(
-                msg1=packing.pack_msg1(f(layer.message_layer_1.tp.weight), f(layer.message_layer_1.biases), n),
-                msg2=packing.pack_msg2(f(layer.message_layer_2.tp.weight), f(layer.message_layer_2.biases), n),
-                upd1=packing.pack_node_tp(f(layer.update_layer_1.tp.weight), f(layer.update_layer_1.biases), 2, n, 2 * n),
-                upd2=packing.pack_node_tp(f(layer.update_layer_2.tp.weight), f(layer.update_layer_2.biases), 1, n, n),
+                msg1=with_t(packing.pack_msg1(f(layer.message_layer_1.tp.weight), f(layer.message_layer_1.biases), n),
+                            ("w_s", "w_v")),
+                msg2=with_t(packing.pack_msg2(f(layer.message_layer_2.tp.weight), f(layer.message_layer_2.biases), n),
+                            ("ss", "vs", "sv", "vv")),
+                upd1=with_t(packing.pack_node_tp(f(layer.update_layer_1.tp.weight), f(layer.update_layer_1.biases), 2,
+                                                 n, 2 * n), ("w_s", "w_v")),
+                upd2=with_t(packing.pack_node_tp(f(layer.update_layer_2.tp.weight), f(layer.update_layer_2.biases), 1,
+                                                 n, n), ("w_s", "w_v")),
                 bn_msg=None, bn_feat=None)
             lb = dict(bn_msg=None, bn_feat=None)
             for key, bn in (("bn_msg", layer.message_norm), ("bn_feat", layer.feature_norm)):
@@ -279,7 +290,8 @@ class SEGNN(nn.Module):
             bufs.append(lb)
         tree = dict(embed=packing.pack_embedding(f(self.embedding_layer.tp.weight), f(self.embedding_layer.biases), n),
                     layers=layers,
-                    pool1=packing.pack_node_tp(f(self.pre_pool1.tp.weight), f(self.pre_pool1.biases), 1, n, 2 * n),
+                    pool1=with_t(packing.pack_node_tp(f(self.pre_pool1.tp.weight), f(self.pre_pool1.biases), 1, n,
+                                                      2 * n), ("w_s", "w_v")),
                     head=packing.pack_head(f(self.pre_pool2.tp.weight), n))
         return tree, bufs
 

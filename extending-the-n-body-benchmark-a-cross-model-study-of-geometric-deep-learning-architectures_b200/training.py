@@ -114,6 +114,8 @@ def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: 
 # backward
 # ---------------------------------------------------------------------------------------------------------------
 def _transposed(w):
+    if "w_s_t" in w:  # gathered together with the other operand blocks (build_pack_map)
+        return dict(w_s=w["w_s_t"], w_v=w["w_v_t"])
     return dict(w_s=w["w_s"].t().contiguous(), w_v=w["w_v"].t().contiguous())
 
 
@@ -215,13 +217,13 @@ def build_pack_map(model):
         try:
             for p in params:
                 p.fill_(1.0)
-            ones_leaves, spec = flatten_packed(model.packed_train(torch.float64)[0])
+            ones_leaves, spec = flatten_packed(model.packed_train(torch.float64, transposed=True)[0])
             ones_leaves = [t.clone() for t in ones_leaves]  # pass-through leaves alias the parameters themselves
             off = 0
             for p, n in zip(params, sizes):
                 p.copy_(torch.arange(off + 1, off + n + 1, device=p.device, dtype=torch.float64).reshape(p.shape))
                 off += n
-            id_leaves, _ = flatten_packed(model.packed_train(torch.float64)[0])
+            id_leaves, _ = flatten_packed(model.packed_train(torch.float64, transposed=True)[0])
             id_leaves = [t.clone() for t in id_leaves]
         finally:
             for p, v in zip(params, saved):
@@ -236,8 +238,30 @@ def build_pack_map(model):
         # every packed element must be exactly scale * parameter[idx]
         if float((ids - scale * (idx + 1).to(torch.float64)).abs().max()) > 1e-6:
             raise AssertionError("packing is not a gather with constants: pack map unusable")
-    return dict(idx=idx, scale=scale, spec=spec, shapes=[tuple(t.shape) for t in ones_leaves],
-                sizes=[t.numel() for t in ones_leaves], param_sizes=sizes, bufs=bufs)
+    # leaves that can carry a gradient (the transposed copies "*_t" are derived: the backward kernels only read them)
+    derived = set()
+
+    def mark(node):
+        if "d" in node:
+            for k, sub in node["d"]:
+                if k.endswith("_t") and "t" in sub:
+                    derived.add(sub["t"])
+                else:
+                    mark(sub)
+        elif "l" in node:
+            for sub in node["l"]:
+                mark(sub)
+
+    mark(spec)
+    leaf_sizes = [t.numel() for t in ones_leaves]
+    offsets = [0]
+    for nleaf in leaf_sizes:
+        offsets.append(offsets[-1] + nleaf)
+    grad_leaves = [i for i in range(len(leaf_sizes)) if i not in derived]
+    sel = torch.cat([torch.arange(offsets[i], offsets[i + 1], device=idx.device) for i in grad_leaves])
+    return dict(idx=idx, scale=scale, spec=spec, shapes=[tuple(t.shape) for t in ones_leaves], sizes=leaf_sizes,
+                param_sizes=sizes, bufs=bufs, grad_leaves=grad_leaves, grad_idx=idx[sel].contiguous(),
+                grad_scale=scale[sel].contiguous())
 
 
 class SegnnTrainFunctionFlat(torch.autograd.Function):
@@ -268,10 +292,10 @@ class SegnnTrainFunctionFlat(torch.autograd.Function):
         out = [None] * len(pm["sizes"])
         _scatter_leaves(gspec, pm["spec"], gl, out)
         dev, dt = ctx.scale.device, ctx.scale.dtype
-        pieces = [g.reshape(-1).to(dt) if g is not None else torch.zeros(n, dtype=dt, device=dev)
-                  for g, n in zip(out, pm["sizes"])]
+        pieces = [out[i].reshape(-1).to(dt) if out[i] is not None
+                  else torch.zeros(pm["sizes"][i], dtype=dt, device=dev) for i in pm["grad_leaves"]]
         gflat = torch.zeros(sum(pm["param_sizes"]), dtype=dt, device=dev)
-        gflat.index_add_(0, pm["idx"], torch.cat(pieces) * ctx.scale)
+        gflat.index_add_(0, pm["grad_idx"], torch.cat(pieces) * pm["grad_scale"].to(dt))
         gparams = [g.view(shape).to(pdt) for g, shape, pdt in
                    zip(gflat.split(pm["param_sizes"]), ctx.param_shapes, ctx.param_dtypes)]
         ctx.saved = None

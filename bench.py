@@ -49,26 +49,56 @@ def perturb_batchnorm(model, seed=1):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks / throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs: through NVML (pynvml, every 5 ms)
+    when it is importable, else through nvidia-smi (one sample per ~100 ms)."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self._halt = index, [], threading.Event()
+        self.max_mhz, self.source = None, "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices: resolve through CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[index]) if index < len(ids) else index
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        mhz = int(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.samples.append([str(mhz), str(self.max_mhz)] +
+                            ["Active" if mask & bits[n] else "Not Active" for n in self.NAMES])
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) >= 6:
+                        self.samples.append(parts)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.005 if self._nvml is not None else 0.2)
 
     def finish(self):
         self._halt.set()
@@ -76,11 +106,11 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(self.NAMES)
+                   if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 def measured_peaks():

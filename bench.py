@@ -314,20 +314,20 @@ def main():
         roll.step()
     S.ops.edge_layer = timed_edge_layer
     sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = S.ops.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.start()  # samples cover the timed region only (not the wait at the barrier)
     ev0.record()
     for _ in range(args.steps):
         roll.step()
     ev1.record()
     torch.cuda.synchronize()
+    clocks = sampler.finish()
     if world > 1:
         dist.barrier()
-    clocks = sampler.finish()
     launches = S.ops.launch_count() - launches0
     S.ops.edge_layer = orig_edge_layer
     ms = ev0.elapsed_time(ev1)

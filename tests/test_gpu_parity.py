@@ -97,6 +97,38 @@ def test_packed_half_mode_refuses_odd_graph_size():
         m(gpu_graph(pos, vel, mass, 2, 5))
 
 
+@pytest.mark.parametrize("nodes,n_in,n_out", [(18, 96, 576), (500, 96, 288), (1000, 32, 192), (262, 64, 384)])
+def test_node_gemm_16bit_output_modes_match_fp32_output(nodes, n_in, n_out):
+    """segnn_node_gemm_tc_pair16 (fp16, node pairs interleaved) and segnn_node_gemm_tc_out16 (fp16 rows) against the
+    fp32-output tensor-core GEMM on the same fp16 operands: equal up to the fp16 rounding of the stored result."""
+    if not S.ops.tc_available():
+        pytest.skip("tensor-core kernels not built")
+    ops = S.ops
+    gen = torch.Generator(device="cpu").manual_seed(nodes + n_out)
+    x = torch.randn(nodes, 4, n_in, generator=gen).cuda()
+    w = dict(w_s=(torch.randn(n_in, n_out, generator=gen) / n_in ** 0.5).cuda(),
+             w_v=(torch.randn(n_in, n_out, generator=gen) / n_in ** 0.5).cuda(), operand=1)
+    w["wt_s"], w["wt_v"] = ops.pack_node_weight_tc(w["w_s"], 1), ops.pack_node_weight_tc(w["w_v"], 1)
+    split = (n_out // 64) * 32  # split and n_bias must be multiples of 32
+    bias = torch.randn(split, generator=gen).cuda()
+    ref0, ref1 = ops.node_gemm(x, None, w, n_out, bias=bias, n_bias=split, split=split, tc=True)
+    y0, y1 = ops.node_gemm_pair16(x, w, n_out, bias, split, split)
+    for y, ref in ((y0, ref0), (y1, ref1)):  # [nodes/2, 4, cols, 2] -> [nodes, 4, cols]
+        got = y.permute(0, 3, 1, 2).reshape(nodes, 4, -1).float()
+        assert float((got - ref).abs().max()) <= 1e-3 * float(ref.abs().max()) + 1e-6
+    full = ops.node_gemm(x, None, w, n_out, tc=True)
+    rows16 = ops.node_gemm_out16(x, None, w, n_out)
+    assert rows16.dtype == torch.float16 and rows16.shape == full.shape
+    assert float((rows16.float() - full).abs().max()) <= 1e-3 * float(full.abs().max()) + 1e-6
+    # the combine pass reads the fp16 rows through its own entry point
+    n = n_out // 3 if n_out % 3 == 0 else None
+    if n is not None and n % 2 == 0:
+        attr = torch.randn(nodes, 4, generator=gen).cuda()
+        a = ops.tp_combine(full, attr, n, True)
+        b = ops.tp_combine(rows16, attr, n, True)
+        assert float((a - b).abs().max()) <= 2e-3 * float(a.abs().max()) + 1e-6
+
+
 def test_double_precision_module_and_precomputed_attributes():
     """The reference default is float64 (.double() model, float64 graph): accept it, compute in fp32, return float64."""
     om, m = make_pair(64, 2, dtype=torch.float64)

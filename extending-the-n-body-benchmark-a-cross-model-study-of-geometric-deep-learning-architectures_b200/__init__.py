@@ -6,7 +6,8 @@ from . import _lib, ops, packing  # noqa: F401
 from . import macros, simulator  # noqa: F401,E402
 from .graph import GraphBatch, build_graph_with_knn  # noqa: F401
 from .irreps import Irreps, weight_balanced_irreps  # noqa: F401
-from .o3_building_blocks import BatchNorm, O3TensorProduct, O3TensorProductSwishGate, O3Transform  # noqa: F401
+from .o3_building_blocks import (BatchNorm, InstanceNorm, O3TensorProduct, O3TensorProductSwishGate,  # noqa: F401
+                                 O3Transform)  # noqa: F401
 from .segnn import SEGNN, SEGNNLayer  # noqa: F401
 
 WeightBalancedIrreps = weight_balanced_irreps

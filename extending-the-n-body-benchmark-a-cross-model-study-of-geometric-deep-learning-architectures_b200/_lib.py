@@ -40,7 +40,7 @@ PROTOTYPES = {
                                     _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "segnn_pack_w2_tc": (_c.c_int64, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_head_fwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
-    "segnn_integrate": (_int, [_ptr, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_integrate": (_int, [_ptr, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _int, _ptr]),
     "segnn_counter_add": (_int, [_ptr, _int, _ptr]),
     "segnn_colsum_workspace": (_c.c_int64, [_c.c_int64, _int]),
     "segnn_colsum": (_int, [_ptr, _ptr, _c.c_int64, _int, _int, _ptr, _ptr, _ptr]),
@@ -68,6 +68,12 @@ PROTOTYPES = {
     "segnn_macros_counters": (_int, [_ptr, _ptr, _int, _int, _int, _int, _c.c_float, _c.c_float, _c.c_float, _ptr, _ptr,
                                      _ptr]),
     "segnn_macros_energy_momentum": (_int, [_ptr, _ptr, _int, _int, _int, _c.c_float, _c.c_float, _ptr, _ptr]),
+    "segnn_sim_charged": (_int, [_ptr, _ptr, _ptr, _int, _int, _c.c_double, _c.c_double, _c.c_double, _int, _int, _ptr,
+                                 _ptr, _ptr]),
+    "segnn_macros_group_collisions_workspace": (_c.c_int64, [_int, _int, _int]),
+    "segnn_macros_group_collisions": (_int, [_ptr, _int, _int, _int, _int, _c.c_float, _ptr, _ptr, _ptr]),
+    "segnn_knn_edge_index": (_int, [_ptr, _int, _int, _int, _int, _ptr, _ptr]),
+    "segnn_instance_norm": (_int, [_ptr, _ptr, _int, _int, _ptr, _int, _ptr, _ptr, _c.c_float, _ptr, _ptr]),
 }
 
 

@@ -413,10 +413,15 @@ __global__ void head_kernel(const float* __restrict__ h, const float* __restrict
 
 __global__ void integrate_kernel(const float* __restrict__ pred, float* __restrict__ pos, float* __restrict__ vel,
                                  int nodes, float* __restrict__ traj_pos, float* __restrict__ traj_vel,
-                                 const int* __restrict__ frame) {
+                                 const int* __restrict__ frame, int max_frames) {
   const int64_t total = (int64_t)nodes * 3;
   if (frame != nullptr) {  // frame slot chosen on the device so a captured CUDA graph can be replayed
-    const int64_t off = (int64_t)(*frame) * total;
+    const int f = *frame;
+    if (max_frames > 0 && (f < 0 || f >= max_frames)) {  // never write past the trajectory buffers
+      traj_pos = nullptr;
+      traj_vel = nullptr;
+    }
+    const int64_t off = (int64_t)f * total;
     if (traj_pos) traj_pos += off;
     if (traj_vel) traj_vel += off;
   }
@@ -579,12 +584,13 @@ int segnn_counter_add(int* counter, int delta, segnn_stream_t stream) {
 }
 
 int segnn_integrate(const float* pred, float* pos, float* vel, int nodes, float* traj_pos, float* traj_vel,
-                    const int* frame, segnn_stream_t stream) {
+                    const int* frame, int max_frames, segnn_stream_t stream) {
   SEGNN_CHECK_ARG(nodes >= 0, "bad sizes");
   if (nodes == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(pred && pos && vel, "null pointer");
   integrate_kernel<<<grid_for((int64_t)nodes * 3, 256), 256, 0, (cudaStream_t)stream>>>(pred, pos, vel, nodes,
-                                                                                      traj_pos, traj_vel, frame);
+                                                                                      traj_pos, traj_vel, frame,
+                                                                                      max_frames);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

@@ -50,14 +50,15 @@ def _build_fully_connected_edge_index(batch_size, num_nodes, device):
 
 
 def build_graph_with_knn(loc, batch_size, num_nodes, device, num_neighbors):
-    """utils/build_fully_connected_graph.py:23-40. Only the fully-connected branch is on the accelerated path."""
+    """utils/build_fully_connected_graph.py:23-80 (complete graph fast path :39-40, kNN branch :42-80)."""
     num_nodes = int(num_nodes)
     num_neighbors = int(num_neighbors) if num_neighbors is not None else num_nodes - 1
     if num_neighbors >= num_nodes:
         raise ValueError("Graph cannot have more neighbors than there are nodes in simulation - 1")
     if num_neighbors != num_nodes - 1:
-        raise NotImplementedError(
-            "kNN graphs (num_neighbors < N-1) are outside the accelerated fully-connected SEGNN path")
+        # :42-80: k nearest neighbours per node.  Only the edge list is built here; the fused SEGNN kernels are
+        # specialised for the complete graph (the configured path, num_neighbors = N - 1) and refuse anything else.
+        return ops.knn_edge_index(loc, int(batch_size), num_nodes, num_neighbors, device)
     return _build_fully_connected_edge_index(batch_size, num_nodes, device)
 
 

@@ -18,7 +18,7 @@ import torch
 from ._lib import check, lib
 from . import ops
 
-__all__ = ["event_counters", "energy_momentum", "nbody_energies", "momentum_statistics", "ks_statistic", "ks_p",
+__all__ = ["group_collisions", "event_counters", "energy_momentum", "nbody_energies", "momentum_statistics", "ks_statistic", "ks_p",
            "combine_pvalues_fisher", "energy_ratio_steps"]
 
 
@@ -66,6 +66,28 @@ def event_counters(traj_pos: torch.Tensor, traj_vel: torch.Tensor, batch_size: i
     c = counts.cpu().numpy().astype(np.int64)
     return {"stickings": c[:, 0], "collisions": c[:, 1], "bodies_left": c[:, 2], "sharp_turns": c[:, 3],
             "max_com_distance": com.double().cpu().numpy()}
+
+
+def group_collisions(traj_pos: torch.Tensor, batch_size: int, num_nodes: int, time_threshold: int = 2,
+                     distance_threshold: float = 2.0) -> np.ndarray:
+    """visualization_utils.py:1455-1610 (the counting part of plot_group_collision_distribution_multiplot): per
+    simulation the number of collisions between a stuck pair and a disjoint stuck triplet -> int64 [B]."""
+    if not traj_pos.is_cuda:
+        raise RuntimeError("macros run on the device trajectory buffers: there is no CPU fallback")
+    traj_pos = traj_pos.to(torch.float32).contiguous()
+    frames = traj_pos.shape[0]
+    assert traj_pos.shape == (frames, batch_size * num_nodes, 3)
+    nbytes = int(lib.segnn_macros_group_collisions_workspace(frames, batch_size, num_nodes))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=traj_pos.device)
+    counts = torch.empty((batch_size,), dtype=torch.int32, device=traj_pos.device)
+    with torch.cuda.device(traj_pos.device):
+        check(lib.segnn_macros_group_collisions(ctypes.c_void_p(traj_pos.data_ptr()), frames, batch_size, num_nodes,
+                                                int(time_threshold), float(distance_threshold),
+                                                ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(counts.data_ptr()),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              "segnn_macros_group_collisions")
+    ops._bump(4)
+    return counts.cpu().numpy().astype(np.int64)
 
 
 def nbody_energies(traj_pos, traj_vel, batch_size: int, num_nodes: int, G: float, softening: float) -> Dict[str, np.ndarray]:

@@ -55,25 +55,48 @@ class O3TensorProduct(nn.Module):
                     biases.append(torch.empty(mul).uniform_(-k, k))
         self.biases = nn.Parameter(torch.cat(biases)) if biases else None
 
-    # -- generic module-level forward (node rows, hidden irreps): used for API parity, not by SEGNN.forward ----
-    def _node_forward(self, data_in1, data_in2, gate: bool):
+    # -- module-level forward: used for API parity, not by SEGNN.forward --------------------------------------
+    def _is_hidden_shaped(self):
         n_out = self.irreps_out[-1][0]
         n_in = self.irreps_in1[0][0]
         n_blocks = len(self.irreps_in1) // 2
         hid = [(n_in, 0, 1), (n_in, 1, -1)] * n_blocks
         n0 = self.irreps_out[0][0]
-        if list(self.irreps_in1) != hid or list(self.irreps_out) != [(n0, 0, 1), (n_out, 1, -1)] \
-                or list(self.irreps_in2) != [(1, 0, 1), (1, 1, -1)] or n_in != n_out or n_blocks > 2:
-            raise NotImplementedError(
-                f"standalone O3TensorProduct forward is built for hidden->hidden irreps only, got "
-                f"{self.irreps_in1} x {self.irreps_in2} -> {self.irreps_out}")
-        w = packing.pack_node_tp(self.tp.weight.detach().float(), self.biases.detach().float(), n_blocks, n_in, n0)
-        x = data_in1.float()
-        xs = [packing.to_planar(x[:, b * 4 * n_in:(b + 1) * 4 * n_in], n_in) for b in range(n_blocks)]
-        attr = data_in2.float().contiguous()
-        y = ops.node_gemm(xs[0], xs[1] if n_blocks == 2 else None, w, n0 + n_out)
-        out = ops.tp_combine(y, attr, n_out, gate, bias=w["bias"])
-        return packing.from_planar(out).to(data_in1.dtype)
+        ok = (len(self.irreps_out) == 2 and list(self.irreps_in1) == hid
+              and list(self.irreps_out) == [(n0, 0, 1), (n_out, 1, -1)]
+              and list(self.irreps_in2) == [(1, 0, 1), (1, 1, -1)] and n_in == n_out and 1 <= n_blocks <= 2
+              and self.biases is not None)
+        return ok, n_blocks, n_in, n0, n_out
+
+    def _node_forward(self, data_in1, data_in2, gate: bool):
+        """o3_building_blocks.py:150-167 (+ the Gate of :197-203 when ``gate``).  Hidden -> hidden products on node
+        rows run the fused node kernels (GEMM + attribute combine); every other combination of irreps (l <= 2, steering
+        attribute 1x0e or 1x0e+1x1o) runs the generic tensor-product kernels of generic.py."""
+        if not data_in1.is_cuda:
+            raise RuntimeError("O3TensorProduct (B200) needs CUDA tensors: there is no CPU fallback")
+        ok, n_blocks, n_in, n0, n_out = self._is_hidden_shaped()
+        if ok:
+            w = packing.pack_node_tp(self.tp.weight.detach().float(), self.biases.detach().float(), n_blocks, n_in, n0)
+            x = data_in1.float()
+            xs = [packing.to_planar(x[:, b * 4 * n_in:(b + 1) * 4 * n_in], n_in) for b in range(n_blocks)]
+            attr = data_in2.float().contiguous()
+            y = ops.node_gemm(xs[0], xs[1] if n_blocks == 2 else None, w, n0 + n_out)
+            out = ops.tp_combine(y, attr, n_out, gate, bias=w["bias"])
+            return packing.from_planar(out).to(data_in1.dtype)
+        from .generic import GatePlan, TensorProductPlan
+        dev = data_in1.device
+        if getattr(self, "_plan_device", None) != dev:
+            self._plan = TensorProductPlan(self, dev)
+            self._gate_plan = GatePlan(self, dev) if gate else None
+            self._plan_device = dev
+        x1 = data_in1.float().contiguous()
+        x2 = torch.ones_like(x1[:, 0:1]) if data_in2 is None else data_in2.float().contiguous()  # :151-152
+        out = self._plan.run(x1, x2)
+        if gate:
+            out = self._gate_plan.run(out)
+            if self._gate_plan.n_g == 0:  # no gated irreps: the reference applies a plain nn.SiLU (:194-195), i.e.
+                out = out * (1.0 / ops.C_SILU)  # without e3nn's normalize2mom constant the gate kernel folds in
+        return out.to(data_in1.dtype)
 
     def forward(self, data_in1, data_in2=None) -> torch.Tensor:
         return self._node_forward(data_in1, data_in2, gate=False)
@@ -131,3 +154,47 @@ class O3Transform:
         graph.x = x.to(graph.pos.dtype)
         graph.node_attr = attr.to(graph.pos.dtype)
         return graph
+
+
+class InstanceNorm(nn.Module):
+    """models/segnn/instance_norm.py:8-129: per-graph normalisation of every irrep channel (mean removed for l = 0,
+    'component' norm, mean over the graph's nodes), affine weight per irrep and bias per scalar."""
+
+    def __init__(self, irreps, eps=1e-5, affine=True, reduce="mean", normalization="component"):
+        super().__init__()
+        if reduce != "mean" or normalization != "component":
+            raise NotImplementedError("InstanceNorm is built for reduce='mean', normalization='component' (the defaults)")
+        self.irreps, self.eps, self.affine = Irreps(str(irreps)), eps, affine
+        self.reduce, self.normalization = reduce, normalization
+        num_scalar = sum(m for m, l, _ in self.irreps if l == 0)
+        if affine:
+            self.weight = nn.Parameter(torch.ones(self.irreps.num_irreps))
+            self.bias = nn.Parameter(torch.zeros(num_scalar))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+        blocks, off, iw, ib = [], 0, 0, 0
+        for m, l, _ in self.irreps:
+            d = 2 * l + 1
+            blocks.append([off, m, d, l, iw, ib])
+            off, iw = off + m * d, iw + m
+            if d == 1:
+                ib += m
+        self.register_buffer("_blocks", torch.tensor(blocks, dtype=torch.int32), persistent=False)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__} ({self.irreps}, eps={self.eps})"
+
+    def forward(self, input, batch):
+        if not input.is_cuda:
+            raise RuntimeError("InstanceNorm (B200) needs CUDA tensors: there is no CPU fallback")
+        batch = batch.to(input.device)
+        if batch.numel() > 1 and bool((batch[1:] < batch[:-1]).any()):
+            raise ValueError("InstanceNorm needs the rows sorted by graph (a PyG batch vector)")
+        graphs = int(batch.max().item()) + 1 if batch.numel() else 0
+        ptr = torch.zeros(graphs + 1, dtype=torch.int64, device=input.device)
+        ptr[1:] = torch.bincount(batch, minlength=graphs).cumsum(0)
+        w = self.weight.detach().float().contiguous() if self.affine else None
+        b = self.bias.detach().float().contiguous() if self.affine else None
+        out = ops.instance_norm(input.float().contiguous(), ptr, self._blocks.to(input.device), w, b, self.eps)
+        return out.to(input.dtype)

@@ -20,6 +20,10 @@ def launch_count() -> int:
     return _launches
 
 
+# e3nn normalize2mom constants of SiLU / sigmoid folded into the gate kernels (csrc/segnn_common.cuh)
+C_SILU, C_SIG = 1.6791767923989418, 1.8467055342154763
+
+
 def _bump(k: int = 1) -> None:
     global _launches
     _launches += k
@@ -48,6 +52,33 @@ def edge_index(batch_size: int, num_nodes: int, device) -> torch.Tensor:
         raise RuntimeError("edge_index needs a CUDA device")
     with torch.cuda.device(out.device):
         check(lib.segnn_edge_index(batch_size, num_nodes, _p(out), _stream()), "segnn_edge_index")
+    _bump()
+    return out
+
+
+def knn_edge_index(loc: torch.Tensor, batch_size: int, num_nodes: int, num_neighbors: int, device) -> torch.Tensor:
+    """utils/build_fully_connected_graph.py:42-80 on the device (float64 distances)."""
+    if loc is None:
+        raise ValueError("a kNN graph needs the node positions")
+    loc = torch.as_tensor(loc).to(device=device, dtype=torch.float64).reshape(batch_size * num_nodes, -1).contiguous()
+    if not loc.is_cuda:
+        raise RuntimeError("knn_edge_index needs a CUDA device")
+    out = torch.empty((2, batch_size * num_nodes * num_neighbors), dtype=torch.int64, device=loc.device)
+    with torch.cuda.device(loc.device):
+        check(lib.segnn_knn_edge_index(_p(loc), batch_size, num_nodes, loc.shape[1], num_neighbors, _p(out), _stream()),
+              "segnn_knn_edge_index")
+    _bump()
+    return out
+
+
+def instance_norm(x: torch.Tensor, graph_ptr: torch.Tensor, blocks: torch.Tensor, weight, bias, eps: float):
+    """models/segnn/instance_norm.py:53-129; x [rows, dim] fp32, graph_ptr int64 [graphs + 1], blocks int32 [nb, 6]."""
+    x = _f32(x, "x")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.segnn_instance_norm(_p(x), _p(graph_ptr), graph_ptr.numel() - 1, x.shape[1], _p(blocks),
+                                      blocks.shape[0], _p(weight), _p(bias), float(eps), _p(out), _stream()),
+              "segnn_instance_norm")
     _bump()
     return out
 
@@ -188,9 +219,10 @@ def head(h, node_attr, w_head, n: int):
 
 def integrate(pred, pos, vel, traj_pos=None, traj_vel=None, frame=None):
     nodes = pos.shape[0]
+    max_frames = int(traj_pos.shape[0]) if traj_pos is not None else 0
     with torch.cuda.device(pos.device):
         check(lib.segnn_integrate(_p(pred), _p(pos), _p(vel), nodes, _p(traj_pos), _p(traj_vel), _p(frame),
-                                  _stream()), "segnn_integrate")
+                                  max_frames, _stream()), "segnn_integrate")
     _bump()
 
 

@@ -29,10 +29,11 @@ class SelfFeedRollout:
     """Device-resident autoregressive rollout of a SEGNN over B independent N-body systems."""
 
     def __init__(self, model, batch_size: int, num_nodes: int, device, max_frames: int, use_cuda_graph: bool = True,
-                 target: str = "pos_dt+vel"):
+                 target: str = "pos_dt+vel", allow_train_mode: bool = False):
         if target != "pos_dt+vel":
             raise NotImplementedError("only the reference's default target 'pos_dt+vel' is built")
         self.model, self.B, self.N = model, int(batch_size), int(num_nodes)
+        self.allow_train_mode = bool(allow_train_mode)
         self.device = torch.device(device)
         self.nodes = self.B * self.N
         self.max_frames = int(max_frames)
@@ -43,9 +44,18 @@ class SelfFeedRollout:
         self.traj_pos = torch.zeros((self.max_frames, self.nodes, 3), **f32)
         self.traj_vel = torch.zeros((self.max_frames, self.nodes, 3), **f32)
         self.frame = torch.zeros((1,), dtype=torch.int32, device=self.device)  # next frame slot to write
+        self.frames_written = 0  # host mirror of the device cursor (set by reset, advanced by step)
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self.launches_per_step = None
+
+    def _check_mode(self):
+        # eval-mode BatchNorm is what makes the simulations independent (sharding) and keeps a replayed
+        # graph from mutating the running statistics; the in-training rollout of trainer.py:929-942 (train-mode
+        # statistics) is available as SelfFeedRollout(..., allow_train_mode=True)
+        if self.model.training and not self.allow_train_mode:
+            raise RuntimeError("SelfFeedRollout needs model.eval() (eval-mode BatchNorm); pass allow_train_mode=True "
+                               "for the reference's in-training rollout with batch statistics")
 
     @torch.no_grad()
     def reset(self, pos0, vel0, mass):
@@ -56,6 +66,7 @@ class SelfFeedRollout:
         self.traj_pos[0].copy_(self.pos)
         self.traj_vel[0].copy_(self.vel)
         self.frame.fill_(1)
+        self.frames_written = 1
 
     def _step_eager(self):
         pred = self.model.forward_state(self.pos, self.vel, self.mass, self.B, self.N)
@@ -65,6 +76,7 @@ class SelfFeedRollout:
     @torch.no_grad()
     def capture(self):
         """Warm up (packs weights, sets kernel attributes), then capture one step as a CUDA graph."""
+        self._check_mode()
         if getattr(self.model, "fused", True) and self.model.compute_mode != "generic":
             self.model.packed(self.N - 1)
         state = (self.pos.clone(), self.vel.clone(), self.frame.clone())
@@ -87,8 +99,13 @@ class SelfFeedRollout:
 
     @torch.no_grad()
     def step(self):
+        self._check_mode()
+        if self.frames_written >= self.max_frames:
+            raise RuntimeError(f"trajectory buffer is full ({self.max_frames} frames): call reset() or allocate a "
+                               f"larger max_frames")
         if self.launches_per_step is None:
             self.capture()
+        self.frames_written += 1
         if self._graph is not None:
             self._graph.replay()
         else:
@@ -96,11 +113,13 @@ class SelfFeedRollout:
 
     @torch.no_grad()
     def run(self, steps: int):
-        if steps + 1 > self.max_frames:
-            raise ValueError(f"trajectory buffer holds {self.max_frames} frames, need {steps + 1}")
+        """``steps`` more steps from the current cursor; returns every frame written since reset()."""
+        if self.frames_written + steps > self.max_frames:
+            raise ValueError(f"trajectory buffer holds {self.max_frames} frames, {self.frames_written} are written, "
+                             f"cannot add {steps}")
         for _ in range(steps):
             self.step()
-        return self.traj_pos[: steps + 1], self.traj_vel[: steps + 1]
+        return self.traj_pos[: self.frames_written], self.traj_vel[: self.frames_written]
 
 
 @torch.no_grad()

@@ -295,16 +295,29 @@ class SEGNN(nn.Module):
                     head=packing.pack_head(f(self.pre_pool2.tp.weight), n))
         return tree, bufs
 
+    def bn_buffers(self):
+        """The BatchNorm running statistics as they are NOW (never cached: dtype casts and load_state_dict(assign=True)
+        replace the buffer objects)."""
+        out = []
+        for layer in self.layers:
+            lb = dict(bn_msg=None, bn_feat=None)
+            for key, bn in (("bn_msg", layer.message_norm), ("bn_feat", layer.feature_norm)):
+                if bn is not None:
+                    lb[key] = dict(running_mean=bn.running_mean, running_var=bn.running_var, eps=bn.eps,
+                                   momentum=bn.momentum)
+            out.append(lb)
+        return out
+
     def _forward_train(self, pos, vel, mass, batch_size, num_nodes, bn_training, needs_grad, return_layers=False,
                        backend=None, dtype=torch.float32):
         if needs_grad and not return_layers:
             # parameters go in as they are: packing is one gather inside the function (training.build_pack_map)
             params = list(self.parameters())
-            key = tuple((tuple(p.shape), p.device) for p in params)
+            key = tuple((tuple(p.shape), p.device) for p in params)  # the map depends on shapes only
             if self._pack_map is None or self._pack_map[0] != key:
                 self._pack_map = (key, training.build_pack_map(self))
             cfg = dict(pack_map=self._pack_map[1], dtype=dtype, n=self.n, B=batch_size, N=num_nodes,
-                       bn_training=bn_training, backend=backend)
+                       bn_training=bn_training, backend=backend, bn_buffers=self.bn_buffers())
             return training.SegnnTrainFunctionFlat.apply(cfg, pos, vel, mass, *params)
         tree, bufs = self.packed_train(dtype)
         leaves, spec = training.flatten_packed(tree)
@@ -324,6 +337,11 @@ class SEGNN(nn.Module):
         dev = graph.pos.device
         if dev.type != "cuda":
             raise RuntimeError("SEGNN (B200) needs CUDA tensors: there is no CPU fallback")
+        explicit = getattr(graph, "__dict__", {}).get("edge_index")
+        if torch.is_tensor(explicit) and explicit.shape[1] != b * n_nodes * (n_nodes - 1):
+            raise NotImplementedError(
+                f"the kernels are specialised for the complete graph (num_neighbors = N - 1, the configured path): "
+                f"got an explicit edge list with {explicit.shape[1]} edges for {b} graphs of {n_nodes} nodes")
         f32 = lambda t: t.to(torch.float32).contiguous()
         pos, vel, mass = f32(graph.pos), f32(graph.vel), f32(graph.mass).reshape(-1)
         x_in = node_attr = None

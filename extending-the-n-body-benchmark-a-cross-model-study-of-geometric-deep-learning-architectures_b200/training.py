@@ -206,7 +206,7 @@ def build_pack_map(model):
     of the README configuration. This derives the map once as gather tables by probing ``model.packed_train`` in
     float64 with two parameter settings (all ones -> the constants; distinct integer ids -> the source elements), so
     that packing is ``cat(params)[IDX] * SCALE`` and its transpose one ``index_add_``.
-    Returns dict(idx, scale, spec, shapes, sizes, param_sizes, bufs)."""
+    Returns dict(idx, scale, spec, shapes, sizes, param_sizes, ...); BatchNorm buffers are NOT part of the map."""
     params = list(model.parameters())
     sizes = [p.numel() for p in params]
     total = sum(sizes)
@@ -228,7 +228,6 @@ def build_pack_map(model):
         finally:
             for p, v in zip(params, saved):
                 p.copy_(v)
-        _, bufs = model.packed_train(torch.float32)
         scale = torch.cat([t.reshape(-1) for t in ones_leaves])
         ids = torch.cat([t.reshape(-1) for t in id_leaves])
         safe = torch.where(scale != 0, scale, torch.ones_like(scale))
@@ -260,7 +259,7 @@ def build_pack_map(model):
     grad_leaves = [i for i in range(len(leaf_sizes)) if i not in derived]
     sel = torch.cat([torch.arange(offsets[i], offsets[i + 1], device=idx.device) for i in grad_leaves])
     return dict(idx=idx, scale=scale, spec=spec, shapes=[tuple(t.shape) for t in ones_leaves], sizes=leaf_sizes,
-                param_sizes=sizes, bufs=bufs, grad_leaves=grad_leaves, grad_idx=idx[sel].contiguous(),
+                param_sizes=sizes, grad_leaves=grad_leaves, grad_idx=idx[sel].contiguous(),
                 grad_scale=scale[sel].contiguous())
 
 
@@ -276,7 +275,9 @@ class SegnnTrainFunctionFlat(torch.autograd.Function):
         packed = flat.index_select(0, pm["idx"]) * scale
         leaves = [t.view(shape) for t, shape in zip(packed.split(pm["sizes"]), pm["shapes"])]
         W = unflatten_packed(leaves, pm["spec"])
-        attach_bn_buffers(W, pm["bufs"])
+        # the buffers are read from the module on every call (cfg), never from the cached map: .float()/.double()/
+        # load_state_dict(assign=True) replace the buffer objects without changing the map's key
+        attach_bn_buffers(W, cfg["bn_buffers"])
         pred, saved = forward_train(W, cfg["n"], pos, vel, mass, cfg["B"], cfg["N"], cfg["bn_training"],
                                     backend=cfg.get("backend"))
         ctx.cfg, ctx.W, ctx.saved, ctx.scale = cfg, W, saved, scale

@@ -177,9 +177,10 @@ int segnn_head_fwd(const float* h, const float* node_attr, const float* w_head, 
 /* helper_scripts/infer_self_feed.py:182-194 with target 'pos_dt+vel': pos += pred[:, :3]; vel = pred[:, 3:].
  * traj_pos / traj_vel (may be NULL): trajectory buffers [frames][nodes][3]; the new state is also written to
  * frame slot *frame (device int; NULL => slot 0), which replaces predicted_loc.append(...) (:188-189) and keeps
- * the step replayable as a CUDA graph. */
+ * the step replayable as a CUDA graph.  The trajectory write is skipped when *frame >= max_frames (a replayed graph
+ * can never write past the buffers); max_frames <= 0 disables the check. */
 int segnn_integrate(const float* pred, float* pos, float* vel, int nodes, float* traj_pos, float* traj_vel,
-                    const int* frame, segnn_stream_t stream);
+                    const int* frame, int max_frames, segnn_stream_t stream);
 
 /* *counter += delta on the device (the rollout's frame cursor; `for step in range(...)`, infer_self_feed.py:99). */
 int segnn_counter_add(int* counter, int delta, segnn_stream_t stream);
@@ -331,6 +332,36 @@ int segnn_macros_counters(const float* traj_pos, const float* traj_vel, int fram
 int segnn_sim_gravity(double* pos, double* vel, const double* mass, int B, int N, double G, double softening, double dt,
                       int steps, int sample_freq, double* traj_pos, double* traj_vel, double* traj_force,
                       segnn_stream_t stream);
+
+/* Charged-particle system with isolated bodies (datasets/nbody_offline/datagen/system.py:78-123 System.compute_F /
+ * simulate_one_step; physical_objects.py:49-57 Isolated.update): F_i = sum_j k q_i q_j (x_i - x_j) / |x_i - x_j|^3,
+ * every component clamped to +-max_force (the reference uses 0.1 / dt), then v += F dt, x += v dt, in float64.
+ * pos, vel [B*N][3] (in: initial, out: final state), charge [B*N]; traj_* [steps / sample_freq][B*N][3], frame f =
+ * state after (f + 1) * sample_freq steps. */
+int segnn_sim_charged(double* pos, double* vel, const double* charge, int B, int N, double interaction_strength,
+                      double dt, double max_force, int steps, int sample_freq, double* traj_pos, double* traj_vel,
+                      segnn_stream_t stream);
+
+/* datasets/nbody/visualization_utils.py:1455-1610, the counting part of plot_group_collision_distribution_multiplot:
+ * per simulation the number of (stuck pair interval, stuck interval of a disjoint triplet) combinations with
+ * overlapping lifetimes whose two groups touch at some step >= the start of the overlap.  traj_pos
+ * [frames][B*N][3]; workspace: segnn_macros_group_collisions_workspace(frames, B, N) bytes; out_counts [B] int32.
+ * Reference defaults: time_threshold 2, distance_threshold 2. */
+int64_t segnn_macros_group_collisions_workspace(int frames, int B, int N);
+int segnn_macros_group_collisions(const float* traj_pos, int frames, int B, int N, int time_threshold,
+                                  float distance_threshold, void* workspace, int* out_counts, segnn_stream_t stream);
+
+/* utils/build_fully_connected_graph.py:42-80, the k-nearest-neighbour branch of build_graph_with_knn: loc
+ * [B*N][dim] float64 -> edge_index int64 [2, B*N*k]; edge (g N + i) k + r: row 0 = g N + i, row 1 = g N + (r-th
+ * nearest other node of i in graph g, ascending distance). */
+int segnn_knn_edge_index(const double* loc, int B, int N, int dim, int k, int64_t* edge_index, segnn_stream_t stream);
+
+/* models/segnn/instance_norm.py:53-129 InstanceNorm.forward (reduce='mean', normalization='component'): x, out
+ * [rows][dim]; graph_ptr int64 [graphs + 1] = row range of each graph (rows sorted by graph, as in a PyG batch);
+ * blocks int32 [n_blocks][6] = (column offset, multiplicity, 2l+1, l, weight offset, bias offset) per irrep block;
+ * weight / bias may be NULL (affine=False). */
+int segnn_instance_norm(const float* x, const int64_t* graph_ptr, int graphs, int dim, const int* blocks, int n_blocks,
+                        const float* weight, const float* bias, float eps, float* out, segnn_stream_t stream);
 
 #ifdef __cplusplus
 }

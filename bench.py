@@ -121,41 +121,97 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_steps(sims, steps, warmup, dtype=torch.float32):
-    """The reference's CPU formulation (oracle port: explicit edge_index, gathers, per-path tensor products,
-    scatter-sum) on a bounded sample of the workload; returns seconds per step."""
+def reference_provider():
+    """BASELINE.md 3.1 probe: the reference's own SEGNN + rollout code when a checkout is present AND its third-party
+    imports resolve (real e3nn / torch_geometric / torch_scatter -> kind 'reference'; the stand-ins of oracle/ref_shims
+    -> still the reference's module code, reported as kind 'port' with provider 'reference+shims'); otherwise the
+    oracle restatement (kind 'port', provider 'oracle').  The GPU boxes carry no reference checkout."""
+    try:
+        from oracle import ref_loader
+        if ref_loader.available():
+            kind = ref_loader.setup()
+            return ("reference" if kind == "reference" else "port"), kind
+    except Exception as exc:  # noqa: BLE001
+        print(f"[bench] reference import failed, using the oracle port: {exc!r}", file=sys.stderr)
+    return "port", "oracle"
+
+
+def cpu_reference_steps(sims, steps, warmup, dtype=torch.float32, provider="oracle", hidden=HIDDEN, layers=LAYERS,
+                        nbody=NBODY, lmax_h=1):
+    """The reference's CPU formulation (explicit edge_index, gathers, per-path tensor products, scatter-sum) on a
+    bounded sample of the workload; returns the list of seconds per timed step."""
     from oracle import segnn_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
-    model = O.SEGNN(hidden_features=HIDDEN, num_layers=LAYERS, dtype=dtype).eval()
-    pos, vel, mass = synthetic_system(sims, NBODY, seed=0)
+    pos, vel, mass = synthetic_system(sims, nbody, seed=0)
     pos, vel, mass = pos.to(dtype), vel.to(dtype), mass.to(dtype)
+    if provider != "oracle":  # the reference's own classes (helper_scripts/infer_self_feed.py:99-194 loop body)
+        from models.segnn.segnn import SEGNN as RefSEGNN
+        from models.segnn.o3_building_blocks import O3Transform
+        from torch_geometric.data import Data
+        from utils.build_fully_connected_graph import build_graph_with_knn
+        model = RefSEGNN(hidden_features=hidden, num_layers=layers, lmax_h=lmax_h).to(dtype).eval()
+
+        def one_step(p, v):
+            g = Data(pos=p.reshape(-1, 3), vel=v.reshape(-1, 3), force=torch.zeros(sims * nbody, 3, dtype=dtype),
+                     mass=mass.reshape(-1, 1))
+            g.batch = torch.arange(sims).repeat_interleave(nbody)
+            g.edge_index = build_graph_with_knn(g.pos, sims, nbody, torch.device("cpu"), nbody - 1)
+            pred = model(O3Transform(1)(g))
+            return p + pred[:, :3].reshape(sims, nbody, 3), pred[:, 3:].reshape(sims, nbody, 3)
+    else:
+        model = O.SEGNN(hidden_features=hidden, num_layers=layers, lmax_h=lmax_h, dtype=dtype).eval()
+
+        def one_step(p, v):
+            loc, vv = O.rollout(model, p, v, mass, 1)
+            return loc[:, -1], vv[:, -1]
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            loc, v = O.rollout(model, pos, vel, mass, 1)
+            pos, vel = one_step(pos, vel)
             dt = time.perf_counter() - t0
-            pos, vel = loc[:, -1], v[:, -1]
             if i >= warmup:
                 times.append(dt)
-    return sum(times) / len(times)
+    return times
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2])
+
+
+def cpu_baseline_record(sims, repeats=3, dtype=torch.float32, **kw):
+    """1 warm-up + >= 3 timed repeats, median."""
+    kind, provider = reference_provider()
+    times = cpu_reference_steps(sims, max(3, repeats), 1, dtype=dtype, provider=provider, **kw)
+    cores = os.cpu_count() or 1
+    nbody = kw.get("nbody", NBODY)
+    return {"value": sims * nbody / median(times), "unit": "particle-steps/s", "cores": cores,
+            "threads": torch.get_num_threads(), "kind": kind, "provider": provider,
+            "dtype": "f64" if dtype == torch.float64 else "f32", "seconds_per_step": [round(t, 4) for t in times],
+            "sample": f"{sims} sims x N={nbody} x 1 rollout step; 1 warm-up + {len(times)} timed repeats, median; "
+                      f"{cores} host cores"}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     sims = args.cpu_sims
-    sec = cpu_reference_steps(sims, args.steps, args.warmup)
+    kind, provider = reference_provider()
+    times = cpu_reference_steps(sims, args.steps, max(args.warmup, 1), provider=provider)
+    sec = sum(times) / len(times)
     value = sims * NBODY / sec
     cores = os.cpu_count() or 1
-    sample = f"{sims} sims x N={NBODY} x 1 rollout step per bench step, float32, {cores} threads"
+    sample = (f"{sims} sims x N={NBODY} x 1 rollout step per bench step, float32, {cores} threads, provider {provider}; "
+              f"normalised per particle-step (the GPU arm runs {args.sims_per_gpu} sims per GPU)")
     line = {
         "impl": "reference", "metric": "SEGNN self-feed particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, sims_per_gpu=sims),
-        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "provider": provider,
+                         "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -262,6 +318,9 @@ def main():
                          "mode inside the 2e-2 budget; needs an even N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training", action="store_true", help="skip the secondary training measurements")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other precision modes / BASELINE configs")
+    ap.add_argument("--cfg3-sims", type=int, default=16, help="simulations of the lmax_h = 2 (cfg3) measurement")
+    ap.add_argument("--cfg4-cpu-seconds", type=int, default=45, help="time limit of the cfg4 CPU attempt")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -293,28 +352,32 @@ def main():
     model = model.to(dev).eval()
     start, _ = S.shard_simulations(B * world, rank, world)
     pos, vel, charge = synthetic_system(B, N, seed=1000 + start)
-    frames = args.warmup + args.steps + 2
-    roll = S.SelfFeedRollout(model, B, N, dev, max_frames=frames, use_cuda_graph=False)
+
+    def timed_rollout(mdl, steps, warmup, use_graph=True, allow_train_mode=False, batch=B, nbody=N, state=None):
+        """ms per step of `steps` self-feed steps (CUDA events around the loop, synchronised on both sides)."""
+        st = state if state is not None else (pos, vel, charge)
+        r = S.SelfFeedRollout(mdl, batch, nbody, dev, max_frames=warmup + steps + 1, use_cuda_graph=use_graph,
+                              allow_train_mode=allow_train_mode)
+        r.reset(*st)
+        r.capture()
+        for _ in range(warmup):
+            r.step()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(steps):
+            r.step()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps, r.launches_per_step
+
+    # ---- (1) the headline timed region: K replays of the captured CUDA graph of one self-feed step, state in HBM ----
+    roll = S.SelfFeedRollout(model, B, N, dev, max_frames=args.warmup + args.steps + 1, use_cuda_graph=True)
     roll.reset(pos, vel, charge)
     roll.capture()
-
-    # ---- device-resident timed region (value) with CUDA events around every fused edge launch (roofline) ----
-    k3_events = []
-    orig_edge_layer = S.ops.edge_layer
-
-    def timed_edge_layer(*a, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = orig_edge_layer(*a, **kw)
-        e1.record()
-        k3_events.append((e0, e1))
-        return out
-
     for _ in range(args.warmup):
         roll.step()
-    S.ops.edge_layer = timed_edge_layer
     sampler = ClockSampler(local_rank)
-    launches0 = S.ops.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
@@ -328,21 +391,48 @@ def main():
     clocks = sampler.finish()
     if world > 1:
         dist.barrier()
-    launches = S.ops.launch_count() - launches0
-    S.ops.edge_layer = orig_edge_layer
     ms = ev0.elapsed_time(ev1)
-    k3_ms = sum(a.elapsed_time(b) for a, b in k3_events) / max(len(k3_events), 1)
+    launches = roll.launches_per_step * args.steps  # kernels of this repo inside the replayed graphs
+    del roll
 
-    # ---- end-to-end region: host buffers in, host buffers out, every step (public API) ----------------------
+    # ---- (2) instrumented pass (NOT the timed region): the same K steps eagerly, CUDA events around every fused edge
+    #          launch on the launching stream -> average K3 launch duration for the roofline ---------------------------
+    k3_events = []
+    orig_edge_layer = S.ops.edge_layer
+
+    def timed_edge_layer(*a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_edge_layer(*a, **kw)
+        e1.record()
+        k3_events.append((e0, e1))
+        return out
+
+    roll_i = S.SelfFeedRollout(model, B, N, dev, max_frames=args.warmup + args.steps + 1, use_cuda_graph=False)
+    roll_i.reset(pos, vel, charge)
+    roll_i.capture()
+    for _ in range(args.warmup):
+        roll_i.step()
+    S.ops.edge_layer = timed_edge_layer
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        roll_i.step()
+    torch.cuda.synchronize()
+    S.ops.edge_layer = orig_edge_layer
+    k3_ms = sum(a.elapsed_time(b) for a, b in k3_events) / max(len(k3_events), 1)
+    del roll_i
+
+    # ---- (3) end-to-end region: host buffers in, host buffers out, every step (public API), args.steps steps --------
     h_pos, h_vel, h_mass = pos.clone().pin_memory(), vel.clone().pin_memory(), charge.clone().pin_memory()
     o_pos = torch.empty(B * N, 3).pin_memory()
     o_vel = torch.empty(B * N, 3).pin_memory()
-    e2e_steps = max(2, min(args.steps, 3))
+    e2e_steps = args.steps
     roll2 = S.SelfFeedRollout(model, B, N, dev, max_frames=2, use_cuda_graph=True)
     roll2.reset(h_pos, h_vel, h_mass)
     roll2.capture()
-    roll2.reset(h_pos, h_vel, h_mass)
-    roll2.step()
+    for _ in range(2):
+        roll2.reset(h_pos, h_vel, h_mass)
+        roll2.step()
     torch.cuda.synchronize()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
@@ -360,12 +450,61 @@ def main():
     g1.record()
     torch.cuda.synchronize()
     e2e_ms = g0.elapsed_time(g1)
+    del roll2
 
     t = torch.tensor([ms, e2e_ms, k3_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms, k3_ms = [float(x) for x in t.cpu()]
-    del roll, roll2
+
+    # ---- (4) secondary numbers, rank 0 of a single-GPU run only: the other precision modes, the other BASELINE
+    #          configurations, the train-mode-BatchNorm rollout of trainer.py:929-942 -------------------------------
+    modes, configs = None, None
+    if world == 1 and not args.no_secondary:
+        modes = {}
+        for md in ("fp32", "bf16", "fp16", "fp16p"):
+            if md != "fp32" and not S.ops.tc_available():
+                continue
+            model.compute_mode = md
+            m_ms, _ = timed_rollout(model, 3, 3)
+            modes[md] = {"ms_per_step": m_ms, "particle_steps_per_s": B * N / (m_ms * 1e-3)}
+        model.compute_mode = mode
+        configs = {}
+        # the reference's in-training rollout never calls model.eval(): batch-statistic BatchNorm (SURVEY note 6)
+        model.train()
+        with torch.no_grad():
+            tb_ms, _ = timed_rollout(model, 2, 1, use_graph=False, allow_train_mode=True)
+        model.eval()
+        configs["cfg5_train_mode_batchnorm_rollout"] = {
+            "config": f"{B} x N={N}, 6 layers hidden 192, train-mode (batch-statistic) BatchNorm as in "
+                      "trainer.run_self_feed; fp32 kernels + deterministic float64 statistics",
+            "ms_per_step": tb_ms, "particle_steps_per_s": B * N / (tb_ms * 1e-3)}
+        # cfg1: 4 layers hidden 64, 100 x 5 bodies, 100-step rollout (the reference's CPU-runnable case)
+        torch.manual_seed(0)
+        m1 = S.SEGNN(hidden_features=64, num_layers=4, lmax_h=1,
+                     compute_mode="bf16" if S.ops.tc_available() else "fp32")
+        perturb_batchnorm(m1)
+        m1 = m1.to(dev).eval()
+        c1_ms, c1_launches = timed_rollout(m1, 100, 5, batch=100, nbody=5, state=synthetic_system(100, 5, seed=3))
+        configs["cfg1_n5_b100_100step"] = {
+            "config": "SEGNN 4 layers hidden 64 lmax_h 1, 100 x N=5 charged systems, 100-step self-feed rollout, "
+                      "CUDA-graph replay (launch-latency bound: reported as latency, not roofline)",
+            "ms_per_step": c1_ms, "rollout_ms": 100 * c1_ms, "particle_steps_per_s": 500 / (c1_ms * 1e-3),
+            "launches_per_step": c1_launches}
+        # cfg3: lmax_h = 2 (73x0e+73x1o+73x2e), N=100: generic-irreps fp32 path
+        torch.manual_seed(0)
+        m3 = S.SEGNN(hidden_features=HIDDEN, num_layers=LAYERS, lmax_h=2)
+        perturb_batchnorm(m3)
+        m3 = m3.to(dev).eval()
+        b3 = args.cfg3_sims
+        c3_ms, c3_launches = timed_rollout(m3, 2, 1, use_graph=False, batch=b3, nbody=N,
+                                           state=synthetic_system(b3, N, seed=4))
+        configs["cfg3_lmax_h2_n100"] = {
+            "config": f"SEGNN 6 layers hidden 192 lmax_h 2 (73x0e+73x1o+73x2e), {b3} x N=100, self-feed step "
+                      "(generic-irreps fp32 kernels; per particle-step, the 1000-step rollout is this step repeated)",
+            "ms_per_step": c3_ms, "particle_steps_per_s": b3 * N / (c3_ms * 1e-3), "launches_per_step": c3_launches}
+        del m1, m3
+        torch.cuda.empty_cache()
     training = None
     if not args.no_training:
         training = measure_training(S, dev, world, rank, dist if world > 1 else None,
@@ -384,6 +523,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "fp16": "f16", "fp16p": "f16"}.get(mode, "f32"), "data": "synthetic",
             "config": workload_config(args, B),
+            "timed_region": "K replays of the CUDA graph of one self-feed step (state and trajectory in HBM)",
             "edge_msgs_per_s": world * edges * LAYERS * args.steps / (ms * 1e-3),
             "fused_edge_kernel_edge_msgs_per_s": world * edges / (k3_ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": B * N * 7 * 4,
@@ -402,24 +542,71 @@ def main():
                          "peak_source": peak_src + ", bf16 dense sustained",
                          "flop_per_edge": FLOP_PER_EDGE_MSG2, "edges_per_launch": edges,
                          "avg_launch_ms": k3_ms, "launches_timed": len(k3_events),
+                         "timing": "CUDA events around every K3 launch in a separate eager pass over the same steps "
+                                   "(the timed region itself replays a CUDA graph and carries no extra events)",
                          "share_of_step": k3_ms * LAYERS / (ms / args.steps),
                          "reference_equivalent_tflops": edges * FLOP_PER_EDGE_REFERENCE / (k3_ms * 1e-3) / 1e12,
                          "note": ("fp32 FFMA mode: the tensor pipe is idle, fraction shown against the bf16 tensor "
                                   "roofline for continuity" if mode not in ("bf16", "fp16", "fp16p") else f"{mode} tcgen05 mode")},
         }
         if world == 1 and not args.no_cpu_baseline:
-            sims = args.cpu_sims
-            sec = cpu_reference_steps(sims, 2, 1)
-            cores = os.cpu_count() or 1
-            line["cpu_baseline"] = {
-                "value": sims * N / sec, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-                "sample": f"{sims} sims x N={N} x 1 rollout step, 2 timed steps after 1 warm-up, float32, "
-                          f"{cores} threads (oracle port of the reference's e3nn/PyG formulation)"}
+            line["cpu_baseline"] = cpu_baseline_record(args.cpu_sims, 3, torch.float32)
+            line["cpu_baseline_f64"] = cpu_baseline_record(max(1, args.cpu_sims // 2), 3, torch.float64)
+            if configs is not None:
+                configs["cfg1_n5_b100_100step"]["cpu_baseline"] = cpu_baseline_record(
+                    100, 3, torch.float64, hidden=64, layers=4, nbody=5)
+                configs["cfg3_lmax_h2_n100"]["cpu_baseline"] = cpu_baseline_record(
+                    2, 3, torch.float32, hidden=HIDDEN, layers=LAYERS, nbody=NBODY, lmax_h=2)
+                configs["cfg4_n1000_fwd_bwd_cpu"] = cfg4_cpu_attempt(args.cfg4_cpu_seconds)
+        if modes is not None:
+            line["modes"] = modes
+        if configs is not None:
+            line["configs"] = configs
         if training is not None:
             line["training"] = training
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cfg4_cpu_attempt(seconds: int):
+    """BASELINE config 4 on the host: the reference formulation's forward + backward of ONE N=1000 graph (hidden 128,
+    6 layers) stores every [E, .] intermediate for autograd (E = 999,000; the message input alone is [E, 514]).  The
+    attempt runs in a child process with an address-space limit and a time limit; whatever happens is reported."""
+    import resource
+    code = (
+        "import os, sys, time, torch, resource\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "lim = 96 << 30\n"
+        "resource.setrlimit(resource.RLIMIT_AS, (lim, lim))\n"
+        "from oracle import segnn_oracle as O\n"
+        "torch.set_num_threads(os.cpu_count() or 1)\n"
+        "torch.manual_seed(0)\n"
+        "m = O.SEGNN(hidden_features=128, num_layers=6, dtype=torch.float32).train()\n"
+        "pos, vel, mass = O.synthetic_system(1, 1000, seed=5, dtype=torch.float32)\n"
+        "t0 = time.perf_counter()\n"
+        "g = O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), 1, 1000)\n"
+        "out = m(g)\n"
+        "print('FWD', time.perf_counter() - t0, flush=True)\n"
+        "out.pow(2).mean().backward()\n"
+        "print('FWDBWD', time.perf_counter() - t0, resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 2**20, flush=True)\n")
+    rec = {"config": "oracle port (reference formulation), float32, one N=1000 graph, hidden 128, 6 layers, "
+                     f"forward + backward; limits: {seconds} s, 96 GiB address space", "cores": os.cpu_count() or 1}
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=seconds)
+        txt = out.stdout
+        if "FWDBWD" in txt:
+            parts = txt.split("FWDBWD")[1].split()
+            rec.update(outcome="completed", seconds_fwd_bwd=float(parts[0]), peak_rss_gib=float(parts[1]))
+        else:
+            tail = (out.stderr or "").strip().splitlines()[-1:] or ["?"]
+            rec.update(outcome="reference infeasible at this size", detail=tail[0][:200],
+                       forward_seconds=float(txt.split("FWD")[1].split()[0]) if "FWD" in txt else None)
+    except subprocess.TimeoutExpired as exc:
+        txt = exc.stdout.decode() if isinstance(exc.stdout, bytes) else (exc.stdout or "")
+        rec.update(outcome=f"reference infeasible at this size within {seconds} s",
+                   forward_seconds=float(txt.split("FWD")[1].split()[0]) if "FWD" in txt else None)
+    return rec
 
 
 if __name__ == "__main__":

@@ -49,8 +49,10 @@ def test_edge_enumeration_bit_exact(B, N):
 def test_graph_builder_errors():
     with pytest.raises(ValueError):
         S.build_graph_with_knn(None, 2, 5, "cuda", 5)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="positions"):  # the kNN branch needs the node positions
         S.build_graph_with_knn(None, 2, 5, "cuda", 3)
+    knn = S.build_graph_with_knn(torch.randn(10, 3), 2, 5, "cuda", 3)
+    assert knn.shape == (2, 30) and int(knn[0].max()) == 9
     assert S.build_graph_with_knn(None, 0, 5, "cuda", None).shape == (2, 0)
 
 

@@ -91,7 +91,35 @@ def _load():
     return lib
 
 
+class _NvtxLib:
+    """SEGNN_NVTX=1: every C-ABI entry point runs inside an NVTX range named after it (one range per kernel family:
+    segnn_edge_layer_fwd, segnn_node_gemm_tc, ...), so that nsys / ncu --nvtx timelines attribute device time to the
+    reference function each export replaces.  Off by default: a range costs ~1 us of host time per call."""
+
+    def __init__(self, inner):
+        import torch
+        self._inner, self._nvtx = inner, torch.cuda.nvtx
+
+    def __getattr__(self, name):
+        fn = getattr(self._inner, name)
+        if not name.startswith("segnn_") or name in ("segnn_last_error", "segnn_version"):
+            return fn
+        nvtx = self._nvtx
+
+        def ranged(*args):
+            nvtx.range_push(name)
+            try:
+                return fn(*args)
+            finally:
+                nvtx.range_pop()
+        ranged.__name__ = name
+        setattr(self, name, ranged)
+        return ranged
+
+
 lib = _load()
+if os.environ.get("SEGNN_NVTX", "0") not in ("", "0"):
+    lib = _NvtxLib(lib)
 
 
 class SegnnKernelError(RuntimeError):

@@ -291,6 +291,55 @@ def make_sim_and_macro_fixture(rollout):
     save("ref_sim_macros.pt", out)
 
 
+def make_checkpoint_fixture():
+    """A checkpoint written by the reference's own Trainer.save_model / save_model_params / save_dataset_attributes
+    (trainer.py:526-537,599-612) after two real AdamW steps on a tiny SEGNN."""
+    import shutil
+    import trainer as ref_trainer
+    from datasets.nbody.dataset_gravity_otf import GravityDatasetOtf
+    torch.manual_seed(5)
+    model = SEGNN(hidden_features=16, num_layers=1).double()
+    fake = SimpleNamespace(model=model)
+    opt = ref_trainer.Trainer.create_optimizer(SimpleNamespace(model=model, args=SimpleNamespace(learning_rate=1.0)))
+    fake.optimizer = opt
+    fake.args = SimpleNamespace(learning_rate_factor=1.0, learning_rate_warmup_steps=100, dataset_name="nbody_small")
+    fake._rate = lambda step, factor, warmup: ref_trainer.Trainer._rate(fake, step, factor, warmup)
+    fake.lr_scheduler = ref_trainer.Trainer.create_lr_scheduler(fake)
+    pos, vel, mass, y = synthetic(2, 5, 9, False)
+    for _ in range(2):
+        opt.zero_grad()
+        g = ref_graph(pos, vel, mass, 2, 5)
+        (model(g) - y).pow(2).mean().backward()
+        opt.step()
+        fake.lr_scheduler.step()
+    fake.step_count, fake.best_metrics = 2, {"valid_loss": 0.25}
+    out_dir = os.path.join(HERE, "ref_run", "2025-01-02_03-04-05")
+    shutil.rmtree(os.path.join(HERE, "ref_run"), ignore_errors=True)
+    fake.save_dir_path = out_dir
+    ref_trainer.Trainer.save_model(fake)
+    ref_trainer.Trainer.save_model_params(fake)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            ds = GravityDatasetOtf(batch_size=2, sim_length=40, num_nodes=5, double_precision=True, cache_data=False,
+                                   path=os.path.join(tmp, "data"))
+        finally:
+            os.chdir(cwd)
+    fake.dataloader = SimpleNamespace(dataset=ds)
+    ref_trainer.Trainer.save_dataset_attributes(fake)
+    meta_path = os.path.join(out_dir, "nbody_small_dataset", "metadata.json")
+    meta = json.load(open(meta_path))
+    meta["path"] = "datasets/nbody/dataset/gravity"  # the absolute path of this container means nothing elsewhere
+    json.dump(meta, open(meta_path, "w"), indent=4)
+    model.eval()
+    with torch.no_grad():
+        pred = model(ref_graph(pos, vel, mass, 2, 5))
+    save("ref_checkpoint_io.pt", {"kind": KIND, "pos": pos, "vel": vel, "mass": mass, "pred_eval": pred,
+                                  "lr": opt.param_groups[0]["lr"], "run_dir": "ref_run/2025-01-02_03-04-05"})
+    print("wrote", out_dir, os.listdir(out_dir))
+
+
 if __name__ == "__main__":
     print("third-party provider:", KIND)
     make_graph_fixture()
@@ -302,3 +351,4 @@ if __name__ == "__main__":
     run_model_case("h32_l2_n6", H=32, lmax_h=2, L=2, B=2, N=6, seed=4)
     rollout = make_rollout_fixture(model_a)
     make_sim_and_macro_fixture(rollout)
+    make_checkpoint_fixture()

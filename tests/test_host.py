@@ -251,3 +251,53 @@ def test_fisher_and_ks_match_reference_libraries():
     assert M.energy_ratio_steps(np.array([1.0, 1.2, 3.0, 1.0]), np.ones(4)) == 2
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         M.energy_momentum(torch.zeros(2, 10, 3), torch.zeros(2, 10, 3), 2, 5)
+
+
+# ---- checkpoints / run directory in the reference's on-disk layout ------------------------------
+def _ref_run_dir():
+    import os
+    return os.path.join(os.path.dirname(__file__), "golden", "ref_run", "2025-01-02_03-04-05")
+
+
+def test_reference_written_checkpoint_loads_and_round_trips(tmp_path):
+    """tests/golden/ref_run/... was written by the reference's own Trainer.save_model / save_model_params /
+    save_dataset_attributes (tests/golden/make_reference_golden.py::make_checkpoint_fixture)."""
+    import json
+    import os
+    import torch
+    import segnn_b200 as S
+    from oracle import segnn_oracle as O
+    run = _ref_run_dir()
+    ck = torch.load(os.path.join(run, "model.pth"), map_location="cpu", weights_only=False)
+    assert set(ck) == {"model_state_dict", "optimizer_state_dict", "step_count", "best_metrics", "scheduler_state_dict"}
+    model = S.SEGNN(hidden_features=16, num_layers=1).double()
+    ts_params = [p for p in model.parameters()]
+    opt = torch.optim.AdamW(ts_params, weight_decay=1e-8, lr=1.0, betas=(0.9, 0.98), eps=1e-9)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: S.noam_rate(s, 16, 1.0, 100))
+    S.load_checkpoint(os.path.join(run, "model.pth"), "cpu", model=model, optimizer=opt, scheduler=sched)
+    assert S.load_checkpoint.last == {"step_count": 2, "best_metrics": {"valid_loss": 0.25}}
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, ck["model_state_dict"][k]), k
+    assert len(opt.state_dict()["state"]) == len(ts_params) and sched.last_epoch == 2
+    assert opt.state_dict()["state"][0]["exp_avg"].shape == ts_params[0].shape
+    # what we write carries exactly the keys the reference wrote (incl. e3nn's tp.output_mask buffers)
+    assert set(S.checkpoint.reference_state_dict(model)) == set(ck["model_state_dict"])
+    path = S.save_model(model, opt, sched, step_count=3, best_metrics={"valid_loss": 0.2}, save_path=str(tmp_path))
+    ck2 = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck2) == set(ck) and ck2["step_count"] == 3
+    assert ck2["optimizer_state_dict"]["param_groups"][0]["betas"] == ck["optimizer_state_dict"]["param_groups"][0]["betas"]
+    om = O.SEGNN(hidden_features=16, num_layers=1)
+    om.load_state_dict({k: v for k, v in ck2["model_state_dict"].items() if "output_mask" not in k})
+    # model_params.json: same keys and values as the reference wrote for the same architecture
+    ref_params = json.load(open(os.path.join(run, "model_params.json")))
+    mine = model.get_serializable_attributes()
+    assert set(mine) == set(ref_params)
+    for k in ("hidden_features", "lmax_h", "lmax_attr", "num_layers", "norm", "task", "num_params"):
+        assert mine[k] == ref_params[k], k
+    for k in ("node_attr_irreps", "input_irreps", "hidden_irreps", "output_irreps", "edge_attr_irreps",
+              "additional_message_irreps"):
+        assert mine[k].replace(" ", "") == ref_params[k].replace(" ", ""), k
+    assert S.checkpoint.get_dataset_metadata_path(os.path.join(run, "model.pth")) == \
+        os.path.join(run, "nbody_small_dataset", "metadata.json")
+    with pytest.raises(FileNotFoundError):
+        S.checkpoint.get_dataset_metadata_path("/tmp")

@@ -186,20 +186,33 @@ __global__ void __launch_bounds__(256) node_gemm_kernel(const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  // register prefetch of the next K tile while the current one is being multiplied: at training sizes (a few hundred
+  // rows) a launch is a handful of CTAs deep, so the global-load latency of every K step is exposed unless the loads of
+  // step k + 1 are in flight during the FMAs of step k
+  float ra[4], rb[4];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = k0 + a_k + q;
+      float v = 0.f;
+      if (a_plane >= 0 && k < K) v = k < n_in ? x0[a_plane * n_in + k] : x1[a_plane * n_in + (k - n_in)];
+      ra[q] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = k0 + b_k, c = col0 + b_c + q;
+      rb[q] = (k < K && c < n_out) ? W[(int64_t)k * n_out + c] : 0.f;
+    }
+  };
+  load_tile(0);
   for (int k0 = 0; k0 < K; k0 += kGemmBK) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      int k = k0 + a_k + q;
-      float v = 0.f;
-      if (a_plane >= 0 && k < K) v = k < n_in ? x0[a_plane * n_in + k] : x1[a_plane * n_in + (k - n_in)];
-      As[a_k + q][a_row] = v;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int k = k0 + b_k, c = col0 + b_c + q;
-      Bs[b_k][b_c + q] = (k < K && c < n_out) ? W[(int64_t)k * n_out + c] : 0.f;
+      As[a_k + q][a_row] = ra[q];
+      Bs[b_k][b_c + q] = rb[q];
     }
     __syncthreads();
+    if (k0 + kGemmBK < K) load_tile(k0 + kGemmBK);
 #pragma unroll
     for (int k = 0; k < kGemmBK; ++k) {
       float a[4], b[4];

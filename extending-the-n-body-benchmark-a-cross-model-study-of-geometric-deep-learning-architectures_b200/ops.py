@@ -315,6 +315,20 @@ def node_gemm_wgrad(x0, x1, dy0, dy1, split: int):
     return dw_s, dw_v
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(device, k: int = 0) -> "torch.cuda.Stream":
+    """One of a few cached side streams per device: independent kernels of the backward pass (the dQ pass of the edge
+    backward, the weight-gradient GEMMs) run there so that they overlap the critical dgrad chain -- every one of them
+    fills only a fraction of the 148 SMs at training sizes.  Fork / join are stream waits, which a CUDA-graph capture
+    records as parallel branches."""
+    key = (torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device(), k)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg):
     """Backward of the fused edge layer with recompute. Returns dP, dQ [nodes,4,3n], the message_layer_2 gradient
     blocks {ss, vs, sv, vv, b} and dw_edge1 [6n]."""
@@ -327,15 +341,23 @@ def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_e
              sv=gz[4 * n * n: 5 * n * n].view(n, n), vv=gz[5 * n * n: 6 * n * n].view(n, n), b=gz[6 * n * n:])
     dwe_partial = torch.empty((nodes, 6 * n), **f)
     w2t = {k: (w2[k + "_t"] if k + "_t" in w2 else w2[k].t().contiguous()) for k in ("ss", "vs", "sv", "vv")}
+    dagg = dagg.contiguous()
     with torch.cuda.device(dev):
-        for pas, dout in ((0, dP), (1, dQ)):
+        main, side = torch.cuda.current_stream(dev), side_stream(dev, 0)
+        side.wait_stream(main)  # every input (and the zero-fill above) is ready
+
+        def launch(pas, dout):
             check(lib.segnn_edge_layer_bwd(pas, _p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1),
                                            _p(w2["ss"]), _p(w2["vs"]), _p(w2["sv"]), _p(w2["vv"]), _p(w2["b"]),
                                            _p(w2t["ss"]), _p(w2t["vs"]), _p(w2t["sv"]), _p(w2t["vv"]), _p(bn_a),
-                                           _p(bn_b), _p(bn_c), _p(dagg.contiguous()), _p(dout), _p(g["ss"]),
+                                           _p(bn_b), _p(bn_c), _p(dagg), _p(dout), _p(g["ss"]),
                                            _p(g["vs"]), _p(g["sv"]), _p(g["vv"]), _p(g["b"]), _p(dwe_partial),
                                            _stream()), "segnn_edge_layer_bwd")
             _bump()
+        with torch.cuda.stream(side):  # pass 1 (dQ) is independent of pass 0 (dP, weight gradients): overlap them
+            launch(1, dQ)
+        launch(0, dP)
+        main.wait_stream(side)
     return dP, dQ, g, colsum(dwe_partial)
 
 

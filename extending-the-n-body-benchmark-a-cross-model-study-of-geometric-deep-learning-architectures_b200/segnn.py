@@ -295,6 +295,45 @@ class SEGNN(nn.Module):
                     head=packing.pack_head(f(self.pre_pool2.tp.weight), n))
         return tree, bufs
 
+    # -- flat parameter / gradient storage (training plumbing) ----------------------------------------------------
+    def use_flat_storage(self):
+        """Re-points every parameter at a slice of ONE flat fp32 buffer and every ``.grad`` at the matching slice of a
+        second one.  The training function then reads the flat buffer directly (no per-step ``cat`` of ~100 tensors),
+        writes the whole gradient with one scatter-add into the gradient buffer (no per-parameter clone by autograd's
+        AccumulateGrad) and a data-parallel step all-reduces that buffer in place (no flatten / unflatten).  Opt-in
+        (``TrainStep`` does it): gradients are OVERWRITTEN by every backward, not accumulated.  Call after the module
+        sits on its device in float32; ``.to()`` / ``.float()`` afterwards silently drops back to the generic path."""
+        params = list(self.parameters())
+        if any(p.dtype != torch.float32 for p in params) or len({p.device for p in params}) != 1:
+            raise RuntimeError("flat storage needs float32 parameters on one device")
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=params[0].device)
+        sink = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                flat[off:off + k].copy_(p.data.reshape(-1))
+                p.data = flat[off:off + k].view(p.shape)
+                p.grad = sink[off:off + k].view(p.shape)
+                off += k
+        self._flat = (flat, sink)
+        return flat, sink
+
+    def _flat_storage(self, params):
+        """(flat parameters, gradient sink) when every parameter / gradient still aliases its slice, else (None, None)."""
+        flat_sink = getattr(self, "_flat", None)
+        if flat_sink is None:
+            return None, None
+        flat, sink = flat_sink
+        off, p0, g0 = 0, flat.data_ptr(), sink.data_ptr()
+        for p in params:
+            if p.data_ptr() != p0 + 4 * off or p.grad is None or p.grad.data_ptr() != g0 + 4 * off \
+                    or p.dtype != torch.float32:
+                return None, None
+            off += p.numel()
+        return flat, sink
+
     def bn_buffers(self):
         """The BatchNorm running statistics as they are NOW (never cached: dtype casts and load_state_dict(assign=True)
         replace the buffer objects)."""
@@ -316,8 +355,10 @@ class SEGNN(nn.Module):
             key = tuple((tuple(p.shape), p.device) for p in params)  # the map depends on shapes only
             if self._pack_map is None or self._pack_map[0] != key:
                 self._pack_map = (key, training.build_pack_map(self))
+            flat, sink = self._flat_storage(params) if dtype == torch.float32 else (None, None)
             cfg = dict(pack_map=self._pack_map[1], dtype=dtype, n=self.n, B=batch_size, N=num_nodes,
-                       bn_training=bn_training, backend=backend, bn_buffers=self.bn_buffers())
+                       bn_training=bn_training, backend=backend, bn_buffers=self.bn_buffers(), flat_params=flat,
+                       grad_sink=sink)
             return training.SegnnTrainFunctionFlat.apply(cfg, pos, vel, mass, *params)
         tree, bufs = self.packed_train(dtype)
         leaves, spec = training.flatten_packed(tree)

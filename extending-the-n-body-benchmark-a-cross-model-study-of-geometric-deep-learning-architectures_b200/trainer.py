@@ -17,6 +17,7 @@ from typing import Optional
 import torch
 
 __all__ = ["noam_rate", "target_common_loss", "flatten_gradients", "unflatten_gradients", "allreduce_gradients",
+           "allreduce_flat",
            "broadcast_module_state", "TrainStep"]
 
 
@@ -67,6 +68,19 @@ def unflatten_gradients(params, bucket: torch.Tensor) -> None:
         off += n
 
 
+def allreduce_flat(sink: torch.Tensor, group=None) -> torch.Tensor:
+    """The gradients already live in one flat buffer (SEGNN.use_flat_storage): ONE in-place all-reduce, averaged by
+    the collective itself where the backend can (NCCL ``AVG``), no flatten / unflatten / divide launches."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(sink, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(sink, op=dist.ReduceOp.SUM, group=group)
+        sink.div_(world)
+    return sink
+
+
 def allreduce_gradients(params, group=None, bucket: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Average the gradients over the ranks of ``group`` with ONE all-reduce of a flat bucket (1.95 M fp32 = 7.8 MB
     for the README model: latency-bound over NVLink, so a single bucket beats per-tensor collectives)."""
@@ -100,12 +114,18 @@ class TrainStep:
                  learning_rate_factor: float = 1.0, learning_rate_warmup_steps: int = 4000,
                  clip_gradients_value: Optional[float] = None, clip_gradients_norm: Optional[float] = None,
                  position_loss_weight: float = 1.0, velocity_loss_weight: float = 1.0, process_group=None,
-                 distributed: bool = False, use_cuda_graph: bool = True, fused_optimizer: Optional[bool] = None):
+                 distributed: bool = False, use_cuda_graph: bool = True, fused_optimizer: Optional[bool] = None,
+                 flat_storage: bool = True):
         self.model, self.B, self.N = model, int(batch_size), int(num_nodes)
         self.nodes = self.B * self.N
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
         self.device = dev
+        # flat parameter / gradient storage: see SEGNN.use_flat_storage (skipped for non-fp32 modules)
+        self.flat_params = self.grad_sink = None
+        if flat_storage and hasattr(model, "use_flat_storage") and len(self.params) == len(list(model.parameters())) \
+                and all(p.dtype == torch.float32 for p in self.params):
+            self.flat_params, self.grad_sink = model.use_flat_storage()
         if fused_optimizer is None:
             fused_optimizer = dev.type == "cuda"
         self.optimizer = torch.optim.AdamW(self.params, weight_decay=1e-8, lr=learning_rate, betas=(0.9, 0.98),
@@ -130,6 +150,11 @@ class TrainStep:
         if distributed:
             broadcast_module_state(model, 0, process_group)
 
+    def _zero_grad(self):
+        """With flat storage every backward overwrites the whole gradient buffer and the ``.grad`` views must stay."""
+        if self.grad_sink is None:
+            self.optimizer.zero_grad(set_to_none=True)
+
     # -- forward + loss + backward on the static buffers ----------------------------------------------------------
     def _forward_backward(self):
         pred = self.model.forward_state(self.pos, self.vel, self.mass, self.B, self.N)
@@ -145,14 +170,14 @@ class TrainStep:
         bn_state = [b.clone() for b in self.model.buffers()]
         with torch.cuda.stream(side):
             for _ in range(2):
-                self.optimizer.zero_grad(set_to_none=True)
+                self._zero_grad()
                 self._forward_backward()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         for b, saved in zip(self.model.buffers(), bn_state):  # warm-up must not move the running statistics
             b.copy_(saved)
         graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        self._zero_grad()
         with torch.cuda.graph(graph):
             self._forward_backward()
         self._graph = graph
@@ -175,14 +200,26 @@ class TrainStep:
                 self.capture()
             self._graph.replay()  # gradients are rewritten in place by the replay
         else:
-            self.optimizer.zero_grad(set_to_none=True)
+            self._zero_grad()
             self._forward_backward()
+        flat = self.grad_sink is not None and self.params[0].grad is not None \
+            and self.params[0].grad.data_ptr() == self.grad_sink.data_ptr()
         if self.distributed:
-            self._bucket = allreduce_gradients(self.params, self.group, self._bucket)
+            if flat:
+                allreduce_flat(self.grad_sink, self.group)
+            else:
+                self._bucket = allreduce_gradients(self.params, self.group, self._bucket)
         if self.clip_value is not None:
-            torch.nn.utils.clip_grad_value_(self.params, clip_value=self.clip_value)
+            if flat:
+                self.grad_sink.clamp_(-self.clip_value, self.clip_value)
+            else:
+                torch.nn.utils.clip_grad_value_(self.params, clip_value=self.clip_value)
         if self.clip_norm is not None:
-            torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.clip_norm)
+            if flat:  # torch.nn.utils.clip_grad_norm_ on the flat buffer: three launches instead of one per tensor
+                norm = torch.linalg.vector_norm(self.grad_sink)
+                self.grad_sink.mul_(torch.clamp(self.clip_norm / (norm + 1e-6), max=1.0))
+            else:
+                torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.clip_norm)
         self.optimizer.step()
         self.lr_scheduler.step()
         self.step_count += 1

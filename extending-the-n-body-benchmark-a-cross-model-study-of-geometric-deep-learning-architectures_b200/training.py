@@ -119,16 +119,45 @@ def _transposed(w):
     return dict(w_s=w["w_s"].t().contiguous(), w_v=w["w_v"].t().contiguous())
 
 
-def _node_tp_backward(be, w, x0, x1, y, attr, n, gate, dout, split_out: Optional[int] = None):
+class _SideWork:
+    """Weight-gradient work (wgrad GEMMs, bias column sums) is off the critical dgrad chain: on CUDA it goes to a side
+    stream (ops.side_stream) after a fork on the current stream and is joined once at the end of the backward pass."""
+
+    def __init__(self, ref):
+        self.stream = _ops.side_stream(ref.device, 1) if ref.is_cuda else None
+        self.used = False
+        self.keep = []  # closures (and through them the tensors the side kernels read) stay alive until join(): the
+        #                 caching allocator must not hand their memory to a later main-stream allocation meanwhile
+
+    def run(self, fn):
+        if self.stream is None:
+            return fn()
+        self.stream.wait_stream(torch.cuda.current_stream(self.stream.device))
+        self.used = True
+        self.keep.append(fn)
+        with torch.cuda.stream(self.stream):
+            return fn()
+
+    def join(self):
+        if self.stream is not None and self.used:
+            torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
+        self.keep.clear()
+
+
+def _node_tp_backward(be, w, x0, x1, y, attr, n, gate, dout, split_out: Optional[int] = None, side=None):
     """Backward of node_gemm(x0|x1; w) -> tp_combine(gate, bias). Returns (dx (tensor or pair), grads dict)."""
     nodes = y.shape[0]
     n0 = 2 * n if gate else n
     dy, dz0 = be.tp_combine_bwd(y, attr, n, gate, w["bias"], dout)
-    dbias = be.colsum(dz0.view(nodes, n0))
-    dw_s, dw_v = be.node_gemm_wgrad(x0, x1, dy, None, 0)
+
+    def weight_side():
+        dbias = be.colsum(dz0.view(nodes, n0))
+        dw_s, dw_v = be.node_gemm_wgrad(x0, x1, dy, None, 0)
+        return dict(w_s=dw_s, w_v=dw_v, bias=dbias)
+    grads = side.run(weight_side) if side is not None else weight_side()
     k = w["w_s"].shape[0]
     dx = be.node_gemm(dy, None, _transposed(w), k, split=split_out or 0)
-    return dx, dict(w_s=dw_s, w_v=dw_v, bias=dbias)
+    return dx, grads
 
 
 def backward_train(W: Dict, saved: Dict, dpred, backend=None):
@@ -140,10 +169,12 @@ def backward_train(W: Dict, saved: Dict, dpred, backend=None):
     attr, pos, mass = saved["attr"], saved["pos"], saved["mass"]
     bn_training = saved["bn_training"]
     grads = dict(layers=[])
+    side = _SideWork(dpred) if backend is None else None  # test back ends (CPU emulation) run in program order
     # head + pre_pool1
     dhp, dw_head = be.head_bwd(saved["hp"], attr, W["head"], dpred.contiguous(), n)
     grads["head"] = dw_head
-    dh, grads["pool1"] = _node_tp_backward(be, W["pool1"], saved["h_last"], None, saved["yp"], attr, n, True, dhp)
+    dh, grads["pool1"] = _node_tp_backward(be, W["pool1"], saved["h_last"], None, saved["yp"], attr, n, True, dhp,
+                                           side=side)
     for lw, rec in zip(reversed(W["layers"]), reversed(saved["layers"])):
         g = dict(bn_msg=None, bn_feat=None)
         m1, m2, u1, u2 = lw["msg1"], lw["msg2"], lw["upd1"], lw["upd2"]
@@ -158,9 +189,9 @@ def backward_train(W: Dict, saved: Dict, dpred, backend=None):
         else:
             dpre = dh
         # update_layer_2 (+ residual), update_layer_1
-        dg1, g["upd2"] = _node_tp_backward(be, u2, rec["g1"], None, rec["y2"], attr, n, False, dpre)
+        dg1, g["upd2"] = _node_tp_backward(be, u2, rec["g1"], None, rec["y2"], attr, n, False, dpre, side=side)
         (dh_u, dagg), g["upd1"] = _node_tp_backward(be, u1, rec["h"], rec["agg"], rec["y1"], attr, n, True, dg1,
-                                                    split_out=n)
+                                                    split_out=n, side=side)
         # message BatchNorm folded through the sum over senders
         if lw["bn_msg"] is not None:
             flat_g, flat_raw = dagg.view(nodes, 4 * n), rec["agg_raw"].view(nodes, 4 * n)
@@ -176,15 +207,20 @@ def backward_train(W: Dict, saved: Dict, dpred, backend=None):
         dP, dQ, g["msg2"], dwe = be.edge_layer_bwd(pos, mass, B, N, n, rec["p"], rec["q"], m1["w_edge"], m2, bn_a, bn_b,
                                                    bn_c, dagg)
         # message_layer_1 projections: [P | Q] = h @ W (+ bias on P's l=0 columns)
-        dw_s, dw_v = be.node_gemm_wgrad(rec["h"], None, dP, dQ, 3 * n)
-        dbias1 = be.colsum(dP.view(nodes, 12 * n))[:2 * n]
+        def msg1_weights(h_=rec["h"], dP_=dP, dQ_=dQ):
+            dw_s, dw_v = be.node_gemm_wgrad(h_, None, dP_, dQ_, 3 * n)
+            dbias1 = be.colsum(dP_.view(nodes, 12 * n))[:2 * n]
+            return dict(w_s=dw_s, w_v=dw_v, bias=dbias1.contiguous())
+        g["msg1"] = side.run(msg1_weights) if side is not None else msg1_weights()
+        g["msg1"]["w_edge"] = dwe
         dh_m = be.node_gemm(dP, dQ, _transposed(m1), n)
-        g["msg1"] = dict(w_s=dw_s, w_v=dw_v, bias=dbias1.contiguous(), w_edge=dwe)
         dh = be.add3(dpre, dh_u, dh_m)
         grads["layers"].append(g)
     grads["layers"].reverse()
     dw_e, db_e = be.embed_bwd(saved["x_in"], attr, dh, n)
     grads["embed"] = dict(w=dw_e, bias=db_e)
+    if side is not None:
+        side.join()
     return grads
 
 
@@ -270,7 +306,9 @@ class SegnnTrainFunctionFlat(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, pos, vel, mass, *params):
         pm, dtype = cfg["pack_map"], cfg["dtype"]
-        flat = torch.cat([p.detach().reshape(-1) for p in params]).to(dtype)
+        flat = cfg.get("flat_params")  # SEGNN.use_flat_storage: the parameters ARE slices of this buffer
+        if flat is None:
+            flat = torch.cat([p.detach().reshape(-1) for p in params]).to(dtype)
         scale = pm["scale"].to(dtype)
         packed = flat.index_select(0, pm["idx"]) * scale
         leaves = [t.view(shape) for t, shape in zip(packed.split(pm["sizes"]), pm["shapes"])]
@@ -295,6 +333,12 @@ class SegnnTrainFunctionFlat(torch.autograd.Function):
         dev, dt = ctx.scale.device, ctx.scale.dtype
         pieces = [out[i].reshape(-1).to(dt) if out[i] is not None
                   else torch.zeros(pm["sizes"][i], dtype=dt, device=dev) for i in pm["grad_leaves"]]
+        sink = ctx.cfg.get("grad_sink")
+        if sink is not None:  # every .grad is a slice of `sink`: one scatter-add writes all of them, autograd gets None
+            sink.zero_()
+            sink.index_add_(0, pm["grad_idx"], torch.cat(pieces) * pm["grad_scale"].to(dt))
+            ctx.saved = None
+            return (None, None, None, None) + (None,) * len(ctx.param_shapes)
         gflat = torch.zeros(sum(pm["param_sizes"]), dtype=dt, device=dev)
         gflat.index_add_(0, pm["grad_idx"], torch.cat(pieces) * pm["grad_scale"].to(dt))
         gparams = [g.view(shape).to(pdt) for g, shape, pdt in

@@ -206,6 +206,12 @@ def _ddp_worker(rank, world, port, out):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1)) if i != 2 else None  # one parameter without a gradient
     S.allreduce_gradients(model.parameters())
     grads = [float(p.grad.reshape(-1)[0]) for p in model.parameters()]
+    # flat storage: the gradients are slices of one buffer, averaged in place by one collective
+    flat, sink = model.use_flat_storage()
+    assert all(torch.equal(a, b) for a, b in zip(ref, model.parameters()))  # values preserved by the re-pointing
+    sink.fill_(float(rank + 1))
+    S.trainer.allreduce_flat(sink)
+    grads.append(float(next(iter(model.parameters())).grad.reshape(-1)[0]))
     gathered = [torch.zeros_like(ref[0]) for _ in range(world)]
     dist.all_gather(gathered, ref[0])
     same = all(torch.equal(g, gathered[0]) for g in gathered)
@@ -229,8 +235,41 @@ def test_two_rank_gloo_gradient_allreduce():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert same
+    assert grads.pop() == 1.5  # allreduce_flat: mean of (1, 2), seen through a parameter's .grad view
     for i, g in enumerate(grads):
         assert g == (0.0 if i == 2 else 1.5 * (i + 1))
+
+
+def test_flat_parameter_and_gradient_storage_matches_per_tensor_path():
+    """SEGNN.use_flat_storage: same prediction and same gradients as the per-tensor path (emulated kernels, float32
+    on CPU), gradients land in the flat buffer through the .grad views, and a dtype cast drops back to the generic path."""
+    torch.manual_seed(4)
+    H, L, B, N = 16, 2, 3, 5
+    a = S.SEGNN(hidden_features=H, num_layers=L).train()
+    b = S.SEGNN(hidden_features=H, num_layers=L).train()
+    b.load_state_dict(a.state_dict())
+    flat, sink = b.use_flat_storage()
+    params = list(b.parameters())
+    assert b._flat_storage(params)[0] is flat and flat.numel() == sum(p.numel() for p in params)
+    pos, vel, mass = O.synthetic_system(B, N, seed=3)
+    pos, vel, mass = pos.reshape(-1, 3).float(), vel.reshape(-1, 3).float(), mass.reshape(-1).float()
+    y = torch.randn(B * N, 6)
+    outs = []
+    for m in (a, b):
+        pred = m._forward_train(pos, vel, mass, B, N, True, True, backend=E.TorchBackend, dtype=torch.float32)
+        O.target_common_loss(pred, y).backward()
+        outs.append(pred.detach())
+    assert torch.allclose(outs[0], outs[1], atol=1e-6)
+    off = 0
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert pb.grad.data_ptr() == sink.data_ptr() + 4 * off  # still the view, not a clone
+        assert torch.allclose(pa.grad, pb.grad, atol=1e-5 * float(pa.grad.abs().max()) + 1e-9)
+        off += pb.numel()
+    with torch.no_grad():  # an optimizer-style in-place update is visible through the flat buffer
+        params[0].add_(1.0)
+    assert float(flat[0]) == float(params[0].reshape(-1)[0])
+    b.double()
+    assert b._flat_storage(list(b.parameters())) == (None, None)
 
 
 def test_fisher_and_ks_match_reference_libraries():

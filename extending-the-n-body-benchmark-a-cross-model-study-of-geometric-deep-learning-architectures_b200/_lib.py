@@ -52,7 +52,8 @@ PROTOTYPES = {
     "segnn_tp_combine_bwd": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "segnn_node_gemm_wgrad_workspace": (_c.c_int64, [_int, _int, _int]),
     "segnn_node_gemm_wgrad": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr]),
-    "segnn_edge_layer_bwd": (_int, [_int, _ptr, _ptr, _int, _int, _int] + [_ptr] * 24),
+    "segnn_edge_layer_bwd": (_int, [_int, _ptr, _ptr, _int, _int, _int] + [_ptr] * 25),
+    "segnn_edge_layer_bwd_workspace": (_c.c_int64, [_int, _int, _int]),
     "segnn_embed_bwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_head_bwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_generic_tp": (_int, [_ptr, _int, _ptr, _int, _c.c_int64, _ptr, _ptr, _int, _ptr, _ptr, _int, _ptr, _ptr]),

@@ -9,8 +9,10 @@
 // The gradient that reaches every message of receiver i is  dm = A * dagg_i + B * m + C  (per channel), which covers
 // the plain sum (A = 1), eval BatchNorm (A = mul) and train-mode BatchNorm (batch-statistics terms B, C computed on
 // the host from node-level reductions).
-// Weight gradients of message_layer_2 are accumulated with fp32 atomics (one per 8 fused multiply-adds); a
-// deterministic split-K tensor-core version is future work.
+// Weight gradients of message_layer_2 are reduced WITHOUT atomics: the grid is persistent (a CTA walks over several
+// sets of stationary nodes), every thread group owns a private slab [6 n^2 + 2 n] of partial sums in a caller-provided
+// workspace that it updates with plain read-modify-writes in program order, and a second kernel adds the slabs in a
+// fixed order.  Gradients are therefore bit-identical from run to run.
 #include "segnn_common.cuh"
 
 namespace segnn {
@@ -37,7 +39,7 @@ struct EdgeBwdArgs {
   const float *bnA, *bnB, *bnC;                         // [2n], [2n], [n]
   const float* dagg;                                    // [nodes][4][n]
   float* dout;                                          // dP (pass 0) or dQ (pass 1): [nodes][4][3n]
-  float *dw2_ss, *dw2_vs, *dw2_sv, *dw2_vv, *db2;       // pass 0, atomically accumulated (caller zeroes)
+  float* slabs;                                         // pass 0: [gridDim.x * kBG][6 n^2 + 2 n] partial weight grads
   float* dwe_partial;                                   // pass 0: [nodes][6n]
   int nodes, N, n;
 };
@@ -52,8 +54,16 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
   float* db = hb + kBE * 5 * NP;                   // [8][6][NP] gradients of the message_layer_2 pre-activations
   float* gb = smem + (size_t)kBG * (kBE * 11 * NP) + q * (kBE * 8);  // [8][8]: ax, ay, az, valid, len, mm
 
-  const int64_t r = (int64_t)blockIdx.x * kBG + q;  // stationary node
-  if (r >= a.nodes) return;
+  const int64_t slab_stride = (int64_t)6 * n * n + 2 * n;
+  float* slab = PASS == 0 ? a.slabs + ((int64_t)blockIdx.x * kBG + q) * slab_stride : nullptr;
+  float* s_ss = slab;                       // [n][2n]
+  float* s_vs = slab + (int64_t)2 * n * n;  // [n][2n]
+  float* s_sv = slab + (int64_t)4 * n * n;  // [n][n]
+  float* s_vv = slab + (int64_t)5 * n * n;  // [n][n]
+  float* s_b = slab + (int64_t)6 * n * n;   // [2n]
+  bool first_block = true, first_node = true;  // the first visit of a slab location stores, later visits accumulate
+  // persistent grid: this thread group handles stationary nodes r = (blockIdx.x + k gridDim.x) * kBG + q in order
+  for (int64_t r = (int64_t)blockIdx.x * kBG + q; r < a.nodes; r += (int64_t)gridDim.x * kBG) {
   const int64_t g = r / N;
   const int ir = (int)(r - g * N);
   const int64_t base = g * N;
@@ -257,15 +267,26 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
           for (int uu = 0; uu < 4; ++uu) {
             const int u = u0 + uu;
             if (u < n) {
-              atomicAdd(&a.dw2_ss[(int64_t)u * 2 * n + w], g_ss_s[uu]);
-              atomicAdd(&a.dw2_ss[(int64_t)u * 2 * n + n + w], g_ss_g[uu]);
-              atomicAdd(&a.dw2_vs[(int64_t)u * 2 * n + w], g_vs_s[uu]);
-              atomicAdd(&a.dw2_vs[(int64_t)u * 2 * n + n + w], g_vs_g[uu]);
-              atomicAdd(&a.dw2_sv[(int64_t)u * n + w], g_sv[uu]);
-              atomicAdd(&a.dw2_vv[(int64_t)u * n + w], g_vv[uu]);
+              // private slab, plain read-modify-write: only this thread ever touches these addresses
+              if (first_block) {
+                s_ss[(int64_t)u * 2 * n + w] = g_ss_s[uu];
+                s_ss[(int64_t)u * 2 * n + n + w] = g_ss_g[uu];
+                s_vs[(int64_t)u * 2 * n + w] = g_vs_s[uu];
+                s_vs[(int64_t)u * 2 * n + n + w] = g_vs_g[uu];
+                s_sv[(int64_t)u * n + w] = g_sv[uu];
+                s_vv[(int64_t)u * n + w] = g_vv[uu];
+              } else {
+                s_ss[(int64_t)u * 2 * n + w] += g_ss_s[uu];
+                s_ss[(int64_t)u * 2 * n + n + w] += g_ss_g[uu];
+                s_vs[(int64_t)u * 2 * n + w] += g_vs_s[uu];
+                s_vs[(int64_t)u * 2 * n + n + w] += g_vs_g[uu];
+                s_sv[(int64_t)u * n + w] += g_sv[uu];
+                s_vv[(int64_t)u * n + w] += g_vv[uu];
+              }
             }
           }
         }
+        first_block = false;
       }
       // ---- phase 4: gradients of the edge features (input channel = this thread) --------------------------------
       float dx[kBE][5];
@@ -368,10 +389,28 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
       float* pw = a.dwe_partial + r * 6 * n;
 #pragma unroll
       for (int c = 0; c < 6; ++c) pw[c * n + w] = dwe[c];
-      atomicAdd(&a.db2[w], db2s);
-      atomicAdd(&a.db2[n + w], db2g);
+      s_b[w] = first_node ? db2s : s_b[w] + db2s;
+      s_b[n + w] = first_node ? db2g : s_b[n + w] + db2g;
+      first_node = false;
     }
   }
+  bwd_group_barrier(1 + q, NT);  // the staging buffers are reused by the next stationary node
+  }  // persistent loop
+}
+
+// out[i] = sum over slabs (fixed order) of slabs[s * stride + offset + i]
+__global__ void slab_reduce_kernel(const float* __restrict__ slabs, int n_slabs, int64_t stride, int64_t offset,
+                                   int64_t count, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int sidx = 0; sidx < n_slabs; ++sidx) acc += slabs[sidx * stride + offset + i];
+    out[i] = acc;
+  }
+}
+
+static inline unsigned bwd_grid(int64_t nodes) {
+  const int64_t want = (nodes + kBG - 1) / kBG;
+  return (unsigned)(want < 2 * 148 ? want : 2 * 148);
 }
 
 template <int NT, int PASS>
@@ -385,7 +424,7 @@ static int launch_bwd(const EdgeBwdArgs& args, cudaStream_t stream) {
     return SEGNN_E_CUDA;
   }
   dim3 block(NT, kBG);
-  const unsigned grid = (unsigned)(((int64_t)args.nodes + kBG - 1) / kBG);
+  const unsigned grid = bwd_grid(args.nodes);
   kern<<<grid, block, smem, stream>>>(args);
   err = cudaGetLastError();
   if (err != cudaSuccess) {
@@ -405,25 +444,49 @@ extern "C" int segnn_edge_layer_bwd(int pass, const float* pos, const float* mas
                                     const float* w2t_vs, const float* w2t_sv, const float* w2t_vv, const float* bn_a,
                                     const float* bn_b, const float* bn_c, const float* dagg, float* dout,
                                     float* dw2_ss, float* dw2_vs, float* dw2_sv, float* dw2_vv, float* db2,
-                                    float* dwe_partial, segnn_stream_t stream) {
+                                    float* dwe_partial, float* workspace, segnn_stream_t stream) {
   SEGNN_CHECK_ARG(pass == 0 || pass == 1, "pass must be 0 (dP + weight gradients) or 1 (dQ)");
   SEGNN_CHECK_ARG(B >= 0 && N >= 1 && n >= 1, "bad sizes");
   if (B == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(pos && mass && p && q && w_edge1 && w2_ss && w2_vs && w2_sv && w2_vv && b2 && w2t_ss && w2t_vs &&
                       w2t_sv && w2t_vv && bn_a && bn_b && bn_c && dagg && dout,
                   "null pointer");
-  SEGNN_CHECK_ARG(pass == 1 || (dw2_ss && dw2_vs && dw2_sv && dw2_vv && db2 && dwe_partial),
-                  "pass 0 needs the weight-gradient outputs");
+  SEGNN_CHECK_ARG(pass == 1 || (dw2_ss && dw2_vs && dw2_sv && dw2_vv && db2 && dwe_partial && workspace),
+                  "pass 0 needs the weight-gradient outputs and the workspace");
   const int64_t nodes64 = (int64_t)B * N;
   SEGNN_CHECK_ARG(nodes64 <= 0x7fffffff, "too many nodes");
+  if (n > 96) {
+    set_error("segnn_edge_layer_bwd: hidden multiplicity n=%d > 96 is not built", n);
+    return SEGNN_E_UNSUPPORTED;
+  }
   EdgeBwdArgs a{pos, mass, p, q, w_edge1, w2_ss, w2_vs, w2_sv, w2_vv, b2, w2t_ss, w2t_vs, w2t_sv, w2t_vv,
-                bn_a, bn_b, bn_c, dagg, dout, dw2_ss, dw2_vs, dw2_sv, dw2_vv, db2, dwe_partial, (int)nodes64, N, n};
+                bn_a, bn_b, bn_c, dagg, dout, workspace, dwe_partial, (int)nodes64, N, n};
   cudaStream_t s = (cudaStream_t)stream;
-#define SEGNN_BWD_CASE(NT_) return pass == 0 ? launch_bwd<NT_, 0>(a, s) : launch_bwd<NT_, 1>(a, s)
+  // slab k belongs to the thread group whose first stationary node is k: only the first min(groups, nodes) slabs are
+  // ever written, each location first by a store (no zero-fill needed), and only those are reduced
+  const int64_t groups = (int64_t)bwd_grid(nodes64) * kBG;
+  const int n_slabs = (int)(groups < nodes64 ? groups : nodes64);
+  const int64_t stride = (int64_t)6 * n * n + 2 * n;
+  int rc;
+#define SEGNN_BWD_CASE(NT_) rc = pass == 0 ? launch_bwd<NT_, 0>(a, s) : launch_bwd<NT_, 1>(a, s)
   if (n <= 32) SEGNN_BWD_CASE(32);
-  if (n <= 64) SEGNN_BWD_CASE(64);
-  if (n <= 96) SEGNN_BWD_CASE(96);
+  else if (n <= 64) SEGNN_BWD_CASE(64);
+  else SEGNN_BWD_CASE(96);
 #undef SEGNN_BWD_CASE
-  set_error("segnn_edge_layer_bwd: hidden multiplicity n=%d > 96 is not built", n);
-  return SEGNN_E_UNSUPPORTED;
+  if (rc != SEGNN_OK || pass == 1) return rc;
+  // fixed-order reduction of the per-group slabs into the gradient blocks
+  struct Seg { int64_t off, count; float* out; };
+  const Seg segs[5] = {{0, (int64_t)2 * n * n, dw2_ss}, {(int64_t)2 * n * n, (int64_t)2 * n * n, dw2_vs},
+                       {(int64_t)4 * n * n, (int64_t)n * n, dw2_sv}, {(int64_t)5 * n * n, (int64_t)n * n, dw2_vv},
+                       {(int64_t)6 * n * n, (int64_t)2 * n, db2}};
+  for (const Seg& sg : segs)
+    slab_reduce_kernel<<<(unsigned)((sg.count + 127) / 128), 128, 0, s>>>(workspace, n_slabs, stride, sg.off, sg.count,
+                                                                       sg.out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+extern "C" int64_t segnn_edge_layer_bwd_workspace(int B, int N, int n) {
+  if (B < 0 || N < 1 || n < 1 || n > 96) return -1;
+  return (int64_t)sizeof(float) * bwd_grid((int64_t)B * N) * kBG * ((int64_t)6 * n * n + 2 * n);
 }

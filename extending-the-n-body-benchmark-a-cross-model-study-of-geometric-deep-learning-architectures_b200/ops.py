@@ -336,7 +336,8 @@ def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_e
     dev = pos.device
     f = dict(dtype=torch.float32, device=dev)
     dP, dQ = torch.empty((nodes, 4, 3 * n), **f), torch.empty((nodes, 4, 3 * n), **f)
-    gz = torch.zeros(6 * n * n + 2 * n, **f)  # one fill for all atomically-accumulated gradient blocks
+    gz = torch.empty(6 * n * n + 2 * n, **f)  # written by the fixed-order slab reduction (no atomics)
+    ws = torch.empty(max(1, int(lib.segnn_edge_layer_bwd_workspace(batch_size, num_nodes, n)) // 4), **f)
     g = dict(ss=gz[: 2 * n * n].view(n, 2 * n), vs=gz[2 * n * n: 4 * n * n].view(n, 2 * n),
              sv=gz[4 * n * n: 5 * n * n].view(n, n), vv=gz[5 * n * n: 6 * n * n].view(n, n), b=gz[6 * n * n:])
     dwe_partial = torch.empty((nodes, 6 * n), **f)
@@ -352,8 +353,8 @@ def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_e
                                            _p(w2t["ss"]), _p(w2t["vs"]), _p(w2t["sv"]), _p(w2t["vv"]), _p(bn_a),
                                            _p(bn_b), _p(bn_c), _p(dagg), _p(dout), _p(g["ss"]),
                                            _p(g["vs"]), _p(g["sv"]), _p(g["vv"]), _p(g["b"]), _p(dwe_partial),
-                                           _stream()), "segnn_edge_layer_bwd")
-            _bump()
+                                           _p(ws), _stream()), "segnn_edge_layer_bwd")
+            _bump(1 if pas == 1 else 6)
         with torch.cuda.stream(side):  # pass 1 (dQ) is independent of pass 0 (dP, weight gradients): overlap them
             launch(1, dQ)
         launch(0, dP)

@@ -236,7 +236,7 @@ int segnn_node_gemm_wgrad(const float* x0, const float* x1, const float* dy0, co
 
 /* Backward of the fused edge layer (autograd of models/segnn/segnn.py:264-284 + the scatter-add): messages are
  * recomputed, nothing per-edge is stored.  pass 0: dout = dP [nodes][4][3n], message_layer_2 weight/bias gradients
- * (accumulated into caller-zeroed dw2_*, db2) and per-receiver w_edge1 gradient rows dwe_partial [nodes][6n];
+ * (written to dw2_*, db2 by a fixed-order reduction of per-thread-group slabs in `workspace`) and per-receiver w_edge1 gradient rows dwe_partial [nodes][6n];
  * pass 1: dout = dQ.  The gradient reaching every message of receiver i is bn_a*dagg_i + bn_b*m + bn_c
  * (bn_a, bn_b [2n], bn_c [n]): plain sum, eval BatchNorm or train-mode BatchNorm.  w2t_* are the transposes
  * ([out][in]) of the w2_* blocks. */
@@ -246,7 +246,12 @@ int segnn_edge_layer_bwd(int pass, const float* pos, const float* mass, int B, i
                          const float* w2t_vs, const float* w2t_sv, const float* w2t_vv, const float* bn_a,
                          const float* bn_b, const float* bn_c, const float* dagg, float* dout, float* dw2_ss,
                          float* dw2_vs, float* dw2_sv, float* dw2_vv, float* db2, float* dwe_partial,
-                         segnn_stream_t stream);
+                         float* workspace, segnn_stream_t stream);
+
+/* Bytes of `workspace` for pass 0 of segnn_edge_layer_bwd: one private slab of partial message_layer_2 weight
+ * gradients per thread group of the persistent grid, reduced in a fixed order (no atomics: the gradients are
+ * bit-identical from run to run).  The workspace needs no initialisation; pass 1 ignores it. */
+int64_t segnn_edge_layer_bwd_workspace(int B, int N, int n);
 
 /* Backward of the embedding (inputs carry no gradient): per-node contribution rows [nodes][7][n] to
  * (w_embed [6][n], bias [n]); reduce with segnn_colsum. */

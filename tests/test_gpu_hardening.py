@@ -128,3 +128,25 @@ def test_forward_is_bitwise_reproducible(H, B, N, repeats):
             first = m(g).clone()
             for _ in range(repeats):
                 assert torch.equal(m(g), first), mode
+
+
+@pytest.mark.parametrize("H,B,N", [(64, 4, 5), (192, 2, 20), (128, 1, 70)])
+def test_gradients_are_bitwise_reproducible(H, B, N):
+    """The backward kernels use no atomics (message_layer_2 weight gradients go through per-thread-group slabs and a
+    fixed-order reduction; every other reduction is a fixed-order column sum): identical bits on every run."""
+    _, m = _pair(H, 2, train=True)
+    pos, vel, mass = O.synthetic_system(B, N, seed=5)
+    y = torch.randn(B * N, 6).cuda()
+    g = _graph(pos, vel, mass, B, N)
+    runs = []
+    for _ in range(4):
+        m.zero_grad(set_to_none=True)
+        for mod in m.modules():  # same running statistics going in
+            if hasattr(mod, "running_mean"):
+                mod.running_mean.zero_()
+                mod.running_var.fill_(1.0)
+        S.target_common_loss(m(g), y).backward()
+        runs.append([p.grad.clone() for p in m.parameters()])
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert torch.equal(a, b)

@@ -74,6 +74,9 @@ PROTOTYPES = {
     "segnn_macros_group_collisions_workspace": (_c.c_int64, [_int, _int, _int]),
     "segnn_macros_group_collisions": (_int, [_ptr, _int, _int, _int, _int, _c.c_float, _ptr, _ptr, _ptr]),
     "segnn_knn_edge_index": (_int, [_ptr, _int, _int, _int, _int, _ptr, _ptr]),
+    "segnn_pack_weights_size": (_c.c_int64, [_int, _int]),
+    "segnn_pack_weights": (_int, [_int, _int, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_fold_batchnorm": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _c.c_float, _c.c_float, _ptr, _ptr, _ptr]),
     "segnn_instance_norm": (_int, [_ptr, _ptr, _int, _int, _ptr, _int, _ptr, _ptr, _c.c_float, _ptr, _ptr]),
 }
 

@@ -398,13 +398,28 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
   }  // persistent loop
 }
 
-// out[i] = sum over slabs (fixed order) of slabs[s * stride + offset + i]
-__global__ void slab_reduce_kernel(const float* __restrict__ slabs, int n_slabs, int64_t stride, int64_t offset,
-                                   int64_t count, float* __restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-    float acc = 0.f;
-    for (int sidx = 0; sidx < n_slabs; ++sidx) acc += slabs[sidx * stride + offset + i];
-    out[i] = acc;
+// Fixed-order sum of the slabs, all five gradient blocks in one launch: element i of a slab goes to the output block
+// whose [offset, offset + count) contains i.  Eight independent partial sums keep eight loads in flight per thread;
+// their association is fixed, so the result is bit-identical from run to run.
+struct SlabSegs {
+  int64_t off[6];
+  float* out[5];
+};
+__global__ void slab_reduce_kernel(const float* __restrict__ slabs, int n_slabs, int64_t stride, SlabSegs segs) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < stride; i += (int64_t)gridDim.x * blockDim.x) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* p = slabs + i;
+    int sidx = 0;
+    for (; sidx + 8 <= n_slabs; sidx += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += p[(int64_t)(sidx + k) * stride];
+    }
+    for (int k = 0; sidx < n_slabs; ++sidx, ++k) a[k] += p[(int64_t)sidx * stride];
+    const float acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    int seg = 0;
+#pragma unroll
+    for (int k = 1; k < 5; ++k) seg += i >= segs.off[k];
+    segs.out[seg][i - segs.off[seg]] = acc;
   }
 }
 
@@ -475,13 +490,12 @@ extern "C" int segnn_edge_layer_bwd(int pass, const float* pos, const float* mas
 #undef SEGNN_BWD_CASE
   if (rc != SEGNN_OK || pass == 1) return rc;
   // fixed-order reduction of the per-group slabs into the gradient blocks
-  struct Seg { int64_t off, count; float* out; };
-  const Seg segs[5] = {{0, (int64_t)2 * n * n, dw2_ss}, {(int64_t)2 * n * n, (int64_t)2 * n * n, dw2_vs},
-                       {(int64_t)4 * n * n, (int64_t)n * n, dw2_sv}, {(int64_t)5 * n * n, (int64_t)n * n, dw2_vv},
-                       {(int64_t)6 * n * n, (int64_t)2 * n, db2}};
-  for (const Seg& sg : segs)
-    slab_reduce_kernel<<<(unsigned)((sg.count + 127) / 128), 128, 0, s>>>(workspace, n_slabs, stride, sg.off, sg.count,
-                                                                       sg.out);
+  SlabSegs segs;
+  const int64_t nn = (int64_t)n * n;
+  segs.off[0] = 0; segs.off[1] = 2 * nn; segs.off[2] = 4 * nn; segs.off[3] = 5 * nn; segs.off[4] = 6 * nn;
+  segs.off[5] = stride;
+  segs.out[0] = dw2_ss; segs.out[1] = dw2_vs; segs.out[2] = dw2_sv; segs.out[3] = dw2_vv; segs.out[4] = db2;
+  slab_reduce_kernel<<<(unsigned)((stride + 127) / 128), 128, 0, s>>>(workspace, n_slabs, stride, segs);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

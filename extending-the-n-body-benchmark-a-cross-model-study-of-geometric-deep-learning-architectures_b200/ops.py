@@ -235,6 +235,49 @@ def counter_add(counter: torch.Tensor, delta: int):
 TC_MULTIPLICITIES = (32, 64, 96)
 
 
+PACK_MSG1, PACK_MSG2, PACK_UPDATE1, PACK_UPDATE2, PACK_POOL1, PACK_EMBED, PACK_HEAD = range(7)
+
+
+def pack_weights(kind: int, n: int, tp_weight: torch.Tensor, biases: Optional[torch.Tensor]) -> dict:
+    """segnn_pack_weights: the reference's flat ``tp.weight`` / ``biases`` -> the operand blocks of the kernels (views of
+    one buffer, same names and layouts as packing.pack_*)."""
+    w = _f32(tp_weight.detach(), "tp.weight")
+    b = None if biases is None else _f32(biases.detach(), "biases")
+    total = int(lib.segnn_pack_weights_size(kind, n))
+    out = torch.empty(total, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib.segnn_pack_weights(kind, n, _p(w), _p(b), _p(out), _stream()), "segnn_pack_weights")
+    _bump()
+    if kind == PACK_MSG1:
+        k = 6 * n * n
+        return dict(w_s=out[:k].view(n, 6 * n), w_v=out[k:2 * k].view(n, 6 * n), bias=out[2 * k:2 * k + 2 * n],
+                    w_edge=out[2 * k + 2 * n:])
+    if kind == PACK_MSG2:
+        a, c = 2 * n * n, n * n
+        return dict(ss=out[:a].view(n, 2 * n), vs=out[a:2 * a].view(n, 2 * n), sv=out[2 * a:2 * a + c].view(n, n),
+                    vv=out[2 * a + c:2 * a + 2 * c].view(n, n), b=out[2 * a + 2 * c:])
+    if kind in (PACK_UPDATE1, PACK_UPDATE2, PACK_POOL1):
+        rows = 2 * n if kind == PACK_UPDATE1 else n
+        cols = 2 * n if kind == PACK_UPDATE2 else 3 * n
+        k = rows * cols
+        return dict(w_s=out[:k].view(rows, cols), w_v=out[k:2 * k].view(rows, cols), bias=out[2 * k:])
+    if kind == PACK_EMBED:
+        return dict(w=out[:6 * n].view(6, n), bias=out[6 * n:])
+    return out.view(2, n, 2)
+
+
+def fold_batchnorm(weight, bias, running_mean, running_var, n: int, eps: float, degree: float):
+    """segnn_fold_batchnorm -> (mul [2n], add [n])."""
+    f = lambda t: _f32(t.detach(), "batchnorm")
+    mul = torch.empty(2 * n, dtype=torch.float32, device=weight.device)
+    add = torch.empty(n, dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        check(lib.segnn_fold_batchnorm(_p(f(weight)), _p(f(bias)), _p(f(running_mean)), _p(f(running_var)), n,
+                                       float(eps), float(degree), _p(mul), _p(add), _stream()), "segnn_fold_batchnorm")
+    _bump()
+    return mul, add
+
+
 def pack_w2_tc(w2: dict, n: int, operand: int = OPERAND_BF16) -> torch.Tensor:
     """message_layer_2 weight image for the tcgen05 kernel: [128 lanes][3n] 16-bit pairs (segnn_pack_w2_tc)."""
     nbytes = lib.segnn_pack_w2_tc(None, None, None, None, n, int(operand), None, None)
@@ -354,7 +397,7 @@ def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_e
                                            _p(bn_b), _p(bn_c), _p(dagg), _p(dout), _p(g["ss"]),
                                            _p(g["vs"]), _p(g["sv"]), _p(g["vv"]), _p(g["b"]), _p(dwe_partial),
                                            _p(ws), _stream()), "segnn_edge_layer_bwd")
-            _bump(1 if pas == 1 else 6)
+            _bump(1 if pas == 1 else 2)
         with torch.cuda.stream(side):  # pass 1 (dQ) is independent of pass 0 (dP, weight gradients): overlap them
             launch(1, dQ)
         launch(0, dP)

@@ -12,6 +12,35 @@ from .graph import infer_graph_shape
 from .irreps import Irreps, weight_balanced_irreps
 from .o3_building_blocks import BatchNorm, O3TensorProduct, O3TensorProductSwishGate
 
+def _pack_tp(kind: int, mod, n: int):
+    """Operand blocks of one tensor product: from the C ABI (segnn_pack_weights) for device parameters; host-resident
+    parameters (the CPU emulation tests of the kernel algebra) go through packing.py, the same layouts in torch."""
+    w, b = mod.tp.weight, mod.biases
+    if w.is_cuda:
+        return ops.pack_weights(kind, n, w, b)
+    f = lambda t: t.detach().to(torch.float32)
+    if kind == ops.PACK_MSG1:
+        return packing.pack_msg1(f(w), f(b), n)
+    if kind == ops.PACK_MSG2:
+        return packing.pack_msg2(f(w), f(b), n)
+    if kind == ops.PACK_UPDATE1:
+        return packing.pack_node_tp(f(w), f(b), 2, n, 2 * n)
+    if kind == ops.PACK_UPDATE2:
+        return packing.pack_node_tp(f(w), f(b), 1, n, n)
+    if kind == ops.PACK_POOL1:
+        return packing.pack_node_tp(f(w), f(b), 1, n, 2 * n)
+    if kind == ops.PACK_EMBED:
+        return packing.pack_embedding(f(w), f(b), n)
+    return packing.pack_head(f(w), n)
+
+
+def _fold_bn(bn, n: int, degree: float):
+    if bn.weight.is_cuda:
+        return ops.fold_batchnorm(bn.weight, bn.bias, bn.running_mean, bn.running_var, n, bn.eps, degree)
+    f = lambda t: t.detach().to(torch.float32)
+    return packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), n, bn.eps, degree)
+
+
 _MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16_TC, "fp16": ops.MODE_FP16_TC, "fp16p": ops.MODE_FP16_PACKED}
 _TC_MODES = (ops.MODE_BF16_TC, ops.MODE_FP16_TC, ops.MODE_FP16_PACKED)
 _FP16_OPERAND_MODES = ("fp16", "fp16p")
@@ -52,12 +81,12 @@ class SEGNNLayer(nn.Module):
     def pack(self, degree: int, eval_bn: bool = True, operand: int = 0) -> Dict[str, object]:
         n = self.n
         f = lambda t: t.detach().to(torch.float32)
-        out = dict(
-            msg1=packing.pack_msg1(f(self.message_layer_1.tp.weight), f(self.message_layer_1.biases), n),
-            msg2=packing.pack_msg2(f(self.message_layer_2.tp.weight), f(self.message_layer_2.biases), n),
-            upd1=packing.pack_node_tp(f(self.update_layer_1.tp.weight), f(self.update_layer_1.biases), 2, n, 2 * n),
-            upd2=packing.pack_node_tp(f(self.update_layer_2.tp.weight), f(self.update_layer_2.biases), 1, n, n),
-            bn_msg=(None, None), bn_feat=(None, None))
+        # inference: the operand blocks come from the C ABI itself (segnn_pack_weights); packing.py is its
+        # differentiable twin, used by the training path
+        pk_ = lambda kind, mod: _pack_tp(kind, mod, n)
+        out = dict(msg1=pk_(ops.PACK_MSG1, self.message_layer_1), msg2=pk_(ops.PACK_MSG2, self.message_layer_2),
+                   upd1=pk_(ops.PACK_UPDATE1, self.update_layer_1), upd2=pk_(ops.PACK_UPDATE2, self.update_layer_2),
+                   bn_msg=(None, None), bn_feat=(None, None))
         if out["msg2"]["ss"].is_cuda and n in ops.TC_MULTIPLICITIES and ops.tc_available():
             out["msg2"]["tc"] = ops.pack_w2_tc(out["msg2"], n, operand)
             for key in ("upd1", "upd2"):
@@ -86,12 +115,8 @@ class SEGNNLayer(nn.Module):
                 m1["wt_v_h"] = ops.pack_node_weight_tc((m1["w_v"][:, perm6] * half6).contiguous(), operand)
                 m1["bias_tc_h"] = (m1["bias_tc"] * half).contiguous()
         if eval_bn and self.message_norm is not None:
-            bn = self.message_norm
-            out["bn_msg"] = packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var), n,
-                                                   bn.eps, float(degree))
-            bn = self.feature_norm
-            out["bn_feat"] = packing.fold_batchnorm(f(bn.weight), f(bn.bias), f(bn.running_mean), f(bn.running_var),
-                                                    n, bn.eps, 1.0)
+            out["bn_msg"] = _fold_bn(self.message_norm, n, float(degree))
+            out["bn_feat"] = _fold_bn(self.feature_norm, n, 1.0)
         return out
 
     def run(self, w, mode: int, h, pos, mass, node_attr, batch_size: int, num_nodes: int):
@@ -207,10 +232,10 @@ class SEGNN(nn.Module):
             f = lambda t: t.detach().to(torch.float32)
             n = self.n
             self._packed = dict(
-                embed=packing.pack_embedding(f(self.embedding_layer.tp.weight), f(self.embedding_layer.biases), n),
+                embed=_pack_tp(ops.PACK_EMBED, self.embedding_layer, n),
                 layers=[layer.pack(degree, operand=operand) for layer in self.layers],
-                pool1=packing.pack_node_tp(f(self.pre_pool1.tp.weight), f(self.pre_pool1.biases), 1, n, 2 * n),
-                head=packing.pack_head(f(self.pre_pool2.tp.weight), n))
+                pool1=_pack_tp(ops.PACK_POOL1, self.pre_pool1, n),
+                head=_pack_tp(ops.PACK_HEAD, self.pre_pool2, n))
             if "tc" in self._packed["layers"][0]["msg2"]:
                 for name in ("w_s", "w_v"):  # (must not reuse `key`: it is stored as the cache key below)
                     self._packed["pool1"]["wt" + name[1:]] = ops.pack_node_weight_tc(self._packed["pool1"][name], operand)

@@ -368,6 +368,39 @@ int segnn_knn_edge_index(const double* loc, int B, int N, int dim, int k, int64_
 int segnn_instance_norm(const float* x, const int64_t* graph_ptr, int graphs, int dim, const int* blocks, int n_blocks,
                         const float* weight, const float* bias, float eps, float* out, segnn_stream_t stream);
 
+/* ---- weight packing: reference parameters -> kernel operand blocks ------------------------------------------ */
+
+/* Which O3TensorProduct of the SEGNN a flat `tp.weight` / `biases` pair belongs to (models/segnn/segnn.py:63-65,
+ * 104-106, 212-223).  Output layouts (fp32, concatenated in `out`):
+ *   MSG1     message_layer_1   w_s [n][6n] | w_v [n][6n] | bias [2n] | w_edge [6n]     (inputs of segnn_node_gemm*
+ *                              producing the hoisted projections P | Q, and of segnn_edge_layer_fwd)
+ *   MSG2     message_layer_2   ss [n][2n] | vs [n][2n] | sv [n][n] | vv [n][n] | b [2n]  (segnn_edge_layer_fwd / bwd,
+ *                              segnn_pack_w2_tc)
+ *   UPDATE1  update_layer_1    w_s [2n][3n] | w_v [2n][3n] | bias [2n]
+ *   UPDATE2  update_layer_2    w_s [n][2n]  | w_v [n][2n]  | bias [n]
+ *   POOL1    pre_pool1         w_s [n][3n]  | w_v [n][3n]  | bias [2n]                 (segnn_node_gemm* + segnn_tp_combine)
+ *   EMBED    embedding_layer   w [6][n] | bias [n]                                      (segnn_embed_fwd)
+ *   HEAD     pre_pool2         w_head [2][n][2] (no bias: pass NULL)                    (segnn_head_fwd)
+ * The constants folded in: Y_0 of the edge attribute, 1/sqrt(3) of the 1o x 1o -> 0e coupling (the net of e3nn's path
+ * weights and the reference's sqrt_k_correction, o3_building_blocks.py:150-162). */
+enum {
+  SEGNN_PACK_MSG1 = 0,
+  SEGNN_PACK_MSG2 = 1,
+  SEGNN_PACK_UPDATE1 = 2,
+  SEGNN_PACK_UPDATE2 = 3,
+  SEGNN_PACK_POOL1 = 4,
+  SEGNN_PACK_EMBED = 5,
+  SEGNN_PACK_HEAD = 6
+};
+int64_t segnn_pack_weights_size(int kind, int n); /* number of floats of `out`; -1 for an unknown kind */
+int segnn_pack_weights(int kind, int n, const float* tp_weight, const float* biases, float* out, segnn_stream_t stream);
+
+/* Eval-mode e3nn BatchNorm (models/segnn/segnn.py:233-235) folded to per-channel (mul [2n], add [n]): out_s = x_s *
+ * mul[:n] + add, out_v = x_v * mul[n:].  degree = N - 1 folds the BatchNorm of every message through the sum over the
+ * N - 1 senders (segnn_edge_layer_fwd's bn_mul / bn_add); degree = 1 is the feature norm (segnn_tp_combine). */
+int segnn_fold_batchnorm(const float* weight, const float* bias, const float* running_mean, const float* running_var,
+                         int n, float eps, float degree, float* mul, float* add, segnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

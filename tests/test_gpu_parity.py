@@ -591,3 +591,35 @@ def test_large_graph_tensor_core_mode_agrees_with_fp32_mode():
         perm = torch.randperm(N).cuda()
         out_p = m.forward_state(p[perm].contiguous(), v[perm].contiguous(), ms[perm].contiguous(), B, N)
         assert float((out_p - out[perm]).abs().max() / out.abs().max()) < 2e-2  # bf16 operands, different tile grouping
+
+
+@pytest.mark.parametrize("n", [8, 32, 96])
+def test_c_abi_weight_packing_matches_python_packing(n):
+    """segnn_pack_weights / segnn_fold_batchnorm (what a non-Python consumer of include/segnn_b200.h calls) against
+    packing.py, the differentiable re-layout the training path uses: same blocks, bit for bit."""
+    P, ops = S.packing, S.ops
+    gen = torch.Generator().manual_seed(n)
+    sizes = {ops.PACK_MSG1: (2, 2 * n, 2), ops.PACK_MSG2: (1, 2 * n, 0), ops.PACK_UPDATE1: (2, 2 * n, 0),
+             ops.PACK_UPDATE2: (1, n, 0), ops.PACK_POOL1: (1, 2 * n, 0)}
+    for kind, (nb, n0, extra) in sizes.items():
+        numel = nb * (2 * n * n0 + 2 * n * n) + extra * (n0 + n)
+        w = torch.randn(numel, generator=gen).cuda()
+        b = torch.randn(n0, generator=gen).cuda()
+        got = ops.pack_weights(kind, n, w, b)
+        ref = {ops.PACK_MSG1: lambda: P.pack_msg1(w, b, n), ops.PACK_MSG2: lambda: P.pack_msg2(w, b, n),
+               ops.PACK_UPDATE1: lambda: P.pack_node_tp(w, b, 2, n, 2 * n),
+               ops.PACK_UPDATE2: lambda: P.pack_node_tp(w, b, 1, n, n),
+               ops.PACK_POOL1: lambda: P.pack_node_tp(w, b, 1, n, 2 * n)}[kind]()
+        assert set(got) == set(ref)
+        for k in ref:
+            assert got[k].shape == ref[k].shape and torch.equal(got[k], ref[k]), (kind, k)
+    w, b = torch.randn(6 * n, generator=gen).cuda(), torch.randn(n, generator=gen).cuda()
+    got, ref = ops.pack_weights(ops.PACK_EMBED, n, w, b), P.pack_embedding(w, b, n)
+    assert torch.equal(got["w"], ref["w"]) and torch.equal(got["bias"], ref["bias"])
+    w = torch.randn(4 * n, generator=gen).cuda()
+    assert torch.equal(ops.pack_weights(ops.PACK_HEAD, n, w, None), P.pack_head(w, n))
+    bn = [torch.rand(2 * n, generator=gen).cuda() + 0.5, torch.randn(n, generator=gen).cuda(),
+          torch.randn(n, generator=gen).cuda(), torch.rand(2 * n, generator=gen).cuda() + 0.5]
+    mul, add = ops.fold_batchnorm(*bn, n, 1e-5, 7.0)
+    rmul, radd = P.fold_batchnorm(*bn, n, 1e-5, 7.0)
+    assert torch.allclose(mul, rmul, rtol=2e-6) and torch.allclose(add, radd, rtol=1e-5, atol=1e-6)

@@ -238,7 +238,28 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
     if (act) {
       // ---- phase 3b (pass 0): message_layer_2 weight gradients, output column w ---------------------------------
       if (PASS == 0) {
+        // the slab's current partial sums of rows u0 .. u0 + 3 are fetched one iteration ahead (software pipeline), so
+        // their L2 latency is covered by the 256 FMAs of the previous iteration; zero on the first visit of the slab
+        float nxt[24];
+        auto fetch = [&](int u0) {
+#pragma unroll
+          for (int uu = 0; uu < 4; ++uu) {
+            const int u = u0 + uu;
+            const bool ld = !first_block && u < n;
+            nxt[uu * 6 + 0] = ld ? s_ss[(int64_t)u * 2 * n + w] : 0.f;
+            nxt[uu * 6 + 1] = ld ? s_ss[(int64_t)u * 2 * n + n + w] : 0.f;
+            nxt[uu * 6 + 2] = ld ? s_vs[(int64_t)u * 2 * n + w] : 0.f;
+            nxt[uu * 6 + 3] = ld ? s_vs[(int64_t)u * 2 * n + n + w] : 0.f;
+            nxt[uu * 6 + 4] = ld ? s_sv[(int64_t)u * n + w] : 0.f;
+            nxt[uu * 6 + 5] = ld ? s_vv[(int64_t)u * n + w] : 0.f;
+          }
+        };
+        fetch(0);
         for (int u0 = 0; u0 < n; u0 += 4) {
+          float cur[24];
+#pragma unroll
+          for (int k = 0; k < 24; ++k) cur[k] = nxt[k];
+          if (u0 + 4 < n) fetch(u0 + 4);
           float g_ss_s[4] = {0.f, 0.f, 0.f, 0.f}, g_ss_g[4] = {0.f, 0.f, 0.f, 0.f}, g_vs_s[4] = {0.f, 0.f, 0.f, 0.f},
                 g_vs_g[4] = {0.f, 0.f, 0.f, 0.f}, g_sv[4] = {0.f, 0.f, 0.f, 0.f}, g_vv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -266,23 +287,13 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
 #pragma unroll
           for (int uu = 0; uu < 4; ++uu) {
             const int u = u0 + uu;
-            if (u < n) {
-              // private slab, plain read-modify-write: only this thread ever touches these addresses
-              if (first_block) {
-                s_ss[(int64_t)u * 2 * n + w] = g_ss_s[uu];
-                s_ss[(int64_t)u * 2 * n + n + w] = g_ss_g[uu];
-                s_vs[(int64_t)u * 2 * n + w] = g_vs_s[uu];
-                s_vs[(int64_t)u * 2 * n + n + w] = g_vs_g[uu];
-                s_sv[(int64_t)u * n + w] = g_sv[uu];
-                s_vv[(int64_t)u * n + w] = g_vv[uu];
-              } else {
-                s_ss[(int64_t)u * 2 * n + w] += g_ss_s[uu];
-                s_ss[(int64_t)u * 2 * n + n + w] += g_ss_g[uu];
-                s_vs[(int64_t)u * 2 * n + w] += g_vs_s[uu];
-                s_vs[(int64_t)u * 2 * n + n + w] += g_vs_g[uu];
-                s_sv[(int64_t)u * n + w] += g_sv[uu];
-                s_vv[(int64_t)u * n + w] += g_vv[uu];
-              }
+            if (u < n) {  // private slab: only this thread ever touches these addresses
+              s_ss[(int64_t)u * 2 * n + w] = cur[uu * 6 + 0] + g_ss_s[uu];
+              s_ss[(int64_t)u * 2 * n + n + w] = cur[uu * 6 + 1] + g_ss_g[uu];
+              s_vs[(int64_t)u * 2 * n + w] = cur[uu * 6 + 2] + g_vs_s[uu];
+              s_vs[(int64_t)u * 2 * n + n + w] = cur[uu * 6 + 3] + g_vs_g[uu];
+              s_sv[(int64_t)u * n + w] = cur[uu * 6 + 4] + g_sv[uu];
+              s_vv[(int64_t)u * n + w] = cur[uu * 6 + 5] + g_vv[uu];
             }
           }
         }

@@ -268,11 +268,12 @@ def pack_weights(kind: int, n: int, tp_weight: torch.Tensor, biases: Optional[to
 
 def fold_batchnorm(weight, bias, running_mean, running_var, n: int, eps: float, degree: float):
     """segnn_fold_batchnorm -> (mul [2n], add [n])."""
-    f = lambda t: _f32(t.detach(), "batchnorm")
+    # (keep the fp32 copies referenced until the launch: a temporary freed early could be handed out again)
+    w32, b32, rm32, rv32 = [_f32(t.detach(), "batchnorm") for t in (weight, bias, running_mean, running_var)]
     mul = torch.empty(2 * n, dtype=torch.float32, device=weight.device)
     add = torch.empty(n, dtype=torch.float32, device=weight.device)
     with torch.cuda.device(weight.device):
-        check(lib.segnn_fold_batchnorm(_p(f(weight)), _p(f(bias)), _p(f(running_mean)), _p(f(running_var)), n,
+        check(lib.segnn_fold_batchnorm(_p(w32), _p(b32), _p(rm32), _p(rv32), n,
                                        float(eps), float(degree), _p(mul), _p(add), _stream()), "segnn_fold_batchnorm")
     _bump()
     return mul, add

@@ -72,7 +72,8 @@ def test_o3_transform(B, N):
 
 
 @pytest.mark.parametrize("H,L,B,N", [(64, 4, 100, 5), (192, 6, 64, 5), (192, 6, 2, 100), (128, 2, 1, 37),
-                                       (50, 2, 3, 9), (64, 1, 1, 2), (192, 6, 3, 6), (128, 3, 2, 38), (64, 2, 5, 12)])
+                                       (50, 2, 3, 9), (64, 1, 1, 2), (192, 6, 3, 6), (128, 3, 2, 38), (64, 2, 5, 12),
+                                       (64, 2, 1, 300), (192, 2, 1, 300)])
 def test_segnn_per_layer_parity(H, L, B, N):
     om, m = make_pair(H, L, seed=H + N)
     pos, vel, mass = O.synthetic_system(B, N, seed=5)
@@ -84,9 +85,14 @@ def test_segnn_per_layer_parity(H, L, B, N):
             out, layers = m(gpu_graph(pos, vel, mass, B, N), return_layers=True)
             print(f"[{mode}] H={H} N={N}: per-layer rel err", [f"{rel(a, b):.2e}" for a, b in zip(layers, ref_layers)],
                   f"out {rel(out, ref):.2e}")
+            # 16-bit operand rounding is coherent across the N - 1 messages of a receiver, so its error grows like
+            # sqrt(N): the per-mode figures are for N <= 100; at N = 300 the fp16 modes measure
+            # 3.2e-3 .. 4.2e-3 (held to 6e-3, inside north_star's 2e-2) and bf16 1.3e-2 .. 2.5e-2 (held to 4e-2, which
+            # is why graphs with N > 100 run the fp16 modes)
+            tol = TOL[mode] if N <= 100 or mode == "fp32" else (4e-2 if mode == "bf16" else 6e-3)
             for i, (a, b) in enumerate(zip(layers, ref_layers)):
-                assert rel(a, b) < TOL[mode], f"{mode} layer {i}: {rel(a, b)}"
-            assert rel(out, ref) < TOL[mode], f"{mode} output: {rel(out, ref)}"
+                assert rel(a, b) < tol, f"{mode} layer {i}: {rel(a, b)}"
+            assert rel(out, ref) < tol, f"{mode} output: {rel(out, ref)}"
 
 
 def test_packed_half_mode_refuses_odd_graph_size():
@@ -281,7 +287,7 @@ def _grad_case(H, L, B, N, bn_train, seed=0):
 
 
 @pytest.mark.parametrize("H,L,B,N,bn_train", [(64, 2, 4, 5, True), (64, 2, 4, 5, False), (192, 1, 2, 20, True),
-                                                (128, 2, 1, 33, True), (50, 1, 3, 6, True)])
+                                                (128, 2, 1, 33, True), (50, 1, 3, 6, True), (64, 1, 1, 200, True)])
 def test_training_gradients_match_oracle(H, L, B, N, bn_train):
     """fp32 kernels vs float64 autograd: prediction 1e-5 (north_star fp32 tolerance); gradients within 1e-4 of each
     parameter's max-norm plus 1e-5 of the largest gradient in the model. The second term covers parameters that sit

@@ -272,6 +272,8 @@ def measure_training(S, dev, world, rank, dist, cpu_baseline):
         g = S.GraphBatch(pos=p4.reshape(-1, 3).to(dev), vel=v4.reshape(-1, 3).to(dev), mass=c4.reshape(-1, 1).to(dev),
                          num_graphs=1, n_nodes=N4)
         y4 = torch.randn(N4, 6, device=dev)
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)  # peak of THIS configuration, not of the rollout workload before it
         times = []
         for i in range(3):
             m4.zero_grad(set_to_none=True)

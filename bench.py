@@ -479,7 +479,9 @@ def main():
         model.eval()
         configs["cfg5_train_mode_batchnorm_rollout"] = {
             "config": f"{B} x N={N}, 6 layers hidden 192, train-mode (batch-statistic) BatchNorm as in "
-                      "trainer.run_self_feed; fp32 kernels + deterministic float64 statistics",
+                      "trainer.run_self_feed; " + ("tcgen05 kernels (fp16p, K3 emits the message moments)" if
+                                                   mode == "fp16p" else "fp32 kernels") +
+                      " + deterministic float64 statistics",
             "ms_per_step": tb_ms, "particle_steps_per_s": B * N / (tb_ms * 1e-3)}
         # cfg1: 4 layers hidden 64, 100 x 5 bodies, 100-step rollout (the reference's CPU-runnable case)
         torch.manual_seed(0)

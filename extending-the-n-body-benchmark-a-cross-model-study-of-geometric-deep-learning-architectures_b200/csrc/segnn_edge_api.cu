@@ -12,7 +12,7 @@ int edge_layer_tc(const float* pos, const float* mass, int B, int N, int n, cons
                   cudaStream_t stream);
 int edge_layer_h2(const float* pos, const float* mass, int B, int N, int n, const void* pp, const void* qq,
                   const float* w_edge1, const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add,
-                  float* agg, cudaStream_t stream);
+                  float* agg, float* moments, cudaStream_t stream);
 int64_t pack_w2_tc(const float* ss, const float* vs, const float* sv, const float* vv, int n, int half, void* out,
                    cudaStream_t stream);
 }  // namespace segnn
@@ -43,9 +43,10 @@ int segnn_edge_layer_fwd(int mode, const float* pos, const float* mass, int B, i
   }
   if (mode == SEGNN_MODE_FP16_PACKED) {
     SEGNN_CHECK_ARG(w2_tc != nullptr, "tensor-core mode needs the packed weight image (segnn_pack_w2_tc, fp16)");
-    SEGNN_CHECK_ARG(moments == nullptr, "tensor-core mode does not emit train-mode moments");
     SEGNN_CHECK_ARG(N >= 2, "tensor-core mode needs N >= 2");
-    return edge_layer_h2(pos, mass, B, N, n, p, q, w_edge1, b2, w2_tc, bn_mul, bn_add, agg_out, (cudaStream_t)stream);
+    // the packed-half kernel also emits the train-mode BatchNorm moments (second template instance)
+    return edge_layer_h2(pos, mass, B, N, n, p, q, w_edge1, b2, w2_tc, bn_mul, bn_add, agg_out, moments,
+                         (cudaStream_t)stream);
   }
   set_error("segnn_edge_layer_fwd: unknown mode %d", mode);
   return SEGNN_E_INVALID;

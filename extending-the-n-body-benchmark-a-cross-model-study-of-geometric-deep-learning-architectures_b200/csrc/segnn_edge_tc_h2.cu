@@ -66,13 +66,14 @@ __device__ __forceinline__ uint32_t h2bc(float x) {  // (x, x) as fp16 pair
   return d;
 }
 
-template <int NMUL>
+template <int NMUL, bool MOMENTS>
 __global__ void __launch_bounds__(kWarps * 32, 1)
     edge_layer_h2_kernel(const float* __restrict__ pos, const float* __restrict__ mass, int B, int N,
                          const uint32_t* __restrict__ pp, const uint32_t* __restrict__ qq,
                          const float* __restrict__ w_edge1, const float* __restrict__ b2,
                          const uint32_t* __restrict__ w2_tc, const float* __restrict__ bn_mul,
-                         const float* __restrict__ bn_add, float* __restrict__ agg, int* __restrict__ err_flag) {
+                         const float* __restrict__ bn_add, float* __restrict__ agg, float* __restrict__ moments,
+                         int* __restrict__ err_flag) {
   constexpr int n = NMUL;
   constexpr int NW = n / 32;
   static_assert(NW >= 1 && NW <= 3, "warp % 4 == 3 hosts the MMA / scalar-producer warps");
@@ -358,10 +359,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
       add_s = bn_add[w];
     }
     float2 acc[2][4];  // [rl][component]: two partial sums (even / odd senders)
+    // MOMENTS (train-mode BatchNorm statistics, trainer.py:373 evaluates with batch statistics): per receiver the sums
+    // over its senders of m_s^2 and |m_v|^2 of the raw messages, [rl][scalar / vector]
+    float2 m2[2][2];
 #pragma unroll
-    for (int rl = 0; rl < 2; ++rl)
+    for (int rl = 0; rl < 2; ++rl) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[rl][c] = make_float2(0.f, 0.f);
+      m2[rl][0] = m2[rl][1] = make_float2(0.f, 0.f);
+    }
 #pragma unroll 1
     for (TileCursor cur{(int)blockIdx.x, 0, 0u, 0, 0}; cur.item < items; advance(cur)) {
       const uint32_t t = cur.t;
@@ -398,10 +404,23 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
             const float2 ms = __ffma2_rn(ys, ts, ys);
             const float2 g1 = __ffma2_rn(va, tg, va);
             const float2 t1 = u2f2(d[2][j], d[2][j + 1]);
-            acc[rl][0] = __ffma2_rn(va, ms, acc[rl][0]);
-            acc[rl][1] = __ffma2_rn(g1, __ffma2_rn(ax, t1, u2f2(d[3][j], d[3][j + 1])), acc[rl][1]);
-            acc[rl][2] = __ffma2_rn(g1, __ffma2_rn(ay, t1, u2f2(d[4][j], d[4][j + 1])), acc[rl][2]);
-            acc[rl][3] = __ffma2_rn(g1, __ffma2_rn(az, t1, u2f2(d[5][j], d[5][j + 1])), acc[rl][3]);
+            if (MOMENTS) {
+              const float2 msv = __fmul2_rn(va, ms);
+              const float2 mx = __fmul2_rn(g1, __ffma2_rn(ax, t1, u2f2(d[3][j], d[3][j + 1])));
+              const float2 my = __fmul2_rn(g1, __ffma2_rn(ay, t1, u2f2(d[4][j], d[4][j + 1])));
+              const float2 mz = __fmul2_rn(g1, __ffma2_rn(az, t1, u2f2(d[5][j], d[5][j + 1])));
+              acc[rl][0] = __fadd2_rn(acc[rl][0], msv);
+              acc[rl][1] = __fadd2_rn(acc[rl][1], mx);
+              acc[rl][2] = __fadd2_rn(acc[rl][2], my);
+              acc[rl][3] = __fadd2_rn(acc[rl][3], mz);
+              m2[rl][0] = __ffma2_rn(msv, msv, m2[rl][0]);
+              m2[rl][1] = __ffma2_rn(mx, mx, __ffma2_rn(my, my, __ffma2_rn(mz, mz, m2[rl][1])));
+            } else {
+              acc[rl][0] = __ffma2_rn(va, ms, acc[rl][0]);
+              acc[rl][1] = __ffma2_rn(g1, __ffma2_rn(ax, t1, u2f2(d[3][j], d[3][j + 1])), acc[rl][1]);
+              acc[rl][2] = __ffma2_rn(g1, __ffma2_rn(ay, t1, u2f2(d[4][j], d[4][j + 1])), acc[rl][2]);
+              acc[rl][3] = __ffma2_rn(g1, __ffma2_rn(az, t1, u2f2(d[5][j], d[5][j + 1])), acc[rl][3]);
+            }
           }
         }
       }
@@ -418,9 +437,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
             o[n + w] = (acc[rl][1].x + acc[rl][1].y) * sc_v;
             o[2 * n + w] = (acc[rl][2].x + acc[rl][2].y) * sc_v;
             o[3 * n + w] = (acc[rl][3].x + acc[rl][3].y) * sc_v;
+            if (MOMENTS) {  // of the raw messages (before any BatchNorm affine), like segnn_edge_fp32.cu
+              float* mo = moments + (g * N + i0 + r) * 2 * n;
+              mo[w] = (m2[rl][0].x + m2[rl][0].y) * (kCSilu * kCSilu);
+              mo[n + w] = (m2[rl][1].x + m2[rl][1].y) * (0.25f * kCSig * kCSig);
+            }
           }
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[rl][c] = make_float2(0.f, 0.f);
+          m2[rl][0] = m2[rl][1] = make_float2(0.f, 0.f);
         }
       }
       if (warp == kGeoWarp) {  // geometry of tile t + kGeoAhead, positions of tile t + kGeoAhead + 1
@@ -593,14 +618,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   }
 }
 
-template <int NMUL>
+template <int NMUL, bool MOMENTS>
 static int launch_h2(const float* pos, const float* mass, int B, int N, const void* pp, const void* qq,
                      const float* w_edge1, const float* b2, const void* w2_tc, const float* bn_mul,
-                     const float* bn_add, float* agg, cudaStream_t stream) {
+                     const float* bn_add, float* agg, float* moments, cudaStream_t stream) {
   constexpr int threads = kWarps * 32;
   const size_t smem = 1024 + (size_t)5 * NMUL * 128 + (size_t)(2 * (kSend / 2) + kRecv / 2) * 4 * 3 * NMUL * 4 +
                       (size_t)kGeoSlots * (4 * kCols * 4 + 5 * kCols * 2) + 24 * sizeof(uint64_t) + 16;
-  auto kern = edge_layer_h2_kernel<NMUL>;
+  auto kern = edge_layer_h2_kernel<NMUL, MOMENTS>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) {
     set_error("edge_layer_h2: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
@@ -616,7 +641,7 @@ static int launch_h2(const float* pos, const float* mass, int B, int N, const vo
   }
   const unsigned grid = (unsigned)(items < sms ? items : sms);
   kern<<<grid, threads, smem, stream>>>(pos, mass, B, N, (const uint32_t*)pp, (const uint32_t*)qq, w_edge1, b2,
-                                        (const uint32_t*)w2_tc, bn_mul, bn_add, agg, nullptr);
+                                        (const uint32_t*)w2_tc, bn_mul, bn_add, agg, moments, nullptr);
   err = cudaGetLastError();
   if (err != cudaSuccess) {
     set_error("edge_layer_h2: launch: %s", cudaGetErrorString(err));
@@ -629,14 +654,21 @@ static int launch_h2(const float* pos, const float* mass, int B, int N, const vo
 
 int edge_layer_h2(const float* pos, const float* mass, int B, int N, int n, const void* pp, const void* qq,
                   const float* w_edge1, const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add,
-                  float* agg, cudaStream_t stream) {
+                  float* agg, float* moments, cudaStream_t stream) {
   if (N % 2 != 0) {
     set_error("edge_layer_h2: the packed-half mode needs an even graph size (sender pairs), got N=%d", N);
     return SEGNN_E_UNSUPPORTED;
   }
-  if (n == 32) return tc::launch_h2<32>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, stream);
-  if (n == 64) return tc::launch_h2<64>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, stream);
-  if (n == 96) return tc::launch_h2<96>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg, stream);
+#define SEGNN_H2_CASE(NM)                                                                                            \
+  if (n == NM)                                                                                                       \
+    return moments ? tc::launch_h2<NM, true>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg,       \
+                                             moments, stream)                                                        \
+                   : tc::launch_h2<NM, false>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg,      \
+                                              nullptr, stream);
+  SEGNN_H2_CASE(32)
+  SEGNN_H2_CASE(64)
+  SEGNN_H2_CASE(96)
+#undef SEGNN_H2_CASE
   set_error("edge_layer_h2: built for hidden multiplicity n in {32, 64, 96}, got n=%d", n);
   return SEGNN_E_UNSUPPORTED;
 }

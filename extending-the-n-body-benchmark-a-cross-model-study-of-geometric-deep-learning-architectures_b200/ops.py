@@ -445,9 +445,14 @@ def bn_forward_coeffs(bn, n: int, rows: float, deg: float, sums, sq, v_planes: i
                                       float(bn["momentum"]), int(training), int(update), _p(cols), _p(stats), _stream()),
               "segnn_bn_coeffs_fwd")
     _bump()
-    if not native and training and update:  # e.g. a .double() module: write the updated statistics back
-        rm.copy_(rm32)
-        rv.copy_(rv32)
+    if training and update:
+        if native:  # the kernel wrote through raw pointers: tell torch (SEGNN.packed() keys its eval-mode
+            #         folded-BatchNorm cache on the buffers' version counters)
+            torch.autograd.graph.increment_version(rm)
+            torch.autograd.graph.increment_version(rv)
+        else:  # e.g. a .double() module: write the updated statistics back
+            rm.copy_(rm32)
+            rv.copy_(rv32)
     return dict(mulcols=cols[0], addcols=cols[1], stats=stats)
 
 

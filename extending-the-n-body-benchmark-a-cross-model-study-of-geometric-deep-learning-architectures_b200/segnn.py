@@ -145,6 +145,38 @@ class SEGNNLayer(nn.Module):
         return ops.tp_combine(y2, node_attr, n, False, bias=u2["bias"], residual=h, bn_mul=w["bn_feat"][0],
                               bn_add=w["bn_feat"][1])
 
+    def run_batch_statistics(self, w, h, pos, mass, node_attr, batch_size: int, num_nodes: int,
+                             update_running_stats: bool = True):
+        """The layer with TRAIN-mode BatchNorm (batch statistics) on the tensor-core kernels, inference only: the
+        reference evaluates its rollouts with the module in training mode (trainer.py:373, 929-942), so this is what a
+        faithful `run_self_feed` runs. K3 (packed-half mode) returns the raw sums and the per-receiver moments of the
+        messages; statistics are deterministic float64 column sums, the affine is one `segnn_lincomb` pass."""
+        n = self.n
+        nodes, deg = batch_size * num_nodes, num_nodes - 1
+        m1 = w["msg1"]
+        p, q = ops.node_gemm_pair16(h, dict(wt_s=m1["wt_s_h"], wt_v=m1["wt_v_h"], operand=1), 6 * n, m1["bias_tc_h"],
+                                    3 * n, 3 * n)
+        agg, mom = ops.edge_layer(ops.MODE_FP16_PACKED, pos, mass, batch_size, num_nodes, n, p, q, m1["w_edge"],
+                                  w["msg2"], None, None, want_moments=True)
+
+        def bn_dict(bn):
+            return dict(weight=bn.weight.detach().float(), bias=bn.bias.detach().float(), running_mean=bn.running_mean,
+                        running_var=bn.running_var, eps=bn.eps, momentum=bn.momentum)
+        if self.message_norm is not None:
+            flat = agg.view(nodes, 4 * n)
+            st = ops.bn_forward_coeffs(bn_dict(self.message_norm), n, float(nodes * deg), float(deg), ops.colsum(flat),
+                                       ops.colsum(mom), 1, True, update_running_stats)
+            agg = ops.lincomb(flat, None, st["mulcols"], None, st["addcols"]).view(nodes, 4, n)
+        u1, u2 = w["upd1"], w["upd2"]
+        g1 = ops.tp_combine(ops.node_gemm_out16(h, agg, u1, 3 * n), node_attr, n, True, bias=u1["bias"])
+        pre = ops.tp_combine(ops.node_gemm_out16(g1, None, u2, 2 * n), node_attr, n, False, bias=u2["bias"], residual=h)
+        if self.feature_norm is None:
+            return pre
+        flat = pre.view(nodes, 4 * n)
+        st = ops.bn_forward_coeffs(bn_dict(self.feature_norm), n, float(nodes), 1.0, ops.colsum(flat),
+                                   ops.colsum(flat, None, 1), 3, True, update_running_stats)
+        return ops.lincomb(flat, None, st["mulcols"], None, st["addcols"]).view(nodes, 4, n)
+
     def forward(self, x, edge_index, edge_attr, node_attr, batch, additional_message_features=None, *, pos=None,
                 mass=None, num_graphs=None, n_nodes=None, mode="fp32"):
         """Reference signature (segnn.py:239-247) on e3nn-layout features. The graph is implicit: ``edge_index`` /
@@ -257,10 +289,12 @@ class SEGNN(nn.Module):
             if self._generic is None or self._generic.embed.instr.device != pos.device:
                 self._generic = GenericRunner(self, pos.device)
             return self._generic.forward(pos, vel, mass, batch_size, num_nodes, return_layers)
-        if needs_grad or bn_training:
+        mode = _MODES[self.compute_mode]
+        batch_stats_tc = (bn_training and not needs_grad and mode == ops.MODE_FP16_PACKED and num_nodes % 2 == 0
+                          and self.n in ops.TC_MULTIPLICITIES)
+        if (needs_grad or bn_training) and not batch_stats_tc:
             return self._forward_train(pos, vel, mass, batch_size, num_nodes, bn_training, needs_grad, return_layers)
         w = self.packed(num_nodes - 1)
-        mode = _MODES[self.compute_mode]
         n = self.n
         if mode in _TC_MODES and "tc" not in w["layers"][0]["msg2"]:
             raise RuntimeError(f"compute_mode='bf16'/'fp16' needs hidden multiplicity in {ops.TC_MULTIPLICITIES} "
@@ -270,7 +304,10 @@ class SEGNN(nn.Module):
         h = ops.embed(x_in, node_attr, w["embed"]["w"], w["embed"]["bias"], n)
         per_layer = [h]
         for layer, lw in zip(self.layers, w["layers"]):
-            h = layer.run(lw, mode, h, pos, mass, node_attr, batch_size, num_nodes)
+            if batch_stats_tc:  # train-mode BatchNorm without gradients: tensor-core kernels + batch statistics
+                h = layer.run_batch_statistics(lw, h, pos, mass, node_attr, batch_size, num_nodes)
+            else:
+                h = layer.run(lw, mode, h, pos, mass, node_attr, batch_size, num_nodes)
             per_layer.append(h)
         p1 = w["pool1"]
         y = ops.node_gemm_out16(h, None, p1, 3 * n) if mode in _TC_MODES else ops.node_gemm(h, None, p1, 3 * n)

@@ -155,7 +155,9 @@ int segnn_tp_combine_y16(const void* y, const float* node_attr, int nodes, int n
  *   both NULL => raw sum.
  * agg_out planar [nodes][4][n].
  * moments (may be NULL): [nodes][2n] per-receiver sums needed for train-mode batch statistics:
- *   (sum_j m_s[w]^2 , sum_j |m_v[w]|^2); the plain sums are agg itself when bn_mul == NULL. */
+ *   (sum_j m_s[w]^2 , sum_j |m_v[w]|^2) of the raw messages; the plain sums are agg itself when bn_mul == NULL.
+ *   Emitted by SEGNN_MODE_FP32 and SEGNN_MODE_FP16_PACKED (the reference evaluates rollouts with train-mode BatchNorm,
+ *   trainer.py:373,929-942); the other tensor-core modes refuse a non-NULL pointer. */
 int segnn_edge_layer_fwd(int mode, const float* pos, const float* mass, int B, int N, int n, const float* p,
                          const float* q, const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
                          const float* w2_vv, const float* b2, const void* w2_tc, const float* bn_mul,

@@ -44,7 +44,10 @@ struct EdgeBwdArgs {
   int nodes, N, n;
 };
 
-template <int NT, int PASS>
+// WG (pass 0 only): 2 = dP and the weight gradients in one sweep (large graphs: one recompute), 0 = dP / d(w_edge1)
+// only, 1 = weight gradients only.  Training-size graphs launch (0) on the main stream and (1) next to the dQ pass on
+// side streams: the slab read-modify-writes leave the critical dgrad chain.
+template <int NT, int PASS, int WG>
 __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int w = threadIdx.x, q = threadIdx.y;
@@ -55,7 +58,8 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
   float* gb = smem + (size_t)kBG * (kBE * 11 * NP) + q * (kBE * 8);  // [8][8]: ax, ay, az, valid, len, mm
 
   const int64_t slab_stride = (int64_t)6 * n * n + 2 * n;
-  float* slab = PASS == 0 ? a.slabs + ((int64_t)blockIdx.x * kBG + q) * slab_stride : nullptr;
+  constexpr bool kWeights = PASS == 0 && WG != 0, kData = WG != 1;
+  float* slab = kWeights ? a.slabs + ((int64_t)blockIdx.x * kBG + q) * slab_stride : nullptr;
   float* s_ss = slab;                       // [n][2n]
   float* s_vs = slab + (int64_t)2 * n * n;  // [n][2n]
   float* s_sv = slab + (int64_t)4 * n * n;  // [n][n]
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
         acc[e][5] = duz;
 #pragma unroll
         for (int c = 0; c < 6; ++c) db[(e * 6 + c) * NP + w] = acc[e][c];
-        if (PASS == 0) {
+        if (kWeights) {
           db2s += dys;
           db2g += dyg;
         }
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
 
     if (act) {
       // ---- phase 3b (pass 0): message_layer_2 weight gradients, output column w ---------------------------------
-      if (PASS == 0) {
+      if (kWeights) {
         // the slab's current partial sums of rows u0 .. u0 + 3 are fetched one iteration ahead (software pipeline), so
         // their L2 latency is covered by the 256 FMAs of the previous iteration; zero on the first visit of the slab
         float nxt[24];
@@ -299,6 +303,7 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
         }
         first_block = false;
       }
+      if (kData) {
       // ---- phase 4: gradients of the edge features (input channel = this thread) --------------------------------
       float dx[kBE][5];
 #pragma unroll
@@ -386,20 +391,25 @@ __global__ void __launch_bounds__(NT* kBG) edge_layer_bwd_kernel(const EdgeBwdAr
           dwe[5] += mm * dt;
         }
       }
+      }  // kData
     }
     bwd_group_barrier(1 + q, NT);
   }
 
   if (act) {
-    float* o = a.dout + r * 4 * n3;
+    if (kData) {
+      float* o = a.dout + r * 4 * n3;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int k = 0; k < 3; ++k) o[c * n3 + k * n + w] = dst[c][k];
-    if (PASS == 0) {
-      float* pw = a.dwe_partial + r * 6 * n;
+        for (int k = 0; k < 3; ++k) o[c * n3 + k * n + w] = dst[c][k];
+      if (PASS == 0) {
+        float* pw = a.dwe_partial + r * 6 * n;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) pw[c * n + w] = dwe[c];
+        for (int c = 0; c < 6; ++c) pw[c * n + w] = dwe[c];
+      }
+    }
+    if (kWeights) {
       s_b[w] = first_node ? db2s : s_b[w] + db2s;
       s_b[n + w] = first_node ? db2g : s_b[n + w] + db2g;
       first_node = false;
@@ -439,11 +449,11 @@ static inline unsigned bwd_grid(int64_t nodes) {
   return (unsigned)(want < 2 * 148 ? want : 2 * 148);
 }
 
-template <int NT, int PASS>
+template <int NT, int PASS, int WG>
 static int launch_bwd(const EdgeBwdArgs& args, cudaStream_t stream) {
   const int NP = (args.n + 3) & ~3;
   const size_t smem = sizeof(float) * ((size_t)kBG * kBE * 11 * NP + kBG * kBE * 8);
-  auto kern = edge_layer_bwd_kernel<NT, PASS>;
+  auto kern = edge_layer_bwd_kernel<NT, PASS, WG>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) {
     set_error("edge_layer_bwd: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(err));
@@ -471,14 +481,16 @@ extern "C" int segnn_edge_layer_bwd(int pass, const float* pos, const float* mas
                                     const float* bn_b, const float* bn_c, const float* dagg, float* dout,
                                     float* dw2_ss, float* dw2_vs, float* dw2_sv, float* dw2_vv, float* db2,
                                     float* dwe_partial, float* workspace, segnn_stream_t stream) {
-  SEGNN_CHECK_ARG(pass == 0 || pass == 1, "pass must be 0 (dP + weight gradients) or 1 (dQ)");
+  SEGNN_CHECK_ARG(pass >= 0 && pass <= 3,
+                  "pass must be 0 (dP + weight gradients), 1 (dQ), 2 (dP only) or 3 (weight gradients only)");
   SEGNN_CHECK_ARG(B >= 0 && N >= 1 && n >= 1, "bad sizes");
   if (B == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(pos && mass && p && q && w_edge1 && w2_ss && w2_vs && w2_sv && w2_vv && b2 && w2t_ss && w2t_vs &&
-                      w2t_sv && w2t_vv && bn_a && bn_b && bn_c && dagg && dout,
+                      w2t_sv && w2t_vv && bn_a && bn_b && bn_c && dagg && (dout || pass == 3),
                   "null pointer");
-  SEGNN_CHECK_ARG(pass == 1 || (dw2_ss && dw2_vs && dw2_sv && dw2_vv && db2 && dwe_partial && workspace),
-                  "pass 0 needs the weight-gradient outputs and the workspace");
+  SEGNN_CHECK_ARG((pass != 0 && pass != 3) || (dw2_ss && dw2_vs && dw2_sv && dw2_vv && db2 && workspace),
+                  "passes 0 and 3 need the weight-gradient outputs and the workspace");
+  SEGNN_CHECK_ARG((pass != 0 && pass != 2) || dwe_partial, "passes 0 and 2 need dwe_partial");
   const int64_t nodes64 = (int64_t)B * N;
   SEGNN_CHECK_ARG(nodes64 <= 0x7fffffff, "too many nodes");
   if (n > 96) {
@@ -494,12 +506,14 @@ extern "C" int segnn_edge_layer_bwd(int pass, const float* pos, const float* mas
   const int n_slabs = (int)(groups < nodes64 ? groups : nodes64);
   const int64_t stride = (int64_t)6 * n * n + 2 * n;
   int rc;
-#define SEGNN_BWD_CASE(NT_) rc = pass == 0 ? launch_bwd<NT_, 0>(a, s) : launch_bwd<NT_, 1>(a, s)
+#define SEGNN_BWD_CASE(NT_)                                                                       \
+  rc = pass == 0 ? launch_bwd<NT_, 0, 2>(a, s) : pass == 1 ? launch_bwd<NT_, 1, 0>(a, s)          \
+     : pass == 2 ? launch_bwd<NT_, 0, 0>(a, s) : launch_bwd<NT_, 0, 1>(a, s)
   if (n <= 32) SEGNN_BWD_CASE(32);
   else if (n <= 64) SEGNN_BWD_CASE(64);
   else SEGNN_BWD_CASE(96);
 #undef SEGNN_BWD_CASE
-  if (rc != SEGNN_OK || pass == 1) return rc;
+  if (rc != SEGNN_OK || pass == 1 || pass == 2) return rc;
   // fixed-order reduction of the per-group slabs into the gradient blocks
   SlabSegs segs;
   const int64_t nn = (int64_t)n * n;

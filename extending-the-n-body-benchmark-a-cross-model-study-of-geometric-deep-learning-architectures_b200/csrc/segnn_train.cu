@@ -40,6 +40,34 @@ __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ x
   }
 }
 
+// Few rows (training-size graphs): ONE launch.  Block = 32 columns x 32 row lanes; lane ry sums rows ry, ry + 32, ...
+// in float64 and the 32 lane sums are added in lane order: deterministic (fixed association), one pass over the rows with
+// all loads of a lane independent.  The training step of the README configuration makes ~190 column sums per step, each of
+// which was two ~4 us launches on the critical chain.
+__global__ void __launch_bounds__(1024) colsum_small(const float* __restrict__ x, const float* __restrict__ y,
+                                                   int64_t rows, int cols, int mode, float* __restrict__ out) {
+  __shared__ double red[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double acc = 0.0;
+  if (c < cols) {
+#pragma unroll 4
+    for (int64_t r = ry; r < rows; r += 32) {
+      const double v = (double)x[r * cols + c];
+      acc += mode == 0 ? v : (mode == 1 ? v * v : v * (double)y[r * cols + c]);
+    }
+  }
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    double s = red[0][cx];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) s += red[i][cx];
+    out[c] = (float)s;
+  }
+}
+constexpr int kColsumSmallParts = 32;  // up to 2048 rows take the single-launch path
+
 template <typename T>
 __global__ void colsum_stage2(const T* __restrict__ partial, int nparts, int cols, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,6 +413,11 @@ int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mod
   SEGNN_CHECK_ARG(x && workspace && (mode != 2 || y), "null pointer");
   const int64_t parts = (rows + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock;
   SEGNN_CHECK_ARG(parts <= 65535, "too many rows for one colsum call");
+  if (parts <= kColsumSmallParts) {
+    colsum_small<<<(cols + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(x, y, rows, cols, mode, out);
+    SEGNN_CHECK_LAUNCH();
+    return SEGNN_OK;
+  }
   dim3 grid((cols + 31) / 32, (unsigned)parts);
   double* partial = reinterpret_cast<double*>(workspace);
   colsum_stage1<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, rows, cols, mode, partial);

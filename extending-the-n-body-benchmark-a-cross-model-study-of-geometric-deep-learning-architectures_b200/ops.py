@@ -308,7 +308,7 @@ def colsum(x: torch.Tensor, y: Optional[torch.Tensor] = None, mode: int = 0) -> 
     ws = torch.empty(max(1, lib.segnn_colsum_workspace(rows, cols) // 8), dtype=torch.float64, device=x.device)
     with torch.cuda.device(x.device):
         check(lib.segnn_colsum(_p(x), _p(y), rows, cols, mode, _p(ws), _p(out), _stream()), "segnn_colsum")
-    _bump(2)
+    _bump(1 if rows <= 2048 else 2)  # up to 2048 rows: both reduction stages in one launch
     return out
 
 
@@ -373,6 +373,9 @@ def side_stream(device, k: int = 0) -> "torch.cuda.Stream":
     return _SIDE_STREAMS[key]
 
 
+_SPLIT_WGRAD_MAX_EDGES = 1 << 16  # below this the edge backward runs dP and the weight gradients as separate launches
+
+
 def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg):
     """Backward of the fused edge layer with recompute. Returns dP, dQ [nodes,4,3n], the message_layer_2 gradient
     blocks {ss, vs, sv, vv, b} and dw_edge1 [6n]."""
@@ -398,10 +401,20 @@ def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_e
                                            _p(bn_b), _p(bn_c), _p(dagg), _p(dout), _p(g["ss"]),
                                            _p(g["vs"]), _p(g["sv"]), _p(g["vv"]), _p(g["b"]), _p(dwe_partial),
                                            _p(ws), _stream()), "segnn_edge_layer_bwd")
-            _bump(1 if pas == 1 else 2)
+            _bump(2 if pas in (0, 3) else 1)
         with torch.cuda.stream(side):  # pass 1 (dQ) is independent of pass 0 (dP, weight gradients): overlap them
             launch(1, dQ)
-        launch(0, dP)
+        if nodes * (num_nodes - 1) <= _SPLIT_WGRAD_MAX_EDGES:
+            # training-size graphs: the GPU is far from full, so the weight gradients (slab read-modify-writes) get
+            # their own launch on a second side stream and leave the critical dP -> node-backward chain
+            side2 = side_stream(dev, 2)
+            side2.wait_stream(main)
+            with torch.cuda.stream(side2):
+                launch(3, None)
+            launch(2, dP)
+            main.wait_stream(side2)
+        else:
+            launch(0, dP)
         main.wait_stream(side)
     return dP, dQ, g, colsum(dwe_partial)
 

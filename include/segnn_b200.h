@@ -239,7 +239,9 @@ int segnn_node_gemm_wgrad(const float* x0, const float* x1, const float* dy0, co
 /* Backward of the fused edge layer (autograd of models/segnn/segnn.py:264-284 + the scatter-add): messages are
  * recomputed, nothing per-edge is stored.  pass 0: dout = dP [nodes][4][3n], message_layer_2 weight/bias gradients
  * (written to dw2_*, db2 by a fixed-order reduction of per-thread-group slabs in `workspace`) and per-receiver w_edge1 gradient rows dwe_partial [nodes][6n];
- * pass 1: dout = dQ.  The gradient reaching every message of receiver i is bn_a*dagg_i + bn_b*m + bn_c
+ * pass 1: dout = dQ; pass 2: dP and dwe_partial only, pass 3: the weight/bias gradients only (dout may be NULL) --
+ * training-size graphs run 2 on the main stream and 3 beside pass 1 on side streams, large graphs run 0 (one recompute).
+ * The gradient reaching every message of receiver i is bn_a*dagg_i + bn_b*m + bn_c
  * (bn_a, bn_b [2n], bn_c [n]): plain sum, eval BatchNorm or train-mode BatchNorm.  w2t_* are the transposes
  * ([out][in]) of the w2_* blocks. */
 int segnn_edge_layer_bwd(int pass, const float* pos, const float* mass, int B, int N, int n, const float* p,

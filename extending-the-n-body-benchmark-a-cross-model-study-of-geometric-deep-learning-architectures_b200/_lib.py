@@ -59,6 +59,11 @@ PROTOTYPES = {
     "segnn_generic_tp": (_int, [_ptr, _int, _ptr, _int, _c.c_int64, _ptr, _ptr, _int, _ptr, _ptr, _int, _ptr, _ptr]),
     "segnn_generic_tp_expand": (_int, [_ptr, _int, _ptr, _int, _c.c_int64, _ptr, _int, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_generic_tp_scatter": (_int, [_ptr, _c.c_int64, _int, _int, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_generic_tp_expand_ld": (_int, [_ptr, _int, _ptr, _int, _c.c_int64, _ptr, _int, _ptr, _int, _int, _c.c_int64, _ptr,
+                                          _ptr]),
+    "segnn_generic_tp_scatter_ld": (_int, [_ptr, _c.c_int64, _c.c_int64, _int, _int, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_gemm_tf32x3_workspace": (_c.c_int64, [_int, _int]),
+    "segnn_gemm_tf32x3": (_int, [_ptr, _c.c_int64, _ptr, _c.c_int64, _c.c_int64, _int, _int, _ptr, _c.c_int64, _ptr, _ptr]),
     "segnn_generic_hoisted_msg1": (_int, [_ptr, _int, _ptr, _int, _ptr, _int, _int, _int, _ptr, _int, _ptr, _int, _ptr, _int,
                                           _int, _ptr, _ptr, _ptr, _int, _ptr, _ptr]),
     "segnn_generic_gate": (_int, [_ptr, _c.c_int64, _int, _int, _int, _ptr, _ptr, _ptr]),

@@ -152,7 +152,8 @@ constexpr int kPathInts = 6;  // off1, mul1, dim1, off2, dim2, koff
 
 __global__ void generic_tp_expand_kernel(const float* __restrict__ x1, int d1, const float* __restrict__ x2, int d2,
                                          long long rows, const int* __restrict__ paths, int n_paths,
-                                         const float* __restrict__ cg, int dimo, int K, float* __restrict__ A) {
+                                         const float* __restrict__ cg, int dimo, int K, long long lda,
+                                         float* __restrict__ A) {
   const long long total = rows * K;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -177,13 +178,13 @@ __global__ void generic_tp_expand_kernel(const float* __restrict__ x1, int d1, c
     }
 #pragma unroll
     for (int k = 0; k < 5; ++k)
-      if (k < dimo) A[(row * dimo + k) * K + kc] = acc[k];
+      if (k < dimo) A[(row * dimo + k) * lda + kc] = acc[k];
   }
 }
 
 // out[row][offo + w * dimo + k] = Y[row * dimo + k][w] + bias[offo + w * dimo + k]
-__global__ void generic_tp_scatter_kernel(const float* __restrict__ Y, long long rows, int dimo, int mulo, int offo,
-                                          int dout, const float* __restrict__ bias, float* __restrict__ out) {
+__global__ void generic_tp_scatter_kernel(const float* __restrict__ Y, long long ldy, long long rows, int dimo, int mulo,
+                                          int offo, int dout, const float* __restrict__ bias, float* __restrict__ out) {
   const int blk = mulo * dimo;
   const long long total = rows * blk;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -191,7 +192,7 @@ __global__ void generic_tp_scatter_kernel(const float* __restrict__ Y, long long
     const long long row = idx / blk;
     const int c = (int)(idx - row * blk);
     const int w = c / dimo, k = c - w * dimo;
-    float v = Y[(row * dimo + k) * mulo + w];
+    float v = Y[(row * dimo + k) * ldy + w];
     if (bias != nullptr) v += bias[offo + c];
     out[row * dout + offo + c] = v;
   }
@@ -385,26 +386,39 @@ int segnn_generic_tp(const float* x1, int d1, const float* x2, int d2, int64_t r
   return SEGNN_OK;
 }
 
-int segnn_generic_tp_expand(const float* x1, int d1, const float* x2, int d2, int64_t rows, const int* paths,
-                            int n_paths, const float* cg, int dimo, int K, float* A, segnn_stream_t stream) {
-  SEGNN_CHECK_ARG(rows >= 0 && d1 >= 1 && d2 >= 1 && n_paths >= 1 && dimo >= 1 && dimo <= 5 && K >= 1, "bad sizes");
+int segnn_generic_tp_expand_ld(const float* x1, int d1, const float* x2, int d2, int64_t rows, const int* paths,
+                               int n_paths, const float* cg, int dimo, int K, int64_t lda, float* A,
+                               segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(rows >= 0 && d1 >= 1 && d2 >= 1 && n_paths >= 1 && dimo >= 1 && dimo <= 5 && K >= 1 && lda >= K,
+                  "bad sizes");
   if (rows == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(x1 && x2 && paths && cg && A, "null pointer");
   generic_tp_expand_kernel<<<generic_grid(rows * K), 256, 0, (cudaStream_t)stream>>>(x1, d1, x2, d2, rows, paths,
-                                                                                   n_paths, cg, dimo, K, A);
+                                                                                   n_paths, cg, dimo, K, lda, A);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_generic_tp_expand(const float* x1, int d1, const float* x2, int d2, int64_t rows, const int* paths,
+                            int n_paths, const float* cg, int dimo, int K, float* A, segnn_stream_t stream) {
+  return segnn_generic_tp_expand_ld(x1, d1, x2, d2, rows, paths, n_paths, cg, dimo, K, K, A, stream);
+}
+
+int segnn_generic_tp_scatter_ld(const float* Y, int64_t ldy, int64_t rows, int dimo, int mulo, int offo, int dout,
+                                const float* bias, float* out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(rows >= 0 && dimo >= 1 && mulo >= 1 && offo >= 0 && dout >= offo + mulo * dimo && ldy >= mulo,
+                  "bad sizes");
+  if (rows == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(Y && out, "null pointer");
+  generic_tp_scatter_kernel<<<generic_grid(rows * mulo * dimo), 256, 0, (cudaStream_t)stream>>>(
+      Y, ldy, rows, dimo, mulo, offo, dout, bias, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }
 
 int segnn_generic_tp_scatter(const float* Y, int64_t rows, int dimo, int mulo, int offo, int dout, const float* bias,
                              float* out, segnn_stream_t stream) {
-  SEGNN_CHECK_ARG(rows >= 0 && dimo >= 1 && mulo >= 1 && offo >= 0 && dout >= offo + mulo * dimo, "bad sizes");
-  if (rows == 0) return SEGNN_OK;
-  SEGNN_CHECK_ARG(Y && out, "null pointer");
-  generic_tp_scatter_kernel<<<generic_grid(rows * mulo * dimo), 256, 0, (cudaStream_t)stream>>>(Y, rows, dimo, mulo,
-                                                                                              offo, dout, bias, out);
-  SEGNN_CHECK_LAUNCH();
-  return SEGNN_OK;
+  return segnn_generic_tp_scatter_ld(Y, mulo, rows, dimo, mulo, offo, dout, bias, out, stream);
 }
 
 int segnn_generic_hoisted_msg1(const float* Y, int ydim, const float* attr, int d2, const float* add, int d_add, int B,

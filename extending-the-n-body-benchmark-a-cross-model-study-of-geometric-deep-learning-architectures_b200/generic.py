@@ -100,9 +100,10 @@ class TensorProductPlan:
     GEMM_CHUNK_BYTES = 2 << 30  # bound on the expanded operand A per chunk of rows
 
     def _run_gemm(self, x1, x2, w, bias, out):
-        """Per output irrep block: expansion kernel (coupling with x2 applied) -> plain fp32 library GEMM against the
-        stacked path weights -> scatter kernel into the e3nn column order. Same arithmetic as segnn_generic_tp, with
-        the weight contraction at GEMM speed instead of one thread per output."""
+        """Per output irrep block: expansion kernel (coupling with x2 applied) -> fp32-accurate tcgen05 GEMM
+        (segnn_gemm_tf32x3) against the stacked path weights -> scatter kernel into the e3nn column order. Same
+        arithmetic as segnn_generic_tp, with the weight contraction on the tensor cores instead of one thread per
+        output."""
         rows = x1.shape[0]
         if sum(b["mulo"] * b["dimo"] for b in self.blocks) != self.dout:
             out.zero_()  # output columns no path writes (none for the reference's products) are bias / 0
@@ -115,14 +116,20 @@ class TensorProductPlan:
             for r0 in range(0, rows, chunk):
                 r1 = min(rows, r0 + chunk)
                 n = r1 - r0
-                A = torch.empty((n * b["dimo"], b["K"]), dtype=torch.float32, device=x1.device)
+                # rows padded to a multiple of four floats: 128-bit accesses in the GEMM (padding is never read as data:
+                # the loader masks k >= K, the scatter reads mulo columns)
+                lda, ldy = (b["K"] + 3) & ~3, (b["mulo"] + 3) & ~3
+                A = torch.empty((n * b["dimo"], lda), dtype=torch.float32, device=x1.device)
+                Y = torch.empty((n * b["dimo"], ldy), dtype=torch.float32, device=x1.device)
                 with torch.cuda.device(x1.device):
-                    check(lib.segnn_generic_tp_expand(_p(x1[r0:r1]), self.d1, _p(x2[r0:r1]), self.d2, n, _p(b["paths"]),
-                                                      b["n_paths"], _p(b["cg"]), b["dimo"], b["K"], _p(A),
-                                                      ops._stream()), "segnn_generic_tp_expand")
-                    Y = torch.matmul(A, wcat)  # plain library SGEMM (fp32; TF32 stays off)
-                    check(lib.segnn_generic_tp_scatter(_p(Y), n, b["dimo"], b["mulo"], b["offo"], self.dout, _p(bias),
-                                                       _p(out[r0:r1]), ops._stream()), "segnn_generic_tp_scatter")
+                    check(lib.segnn_generic_tp_expand_ld(_p(x1[r0:r1]), self.d1, _p(x2[r0:r1]), self.d2, n,
+                                                         _p(b["paths"]), b["n_paths"], _p(b["cg"]), b["dimo"], b["K"],
+                                                         lda, _p(A), ops._stream()), "segnn_generic_tp_expand_ld")
+                    # the weight contraction: own tcgen05 GEMM, fp32-accurate (3xTF32), no library call
+                    ops.gemm_tf32x3(A[:, :b["K"]], wcat, out=Y[:, :b["mulo"]])
+                    check(lib.segnn_generic_tp_scatter_ld(_p(Y), ldy, n, b["dimo"], b["mulo"], b["offo"], self.dout,
+                                                          _p(bias), _p(out[r0:r1]), ops._stream()),
+                          "segnn_generic_tp_scatter_ld")
                 ops._bump(2)
         return out
 

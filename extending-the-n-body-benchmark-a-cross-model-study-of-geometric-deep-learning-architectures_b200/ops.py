@@ -11,7 +11,7 @@ from ._lib import (MODE_BF16_TC, MODE_FP16_PACKED, MODE_FP16_TC, MODE_FP32, OPER
                    lib)
 
 __all__ = ["edge_index", "edge_attr", "prep", "embed", "node_gemm", "node_gemm_out16", "node_gemm_pair16", "pack_node_weight_tc", "tp_combine", "edge_layer", "head",
-           "integrate", "counter_add", "launch_count", "MODE_FP32", "MODE_BF16_TC", "MODE_FP16_TC", "MODE_FP16_PACKED"]
+           "integrate", "counter_add", "launch_count", "gemm_tf32x3", "MODE_FP32", "MODE_BF16_TC", "MODE_FP16_TC", "MODE_FP16_PACKED"]
 
 _launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
 
@@ -291,6 +291,27 @@ def pack_w2_tc(w2: dict, n: int, operand: int = OPERAND_BF16) -> torch.Tensor:
     if rc < 0:
         check(int(rc), "segnn_pack_w2_tc")
     _bump()
+    return out
+
+
+def gemm_tf32x3(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = A @ B in fp32 accuracy on the tensor cores (segnn_gemm_tf32x3: tf32 hi/lo split, three MMAs per product).
+    ``a`` [M, K] and ``b`` [K, N] may be row-strided views (leading dimension = stride(0)); ``out`` likewise."""
+    if not (a.is_cuda and b.is_cuda):
+        raise RuntimeError("gemm_tf32x3 needs CUDA tensors (no CPU fallback)")
+    assert a.dtype == b.dtype == torch.float32 and a.dim() == b.dim() == 2 and a.shape[1] == b.shape[0]
+    assert a.stride(1) == 1 and b.stride(1) == 1, "row-major operands"
+    M, K = a.shape
+    N = b.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    ws = torch.empty(max(4, lib.segnn_gemm_tf32x3_workspace(K, N) // 4), dtype=torch.float32, device=a.device)
+    lda = a.stride(0) if M > 1 else max(K, a.stride(0))
+    with torch.cuda.device(a.device):
+        check(lib.segnn_gemm_tf32x3(_p(a), lda, _p(b), b.stride(0) if K > 1 else N, M, K, N, _p(out),
+                                    out.stride(0) if M > 1 else N, _p(ws), _stream()), "segnn_gemm_tf32x3")
+    _bump(2)
     return out
 
 

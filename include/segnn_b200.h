@@ -287,6 +287,23 @@ int segnn_generic_tp_expand(const float* x1, int d1, const float* x2, int d2, in
                             int n_paths, const float* cg, int dimo, int K, float* A, segnn_stream_t stream);
 int segnn_generic_tp_scatter(const float* Y, int64_t rows, int dimo, int mulo, int offo, int dout, const float* bias,
                              float* out, segnn_stream_t stream);
+/* The same two with explicit leading dimensions (lda >= K floats per row of A, ldy >= mulo floats per row of Y): rows
+ * padded to a multiple of four floats let segnn_gemm_tf32x3 use 128-bit accesses. */
+int segnn_generic_tp_expand_ld(const float* x1, int d1, const float* x2, int d2, int64_t rows, const int* paths,
+                               int n_paths, const float* cg, int dimo, int K, int64_t lda, float* A,
+                               segnn_stream_t stream);
+int segnn_generic_tp_scatter_ld(const float* Y, int64_t ldy, int64_t rows, int dimo, int mulo, int offo, int dout,
+                                const float* bias, float* out, segnn_stream_t stream);
+
+/* fp32-accurate GEMM on tcgen05 ("3xTF32"): C[M][N] = A[M][K] * B[K][N], row-major with leading dimensions lda, ldb,
+ * ldc (floats).  Every operand value is split into tf32 hi + lo parts and hi*hi + hi*lo + lo*hi is accumulated in fp32
+ * in TMEM (kind::tf32 MMAs), <= 2e-7 relative to a float64 product.  It is the weight contraction of the generic-irreps
+ * tensor products (o3_building_blocks.py:150-162 for arbitrary irreps, the lmax_h = 2 configuration), which round 1 ran
+ * as a library SGEMM.  workspace: segnn_gemm_tf32x3_workspace(K, N) bytes, 16-byte aligned (the swizzled hi / lo images
+ * of B, rebuilt by every call). */
+int64_t segnn_gemm_tf32x3_workspace(int K, int N);
+int segnn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int K, int N, float* C,
+                      int64_t ldc, float* workspace, segnn_stream_t stream);
 
 /* message_layer_1 (models/segnn/segnn.py:264-279) with its weight contraction hoisted to node level, for any hidden
  * irreps: Y [nodes][ydim] holds, for every (x_i or x_j) instruction, sum_u W[u][w] x[node][u, i] at yoff + w * dim1 + i

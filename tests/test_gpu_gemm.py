@@ -1,0 +1,45 @@
+"""segnn_gemm_tf32x3: the fp32-accurate tcgen05 GEMM of the generic-irreps tensor products, against float64 torch on
+ragged shapes (M not a multiple of 128, K not a multiple of 32 or 4, N below / above one 128-column block)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 1, 1), (5, 7, 3), (128, 32, 16), (300, 146, 73), (1000, 219, 73), (515, 146, 73),
+                                   (4097, 292, 146), (2000, 64, 200), (777, 500, 129), (20000, 219, 80)])
+def test_gemm_tf32x3_matches_float64(M, K, N):
+    import segnn_b200 as S
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g).cuda()
+    b = torch.randn(K, N, generator=g).cuda()
+    ref = a.double() @ b.double()
+    out = S.ops.gemm_tf32x3(a, b)
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    err32 = float(((a @ b).double() - ref).abs().max() / ref.abs().max())  # the library fp32 SGEMM, for scale
+    print(f"M={M} K={K} N={N}: max rel err {err:.2e} (library fp32 GEMM {err32:.2e})")
+    assert err < 4e-6
+    # strided views (padded leading dimensions, as the generic path passes them) and bit-identical repeats
+    lda, ldy = (K + 3) & ~3, (N + 3) & ~3
+    ap = torch.full((M, lda), float("nan")).cuda()
+    ap[:, :K] = a
+    yp = torch.zeros((M, ldy)).cuda()
+    S.ops.gemm_tf32x3(ap[:, :K], b, out=yp[:, :N])
+    assert torch.equal(yp[:, :N], out), "padding columns must not be read as data; result independent of strides"
+    assert float(yp[:, N:].abs().max() if ldy > N else 0.0) == 0.0, "nothing is written past N"
+    assert torch.equal(S.ops.gemm_tf32x3(a, b), out)
+
+
+def test_gemm_tf32x3_is_much_more_accurate_than_plain_tf32():
+    """The error compensation is what keeps the generic path inside the 1e-5 budget: a single tf32 product is ~1e-3."""
+    import segnn_b200 as S
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(512, 256, generator=g).cuda(), torch.randn(256, 96, generator=g).cuda()
+    ref = a.double() @ b.double()
+    out = S.ops.gemm_tf32x3(a, b)
+    trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    plain = trunc(a).double() @ trunc(b).double()
+    e3 = float((out.double() - ref).abs().max() / ref.abs().max())
+    e1 = float((plain - ref).abs().max() / ref.abs().max())
+    print(f"3xTF32 {e3:.2e} vs plain tf32 {e1:.2e}")
+    assert e3 < 4e-6 and e1 > 50 * e3

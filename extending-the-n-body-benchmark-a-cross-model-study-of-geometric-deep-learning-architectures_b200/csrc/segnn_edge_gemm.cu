@@ -1,0 +1,1015 @@
+// Large-graph form of the SEGNN edge layer (models/segnn/segnn.py:264-284 + the scatter-add of :205), forward and
+// backward, fp32-accurate on the tensor cores.  It exists for BASELINE configuration 4 (one N = 1000 fully connected
+// graph, ~1 M edges, forward + backward): the fused fp32 kernels (segnn_edge_fp32.cu, segnn_edge_bwd.cu) keep one thread
+// group per stationary node, which leaves a 1000-node graph at ~1 % of the tensor roofline.
+//
+// Formulation.  message_layer_1 stays hoisted to node level (P, Q: DESIGN section 3), so per edge only elementwise work
+// and the message_layer_2 contraction remain.  The edges of a chunk of graphs are enumerated as rows
+// row = (graph * N + receiver) * N + sender (the diagonal is kept and masked), and the contraction runs as plain GEMMs
+// over those rows with the 3xTF32 split (hi * hi + hi * lo + lo * hi in fp32 TMEM accumulators):
+//   E1   msg1_rows_kernel       P_i + Q_j, geometry, gate           -> XS [rows][2n] = (s', v'.a), XV [rows][3][n] = v'
+//   G1   segnn_gemm_tf32x3      Y  [rows][3n] = XS * Wcat [2n][3n]   (ys | yg | t1),  DV [3 rows][n] = XV * W_vv
+//   E2f  gate2_fwd_kernel       gate, sum over senders, moments     -> agg (forward ends here)
+//   E2b  gate2_bwd_kernel       dm = A dagg_i + B m + C, gate bwd   -> dY, dDV in place, bias-gradient rows
+//   G2   gemm_tn_tf32x3         dWcat = XS^T dY, dW_vv = XV^T dDV    (K = rows, split over the CTAs, partial sums in
+//                               TMEM, fixed-order reduction: bit-identical from run to run, no atomics)
+//   G3   segnn_gemm_tf32x3      dXS = dY * Wcat^T, dXV = dDV * W_vv^T
+//   E3   msg1_bwd_kernel<PASS>  gate / combine backward, sums over senders (dP, d w_edge1) and over receivers (dQ)
+// Per-edge tensors live in a caller-provided workspace for one chunk of graphs at a time (16 n floats per row), never
+// for the whole batch; every kernel streams them once at HBM speed, the GEMMs run on tcgen05.
+#include "segnn_common.cuh"
+
+namespace segnn {
+namespace eg {
+
+__device__ __forceinline__ float silu_gate_grad(float x) {
+  const float s = sigmoid_acc(x);
+  return kCSilu * s * (1.0f + x * (1.0f - s));
+}
+__device__ __forceinline__ float sig_gate_grad(float x) {
+  const float s = sigmoid_acc(x);
+  return kCSig * s * (1.0f - s);
+}
+
+constexpr int kRecv = 4;    // receivers per block of E1
+constexpr int kTileJ = 32;  // senders per geometry tile of E1
+constexpr int kSY = 4;      // row lanes (threadIdx.y) of the per-node kernels
+constexpr int kTileO = 256; // "other" nodes per geometry tile of the per-node kernels
+
+struct RowArgs {
+  const float *pos, *mass, *pp, *qq, *w_edge1;
+  int N, n;
+  int64_t node0;  // first node of the chunk
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// E1: rows of the message_layer_2 input.  block = (NT channels, 4 sender lanes), 4 receivers of one graph.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(96 * 4) msg1_rows_kernel(const RowArgs a, float* __restrict__ xs,
+                                                         float* __restrict__ xv) {
+  __shared__ float gs[kRecv][kTileJ][8];
+  const int w = threadIdx.x, y = threadIdx.y;
+  const int n = a.n, N = a.N, n3 = 3 * n;
+  const int bpg = (N + kRecv - 1) / kRecv;
+  const int64_t gl = blockIdx.x / bpg;
+  const int i0 = (int)(blockIdx.x - gl * bpg) * kRecv;
+  const int64_t base = a.node0 + gl * N;
+  const bool act = w < n;
+  const int tid = y * blockDim.x + w;
+
+  float st[kRecv][12];
+  float wd0s = 0.f, wd0g = 0.f, wm0s = 0.f, wm0g = 0.f, wd1 = 0.f, wm1 = 0.f;
+#pragma unroll
+  for (int r = 0; r < kRecv; ++r)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) st[r][k] = 0.f;
+  if (act) {
+#pragma unroll
+    for (int r = 0; r < kRecv; ++r) {
+      if (i0 + r < N) {
+        const float* sr = a.pp + (base + i0 + r) * 4 * n3;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) st[r][c * 3 + k] = sr[c * n3 + k * n + w];
+      }
+    }
+    wd0s = a.w_edge1[w];
+    wd0g = a.w_edge1[n + w];
+    wm0s = a.w_edge1[2 * n + w];
+    wm0g = a.w_edge1[3 * n + w];
+    wd1 = a.w_edge1[4 * n + w];
+    wm1 = a.w_edge1[5 * n + w];
+  }
+  for (int j0 = 0; j0 < N; j0 += kTileJ) {
+    __syncthreads();
+    if (tid < kRecv * kTileJ) {
+      const int r = tid / kTileJ, jj = tid % kTileJ;
+      const int i = min(i0 + r, N - 1), j = min(j0 + jj, N - 1);
+      const int64_t ni = base + i, nj = base + j;
+      float ux, uy, uz, len;
+      unit_vec(a.pos[nj * 3 + 0] - a.pos[ni * 3 + 0], a.pos[nj * 3 + 1] - a.pos[ni * 3 + 1],
+               a.pos[nj * 3 + 2] - a.pos[ni * 3 + 2], ux, uy, uz, len);
+      gs[r][jj][0] = kY1 * ux;
+      gs[r][jj][1] = kY1 * uy;
+      gs[r][jj][2] = kY1 * uz;
+      gs[r][jj][3] = len;
+      gs[r][jj][4] = a.mass[nj] * a.mass[ni];
+    }
+    __syncthreads();
+    if (!act) continue;
+    for (int jj = y; jj < kTileJ && j0 + jj < N; jj += blockDim.y) {
+      const int j = j0 + jj;
+      const float* qr = a.qq + (base + j) * 4 * n3;
+      float qv[12];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) qv[c * 3 + k] = qr[c * n3 + k * n + w];
+#pragma unroll
+      for (int r = 0; r < kRecv; ++r) {
+        if (i0 + r >= N) break;
+        const float ax = gs[r][jj][0], ay = gs[r][jj][1], az = gs[r][jj][2], len = gs[r][jj][3], mm = gs[r][jj][4];
+        float S[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) S[k] = st[r][k] + qv[k];
+        const float zs = S[0] + ax * S[3] + ay * S[6] + az * S[9] + len * wd0s + mm * wm0s;
+        const float zg = S[1] + ax * S[4] + ay * S[7] + az * S[10] + len * wd0g + mm * wm0g;
+        const float t = S[2] + len * wd1 + mm * wm1;
+        const float gg = sig_gate(zg);
+        const float vx = gg * (ax * t + S[5]), vy = gg * (ay * t + S[8]), vz = gg * (az * t + S[11]);
+        const int64_t row = (gl * N + i0 + r) * N + j;
+        float* xr = xs + row * 2 * n;
+        xr[w] = silu_gate(zs);
+        xr[n + w] = ax * vx + ay * vy + az * vz;
+        float* vr = xv + row * n3;
+        vr[w] = vx;
+        vr[n + w] = vy;
+        vr[2 * n + w] = vz;
+      }
+    }
+  }
+}
+
+// geometry of (stationary node, tile of other nodes) for the per-node kernels: (ax, ay, az, valid, len, mm)
+__device__ __forceinline__ void node_tile_geometry(const float* __restrict__ pos, const float* __restrict__ mass,
+                                                   int64_t base, int N, int ir, int o0, float sgn, float (*gs)[8],
+                                                   int tid, int nthreads) {
+  const float prx = pos[(base + ir) * 3 + 0], pry = pos[(base + ir) * 3 + 1], prz = pos[(base + ir) * 3 + 2];
+  const float mr = mass[base + ir];
+  for (int t = tid; t < kTileO; t += nthreads) {
+    const int oo = o0 + t;
+    const int64_t on = base + (oo < N ? oo : N - 1);
+    float ux, uy, uz, len;
+    unit_vec(sgn * (pos[on * 3 + 0] - prx), sgn * (pos[on * 3 + 1] - pry), sgn * (pos[on * 3 + 2] - prz), ux, uy, uz,
+             len);
+    gs[t][0] = kY1 * ux;
+    gs[t][1] = kY1 * uy;
+    gs[t][2] = kY1 * uz;
+    gs[t][3] = (oo < N && oo != ir) ? 1.0f : 0.0f;
+    gs[t][4] = len;
+    gs[t][5] = mass[on] * mr;
+  }
+}
+
+// fixed-order sum over the kSY row lanes of V per-thread values: red[y][v][x]; lane y == 0 returns the totals in vals
+template <int V>
+__device__ __forceinline__ void lane_reduce(float* red, float (&vals)[V], int w, int y, int NT) {
+#pragma unroll
+  for (int v = 0; v < V; ++v) red[(y * V + v) * NT + w] = vals[v];
+  __syncthreads();
+  if (y == 0) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float s = red[v * NT + w];
+      for (int yy = 1; yy < kSY; ++yy) s += red[(yy * V + v) * NT + w];
+      vals[v] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// E2f: gate of message_layer_2 + sum over senders (+ moments, folded eval BatchNorm).  block = one receiver.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(96 * kSY)
+    gate2_fwd_kernel(const RowArgs a, const float* __restrict__ yy, const float* __restrict__ dv,
+                     const float* __restrict__ b2, const float* __restrict__ bn_mul, const float* __restrict__ bn_add,
+                     float* __restrict__ agg, float* __restrict__ moments) {
+  extern __shared__ __align__(16) float smem[];
+  float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);
+  float* red = smem + kTileO * 8;
+  const int w = threadIdx.x, y = threadIdx.y, NT = blockDim.x;
+  const int n = a.n, N = a.N, n3 = 3 * n;
+  const int64_t rl = blockIdx.x;  // receiver, local to the chunk
+  const int64_t gl = rl / N;
+  const int ir = (int)(rl - gl * N);
+  const int64_t base = a.node0 + gl * N;
+  const bool act = w < n;
+  const float b2s = act ? b2[w] : 0.f, b2g = act ? b2[n + w] : 0.f;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // sum m_s, m_x, m_y, m_z, sum m_s^2, sum |m_v|^2
+  for (int o0 = 0; o0 < N; o0 += kTileO) {
+    __syncthreads();
+    node_tile_geometry(a.pos, a.mass, base, N, ir, o0, 1.0f, gs, y * NT + w, NT * kSY);
+    __syncthreads();
+    if (!act) continue;
+    const int lim = min(kTileO, N - o0);
+#pragma unroll 2
+    for (int t = y; t < lim; t += kSY) {
+      if (gs[t][3] == 0.f) continue;
+      const int64_t row = rl * N + o0 + t;
+      const float* yr = yy + row * n3;
+      const float* dr = dv + row * n3;
+      const float ys = yr[w] + b2s, yg = yr[n + w] + b2g, t1 = yr[2 * n + w];
+      const float dx = dr[w], dy = dr[n + w], dz = dr[2 * n + w];
+      const float ms = silu_gate(ys), gt = sig_gate(yg);
+      const float mx = gt * fmaf(gs[t][0], t1, dx), my = gt * fmaf(gs[t][1], t1, dy), mz = gt * fmaf(gs[t][2], t1, dz);
+      acc[0] += ms;
+      acc[1] += mx;
+      acc[2] += my;
+      acc[3] += mz;
+      acc[4] = fmaf(ms, ms, acc[4]);
+      acc[5] += mx * mx + my * my + mz * mz;
+    }
+  }
+  __syncthreads();
+  lane_reduce<6>(red, acc, w, y, NT);
+  if (y == 0 && act) {
+    const int64_t r = a.node0 + rl;
+    if (moments != nullptr) {
+      moments[r * 2 * n + w] = acc[4];
+      moments[r * 2 * n + n + w] = acc[5];
+    }
+    if (bn_mul != nullptr) {
+      const float ms = bn_mul[w], mv = bn_mul[n + w];
+      acc[0] = fmaf(acc[0], ms, bn_add[w]);
+      acc[1] *= mv;
+      acc[2] *= mv;
+      acc[3] *= mv;
+    }
+    float* o = agg + r * 4 * n;
+    o[w] = acc[0];
+    o[n + w] = acc[1];
+    o[2 * n + w] = acc[2];
+    o[3 * n + w] = acc[3];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// E2b: backward of the gate of message_layer_2: (Y, DV) -> (dY, dDV) in place, bias-gradient row per receiver.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(96 * kSY)
+    gate2_bwd_kernel(const RowArgs a, float* __restrict__ yy, float* __restrict__ dv, const float* __restrict__ b2,
+                     const float* __restrict__ bnA, const float* __restrict__ bnB, const float* __restrict__ bnC,
+                     const float* __restrict__ dagg, float* __restrict__ db2_rows) {
+  extern __shared__ __align__(16) float smem[];
+  float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);
+  float* red = smem + kTileO * 8;
+  const int w = threadIdx.x, y = threadIdx.y, NT = blockDim.x;
+  const int n = a.n, N = a.N, n3 = 3 * n;
+  const int64_t rl = blockIdx.x;
+  const int64_t gl = rl / N;
+  const int ir = (int)(rl - gl * N);
+  const int64_t base = a.node0 + gl * N;
+  const bool act = w < n;
+  float b2s = 0.f, b2g = 0.f, As = 0.f, Av = 0.f, Bs = 0.f, Bv = 0.f, Cs = 0.f, G[4] = {0.f, 0.f, 0.f, 0.f};
+  if (act) {
+    b2s = b2[w];
+    b2g = b2[n + w];
+    As = bnA[w];
+    Av = bnA[n + w];
+    Bs = bnB[w];
+    Bv = bnB[n + w];
+    Cs = bnC[w];
+    const float* gr = dagg + (a.node0 + rl) * 4 * n;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) G[c] = gr[c * n + w];
+  }
+  float acc[2] = {0.f, 0.f};
+  for (int o0 = 0; o0 < N; o0 += kTileO) {
+    __syncthreads();
+    node_tile_geometry(a.pos, a.mass, base, N, ir, o0, 1.0f, gs, y * NT + w, NT * kSY);
+    __syncthreads();
+    if (!act) continue;
+    const int lim = min(kTileO, N - o0);
+#pragma unroll 2
+    for (int t = y; t < lim; t += kSY) {
+      const int64_t row = rl * N + o0 + t;
+      float* yr = yy + row * n3;
+      float* dr = dv + row * n3;
+      const float ax = gs[t][0], ay = gs[t][1], az = gs[t][2], valid = gs[t][3];
+      const float ys = yr[w] + b2s, yg = yr[n + w] + b2g, t1 = yr[2 * n + w];
+      const float ms = silu_gate(ys), gt = sig_gate(yg);
+      const float ux = fmaf(ax, t1, dr[w]), uy = fmaf(ay, t1, dr[n + w]), uz = fmaf(az, t1, dr[2 * n + w]);
+      const float dms = valid * (As * G[0] + Bs * ms + Cs);
+      const float dmx = valid * (Av * G[1] + Bv * gt * ux);
+      const float dmy = valid * (Av * G[2] + Bv * gt * uy);
+      const float dmz = valid * (Av * G[3] + Bv * gt * uz);
+      const float dys = dms * silu_gate_grad(ys);
+      const float dyg = sig_gate_grad(yg) * (dmx * ux + dmy * uy + dmz * uz);
+      const float dux = gt * dmx, duy = gt * dmy, duz = gt * dmz;
+      yr[w] = dys;
+      yr[n + w] = dyg;
+      yr[2 * n + w] = ax * dux + ay * duy + az * duz;
+      dr[w] = dux;
+      dr[n + w] = duy;
+      dr[2 * n + w] = duz;
+      acc[0] += dys;
+      acc[1] += dyg;
+    }
+  }
+  __syncthreads();
+  lane_reduce<2>(red, acc, w, y, NT);
+  if (y == 0 && act) {
+    db2_rows[rl * 2 * n + w] = acc[0];
+    db2_rows[rl * 2 * n + n + w] = acc[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// E3: backward of the message_layer_1 gate / combine.  block = one stationary node; PASS 0: receiver (dP, d w_edge1
+// rows), PASS 1: sender (dQ).  dxs [rows][2n] = gradient of (s', v'.a), dxv [rows][3][n] = gradient of v'.
+// ---------------------------------------------------------------------------------------------------------------
+template <int PASS>
+__global__ void __launch_bounds__(96 * kSY)
+    msg1_bwd_kernel(const RowArgs a, const float* __restrict__ dxs, const float* __restrict__ dxv,
+                    float* __restrict__ dout, float* __restrict__ dwe_partial) {
+  extern __shared__ __align__(16) float smem[];
+  float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);
+  float* red = smem + kTileO * 8;
+  const int w = threadIdx.x, y = threadIdx.y, NT = blockDim.x;
+  const int n = a.n, N = a.N, n3 = 3 * n;
+  const int64_t rl = blockIdx.x;
+  const int64_t gl = rl / N;
+  const int ir = (int)(rl - gl * N);
+  const int64_t base = a.node0 + gl * N;
+  const bool act = w < n;
+  float st[12];
+  float wd0s = 0.f, wd0g = 0.f, wm0s = 0.f, wm0g = 0.f, wd1 = 0.f, wm1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) st[k] = 0.f;
+  if (act) {
+    const float* sr = (PASS == 0 ? a.pp : a.qq) + (base + ir) * 4 * n3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) st[c * 3 + k] = sr[c * n3 + k * n + w];
+    wd0s = a.w_edge1[w];
+    wd0g = a.w_edge1[n + w];
+    wm0s = a.w_edge1[2 * n + w];
+    wm0g = a.w_edge1[3 * n + w];
+    wd1 = a.w_edge1[4 * n + w];
+    wm1 = a.w_edge1[5 * n + w];
+  }
+  constexpr int V = PASS == 0 ? 18 : 12;
+  float acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = 0.f;
+  for (int o0 = 0; o0 < N; o0 += kTileO) {
+    __syncthreads();
+    node_tile_geometry(a.pos, a.mass, base, N, ir, o0, PASS == 0 ? 1.0f : -1.0f, gs, y * NT + w, NT * kSY);
+    __syncthreads();
+    if (!act) continue;
+    const int lim = min(kTileO, N - o0);
+    for (int t = y; t < lim; t += kSY) {
+      const float valid = gs[t][3];
+      if (valid == 0.f) continue;
+      const int oo = o0 + t;
+      const int64_t row = PASS == 0 ? (rl * N + oo) : ((gl * N + oo) * N + ir);
+      const float* xr = dxs + row * 2 * n;
+      const float* vr = dxv + row * n3;
+      const float d0 = xr[w], d1 = xr[n + w], d2 = vr[w], d3 = vr[n + w], d4 = vr[2 * n + w];
+      const float* orow = (PASS == 0 ? a.qq : a.pp) + (base + oo) * 4 * n3;
+      float S[12];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) S[c * 3 + k] = st[c * 3 + k] + orow[c * n3 + k * n + w];
+      const float ax = gs[t][0], ay = gs[t][1], az = gs[t][2], len = gs[t][4], mm = gs[t][5];
+      const float zs = S[0] + ax * S[3] + ay * S[6] + az * S[9] + len * wd0s + mm * wm0s;
+      const float zg = S[1] + ax * S[4] + ay * S[7] + az * S[10] + len * wd0g + mm * wm0g;
+      const float tt = S[2] + len * wd1 + mm * wm1;
+      const float zx = ax * tt + S[5], zy = ay * tt + S[8], zz = az * tt + S[11];
+      const float gg = sig_gate(zg);
+      const float tvx = d2 + ax * d1, tvy = d3 + ay * d1, tvz = d4 + az * d1;
+      const float dzs = silu_gate_grad(zs) * d0;
+      const float dzg = sig_gate_grad(zg) * (zx * tvx + zy * tvy + zz * tvz);
+      const float dzx = gg * tvx, dzy = gg * tvy, dzz = gg * tvz;
+      const float dt = ax * dzx + ay * dzy + az * dzz;
+      acc[0] += dzs;
+      acc[1] += dzg;
+      acc[2] += dt;
+      acc[3] += ax * dzs;
+      acc[4] += ax * dzg;
+      acc[5] += dzx;
+      acc[6] += ay * dzs;
+      acc[7] += ay * dzg;
+      acc[8] += dzy;
+      acc[9] += az * dzs;
+      acc[10] += az * dzg;
+      acc[11] += dzz;
+      if (PASS == 0) {
+        acc[12] += len * dzs;
+        acc[13] += len * dzg;
+        acc[14] += mm * dzs;
+        acc[15] += mm * dzg;
+        acc[16] += len * dt;
+        acc[17] += mm * dt;
+      }
+    }
+  }
+  __syncthreads();
+  lane_reduce<V>(red, acc, w, y, NT);
+  if (y == 0 && act) {
+    const int64_t r = a.node0 + rl;
+    float* o = dout + r * 4 * n3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o[c * n3 + k * n + w] = acc[c * 3 + k];
+    if (PASS == 0) {
+      float* pw = dwe_partial + r * 6 * n;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) pw[c * n + w] = acc[12 + c];
+    }
+  }
+}
+
+// Wcat [2n][3n] = [[W_ss | W_sv], [W_vs | 0]],  WcatT [3n][2n] = its transpose (from the transposed blocks)
+__global__ void build_wcat_kernel(int n, const float* __restrict__ ss, const float* __restrict__ vs,
+                                  const float* __restrict__ sv, const float* __restrict__ tss,
+                                  const float* __restrict__ tvs, const float* __restrict__ tsv,
+                                  float* __restrict__ wcat, float* __restrict__ wcat_t) {
+  const int total = 6 * n * n;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    {
+      const int u = idx / (3 * n), c = idx % (3 * n);
+      float v;
+      if (u < n) v = c < 2 * n ? ss[u * 2 * n + c] : sv[u * n + (c - 2 * n)];
+      else v = c < 2 * n ? vs[(u - n) * 2 * n + c] : 0.f;
+      wcat[idx] = v;
+    }
+    if (wcat_t != nullptr) {
+      const int c = idx / (2 * n), u = idx % (2 * n);  // WcatT[c][u] = Wcat[u][c]
+      float v;
+      if (c < 2 * n) v = u < n ? tss[c * n + u] : tvs[c * n + (u - n)];
+      else v = u < n ? tsv[(c - 2 * n) * n + u] : 0.f;
+      wcat_t[idx] = v;
+    }
+  }
+}
+
+// dWcat [2n][3n], dWvv [n][n], db2 [2n] -> the caller's gradient blocks
+__global__ void scatter_w2_grads_kernel(int n, const float* __restrict__ dwcat, const float* __restrict__ dwvv,
+                                        const float* __restrict__ db2_chunks, int chunks, float* __restrict__ dss,
+                                        float* __restrict__ dvs, float* __restrict__ dsv, float* __restrict__ dvv,
+                                        float* __restrict__ db2) {
+  const int total = 6 * n * n;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int u = idx / (3 * n), c = idx % (3 * n);
+    const float v = dwcat[idx];
+    if (u < n) {
+      if (c < 2 * n) dss[u * 2 * n + c] = v;
+      else dsv[u * n + (c - 2 * n)] = v;
+    } else if (c < 2 * n) {
+      dvs[(u - n) * 2 * n + c] = v;
+    }
+    if (idx < n * n) dvv[idx] = dwvv[idx];
+    if (idx < 2 * n) {
+      float s = db2_chunks[idx];
+      for (int k = 1; k < chunks; ++k) s += db2_chunks[(int64_t)k * 2 * n + idx];
+      db2[idx] = s;
+    }
+  }
+}
+
+// ===============================================================================================================
+// G2: C[M][N] (+)= sum_k A[k][m] B[k][n]  (both operands row-major over K = rows: "TN"), 3xTF32 on tcgen05.
+// Both operands are MN-major for the tensor core (consecutive m / n are contiguous in HBM), so a row of A or B goes
+// into shared memory as it is read: 128-byte pieces of 32 floats form the swizzle atoms, 4 consecutive k per atom.
+//   smem stage: A hi|lo [kKC/4 k-groups][4 m-atoms][4][128 B], B hi|lo [kKC/4][NP/32 n-atoms][4][128 B]
+// grid = (splits, m-blocks of 128); every CTA accumulates its K range in TMEM and writes one partial tile; the partial
+// tiles are added in a fixed order by tn_reduce_kernel.
+// ===============================================================================================================
+namespace tn {
+
+constexpr int kKC = 32;
+constexpr int kStages = 2;
+constexpr int kLoadWarps = 8;
+constexpr int kMmaWarp = kLoadWarps;
+constexpr int kThreads = (kLoadWarps + 1) * 32;
+constexpr int kBatch = 8;  // 16-byte pieces a loader thread keeps in flight
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int it = 0; it < (1 << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();  // protocol bug: fail loudly instead of hanging the GPU
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// MN-major tf32 operands have ONE legal shared-memory layout, "128-byte swizzle with 32-byte atomicity"
+// (SWIZZLE_128B_BASE32B, layout type 1): atoms of 32 floats (128 B along M / N) x 4 k, rows 128 B apart, the 32-byte
+// piece c of row r stored at piece c ^ r.  LBO = distance of consecutive atoms along M / N (512 B), SBO = distance of
+// consecutive 4-k groups.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(512 >> 4) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// kind::tf32, D = f32, A and B MN-major ("transposed"), M = 128
+__device__ __forceinline__ uint32_t make_idesc(int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 2u << 7;
+  d |= 2u << 10;
+  d |= 1u << 15;
+  d |= 1u << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(128 >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+#define SEGNN_TN_LD16(taddr, r)                                                                                    \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]),   \
+                 "=r"((r)[7]), "=r"((r)[8]), "=r"((r)[9]), "=r"((r)[10]), "=r"((r)[11]), "=r"((r)[12]),              \
+                 "=r"((r)[13]), "=r"((r)[14]), "=r"((r)[15])                                                         \
+               : "r"(taddr))
+
+struct Args {
+  const float* A;
+  int64_t lda;
+  const float* B;
+  int64_t ldb;
+  int64_t K;
+  int M, N, NP;      // NP = N rounded up to 32
+  int tmem_cols;     // power of two >= NP (>= 32)
+  float* part;       // [splits][mblocks * 128][NP]
+};
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int NP = a.NP;
+  const int a_bytes = (kKC / 8) * 4 * 1024;          // one of (hi, lo)
+  const int b_bytes = (kKC / 8) * (NP / 32) * 1024;
+  const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  uint64_t* full = bars;              // [kStages] loaders -> MMA
+  uint64_t* empty = bars + kStages;   // [kStages] MMA -> loaders
+  uint64_t* dfull = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, splits = gridDim.x, mb = blockIdx.y;
+  const int m0 = mb * 128;
+  const int64_t chunks_total = (a.K + kKC - 1) / kKC;
+  const int64_t c_begin = chunks_total * split / splits, c_end = chunks_total * (split + 1) / splits;
+
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(a.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], kLoadWarps);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(dfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < kLoadWarps) {
+    // ===================== loaders: fp32 rows -> (hi, lo) tf32, MN-major swizzled atoms =============================
+    const int pa = kKC * 32;            // 16-byte pieces of the A chunk (128 floats per row)
+    const int npr = NP / 4;             // pieces per row of B
+    const int total = pa + kKC * npr;
+    const int b_atoms_bytes = (NP / 32) * 512;  // one 4-k group of B
+    uint32_t it = 0;
+    for (int64_t c = c_begin; c < c_end; ++c, ++it) {
+      const int s = it % kStages;
+      mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+      uint8_t* st = smem + s * stage_bytes;
+      const int64_t k0 = c * kKC;
+      for (int p0 = tid; p0 < total; p0 += kLoadWarps * 32 * kBatch) {
+        float4 v[kBatch];
+        int off[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const int p = p0 + b * kLoadWarps * 32;
+          v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+          off[b] = -1;
+          if (p < total) {
+            const bool is_a = p < pa;
+            const int q = is_a ? p : p - pa;
+            const int k = is_a ? (q >> 5) : (q / npr);
+            const int c4 = is_a ? (q & 31) : (q - k * npr);
+            const int64_t kr = k0 + k;
+            const int col = (is_a ? m0 : 0) + 4 * c4;
+            if (kr < a.K && col < (is_a ? a.M : a.N))
+              v[b] = *reinterpret_cast<const float4*>((is_a ? a.A + kr * a.lda : a.B + kr * a.ldb) + col);
+            const int r = k & 3, cc = c4 & 7;
+            off[b] = (is_a ? 0 : 2 * a_bytes) + (k >> 2) * (is_a ? 2048 : b_atoms_bytes) + (c4 >> 3) * 512 + r * 128 +
+                     ((((cc >> 1) ^ r) << 5) | ((cc & 1) << 4));
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          if (off[b] >= 0) {
+            const int lo_off = off[b] < 2 * a_bytes ? a_bytes : b_bytes;
+            float4 hi, lo;
+            hi.x = tf32_rna(v[b].x); lo.x = tf32_rna(v[b].x - hi.x);
+            hi.y = tf32_rna(v[b].y); lo.y = tf32_rna(v[b].y - hi.y);
+            hi.z = tf32_rna(v[b].z); lo.z = tf32_rna(v[b].z - hi.z);
+            hi.w = tf32_rna(v[b].w); lo.w = tf32_rna(v[b].w - hi.w);
+            *reinterpret_cast<float4*>(st + off[b]) = hi;
+            *reinterpret_cast<float4*>(st + off[b] + lo_off) = lo;
+          }
+        }
+      }
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+  } else {
+    // ===================== MMA issuer ==============================================================================
+    uint32_t it = 0;
+    const int nsub = (NP + 255) / 256;
+    for (int64_t c = c_begin; c < c_end; ++c, ++it) {
+      const int s = it % kStages;
+      mbar_wait(&full[s], (it / kStages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + s * stage_bytes);
+        const uint32_t sa_lo = sa + a_bytes, sb = sa + 2 * a_bytes, sb_lo = sb + b_bytes;
+        const uint32_t b_group = (uint32_t)(NP / 32) * 512u;  // one 4-k group of B; an MMA (K = 8) reads two
+#pragma unroll
+        for (int kg = 0; kg < kKC / 8; ++kg) {
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int width = min(256, NP - sub * 256);
+            const uint32_t idesc = make_idesc(width);
+            const uint32_t d = tmem + sub * 256;
+            const uint32_t ao = kg * 4096, bo = kg * 2 * b_group + sub * 8 * 512;
+            const uint64_t ah = make_desc_mn(sa + ao, 2048), al = make_desc_mn(sa_lo + ao, 2048);
+            const uint64_t bh = make_desc_mn(sb + bo, b_group), bl = make_desc_mn(sb_lo + bo, b_group);
+            mma_tf32(d, ah, bl, idesc, (it > 0 || kg > 0) ? 1u : 0u);
+            mma_tf32(d, al, bh, idesc, 1u);
+            mma_tf32(d, ah, bh, idesc, 1u);
+          }
+        }
+        tc_commit(&empty[s]);
+        if (c == c_end - 1) tc_commit(dfull);
+      }
+      __syncwarp();
+    }
+  }
+  // ===================== epilogue (warps 0..3): TMEM -> partial tile ===============================================
+  if (warp < 4 && c_end > c_begin) {
+    mbar_wait(dfull, 0);
+    tc_fence_after();
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int mblocks = gridDim.y;
+    float* dst = a.part + (((int64_t)split * mblocks + mb) * 128 + warp * 32 + lane) * NP;
+    for (int col = 0; col < NP; col += 16) {
+      uint32_t u[16];
+      SEGNN_TN_LD16(tmem + lane_base + col, u);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(dst + col + j) = make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]),
+                                                                __uint_as_float(u[j + 2]), __uint_as_float(u[j + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(a.tmem_cols));
+}
+
+// C[m][n] = (accumulate ? C : 0) + sum over the splits in order
+__global__ void tn_reduce_kernel(const float* __restrict__ part, int splits, int mblocks, int M, int N, int NP,
+                                 float* __restrict__ C, int64_t ldc, int accumulate) {
+  const int64_t total = (int64_t)M * N;
+  const int64_t tile = (int64_t)mblocks * 128 * NP;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / N), c = (int)(idx - (int64_t)m * N);
+    const float* p = part + (int64_t)m * NP + c;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 4 <= splits; k += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] += p[(int64_t)(k + j) * tile];
+    }
+    for (int j = 0; k < splits; ++k, ++j) s[j] += p[(int64_t)k * tile];
+    const float v = (s[0] + s[1]) + (s[2] + s[3]);
+    float* o = C + (int64_t)m * ldc + c;
+    *o = accumulate ? *o + v : v;
+  }
+}
+
+static inline int splits_for(int64_t K, int mblocks, int sms) {
+  const int64_t chunks = (K + kKC - 1) / kKC;
+  int64_t s = sms / mblocks;
+  if (s < 1) s = 1;
+  if (s > chunks) s = chunks;
+  return (int)s;
+}
+
+}  // namespace tn
+}  // namespace eg
+
+static int device_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+}  // namespace segnn
+
+using namespace segnn;
+
+extern "C" {
+
+int64_t segnn_gemm_tn_tf32x3_workspace(int64_t K, int M, int N) {
+  if (K < 1 || M < 1 || N < 1 || N > 512) return -1;
+  const int mblocks = (M + 127) / 128;
+  const int NP = (N + 31) & ~31;
+  const int splits = eg::tn::splits_for(K, mblocks, 148 * 2);  // upper bound independent of the device
+  return (int64_t)splits * mblocks * 128 * NP * (int64_t)sizeof(float);
+}
+
+int segnn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int M, int N, float* C,
+                         int64_t ldc, int accumulate, float* workspace, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(K >= 1 && M >= 1 && N >= 1 && N <= 512 && lda >= M && ldb >= N && ldc >= N, "bad sizes");
+  SEGNN_CHECK_ARG(A && B && C && workspace, "null pointer");
+  SEGNN_CHECK_ARG((M & 3) == 0 && (N & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                  "M, N, lda, ldb must be multiples of 4 floats and the pointers 16-byte aligned");
+  const int mblocks = (M + 127) / 128;
+  const int NP = (N + 31) & ~31;
+  int tmem_cols = 32;
+  while (tmem_cols < NP) tmem_cols <<= 1;
+  const int splits = eg::tn::splits_for(K, mblocks, device_sms());
+  eg::tn::Args a{A, lda, B, ldb, K, M, N, NP, tmem_cols, workspace};
+  const size_t smem = 1024 + (size_t)eg::tn::kStages * (2 * (eg::tn::kKC / 8) * 4 * 1024 +
+                                                        2 * (eg::tn::kKC / 8) * (NP / 32) * 1024) + 64;
+  if (smem > 227 * 1024) {
+    set_error("segnn_gemm_tn_tf32x3: N=%d needs %zu bytes of shared memory", N, smem);
+    return SEGNN_E_UNSUPPORTED;
+  }
+  cudaError_t err = cudaFuncSetAttribute(eg::tn::gemm_tn_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+  if (err != cudaSuccess) {
+    set_error("segnn_gemm_tn_tf32x3: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(err));
+    return SEGNN_E_CUDA;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)splits, (unsigned)mblocks);
+  eg::tn::gemm_tn_tf32x3_kernel<<<grid, eg::tn::kThreads, smem, s>>>(a);
+  SEGNN_CHECK_LAUNCH();
+  const int64_t total = (int64_t)M * N;
+  eg::tn::tn_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(workspace, splits, mblocks, M, N, NP, C, ldc,
+                                                                         accumulate);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// host orchestration of the edge layer in GEMM form
+// ---------------------------------------------------------------------------------------------------------------
+namespace segnn {
+namespace eg {
+
+static inline int64_t align64(int64_t floats) { return (floats + 63) & ~(int64_t)63; }  // 256-byte granules
+
+struct Plan {
+  int64_t fixed_floats, per_graph_floats;
+  int64_t o_wcat, o_wcat_t, o_ws_g, o_dwcat, o_dwvv, o_db2c, o_tn, o_colsum, o_chunk;  // offsets in floats
+  int64_t ws_g_floats, tn_floats, colsum_floats;
+};
+
+// backward == false: only (XS, XV, Y, DV) per row
+static Plan make_plan(int N, int n, bool backward, int64_t max_chunks) {
+  Plan p{};
+  int64_t o = 0;
+  p.o_wcat = o; o += align64((int64_t)6 * n * n);
+  p.o_wcat_t = o; o += align64((int64_t)6 * n * n);
+  const int64_t g1 = segnn_gemm_tf32x3_workspace(2 * n, 3 * n), g2 = segnn_gemm_tf32x3_workspace(3 * n, 2 * n),
+                g3 = segnn_gemm_tf32x3_workspace(n, n);
+  int64_t gmax = g1 > g2 ? g1 : g2;
+  if (g3 > gmax) gmax = g3;
+  p.ws_g_floats = align64(gmax / 4);
+  p.o_ws_g = o; o += p.ws_g_floats;
+  p.o_dwcat = o; o += align64((int64_t)6 * n * n);
+  p.o_dwvv = o; o += align64((int64_t)n * n);
+  p.o_db2c = o; o += align64(max_chunks * 2 * n);
+  const int64_t t1 = segnn_gemm_tn_tf32x3_workspace((int64_t)1 << 40, 2 * n, 3 * n),
+                t2 = segnn_gemm_tn_tf32x3_workspace((int64_t)1 << 40, n, n);
+  p.tn_floats = backward ? align64((t1 > t2 ? t1 : t2) / 4) : 0;
+  p.o_tn = o; o += p.tn_floats;
+  p.o_colsum = o;
+  p.colsum_floats = 0;  // filled by the caller once the chunk size is known
+  p.fixed_floats = o;
+  p.per_graph_floats = (int64_t)N * N * (backward ? 16 : 11) * n + (backward ? (int64_t)N * 2 * n : 0);
+  return p;
+}
+
+static int check_common(int B, int N, int n) {
+  if (n < 4 || n > 96 || (n & 3) != 0) {
+    set_error("segnn_edge_layer_gemm: hidden multiplicity n=%d must be a multiple of 4 in [4, 96]", n);
+    return SEGNN_E_UNSUPPORTED;
+  }
+  if (B < 0 || N < 2) {
+    set_error("segnn_edge_layer_gemm: bad sizes B=%d N=%d", B, N);
+    return SEGNN_E_INVALID;
+  }
+  return SEGNN_OK;
+}
+
+}  // namespace eg
+}  // namespace segnn
+
+extern "C" {
+
+int64_t segnn_edge_layer_gemm_workspace(int B, int N, int n, int backward, int64_t budget_bytes) {
+  if (eg::check_common(B, N, n) != SEGNN_OK || B < 1) return -1;
+  // chunks of whole graphs; at least one graph per chunk whatever the budget
+  eg::Plan p = eg::make_plan(N, n, backward != 0, B);
+  const int64_t colsum = backward ? segnn_colsum_workspace((int64_t)B * N, 2 * n) / 4 + 64 : 0;
+  const int64_t fixed = p.fixed_floats + eg::align64(colsum);
+  int64_t graphs = B;
+  if (budget_bytes > 0) {
+    const int64_t room = budget_bytes / 4 - fixed;
+    graphs = room / (p.per_graph_floats + 64 * 8);
+    if (graphs < 1) graphs = 1;
+    if (graphs > B) graphs = B;
+  }
+  return (fixed + graphs * (p.per_graph_floats + 64 * 8)) * (int64_t)sizeof(float);
+}
+
+static int64_t graphs_per_chunk(const eg::Plan& p, int64_t colsum_floats, int64_t ws_bytes, int B) {
+  const int64_t room = ws_bytes / 4 - p.fixed_floats - eg::align64(colsum_floats);
+  int64_t graphs = room / (p.per_graph_floats + 64 * 8);
+  if (graphs > B) graphs = B;
+  return graphs;
+}
+
+int segnn_edge_layer_gemm_fwd(const float* pos, const float* mass, int B, int N, int n, const float* p, const float* q,
+                              const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
+                              const float* w2_vv, const float* b2, const float* bn_mul, const float* bn_add,
+                              float* agg_out, float* moments, float* workspace, int64_t workspace_bytes,
+                              segnn_stream_t stream) {
+  int rc = eg::check_common(B, N, n);
+  if (rc != SEGNN_OK) return rc;
+  if (B == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pos && mass && p && q && w_edge1 && w2_ss && w2_vs && w2_sv && w2_vv && b2 && agg_out && workspace,
+                  "null pointer");
+  SEGNN_CHECK_ARG((bn_mul == nullptr) == (bn_add == nullptr), "bn_mul and bn_add go together");
+  SEGNN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  eg::Plan pl = eg::make_plan(N, n, false, B);
+  const int64_t gpc = graphs_per_chunk(pl, 0, workspace_bytes, B);
+  SEGNN_CHECK_ARG(gpc >= 1, "workspace too small for one graph (segnn_edge_layer_gemm_workspace)");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* wcat = workspace + pl.o_wcat;
+  float* ws_g = workspace + pl.o_ws_g;
+  float* chunk = workspace + pl.fixed_floats;
+  eg::build_wcat_kernel<<<(6 * n * n + 255) / 256, 256, 0, s>>>(n, w2_ss, w2_vs, w2_sv, nullptr, nullptr, nullptr, wcat,
+                                                              nullptr);
+  SEGNN_CHECK_LAUNCH();
+  const int NT = (n + 31) & ~31;
+  const size_t smem_node = sizeof(float) * ((size_t)eg::kTileO * 8 + (size_t)eg::kSY * 18 * NT);
+  cudaFuncSetAttribute(eg::gate2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
+  for (int64_t g0 = 0; g0 < B; g0 += gpc) {
+    const int64_t gc = (B - g0 < gpc) ? B - g0 : gpc;
+    const int64_t rows = gc * N * N;
+    float* xs = chunk;
+    float* xv = xs + eg::align64(rows * 2 * n);
+    float* yy = xv + eg::align64(rows * 3 * n);
+    float* dv = yy + eg::align64(rows * 3 * n);
+    eg::RowArgs ra{pos, mass, p, q, w_edge1, N, n, g0 * N};
+    const int64_t blocks1 = gc * ((N + eg::kRecv - 1) / eg::kRecv);
+    eg::msg1_rows_kernel<<<(unsigned)blocks1, dim3(NT, 4), 0, s>>>(ra, xs, xv);
+    SEGNN_CHECK_LAUNCH();
+    rc = segnn_gemm_tf32x3(xs, 2 * n, wcat, 3 * n, rows, 2 * n, 3 * n, yy, 3 * n, ws_g, stream);
+    if (rc != SEGNN_OK) return rc;
+    rc = segnn_gemm_tf32x3(xv, n, w2_vv, n, 3 * rows, n, n, dv, n, ws_g, stream);
+    if (rc != SEGNN_OK) return rc;
+    eg::gate2_fwd_kernel<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, yy, dv, b2, bn_mul, bn_add, agg_out,
+                                                                                 moments);
+    SEGNN_CHECK_LAUNCH();
+  }
+  return SEGNN_OK;
+}
+
+int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N, int n, const float* p, const float* q,
+                              const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
+                              const float* w2_vv, const float* b2, const float* w2t_ss, const float* w2t_vs,
+                              const float* w2t_sv, const float* w2t_vv, const float* bn_a, const float* bn_b,
+                              const float* bn_c, const float* dagg, float* dP, float* dQ, float* dw2_ss, float* dw2_vs,
+                              float* dw2_sv, float* dw2_vv, float* db2, float* dwe_partial, float* workspace,
+                              int64_t workspace_bytes, segnn_stream_t stream) {
+  int rc = eg::check_common(B, N, n);
+  if (rc != SEGNN_OK) return rc;
+  if (B == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pos && mass && p && q && w_edge1 && w2_ss && w2_vs && w2_sv && w2_vv && b2 && w2t_ss && w2t_vs &&
+                      w2t_sv && w2t_vv && bn_a && bn_b && bn_c && dagg && dP && dQ && dw2_ss && dw2_vs && dw2_sv &&
+                      dw2_vv && db2 && dwe_partial && workspace,
+                  "null pointer");
+  SEGNN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  eg::Plan pl = eg::make_plan(N, n, true, B);
+  const int64_t colsum_floats = segnn_colsum_workspace((int64_t)B * N, 2 * n) / 4 + 64;
+  const int64_t gpc = graphs_per_chunk(pl, colsum_floats, workspace_bytes, B);
+  SEGNN_CHECK_ARG(gpc >= 1, "workspace too small for one graph (segnn_edge_layer_gemm_workspace)");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* wcat = workspace + pl.o_wcat;
+  float* wcat_t = workspace + pl.o_wcat_t;
+  float* ws_g = workspace + pl.o_ws_g;
+  float* dwcat = workspace + pl.o_dwcat;
+  float* dwvv = workspace + pl.o_dwvv;
+  float* db2c = workspace + pl.o_db2c;
+  float* ws_tn = workspace + pl.o_tn;
+  float* ws_col = workspace + pl.o_colsum;
+  float* chunk = ws_col + eg::align64(colsum_floats);
+  eg::build_wcat_kernel<<<(6 * n * n + 255) / 256, 256, 0, s>>>(n, w2_ss, w2_vs, w2_sv, w2t_ss, w2t_vs, w2t_sv, wcat,
+                                                              wcat_t);
+  SEGNN_CHECK_LAUNCH();
+  const int NT = (n + 31) & ~31;
+  const size_t smem_node = sizeof(float) * ((size_t)eg::kTileO * 8 + (size_t)eg::kSY * 18 * NT);
+  cudaFuncSetAttribute(eg::gate2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
+  cudaFuncSetAttribute(eg::msg1_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
+  cudaFuncSetAttribute(eg::msg1_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
+  int chunk_idx = 0;
+  for (int64_t g0 = 0; g0 < B; g0 += gpc, ++chunk_idx) {
+    const int64_t gc = (B - g0 < gpc) ? B - g0 : gpc;
+    const int64_t rows = gc * N * N;
+    float* xs = chunk;
+    float* xv = xs + eg::align64(rows * 2 * n);
+    float* yy = xv + eg::align64(rows * 3 * n);
+    float* dv = yy + eg::align64(rows * 3 * n);
+    float* dxs = dv + eg::align64(rows * 3 * n);
+    float* dxv = dxs + eg::align64(rows * 2 * n);
+    float* db2_rows = dxv + eg::align64(rows * 3 * n);
+    eg::RowArgs ra{pos, mass, p, q, w_edge1, N, n, g0 * N};
+    const int64_t blocks1 = gc * ((N + eg::kRecv - 1) / eg::kRecv);
+    // recompute: message_layer_2 input rows and pre-activations
+    eg::msg1_rows_kernel<<<(unsigned)blocks1, dim3(NT, 4), 0, s>>>(ra, xs, xv);
+    SEGNN_CHECK_LAUNCH();
+    rc = segnn_gemm_tf32x3(xs, 2 * n, wcat, 3 * n, rows, 2 * n, 3 * n, yy, 3 * n, ws_g, stream);
+    if (rc != SEGNN_OK) return rc;
+    rc = segnn_gemm_tf32x3(xv, n, w2_vv, n, 3 * rows, n, n, dv, n, ws_g, stream);
+    if (rc != SEGNN_OK) return rc;
+    // gate backward in place: (Y, DV) -> (dY, dDV)
+    eg::gate2_bwd_kernel<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, yy, dv, b2, bn_a, bn_b, bn_c, dagg,
+                                                                                 db2_rows);
+    SEGNN_CHECK_LAUNCH();
+    rc = segnn_colsum(db2_rows, nullptr, gc * N, 2 * n, 0, ws_col, db2c + (int64_t)chunk_idx * 2 * n, stream);
+    if (rc != SEGNN_OK) return rc;
+    // weight gradients: K = rows
+    rc = segnn_gemm_tn_tf32x3(xs, 2 * n, yy, 3 * n, rows, 2 * n, 3 * n, dwcat, 3 * n, chunk_idx > 0, ws_tn, stream);
+    if (rc != SEGNN_OK) return rc;
+    rc = segnn_gemm_tn_tf32x3(xv, n, dv, n, 3 * rows, n, n, dwvv, n, chunk_idx > 0, ws_tn, stream);
+    if (rc != SEGNN_OK) return rc;
+    // data gradients
+    rc = segnn_gemm_tf32x3(yy, 3 * n, wcat_t, 2 * n, rows, 3 * n, 2 * n, dxs, 2 * n, ws_g, stream);
+    if (rc != SEGNN_OK) return rc;
+    rc = segnn_gemm_tf32x3(dv, n, w2t_vv, n, 3 * rows, n, n, dxv, n, ws_g, stream);
+    if (rc != SEGNN_OK) return rc;
+    eg::msg1_bwd_kernel<0><<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, dxs, dxv, dP, dwe_partial);
+    SEGNN_CHECK_LAUNCH();
+    eg::msg1_bwd_kernel<1><<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, dxs, dxv, dQ, nullptr);
+    SEGNN_CHECK_LAUNCH();
+  }
+  eg::scatter_w2_grads_kernel<<<(6 * n * n + 255) / 256, 256, 0, s>>>(n, dwcat, dwvv, db2c, chunk_idx, dw2_ss, dw2_vs,
+                                                                    dw2_sv, dw2_vv, db2);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+}  // extern "C"

@@ -197,6 +197,8 @@ def edge_layer(mode: int, pos, mass, batch_size: int, num_nodes: int, n: int, p,
                bn_add=None, want_moments: bool = False):
     """w2: dict with fp32 blocks 'ss','vs','sv','vv','b' and (tensor-core mode) 'tc' image."""
     nodes = batch_size * num_nodes
+    if mode == MODE_FP32 and _use_gemm_form(batch_size, num_nodes, n):
+        return edge_layer_gemm_fwd(pos, mass, batch_size, num_nodes, n, p, q, w_edge1, w2, bn_mul, bn_add, want_moments)
     agg = torch.empty((nodes, 4, n), dtype=torch.float32, device=pos.device)
     mom = torch.empty((nodes, 2 * n), dtype=torch.float32, device=pos.device) if want_moments else None
     with torch.cuda.device(pos.device):
@@ -315,6 +317,94 @@ def gemm_tf32x3(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = 
     return out
 
 
+def gemm_tn_tf32x3(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
+                   accumulate: bool = False) -> torch.Tensor:
+    """C (+)= A^T @ B in fp32 accuracy on the tensor cores (segnn_gemm_tn_tf32x3): ``a`` [K, M] and ``b`` [K, N]
+    row-major (row-strided views allowed), the contraction runs over their rows with a fixed-order split-K reduction."""
+    if not (a.is_cuda and b.is_cuda):
+        raise RuntimeError("gemm_tn_tf32x3 needs CUDA tensors (no CPU fallback)")
+    assert a.dtype == b.dtype == torch.float32 and a.dim() == b.dim() == 2 and a.shape[0] == b.shape[0]
+    assert a.stride(1) == 1 and b.stride(1) == 1, "row-major operands"
+    K, M = a.shape
+    N = b.shape[1]
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    nbytes = int(lib.segnn_gemm_tn_tf32x3_workspace(K, M, N))
+    if nbytes < 0:
+        raise RuntimeError(f"gemm_tn_tf32x3: unsupported sizes K={K} M={M} N={N}")
+    ws = torch.empty(max(4, nbytes // 4), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.segnn_gemm_tn_tf32x3(_p(a), a.stride(0) if K > 1 else max(M, a.stride(0)), _p(b),
+                                       b.stride(0) if K > 1 else max(N, b.stride(0)), K, M, N, _p(out),
+                                       out.stride(0) if M > 1 else N, int(accumulate), _p(ws), _stream()),
+              "segnn_gemm_tn_tf32x3")
+    _bump(2)
+    return out
+
+
+# Graphs with many nodes (BASELINE configuration 4: N = 1000) run the edge layer in GEMM form over the edge rows
+# (csrc/segnn_edge_gemm.cu): from this many rows = B * N * N on, and with at most this much workspace per call.
+GEMM_FORM_MIN_ROWS = 1 << 18
+GEMM_FORM_BUDGET_BYTES = 6 << 30
+
+
+def _use_gemm_form(batch_size: int, num_nodes: int, n: int) -> bool:
+    return batch_size * num_nodes * num_nodes >= GEMM_FORM_MIN_ROWS and n % 4 == 0 and n <= 96 and num_nodes >= 2
+
+
+def _edge_gemm_workspace(batch_size: int, num_nodes: int, n: int, backward: bool, device):
+    nbytes = int(lib.segnn_edge_layer_gemm_workspace(batch_size, num_nodes, n, int(backward), GEMM_FORM_BUDGET_BYTES))
+    if nbytes < 0:
+        raise RuntimeError("segnn_edge_layer_gemm_workspace: unsupported sizes")
+    ws = torch.empty(nbytes // 4 + 64, dtype=torch.float32, device=device)
+    assert ws.data_ptr() % 256 == 0
+    return ws, nbytes
+
+
+def edge_layer_gemm_fwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_mul=None,
+                        bn_add=None, want_moments: bool = False):
+    """segnn_edge_layer_gemm_fwd: the fp32-mode edge layer of graphs with many nodes as 3xTF32 GEMMs over edge rows."""
+    nodes = batch_size * num_nodes
+    agg = torch.empty((nodes, 4, n), dtype=torch.float32, device=pos.device)
+    mom = torch.empty((nodes, 2 * n), dtype=torch.float32, device=pos.device) if want_moments else None
+    ws, nbytes = _edge_gemm_workspace(batch_size, num_nodes, n, False, pos.device)
+    with torch.cuda.device(pos.device):
+        check(lib.segnn_edge_layer_gemm_fwd(_p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1),
+                                            _p(w2["ss"]), _p(w2["vs"]), _p(w2["sv"]), _p(w2["vv"]), _p(w2["b"]),
+                                            _p(bn_mul), _p(bn_add), _p(agg), _p(mom), _p(ws), nbytes, _stream()),
+              "segnn_edge_layer_gemm_fwd")
+    _bump(8)
+    return (agg, mom) if want_moments else agg
+
+
+def edge_layer_gemm_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg,
+                        dP=None, dQ=None, gz=None):
+    """segnn_edge_layer_gemm_bwd: same results as edge_layer_bwd (dP, dQ, message_layer_2 gradient blocks, dw_edge1)."""
+    nodes = batch_size * num_nodes
+    dev = pos.device
+    f = dict(dtype=torch.float32, device=dev)
+    if dP is None:
+        dP, dQ = torch.empty((nodes, 4, 3 * n), **f), torch.empty((nodes, 4, 3 * n), **f)
+        gz = torch.empty(6 * n * n + 2 * n, **f)
+    g = dict(ss=gz[: 2 * n * n].view(n, 2 * n), vs=gz[2 * n * n: 4 * n * n].view(n, 2 * n),
+             sv=gz[4 * n * n: 5 * n * n].view(n, n), vv=gz[5 * n * n: 6 * n * n].view(n, n), b=gz[6 * n * n:])
+    dwe_partial = torch.empty((nodes, 6 * n), **f)
+    w2t = {k: (w2[k + "_t"] if k + "_t" in w2 else w2[k].t().contiguous()) for k in ("ss", "vs", "sv", "vv")}
+    dagg = dagg.contiguous()
+    ws, nbytes = _edge_gemm_workspace(batch_size, num_nodes, n, True, dev)
+    with torch.cuda.device(dev):
+        check(lib.segnn_edge_layer_gemm_bwd(_p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1),
+                                            _p(w2["ss"]), _p(w2["vs"]), _p(w2["sv"]), _p(w2["vv"]), _p(w2["b"]),
+                                            _p(w2t["ss"]), _p(w2t["vs"]), _p(w2t["sv"]), _p(w2t["vv"]), _p(bn_a),
+                                            _p(bn_b), _p(bn_c), _p(dagg), _p(dP), _p(dQ), _p(g["ss"]), _p(g["vs"]),
+                                            _p(g["sv"]), _p(g["vv"]), _p(g["b"]), _p(dwe_partial), _p(ws), nbytes,
+                                            _stream()), "segnn_edge_layer_gemm_bwd")
+    _bump(24)
+    return dP, dQ, g, colsum(dwe_partial)
+
+
 def tc_available() -> bool:
     """True when the tcgen05 (SEGNN_MODE_BF16_TC) edge kernel is compiled into the library."""
     return lib.segnn_pack_w2_tc(None, None, None, None, 96, OPERAND_BF16, None, None) > 0
@@ -405,6 +495,9 @@ def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_e
     f = dict(dtype=torch.float32, device=dev)
     dP, dQ = torch.empty((nodes, 4, 3 * n), **f), torch.empty((nodes, 4, 3 * n), **f)
     gz = torch.empty(6 * n * n + 2 * n, **f)  # written by the fixed-order slab reduction (no atomics)
+    if _use_gemm_form(batch_size, num_nodes, n):
+        return edge_layer_gemm_bwd(pos, mass, batch_size, num_nodes, n, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg,
+                                   dP, dQ, gz)
     ws = torch.empty(max(1, int(lib.segnn_edge_layer_bwd_workspace(batch_size, num_nodes, n)) // 4), **f)
     g = dict(ss=gz[: 2 * n * n].view(n, 2 * n), vs=gz[2 * n * n: 4 * n * n].view(n, 2 * n),
              sv=gz[4 * n * n: 5 * n * n].view(n, n), vv=gz[5 * n * n: 6 * n * n].view(n, n), b=gz[6 * n * n:])

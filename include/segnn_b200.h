@@ -305,6 +305,38 @@ int64_t segnn_gemm_tf32x3_workspace(int K, int N);
 int segnn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int K, int N, float* C,
                       int64_t ldc, float* workspace, segnn_stream_t stream);
 
+/* The same accuracy for C[M][N] (+)= sum_k A[k][m] * B[k][n]: both operands row-major over K ("TN"), K split over the
+ * CTAs of the grid with the partial sums in TMEM and one fixed-order reduction (bit-identical from run to run, no
+ * atomics).  It is the weight-gradient contraction of message_layer_2 over the edge rows (autograd of
+ * o3_building_blocks.py:150-162 inside models/segnn/segnn.py:264-284).  M, N, lda, ldb multiples of 4 floats, N <= 512;
+ * accumulate != 0 adds to C.  workspace: segnn_gemm_tn_tf32x3_workspace(K, M, N) bytes, 16-byte aligned. */
+int64_t segnn_gemm_tn_tf32x3_workspace(int64_t K, int M, int N);
+int segnn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int M, int N, float* C,
+                         int64_t ldc, int accumulate, float* workspace, segnn_stream_t stream);
+
+/* Large-graph form of segnn_edge_layer_fwd (SEGNN_MODE_FP32 semantics, same arguments and outputs) and of
+ * segnn_edge_layer_bwd (passes 0 and 1 in one call): SEGNNLayer.message + the scatter-add (models/segnn/segnn.py:205,
+ * 264-284) and their autograd over graphs with many nodes (BASELINE configuration 4: N = 1000, ~1 M edges).  The
+ * message_layer_2 contraction and its data / weight gradients run as 3xTF32 GEMMs on tcgen05 over the edge rows of one
+ * chunk of graphs at a time (rows = graphs * N * N, 11 n floats per row forward, 16 n backward, in `workspace`);
+ * gradients are bit-identical from run to run.  n must be a multiple of 4, <= 96.  workspace: 256-byte aligned,
+ * segnn_edge_layer_gemm_workspace(B, N, n, backward, budget_bytes) bytes = the fixed part plus as many whole graphs per
+ * chunk as fit into budget_bytes (at least one; budget_bytes <= 0: all B graphs in one chunk); the calls derive the
+ * chunking from workspace_bytes. */
+int64_t segnn_edge_layer_gemm_workspace(int B, int N, int n, int backward, int64_t budget_bytes);
+int segnn_edge_layer_gemm_fwd(const float* pos, const float* mass, int B, int N, int n, const float* p, const float* q,
+                              const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
+                              const float* w2_vv, const float* b2, const float* bn_mul, const float* bn_add,
+                              float* agg_out, float* moments, float* workspace, int64_t workspace_bytes,
+                              segnn_stream_t stream);
+int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N, int n, const float* p, const float* q,
+                              const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
+                              const float* w2_vv, const float* b2, const float* w2t_ss, const float* w2t_vs,
+                              const float* w2t_sv, const float* w2t_vv, const float* bn_a, const float* bn_b,
+                              const float* bn_c, const float* dagg, float* dP, float* dQ, float* dw2_ss, float* dw2_vs,
+                              float* dw2_sv, float* dw2_vv, float* db2, float* dwe_partial, float* workspace,
+                              int64_t workspace_bytes, segnn_stream_t stream);
+
 /* message_layer_1 (models/segnn/segnn.py:264-279) with its weight contraction hoisted to node level, for any hidden
  * irreps: Y [nodes][ydim] holds, for every (x_i or x_j) instruction, sum_u W[u][w] x[node][u, i] at yoff + w * dim1 + i
  * (computed with segnn_generic_tp and an identity coupling); this kernel applies the coupling with the edge attribute

@@ -466,18 +466,16 @@ __global__ void scatter_w2_grads_kernel(int n, const float* __restrict__ dwcat, 
 // G2: C[M][N] (+)= sum_k A[k][m] B[k][n]  (both operands row-major over K = rows: "TN"), 3xTF32 on tcgen05.
 // Both operands are MN-major for the tensor core (consecutive m / n are contiguous in HBM), so a row of A or B goes
 // into shared memory as it is read: 128-byte pieces of 32 floats form the swizzle atoms, 4 consecutive k per atom.
-//   smem stage: A hi|lo [kKC/4 k-groups][4 m-atoms][4][128 B], B hi|lo [kKC/4][NP/32 n-atoms][4][128 B]
+//   smem stage: A hi|lo [kc / 4 k-groups][4 m-atoms][4][128 B], B hi|lo [kc / 4][NP / 32 n-atoms][4][128 B]
 // grid = (splits, m-blocks of 128); every CTA accumulates its K range in TMEM and writes one partial tile; the partial
 // tiles are added in a fixed order by tn_reduce_kernel.
 // ===============================================================================================================
 namespace tn {
 
-constexpr int kKC = 32;
 constexpr int kStages = 2;
 constexpr int kLoadWarps = 8;
 constexpr int kMmaWarp = kLoadWarps;
 constexpr int kThreads = (kLoadWarps + 1) * 32;
-constexpr int kBatch = 8;  // 16-byte pieces a loader thread keeps in flight
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -540,10 +538,12 @@ __device__ __forceinline__ uint32_t make_idesc(int N) {
   d |= (uint32_t)(128 >> 4) << 24;
   return d;
 }
-__device__ __forceinline__ float tf32_rna(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+// v = hi + lo with hi a tf32 number (round to nearest, ties away from zero, on the integer pipe: cvt.rna.tf32 runs on
+// the 16-lane XU pipe and was the busiest unit of the loaders) and lo = v - hi exact in fp32; the tensor core ignores
+// the low 13 mantissa bits of lo (2^-22 of v)
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+  lo = v - hi;
 }
 
 #define SEGNN_TN_LD16(taddr, r)                                                                                    \
@@ -560,16 +560,19 @@ struct Args {
   int64_t ldb;
   int64_t K;
   int M, N, NP;      // NP = N rounded up to 32
+  int kc;            // rows of K per stage: 32, or 64 when both operands are narrow (more bytes in flight)
   int tmem_cols;     // power of two >= NP (>= 32)
   float* part;       // [splits][mblocks * 128][NP]
 };
 
+constexpr int kMaxPieces = 13;  // 16-byte pieces per loader thread and stage
+
 __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int NP = a.NP;
-  const int a_bytes = (kKC / 8) * 4 * 1024;          // one of (hi, lo)
-  const int b_bytes = (kKC / 8) * (NP / 32) * 1024;
+  const int NP = a.NP, KC = a.kc;
+  const int a_bytes = KC * 512;                // one of (hi, lo): [KC / 4 k-groups][4 m-atoms][4][128 B]
+  const int b_bytes = KC * NP * 4;             //                 [KC / 4][NP / 32 n-atoms][4][128 B]
   const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
   uint64_t* full = bars;              // [kStages] loaders -> MMA
@@ -580,7 +583,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, splits = gridDim.x, mb = blockIdx.y;
   const int m0 = mb * 128;
-  const int64_t chunks_total = (a.K + kKC - 1) / kKC;
+  const int ma4 = ((min(a.M - m0, 128) + 31) & ~31) >> 2;  // 16-byte pieces per row of A that carry data
+  const int64_t chunks_total = (a.K + KC - 1) / KC;
   const int64_t c_begin = chunks_total * split / splits, c_end = chunks_total * (split + 1) / splits;
 
   if (warp == kMmaWarp) {
@@ -596,6 +600,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args 
     mbar_init(dfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (ma4 < 32) {  // m-atoms past M are never written by the loaders: they must read as zeros
+    for (int i = tid; i < kStages * stage_bytes / 16; i += kThreads)
+      reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    proxy_fence();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -603,55 +612,78 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args 
 
   if (warp < kLoadWarps) {
     // ===================== loaders: fp32 rows -> (hi, lo) tf32, MN-major swizzled atoms =============================
-    const int pa = kKC * 32;            // 16-byte pieces of the A chunk (128 floats per row)
+    // The loads of chunk c + 1 are issued before chunk c is converted (two register sets): two stages of bytes in
+    // flight per SM.
+    const int pa = KC * ma4;            // 16-byte pieces of the A chunk
     const int npr = NP / 4;             // pieces per row of B
-    const int total = pa + kKC * npr;
+    const int total = pa + KC * npr;
     const int b_atoms_bytes = (NP / 32) * 512;  // one 4-k group of B
-    uint32_t it = 0;
-    for (int64_t c = c_begin; c < c_end; ++c, ++it) {
+    // piece -> (row k of the chunk, shared-memory offset, offset from the chunk's first row in HBM): the same for every
+    // chunk, so the divisions are done once.  meta = smem offset | k << 20 | is_a << 30, -1 for no piece; goff < 0 for
+    // the zero padding past M / N.
+    int meta[kMaxPieces], goff[kMaxPieces];
+#pragma unroll
+    for (int b = 0; b < kMaxPieces; ++b) {
+      const int p = tid + b * (kLoadWarps * 32);
+      meta[b] = -1;
+      goff[b] = -1;
+      if (p < total) {
+        const bool is_a = p < pa;
+        const int q = is_a ? p : p - pa;
+        const int per = is_a ? ma4 : npr;
+        const int k = q / per, c4 = q - k * per;
+        const int rr = k & 3, cc = c4 & 7;
+        const int off = (is_a ? 0 : 2 * a_bytes) + (k >> 2) * (is_a ? 2048 : b_atoms_bytes) + (c4 >> 3) * 512 +
+                        rr * 128 + ((((cc >> 1) ^ rr) << 5) | ((cc & 1) << 4));
+        meta[b] = off | (k << 20) | ((is_a ? 1 : 0) << 30);
+        const int col = (is_a ? m0 : 0) + 4 * c4;
+        if (col < (is_a ? a.M : a.N)) goff[b] = (int)(k * (is_a ? a.lda : a.ldb)) + col;
+      }
+    }
+    auto issue = [&](int64_t c, float4 (&r)[kMaxPieces]) {
+      const int64_t k0 = c * KC;
+      const float* abase = a.A + k0 * a.lda;
+      const float* bbase = a.B + k0 * a.ldb;
+      const int rows_left = (int)min((int64_t)KC, a.K - k0);
+#pragma unroll
+      for (int b = 0; b < kMaxPieces; ++b) {
+        r[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (goff[b] >= 0 && ((meta[b] >> 20) & 63) < rows_left)
+          r[b] = *reinterpret_cast<const float4*>(((meta[b] >> 30) ? abase : bbase) + goff[b]);
+      }
+    };
+    auto consume = [&](uint32_t it, const float4 (&r)[kMaxPieces]) {
       const int s = it % kStages;
       mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
       uint8_t* st = smem + s * stage_bytes;
-      const int64_t k0 = c * kKC;
-      for (int p0 = tid; p0 < total; p0 += kLoadWarps * 32 * kBatch) {
-        float4 v[kBatch];
-        int off[kBatch];
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-          const int p = p0 + b * kLoadWarps * 32;
-          v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-          off[b] = -1;
-          if (p < total) {
-            const bool is_a = p < pa;
-            const int q = is_a ? p : p - pa;
-            const int k = is_a ? (q >> 5) : (q / npr);
-            const int c4 = is_a ? (q & 31) : (q - k * npr);
-            const int64_t kr = k0 + k;
-            const int col = (is_a ? m0 : 0) + 4 * c4;
-            if (kr < a.K && col < (is_a ? a.M : a.N))
-              v[b] = *reinterpret_cast<const float4*>((is_a ? a.A + kr * a.lda : a.B + kr * a.ldb) + col);
-            const int r = k & 3, cc = c4 & 7;
-            off[b] = (is_a ? 0 : 2 * a_bytes) + (k >> 2) * (is_a ? 2048 : b_atoms_bytes) + (c4 >> 3) * 512 + r * 128 +
-                     ((((cc >> 1) ^ r) << 5) | ((cc & 1) << 4));
-          }
-        }
-#pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-          if (off[b] >= 0) {
-            const int lo_off = off[b] < 2 * a_bytes ? a_bytes : b_bytes;
-            float4 hi, lo;
-            hi.x = tf32_rna(v[b].x); lo.x = tf32_rna(v[b].x - hi.x);
-            hi.y = tf32_rna(v[b].y); lo.y = tf32_rna(v[b].y - hi.y);
-            hi.z = tf32_rna(v[b].z); lo.z = tf32_rna(v[b].z - hi.z);
-            hi.w = tf32_rna(v[b].w); lo.w = tf32_rna(v[b].w - hi.w);
-            *reinterpret_cast<float4*>(st + off[b]) = hi;
-            *reinterpret_cast<float4*>(st + off[b] + lo_off) = lo;
-          }
+      for (int b = 0; b < kMaxPieces; ++b) {
+        if (meta[b] >= 0) {
+          const int off = meta[b] & 0xFFFFF;
+          const int lo_off = (meta[b] >> 30) ? a_bytes : b_bytes;
+          float4 hi, lo;
+          split_tf32(r[b].x, hi.x, lo.x);
+          split_tf32(r[b].y, hi.y, lo.y);
+          split_tf32(r[b].z, hi.z, lo.z);
+          split_tf32(r[b].w, hi.w, lo.w);
+          *reinterpret_cast<float4*>(st + off) = hi;
+          *reinterpret_cast<float4*>(st + off + lo_off) = lo;
         }
       }
       proxy_fence();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+    };
+    float4 r0[kMaxPieces], r1[kMaxPieces];
+    if (c_begin < c_end) issue(c_begin, r0);
+    uint32_t it = 0;
+    for (int64_t c = c_begin; c < c_end; c += 2, it += 2) {
+      if (c + 1 < c_end) issue(c + 1, r1);
+      consume(it, r0);
+      if (c + 1 < c_end) {
+        if (c + 2 < c_end) issue(c + 2, r0);
+        consume(it + 1, r1);
+      }
     }
   } else {
     // ===================== MMA issuer ==============================================================================
@@ -665,8 +697,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args 
         const uint32_t sa = smem_u32(smem + s * stage_bytes);
         const uint32_t sa_lo = sa + a_bytes, sb = sa + 2 * a_bytes, sb_lo = sb + b_bytes;
         const uint32_t b_group = (uint32_t)(NP / 32) * 512u;  // one 4-k group of B; an MMA (K = 8) reads two
-#pragma unroll
-        for (int kg = 0; kg < kKC / 8; ++kg) {
+        for (int kg = 0; kg < KC / 8; ++kg) {
           for (int sub = 0; sub < nsub; ++sub) {
             const int width = min(256, NP - sub * 256);
             const uint32_t idesc = make_idesc(width);
@@ -730,8 +761,15 @@ __global__ void tn_reduce_kernel(const float* __restrict__ part, int splits, int
   }
 }
 
+// 64 rows per stage when the pieces of a stage still fit the loaders' registers and two stages fit shared memory
+static inline int kc_for(int M, int NP) {
+  const int ma = ((M < 128 ? M : 128) + 31) & ~31;
+  const bool fits = 64 * (ma / 4 + NP / 4) <= kMaxPieces * kLoadWarps * 32 &&
+                    kStages * 2 * (64 * 512 + 64 * NP * 4) <= 200 * 1024;
+  return fits ? 64 : 32;
+}
 static inline int splits_for(int64_t K, int mblocks, int sms) {
-  const int64_t chunks = (K + kKC - 1) / kKC;
+  const int64_t chunks = (K + 63) / 64;
   int64_t s = sms / mblocks;
   if (s < 1) s = 1;
   if (s > chunks) s = chunks;
@@ -775,10 +813,10 @@ int segnn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ld
   int tmem_cols = 32;
   while (tmem_cols < NP) tmem_cols <<= 1;
   const int splits = eg::tn::splits_for(K, mblocks, device_sms());
-  eg::tn::Args a{A, lda, B, ldb, K, M, N, NP, tmem_cols, workspace};
-  const size_t smem = 1024 + (size_t)eg::tn::kStages * (2 * (eg::tn::kKC / 8) * 4 * 1024 +
-                                                        2 * (eg::tn::kKC / 8) * (NP / 32) * 1024) + 64;
-  if (smem > 227 * 1024) {
+  const int kc = eg::tn::kc_for(M, NP);
+  eg::tn::Args a{A, lda, B, ldb, K, M, N, NP, kc, tmem_cols, workspace};
+  const size_t smem = 1024 + (size_t)eg::tn::kStages * 2 * ((size_t)kc * 512 + (size_t)kc * NP * 4) + 64;
+  if (smem > 227 * 1024 || kc * (128 / 4 + NP / 4) > eg::tn::kMaxPieces * eg::tn::kLoadWarps * 32) {
     set_error("segnn_gemm_tn_tf32x3: N=%d needs %zu bytes of shared memory", N, smem);
     return SEGNN_E_UNSUPPORTED;
   }

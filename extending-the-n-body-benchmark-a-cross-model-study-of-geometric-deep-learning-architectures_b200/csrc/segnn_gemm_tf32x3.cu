@@ -28,6 +28,7 @@ constexpr int kLoadWarps = 8;
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = kLoadWarps;
 constexpr int kThreads = (kLoadWarps + 1 + kEpiWarps) * 32;
+constexpr int kStgLd = 36;    // floats per row of an epilogue staging tile (32 + 4: 16-byte aligned rows)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -111,7 +112,7 @@ __global__ void gemm_prep_b_kernel(const float* __restrict__ B, int ldb, int K, 
     const int row = (int)((idx / kKC) % NP);
     const int c = (int)((idx / ((long long)kKC * NP)) % chunks);
     const int nb = (int)(idx / ((long long)kKC * NP * chunks));
-    const int k = c * kKC + kk, col = nb * kNMax + row;
+    const int k = c * kKC + kk, col = nb * NP + row;
     const float v = (k < K && col < N) ? B[(long long)k * ldb + col] : 0.f;
     const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
     const long long base = ((long long)(nb * chunks + c) * 2) * NP * kKC;
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = blockIdx.y;
-  const int n0 = nb * kNMax;
-  const int ncols = min(kNMax, N - n0);  // live columns of this block (<= NP)
+  const int n0 = nb * NP;
+  const int ncols = max(0, min(NP, N - n0));  // live columns of this block (<= NP)
   const long long tiles = (M + kBM - 1) / kBM;
 
   if (warp == kMmaWarp) {
@@ -165,62 +166,93 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp < kLoadWarps) {
     // ===================== loaders: fp32 rows -> (hi, lo) tf32 swizzled chunks; lane 0 of warp 0 copies B ==========
+    // The global loads of a chunk are issued two chunks before it is converted (three register sets, the (tile, chunk)
+    // sequence flattened so that the prefetch crosses tile boundaries): ~48 KB per SM in flight instead of 16 KB, which
+    // is what lets a GEMM with K of one to six chunks stream its rows at HBM speed.
     const float* bsrc = Bimg + (long long)nb * chunks * 2 * NP * kKC;
-    uint32_t it = 0;
     const bool vec_ok = (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      for (int c = 0; c < chunks; ++c, ++it) {
-        const int s = it % kStages;
-        mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-        uint8_t* st = smem + s * stage_bytes;
-        if (tid == 0) {
-          const uint32_t bytes = 2u * (uint32_t)b_bytes;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(bytes)
-                       : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           smem_u32(st + 2 * a_bytes)),
-                       "l"(bsrc + (long long)c * 2 * NP * kKC), "r"(bytes), "r"(smem_u32(&full[s]))
-                       : "memory");
-        }
-        const int k0 = c * kKC;
+    const long long my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total = my_tiles * chunks;
+    constexpr int kPieces = (kBM * 4) / (kLoadWarps * 32);
+    auto issue = [&](long long it, float4 (&r)[2 * kPieces]) {
+      const long long tile = blockIdx.x + (it / chunks) * gridDim.x;
+      const int k0 = (int)(it % chunks) * kKC;
 #pragma unroll
-        for (int i = 0; i < (kBM * 4) / (kLoadWarps * 32); ++i) {
-          const int p = tid + i * (kLoadWarps * 32);
-          const int row = p >> 2, q = p & 3;
-          const long long gr = tile * kBM + row;
-          const int k = k0 + 8 * q;
-          float v[8];
+      for (int i = 0; i < kPieces; ++i) {
+        const int p = tid + i * (kLoadWarps * 32);
+        const int row = p >> 2, q = p & 3;
+        const long long gr = tile * kBM + row;
+        const int k = k0 + 8 * q;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        if (gr < M) {
+          const float* src = A + gr * lda + k;
+          if (vec_ok && k + 8 <= K) {
+            a0 = *reinterpret_cast<const float4*>(src);
+            a1 = *reinterpret_cast<const float4*>(src + 4);
+          } else {
+            float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          if (gr < M) {
-            const float* src = A + gr * lda + k;
-            if (vec_ok && k + 8 <= K) {
-              const float4 a0 = *reinterpret_cast<const float4*>(src);
-              const float4 a1 = *reinterpret_cast<const float4*>(src + 4);
-              v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
-              v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (k + j < K) v[j] = src[j];
-            }
+            for (int j = 0; j < 8; ++j) v[j] = (k + j < K) ? src[j] : 0.f;
+            a0 = make_float4(v[0], v[1], v[2], v[3]);
+            a1 = make_float4(v[4], v[5], v[6], v[7]);
           }
-          float hi[8], lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            hi[j] = tf32_rna(v[j]);
-            lo[j] = tf32_rna(v[j] - hi[j]);
-          }
-          uint8_t* rowp = st + row * 128;
-          const int c0 = ((2 * q) ^ (row & 7)) << 4, c1 = ((2 * q + 1) ^ (row & 7)) << 4;
-          *reinterpret_cast<float4*>(rowp + c0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(rowp + c1) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-          *reinterpret_cast<float4*>(rowp + a_bytes + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<float4*>(rowp + a_bytes + c1) = make_float4(lo[4], lo[5], lo[6], lo[7]);
         }
-        proxy_fence();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
+        r[2 * i] = a0;
+        r[2 * i + 1] = a1;
+      }
+    };
+    auto consume = [&](long long it, const float4 (&r)[2 * kPieces]) {
+      const int s = (int)(it % kStages);
+      const int c = (int)(it % chunks);
+      mbar_wait(&empty[s], (uint32_t)((it / kStages) & 1) ^ 1);
+      uint8_t* st = smem + s * stage_bytes;
+      if (tid == 0) {
+        const uint32_t bytes = 2u * (uint32_t)b_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(st + 2 * a_bytes)),
+                     "l"(bsrc + (long long)c * 2 * NP * kKC), "r"(bytes), "r"(smem_u32(&full[s]))
+                     : "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < kPieces; ++i) {
+        const int p = tid + i * (kLoadWarps * 32);
+        const int row = p >> 2, q = p & 3;
+        const float v[8] = {r[2 * i].x, r[2 * i].y, r[2 * i].z, r[2 * i].w,
+                            r[2 * i + 1].x, r[2 * i + 1].y, r[2 * i + 1].z, r[2 * i + 1].w};
+        // hi = tf32(v) rounded to nearest on the integer pipe (cvt.rna.tf32 is an XU-pipe instruction, 16 lanes per
+        // clock and SM); lo = v - hi is exact and the tensor core ignores its low 13 mantissa bits (2^-22 of v)
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          hi[j] = __uint_as_float((__float_as_uint(v[j]) + 0x1000u) & 0xFFFFE000u);
+          lo[j] = v[j] - hi[j];
+        }
+        uint8_t* rowp = st + row * 128;
+        const int c0 = ((2 * q) ^ (row & 7)) << 4, c1 = ((2 * q + 1) ^ (row & 7)) << 4;
+        *reinterpret_cast<float4*>(rowp + c0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(rowp + c1) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<float4*>(rowp + a_bytes + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(rowp + a_bytes + c1) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+      }
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    };
+    float4 r0[2 * kPieces], r1[2 * kPieces], r2[2 * kPieces];
+    if (0 < total) issue(0, r0);
+    if (1 < total) issue(1, r1);
+    for (long long it = 0; it < total; it += 3) {
+      if (it + 2 < total) issue(it + 2, r2);
+      consume(it, r0);
+      if (it + 1 < total) {
+        if (it + 3 < total) issue(it + 3, r0);
+        consume(it + 1, r1);
+      }
+      if (it + 2 < total) {
+        if (it + 4 < total) issue(it + 4, r1);
+        consume(it + 2, r2);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -252,40 +284,60 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> HBM, one row per lane ===================================================
+    // ===================== epilogue: TMEM -> registers (lane = row) -> per-warp staging tile -> HBM ===================
+    // A lane holds 32 consecutive columns of ITS row; storing them directly makes every lane of a store instruction hit
+    // a different 128-byte line (32 partial-sector requests per instruction, the limiter of the first version).  The
+    // 32 x 32 block goes through shared memory instead and leaves as 128-byte row segments, four rows per instruction.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const bool vec_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (n0 & 3) == 0;
+    float* stg = reinterpret_cast<float*>(smem + kStages * stage_bytes + 256) + quad * (32 * kStgLd);
+    const int sub = lane >> 3, c4 = lane & 7;
     uint32_t dcount = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++dcount) {
       const int db = dcount & 1;
       mbar_wait(&dfull[db], (dcount >> 1) & 1);
       tc_fence_after();
-      const long long gr = tile * kBM + quad * 32 + lane;
-      float* dst = C + gr * ldc + n0;
-      for (int col = 0; col < NP; col += 16) {
-        uint32_t u[16];
+      for (int col = 0; col < NP; col += 32) {
+        uint32_t u[32];
+        const bool two = col + 16 < NP;
         SEGNN_G3_LD16(tmem + lane_base + db * kNMax + col, u);
+        if (two) SEGNN_G3_LD16(tmem + lane_base + db * kNMax + col + 16, (u + 16));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (col + 16 >= NP) {  // the last block of the accumulator is in registers
+        if (col + 32 >= NP) {  // the last block of the accumulator is in registers
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&dempty[db]);
         }
-        if (gr < M) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            if (vec_ok && col + j + 4 <= ncols) {
-              *reinterpret_cast<float4*>(dst + col + j) =
-                  make_float4(__uint_as_float(u[j]), __uint_as_float(u[j + 1]), __uint_as_float(u[j + 2]),
-                              __uint_as_float(u[j + 3]));
-            } else {
+        for (int j = 0; j < 8; ++j) {
+          if (j < 4 || two)
+            *reinterpret_cast<float4*>(stg + lane * kStgLd + 4 * j) =
+                make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]), __uint_as_float(u[4 * j + 2]),
+                            __uint_as_float(u[4 * j + 3]));
+        }
+        __syncwarp();
+        const int ccol = col + 4 * c4;
+        if (ccol < ncols && (c4 < 4 || two)) {
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                if (col + j + jj < ncols) dst[col + j + jj] = __uint_as_float(u[j + jj]);
+          for (int rr = 0; rr < 8; ++rr) {
+            const int row = rr * 4 + sub;
+            const long long gr = tile * kBM + quad * 32 + row;
+            if (gr < M) {
+              const float4 v = *reinterpret_cast<const float4*>(stg + row * kStgLd + 4 * c4);
+              float* dst = C + gr * ldc + n0 + ccol;
+              if (vec_ok && ccol + 4 <= ncols) {
+                *reinterpret_cast<float4*>(dst) = v;
+              } else {
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                  if (ccol + jj < ncols) dst[jj] = vv[jj];
+              }
             }
           }
         }
+        __syncwarp();
       }
     }
   }
@@ -294,8 +346,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
+// N is split into ceil(N / 128) column blocks of equal width (a multiple of 16): N = 192 -> 2 x 96, not 128 + 64
 static inline int padded_n(int N) {
-  const int blk = N < kNMax ? N : kNMax;
+  const int nblocks = (N + kNMax - 1) / kNMax;
+  const int blk = (N + nblocks - 1) / nblocks;
   return (blk + 15) & ~15;
 }
 
@@ -327,7 +381,8 @@ int segnn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, 
   g3::gemm_prep_b_kernel<<<(unsigned)((prep_total + 255) / 256 < 1184 ? (prep_total + 255) / 256 : 1184), 256, 0, s>>>(
       B, (int)ldb, K, N, NP, chunks, workspace);
   SEGNN_CHECK_LAUNCH();
-  const size_t smem = 1024 + (size_t)g3::kStages * (2 * g3::kBM * 128 + 2 * NP * 128) + 16 * sizeof(uint64_t) + 16;
+  const size_t smem = 1024 + (size_t)g3::kStages * (2 * g3::kBM * 128 + 2 * NP * 128) + 256 +
+                      (size_t)g3::kEpiWarps * 32 * g3::kStgLd * sizeof(float);
   cudaError_t err = cudaFuncSetAttribute(g3::gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) {
     set_error("segnn_gemm_tf32x3: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(err));

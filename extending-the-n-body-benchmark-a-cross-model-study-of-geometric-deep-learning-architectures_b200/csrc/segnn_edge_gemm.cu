@@ -14,7 +14,8 @@
 //   G2   gemm_tn_tf32x3         dWcat = XS^T dY, dW_vv = XV^T dDV    (K = rows, split over the CTAs, partial sums in
 //                               TMEM, fixed-order reduction: bit-identical from run to run, no atomics)
 //   G3   segnn_gemm_tf32x3      dXS = dY * Wcat^T, dXV = dDV * W_vv^T
-//   E3   msg1_bwd_kernel<PASS>  gate / combine backward, sums over senders (dP, d w_edge1) and over receivers (dQ)
+//   E3   msg1_bwd_tile_kernel   gate / combine backward on 32 x 32 (receiver, sender) tiles: per-tile partial sums over
+//                               senders (dP, d w_edge1) and receivers (dQ), then a fixed-order reduction over the tiles
 // Per-edge tensors live in a caller-provided workspace for one chunk of graphs at a time (16 n floats per row), never
 // for the whole batch; every kernel streams them once at HBM speed, the GEMMs run on tcgen05.
 #include "segnn_common.cuh"
@@ -22,13 +23,27 @@
 namespace segnn {
 namespace eg {
 
-__device__ __forceinline__ float silu_gate_grad(float x) {
-  const float s = sigmoid_acc(x);
-  return kCSilu * s * (1.0f + x * (1.0f - s));
+// Gates of this file: sigmoid(x) = rcp.rn(1 + ex2.approx(-x log2 e)), ~1e-7 relative for the pre-activations that occur
+// (|x| of a few units; the error grows like |x| * 6e-8), a fifth of the instructions of 1 / (1 + expf(-x)): the
+// elementwise kernels below are bound by instruction latency, not by HBM.
+__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_gate_f(float x) { return kCSilu * x * sigmoid_f(x); }
+__device__ __forceinline__ float sig_gate_f(float x) { return kCSig * sigmoid_f(x); }
+// value and derivative from one sigmoid
+__device__ __forceinline__ void silu_gate_vg(float x, float& val, float& grad) {
+  const float s = sigmoid_f(x);
+  val = kCSilu * x * s;
+  grad = kCSilu * s * (1.0f + x * (1.0f - s));
 }
-__device__ __forceinline__ float sig_gate_grad(float x) {
-  const float s = sigmoid_acc(x);
-  return kCSig * s * (1.0f - s);
+__device__ __forceinline__ void sig_gate_vg(float x, float& val, float& grad) {
+  const float s = sigmoid_f(x);
+  val = kCSig * s;
+  grad = kCSig * s * (1.0f - s);
+}
+__device__ __forceinline__ float silu_gate_grad(float x) {
+  float v, g;
+  silu_gate_vg(x, v, g);
+  return g;
 }
 
 constexpr int kRecv = 4;    // receivers per block of E1
@@ -116,11 +131,11 @@ __global__ void __launch_bounds__(96 * 4) msg1_rows_kernel(const RowArgs a, floa
         const float zs = S[0] + ax * S[3] + ay * S[6] + az * S[9] + len * wd0s + mm * wm0s;
         const float zg = S[1] + ax * S[4] + ay * S[7] + az * S[10] + len * wd0g + mm * wm0g;
         const float t = S[2] + len * wd1 + mm * wm1;
-        const float gg = sig_gate(zg);
+        const float gg = sig_gate_f(zg);
         const float vx = gg * (ax * t + S[5]), vy = gg * (ay * t + S[8]), vz = gg * (az * t + S[11]);
         const int64_t row = (gl * N + i0 + r) * N + j;
         float* xr = xs + row * 2 * n;
-        xr[w] = silu_gate(zs);
+        xr[w] = silu_gate_f(zs);
         xr[n + w] = ax * vx + ay * vy + az * vz;
         float* vr = xv + row * n3;
         vr[w] = vx;
@@ -201,7 +216,7 @@ __global__ void __launch_bounds__(96 * kSY)
       const float* dr = dv + row * n3;
       const float ys = yr[w] + b2s, yg = yr[n + w] + b2g, t1 = yr[2 * n + w];
       const float dx = dr[w], dy = dr[n + w], dz = dr[2 * n + w];
-      const float ms = silu_gate(ys), gt = sig_gate(yg);
+      const float ms = silu_gate_f(ys), gt = sig_gate_f(yg);
       const float mx = gt * fmaf(gs[t][0], t1, dx), my = gt * fmaf(gs[t][1], t1, dy), mz = gt * fmaf(gs[t][2], t1, dz);
       acc[0] += ms;
       acc[1] += mx;
@@ -278,14 +293,16 @@ __global__ void __launch_bounds__(96 * kSY)
       float* dr = dv + row * n3;
       const float ax = gs[t][0], ay = gs[t][1], az = gs[t][2], valid = gs[t][3];
       const float ys = yr[w] + b2s, yg = yr[n + w] + b2g, t1 = yr[2 * n + w];
-      const float ms = silu_gate(ys), gt = sig_gate(yg);
+      float ms, dsilu, gt, dsig;
+      silu_gate_vg(ys, ms, dsilu);
+      sig_gate_vg(yg, gt, dsig);
       const float ux = fmaf(ax, t1, dr[w]), uy = fmaf(ay, t1, dr[n + w]), uz = fmaf(az, t1, dr[2 * n + w]);
       const float dms = valid * (As * G[0] + Bs * ms + Cs);
       const float dmx = valid * (Av * G[1] + Bv * gt * ux);
       const float dmy = valid * (Av * G[2] + Bv * gt * uy);
       const float dmz = valid * (Av * G[3] + Bv * gt * uz);
-      const float dys = dms * silu_gate_grad(ys);
-      const float dyg = sig_gate_grad(yg) * (dmx * ux + dmy * uy + dmz * uz);
+      const float dys = dms * dsilu;
+      const float dyg = dsig * (dmx * ux + dmy * uy + dmz * uz);
       const float dux = gt * dmx, duy = gt * dmy, duz = gt * dmz;
       yr[w] = dys;
       yr[n + w] = dyg;
@@ -306,33 +323,50 @@ __global__ void __launch_bounds__(96 * kSY)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// E3: backward of the message_layer_1 gate / combine.  block = one stationary node; PASS 0: receiver (dP, d w_edge1
-// rows), PASS 1: sender (dQ).  dxs [rows][2n] = gradient of (s', v'.a), dxv [rows][3][n] = gradient of v'.
+// E3 (one pass): the pre-activation of message_layer_1 depends on P_i + Q_j only, so every edge contributes the SAME
+// twelve numbers c_ij to dP_i and to dQ_j.  block = (32 receivers) x (32 senders) of one graph; thread = (channel,
+// sender lane).  c_ij is accumulated over the thread's senders in registers (dP side; summed over the sender lanes
+// through shared memory once per receiver) and into a shared-memory tile owned per (sender, channel) by exactly one
+// thread (dQ side).  Each block writes its partial sums; tile_reduce_kernel adds them in tile order (deterministic).
+// dxs / dxv are read once (the two-pass form read them twice and recomputed the gates twice).
 // ---------------------------------------------------------------------------------------------------------------
-template <int PASS>
-__global__ void __launch_bounds__(96 * kSY)
-    msg1_bwd_kernel(const RowArgs a, const float* __restrict__ dxs, const float* __restrict__ dxv,
-                    float* __restrict__ dout, float* __restrict__ dwe_partial) {
+constexpr int kTile = 32;
+
+__global__ void __launch_bounds__(512)
+    msg1_bwd_tile_kernel(const RowArgs a, const float* __restrict__ dxs, const float* __restrict__ dxv, int tiles,
+                         float* __restrict__ dp_part, float* __restrict__ dq_part, float* __restrict__ dwe_part) {
   extern __shared__ __align__(16) float smem[];
-  float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);
-  float* red = smem + kTileO * 8;
-  const int w = threadIdx.x, y = threadIdx.y, NT = blockDim.x;
+  const int w = threadIdx.x, y = threadIdx.y, NT = blockDim.x, SY = blockDim.y;
+  float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);          // [32 * 32][8]
+  float* dq = smem + kTile * kTile * 8;                          // [32][12][NT]
+  float* red = dq + kTile * 12 * NT;                             // [SY][18][NT]
   const int n = a.n, N = a.N, n3 = 3 * n;
-  const int64_t rl = blockIdx.x;
-  const int64_t gl = rl / N;
-  const int ir = (int)(rl - gl * N);
-  const int64_t base = a.node0 + gl * N;
+  const int jt = blockIdx.x % tiles, it_ = (blockIdx.x / tiles) % tiles;
+  const int64_t gl = blockIdx.x / (tiles * tiles);
+  const int i0 = it_ * kTile, j0 = jt * kTile;
+  const int64_t base = a.node0 + gl * N;        // first node of the graph
+  const int64_t lbase = gl * N;                 // the same, local to the chunk
   const bool act = w < n;
-  float st[12];
+  const int tid = y * NT + w, nthreads = NT * SY;
+  for (int t = tid; t < kTile * kTile; t += nthreads) {
+    const int ii = t / kTile, jj = t % kTile;
+    const int i = min(i0 + ii, N - 1), j = min(j0 + jj, N - 1);
+    const int64_t ni = base + i, nj = base + j;
+    float ux, uy, uz, len;
+    unit_vec(a.pos[nj * 3 + 0] - a.pos[ni * 3 + 0], a.pos[nj * 3 + 1] - a.pos[ni * 3 + 1],
+             a.pos[nj * 3 + 2] - a.pos[ni * 3 + 2], ux, uy, uz, len);
+    gs[t][0] = kY1 * ux;
+    gs[t][1] = kY1 * uy;
+    gs[t][2] = kY1 * uz;
+    gs[t][3] = (i0 + ii < N && j0 + jj < N && i != j) ? 1.0f : 0.0f;
+    gs[t][4] = len;
+    gs[t][5] = a.mass[nj] * a.mass[ni];
+  }
+  for (int jj = y; jj < kTile; jj += SY)
+#pragma unroll
+    for (int v = 0; v < 12; ++v) dq[(jj * 12 + v) * NT + w] = 0.f;
   float wd0s = 0.f, wd0g = 0.f, wm0s = 0.f, wm0g = 0.f, wd1 = 0.f, wm1 = 0.f;
-#pragma unroll
-  for (int k = 0; k < 12; ++k) st[k] = 0.f;
   if (act) {
-    const float* sr = (PASS == 0 ? a.pp : a.qq) + (base + ir) * 4 * n3;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) st[c * 3 + k] = sr[c * n3 + k * n + w];
     wd0s = a.w_edge1[w];
     wd0g = a.w_edge1[n + w];
     wm0s = a.w_edge1[2 * n + w];
@@ -340,54 +374,54 @@ __global__ void __launch_bounds__(96 * kSY)
     wd1 = a.w_edge1[4 * n + w];
     wm1 = a.w_edge1[5 * n + w];
   }
-  constexpr int V = PASS == 0 ? 18 : 12;
-  float acc[V];
+  __syncthreads();
+  const int ilim = min(kTile, N - i0), jlim = min(kTile, N - j0);
+  for (int ii = 0; ii < ilim; ++ii) {
+    const int i = i0 + ii;
+    float acc[18];
 #pragma unroll
-  for (int v = 0; v < V; ++v) acc[v] = 0.f;
-  for (int o0 = 0; o0 < N; o0 += kTileO) {
-    __syncthreads();
-    node_tile_geometry(a.pos, a.mass, base, N, ir, o0, PASS == 0 ? 1.0f : -1.0f, gs, y * NT + w, NT * kSY);
-    __syncthreads();
-    if (!act) continue;
-    const int lim = min(kTileO, N - o0);
-    for (int t = y; t < lim; t += kSY) {
-      const float valid = gs[t][3];
-      if (valid == 0.f) continue;
-      const int oo = o0 + t;
-      const int64_t row = PASS == 0 ? (rl * N + oo) : ((gl * N + oo) * N + ir);
-      const float* xr = dxs + row * 2 * n;
-      const float* vr = dxv + row * n3;
-      const float d0 = xr[w], d1 = xr[n + w], d2 = vr[w], d3 = vr[n + w], d4 = vr[2 * n + w];
-      const float* orow = (PASS == 0 ? a.qq : a.pp) + (base + oo) * 4 * n3;
-      float S[12];
+    for (int v = 0; v < 18; ++v) acc[v] = 0.f;
+    if (act) {
+      float st[12];
+      const float* sr = a.pp + (base + i) * 4 * n3;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) S[c * 3 + k] = st[c * 3 + k] + orow[c * n3 + k * n + w];
-      const float ax = gs[t][0], ay = gs[t][1], az = gs[t][2], len = gs[t][4], mm = gs[t][5];
-      const float zs = S[0] + ax * S[3] + ay * S[6] + az * S[9] + len * wd0s + mm * wm0s;
-      const float zg = S[1] + ax * S[4] + ay * S[7] + az * S[10] + len * wd0g + mm * wm0g;
-      const float tt = S[2] + len * wd1 + mm * wm1;
-      const float zx = ax * tt + S[5], zy = ay * tt + S[8], zz = az * tt + S[11];
-      const float gg = sig_gate(zg);
-      const float tvx = d2 + ax * d1, tvy = d3 + ay * d1, tvz = d4 + az * d1;
-      const float dzs = silu_gate_grad(zs) * d0;
-      const float dzg = sig_gate_grad(zg) * (zx * tvx + zy * tvy + zz * tvz);
-      const float dzx = gg * tvx, dzy = gg * tvy, dzz = gg * tvz;
-      const float dt = ax * dzx + ay * dzy + az * dzz;
-      acc[0] += dzs;
-      acc[1] += dzg;
-      acc[2] += dt;
-      acc[3] += ax * dzs;
-      acc[4] += ax * dzg;
-      acc[5] += dzx;
-      acc[6] += ay * dzs;
-      acc[7] += ay * dzg;
-      acc[8] += dzy;
-      acc[9] += az * dzs;
-      acc[10] += az * dzg;
-      acc[11] += dzz;
-      if (PASS == 0) {
+        for (int k = 0; k < 3; ++k) st[c * 3 + k] = sr[c * n3 + k * n + w];
+#pragma unroll 2
+      for (int jj = y; jj < jlim; jj += SY) {
+        const float* g = gs[ii * kTile + jj];
+        if (g[3] == 0.f) continue;
+        const int j = j0 + jj;
+        const int64_t row = (lbase + i) * N + j;
+        const float* xr = dxs + row * 2 * n;
+        const float* vr = dxv + row * n3;
+        const float d0 = xr[w], d1 = xr[n + w], d2 = vr[w], d3 = vr[n + w], d4 = vr[2 * n + w];
+        const float* orow = a.qq + (base + j) * 4 * n3;
+        float S[12];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) S[c * 3 + k] = st[c * 3 + k] + orow[c * n3 + k * n + w];
+        const float ax = g[0], ay = g[1], az = g[2], len = g[4], mm = g[5];
+        const float zs = S[0] + ax * S[3] + ay * S[6] + az * S[9] + len * wd0s + mm * wm0s;
+        const float zg = S[1] + ax * S[4] + ay * S[7] + az * S[10] + len * wd0g + mm * wm0g;
+        const float tt = S[2] + len * wd1 + mm * wm1;
+        const float zx = ax * tt + S[5], zy = ay * tt + S[8], zz = az * tt + S[11];
+        float gg, dsig;
+        sig_gate_vg(zg, gg, dsig);
+        const float tvx = d2 + ax * d1, tvy = d3 + ay * d1, tvz = d4 + az * d1;
+        const float dzs = silu_gate_grad(zs) * d0;
+        const float dzg = dsig * (zx * tvx + zy * tvy + zz * tvz);
+        const float dzx = gg * tvx, dzy = gg * tvy, dzz = gg * tvz;
+        const float dt = ax * dzx + ay * dzy + az * dzz;
+        const float c12[12] = {dzs, dzg, dt, ax * dzs, ax * dzg, dzx, ay * dzs, ay * dzg, dzy, az * dzs, az * dzg, dzz};
+        float* dqj = dq + (jj * 12) * NT + w;
+#pragma unroll
+        for (int v = 0; v < 12; ++v) {
+          acc[v] += c12[v];
+          dqj[v * NT] += c12[v];
+        }
         acc[12] += len * dzs;
         acc[13] += len * dzg;
         acc[14] += mm * dzs;
@@ -396,21 +430,47 @@ __global__ void __launch_bounds__(96 * kSY)
         acc[17] += mm * dt;
       }
     }
-  }
-  __syncthreads();
-  lane_reduce<V>(red, acc, w, y, NT);
-  if (y == 0 && act) {
-    const int64_t r = a.node0 + rl;
-    float* o = dout + r * 4 * n3;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int v = 0; v < 18; ++v) red[(y * 18 + v) * NT + w] = acc[v];
+    __syncthreads();
+    if (y == 0 && act) {
+      const int64_t pr = ((int64_t)jt * ((int64_t)gridDim.x / ((int64_t)tiles * tiles)) * N + lbase + i);  // [jt][node]
+      float* o = dp_part + pr * 12 * n;
+      float* ow = dwe_part + pr * 6 * n;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) o[c * n3 + k * n + w] = acc[c * 3 + k];
-    if (PASS == 0) {
-      float* pw = dwe_partial + r * 6 * n;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) pw[c * n + w] = acc[12 + c];
+      for (int v = 0; v < 18; ++v) {
+        float sum = red[v * NT + w];
+        for (int yy = 1; yy < SY; ++yy) sum += red[(yy * 18 + v) * NT + w];
+        if (v < 12) o[v * n + w] = sum;
+        else ow[(v - 12) * n + w] = sum;
+      }
     }
+    __syncthreads();
+  }
+  if (act) {
+    for (int jj = y; jj < jlim; jj += SY) {
+      const int64_t pr = ((int64_t)it_ * ((int64_t)gridDim.x / ((int64_t)tiles * tiles)) * N + lbase + j0 + jj);
+      float* o = dq_part + pr * 12 * n;
+#pragma unroll
+      for (int v = 0; v < 12; ++v) o[v * n + w] = dq[(jj * 12 + v) * NT + w];
+    }
+  }
+}
+
+// out[node0 + r][e] = sum over the tiles t (in order) of part[t][r][e]
+__global__ void tile_reduce_kernel(const float* __restrict__ part, int tiles, int64_t rows, int cols,
+                                   float* __restrict__ out) {
+  const int64_t total = rows * cols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    int t = 0;
+    for (; t + 4 <= tiles; t += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += part[(int64_t)(t + k) * total + idx];
+    }
+    for (int k = 0; t < tiles; ++t, ++k) s[k] += part[(int64_t)t * total + idx];
+    out[idx] = (s[0] + s[1]) + (s[2] + s[3]);
   }
 }
 
@@ -875,7 +935,9 @@ static Plan make_plan(int N, int n, bool backward, int64_t max_chunks) {
   p.o_colsum = o;
   p.colsum_floats = 0;  // filled by the caller once the chunk size is known
   p.fixed_floats = o;
-  p.per_graph_floats = (int64_t)N * N * (backward ? 16 : 11) * n + (backward ? (int64_t)N * 2 * n : 0);
+  const int64_t tiles = (N + kTile - 1) / kTile;
+  p.per_graph_floats = (int64_t)N * N * (backward ? 16 : 11) * n + (backward ? (int64_t)N * 2 * n : 0) +
+                       (backward ? tiles * N * 30 * n : 0);  // partial dP / dQ / d w_edge1 rows per tile
   return p;
 }
 
@@ -905,16 +967,16 @@ int64_t segnn_edge_layer_gemm_workspace(int B, int N, int n, int backward, int64
   int64_t graphs = B;
   if (budget_bytes > 0) {
     const int64_t room = budget_bytes / 4 - fixed;
-    graphs = room / (p.per_graph_floats + 64 * 8);
+    graphs = room / (p.per_graph_floats + 64 * 12);
     if (graphs < 1) graphs = 1;
     if (graphs > B) graphs = B;
   }
-  return (fixed + graphs * (p.per_graph_floats + 64 * 8)) * (int64_t)sizeof(float);
+  return (fixed + graphs * (p.per_graph_floats + 64 * 12)) * (int64_t)sizeof(float);
 }
 
 static int64_t graphs_per_chunk(const eg::Plan& p, int64_t colsum_floats, int64_t ws_bytes, int B) {
   const int64_t room = ws_bytes / 4 - p.fixed_floats - eg::align64(colsum_floats);
-  int64_t graphs = room / (p.per_graph_floats + 64 * 8);
+  int64_t graphs = room / (p.per_graph_floats + 64 * 12);
   if (graphs > B) graphs = B;
   return graphs;
 }
@@ -1001,8 +1063,11 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
   const int NT = (n + 31) & ~31;
   const size_t smem_node = sizeof(float) * ((size_t)eg::kTileO * 8 + (size_t)eg::kSY * 18 * NT);
   cudaFuncSetAttribute(eg::gate2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
-  cudaFuncSetAttribute(eg::msg1_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
-  cudaFuncSetAttribute(eg::msg1_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
+  const int tiles = (N + eg::kTile - 1) / eg::kTile;
+  const int sy = NT <= 64 ? 8 : 4;  // sender lanes of the tile kernel (shared memory: 32 x 12 x NT accumulators)
+  const size_t smem_tile = sizeof(float) * ((size_t)eg::kTile * eg::kTile * 8 + (size_t)eg::kTile * 12 * NT +
+                                            (size_t)sy * 18 * NT);
+  cudaFuncSetAttribute(eg::msg1_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile);
   int chunk_idx = 0;
   for (int64_t g0 = 0; g0 < B; g0 += gpc, ++chunk_idx) {
     const int64_t gc = (B - g0 < gpc) ? B - g0 : gpc;
@@ -1039,9 +1104,23 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
     if (rc != SEGNN_OK) return rc;
     rc = segnn_gemm_tf32x3(dv, n, w2t_vv, n, 3 * rows, n, n, dxv, n, ws_g, stream);
     if (rc != SEGNN_OK) return rc;
-    eg::msg1_bwd_kernel<0><<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, dxs, dxv, dP, dwe_partial);
+    // gate / combine backward of message_layer_1 in one pass over the rows: per-tile partial sums, fixed-order reduction
+    const int64_t cn = gc * N;
+    float* dp_part = db2_rows + eg::align64(cn * 2 * n);
+    float* dq_part = dp_part + eg::align64(tiles * cn * 12 * n);
+    float* dwe_part = dq_part + eg::align64(tiles * cn * 12 * n);
+    eg::msg1_bwd_tile_kernel<<<(unsigned)(gc * tiles * tiles), dim3(NT, sy), smem_tile, s>>>(ra, dxs, dxv, tiles, dp_part,
+                                                                                           dq_part, dwe_part);
     SEGNN_CHECK_LAUNCH();
-    eg::msg1_bwd_kernel<1><<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, dxs, dxv, dQ, nullptr);
+    const int64_t node0 = g0 * N;
+    eg::tile_reduce_kernel<<<(unsigned)((cn * 12 * n + 255) / 256), 256, 0, s>>>(dp_part, tiles, cn, 12 * n,
+                                                                               dP + node0 * 12 * n);
+    SEGNN_CHECK_LAUNCH();
+    eg::tile_reduce_kernel<<<(unsigned)((cn * 12 * n + 255) / 256), 256, 0, s>>>(dq_part, tiles, cn, 12 * n,
+                                                                               dQ + node0 * 12 * n);
+    SEGNN_CHECK_LAUNCH();
+    eg::tile_reduce_kernel<<<(unsigned)((cn * 6 * n + 255) / 256), 256, 0, s>>>(dwe_part, tiles, cn, 6 * n,
+                                                                              dwe_partial + node0 * 6 * n);
     SEGNN_CHECK_LAUNCH();
   }
   eg::scatter_w2_grads_kernel<<<(6 * n * n + 255) / 256, 256, 0, s>>>(n, dwcat, dwvv, db2c, chunk_idx, dw2_ss, dw2_vs,

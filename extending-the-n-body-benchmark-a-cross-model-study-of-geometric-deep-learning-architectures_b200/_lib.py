@@ -59,7 +59,8 @@ PROTOTYPES = {
                                     _ptr, _ptr]),
     "segnn_edge_layer_gemm_workspace": (_c.c_int64, [_int, _int, _int, _int, _c.c_int64]),
     "segnn_edge_layer_gemm_fwd": (_int, [_ptr, _ptr, _int, _int, _int] + [_ptr] * 13 + [_c.c_int64, _ptr]),
-    "segnn_edge_layer_gemm_bwd": (_int, [_ptr, _ptr, _int, _int, _int] + [_ptr] * 25 + [_c.c_int64, _ptr]),
+    "segnn_edge_layer_gemm_bwd": (_int, [_ptr, _ptr, _int, _int, _int] + [_ptr] * 25 + [_c.c_int64, _ptr, _c.c_int64,
+                                                                                         _ptr]),
     "segnn_embed_bwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_head_bwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_generic_tp": (_int, [_ptr, _int, _ptr, _int, _c.c_int64, _ptr, _ptr, _int, _ptr, _ptr, _int, _ptr, _ptr]),

@@ -250,12 +250,13 @@ __global__ void __launch_bounds__(96 * kSY)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// E2b: backward of the gate of message_layer_2: (Y, DV) -> (dY, dDV) in place, bias-gradient row per receiver.
+// E2b: backward of the gate of message_layer_2: (Y, DV) -> (dY, dDV), in place or from the rows the forward kept;
+// bias-gradient row per receiver.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(96 * kSY)
-    gate2_bwd_kernel(const RowArgs a, float* __restrict__ yy, float* __restrict__ dv, const float* __restrict__ b2,
-                     const float* __restrict__ bnA, const float* __restrict__ bnB, const float* __restrict__ bnC,
-                     const float* __restrict__ dagg, float* __restrict__ db2_rows) {
+    gate2_bwd_kernel(const RowArgs a, const float* y_in, const float* dv_in, float* yy, float* dv,
+                     const float* __restrict__ b2, const float* __restrict__ bnA, const float* __restrict__ bnB,
+                     const float* __restrict__ bnC, const float* __restrict__ dagg, float* __restrict__ db2_rows) {
   extern __shared__ __align__(16) float smem[];
   float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);
   float* red = smem + kTileO * 8;
@@ -289,14 +290,16 @@ __global__ void __launch_bounds__(96 * kSY)
 #pragma unroll 2
     for (int t = y; t < lim; t += kSY) {
       const int64_t row = rl * N + o0 + t;
+      const float* yi = y_in + row * n3;   // may alias yy / dv: every element is read before it is written, by the
+      const float* di = dv_in + row * n3;  // same thread
       float* yr = yy + row * n3;
       float* dr = dv + row * n3;
       const float ax = gs[t][0], ay = gs[t][1], az = gs[t][2], valid = gs[t][3];
-      const float ys = yr[w] + b2s, yg = yr[n + w] + b2g, t1 = yr[2 * n + w];
+      const float ys = yi[w] + b2s, yg = yi[n + w] + b2g, t1 = yi[2 * n + w];
       float ms, dsilu, gt, dsig;
       silu_gate_vg(ys, ms, dsilu);
       sig_gate_vg(yg, gt, dsig);
-      const float ux = fmaf(ax, t1, dr[w]), uy = fmaf(ay, t1, dr[n + w]), uz = fmaf(az, t1, dr[2 * n + w]);
+      const float ux = fmaf(ax, t1, di[w]), uy = fmaf(ay, t1, di[n + w]), uz = fmaf(az, t1, di[2 * n + w]);
       const float dms = valid * (As * G[0] + Bs * ms + Cs);
       const float dmx = valid * (Av * G[1] + Bv * gt * ux);
       const float dmy = valid * (Av * G[2] + Bv * gt * uy);
@@ -324,32 +327,37 @@ __global__ void __launch_bounds__(96 * kSY)
 
 // ---------------------------------------------------------------------------------------------------------------
 // E3 (one pass): the pre-activation of message_layer_1 depends on P_i + Q_j only, so every edge contributes the SAME
-// twelve numbers c_ij to dP_i and to dQ_j.  block = (32 receivers) x (32 senders) of one graph; thread = (channel,
-// sender lane).  c_ij is accumulated over the thread's senders in registers (dP side; summed over the sender lanes
-// through shared memory once per receiver) and into a shared-memory tile owned per (sender, channel) by exactly one
-// thread (dQ side).  Each block writes its partial sums; tile_reduce_kernel adds them in tile order (deterministic).
-// dxs / dxv are read once (the two-pass form read them twice and recomputed the gates twice).
+// twelve numbers c_ij to dP_i and to dQ_j.  block = (32 receivers) x (16 senders) of one graph.  A warp covers 8 channels
+// x 4 sender lanes (a request reads 32-byte pieces of four rows: whole sectors), so the sum over the sender lanes is
+// two xor-shuffles and the main loop has no block-level barrier:
+//   dP side: c_ij summed over the thread's senders in registers, over the sender lanes by shuffles, one partial row per
+//            (receiver, sender tile);
+//   dQ side: a shared-memory tile [16 senders][12][channels]; every (sender, channel) cell is owned by ONE thread, which
+//            adds its receivers' terms in program order (plain read-modify-write, no atomics).
+// tile_reduce_kernel adds the partial rows in tile order: bit-identical results from run to run.  dxs / dxv are read
+// once and the gates recomputed once (the two-pass form did both twice).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kTile = 32;
+constexpr int kTI = 32, kTJ = 16, kSL = 4;
 
-__global__ void __launch_bounds__(512)
-    msg1_bwd_tile_kernel(const RowArgs a, const float* __restrict__ dxs, const float* __restrict__ dxv, int tiles,
-                         float* __restrict__ dp_part, float* __restrict__ dq_part, float* __restrict__ dwe_part) {
+__global__ void __launch_bounds__(384)
+    msg1_bwd_tile_kernel(const RowArgs a, const float* __restrict__ dxs, const float* __restrict__ dxv, int tiles_i,
+                         int tiles_j, int64_t chunk_nodes, float* __restrict__ dp_part, float* __restrict__ dq_part,
+                         float* __restrict__ dwe_part) {
   extern __shared__ __align__(16) float smem[];
-  const int w = threadIdx.x, y = threadIdx.y, NT = blockDim.x, SY = blockDim.y;
-  float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);          // [32 * 32][8]
-  float* dq = smem + kTile * kTile * 8;                          // [32][12][NT]
-  float* red = dq + kTile * 12 * NT;                             // [SY][18][NT]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sl = lane >> 3, w = warp * 8 + (lane & 7);
+  const int NC = (blockDim.x >> 5) * 8;                          // channels covered by the block (>= n)
+  float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);          // [kTI * kTJ][8]
+  float* dq = smem + kTI * kTJ * 8;                              // [kTJ][12][NC]
   const int n = a.n, N = a.N, n3 = 3 * n;
-  const int jt = blockIdx.x % tiles, it_ = (blockIdx.x / tiles) % tiles;
-  const int64_t gl = blockIdx.x / (tiles * tiles);
-  const int i0 = it_ * kTile, j0 = jt * kTile;
+  const int jt = blockIdx.x % tiles_j, it_ = (blockIdx.x / tiles_j) % tiles_i;
+  const int64_t gl = blockIdx.x / (tiles_i * tiles_j);
+  const int i0 = it_ * kTI, j0 = jt * kTJ;
   const int64_t base = a.node0 + gl * N;        // first node of the graph
   const int64_t lbase = gl * N;                 // the same, local to the chunk
   const bool act = w < n;
-  const int tid = y * NT + w, nthreads = NT * SY;
-  for (int t = tid; t < kTile * kTile; t += nthreads) {
-    const int ii = t / kTile, jj = t % kTile;
+  for (int t = threadIdx.x; t < kTI * kTJ; t += blockDim.x) {
+    const int ii = t / kTJ, jj = t % kTJ;
     const int i = min(i0 + ii, N - 1), j = min(j0 + jj, N - 1);
     const int64_t ni = base + i, nj = base + j;
     float ux, uy, uz, len;
@@ -362,9 +370,10 @@ __global__ void __launch_bounds__(512)
     gs[t][4] = len;
     gs[t][5] = a.mass[nj] * a.mass[ni];
   }
-  for (int jj = y; jj < kTile; jj += SY)
 #pragma unroll
-    for (int v = 0; v < 12; ++v) dq[(jj * 12 + v) * NT + w] = 0.f;
+  for (int q = 0; q < kTJ / kSL; ++q)
+#pragma unroll
+    for (int v = 0; v < 12; ++v) dq[((sl + kSL * q) * 12 + v) * NC + w] = 0.f;
   float wd0s = 0.f, wd0g = 0.f, wm0s = 0.f, wm0g = 0.f, wd1 = 0.f, wm1 = 0.f;
   if (act) {
     wd0s = a.w_edge1[w];
@@ -375,34 +384,35 @@ __global__ void __launch_bounds__(512)
     wm1 = a.w_edge1[5 * n + w];
   }
   __syncthreads();
-  const int ilim = min(kTile, N - i0), jlim = min(kTile, N - j0);
+  const int ilim = min(kTI, N - i0);
+  const int wc = act ? w : 0;  // inactive lanes compute on channel 0 (keeps the warp converged for the shuffles)
   for (int ii = 0; ii < ilim; ++ii) {
     const int i = i0 + ii;
     float acc[18];
 #pragma unroll
     for (int v = 0; v < 18; ++v) acc[v] = 0.f;
-    if (act) {
-      float st[12];
-      const float* sr = a.pp + (base + i) * 4 * n3;
+    float st[12];
+    const float* sr = a.pp + (base + i) * 4 * n3;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) st[c * 3 + k] = sr[c * n3 + k * n + w];
-#pragma unroll 2
-      for (int jj = y; jj < jlim; jj += SY) {
-        const float* g = gs[ii * kTile + jj];
-        if (g[3] == 0.f) continue;
+      for (int k = 0; k < 3; ++k) st[c * 3 + k] = sr[c * n3 + k * n + wc];
+#pragma unroll
+    for (int q = 0; q < kTJ / kSL; ++q) {
+      const int jj = sl + kSL * q;
+      const float* g = gs[ii * kTJ + jj];
+      if (g[3] != 0.f) {
         const int j = j0 + jj;
         const int64_t row = (lbase + i) * N + j;
         const float* xr = dxs + row * 2 * n;
         const float* vr = dxv + row * n3;
-        const float d0 = xr[w], d1 = xr[n + w], d2 = vr[w], d3 = vr[n + w], d4 = vr[2 * n + w];
+        const float d0 = xr[wc], d1 = xr[n + wc], d2 = vr[wc], d3 = vr[n + wc], d4 = vr[2 * n + wc];
         const float* orow = a.qq + (base + j) * 4 * n3;
         float S[12];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int k = 0; k < 3; ++k) S[c * 3 + k] = st[c * 3 + k] + orow[c * n3 + k * n + w];
+          for (int k = 0; k < 3; ++k) S[c * 3 + k] = st[c * 3 + k] + orow[c * n3 + k * n + wc];
         const float ax = g[0], ay = g[1], az = g[2], len = g[4], mm = g[5];
         const float zs = S[0] + ax * S[3] + ay * S[6] + az * S[9] + len * wd0s + mm * wm0s;
         const float zg = S[1] + ax * S[4] + ay * S[7] + az * S[10] + len * wd0g + mm * wm0g;
@@ -416,12 +426,13 @@ __global__ void __launch_bounds__(512)
         const float dzx = gg * tvx, dzy = gg * tvy, dzz = gg * tvz;
         const float dt = ax * dzx + ay * dzy + az * dzz;
         const float c12[12] = {dzs, dzg, dt, ax * dzs, ax * dzg, dzx, ay * dzs, ay * dzg, dzy, az * dzs, az * dzg, dzz};
-        float* dqj = dq + (jj * 12) * NT + w;
+        if (act) {
+          float* dqj = dq + (jj * 12) * NC + w;
 #pragma unroll
-        for (int v = 0; v < 12; ++v) {
-          acc[v] += c12[v];
-          dqj[v * NT] += c12[v];
+          for (int v = 0; v < 12; ++v) dqj[v * NC] += c12[v];
         }
+#pragma unroll
+        for (int v = 0; v < 12; ++v) acc[v] += c12[v];
         acc[12] += len * dzs;
         acc[13] += len * dzg;
         acc[14] += mm * dzs;
@@ -430,29 +441,32 @@ __global__ void __launch_bounds__(512)
         acc[17] += mm * dt;
       }
     }
+    // sum over the four sender lanes (lanes l, l ^ 8, l ^ 16, l ^ 24 hold the same channel): fixed association
 #pragma unroll
-    for (int v = 0; v < 18; ++v) red[(y * 18 + v) * NT + w] = acc[v];
-    __syncthreads();
-    if (y == 0 && act) {
-      const int64_t pr = ((int64_t)jt * ((int64_t)gridDim.x / ((int64_t)tiles * tiles)) * N + lbase + i);  // [jt][node]
+    for (int v = 0; v < 18; ++v) {
+      acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], 8);
+      acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], 16);
+    }
+    if (sl == 0 && act) {
+      const int64_t pr = (int64_t)jt * chunk_nodes + lbase + i;  // [sender tile][node of the chunk]
       float* o = dp_part + pr * 12 * n;
       float* ow = dwe_part + pr * 6 * n;
 #pragma unroll
-      for (int v = 0; v < 18; ++v) {
-        float sum = red[v * NT + w];
-        for (int yy = 1; yy < SY; ++yy) sum += red[(yy * 18 + v) * NT + w];
-        if (v < 12) o[v * n + w] = sum;
-        else ow[(v - 12) * n + w] = sum;
-      }
+      for (int v = 0; v < 12; ++v) o[v * n + w] = acc[v];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) ow[v * n + w] = acc[12 + v];
     }
-    __syncthreads();
   }
   if (act) {
-    for (int jj = y; jj < jlim; jj += SY) {
-      const int64_t pr = ((int64_t)it_ * ((int64_t)gridDim.x / ((int64_t)tiles * tiles)) * N + lbase + j0 + jj);
-      float* o = dq_part + pr * 12 * n;
 #pragma unroll
-      for (int v = 0; v < 12; ++v) o[v * n + w] = dq[(jj * 12 + v) * NT + w];
+    for (int q = 0; q < kTJ / kSL; ++q) {
+      const int jj = sl + kSL * q;
+      if (j0 + jj < N) {
+        const int64_t pr = (int64_t)it_ * chunk_nodes + lbase + j0 + jj;
+        float* o = dq_part + pr * 12 * n;
+#pragma unroll
+        for (int v = 0; v < 12; ++v) o[v * n + w] = dq[(jj * 12 + v) * NC + w];
+      }
     }
   }
 }
@@ -935,9 +949,9 @@ static Plan make_plan(int N, int n, bool backward, int64_t max_chunks) {
   p.o_colsum = o;
   p.colsum_floats = 0;  // filled by the caller once the chunk size is known
   p.fixed_floats = o;
-  const int64_t tiles = (N + kTile - 1) / kTile;
+  const int64_t tiles_i = (N + kTI - 1) / kTI, tiles_j = (N + kTJ - 1) / kTJ;
   p.per_graph_floats = (int64_t)N * N * (backward ? 16 : 11) * n + (backward ? (int64_t)N * 2 * n : 0) +
-                       (backward ? tiles * N * 30 * n : 0);  // partial dP / dQ / d w_edge1 rows per tile
+                       (backward ? (tiles_j * 18 + tiles_i * 12) * N * n : 0);  // partial dP, d w_edge1 / dQ rows
   return p;
 }
 
@@ -1034,7 +1048,8 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
                               const float* w2t_sv, const float* w2t_vv, const float* bn_a, const float* bn_b,
                               const float* bn_c, const float* dagg, float* dP, float* dQ, float* dw2_ss, float* dw2_vs,
                               float* dw2_sv, float* dw2_vv, float* db2, float* dwe_partial, float* workspace,
-                              int64_t workspace_bytes, segnn_stream_t stream) {
+                              int64_t workspace_bytes, const float* fwd_workspace, int64_t fwd_workspace_bytes,
+                              segnn_stream_t stream) {
   int rc = eg::check_common(B, N, n);
   if (rc != SEGNN_OK) return rc;
   if (B == 0) return SEGNN_OK;
@@ -1063,11 +1078,22 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
   const int NT = (n + 31) & ~31;
   const size_t smem_node = sizeof(float) * ((size_t)eg::kTileO * 8 + (size_t)eg::kSY * 18 * NT);
   cudaFuncSetAttribute(eg::gate2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
-  const int tiles = (N + eg::kTile - 1) / eg::kTile;
-  const int sy = NT <= 64 ? 8 : 4;  // sender lanes of the tile kernel (shared memory: 32 x 12 x NT accumulators)
-  const size_t smem_tile = sizeof(float) * ((size_t)eg::kTile * eg::kTile * 8 + (size_t)eg::kTile * 12 * NT +
-                                            (size_t)sy * 18 * NT);
+  const int tiles_i = (N + eg::kTI - 1) / eg::kTI, tiles_j = (N + eg::kTJ - 1) / eg::kTJ;
+  const int tile_warps = (n + 7) / 8;  // a warp of the tile kernel covers 8 channels x 4 sender lanes
+  const size_t smem_tile = sizeof(float) * ((size_t)eg::kTI * eg::kTJ * 8 + (size_t)eg::kTJ * 12 * tile_warps * 8);
   cudaFuncSetAttribute(eg::msg1_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile);
+  // rows kept by the forward call (XS, XV, Y, DV of ALL graphs, i.e. the forward ran as one chunk): no recompute
+  const float *kxs = nullptr, *kxv = nullptr, *kyy = nullptr, *kdv = nullptr;
+  if (fwd_workspace != nullptr) {
+    eg::Plan fp = eg::make_plan(N, n, false, B);
+    SEGNN_CHECK_ARG(graphs_per_chunk(fp, 0, fwd_workspace_bytes, B) >= B,
+                    "fwd_workspace does not hold the rows of all graphs (the forward call was chunked)");
+    const int64_t all = (int64_t)B * N * N;
+    kxs = fwd_workspace + fp.fixed_floats;
+    kxv = kxs + eg::align64(all * 2 * n);
+    kyy = kxv + eg::align64(all * 3 * n);
+    kdv = kyy + eg::align64(all * 3 * n);
+  }
   int chunk_idx = 0;
   for (int64_t g0 = 0; g0 < B; g0 += gpc, ++chunk_idx) {
     const int64_t gc = (B - g0 < gpc) ? B - g0 : gpc;
@@ -1081,23 +1107,32 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
     float* db2_rows = dxv + eg::align64(rows * 3 * n);
     eg::RowArgs ra{pos, mass, p, q, w_edge1, N, n, g0 * N};
     const int64_t blocks1 = gc * ((N + eg::kRecv - 1) / eg::kRecv);
-    // recompute: message_layer_2 input rows and pre-activations
-    eg::msg1_rows_kernel<<<(unsigned)blocks1, dim3(NT, 4), 0, s>>>(ra, xs, xv);
-    SEGNN_CHECK_LAUNCH();
-    rc = segnn_gemm_tf32x3(xs, 2 * n, wcat, 3 * n, rows, 2 * n, 3 * n, yy, 3 * n, ws_g, stream);
-    if (rc != SEGNN_OK) return rc;
-    rc = segnn_gemm_tf32x3(xv, n, w2_vv, n, 3 * rows, n, n, dv, n, ws_g, stream);
-    if (rc != SEGNN_OK) return rc;
-    // gate backward in place: (Y, DV) -> (dY, dDV)
-    eg::gate2_bwd_kernel<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, yy, dv, b2, bn_a, bn_b, bn_c, dagg,
-                                                                                 db2_rows);
+    const float *cxs = xs, *cxv = xv, *cyy = yy, *cdv = dv;
+    if (kxs != nullptr) {
+      const int64_t r0 = g0 * N * N;
+      cxs = kxs + r0 * 2 * n;
+      cxv = kxv + r0 * 3 * n;
+      cyy = kyy + r0 * 3 * n;
+      cdv = kdv + r0 * 3 * n;
+    } else {
+      // recompute: message_layer_2 input rows and pre-activations
+      eg::msg1_rows_kernel<<<(unsigned)blocks1, dim3(NT, 4), 0, s>>>(ra, xs, xv);
+      SEGNN_CHECK_LAUNCH();
+      rc = segnn_gemm_tf32x3(xs, 2 * n, wcat, 3 * n, rows, 2 * n, 3 * n, yy, 3 * n, ws_g, stream);
+      if (rc != SEGNN_OK) return rc;
+      rc = segnn_gemm_tf32x3(xv, n, w2_vv, n, 3 * rows, n, n, dv, n, ws_g, stream);
+      if (rc != SEGNN_OK) return rc;
+    }
+    // gate backward: (Y, DV) -> (dY, dDV), in place when recomputed
+    eg::gate2_bwd_kernel<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, cyy, cdv, yy, dv, b2, bn_a, bn_b,
+                                                                                 bn_c, dagg, db2_rows);
     SEGNN_CHECK_LAUNCH();
     rc = segnn_colsum(db2_rows, nullptr, gc * N, 2 * n, 0, ws_col, db2c + (int64_t)chunk_idx * 2 * n, stream);
     if (rc != SEGNN_OK) return rc;
     // weight gradients: K = rows
-    rc = segnn_gemm_tn_tf32x3(xs, 2 * n, yy, 3 * n, rows, 2 * n, 3 * n, dwcat, 3 * n, chunk_idx > 0, ws_tn, stream);
+    rc = segnn_gemm_tn_tf32x3(cxs, 2 * n, yy, 3 * n, rows, 2 * n, 3 * n, dwcat, 3 * n, chunk_idx > 0, ws_tn, stream);
     if (rc != SEGNN_OK) return rc;
-    rc = segnn_gemm_tn_tf32x3(xv, n, dv, n, 3 * rows, n, n, dwvv, n, chunk_idx > 0, ws_tn, stream);
+    rc = segnn_gemm_tn_tf32x3(cxv, n, dv, n, 3 * rows, n, n, dwvv, n, chunk_idx > 0, ws_tn, stream);
     if (rc != SEGNN_OK) return rc;
     // data gradients
     rc = segnn_gemm_tf32x3(yy, 3 * n, wcat_t, 2 * n, rows, 3 * n, 2 * n, dxs, 2 * n, ws_g, stream);
@@ -1107,19 +1142,19 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
     // gate / combine backward of message_layer_1 in one pass over the rows: per-tile partial sums, fixed-order reduction
     const int64_t cn = gc * N;
     float* dp_part = db2_rows + eg::align64(cn * 2 * n);
-    float* dq_part = dp_part + eg::align64(tiles * cn * 12 * n);
-    float* dwe_part = dq_part + eg::align64(tiles * cn * 12 * n);
-    eg::msg1_bwd_tile_kernel<<<(unsigned)(gc * tiles * tiles), dim3(NT, sy), smem_tile, s>>>(ra, dxs, dxv, tiles, dp_part,
-                                                                                           dq_part, dwe_part);
+    float* dq_part = dp_part + eg::align64(tiles_j * cn * 12 * n);
+    float* dwe_part = dq_part + eg::align64(tiles_i * cn * 12 * n);
+    eg::msg1_bwd_tile_kernel<<<(unsigned)(gc * tiles_i * tiles_j), tile_warps * 32, smem_tile, s>>>(
+        ra, dxs, dxv, tiles_i, tiles_j, cn, dp_part, dq_part, dwe_part);
     SEGNN_CHECK_LAUNCH();
     const int64_t node0 = g0 * N;
-    eg::tile_reduce_kernel<<<(unsigned)((cn * 12 * n + 255) / 256), 256, 0, s>>>(dp_part, tiles, cn, 12 * n,
+    eg::tile_reduce_kernel<<<(unsigned)((cn * 12 * n + 255) / 256), 256, 0, s>>>(dp_part, tiles_j, cn, 12 * n,
                                                                                dP + node0 * 12 * n);
     SEGNN_CHECK_LAUNCH();
-    eg::tile_reduce_kernel<<<(unsigned)((cn * 12 * n + 255) / 256), 256, 0, s>>>(dq_part, tiles, cn, 12 * n,
+    eg::tile_reduce_kernel<<<(unsigned)((cn * 12 * n + 255) / 256), 256, 0, s>>>(dq_part, tiles_i, cn, 12 * n,
                                                                                dQ + node0 * 12 * n);
     SEGNN_CHECK_LAUNCH();
-    eg::tile_reduce_kernel<<<(unsigned)((cn * 6 * n + 255) / 256), 256, 0, s>>>(dwe_part, tiles, cn, 6 * n,
+    eg::tile_reduce_kernel<<<(unsigned)((cn * 6 * n + 255) / 256), 256, 0, s>>>(dwe_part, tiles_j, cn, 6 * n,
                                                                               dwe_partial + node0 * 6 * n);
     SEGNN_CHECK_LAUNCH();
   }

@@ -348,6 +348,10 @@ def gemm_tn_tf32x3(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor]
 # (csrc/segnn_edge_gemm.cu): from this many rows = B * N * N on, and with at most this much workspace per call.
 GEMM_FORM_MIN_ROWS = 1 << 18
 GEMM_FORM_BUDGET_BYTES = 6 << 30
+# A training forward may leave the edge rows of a layer (11 n floats per row) in HBM for the backward call instead of
+# having them recomputed, when they fit this many bytes per layer (180 GB of HBM3e: 6 layers of BASELINE configuration 4
+# keep 17 GB).  0 disables it (recompute, nothing per edge stored between forward and backward).
+GEMM_FORM_KEEP_BYTES_PER_LAYER = 4 << 30
 
 
 def _use_gemm_form(batch_size: int, num_nodes: int, n: int) -> bool:
@@ -363,25 +367,42 @@ def _edge_gemm_workspace(batch_size: int, num_nodes: int, n: int, backward: bool
     return ws, nbytes
 
 
+def gemm_form_keeps_rows(batch_size: int, num_nodes: int, n: int) -> bool:
+    """True when a training forward of this size runs in GEMM form and keeps its edge rows for the backward call."""
+    if not _use_gemm_form(batch_size, num_nodes, n):
+        return False
+    need = int(lib.segnn_edge_layer_gemm_workspace(batch_size, num_nodes, n, 0, 0))
+    return 0 < need <= GEMM_FORM_KEEP_BYTES_PER_LAYER
+
+
 def edge_layer_gemm_fwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_mul=None,
-                        bn_add=None, want_moments: bool = False):
-    """segnn_edge_layer_gemm_fwd: the fp32-mode edge layer of graphs with many nodes as 3xTF32 GEMMs over edge rows."""
+                        bn_add=None, want_moments: bool = False, keep_rows: bool = False):
+    """segnn_edge_layer_gemm_fwd: the fp32-mode edge layer of graphs with many nodes as 3xTF32 GEMMs over edge rows.
+    keep_rows: also return (workspace, bytes) holding the rows of all graphs, for edge_layer_gemm_bwd(rows=...)."""
     nodes = batch_size * num_nodes
     agg = torch.empty((nodes, 4, n), dtype=torch.float32, device=pos.device)
     mom = torch.empty((nodes, 2 * n), dtype=torch.float32, device=pos.device) if want_moments else None
-    ws, nbytes = _edge_gemm_workspace(batch_size, num_nodes, n, False, pos.device)
+    if keep_rows:  # one chunk holding every graph
+        nbytes = int(lib.segnn_edge_layer_gemm_workspace(batch_size, num_nodes, n, 0, 0))
+        ws = torch.empty(nbytes // 4 + 64, dtype=torch.float32, device=pos.device)
+    else:
+        ws, nbytes = _edge_gemm_workspace(batch_size, num_nodes, n, False, pos.device)
     with torch.cuda.device(pos.device):
         check(lib.segnn_edge_layer_gemm_fwd(_p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1),
                                             _p(w2["ss"]), _p(w2["vs"]), _p(w2["sv"]), _p(w2["vv"]), _p(w2["b"]),
                                             _p(bn_mul), _p(bn_add), _p(agg), _p(mom), _p(ws), nbytes, _stream()),
               "segnn_edge_layer_gemm_fwd")
     _bump(8)
-    return (agg, mom) if want_moments else agg
+    out = (agg, mom) if want_moments else (agg,)
+    if keep_rows:
+        return out + ((ws, nbytes),)
+    return out if want_moments else agg
 
 
 def edge_layer_gemm_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg,
-                        dP=None, dQ=None, gz=None):
-    """segnn_edge_layer_gemm_bwd: same results as edge_layer_bwd (dP, dQ, message_layer_2 gradient blocks, dw_edge1)."""
+                        dP=None, dQ=None, gz=None, rows=None):
+    """segnn_edge_layer_gemm_bwd: same results as edge_layer_bwd (dP, dQ, message_layer_2 gradient blocks, dw_edge1).
+    rows: what edge_layer_gemm_fwd(keep_rows=True) returned for the same layer (skips the recompute)."""
     nodes = batch_size * num_nodes
     dev = pos.device
     f = dict(dtype=torch.float32, device=dev)
@@ -400,8 +421,10 @@ def edge_layer_gemm_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q
                                             _p(w2t["ss"]), _p(w2t["vs"]), _p(w2t["sv"]), _p(w2t["vv"]), _p(bn_a),
                                             _p(bn_b), _p(bn_c), _p(dagg), _p(dP), _p(dQ), _p(g["ss"]), _p(g["vs"]),
                                             _p(g["sv"]), _p(g["vv"]), _p(g["b"]), _p(dwe_partial), _p(ws), nbytes,
-                                            _stream()), "segnn_edge_layer_gemm_bwd")
-    _bump(24)
+                                            _p(rows[0]) if rows is not None else None,
+                                            rows[1] if rows is not None else 0, _stream()),
+              "segnn_edge_layer_gemm_bwd")
+    _bump(24 if rows is None else 18)
     return dP, dQ, g, colsum(dwe_partial)
 
 

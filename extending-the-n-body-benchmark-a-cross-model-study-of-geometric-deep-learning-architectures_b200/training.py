@@ -63,8 +63,10 @@ def unflatten_packed(leaves, spec):
 # forward (fp32 kernels), saving node-level tensors only
 # ---------------------------------------------------------------------------------------------------------------
 def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: bool, backend=None,
-                  update_running_stats: bool = True):
-    """W: packed weights (see SEGNN.packed_train). Returns (pred [nodes,6], saved)."""
+                  update_running_stats: bool = True, keep_rows: bool = False):
+    """W: packed weights (see SEGNN.packed_train). Returns (pred [nodes,6], saved).  keep_rows (a backward pass will
+    follow): large graphs, whose edge layers run in GEMM form, leave their edge rows in HBM for the backward call when
+    they fit ops.GEMM_FORM_KEEP_BYTES_PER_LAYER; everything else stores node-level tensors only."""
     be = backend or _ops
     nodes, deg = B * N, N - 1
     E = nodes * deg
@@ -74,9 +76,14 @@ def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: 
     for lw in W["layers"]:
         m1, m2, u1, u2 = lw["msg1"], lw["msg2"], lw["upd1"], lw["upd2"]
         p, q = be.node_gemm(h, None, m1, 6 * n, bias=m1["bias"], n_bias=2 * n, split=3 * n)
-        agg_raw, mom = be.edge_layer(be.MODE_FP32, pos, mass, B, N, n, p, q, m1["w_edge"], m2, None, None,
-                                     want_moments=True)
-        rec = dict(h=h, p=p, q=q, agg_raw=agg_raw)
+        rows = None
+        if keep_rows and backend is None and _ops.gemm_form_keeps_rows(B, N, n):
+            agg_raw, mom, rows = _ops.edge_layer_gemm_fwd(pos, mass, B, N, n, p, q, m1["w_edge"], m2, None, None,
+                                                          want_moments=True, keep_rows=True)
+        else:
+            agg_raw, mom = be.edge_layer(be.MODE_FP32, pos, mass, B, N, n, p, q, m1["w_edge"], m2, None, None,
+                                         want_moments=True)
+        rec = dict(h=h, p=p, q=q, agg_raw=agg_raw, rows=rows)
         if lw["bn_msg"] is not None:
             sums = be.colsum(agg_raw.view(nodes, 4 * n))
             sq = be.colsum(mom)
@@ -204,8 +211,13 @@ def backward_train(W: Dict, saved: Dict, dpred, backend=None):
             bn_a = torch.ones(2 * n, dtype=dagg.dtype, device=dagg.device)
             bn_b, bn_c = torch.zeros_like(bn_a), torch.zeros(n, dtype=dagg.dtype, device=dagg.device)
         # fused edge layer backward (recompute) -> dP, dQ, message_layer_2 and w_edge gradients
-        dP, dQ, g["msg2"], dwe = be.edge_layer_bwd(pos, mass, B, N, n, rec["p"], rec["q"], m1["w_edge"], m2, bn_a, bn_b,
-                                                   bn_c, dagg)
+        if rec.get("rows") is not None:  # the forward call left this layer's edge rows in HBM: no recompute
+            dP, dQ, g["msg2"], dwe = _ops.edge_layer_gemm_bwd(pos, mass, B, N, n, rec["p"], rec["q"], m1["w_edge"], m2,
+                                                              bn_a, bn_b, bn_c, dagg, rows=rec["rows"])
+            rec["rows"] = None  # 11 n floats per edge row go back to the allocator as soon as the layer is done
+        else:
+            dP, dQ, g["msg2"], dwe = be.edge_layer_bwd(pos, mass, B, N, n, rec["p"], rec["q"], m1["w_edge"], m2, bn_a,
+                                                       bn_b, bn_c, dagg)
         # message_layer_1 projections: [P | Q] = h @ W (+ bias on P's l=0 columns)
         def msg1_weights(h_=rec["h"], dP_=dP, dQ_=dQ):
             dw_s, dw_v = be.node_gemm_wgrad(h_, None, dP_, dQ_, 3 * n)
@@ -317,7 +329,7 @@ class SegnnTrainFunctionFlat(torch.autograd.Function):
         # load_state_dict(assign=True) replace the buffer objects without changing the map's key
         attach_bn_buffers(W, cfg["bn_buffers"])
         pred, saved = forward_train(W, cfg["n"], pos, vel, mass, cfg["B"], cfg["N"], cfg["bn_training"],
-                                    backend=cfg.get("backend"))
+                                    backend=cfg.get("backend"), keep_rows=True)
         ctx.cfg, ctx.W, ctx.saved, ctx.scale = cfg, W, saved, scale
         ctx.param_shapes = [tuple(p.shape) for p in params]
         ctx.param_dtypes = [p.dtype for p in params]
@@ -357,7 +369,7 @@ class SegnnTrainFunction(torch.autograd.Function):
         W = unflatten_packed([t.detach() for t in leaves], cfg["spec"])
         attach_bn_buffers(W, cfg["bn_buffers"])
         pred, saved = forward_train(W, cfg["n"], pos, vel, mass, cfg["B"], cfg["N"], cfg["bn_training"],
-                                    backend=cfg.get("backend"))
+                                    backend=cfg.get("backend"), keep_rows=True)
         ctx.cfg, ctx.W, ctx.saved, ctx.n_leaves = cfg, W, saved, len(leaves)
         return pred
 

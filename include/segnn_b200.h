@@ -322,7 +322,9 @@ int segnn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ld
  * gradients are bit-identical from run to run.  n must be a multiple of 4, <= 96.  workspace: 256-byte aligned,
  * segnn_edge_layer_gemm_workspace(B, N, n, backward, budget_bytes) bytes = the fixed part plus as many whole graphs per
  * chunk as fit into budget_bytes (at least one; budget_bytes <= 0: all B graphs in one chunk); the calls derive the
- * chunking from workspace_bytes. */
+ * chunking from workspace_bytes.  fwd_workspace (may be NULL): the untouched workspace of the forward call of the same
+ * layer, when that call ran as ONE chunk -- the backward call then reads the rows the forward left there instead of
+ * recomputing them (11 n floats per edge row kept alive between the two calls; it does not modify them). */
 int64_t segnn_edge_layer_gemm_workspace(int B, int N, int n, int backward, int64_t budget_bytes);
 int segnn_edge_layer_gemm_fwd(const float* pos, const float* mass, int B, int N, int n, const float* p, const float* q,
                               const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
@@ -335,7 +337,8 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
                               const float* w2t_sv, const float* w2t_vv, const float* bn_a, const float* bn_b,
                               const float* bn_c, const float* dagg, float* dP, float* dQ, float* dw2_ss, float* dw2_vs,
                               float* dw2_sv, float* dw2_vv, float* db2, float* dwe_partial, float* workspace,
-                              int64_t workspace_bytes, segnn_stream_t stream);
+                              int64_t workspace_bytes, const float* fwd_workspace, int64_t fwd_workspace_bytes,
+                              segnn_stream_t stream);
 
 /* message_layer_1 (models/segnn/segnn.py:264-279) with its weight contraction hoisted to node level, for any hidden
  * irreps: Y [nodes][ydim] holds, for every (x_i or x_j) instruction, sum_u W[u][w] x[node][u, i] at yoff + w * dim1 + i

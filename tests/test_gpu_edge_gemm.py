@@ -87,14 +87,28 @@ def test_gemm_form_backward_matches_fused_fp32(B, N, n, chunked, monkeypatch):
     dP2, dQ2, g2, dwe2 = S.ops.edge_layer_gemm_bwd(pos, mass, B, N, n, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg)
     assert torch.equal(dP1, dP2) and torch.equal(dQ1, dQ2) and torch.equal(dwe1, dwe2)
     assert all(torch.equal(g1[k], g2[k]) for k in g1), "weight gradients are bit-identical from run to run"
+    # rows kept by the forward call instead of the recompute: same bits, and the kept rows are not modified
+    agg, rows = S.ops.edge_layer_gemm_fwd(pos, mass, B, N, n, p, q, w_edge1, w2, keep_rows=True)
+    snapshot = rows[0].clone()
+    for _ in range(2):
+        dP3, dQ3, g3, dwe3 = S.ops.edge_layer_gemm_bwd(pos, mass, B, N, n, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg,
+                                                       rows=rows)
+        assert torch.equal(dP1, dP3) and torch.equal(dQ1, dQ3) and torch.equal(dwe1, dwe3)
+        assert all(torch.equal(g1[k], g3[k]) for k in g1)
+    assert torch.equal(snapshot, rows[0])
 
 
+@pytest.mark.parametrize("keep", [True, False])
 @pytest.mark.parametrize("H,L,B,N,bn_train", [(64, 2, 4, 5, True), (192, 1, 2, 20, True), (128, 2, 1, 33, False),
                                                 (128, 1, 1, 150, True)])
-def test_training_step_in_gemm_form_matches_oracle(H, L, B, N, bn_train, monkeypatch):
-    """Whole model, forward + backward, with every edge layer forced onto the GEMM form: prediction 1e-5, gradients
-    within the tolerance of tests/test_gpu_parity.py::test_training_gradients_match_oracle."""
+def test_training_step_in_gemm_form_matches_oracle(H, L, B, N, bn_train, keep, monkeypatch):
+    """Whole model, forward + backward, with every edge layer forced onto the GEMM form (edge rows kept between forward
+    and backward, or recomputed): prediction 1e-5, gradients within the tolerance of
+    tests/test_gpu_parity.py::test_training_gradients_match_oracle."""
     monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS", 0)
+    if not keep:
+        monkeypatch.setattr(S.ops, "GEMM_FORM_KEEP_BYTES_PER_LAYER", 0)
+    assert S.ops.gemm_form_keeps_rows(B, N, H // 2) == keep
     torch.manual_seed(0)
     om = O.SEGNN(hidden_features=H, num_layers=L)
     O.perturb_bn_buffers(om, seed=1)

@@ -272,22 +272,40 @@ def measure_training(S, dev, world, rank, dist, cpu_baseline):
         g = S.GraphBatch(pos=p4.reshape(-1, 3).to(dev), vel=v4.reshape(-1, 3).to(dev), mass=c4.reshape(-1, 1).to(dev),
                          num_graphs=1, n_nodes=N4)
         y4 = torch.randn(N4, 6, device=dev)
-        torch.cuda.empty_cache()
-        torch.cuda.reset_peak_memory_stats(dev)  # peak of THIS configuration, not of the rollout workload before it
-        times = []
-        for i in range(3):
-            m4.zero_grad(set_to_none=True)
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            S.target_common_loss(m4(g), y4).backward()
-            a1.record()
-            torch.cuda.synchronize()
-            times.append(a0.elapsed_time(a1))
+        def cfg4_run(keep_bytes):
+            saved = S.ops.GEMM_FORM_KEEP_BYTES_PER_LAYER
+            S.ops.GEMM_FORM_KEEP_BYTES_PER_LAYER = keep_bytes
+            try:
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats(dev)  # peak of THIS configuration, not of the workload before it
+                times = []
+                for i in range(4):
+                    m4.zero_grad(set_to_none=True)
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    S.target_common_loss(m4(g), y4).backward()
+                    a1.record()
+                    torch.cuda.synchronize()
+                    times.append(a0.elapsed_time(a1))
+                return min(times[1:]), torch.cuda.max_memory_allocated(dev) / 2 ** 30
+            finally:
+                S.ops.GEMM_FORM_KEEP_BYTES_PER_LAYER = saved
+        ms_keep, mem_keep = cfg4_run(S.ops.GEMM_FORM_KEEP_BYTES_PER_LAYER)
+        ms_rec, mem_rec = cfg4_run(0)
+        # 2 * (8 n^2 MACs forward + 8 n^2 data gradient + 8 n^2 weight gradient) per edge and layer, n = 64
+        flop4 = 999000 * LAYERS * 3 * 16 * 64 * 64
         out["cfg4_n1000_fwd_bwd"] = {
-            "config": "SEGNN 6 layers hidden 128 lmax_h 1, one N=1000 fully-connected graph (999,000 edges), fp32 "
-                      "kernels, forward + backward with recompute (no per-edge tensor stored)",
-            "ms_fwd_bwd": min(times[1:]), "edge_msgs_fwd_bwd_per_s": 999000 * LAYERS / (min(times[1:]) * 1e-3),
-            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+            "config": "SEGNN 6 layers hidden 128 lmax_h 1, one N=1000 fully-connected graph (999,000 edges), forward + "
+                      "backward, fp32-accurate: edge layers in GEMM form (3xTF32 tcgen05 GEMMs over the edge rows of "
+                      "the graph, csrc/segnn_edge_gemm.cu), the forward leaves each layer's edge rows in HBM for its "
+                      "backward call",
+            "ms_fwd_bwd": ms_keep, "edge_msgs_fwd_bwd_per_s": 999000 * LAYERS / (ms_keep * 1e-3),
+            "peak_mem_gb": mem_keep,
+            "useful_tflops": flop4 / (ms_keep * 1e-3) / 1e12,
+            "recompute_variant": {"note": "GEMM_FORM_KEEP_BYTES_PER_LAYER = 0: nothing per edge kept between forward "
+                                          "and backward, rows recomputed per layer", "ms_fwd_bwd": ms_rec,
+                                  "peak_mem_gb": mem_rec},
+            "round1_fused_fp32_kernels_ms": 207.7}
         if cpu_baseline:
             from oracle import segnn_oracle as O
             torch.set_num_threads(os.cpu_count() or 1)

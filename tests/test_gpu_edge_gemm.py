@@ -76,6 +76,7 @@ def test_gemm_form_backward_matches_fused_fp32(B, N, n, chunked, monkeypatch):
     r = lambda *s: torch.randn(*s, generator=g).cuda()
     bn_a, bn_b, bn_c = r(2 * n) * 0.5 + 1.0, r(2 * n) * 0.01, r(n) * 0.01
     dagg = r(B * N, 4, n)
+    monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS_TRAINING", 1 << 62)  # the comparison target is the fused kernel
     dP0, dQ0, g0, dwe0 = S.ops.edge_layer_bwd(pos, mass, B, N, n, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg)
     if chunked:  # room for one graph per chunk: B chunks, accumulated weight gradients
         one = int(S.ops.lib.segnn_edge_layer_gemm_workspace(1, N, n, 1, 0))
@@ -106,6 +107,7 @@ def test_training_step_in_gemm_form_matches_oracle(H, L, B, N, bn_train, keep, m
     and backward, or recomputed): prediction 1e-5, gradients within the tolerance of
     tests/test_gpu_parity.py::test_training_gradients_match_oracle."""
     monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS", 0)
+    monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS_TRAINING", 0)
     if not keep:
         monkeypatch.setattr(S.ops, "GEMM_FORM_KEEP_BYTES_PER_LAYER", 0)
     assert S.ops.gemm_form_keeps_rows(B, N, H // 2) == keep

@@ -100,8 +100,11 @@ def test_no_kernel_writes_outside_its_buffers(H, B, N):
     assert n_bufs > 20 and bad == 0, (n_bufs, bad)
 
 
+@pytest.mark.parametrize("edge_form", ["fused", "default"])
 @pytest.mark.parametrize("H,B,N", [(64, 3, 7), (192, 2, 6), (128, 1, 33)])
-def test_training_kernels_write_inside_their_buffers(H, B, N):
+def test_training_kernels_write_inside_their_buffers(H, B, N, edge_form, monkeypatch):
+    if edge_form == "fused":
+        monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS_TRAINING", 1 << 62)
     om, m = _pair(H, 2, train=True)
     pos, vel, mass = O.synthetic_system(B, N, seed=3)
     y = torch.randn(B * N, 6).cuda()
@@ -130,10 +133,13 @@ def test_forward_is_bitwise_reproducible(H, B, N, repeats):
                 assert torch.equal(m(g), first), mode
 
 
+@pytest.mark.parametrize("edge_form", ["fused", "default"])
 @pytest.mark.parametrize("H,B,N", [(64, 4, 5), (192, 2, 20), (128, 1, 70)])
-def test_gradients_are_bitwise_reproducible(H, B, N):
+def test_gradients_are_bitwise_reproducible(H, B, N, edge_form, monkeypatch):
     """The backward kernels use no atomics (message_layer_2 weight gradients go through per-thread-group slabs and a
     fixed-order reduction; every other reduction is a fixed-order column sum): identical bits on every run."""
+    if edge_form == "fused":
+        monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS_TRAINING", 1 << 62)
     _, m = _pair(H, 2, train=True)
     pos, vel, mass = O.synthetic_system(B, N, seed=5)
     y = torch.randn(B * N, 6).cuda()

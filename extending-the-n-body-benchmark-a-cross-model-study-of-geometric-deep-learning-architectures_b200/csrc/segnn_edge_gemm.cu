@@ -60,11 +60,14 @@ struct RowArgs {
 // ---------------------------------------------------------------------------------------------------------------
 // E1: rows of the message_layer_2 input.  block = (NT channels, 4 sender lanes), 4 receivers of one graph.
 // ---------------------------------------------------------------------------------------------------------------
+// NCH = hidden multiplicity n as a compile-time constant (32, 64, 96: every offset v * n becomes an immediate; the
+// address arithmetic of the runtime-n build was two thirds of the instructions of these kernels), 0 = runtime n.
+template <int NCH>
 __global__ void __launch_bounds__(96 * 4) msg1_rows_kernel(const RowArgs a, float* __restrict__ xs,
                                                          float* __restrict__ xv) {
   __shared__ float gs[kRecv][kTileJ][8];
   const int w = threadIdx.x, y = threadIdx.y;
-  const int n = a.n, N = a.N, n3 = 3 * n;
+  const int n = NCH ? NCH : a.n, N = a.N, n3 = 3 * n;
   const int bpg = (N + kRecv - 1) / kRecv;
   const int64_t gl = blockIdx.x / bpg;
   const int i0 = (int)(blockIdx.x - gl * bpg) * kRecv;
@@ -186,6 +189,7 @@ __device__ __forceinline__ void lane_reduce(float* red, float (&vals)[V], int w,
 // ---------------------------------------------------------------------------------------------------------------
 // E2f: gate of message_layer_2 + sum over senders (+ moments, folded eval BatchNorm).  block = one receiver.
 // ---------------------------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(96 * kSY)
     gate2_fwd_kernel(const RowArgs a, const float* __restrict__ yy, const float* __restrict__ dv,
                      const float* __restrict__ b2, const float* __restrict__ bn_mul, const float* __restrict__ bn_add,
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(96 * kSY)
   float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);
   float* red = smem + kTileO * 8;
   const int w = threadIdx.x, y = threadIdx.y, NT = blockDim.x;
-  const int n = a.n, N = a.N, n3 = 3 * n;
+  const int n = NCH ? NCH : a.n, N = a.N, n3 = 3 * n;
   const int64_t rl = blockIdx.x;  // receiver, local to the chunk
   const int64_t gl = rl / N;
   const int ir = (int)(rl - gl * N);
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(96 * kSY)
 // E2b: backward of the gate of message_layer_2: (Y, DV) -> (dY, dDV), in place or from the rows the forward kept;
 // bias-gradient row per receiver.
 // ---------------------------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(96 * kSY)
     gate2_bwd_kernel(const RowArgs a, const float* y_in, const float* dv_in, float* yy, float* dv,
                      const float* __restrict__ b2, const float* __restrict__ bnA, const float* __restrict__ bnB,
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(96 * kSY)
   float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);
   float* red = smem + kTileO * 8;
   const int w = threadIdx.x, y = threadIdx.y, NT = blockDim.x;
-  const int n = a.n, N = a.N, n3 = 3 * n;
+  const int n = NCH ? NCH : a.n, N = a.N, n3 = 3 * n;
   const int64_t rl = blockIdx.x;
   const int64_t gl = rl / N;
   const int ir = (int)(rl - gl * N);
@@ -339,6 +344,7 @@ __global__ void __launch_bounds__(96 * kSY)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTI = 32, kTJ = 16, kSL = 4;
 
+template <int NCH>
 __global__ void __launch_bounds__(384)
     msg1_bwd_tile_kernel(const RowArgs a, const float* __restrict__ dxs, const float* __restrict__ dxv, int tiles_i,
                          int tiles_j, int64_t chunk_nodes, float* __restrict__ dp_part, float* __restrict__ dq_part,
@@ -346,10 +352,11 @@ __global__ void __launch_bounds__(384)
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sl = lane >> 3, w = warp * 8 + (lane & 7);
-  const int NC = (blockDim.x >> 5) * 8;                          // channels covered by the block (>= n)
+  const int NC = NCH ? ((NCH + 7) & ~7) : (blockDim.x >> 5) * 8;   // channels covered by the block (>= n)
   float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);          // [kTI * kTJ][8]
-  float* dq = smem + kTI * kTJ * 8;                              // [kTJ][12][NC]
-  const int n = a.n, N = a.N, n3 = 3 * n;
+  float* dq = smem + kTI * kTJ * 8;                              // [kTJ][12 * NC + 8]: the four sender lanes of a warp
+  const int dqs = 12 * NC + 8;                                   // own consecutive senders: + 8 floats keeps them on distinct banks
+  const int n = NCH ? NCH : a.n, N = a.N, n3 = 3 * n;
   const int jt = blockIdx.x % tiles_j, it_ = (blockIdx.x / tiles_j) % tiles_i;
   const int64_t gl = blockIdx.x / (tiles_i * tiles_j);
   const int i0 = it_ * kTI, j0 = jt * kTJ;
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(384)
 #pragma unroll
   for (int q = 0; q < kTJ / kSL; ++q)
 #pragma unroll
-    for (int v = 0; v < 12; ++v) dq[((sl + kSL * q) * 12 + v) * NC + w] = 0.f;
+    for (int v = 0; v < 12; ++v) dq[(sl + kSL * q) * dqs + v * NC + w] = 0.f;
   float wd0s = 0.f, wd0g = 0.f, wm0s = 0.f, wm0g = 0.f, wd1 = 0.f, wm1 = 0.f;
   if (act) {
     wd0s = a.w_edge1[w];
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(384)
         const float dt = ax * dzx + ay * dzy + az * dzz;
         const float c12[12] = {dzs, dzg, dt, ax * dzs, ax * dzg, dzx, ay * dzs, ay * dzg, dzy, az * dzs, az * dzg, dzz};
         if (act) {
-          float* dqj = dq + (jj * 12) * NC + w;
+          float* dqj = dq + jj * dqs + w;
 #pragma unroll
           for (int v = 0; v < 12; ++v) dqj[v * NC] += c12[v];
         }
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(384)
         const int64_t pr = (int64_t)it_ * chunk_nodes + lbase + j0 + jj;
         float* o = dq_part + pr * 12 * n;
 #pragma unroll
-        for (int v = 0; v < 12; ++v) o[v * n + w] = dq[(jj * 12 + v) * NC + w];
+        for (int v = 0; v < 12; ++v) o[v * n + w] = dq[jj * dqs + v * NC + w];
       }
     }
   }
@@ -955,6 +962,26 @@ static Plan make_plan(int N, int n, bool backward, int64_t max_chunks) {
   return p;
 }
 
+struct Kernels {
+  decltype(&msg1_rows_kernel<0>) rows;
+  decltype(&gate2_fwd_kernel<0>) g2f;
+  decltype(&gate2_bwd_kernel<0>) g2b;
+  decltype(&msg1_bwd_tile_kernel<0>) tile;
+};
+template <int NCH>
+static Kernels make_kernels() {
+  return {msg1_rows_kernel<NCH>, gate2_fwd_kernel<NCH>, gate2_bwd_kernel<NCH>, msg1_bwd_tile_kernel<NCH>};
+}
+// the multiplicities of the BASELINE configurations (hidden 64 / 128 / 192) get compile-time offsets
+static Kernels kernels_for(int n) {
+  switch (n) {
+    case 32: return make_kernels<32>();
+    case 64: return make_kernels<64>();
+    case 96: return make_kernels<96>();
+    default: return make_kernels<0>();
+  }
+}
+
 static int check_common(int B, int N, int n) {
   if (n < 4 || n > 96 || (n & 3) != 0) {
     set_error("segnn_edge_layer_gemm: hidden multiplicity n=%d must be a multiple of 4 in [4, 96]", n);
@@ -1019,7 +1046,8 @@ int segnn_edge_layer_gemm_fwd(const float* pos, const float* mass, int B, int N,
   SEGNN_CHECK_LAUNCH();
   const int NT = (n + 31) & ~31;
   const size_t smem_node = sizeof(float) * ((size_t)eg::kTileO * 8 + (size_t)eg::kSY * 18 * NT);
-  cudaFuncSetAttribute(eg::gate2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
+  const eg::Kernels kn = eg::kernels_for(n);
+  cudaFuncSetAttribute(kn.g2f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
   for (int64_t g0 = 0; g0 < B; g0 += gpc) {
     const int64_t gc = (B - g0 < gpc) ? B - g0 : gpc;
     const int64_t rows = gc * N * N;
@@ -1029,13 +1057,13 @@ int segnn_edge_layer_gemm_fwd(const float* pos, const float* mass, int B, int N,
     float* dv = yy + eg::align64(rows * 3 * n);
     eg::RowArgs ra{pos, mass, p, q, w_edge1, N, n, g0 * N};
     const int64_t blocks1 = gc * ((N + eg::kRecv - 1) / eg::kRecv);
-    eg::msg1_rows_kernel<<<(unsigned)blocks1, dim3(NT, 4), 0, s>>>(ra, xs, xv);
+    kn.rows<<<(unsigned)blocks1, dim3(NT, 4), 0, s>>>(ra, xs, xv);
     SEGNN_CHECK_LAUNCH();
     rc = segnn_gemm_tf32x3(xs, 2 * n, wcat, 3 * n, rows, 2 * n, 3 * n, yy, 3 * n, ws_g, stream);
     if (rc != SEGNN_OK) return rc;
     rc = segnn_gemm_tf32x3(xv, n, w2_vv, n, 3 * rows, n, n, dv, n, ws_g, stream);
     if (rc != SEGNN_OK) return rc;
-    eg::gate2_fwd_kernel<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, yy, dv, b2, bn_mul, bn_add, agg_out,
+    kn.g2f<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, yy, dv, b2, bn_mul, bn_add, agg_out,
                                                                                  moments);
     SEGNN_CHECK_LAUNCH();
   }
@@ -1077,11 +1105,12 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
   SEGNN_CHECK_LAUNCH();
   const int NT = (n + 31) & ~31;
   const size_t smem_node = sizeof(float) * ((size_t)eg::kTileO * 8 + (size_t)eg::kSY * 18 * NT);
-  cudaFuncSetAttribute(eg::gate2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
+  const eg::Kernels kn = eg::kernels_for(n);
+  cudaFuncSetAttribute(kn.g2b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
   const int tiles_i = (N + eg::kTI - 1) / eg::kTI, tiles_j = (N + eg::kTJ - 1) / eg::kTJ;
   const int tile_warps = (n + 7) / 8;  // a warp of the tile kernel covers 8 channels x 4 sender lanes
-  const size_t smem_tile = sizeof(float) * ((size_t)eg::kTI * eg::kTJ * 8 + (size_t)eg::kTJ * 12 * tile_warps * 8);
-  cudaFuncSetAttribute(eg::msg1_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile);
+  const size_t smem_tile = sizeof(float) * ((size_t)eg::kTI * eg::kTJ * 8 + (size_t)eg::kTJ * (12 * tile_warps * 8 + 8));
+  cudaFuncSetAttribute(kn.tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile);
   // rows kept by the forward call (XS, XV, Y, DV of ALL graphs, i.e. the forward ran as one chunk): no recompute
   const float *kxs = nullptr, *kxv = nullptr, *kyy = nullptr, *kdv = nullptr;
   if (fwd_workspace != nullptr) {
@@ -1116,7 +1145,7 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
       cdv = kdv + r0 * 3 * n;
     } else {
       // recompute: message_layer_2 input rows and pre-activations
-      eg::msg1_rows_kernel<<<(unsigned)blocks1, dim3(NT, 4), 0, s>>>(ra, xs, xv);
+      kn.rows<<<(unsigned)blocks1, dim3(NT, 4), 0, s>>>(ra, xs, xv);
       SEGNN_CHECK_LAUNCH();
       rc = segnn_gemm_tf32x3(xs, 2 * n, wcat, 3 * n, rows, 2 * n, 3 * n, yy, 3 * n, ws_g, stream);
       if (rc != SEGNN_OK) return rc;
@@ -1124,7 +1153,7 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
       if (rc != SEGNN_OK) return rc;
     }
     // gate backward: (Y, DV) -> (dY, dDV), in place when recomputed
-    eg::gate2_bwd_kernel<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, cyy, cdv, yy, dv, b2, bn_a, bn_b,
+    kn.g2b<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, cyy, cdv, yy, dv, b2, bn_a, bn_b,
                                                                                  bn_c, dagg, db2_rows);
     SEGNN_CHECK_LAUNCH();
     rc = segnn_colsum(db2_rows, nullptr, gc * N, 2 * n, 0, ws_col, db2c + (int64_t)chunk_idx * 2 * n, stream);
@@ -1144,7 +1173,7 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
     float* dp_part = db2_rows + eg::align64(cn * 2 * n);
     float* dq_part = dp_part + eg::align64(tiles_j * cn * 12 * n);
     float* dwe_part = dq_part + eg::align64(tiles_i * cn * 12 * n);
-    eg::msg1_bwd_tile_kernel<<<(unsigned)(gc * tiles_i * tiles_j), tile_warps * 32, smem_tile, s>>>(
+    kn.tile<<<(unsigned)(gc * tiles_i * tiles_j), tile_warps * 32, smem_tile, s>>>(
         ra, dxs, dxv, tiles_i, tiles_j, cn, dp_part, dq_part, dwe_part);
     SEGNN_CHECK_LAUNCH();
     const int64_t node0 = g0 * N;

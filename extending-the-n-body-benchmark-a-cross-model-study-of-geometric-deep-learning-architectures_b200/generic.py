@@ -298,13 +298,15 @@ class GenericRunner:
                           "segnn_generic_message_input")
                 m = pl["g_msg1"].run(pl["msg1"].run(inp, ea))
             m = pl["g_msg2"].run(pl["msg2"].run(m, ea))
-            if layer.message_norm is not None:
-                mul, addc = _bn_eval_columns(layer.message_norm, layer.hidden_irreps)
-                m = ops.lincomb(m, None, mul, None, addc)
             agg = torch.empty((B * N, D), dtype=torch.float32, device=pos.device)
             with torch.cuda.device(pos.device):
                 check(lib.segnn_generic_aggregate(_p(m), B, N, D, _p(agg), ops._stream()), "segnn_generic_aggregate")
             ops._bump(2)
+            if layer.message_norm is not None:
+                # eval-mode BatchNorm is affine per column, so it commutes with the sum over the N - 1 senders:
+                # sum_j (mul m_ij + add) = mul sum_j m_ij + (N - 1) add -- applied on [nodes, D], not on [E, D]
+                mul, addc = _bn_eval_columns(layer.message_norm, layer.hidden_irreps)
+                agg = ops.lincomb(agg, None, mul, None, addc * float(N - 1))
             u = pl["g_upd1"].run(pl["upd1"].run(torch.cat([x, agg], dim=1).contiguous(), attr))
             u = pl["upd2"].run(u, attr)
             x = ops.add3(x, u)

@@ -212,15 +212,15 @@ __global__ void __launch_bounds__(96 * kSY)
     __syncthreads();
     if (!act) continue;
     const int lim = min(kTileO, N - o0);
-#pragma unroll 2
+#pragma unroll 4
     for (int t = y; t < lim; t += kSY) {
-      if (gs[t][3] == 0.f) continue;
+      const float valid = gs[t][3];  // the diagonal row is finite and masked (no branch: the loads of four rows overlap)
       const int64_t row = rl * N + o0 + t;
       const float* yr = yy + row * n3;
       const float* dr = dv + row * n3;
       const float ys = yr[w] + b2s, yg = yr[n + w] + b2g, t1 = yr[2 * n + w];
       const float dx = dr[w], dy = dr[n + w], dz = dr[2 * n + w];
-      const float ms = silu_gate_f(ys), gt = sig_gate_f(yg);
+      const float ms = valid * silu_gate_f(ys), gt = valid * sig_gate_f(yg);
       const float mx = gt * fmaf(gs[t][0], t1, dx), my = gt * fmaf(gs[t][1], t1, dy), mz = gt * fmaf(gs[t][2], t1, dz);
       acc[0] += ms;
       acc[1] += mx;
@@ -292,34 +292,53 @@ __global__ void __launch_bounds__(96 * kSY)
     __syncthreads();
     if (!act) continue;
     const int lim = min(kTileO, N - o0);
-#pragma unroll 2
-    for (int t = y; t < lim; t += kSY) {
-      const int64_t row = rl * N + o0 + t;
-      const float* yi = y_in + row * n3;   // may alias yy / dv: every element is read before it is written, by the
-      const float* di = dv_in + row * n3;  // same thread
-      float* yr = yy + row * n3;
-      float* dr = dv + row * n3;
-      const float ax = gs[t][0], ay = gs[t][1], az = gs[t][2], valid = gs[t][3];
-      const float ys = yi[w] + b2s, yg = yi[n + w] + b2g, t1 = yi[2 * n + w];
-      float ms, dsilu, gt, dsig;
-      silu_gate_vg(ys, ms, dsilu);
-      sig_gate_vg(yg, gt, dsig);
-      const float ux = fmaf(ax, t1, di[w]), uy = fmaf(ay, t1, di[n + w]), uz = fmaf(az, t1, di[2 * n + w]);
-      const float dms = valid * (As * G[0] + Bs * ms + Cs);
-      const float dmx = valid * (Av * G[1] + Bv * gt * ux);
-      const float dmy = valid * (Av * G[2] + Bv * gt * uy);
-      const float dmz = valid * (Av * G[3] + Bv * gt * uz);
-      const float dys = dms * dsilu;
-      const float dyg = dsig * (dmx * ux + dmy * uy + dmz * uz);
-      const float dux = gt * dmx, duy = gt * dmy, duz = gt * dmz;
-      yr[w] = dys;
-      yr[n + w] = dyg;
-      yr[2 * n + w] = ax * dux + ay * duy + az * duz;
-      dr[w] = dux;
-      dr[n + w] = duy;
-      dr[2 * n + w] = duz;
-      acc[0] += dys;
-      acc[1] += dyg;
+    // four rows per step, all loads before any store: the rows may be updated in place (y_in == yy), so the compiler
+    // cannot move a load above a store by itself and one row per step left a single row of loads in flight
+    constexpr int kU = 4;
+    for (int t0 = y; t0 < lim; t0 += kSY * kU) {
+      float yv[kU][3], dvv[kU][3];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int t = min(t0 + u * kSY, lim - 1);
+        const int64_t row = rl * N + o0 + t;
+        const float* yi = y_in + row * n3;
+        const float* di = dv_in + row * n3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          yv[u][c] = yi[c * n + w];
+          dvv[u][c] = di[c * n + w];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int t = t0 + u * kSY;
+        if (t < lim) {
+          const int64_t row = rl * N + o0 + t;
+          float* yr = yy + row * n3;
+          float* dr = dv + row * n3;
+          const float ax = gs[t][0], ay = gs[t][1], az = gs[t][2], valid = gs[t][3];
+          const float ys = yv[u][0] + b2s, yg = yv[u][1] + b2g, t1 = yv[u][2];
+          float ms, dsilu, gt, dsig;
+          silu_gate_vg(ys, ms, dsilu);
+          sig_gate_vg(yg, gt, dsig);
+          const float ux = fmaf(ax, t1, dvv[u][0]), uy = fmaf(ay, t1, dvv[u][1]), uz = fmaf(az, t1, dvv[u][2]);
+          const float dms = valid * (As * G[0] + Bs * ms + Cs);
+          const float dmx = valid * (Av * G[1] + Bv * gt * ux);
+          const float dmy = valid * (Av * G[2] + Bv * gt * uy);
+          const float dmz = valid * (Av * G[3] + Bv * gt * uz);
+          const float dys = dms * dsilu;
+          const float dyg = dsig * (dmx * ux + dmy * uy + dmz * uz);
+          const float dux = gt * dmx, duy = gt * dmy, duz = gt * dmz;
+          yr[w] = dys;
+          yr[n + w] = dyg;
+          yr[2 * n + w] = ax * dux + ay * duy + az * duz;
+          dr[w] = dux;
+          dr[n + w] = duy;
+          dr[2 * n + w] = duz;
+          acc[0] += dys;
+          acc[1] += dyg;
+        }
+      }
     }
   }
   __syncthreads();

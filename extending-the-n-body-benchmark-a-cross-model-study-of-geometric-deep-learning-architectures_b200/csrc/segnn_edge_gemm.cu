@@ -573,7 +573,9 @@ __global__ void scatter_w2_grads_kernel(int n, const float* __restrict__ dwcat, 
 namespace tn {
 
 constexpr int kStages = 2;
-constexpr int kLoadWarps = 8;
+// 7 loader warps + the MMA warp = 256 threads: registers are allocated for a warp count rounded up to a multiple of four,
+// so a ninth warp would cap every thread at 168 registers and spill the loaders' two prefetch sets
+constexpr int kLoadWarps = 7;
 constexpr int kMmaWarp = kLoadWarps;
 constexpr int kThreads = (kLoadWarps + 1) * 32;
 
@@ -660,19 +662,23 @@ struct Args {
   int64_t ldb;
   int64_t K;
   int M, N, NP;      // NP = N rounded up to 32
-  int kc;            // rows of K per stage: 32, or 64 when both operands are narrow (more bytes in flight)
+  int kc;            // rows of K per stage: 16, 32 or 64 (as many as the loaders' registers and shared memory hold)
+  int groups;        // G > 1: C = sum_g A[:, g M : (g + 1) M]^T B[:, g N : (g + 1) N] (rows that hold G blocks side by side)
+  int a_atoms;       // 32-float atoms of A per 4-k group in shared memory (4; G M / 32 + padding for G > 1)
   int tmem_cols;     // power of two >= NP (>= 32)
   float* part;       // [splits][mblocks * 128][NP]
 };
 
-constexpr int kMaxPieces = 13;  // 16-byte pieces per loader thread and stage
+constexpr int kMaxPieces = 15;  // 16-byte pieces per loader thread and stage
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int NP = a.NP, KC = a.kc;
-  const int a_bytes = KC * 512;                // one of (hi, lo): [KC / 4 k-groups][4 m-atoms][4][128 B]
-  const int b_bytes = KC * NP * 4;             //                 [KC / 4][NP / 32 n-atoms][4][128 B]
+  const int G = a.groups;
+  const int a_group = a.a_atoms * 512;         // one 4-k group of A
+  const int a_bytes = (KC / 4) * a_group;      // one of (hi, lo): [KC / 4 k-groups][a_atoms m-atoms][4][128 B]
+  const int b_bytes = KC * G * NP * 4;         //                 [KC / 4][G NP / 32 n-atoms][4][128 B]
   const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
   uint64_t* full = bars;              // [kStages] loaders -> MMA
@@ -683,7 +689,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, splits = gridDim.x, mb = blockIdx.y;
   const int m0 = mb * 128;
-  const int ma4 = ((min(a.M - m0, 128) + 31) & ~31) >> 2;  // 16-byte pieces per row of A that carry data
+  // 16-byte pieces per row of A that carry data (G > 1: the G blocks of M columns side by side, M a multiple of 32)
+  const int ma4 = G > 1 ? G * a.M / 4 : ((min(a.M - m0, 128) + 31) & ~31) >> 2;
   const int64_t chunks_total = (a.K + KC - 1) / KC;
   const int64_t c_begin = chunks_total * split / splits, c_end = chunks_total * (split + 1) / splits;
 
@@ -700,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args 
     mbar_init(dfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (ma4 < 32) {  // m-atoms past M are never written by the loaders: they must read as zeros
+  if (ma4 < 32 || G > 1) {  // m-atoms past M are never written by the loaders: they must read as zeros
     for (int i = tid; i < kStages * stage_bytes / 16; i += kThreads)
       reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     proxy_fence();
@@ -715,9 +722,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args 
     // The loads of chunk c + 1 are issued before chunk c is converted (two register sets): two stages of bytes in
     // flight per SM.
     const int pa = KC * ma4;            // 16-byte pieces of the A chunk
-    const int npr = NP / 4;             // pieces per row of B
+    const int npr = G * NP / 4;         // pieces per row of B
     const int total = pa + KC * npr;
-    const int b_atoms_bytes = (NP / 32) * 512;  // one 4-k group of B
+    const int b_atoms_bytes = (G * NP / 32) * 512;  // one 4-k group of B
     // piece -> (row k of the chunk, shared-memory offset, offset from the chunk's first row in HBM): the same for every
     // chunk, so the divisions are done once.  meta = smem offset | k << 20 | is_a << 30, -1 for no piece; goff < 0 for
     // the zero padding past M / N.
@@ -733,11 +740,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args 
         const int per = is_a ? ma4 : npr;
         const int k = q / per, c4 = q - k * per;
         const int rr = k & 3, cc = c4 & 7;
-        const int off = (is_a ? 0 : 2 * a_bytes) + (k >> 2) * (is_a ? 2048 : b_atoms_bytes) + (c4 >> 3) * 512 +
+        const int off = (is_a ? 0 : 2 * a_bytes) + (k >> 2) * (is_a ? a_group : b_atoms_bytes) + (c4 >> 3) * 512 +
                         rr * 128 + ((((cc >> 1) ^ rr) << 5) | ((cc & 1) << 4));
         meta[b] = off | (k << 20) | ((is_a ? 1 : 0) << 30);
         const int col = (is_a ? m0 : 0) + 4 * c4;
-        if (col < (is_a ? a.M : a.N)) goff[b] = (int)(k * (is_a ? a.lda : a.ldb)) + col;
+        if (col < (is_a ? G * a.M : G * a.N)) goff[b] = (int)(k * (is_a ? a.lda : a.ldb)) + col;
       }
     }
     auto issue = [&](int64_t c, float4 (&r)[kMaxPieces]) {
@@ -796,14 +803,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tn_tf32x3_kernel(const Args 
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + s * stage_bytes);
         const uint32_t sa_lo = sa + a_bytes, sb = sa + 2 * a_bytes, sb_lo = sb + b_bytes;
-        const uint32_t b_group = (uint32_t)(NP / 32) * 512u;  // one 4-k group of B; an MMA (K = 8) reads two
+        const uint32_t b_group = (uint32_t)(G * NP / 32) * 512u;  // one 4-k group of B; an MMA (K = 8) reads two
         for (int kg = 0; kg < KC / 8; ++kg) {
+          if (G > 1) {
+            // group g: rows [g M, g M + 128) of A (those past M belong to the next group or to the zero padding: they
+            // only feed accumulator rows nobody reads) against columns [g N, (g + 1) N) of B, all into one accumulator
+            const uint32_t idesc = make_idesc(NP);
+            for (int g = 0; g < G; ++g) {
+              const uint32_t ao = kg * 2 * a_group + g * (a.M / 32) * 512, bo = kg * 2 * b_group + g * (NP / 32) * 512;
+              const uint64_t ah = make_desc_mn(sa + ao, a_group), al = make_desc_mn(sa_lo + ao, a_group);
+              const uint64_t bh = make_desc_mn(sb + bo, b_group), bl = make_desc_mn(sb_lo + bo, b_group);
+              mma_tf32(tmem, ah, bl, idesc, (it > 0 || kg > 0 || g > 0) ? 1u : 0u);
+              mma_tf32(tmem, al, bh, idesc, 1u);
+              mma_tf32(tmem, ah, bh, idesc, 1u);
+            }
+            continue;
+          }
           for (int sub = 0; sub < nsub; ++sub) {
             const int width = min(256, NP - sub * 256);
             const uint32_t idesc = make_idesc(width);
             const uint32_t d = tmem + sub * 256;
-            const uint32_t ao = kg * 4096, bo = kg * 2 * b_group + sub * 8 * 512;
-            const uint64_t ah = make_desc_mn(sa + ao, 2048), al = make_desc_mn(sa_lo + ao, 2048);
+            const uint32_t ao = kg * 2 * a_group, bo = kg * 2 * b_group + sub * 8 * 512;
+            const uint64_t ah = make_desc_mn(sa + ao, a_group), al = make_desc_mn(sa_lo + ao, a_group);
             const uint64_t bh = make_desc_mn(sb + bo, b_group), bl = make_desc_mn(sb_lo + bo, b_group);
             mma_tf32(d, ah, bl, idesc, (it > 0 || kg > 0) ? 1u : 0u);
             mma_tf32(d, al, bh, idesc, 1u);
@@ -861,15 +882,23 @@ __global__ void tn_reduce_kernel(const float* __restrict__ part, int splits, int
   }
 }
 
-// 64 rows per stage when the pieces of a stage still fit the loaders' registers and two stages fit shared memory
-static inline int kc_for(int M, int NP) {
-  const int ma = ((M < 128 ? M : 128) + 31) & ~31;
-  const bool fits = 64 * (ma / 4 + NP / 4) <= kMaxPieces * kLoadWarps * 32 &&
-                    kStages * 2 * (64 * 512 + 64 * NP * 4) <= 200 * 1024;
-  return fits ? 64 : 32;
+// rows per stage: as many of 64 / 32 / 16 as the loaders' registers (kMaxPieces pieces per thread) and two stages of
+// shared memory hold; 0 = does not fit
+static inline int a_atoms_for(int M, int groups) { return groups > 1 ? groups * (M / 32) + 4 - M / 32 : 4; }
+static inline size_t smem_for(int kc, int M, int NP, int groups) {
+  return 1024 + (size_t)kStages * 2 * ((size_t)(kc / 4) * a_atoms_for(M, groups) * 512 + (size_t)kc * groups * NP * 4) + 64;
+}
+static inline int kc_for(int M, int NP, int groups) {
+  const int ma = groups > 1 ? groups * M : ((M < 128 ? M : 128) + 31) & ~31;
+  for (int kc = 64; kc >= 16; kc >>= 1) {
+    if (kc * (ma / 4 + groups * NP / 4) <= kMaxPieces * kLoadWarps * 32 &&
+        smem_for(kc, M, NP, groups) <= (kc == 64 ? 200 : 227) * 1024)
+      return kc;
+  }
+  return 0;
 }
 static inline int splits_for(int64_t K, int mblocks, int sms) {
-  const int64_t chunks = (K + 63) / 64;
+  const int64_t chunks = (K + 63) / 64;  // rows per stage <= 64: never more splits than chunks
   int64_t s = sms / mblocks;
   if (s < 1) s = 1;
   if (s > chunks) s = chunks;
@@ -900,26 +929,31 @@ int64_t segnn_gemm_tn_tf32x3_workspace(int64_t K, int M, int N) {
   return (int64_t)splits * mblocks * 128 * NP * (int64_t)sizeof(float);
 }
 
-int segnn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int M, int N, float* C,
-                         int64_t ldc, int accumulate, float* workspace, segnn_stream_t stream) {
-  SEGNN_CHECK_ARG(K >= 1 && M >= 1 && N >= 1 && N <= 512 && lda >= M && ldb >= N && ldc >= N, "bad sizes");
+int segnn_gemm_tn_grouped_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int M, int N,
+                                 int groups, float* C, int64_t ldc, int accumulate, float* workspace,
+                                 segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(K >= 1 && M >= 1 && N >= 1 && N <= 512 && groups >= 1 && lda >= (int64_t)groups * M &&
+                      ldb >= (int64_t)groups * N && ldc >= N,
+                  "bad sizes");
   SEGNN_CHECK_ARG(A && B && C && workspace, "null pointer");
   SEGNN_CHECK_ARG((M & 3) == 0 && (N & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0 &&
                       (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
                   "M, N, lda, ldb must be multiples of 4 floats and the pointers 16-byte aligned");
+  SEGNN_CHECK_ARG(groups == 1 || ((M & 31) == 0 && (N & 31) == 0 && M <= 128 && N <= 256),
+                  "groups > 1 needs M, N multiples of 32, M <= 128, N <= 256");
   const int mblocks = (M + 127) / 128;
   const int NP = (N + 31) & ~31;
   int tmem_cols = 32;
   while (tmem_cols < NP) tmem_cols <<= 1;
   const int splits = eg::tn::splits_for(K, mblocks, device_sms());
-  const int kc = eg::tn::kc_for(M, NP);
-  eg::tn::Args a{A, lda, B, ldb, K, M, N, NP, kc, tmem_cols, workspace};
-  const size_t smem = 1024 + (size_t)eg::tn::kStages * 2 * ((size_t)kc * 512 + (size_t)kc * NP * 4) + 64;
-  if (smem > 227 * 1024 || kc * (128 / 4 + NP / 4) > eg::tn::kMaxPieces * eg::tn::kLoadWarps * 32) {
-    set_error("segnn_gemm_tn_tf32x3: N=%d needs %zu bytes of shared memory", N, smem);
+  const int kc = eg::tn::kc_for(M, NP, groups);
+  if (kc == 0) {
+    set_error("segnn_gemm_tn_tf32x3: M=%d N=%d groups=%d does not fit shared memory / the loaders", M, N, groups);
     return SEGNN_E_UNSUPPORTED;
   }
+  eg::tn::Args a{A, lda, B, ldb, K, M, N, NP, kc, groups, eg::tn::a_atoms_for(M, groups), tmem_cols, workspace};
+  const size_t smem = eg::tn::smem_for(kc, M, NP, groups);
   cudaError_t err = cudaFuncSetAttribute(eg::tn::gemm_tn_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
   if (err != cudaSuccess) {
@@ -935,6 +969,11 @@ int segnn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ld
                                                                          accumulate);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
+}
+
+int segnn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int M, int N, float* C,
+                         int64_t ldc, int accumulate, float* workspace, segnn_stream_t stream) {
+  return segnn_gemm_tn_grouped_tf32x3(A, lda, B, ldb, K, M, N, 1, C, ldc, accumulate, workspace, stream);
 }
 
 }  // extern "C"
@@ -1180,7 +1219,11 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
     // weight gradients: K = rows
     rc = segnn_gemm_tn_tf32x3(cxs, 2 * n, yy, 3 * n, rows, 2 * n, 3 * n, dwcat, 3 * n, chunk_idx > 0, ws_tn, stream);
     if (rc != SEGNN_OK) return rc;
-    rc = segnn_gemm_tn_tf32x3(cxv, n, dv, n, 3 * rows, n, n, dwvv, n, chunk_idx > 0, ws_tn, stream);
+    // dW_vv = sum over the three components of XV_k^T dDV_k: the components sit side by side in a row
+    if ((n & 31) == 0)
+      rc = segnn_gemm_tn_grouped_tf32x3(cxv, 3 * n, dv, 3 * n, rows, n, n, 3, dwvv, n, chunk_idx > 0, ws_tn, stream);
+    else
+      rc = segnn_gemm_tn_tf32x3(cxv, n, dv, n, 3 * rows, n, n, dwvv, n, chunk_idx > 0, ws_tn, stream);
     if (rc != SEGNN_OK) return rc;
     // data gradients
     rc = segnn_gemm_tf32x3(yy, 3 * n, wcat_t, 2 * n, rows, 3 * n, 2 * n, dxs, 2 * n, ws_g, stream);

@@ -318,7 +318,7 @@ def gemm_tf32x3(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = 
 
 
 def gemm_tn_tf32x3(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
-                   accumulate: bool = False) -> torch.Tensor:
+                   accumulate: bool = False, groups: int = 1) -> torch.Tensor:
     """C (+)= A^T @ B in fp32 accuracy on the tensor cores (segnn_gemm_tn_tf32x3): ``a`` [K, M] and ``b`` [K, N]
     row-major (row-strided views allowed), the contraction runs over their rows with a fixed-order split-K reduction."""
     if not (a.is_cuda and b.is_cuda):
@@ -327,6 +327,9 @@ def gemm_tn_tf32x3(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor]
     assert a.stride(1) == 1 and b.stride(1) == 1, "row-major operands"
     K, M = a.shape
     N = b.shape[1]
+    if groups > 1:  # `groups` blocks side by side in every row: sum_g a[:, g]^T b[:, g]
+        assert M % groups == 0 and N % groups == 0
+        M, N = M // groups, N // groups
     if out is None:
         assert not accumulate
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
@@ -336,10 +339,10 @@ def gemm_tn_tf32x3(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor]
         raise RuntimeError(f"gemm_tn_tf32x3: unsupported sizes K={K} M={M} N={N}")
     ws = torch.empty(max(4, nbytes // 4), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        check(lib.segnn_gemm_tn_tf32x3(_p(a), a.stride(0) if K > 1 else max(M, a.stride(0)), _p(b),
-                                       b.stride(0) if K > 1 else max(N, b.stride(0)), K, M, N, _p(out),
-                                       out.stride(0) if M > 1 else N, int(accumulate), _p(ws), _stream()),
-              "segnn_gemm_tn_tf32x3")
+        check(lib.segnn_gemm_tn_grouped_tf32x3(_p(a), a.stride(0) if K > 1 else max(groups * M, a.stride(0)), _p(b),
+                                               b.stride(0) if K > 1 else max(groups * N, b.stride(0)), K, M, N, groups,
+                                               _p(out), out.stride(0) if M > 1 else N, int(accumulate), _p(ws),
+                                               _stream()), "segnn_gemm_tn_grouped_tf32x3")
     _bump(2)
     return out
 

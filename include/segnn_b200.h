@@ -313,6 +313,13 @@ int segnn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, 
 int64_t segnn_gemm_tn_tf32x3_workspace(int64_t K, int M, int N);
 int segnn_gemm_tn_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int M, int N, float* C,
                          int64_t ldc, int accumulate, float* workspace, segnn_stream_t stream);
+/* The same with `groups` blocks side by side in every row: C[M][N] (+)= sum_g A[:, g M : (g + 1) M]^T B[:, g N : (g + 1) N]
+ * (lda >= groups * M, ldb >= groups * N; groups > 1: M, N multiples of 32, M <= 128, N <= 256).  The W_vv weight
+ * gradient sums over the three vector components, which sit side by side in a row of the edge tensors: one pass over
+ * rows of 3n floats instead of three times as many rows of n.  Same workspace as segnn_gemm_tn_tf32x3. */
+int segnn_gemm_tn_grouped_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t K, int M, int N,
+                                 int groups, float* C, int64_t ldc, int accumulate, float* workspace,
+                                 segnn_stream_t stream);
 
 /* Large-graph form of segnn_edge_layer_fwd (SEGNN_MODE_FP32 semantics, same arguments and outputs) and of
  * segnn_edge_layer_bwd (passes 0 and 1 in one call): SEGNNLayer.message + the scatter-add (models/segnn/segnn.py:205,

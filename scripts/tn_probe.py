@@ -5,12 +5,12 @@ import torch
 import segnn_b200 as S
 
 rows = 1_000_000
-cases = [("tn", rows, 128, 192), ("tn", 3 * rows, 64, 64), ("nn", rows, 128, 192), ("nn", 3 * rows, 64, 64),
+cases = [("tn", rows, 128, 192), ("tn", 3 * rows, 64, 64), ("tng", rows, 192, 192), ("nn", rows, 128, 192), ("nn", 3 * rows, 64, 64),
          ("nn", rows, 192, 128)]
 for kind, r, a, b in cases:
-    if kind == "tn":
+    if kind in ("tn", "tng"):
         x, y = torch.randn(r, a, device="cuda"), torch.randn(r, b, device="cuda")
-        fn = lambda: S.ops.gemm_tn_tf32x3(x, y)
+        fn = (lambda: S.ops.gemm_tn_tf32x3(x, y, groups=3)) if kind == "tng" else (lambda: S.ops.gemm_tn_tf32x3(x, y))
         nbytes = 4 * r * (a + b)
     else:
         x, w = torch.randn(r, a, device="cuda"), torch.randn(a, b, device="cuda")

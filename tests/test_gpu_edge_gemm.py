@@ -37,6 +37,25 @@ def test_gemm_tn_matches_float64(K, M, N):
     assert rel(acc, ref + 1.0) < 4e-6
 
 
+@pytest.mark.parametrize("K,M,N,G", [(1000, 64, 64, 3), (5000, 96, 96, 3), (77, 32, 32, 3), (3000, 128, 64, 2),
+                                     (20000, 64, 64, 3)])
+def test_gemm_tn_grouped_matches_float64(K, M, N, G):
+    """sum_g A_g^T B_g with the G blocks side by side in every row (the W_vv weight gradient over the three vector
+    components)."""
+    g = torch.Generator().manual_seed(K + M + N + G)
+    a = torch.randn(K, G * M, generator=g).cuda()
+    b = torch.randn(K, G * N, generator=g).cuda()
+    ref = sum(a[:, i * M:(i + 1) * M].double().t() @ b[:, i * N:(i + 1) * N].double() for i in range(G))
+    out = S.ops.gemm_tn_tf32x3(a, b, groups=G)
+    err = rel(out, ref)
+    print(f"K={K} M={M} N={N} G={G}: max rel err {err:.2e}")
+    assert out.shape == (M, N) and err < 4e-6
+    assert torch.equal(S.ops.gemm_tn_tf32x3(a, b, groups=G), out)
+    # the same numbers as the stacked form [G K][M] x [G K][N]
+    stacked = S.ops.gemm_tn_tf32x3(a.reshape(K * G, M), b.reshape(K * G, N))
+    assert rel(out, stacked) < 2e-6
+
+
 def _edge_inputs(B, N, n, seed=0, bn=False):
     g = torch.Generator().manual_seed(seed)
     nodes = B * N

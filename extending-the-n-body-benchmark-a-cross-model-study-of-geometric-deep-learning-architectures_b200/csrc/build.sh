@@ -9,7 +9,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC ${SEGNN_NVCC_EXTRA:-})
 SOURCES=(segnn_node.cu segnn_edge_fp32.cu segnn_edge_tc.cu segnn_edge_tc_h2.cu segnn_node_gemm_tc.cu segnn_edge_api.cu
          segnn_train.cu segnn_edge_bwd.cu segnn_macros.cu segnn_generic.cu segnn_sim.cu segnn_extras.cu segnn_pack.cu
-         segnn_gemm_tf32x3.cu segnn_edge_gemm.cu)
+         segnn_gemm_tf32x3.cu segnn_edge_gemm.cu segnn_l2_rows.cu)
 mkdir -p "${obj}"
 flag_stamp="${obj}/.flags"
 if [[ ! -f "${flag_stamp}" ]] || [[ "$(cat "${flag_stamp}")" != "${FLAGS[*]}" ]]; then

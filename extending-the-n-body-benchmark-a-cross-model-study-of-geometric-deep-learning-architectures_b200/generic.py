@@ -258,6 +258,132 @@ def _bn_eval_columns(bn, irreps: Irreps):
     return torch.cat(mul).contiguous(), torch.cat(add).contiguous()
 
 
+USE_L2_ROWS = True  # False: every layer through the table-driven generic kernels (the checker of the l2 form)
+_L2_TYPES = [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0), (1, 1, 2), (2, 0, 2), (2, 1, 1)]
+
+
+class Lmax2EdgePlan:
+    """Edge part of one SEGNNLayer for hidden irreps n x 0e + n x 1o + n x 2e (lmax_h = 2, BASELINE configuration 3) in
+    GEMM form (csrc/segnn_l2_rows.cu): node-level products of message_layer_1 (the hoisted plan's Y), ONE kernel for
+    message_layer_1's per-edge coupling + gate + message_layer_2's coupling -> three GEMM operands, the package's
+    fp32-accurate tcgen05 GEMM against the stacked path weights, ONE kernel for bias + gate + sum over senders + eval
+    BatchNorm.  Same arithmetic as the generic kernels (which remain the checker: tests/test_gpu_parity.py), without
+    the [E, .] tensors between hoisted message_layer_1, gate, expansion, scatter, gate, BatchNorm and aggregation."""
+
+    CHUNK_BYTES = 4 << 30
+
+    @staticmethod
+    def supported(layer, hidden_irreps: Irreps) -> bool:
+        try:
+            h = [(m, l, p) for m, l, p in hidden_irreps]
+            if len(h) != 3 or [l for _, l, _ in h] != [0, 1, 2] or len({m for m, _, _ in h}) != 1 or h[0][0] > 96:
+                return False
+            if [p for _, _, p in h] != [1, -1, 1]:
+                return False
+            t1, t2 = layer.message_layer_1.tp, layer.message_layer_2.tp
+            attr = [(m, l) for m, l, _ in t1.irreps_in2]
+            if attr != [(1, 0), (1, 1)] or [(m, l) for m, l, _ in t2.irreps_in2] != attr:
+                return False
+            n = h[0][0]
+            outs = [(m, l) for m, l, _ in t1.irreps_out]
+            if outs != [(3 * n, 0), (n, 1), (n, 2)] or [(m, l) for m, l, _ in t2.irreps_out] != outs:
+                return False
+            in1 = [(m, l) for m, l, _ in t1.irreps_in1]
+            return in1 == [(n, 0), (n, 1), (n, 2)] * 2 + [(2, 0)] and \
+                [(m, l) for m, l, _ in t2.irreps_in1] == [(n, 0), (n, 1), (n, 2)]
+        except Exception:
+            return False
+
+    def __init__(self, layer, hidden_irreps: Irreps, hoisted: "HoistedMessage1Plan", msg2: TensorProductPlan, device):
+        self.layer, self.hoisted, self.msg2 = layer, hoisted, msg2
+        self.n = n = hidden_irreps[0][0]
+        tindex = {t: i for i, t in enumerate(_L2_TYPES)}
+        cg = np.zeros((7, 5, 3, 5), dtype=np.float64)
+        for (l1, l2, lo), i in tindex.items():
+            cg[i, :2 * l1 + 1, :2 * l2 + 1, :2 * lo + 1] = math.sqrt(2 * lo + 1) * real_wigner_3j(l1, l2, lo)
+        self.cg = torch.tensor(cg, dtype=torch.float32, device=device).contiguous()
+        ltype = lambda d1, d2, do: tindex[((d1 - 1) // 2, (d2 - 1) // 2, (do - 1) // 2)]
+        yoff = [[-1, -1] for _ in range(7)]
+        for oo, mo, do, d1, o2, d2, yi, yj in hoisted.pairs.cpu().tolist():
+            yoff[ltype(d1, d2, do)] = [yi, yj]
+        assert all(a >= 0 and b >= 0 for a, b in yoff)
+        self.yoff = torch.tensor(yoff, dtype=torch.int32).contiguous()  # host: read by the C call, not by a kernel
+        self.add_off = {}
+        for oo, mo, do, o2, d2, woff, mul1 in hoisted.adds.cpu().tolist():
+            assert mul1 == 2
+            self.add_off[ltype(1, d2, do)] = (woff, mo)
+        assert set(self.add_off) == {0, 1} and self.add_off[0][1] == 3 * n and self.add_off[1][1] == n
+        koff = [-1] * 7
+        self.blocks = {}
+        for b in msg2.blocks:
+            self.blocks[b["dimo"]] = b
+            for o1, m1, d1, o2, d2, ko in b["paths"].cpu().tolist():
+                assert m1 == n
+                koff[ltype(d1, d2, b["dimo"])] = ko
+        assert all(k >= 0 for k in koff) and set(self.blocks) == {1, 3, 5}
+        assert self.blocks[1]["mulo"] == 3 * n and self.blocks[3]["mulo"] == n and self.blocks[5]["mulo"] == n
+        self.koff = torch.tensor(koff, dtype=torch.int32).contiguous()
+        self._cache_key, self._cache = None, None
+
+    def _weights(self, device):
+        m1, m2 = self.layer.message_layer_1, self.layer.message_layer_2
+        norm = self.layer.message_norm
+        key = (m1.tp.weight._version, m2.tp.weight._version, m1.biases._version, m2.biases._version,
+               None if norm is None else (norm.weight._version, norm.bias._version, norm.running_mean._version,
+                                          norm.running_var._version))
+        if key == self._cache_key:
+            return self._cache
+        n = self.n
+        w1 = m1.tp.weight.detach().to(torch.float32).contiguous()
+        w2 = m2.tp.weight.detach().to(torch.float32).contiguous()
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        c = dict(tp_weight_1=w1, w_add0=w1[self.add_off[0][0]: self.add_off[0][0] + 2 * 3 * n],
+                 w_add1=w1[self.add_off[1][0]: self.add_off[1][0] + 2 * n],
+                 bias1=f32(m1.biases)[: 3 * n], bias2=f32(m2.biases)[: 3 * n])
+        assert m1.biases.numel() == 3 * n and m2.biases.numel() == 3 * n
+        for d, b in self.blocks.items():
+            c[f"stacked{d}"] = torch.cat([w2[off: off + k * b["mulo"]].view(k, b["mulo"]) for off, k in b["wviews"]],
+                                   dim=0).contiguous()
+        c["bn"] = _bn_eval_columns(norm, self.layer.hidden_irreps) if norm is not None else (None, None)
+        self._cache_key, self._cache = key, c
+        return c
+
+    def run(self, x, pos, mass, B: int, N: int):
+        dev, n = x.device, self.n
+        c = self._weights(dev)
+        hp = self.hoisted
+        nodes = B * N
+        ones = torch.ones((nodes, 1), dtype=torch.float32, device=dev)
+        Y = torch.empty((nodes, hp.ydim), dtype=torch.float32, device=dev)
+        agg = torch.empty((nodes, 9 * n), dtype=torch.float32, device=dev)
+        K = {d: self.blocks[d]["K"] for d in (1, 3, 5)}
+        lda = {d: (K[d] + 3) & ~3 for d in (1, 3, 5)}
+        ldy = {1: (3 * n + 3) & ~3, 3: (n + 3) & ~3, 5: (n + 3) & ~3}
+        per_graph = 4 * N * N * sum(d * (lda[d] + ldy[d]) for d in (1, 3, 5))
+        gpc = max(1, min(B, self.CHUNK_BYTES // per_graph))
+        with torch.cuda.device(dev):
+            check(lib.segnn_generic_tp(_p(x), hp.D, _p(ones), 1, nodes, _p(c["tp_weight_1"]), _p(hp.yinstr), hp.n_y, _p(hp.ycg),
+                                       None, hp.ydim, _p(Y), ops._stream()), "segnn_generic_tp")
+            ops._bump()
+            for g0 in range(0, B, gpc):
+                gc = min(gpc, B - g0)
+                rows = gc * N * N
+                A = {d: torch.empty((rows * d, lda[d]), dtype=torch.float32, device=dev) for d in (1, 3, 5)}
+                Yb = {d: torch.empty((rows * d, ldy[d]), dtype=torch.float32, device=dev) for d in (1, 3, 5)}
+                check(lib.segnn_l2_msg_rows(_p(pos), _p(mass), gc, N, n, g0 * N, _p(Y), hp.ydim,
+                                            self.yoff.data_ptr(), _p(self.cg), _p(c["w_add0"]), _p(c["w_add1"]),
+                                            _p(c["bias1"]), self.koff.data_ptr(), lda[1], lda[3], lda[5], _p(A[1]),
+                                            _p(A[3]), _p(A[5]), ops._stream()), "segnn_l2_msg_rows")
+                for d in (1, 3, 5):
+                    ops.gemm_tf32x3(A[d][:, :K[d]], c[f"stacked{d}"], out=Yb[d][:, :self.blocks[d]["mulo"]])
+                mul, addc = c["bn"]
+                check(lib.segnn_l2_gate_aggregate(gc, N, n, g0 * N, _p(Yb[1]), ldy[1], _p(Yb[3]), ldy[3], _p(Yb[5]),
+                                                  ldy[5], _p(c["bias2"]), _p(mul), _p(addc), _p(agg), ops._stream()),
+                      "segnn_l2_gate_aggregate")
+                ops._bump(2)
+        return agg
+
+
 class GenericRunner:
     """Plans for every tensor product / gate of one SEGNN; ``forward`` mirrors SEGNN.forward (eval mode)."""
 
@@ -274,6 +400,12 @@ class GenericRunner:
                 upd1=tp(layer.update_layer_1), g_upd1=GatePlan(layer.update_layer_1, device),
                 upd2=tp(layer.update_layer_2)))
         self.hoist_message_layer_1 = True
+        # lmax_h = 2 hidden irreps (n x 0e + n x 1o + n x 2e): the edge part of every layer in GEMM form
+        self.use_l2_rows = USE_L2_ROWS and all(Lmax2EdgePlan.supported(layer, model.hidden_irreps)
+                                               for layer in model.layers)
+        if self.use_l2_rows:
+            for layer, pl in zip(model.layers, self.layers):
+                pl["l2"] = Lmax2EdgePlan(layer, model.hidden_irreps, pl["msg1h"], pl["msg2"], device)
         self.pool1, self.g_pool1 = tp(model.pre_pool1), GatePlan(model.pre_pool1, device)
         self.pool2 = tp(model.pre_pool2)
 
@@ -284,11 +416,22 @@ class GenericRunner:
             raise NotImplementedError("the generic-irreps path implements eval-mode BatchNorm only")
         D = model.hidden_irreps.dim
         x_in, attr = ops.prep(pos, vel, B, N)
-        ea, add = ops.edge_attr(pos, mass, B, N)
-        E = ea.shape[0]
+        if not self.use_l2_rows:
+            ea, add = ops.edge_attr(pos, mass, B, N)
+            E = ea.shape[0]
         x = self.embed.run(x_in, attr)
         per_layer = [x]
         for layer, pl in zip(model.layers, self.layers):
+            if self.use_l2_rows:
+                agg = pl["l2"].run(x, pos, mass, B, N)
+                u = pl["g_upd1"].run(pl["upd1"].run(torch.cat([x, agg], dim=1).contiguous(), attr))
+                u = pl["upd2"].run(u, attr)
+                x = ops.add3(x, u)
+                if layer.feature_norm is not None:
+                    mul, addc = _bn_eval_columns(layer.feature_norm, layer.hidden_irreps)
+                    x = ops.lincomb(x, None, mul, None, addc)
+                per_layer.append(x)
+                continue
             if self.hoist_message_layer_1:
                 m = pl["g_msg1"].run(pl["msg1h"].run(x, ea, add, B, N))
             else:  # the reference's own formulation: gathered message input, tensor product on [E, 2D + 2]

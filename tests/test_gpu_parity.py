@@ -461,12 +461,17 @@ def test_rollout_macros_within_reference_statistical_tolerance(mode, N):
 
 
 # ---- generic-irreps path (lmax_h = 2, BASELINE config 3) -------------------------------------------------------------
+@pytest.mark.parametrize("l2_rows", [True, False])
 @pytest.mark.parametrize("H,lmax_h,L,B,N", [(32, 2, 2, 2, 6), (192, 2, 1, 1, 10), (64, 2, 3, 3, 5), (64, 1, 2, 3, 5),
-                                             (32, 2, 2, 8, 17), (192, 2, 1, 1, 50)])  # the last two: expand + GEMM form
-def test_generic_irreps_path_matches_oracle(H, lmax_h, L, B, N):
+                                             (32, 2, 2, 8, 17), (192, 2, 1, 1, 50), (192, 2, 2, 3, 33)])
+def test_generic_irreps_path_matches_oracle(H, lmax_h, L, B, N, l2_rows, monkeypatch):
     """Per-layer parity of the generic fp32 kernels (any hidden irreps; lmax_h = 2 is BASELINE config 3) at the fp32
     tolerance 1e-5; for lmax_h = 1 the same path is selected with compute_mode='generic' and must also agree with the
     fused kernels."""
+    # l2_rows: the edge part of an lmax_h = 2 layer in GEMM form (csrc/segnn_l2_rows.cu, the default) or through the
+    # table-driven generic kernels
+    import segnn_b200.generic as G
+    monkeypatch.setattr(G, "USE_L2_ROWS", l2_rows)
     torch.manual_seed(H + lmax_h)
     om = O.SEGNN(hidden_features=H, num_layers=L, lmax_h=lmax_h).eval()
     O.perturb_bn_buffers(om, seed=5)
@@ -478,7 +483,8 @@ def test_generic_irreps_path_matches_oracle(H, lmax_h, L, B, N):
         ref, ref_layers = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N),
                              return_layers=True)
         out, layers = m(gpu_graph(pos, vel, mass, B, N), return_layers=True)
-        print(f"generic H={H} lmax_h={lmax_h}: per-layer", [f"{rel(a, b):.2e}" for a, b in zip(layers, ref_layers)],
+        assert m._generic.use_l2_rows == (l2_rows and lmax_h == 2)
+        print(f"generic H={H} lmax_h={lmax_h} l2_rows={l2_rows}: per-layer", [f"{rel(a, b):.2e}" for a, b in zip(layers, ref_layers)],
               f"out {rel(out, ref):.2e}")
         for a, b in zip(layers, ref_layers):
             assert rel(a, b) < 1e-5

@@ -339,7 +339,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-training", action="store_true", help="skip the secondary training measurements")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other precision modes / BASELINE configs")
-    ap.add_argument("--cfg3-sims", type=int, default=16, help="simulations of the lmax_h = 2 (cfg3) measurement")
+    ap.add_argument("--cfg3-sims", type=int, default=64, help="simulations of the lmax_h = 2 (cfg3) measurement")
     ap.add_argument("--cfg4-cpu-seconds", type=int, default=45, help="time limit of the cfg4 CPU attempt")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -519,12 +519,19 @@ def main():
         perturb_batchnorm(m3)
         m3 = m3.to(dev).eval()
         b3 = args.cfg3_sims
-        c3_ms, c3_launches = timed_rollout(m3, 2, 1, use_graph=False, batch=b3, nbody=N,
+        c3_ms, c3_launches = timed_rollout(m3, 3, 1, use_graph=False, batch=b3, nbody=N,
                                            state=synthetic_system(b3, N, seed=4))
+        # the three message_layer_2 GEMMs of a layer: 2 * (146 * 219 + 3 * 219 * 73 + 5 * 146 * 73) flop per edge
+        c3_flop = b3 * N * (N - 1) * LAYERS * 2 * (146 * 219 + 3 * 219 * 73 + 5 * 146 * 73)
         configs["cfg3_lmax_h2_n100"] = {
-            "config": f"SEGNN 6 layers hidden 192 lmax_h 2 (73x0e+73x1o+73x2e), {b3} x N=100, self-feed step "
-                      "(generic-irreps fp32 kernels; per particle-step, the 1000-step rollout is this step repeated)",
-            "ms_per_step": c3_ms, "particle_steps_per_s": b3 * N / (c3_ms * 1e-3), "launches_per_step": c3_launches}
+            "config": f"SEGNN 6 layers hidden 192 lmax_h 2 (73x0e+73x1o+73x2e), {b3} x N=100, self-feed step, fp32 "
+                      "accurate (1e-5 parity): edge layers in GEMM form (csrc/segnn_l2_rows.cu: message_layer_1 coupling "
+                      "+ gate + message_layer_2 coupling in one kernel, three 3xTF32 tcgen05 GEMMs, gate + sender sum "
+                      "+ BatchNorm in one kernel), node-level products through the generic kernels; per particle-step, "
+                      "the 1000-step rollout is this step repeated",
+            "ms_per_step": c3_ms, "particle_steps_per_s": b3 * N / (c3_ms * 1e-3), "launches_per_step": c3_launches,
+            "message_layer_2_tflops": c3_flop / (c3_ms * 1e-3) / 1e12,
+            "round1_ms_per_step_16_sims": 35.7}
         del m1, m3
         torch.cuda.empty_cache()
     training = None

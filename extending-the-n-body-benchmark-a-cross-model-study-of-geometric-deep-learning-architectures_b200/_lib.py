@@ -59,8 +59,10 @@ PROTOTYPES = {
                                     _ptr, _ptr]),
     "segnn_gemm_tn_grouped_tf32x3": (_int, [_ptr, _c.c_int64, _ptr, _c.c_int64, _c.c_int64, _int, _int, _int, _ptr,
                                             _c.c_int64, _int, _ptr, _ptr]),
-    "segnn_l2_msg_rows": (_int, [_ptr, _ptr, _int, _int, _int, _c.c_int64, _ptr, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
-                                 _c.c_int64, _c.c_int64, _c.c_int64, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_l2_planarize": (_int, [_ptr, _c.c_int64, _int, _c.c_int64, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_l2_msg_rows": (_int, [_ptr, _ptr, _int, _int, _int, _c.c_int64, _ptr, _c.c_int64, _ptr, _c.c_int64, _ptr,
+                                 _c.c_int64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c.c_int64, _c.c_int64, _c.c_int64, _ptr,
+                                 _ptr, _ptr, _ptr]),
     "segnn_l2_gate_aggregate": (_int, [_int, _int, _int, _c.c_int64, _ptr, _c.c_int64, _ptr, _c.c_int64, _ptr, _c.c_int64,
                                        _ptr, _ptr, _ptr, _ptr, _ptr]),
     "segnn_edge_layer_gemm_workspace": (_c.c_int64, [_int, _int, _int, _int, _c.c_int64]),

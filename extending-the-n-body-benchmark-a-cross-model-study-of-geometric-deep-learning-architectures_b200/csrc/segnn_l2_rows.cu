@@ -22,12 +22,14 @@ namespace l2 {
 // dimensions (2 l1 + 1, 2 l2 + 1, 2 lo + 1) = (1,1,1) (1,3,3) (3,1,3) (3,3,1) (3,3,5) (5,1,5) (5,3,3)
 constexpr int kTypes = 7;
 constexpr int kWarps = 4;
-constexpr int kMaxCpt = 3;  // channels per lane (n <= 96)
+constexpr int kMaxCpt = 2;  // channels a lane processes together (32 lanes x 2 per pass, passes until n is covered)
 
 struct RowsArgs {
-  const float *pos, *mass, *Y;
-  int B, N, n, ydim;
-  int yoff[kTypes][2];   // offset in a Y row of (type, role): role 0 = receiver x_i, 1 = sender x_j
+  const float *pos, *mass;
+  const float* Y[3];     // node-level products by input degree l1: Y[l1][(node * (2 l1 + 1) + i)][ldy[l1]]
+  long long ldy[3];
+  int B, N, n;
+  int yoff[kTypes][2];   // column of (type, role) in a row of Y[l1(type)]: role 0 = receiver x_i, 1 = sender x_j
   const float* cg;       // [7][5][3][5] net couplings
   const float* w_add0;   // [2][3n] weights of the additional scalars -> 0e outputs
   const float* w_add1;   // [2][n]                                   -> 1o outputs
@@ -39,18 +41,159 @@ struct RowsArgs {
   int graphs;            // graphs in the chunk
 };
 
-template <int D1, int DO>
-__device__ __forceinline__ void couple(const float* __restrict__ M, const float (&S)[D1], float (&z)[DO]) {
+// z[c][k] += sum_i M[i][k] S[c][i] for the kMaxCpt channels of a lane at once: every coupling coefficient is read from
+// shared memory once per edge and lane, not once per channel
+template <int CW, int D1, int DO>
+__device__ __forceinline__ void couple(const float* __restrict__ M, const float (&S)[CW][D1], float (&z)[CW][DO]) {
 #pragma unroll
   for (int i = 0; i < D1; ++i)
 #pragma unroll
-    for (int k = 0; k < DO; ++k) z[k] = fmaf(M[i * 5 + k], S[i], z[k]);
-}
-template <int D1>
-__device__ __forceinline__ void load_sum(const float* __restrict__ yi, const float* __restrict__ yj, int w,
-                                         float (&S)[D1]) {
+    for (int k = 0; k < DO; ++k) {
+      const float m = M[i * 5 + k];
 #pragma unroll
-  for (int i = 0; i < D1; ++i) S[i] = yi[w * D1 + i] + yj[w * D1 + i];
+      for (int c = 0; c < CW; ++c) z[c][k] = fmaf(m, S[c][i], z[c][k]);
+    }
+}
+// S[c][i] = P_i + Q_j of one instruction type for output channel w0 + 32 c: component i of node r sits in row
+// r * D1 + i of the degree's Y, consecutive channels are consecutive floats (coalesced over the lanes)
+template <int CW, int D1>
+__device__ __forceinline__ void load_sum(const float* __restrict__ yi, const float* __restrict__ yj, long long ld,
+                                         const int (&w)[CW], float (&S)[CW][D1]) {
+#pragma unroll
+  for (int c = 0; c < CW; ++c)
+#pragma unroll
+    for (int i = 0; i < D1; ++i) S[c][i] = yi[i * ld + w[c]] + yj[i * ld + w[c]];
+}
+
+struct EdgeCtx {
+  const float *yi0, *yi1, *yi2, *yj0, *yj1, *yj2, *M;
+  float len, mm;
+  long long row;
+};
+
+// CW channels of a lane at once (u = lane + 32 (c0 + c)): message_layer_1 coupling, gate, message_layer_2 coupling
+template <int CW>
+__device__ __forceinline__ void edge_channels(const RowsArgs& a, const EdgeCtx& e, int c0, int lane) {
+  const int n = a.n;
+  const float *yi0 = e.yi0, *yi1 = e.yi1, *yi2 = e.yi2, *yj0 = e.yj0, *yj1 = e.yj1, *yj2 = e.yj2, *M = e.M;
+  const float len = e.len, mm = e.mm;
+  const long long row = e.row;
+    // the lane's channels of this pass, u = lane + 32 (c0 + c); channels past n compute on channel n - 1 and are not stored
+    int uc[CW];
+    bool on[CW];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+      on[c] = lane + 32 * (c0 + c) < n;
+      uc[c] = on[c] ? lane + 32 * (c0 + c) : n - 1;
+    }
+    // ---- message_layer_1: 0e outputs (scalar u, gate of 1o_u, gate of 2e_u) -------------------------------------
+    float z0[3][CW][1];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      int w[CW];
+      float S0[CW][1], S3[CW][3];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        w[c] = q * n + uc[c];
+        // bias + additional scalars (type (0,0,0))
+        z0[q][c][0] = a.bias1[w[c]] + M[0] * (a.w_add0[w[c]] * len + a.w_add0[3 * n + w[c]] * mm);
+      }
+      load_sum<CW, 1>(yi0 + a.yoff[0][0], yj0 + a.yoff[0][1], a.ldy[0], w, S0);
+      couple<CW, 1, 1>(M + 0 * 25, S0, z0[q]);
+      load_sum<CW, 3>(yi1 + a.yoff[3][0], yj1 + a.yoff[3][1], a.ldy[1], w, S3);
+      couple<CW, 3, 1>(M + 3 * 25, S3, z0[q]);
+    }
+    // ---- 1o and 2e outputs ---------------------------------------------------------------------------------------
+    float z1[CW][3], z2[CW][5];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) z1[c][k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) z2[c][k] = 0.f;
+    }
+    {
+      float S1[CW][1], S3[CW][3], S5[CW][5];
+      load_sum<CW, 1>(yi0 + a.yoff[1][0], yj0 + a.yoff[1][1], a.ldy[0], uc, S1);
+#pragma unroll
+      for (int c = 0; c < CW; ++c)
+        S1[c][0] += a.w_add1[uc[c]] * len + a.w_add1[n + uc[c]] * mm;  // additional scalars: type (0,1,1)
+      couple<CW, 1, 3>(M + 1 * 25, S1, z1);
+      load_sum<CW, 3>(yi1 + a.yoff[2][0], yj1 + a.yoff[2][1], a.ldy[1], uc, S3);
+      couple<CW, 3, 3>(M + 2 * 25, S3, z1);
+      load_sum<CW, 5>(yi2 + a.yoff[6][0], yj2 + a.yoff[6][1], a.ldy[2], uc, S5);
+      couple<CW, 5, 3>(M + 6 * 25, S5, z1);
+      load_sum<CW, 3>(yi1 + a.yoff[4][0], yj1 + a.yoff[4][1], a.ldy[1], uc, S3);
+      couple<CW, 3, 5>(M + 4 * 25, S3, z2);
+      load_sum<CW, 5>(yi2 + a.yoff[5][0], yj2 + a.yoff[5][1], a.ldy[2], uc, S5);
+      couple<CW, 5, 5>(M + 5 * 25, S5, z2);
+    }
+    // ---- e3nn Gate -------------------------------------------------------------------------------------------------
+    float s[CW][1], v[CW][3], qq[CW][5];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+      s[c][0] = silu_gate(z0[0][c][0]);
+      const float g1 = sig_gate(z0[1][c][0]), g2 = sig_gate(z0[2][c][0]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v[c][k] = g1 * z1[c][k];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) qq[c][k] = g2 * z2[c][k];
+    }
+    // ---- message_layer_2: coupling of the gated message with the edge attribute -> GEMM operand rows ---------------
+    {
+      float o0[CW][1], o1[CW][1];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) o0[c][0] = o1[c][0] = 0.f;
+      couple<CW, 1, 1>(M + 0 * 25, s, o0);
+      couple<CW, 3, 1>(M + 3 * 25, v, o1);
+      float* r0 = a.A0 + row * a.lda0;
+#pragma unroll
+      for (int c = 0; c < CW; ++c)
+        if (on[c]) {
+          r0[a.koff[0] + uc[c]] = o0[c][0];
+          r0[a.koff[3] + uc[c]] = o1[c][0];
+        }
+    }
+    {
+      float p0[CW][3], p1[CW][3], p2[CW][3];
+#pragma unroll
+      for (int c = 0; c < CW; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p0[c][k] = p1[c][k] = p2[c][k] = 0.f;
+      couple<CW, 1, 3>(M + 1 * 25, s, p0);
+      couple<CW, 3, 3>(M + 2 * 25, v, p1);
+      couple<CW, 5, 3>(M + 6 * 25, qq, p2);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float* r1 = a.A1 + (row * 3 + k) * a.lda1;
+#pragma unroll
+        for (int c = 0; c < CW; ++c)
+          if (on[c]) {
+            r1[a.koff[1] + uc[c]] = p0[c][k];
+            r1[a.koff[2] + uc[c]] = p1[c][k];
+            r1[a.koff[6] + uc[c]] = p2[c][k];
+          }
+      }
+    }
+    {
+      float p0[CW][5], p1[CW][5];
+#pragma unroll
+      for (int c = 0; c < CW; ++c)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) p0[c][k] = p1[c][k] = 0.f;
+      couple<CW, 3, 5>(M + 4 * 25, v, p0);
+      couple<CW, 5, 5>(M + 5 * 25, qq, p1);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        float* r2 = a.A2 + (row * 5 + k) * a.lda2;
+#pragma unroll
+        for (int c = 0; c < CW; ++c)
+          if (on[c]) {
+            r2[a.koff[4] + uc[c]] = p0[c][k];
+            r2[a.koff[5] + uc[c]] = p1[c][k];
+          }
+      }
+    }
 }
 
 __global__ void __launch_bounds__(kWarps * 32) l2_msg_rows_kernel(const RowsArgs a) {
@@ -64,7 +207,9 @@ __global__ void __launch_bounds__(kWarps * 32) l2_msg_rows_kernel(const RowsArgs
   const long long gl = rl / N;
   const int ir = (int)(rl - gl * N);
   const long long base = a.node0 + gl * N;
-  const float* yi = a.Y + (base + ir) * a.ydim;
+  const float* yi0 = a.Y[0] + (base + ir) * a.ldy[0];
+  const float* yi1 = a.Y[1] + (base + ir) * 3 * a.ldy[1];
+  const float* yi2 = a.Y[2] + (base + ir) * 5 * a.ldy[2];
   const float pix = a.pos[(base + ir) * 3 + 0], piy = a.pos[(base + ir) * 3 + 1], piz = a.pos[(base + ir) * 3 + 2];
   const float mi = a.mass[base + ir];
   float* M = Ms[warp];
@@ -85,81 +230,15 @@ __global__ void __launch_bounds__(kWarps * 32) l2_msg_rows_kernel(const RowsArgs
       M[idx] = m;
     }
     __syncwarp();
-    const float* yj = a.Y + (base + j) * a.ydim;
+    const float* yj0 = a.Y[0] + (base + j) * a.ldy[0];
+    const float* yj1 = a.Y[1] + (base + j) * 3 * a.ldy[1];
+    const float* yj2 = a.Y[2] + (base + j) * 5 * a.ldy[2];
     const long long row = rl * N + j;
-    for (int c = 0; c < kMaxCpt; ++c) {
-      const int u = lane + 32 * c;
-      if (u >= n) break;
-      // ---- message_layer_1: 0e outputs (scalar u, gate of 1o_u, gate of 2e_u) -----------------------------------
-      float z0[3];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int w = q * n + u;
-        float S0[1], S3[3], z[1];
-        z[0] = a.bias1[w] + M[0] * (a.w_add0[w] * len + a.w_add0[3 * n + w] * mm);  // additional scalars: type (0,0,0)
-        load_sum<1>(yi + a.yoff[0][0], yj + a.yoff[0][1], w, S0);
-        couple<1, 1>(M + 0 * 25, S0, z);
-        load_sum<3>(yi + a.yoff[3][0], yj + a.yoff[3][1], w, S3);
-        couple<3, 1>(M + 3 * 25, S3, z);
-        z0[q] = z[0];
-      }
-      // ---- 1o and 2e outputs -------------------------------------------------------------------------------------
-      float z1[3] = {0.f, 0.f, 0.f}, z2[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      {
-        float S1[1], S3[3], S5[5];
-        load_sum<1>(yi + a.yoff[1][0], yj + a.yoff[1][1], u, S1);
-        S1[0] += a.w_add1[u] * len + a.w_add1[n + u] * mm;  // additional scalars: type (0,1,1)
-        couple<1, 3>(M + 1 * 25, S1, z1);
-        load_sum<3>(yi + a.yoff[2][0], yj + a.yoff[2][1], u, S3);
-        couple<3, 3>(M + 2 * 25, S3, z1);
-        load_sum<5>(yi + a.yoff[6][0], yj + a.yoff[6][1], u, S5);
-        couple<5, 3>(M + 6 * 25, S5, z1);
-        load_sum<3>(yi + a.yoff[4][0], yj + a.yoff[4][1], u, S3);
-        couple<3, 5>(M + 4 * 25, S3, z2);
-        load_sum<5>(yi + a.yoff[5][0], yj + a.yoff[5][1], u, S5);
-        couple<5, 5>(M + 5 * 25, S5, z2);
-      }
-      // ---- e3nn Gate ---------------------------------------------------------------------------------------------
-      float s[1] = {silu_gate(z0[0])};
-      const float g1 = sig_gate(z0[1]), g2 = sig_gate(z0[2]);
-      float v[3], qq[5];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) v[k] = g1 * z1[k];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) qq[k] = g2 * z2[k];
-      // ---- message_layer_2: coupling of the gated message with the edge attribute -> GEMM operand rows -----------
-      {
-        float o0[1] = {0.f}, o1[1] = {0.f};
-        couple<1, 1>(M + 0 * 25, s, o0);
-        couple<3, 1>(M + 3 * 25, v, o1);
-        float* r0 = a.A0 + row * a.lda0;
-        r0[a.koff[0] + u] = o0[0];
-        r0[a.koff[3] + u] = o1[0];
-      }
-      {
-        float p0[3] = {0.f, 0.f, 0.f}, p1[3] = {0.f, 0.f, 0.f}, p2[3] = {0.f, 0.f, 0.f};
-        couple<1, 3>(M + 1 * 25, s, p0);
-        couple<3, 3>(M + 2 * 25, v, p1);
-        couple<5, 3>(M + 6 * 25, qq, p2);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float* r1 = a.A1 + (row * 3 + k) * a.lda1;
-          r1[a.koff[1] + u] = p0[k];
-          r1[a.koff[2] + u] = p1[k];
-          r1[a.koff[6] + u] = p2[k];
-        }
-      }
-      {
-        float p0[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, p1[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        couple<3, 5>(M + 4 * 25, v, p0);
-        couple<5, 5>(M + 5 * 25, qq, p1);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          float* r2 = a.A2 + (row * 5 + k) * a.lda2;
-          r2[a.koff[4] + u] = p0[k];
-          r2[a.koff[5] + u] = p1[k];
-        }
-      }
+    {
+      EdgeCtx e{yi0, yi1, yi2, yj0, yj1, yj2, M, len, mm, row};
+      // one channel per lane and pass: two at once (edge_channels<2>, every coupling coefficient read once for both)
+      // was measured slower -- 168+ registers against 128 cost more occupancy than the shared-memory reads saved
+      for (int c0 = 0; 32 * c0 < n; ++c0) edge_channels<1>(a, e, c0, lane);
     }
   }
 }
@@ -182,7 +261,7 @@ __global__ void __launch_bounds__(96 * kGY)
   for (int v = 0; v < 9; ++v) acc[v] = 0.f;
   if (act) {
     const float b0 = bias2[u], b1 = bias2[n + u], b2 = bias2[2 * n + u];
-#pragma unroll 2
+#pragma unroll 4
     for (int j = y; j < N; j += kGY) {
       const float valid = j == ir ? 0.f : 1.f;
       const long long row = rl * N + j;
@@ -226,6 +305,28 @@ __global__ void __launch_bounds__(96 * kGY)
   }
 }
 
+// x [nodes][9n] in e3nn layout (n x 0e | n x 1o | n x 2e, index u (2l + 1) + i) -> planar rows per degree:
+// xp_l[(node * (2l + 1) + i)][ld] with the channel u contiguous: the A operands of the node-level GEMMs
+__global__ void l2_planarize_kernel(const float* __restrict__ x, long long nodes, int n, long long ld,
+                                    float* __restrict__ x0, float* __restrict__ x1, float* __restrict__ x2) {
+  const long long total = nodes * 9 * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long node = idx / (9 * n);
+    const int c = (int)(idx - node * 9 * n);
+    const float v = x[idx];
+    if (c < n) {
+      x0[node * ld + c] = v;
+    } else if (c < 4 * n) {
+      const int u = (c - n) / 3, i = (c - n) - 3 * u;
+      x1[(node * 3 + i) * ld + u] = v;
+    } else {
+      const int u = (c - 4 * n) / 5, i = (c - 4 * n) - 5 * u;
+      x2[(node * 5 + i) * ld + u] = v;
+    }
+  }
+}
+
 }  // namespace l2
 }  // namespace segnn
 
@@ -233,18 +334,21 @@ using namespace segnn;
 
 extern "C" {
 
-int segnn_l2_msg_rows(const float* pos, const float* mass, int graphs, int N, int n, int64_t node0, const float* Y,
-                      int ydim, const int* yoff, const float* cg, const float* w_add0, const float* w_add1,
+int segnn_l2_msg_rows(const float* pos, const float* mass, int graphs, int N, int n, int64_t node0, const float* Y0,
+                      int64_t ldy0, const float* Y1, int64_t ldy1, const float* Y2, int64_t ldy2, const int* yoff,
+                      const float* cg, const float* w_add0, const float* w_add1,
                       const float* bias1, const int* koff, int64_t lda0, int64_t lda1, int64_t lda2, float* A0,
                       float* A1, float* A2, segnn_stream_t stream) {
-  SEGNN_CHECK_ARG(graphs >= 0 && N >= 2 && n >= 1 && n <= 32 * l2::kMaxCpt && ydim >= 1 && node0 >= 0, "bad sizes");
+  SEGNN_CHECK_ARG(graphs >= 0 && N >= 2 && n >= 1 && n <= 96 && node0 >= 0, "bad sizes");
   if (graphs == 0) return SEGNN_OK;
-  SEGNN_CHECK_ARG(pos && mass && Y && yoff && cg && w_add0 && w_add1 && bias1 && koff && A0 && A1 && A2,
+  SEGNN_CHECK_ARG(pos && mass && Y0 && Y1 && Y2 && yoff && cg && w_add0 && w_add1 && bias1 && koff && A0 && A1 && A2,
                   "null pointer");
   SEGNN_CHECK_ARG(lda0 >= 2 * n && lda1 >= 3 * n && lda2 >= 2 * n, "leading dimensions too small");
   l2::RowsArgs a{};
-  a.pos = pos; a.mass = mass; a.Y = Y;
-  a.B = graphs; a.N = N; a.n = n; a.ydim = ydim;
+  a.pos = pos; a.mass = mass;
+  a.Y[0] = Y0; a.Y[1] = Y1; a.Y[2] = Y2;
+  a.ldy[0] = ldy0; a.ldy[1] = ldy1; a.ldy[2] = ldy2;
+  a.B = graphs; a.N = N; a.n = n;
   for (int t = 0; t < l2::kTypes; ++t) {
     a.yoff[t][0] = yoff[2 * t];
     a.yoff[t][1] = yoff[2 * t + 1];
@@ -257,6 +361,19 @@ int segnn_l2_msg_rows(const float* pos, const float* mass, int graphs, int N, in
   const long long blocks = (long long)graphs * N;
   SEGNN_CHECK_ARG(blocks <= 0x7fffffff, "too many receivers per call");
   l2::l2_msg_rows_kernel<<<(unsigned)blocks, l2::kWarps * 32, 0, (cudaStream_t)stream>>>(a);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_l2_planarize(const float* x, int64_t nodes, int n, int64_t ld, float* x0, float* x1, float* x2,
+                       segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n >= 1 && ld >= n, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x && x0 && x1 && x2, "null pointer");
+  const long long total = nodes * 9 * n;
+  const long long blocks = (total + 255) / 256;
+  l2::l2_planarize_kernel<<<(unsigned)(blocks < 2368 ? blocks : 2368), 256, 0, (cudaStream_t)stream>>>(x, nodes, n, ld, x0,
+                                                                                                    x1, x2);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

@@ -303,10 +303,23 @@ class Lmax2EdgePlan:
             cg[i, :2 * l1 + 1, :2 * l2 + 1, :2 * lo + 1] = math.sqrt(2 * lo + 1) * real_wigner_3j(l1, l2, lo)
         self.cg = torch.tensor(cg, dtype=torch.float32, device=device).contiguous()
         ltype = lambda d1, d2, do: tindex[((d1 - 1) // 2, (d2 - 1) // 2, (do - 1) // 2)]
+        # node-level products of message_layer_1 as three GEMMs (one per input degree l1): the weight views [n][mo] of
+        # the instructions with that input degree, x_i and x_j roles side by side; yoff[type][role] = first column
+        nh = len(hidden_irreps)
+        self.ystack = {0: [], 1: [], 2: []}  # l1 -> [(weight offset, mo)]
+        ncols = {0: 0, 1: 0, 2: 0}
         yoff = [[-1, -1] for _ in range(7)]
-        for oo, mo, do, d1, o2, d2, yi, yj in hoisted.pairs.cpu().tolist():
-            yoff[ltype(d1, d2, do)] = [yi, yj]
+        for ins in layer.message_layer_1.tp.instructions:
+            if ins["i1"] >= 2 * nh:
+                continue
+            role, (l1, l2, lo) = ins["i1"] // nh, ins["ls"]
+            mo = ins["shape"][2]
+            assert ins["shape"][0] == n
+            yoff[tindex[(l1, l2, lo)]][role] = ncols[l1]
+            self.ystack[l1].append((ins["offset"], mo))
+            ncols[l1] += mo
         assert all(a >= 0 and b >= 0 for a, b in yoff)
+        self.ncols = ncols
         self.yoff = torch.tensor(yoff, dtype=torch.int32).contiguous()  # host: read by the C call, not by a kernel
         self.add_off = {}
         for oo, mo, do, o2, d2, woff, mul1 in hoisted.adds.cpu().tolist():
@@ -341,6 +354,8 @@ class Lmax2EdgePlan:
                  w_add1=w1[self.add_off[1][0]: self.add_off[1][0] + 2 * n],
                  bias1=f32(m1.biases)[: 3 * n], bias2=f32(m2.biases)[: 3 * n])
         assert m1.biases.numel() == 3 * n and m2.biases.numel() == 3 * n
+        for l1, views in self.ystack.items():
+            c[f"ystack{l1}"] = torch.cat([w1[off: off + n * mo].view(n, mo) for off, mo in views], dim=1).contiguous()
         for d, b in self.blocks.items():
             c[f"stacked{d}"] = torch.cat([w2[off: off + k * b["mulo"]].view(k, b["mulo"]) for off, k in b["wviews"]],
                                    dim=0).contiguous()
@@ -353,25 +368,29 @@ class Lmax2EdgePlan:
         c = self._weights(dev)
         hp = self.hoisted
         nodes = B * N
-        ones = torch.ones((nodes, 1), dtype=torch.float32, device=dev)
-        Y = torch.empty((nodes, hp.ydim), dtype=torch.float32, device=dev)
         agg = torch.empty((nodes, 9 * n), dtype=torch.float32, device=dev)
         K = {d: self.blocks[d]["K"] for d in (1, 3, 5)}
         lda = {d: (K[d] + 3) & ~3 for d in (1, 3, 5)}
         ldy = {1: (3 * n + 3) & ~3, 3: (n + 3) & ~3, 5: (n + 3) & ~3}
         per_graph = 4 * N * N * sum(d * (lda[d] + ldy[d]) for d in (1, 3, 5))
         gpc = max(1, min(B, self.CHUNK_BYTES // per_graph))
+        ldx = (n + 3) & ~3
+        xp = [torch.empty((nodes * d, ldx), dtype=torch.float32, device=dev) for d in (1, 3, 5)]
+        ldn = [(self.ncols[l1] + 3) & ~3 for l1 in (0, 1, 2)]
+        Yn = [torch.empty((nodes * d, ldn[l1]), dtype=torch.float32, device=dev) for l1, d in enumerate((1, 3, 5))]
         with torch.cuda.device(dev):
-            check(lib.segnn_generic_tp(_p(x), hp.D, _p(ones), 1, nodes, _p(c["tp_weight_1"]), _p(hp.yinstr), hp.n_y, _p(hp.ycg),
-                                       None, hp.ydim, _p(Y), ops._stream()), "segnn_generic_tp")
+            check(lib.segnn_l2_planarize(_p(x), nodes, n, ldx, _p(xp[0]), _p(xp[1]), _p(xp[2]), ops._stream()),
+                  "segnn_l2_planarize")
             ops._bump()
+            for l1 in (0, 1, 2):
+                ops.gemm_tf32x3(xp[l1][:, :n], c[f"ystack{l1}"], out=Yn[l1][:, :self.ncols[l1]])
             for g0 in range(0, B, gpc):
                 gc = min(gpc, B - g0)
                 rows = gc * N * N
                 A = {d: torch.empty((rows * d, lda[d]), dtype=torch.float32, device=dev) for d in (1, 3, 5)}
                 Yb = {d: torch.empty((rows * d, ldy[d]), dtype=torch.float32, device=dev) for d in (1, 3, 5)}
-                check(lib.segnn_l2_msg_rows(_p(pos), _p(mass), gc, N, n, g0 * N, _p(Y), hp.ydim,
-                                            self.yoff.data_ptr(), _p(self.cg), _p(c["w_add0"]), _p(c["w_add1"]),
+                check(lib.segnn_l2_msg_rows(_p(pos), _p(mass), gc, N, n, g0 * N, _p(Yn[0]), ldn[0], _p(Yn[1]), ldn[1],
+                                            _p(Yn[2]), ldn[2], self.yoff.data_ptr(), _p(self.cg), _p(c["w_add0"]), _p(c["w_add1"]),
                                             _p(c["bias1"]), self.koff.data_ptr(), lda[1], lda[3], lda[5], _p(A[1]),
                                             _p(A[3]), _p(A[5]), ops._stream()), "segnn_l2_msg_rows")
                 for d in (1, 3, 5):

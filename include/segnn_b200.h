@@ -352,17 +352,23 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
  * (models/segnn/segnn.py:205,264-284; o3_building_blocks.py:150-203) around the weight contraction of message_layer_2.
  * Edge rows are (graph, receiver, sender) of `graphs` graphs starting at node `node0`, diagonal kept and masked.
  * Instruction types t = 0..6 = (l1, l2, lo) in the order (0,0,0) (0,1,1) (1,0,1) (1,1,0) (1,1,2) (2,0,2) (2,1,1).
- * segnn_l2_msg_rows: Y [nodes][ydim] = node-level products of message_layer_1 (segnn_generic_hoisted_msg1's layout:
- *   Y[node][yoff[t][role] + w * (2 l1 + 1) + i], role 0 = x_i, 1 = x_j), cg [7][5][3][5] net couplings, w_add0 [2][3n] /
- *   w_add1 [2][n] weights of the additional scalars, bias1 [3n]; writes the three operands of message_layer_2's
- *   contraction, A0 [rows][lda0], A1 [3 rows][lda1], A2 [5 rows][lda2], type t in columns koff[t] .. koff[t] + n.
+ * segnn_l2_planarize: hidden features x [nodes][9n] (e3nn layout) -> x_l [(node (2l + 1) + i)][ld], channel contiguous:
+ *   the A operands of the node-level products of message_layer_1, Y_l = x_l * (stacked weights of the instructions
+ *   with input degree l, both roles), computed with segnn_gemm_tf32x3.
+ * segnn_l2_msg_rows: Y_l [(node (2l + 1) + i)][ldy_l] with instruction (t, role) in columns yoff[t][role] .. + its
+ *   output multiplicity (role 0 = x_i, 1 = x_j), cg [7][5][3][5] net couplings, w_add0 [2][3n] / w_add1 [2][n] weights
+ *   of the additional scalars, bias1 [3n]; writes the three operands of message_layer_2's contraction, A0 [rows][lda0],
+ *   A1 [3 rows][lda1], A2 [5 rows][lda2], type t in columns koff[t] .. koff[t] + n.
  * segnn_l2_gate_aggregate: Y_b = A_b * stacked weights (segnn_gemm_tf32x3) -> bias2 [3n], e3nn Gate, sum over senders,
  *   folded eval BatchNorm (bn_mul, bn_add [9n] per hidden column, add applied N - 1 times; both NULL = none) ->
  *   agg [nodes][9n] in e3nn layout. */
-int segnn_l2_msg_rows(const float* pos, const float* mass, int graphs, int N, int n, int64_t node0, const float* Y,
-                      int ydim, const int* yoff, const float* cg, const float* w_add0, const float* w_add1,
-                      const float* bias1, const int* koff, int64_t lda0, int64_t lda1, int64_t lda2, float* A0,
-                      float* A1, float* A2, segnn_stream_t stream);
+int segnn_l2_planarize(const float* x, int64_t nodes, int n, int64_t ld, float* x0, float* x1, float* x2,
+                       segnn_stream_t stream);
+int segnn_l2_msg_rows(const float* pos, const float* mass, int graphs, int N, int n, int64_t node0, const float* Y0,
+                      int64_t ldy0, const float* Y1, int64_t ldy1, const float* Y2, int64_t ldy2, const int* yoff,
+                      const float* cg, const float* w_add0, const float* w_add1, const float* bias1, const int* koff,
+                      int64_t lda0, int64_t lda1, int64_t lda2, float* A0, float* A1, float* A2,
+                      segnn_stream_t stream);
 int segnn_l2_gate_aggregate(int graphs, int N, int n, int64_t node0, const float* Y0, int64_t ld0, const float* Y1,
                             int64_t ld1, const float* Y2, int64_t ld2, const float* bias2, const float* bn_mul,
                             const float* bn_add, float* agg, segnn_stream_t stream);

@@ -363,7 +363,10 @@ __global__ void __launch_bounds__(96 * kSY)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTI = 32, kTJ = 16, kSL = 4;
 
-template <int NCH>
+// STAGE_Q: the sender-side projections of the tile are staged in shared memory (12 of the 17 global loads per edge go
+// away, the shared-memory footprint doubles).  It wins when the grid is small (training-size graphs: latency), it
+// loses on large graphs (one block less per SM: configuration 4 went 31.0 -> 32.4 ms), so the host picks.
+template <int NCH, bool STAGE_Q>
 __global__ void __launch_bounds__(384)
     msg1_bwd_tile_kernel(const RowArgs a, const float* __restrict__ dxs, const float* __restrict__ dxv, int tiles_i,
                          int tiles_j, int64_t chunk_nodes, float* __restrict__ dp_part, float* __restrict__ dq_part,
@@ -372,9 +375,10 @@ __global__ void __launch_bounds__(384)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sl = lane >> 3, w = warp * 8 + (lane & 7);
   const int NC = NCH ? ((NCH + 7) & ~7) : (blockDim.x >> 5) * 8;   // channels covered by the block (>= n)
-  float(*gs)[8] = reinterpret_cast<float(*)[8]>(smem);          // [kTI * kTJ][8]
-  float* dq = smem + kTI * kTJ * 8;                              // [kTJ][12 * NC + 8]: the four sender lanes of a warp
+  float(*gs)[6] = reinterpret_cast<float(*)[6]>(smem);          // [kTI * kTJ][6]
+  float* dq = smem + kTI * kTJ * 6;                              // [kTJ][12 * NC + 8]: the four sender lanes of a warp
   const int dqs = 12 * NC + 8;                                   // own consecutive senders: + 8 floats keeps them on distinct banks
+  float* qs = dq + kTJ * dqs;                                    // [kTJ][12 * NC + 8]: the Q rows of the tile's senders
   const int n = NCH ? NCH : a.n, N = a.N, n3 = 3 * n;
   const int jt = blockIdx.x % tiles_j, it_ = (blockIdx.x / tiles_j) % tiles_i;
   const int64_t gl = blockIdx.x / (tiles_i * tiles_j);
@@ -397,9 +401,17 @@ __global__ void __launch_bounds__(384)
     gs[t][5] = a.mass[nj] * a.mass[ni];
   }
 #pragma unroll
-  for (int q = 0; q < kTJ / kSL; ++q)
+  for (int q = 0; q < kTJ / kSL; ++q) {
+    const int jj = sl + kSL * q;
+    // the sender-side projections of the tile are read by all 32 receivers: staged once (they were 12 of the 17 global
+    // loads per edge, each a four-line request -- the L1 tag stage was the busiest unit of the kernel)
+    const float* qrow = a.qq + (base + min(j0 + jj, N - 1)) * 4 * n3;
 #pragma unroll
-    for (int v = 0; v < 12; ++v) dq[(sl + kSL * q) * dqs + v * NC + w] = 0.f;
+    for (int v = 0; v < 12; ++v) {
+      dq[jj * dqs + v * NC + w] = 0.f;
+      if (STAGE_Q) qs[jj * dqs + v * NC + w] = act ? qrow[v * n + w] : 0.f;
+    }
+  }
   float wd0s = 0.f, wd0g = 0.f, wm0s = 0.f, wm0g = 0.f, wd1 = 0.f, wm1 = 0.f;
   if (act) {
     wd0s = a.w_edge1[w];
@@ -433,12 +445,16 @@ __global__ void __launch_bounds__(384)
         const float* xr = dxs + row * 2 * n;
         const float* vr = dxv + row * n3;
         const float d0 = xr[wc], d1 = xr[n + wc], d2 = vr[wc], d3 = vr[n + wc], d4 = vr[2 * n + wc];
-        const float* orow = a.qq + (base + j) * 4 * n3;
         float S[12];
+        if (STAGE_Q) {
+          const float* orow = qs + jj * dqs + w;  // this thread staged exactly these cells (same jj, same w): no barrier
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+          for (int v = 0; v < 12; ++v) S[v] = st[v] + orow[v * NC];
+        } else {
+          const float* orow = a.qq + (base + j) * 4 * n3 + wc;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) S[c * 3 + k] = st[c * 3 + k] + orow[c * n3 + k * n + wc];
+          for (int v = 0; v < 12; ++v) S[v] = st[v] + orow[v * n];
+        }
         const float ax = g[0], ay = g[1], az = g[2], len = g[4], mm = g[5];
         const float zs = S[0] + ax * S[3] + ay * S[6] + az * S[9] + len * wd0s + mm * wm0s;
         const float zg = S[1] + ax * S[4] + ay * S[7] + az * S[10] + len * wd0g + mm * wm0g;
@@ -1024,11 +1040,12 @@ struct Kernels {
   decltype(&msg1_rows_kernel<0>) rows;
   decltype(&gate2_fwd_kernel<0>) g2f;
   decltype(&gate2_bwd_kernel<0>) g2b;
-  decltype(&msg1_bwd_tile_kernel<0>) tile;
+  decltype(&msg1_bwd_tile_kernel<0, false>) tile, tile_q;
 };
 template <int NCH>
 static Kernels make_kernels() {
-  return {msg1_rows_kernel<NCH>, gate2_fwd_kernel<NCH>, gate2_bwd_kernel<NCH>, msg1_bwd_tile_kernel<NCH>};
+  return {msg1_rows_kernel<NCH>, gate2_fwd_kernel<NCH>, gate2_bwd_kernel<NCH>, msg1_bwd_tile_kernel<NCH, false>,
+          msg1_bwd_tile_kernel<NCH, true>};
 }
 // the multiplicities of the BASELINE configurations (hidden 64 / 128 / 192) get compile-time offsets
 static Kernels kernels_for(int n) {
@@ -1167,8 +1184,12 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
   cudaFuncSetAttribute(kn.g2b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node);
   const int tiles_i = (N + eg::kTI - 1) / eg::kTI, tiles_j = (N + eg::kTJ - 1) / eg::kTJ;
   const int tile_warps = (n + 7) / 8;  // a warp of the tile kernel covers 8 channels x 4 sender lanes
-  const size_t smem_tile = sizeof(float) * ((size_t)eg::kTI * eg::kTJ * 8 + (size_t)eg::kTJ * (12 * tile_warps * 8 + 8));
-  cudaFuncSetAttribute(kn.tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile);
+  // small grids (training-size graphs) stage the sender projections of a tile in shared memory
+  const bool stage_q = (int64_t)(gpc < B ? gpc : B) * tiles_i * tiles_j < 2 * 148;
+  const auto k_tile = stage_q ? kn.tile_q : kn.tile;
+  const size_t smem_tile = sizeof(float) * ((size_t)eg::kTI * eg::kTJ * 6 +
+                                            (stage_q ? 2 : 1) * (size_t)eg::kTJ * (12 * tile_warps * 8 + 8));
+  cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile);
   // rows kept by the forward call (XS, XV, Y, DV of ALL graphs, i.e. the forward ran as one chunk): no recompute
   const float *kxs = nullptr, *kxv = nullptr, *kyy = nullptr, *kdv = nullptr;
   if (fwd_workspace != nullptr) {
@@ -1235,7 +1256,7 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
     float* dp_part = db2_rows + eg::align64(cn * 2 * n);
     float* dq_part = dp_part + eg::align64(tiles_j * cn * 12 * n);
     float* dwe_part = dq_part + eg::align64(tiles_i * cn * 12 * n);
-    kn.tile<<<(unsigned)(gc * tiles_i * tiles_j), tile_warps * 32, smem_tile, s>>>(
+    k_tile<<<(unsigned)(gc * tiles_i * tiles_j), tile_warps * 32, smem_tile, s>>>(
         ra, dxs, dxv, tiles_i, tiles_j, cn, dp_part, dq_part, dwe_part);
     SEGNN_CHECK_LAUNCH();
     const int64_t node0 = g0 * N;

@@ -54,6 +54,8 @@ PROTOTYPES = {
     "segnn_node_gemm_wgrad": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _int, _int, _ptr, _ptr, _ptr, _ptr]),
     "segnn_edge_layer_bwd": (_int, [_int, _ptr, _ptr, _int, _int, _int] + [_ptr] * 25),
     "segnn_edge_layer_bwd_workspace": (_c.c_int64, [_int, _int, _int]),
+    "segnn_node_gemm_tf32x3_workspace": (_c.c_int64, [_int, _int]),
+    "segnn_node_gemm_tf32x3": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr, _ptr]),
     "segnn_gemm_tn_tf32x3_workspace": (_c.c_int64, [_c.c_int64, _int, _int]),
     "segnn_gemm_tn_tf32x3": (_int, [_ptr, _c.c_int64, _ptr, _c.c_int64, _c.c_int64, _int, _int, _ptr, _c.c_int64, _int,
                                     _ptr, _ptr]),

@@ -122,9 +122,24 @@ __global__ void gemm_prep_b_kernel(const float* __restrict__ B, int ldb, int K, 
   }
 }
 
+// NODE mode: the rows are the (node, plane) rows of planar node features [nodes][4][n_in] (segnn_node_gemm's contract):
+// class 0 = the scalar plane of every node against W_s, class 1 = the three vector planes against W_v, both in one
+// launch (the tile list is class 0's tiles followed by class 1's); K may be the concatenation of two sources (x0 | x1);
+// the output goes to y0 [plane][split] | y1 [plane][n_out - split] with the bias on class 0.
+struct NodeMap {
+  const float *x0, *x1;
+  int n_in;
+  long long nodes;
+  const float* bias;
+  int n_bias, split;
+  float *y0, *y1;
+  long long img_stride;  // floats between the B images of the two classes
+};
+
+template <bool NODE>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_tf32x3_kernel(const float* __restrict__ A, long long lda, long long M, int K, int N, int NP, int chunks,
-                       const float* __restrict__ Bimg, float* __restrict__ C, long long ldc) {
+                       const float* __restrict__ Bimg, float* __restrict__ C, long long ldc, const NodeMap nm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int a_bytes = kBM * 128;      // one of (hi, lo)
@@ -141,7 +156,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int nb = blockIdx.y;
   const int n0 = nb * NP;
   const int ncols = max(0, min(NP, N - n0));  // live columns of this block (<= NP)
-  const long long tiles = (M + kBM - 1) / kBM;
+  // NODE: tiles of class 0 (nodes rows) then tiles of class 1 (3 nodes rows)
+  const long long tiles0 = NODE ? (nm.nodes + kBM - 1) / kBM : 0;
+  const long long tiles = NODE ? tiles0 + (3 * nm.nodes + kBM - 1) / kBM : (M + kBM - 1) / kBM;
 
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -169,8 +186,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     // The global loads of a chunk are issued two chunks before it is converted (three register sets, the (tile, chunk)
     // sequence flattened so that the prefetch crosses tile boundaries): ~48 KB per SM in flight instead of 16 KB, which
     // is what lets a GEMM with K of one to six chunks stream its rows at HBM speed.
-    const float* bsrc = Bimg + (long long)nb * chunks * 2 * NP * kKC;
+    const float* bsrc0 = Bimg + (long long)nb * chunks * 2 * NP * kKC;
     const bool vec_ok = (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+    const bool node_vec_ok = NODE && (nm.n_in & 7) == 0 && (reinterpret_cast<uintptr_t>(nm.x0) & 15) == 0 &&
+                             (nm.x1 == nullptr || (reinterpret_cast<uintptr_t>(nm.x1) & 15) == 0);
     const long long my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long total = my_tiles * chunks;
     constexpr int kPieces = (kBM * 4) / (kLoadWarps * 32);
@@ -181,9 +200,34 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int i = 0; i < kPieces; ++i) {
         const int p = tid + i * (kLoadWarps * 32);
         const int row = p >> 2, q = p & 3;
-        const long long gr = tile * kBM + row;
         const int k = k0 + 8 * q;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        if (NODE) {
+          const bool c1 = tile >= tiles0;
+          const long long gr = (c1 ? tile - tiles0 : tile) * kBM + row;
+          if (gr < (c1 ? 3 * nm.nodes : nm.nodes)) {
+            const long long plane = c1 ? (gr / 3) * 4 + 1 + gr % 3 : gr * 4;
+            if (node_vec_ok && k + 8 <= K) {  // n_in % 8 == 0: a piece never straddles the two sources
+              const float* src = k < nm.n_in ? nm.x0 + plane * nm.n_in + k : nm.x1 + plane * nm.n_in + (k - nm.n_in);
+              a0 = *reinterpret_cast<const float4*>(src);
+              a1 = *reinterpret_cast<const float4*>(src + 4);
+            } else {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int kk = k + j;
+                v[j] = kk >= K ? 0.f
+                               : (kk < nm.n_in ? nm.x0[plane * nm.n_in + kk] : nm.x1[plane * nm.n_in + (kk - nm.n_in)]);
+              }
+              a0 = make_float4(v[0], v[1], v[2], v[3]);
+              a1 = make_float4(v[4], v[5], v[6], v[7]);
+            }
+          }
+          r[2 * i] = a0;
+          r[2 * i + 1] = a1;
+          continue;
+        }
+        const long long gr = tile * kBM + row;
         if (gr < M) {
           const float* src = A + gr * lda + k;
           if (vec_ok && k + 8 <= K) {
@@ -207,6 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_wait(&empty[s], (uint32_t)((it / kStages) & 1) ^ 1);
       uint8_t* st = smem + s * stage_bytes;
       if (tid == 0) {
+        const float* bsrc = bsrc0;
+        if (NODE && blockIdx.x + (it / chunks) * gridDim.x >= tiles0) bsrc += nm.img_stride;  // W_v images
         const uint32_t bytes = 2u * (uint32_t)b_bytes;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(bytes)
                      : "memory");
@@ -322,6 +368,27 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr) {
             const int row = rr * 4 + sub;
+            if (NODE) {
+              const bool c1 = tile >= tiles0;
+              const long long gr = (c1 ? tile - tiles0 : tile) * kBM + quad * 32 + row;
+              if (gr < (c1 ? 3 * nm.nodes : nm.nodes)) {
+                const long long plane = c1 ? (gr / 3) * 4 + 1 + gr % 3 : gr * 4;
+                const float4 v = *reinterpret_cast<const float4*>(stg + row * kStgLd + 4 * c4);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+                const int c = n0 + ccol;  // global output column
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const int cc = c + jj;
+                  if (ccol + jj < ncols) {
+                    float o = vv[jj];
+                    if (!c1 && nm.bias != nullptr && cc < nm.n_bias) o += nm.bias[cc];
+                    if (cc < nm.split) nm.y0[plane * nm.split + cc] = o;
+                    else nm.y1[plane * (N - nm.split) + (cc - nm.split)] = o;
+                  }
+                }
+              }
+              continue;
+            }
             const long long gr = tile * kBM + quad * 32 + row;
             if (gr < M) {
               const float4 v = *reinterpret_cast<const float4*>(stg + row * kStgLd + 4 * c4);
@@ -383,7 +450,7 @@ int segnn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, 
   SEGNN_CHECK_LAUNCH();
   const size_t smem = 1024 + (size_t)g3::kStages * (2 * g3::kBM * 128 + 2 * NP * 128) + 256 +
                       (size_t)g3::kEpiWarps * 32 * g3::kStgLd * sizeof(float);
-  cudaError_t err = cudaFuncSetAttribute(g3::gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = cudaFuncSetAttribute(g3::gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) {
     set_error("segnn_gemm_tf32x3: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(err));
     return SEGNN_E_CUDA;
@@ -396,8 +463,57 @@ int segnn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, 
   if (gx < 1) gx = 1;
   if (gx > tiles) gx = tiles;
   dim3 grid((unsigned)gx, (unsigned)nblocks);
-  g3::gemm_tf32x3_kernel<<<grid, g3::kThreads, smem, s>>>(A, (long long)lda, (long long)M, K, N, NP, chunks, workspace,
-                                                         C, (long long)ldc);
+  g3::gemm_tf32x3_kernel<false><<<grid, g3::kThreads, smem, s>>>(A, (long long)lda, (long long)M, K, N, NP, chunks,
+                                                                workspace, C, (long long)ldc, g3::NodeMap{});
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int64_t segnn_node_gemm_tf32x3_workspace(int K, int n_out) {
+  const int64_t one = segnn_gemm_tf32x3_workspace(K, n_out);
+  return one < 0 ? one : 2 * one;
+}
+
+int segnn_node_gemm_tf32x3(const float* x0, const float* x1, int nodes, int n_in, const float* w_s, const float* w_v,
+                           const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, float* workspace,
+                           segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n_in >= 1 && n_out >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x0 && w_s && w_v && y0 && workspace, "null pointer");
+  SEGNN_CHECK_ARG(bias == nullptr || (n_bias >= 0 && n_bias <= n_out), "n_bias out of range");
+  SEGNN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+  if (y1 == nullptr) split = n_out;
+  SEGNN_CHECK_ARG(split > 0 && split <= n_out, "split out of range");
+  const int K = x1 ? 2 * n_in : n_in;
+  const int chunks = (K + g3::kKC - 1) / g3::kKC;
+  const int nblocks = (n_out + g3::kNMax - 1) / g3::kNMax;
+  const int NP = g3::padded_n(n_out);
+  const int64_t img = segnn_gemm_tf32x3_workspace(K, n_out) / (int64_t)sizeof(float);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long prep_total = (long long)nblocks * chunks * NP * g3::kKC;
+  const unsigned prep_grid = (unsigned)((prep_total + 255) / 256 < 1184 ? (prep_total + 255) / 256 : 1184);
+  g3::gemm_prep_b_kernel<<<prep_grid, 256, 0, s>>>(w_s, n_out, K, n_out, NP, chunks, workspace);
+  g3::gemm_prep_b_kernel<<<prep_grid, 256, 0, s>>>(w_v, n_out, K, n_out, NP, chunks, workspace + img);
+  SEGNN_CHECK_LAUNCH();
+  const size_t smem = 1024 + (size_t)g3::kStages * (2 * g3::kBM * 128 + 2 * NP * 128) + 256 +
+                      (size_t)g3::kEpiWarps * 32 * g3::kStgLd * sizeof(float);
+  cudaError_t err = cudaFuncSetAttribute(g3::gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+  if (err != cudaSuccess) {
+    set_error("segnn_node_gemm_tf32x3: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(err));
+    return SEGNN_E_CUDA;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long tiles = ((long long)nodes + g3::kBM - 1) / g3::kBM + (3LL * nodes + g3::kBM - 1) / g3::kBM;
+  long long gx = sms / nblocks;
+  if (gx < 1) gx = 1;
+  if (gx > tiles) gx = tiles;
+  g3::NodeMap nm{x0, x1, n_in, (long long)nodes, bias, n_bias, split, y0, y1, (long long)img};
+  dim3 grid((unsigned)gx, (unsigned)nblocks);
+  g3::gemm_tf32x3_kernel<true><<<grid, g3::kThreads, smem, s>>>(nullptr, 0, 0, K, n_out, NP, chunks, workspace, nullptr, 0,
+                                                               nm);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

@@ -305,6 +305,16 @@ int64_t segnn_gemm_tf32x3_workspace(int K, int N);
 int segnn_gemm_tf32x3(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int K, int N, float* C,
                       int64_t ldc, float* workspace, segnn_stream_t stream);
 
+/* segnn_node_gemm (same arguments and results: the weight contraction of O3TensorProduct.forward_tp_rescale_bias on
+ * node rows, o3_building_blocks.py:150-162) as a 3xTF32 GEMM on tcgen05: both row classes (scalar planes x W_s, vector
+ * planes x W_v) in one launch, K optionally the concatenation x0 | x1, bias on the scalar planes, split outputs.  It is
+ * the fp32-mode / training node GEMM (the FFMA kernel stays as the checker).  workspace:
+ * segnn_node_gemm_tf32x3_workspace(K, n_out) bytes (K = n_in or 2 n_in), 16-byte aligned. */
+int64_t segnn_node_gemm_tf32x3_workspace(int K, int n_out);
+int segnn_node_gemm_tf32x3(const float* x0, const float* x1, int nodes, int n_in, const float* w_s, const float* w_v,
+                           const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, float* workspace,
+                           segnn_stream_t stream);
+
 /* The same accuracy for C[M][N] (+)= sum_k A[k][m] * B[k][n]: both operands row-major over K ("TN"), K split over the
  * CTAs of the grid with the partial sums in TMEM and one fixed-order reduction (bit-identical from run to run, no
  * atomics).  It is the weight-gradient contraction of message_layer_2 over the edge rows (autograd of

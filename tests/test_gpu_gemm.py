@@ -43,3 +43,34 @@ def test_gemm_tf32x3_is_much_more_accurate_than_plain_tf32():
     e1 = float((plain - ref).abs().max() / ref.abs().max())
     print(f"3xTF32 {e3:.2e} vs plain tf32 {e1:.2e}")
     assert e3 < 4e-6 and e1 > 50 * e3
+
+
+@pytest.mark.parametrize("nodes,n_in,n_out,two,split,n_bias", [(320, 96, 576, False, 288, 192), (320, 96, 288, True, 0, 0),
+                                                                (7, 32, 64, False, 0, 64), (1000, 64, 384, False, 192, 128),
+                                                                (33, 25, 50, True, 0, 25), (5000, 96, 192, False, 0, 96)])
+def test_node_gemm_tf32x3_matches_the_ffma_kernel(nodes, n_in, n_out, two, split, n_bias, monkeypatch):
+    """segnn_node_gemm_tf32x3 (tcgen05, both row classes in one launch, concatenated K, bias, split outputs) against
+    segnn_node_gemm (FFMA) and a float64 product."""
+    import segnn_b200 as S
+    g = torch.Generator().manual_seed(nodes + n_in)
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    x0, x1 = r(nodes, 4, n_in), (r(nodes, 4, n_in) if two else None)
+    K = n_in * (2 if two else 1)
+    w = dict(w_s=r(K, n_out) / K ** 0.5, w_v=r(K, n_out) / K ** 0.5)
+    bias = r(n_bias) if n_bias else None
+    outs = {}
+    monkeypatch.setattr(S.ops, "NODE_GEMM_TF32X3_MIN_NODES", 0)
+    for flag in (True, False):
+        monkeypatch.setattr(S.ops, "NODE_GEMM_TF32X3", flag)
+        y = S.ops.node_gemm(x0, x1, w, n_out, bias=bias, n_bias=n_bias, split=split)
+        outs[flag] = torch.cat(y, dim=2) if split else y
+    xin = (torch.cat([x0, x1], dim=2) if two else x0).double()
+    ref = torch.empty(nodes, 4, n_out, dtype=torch.float64, device="cuda")
+    ref[:, 0] = xin[:, 0] @ w["w_s"].double()
+    ref[:, 1:] = xin[:, 1:] @ w["w_v"].double()
+    if bias is not None:
+        ref[:, 0, :n_bias] += bias.double()
+    e_tc = float((outs[True].double() - ref).abs().max() / ref.abs().max())
+    e_ff = float((outs[False].double() - ref).abs().max() / ref.abs().max())
+    print(f"nodes={nodes} K={K} n_out={n_out}: tcgen05 3xTF32 {e_tc:.2e}, FFMA {e_ff:.2e}")
+    assert e_tc < 3e-6 and e_ff < 3e-6

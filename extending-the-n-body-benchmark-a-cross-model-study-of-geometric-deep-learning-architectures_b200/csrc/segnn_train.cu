@@ -77,6 +77,30 @@ __global__ void colsum_stage2(const T* __restrict__ partial, int nparts, int col
   out[c] = (float)acc;
 }
 
+// Many partial rows (102,400-node batches give 1,600): 32 columns x 32 part lanes per block; lane ry adds parts ry,
+// ry + 32, ... and the 32 lane sums are combined in lane order -- the same fixed association on every run.  One thread
+// per column walking all the parts took 165 us per column sum of a train-mode BatchNorm rollout step (24 per step).
+template <typename T>
+__global__ void __launch_bounds__(1024) colsum_stage2_wide(const T* __restrict__ partial, int nparts, int cols,
+                                                         float* __restrict__ out) {
+  __shared__ T red[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  T acc = 0;
+  if (c < cols) {
+#pragma unroll 4
+    for (int p = ry; p < nparts; p += 32) acc += partial[(int64_t)p * cols + c];
+  }
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    T s = red[0][cx];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) s += red[i][cx];
+    out[c] = (float)s;
+  }
+}
+
 // out[r][c] = A[c] * dy[r][c] + B[c] * x[r][c] + C[c]   (x / B / C may be NULL)
 __global__ void lincomb_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ A,
                                const float* __restrict__ B, const float* __restrict__ C, int64_t rows, int cols,
@@ -89,6 +113,32 @@ __global__ void lincomb_kernel(const float* __restrict__ dy, const float* __rest
     if (x != nullptr) v = fmaf(B[c], x[idx], v);
     if (C != nullptr) v += C[c];
     out[idx] = v;
+  }
+}
+
+// The same on float4 columns: a thread keeps its four column coefficients in registers and walks the rows (no
+// per-element modulo, 128-bit accesses): 2.4 -> ~5 TB/s on the [102400, 384] passes of a train-mode BatchNorm rollout.
+__global__ void __launch_bounds__(1024)
+    lincomb4_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ A,
+                    const float4* __restrict__ B, const float4* __restrict__ C, int64_t rows, int cols4,
+                    float4* __restrict__ out) {
+  for (int c4 = threadIdx.x; c4 < cols4; c4 += blockDim.x) {
+    const float4 a = A[c4];
+    const float4 b = x != nullptr ? B[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 c = C != nullptr ? C[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (int64_t)gridDim.x * blockDim.y) {
+      const float4 d = dy[r * cols4 + c4];
+      float4 v = make_float4(fmaf(a.x, d.x, c.x), fmaf(a.y, d.y, c.y), fmaf(a.z, d.z, c.z), fmaf(a.w, d.w, c.w));
+      if (x != nullptr) {
+        const float4 xv = x[r * cols4 + c4];
+        v.x = fmaf(b.x, xv.x, v.x);
+        v.y = fmaf(b.y, xv.y, v.y);
+        v.z = fmaf(b.z, xv.z, v.z);
+        v.w = fmaf(b.w, xv.w, v.w);
+      }
+      out[r * cols4 + c4] = v;
+    }
   }
 }
 
@@ -421,7 +471,10 @@ int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mod
   dim3 grid((cols + 31) / 32, (unsigned)parts);
   double* partial = reinterpret_cast<double*>(workspace);
   colsum_stage1<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, rows, cols, mode, partial);
-  colsum_stage2<double><<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, (int)parts, cols, out);
+  if (parts > 64)
+    colsum_stage2_wide<double><<<(cols + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partial, (int)parts, cols, out);
+  else
+    colsum_stage2<double><<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, (int)parts, cols, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }
@@ -431,6 +484,20 @@ int segnn_lincomb(const float* dy, const float* x, const float* A, const float* 
   SEGNN_CHECK_ARG(rows >= 0 && cols >= 1, "bad sizes");
   if (rows == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(dy && A && out && (x == nullptr || B != nullptr), "null pointer");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if ((cols & 3) == 0 && rows >= 4096 && al16(dy) && al16(x) && al16(A) && al16(B) && al16(C) && al16(out)) {
+    const int cols4 = cols / 4;
+    const int bx = cols4 >= 256 ? 256 : ((cols4 + 31) & ~31);
+    const int by = 1024 / bx;
+    int64_t blocks = (rows + by - 1) / by;
+    if (blocks > 8 * 148) blocks = 8 * 148;
+    lincomb4_kernel<<<(unsigned)blocks, dim3(bx, by), 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(A),
+        reinterpret_cast<const float4*>(B), reinterpret_cast<const float4*>(C), rows, cols4,
+        reinterpret_cast<float4*>(out));
+    SEGNN_CHECK_LAUNCH();
+    return SEGNN_OK;
+  }
   lincomb_kernel<<<grid_for_train(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, A, B, C, rows, cols, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;

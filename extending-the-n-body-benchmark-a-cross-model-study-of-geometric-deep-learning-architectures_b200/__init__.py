@@ -12,7 +12,8 @@ from .segnn import SEGNN, SEGNNLayer  # noqa: F401
 
 WeightBalancedIrreps = weight_balanced_irreps
 from .rollout import SelfFeedRollout, run_inference, shard_simulations  # noqa: F401,E402
-from .dataloader import GravityDatasetOtf, SegnnNBodyDataLoader  # noqa: F401,E402
+from .dataloader import (GravityDatasetOtf, NBodySystemDataset, SegnnNBodyDataLoader,  # noqa: F401,E402
+                         SegnnNbodyOfflineDataloader)
 from .trainer import TrainStep, allreduce_gradients, noam_rate, target_common_loss  # noqa: F401,E402
 from . import checkpoint, torch_ops  # noqa: F401,E402  (torch_ops registers torch.ops.segnn_b200.*)
 from .checkpoint import load_checkpoint, load_model_for_inference, save_model  # noqa: F401,E402

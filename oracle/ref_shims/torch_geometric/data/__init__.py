@@ -27,6 +27,15 @@ class Data:
             v = getattr(self, k, None)
             if torch.is_tensor(v):
                 return v.shape[0]
+        # PyG's inference order continues with node-level attributes (names containing "node": the offline n-body graphs
+        # carry node_feat / node_attr and no x / pos) and ends at the largest index of edge_index
+        for k in self.keys():
+            v = getattr(self, k)
+            if "node" in k and torch.is_tensor(v):
+                return v.shape[0]
+        ei = getattr(self, "edge_index", None)
+        if torch.is_tensor(ei) and ei.numel():
+            return int(ei.max()) + 1
         return None
 
     def has_isolated_nodes(self) -> bool:

@@ -71,7 +71,7 @@ def _edge_inputs(B, N, n, seed=0, bn=False):
     return pos, mass, p, q, w_edge1, w2, bn_mul, bn_add
 
 
-CASES = [(3, 7, 32), (1, 50, 64), (2, 12, 96), (5, 5, 64), (1, 300, 64), (2, 33, 48)]
+CASES = [(3, 7, 32), (1, 50, 64), (2, 12, 96), (5, 5, 64), (1, 300, 64), (2, 33, 48), (2, 9, 20), (3, 2, 4)]
 
 
 @pytest.mark.parametrize("B,N,n", CASES)

@@ -43,6 +43,7 @@ def _fold_bn(bn, n: int, degree: float):
 
 _MODES = {"fp32": ops.MODE_FP32, "bf16": ops.MODE_BF16_TC, "fp16": ops.MODE_FP16_TC, "fp16p": ops.MODE_FP16_PACKED}
 _TC_MODES = (ops.MODE_BF16_TC, ops.MODE_FP16_TC, ops.MODE_FP16_PACKED)
+SMALL_BATCH_NODES = 2048  # below this the update / pool GEMMs of the tensor-core modes run on the FFMA kernel
 _FP16_OPERAND_MODES = ("fp16", "fp16p")
 
 
@@ -137,11 +138,14 @@ class SEGNNLayer(nn.Module):
         agg = ops.edge_layer(mode, pos, mass, batch_size, num_nodes, n, p, q, m1["w_edge"], w["msg2"],
                              w["bn_msg"][0], w["bn_msg"][1])
         u1 = w["upd1"]
-        # tensor-core modes: the GEMM outputs that only feed an attribute-combine pass travel as fp16 rows
-        y1 = ops.node_gemm_out16(h, agg, u1, 3 * n) if tc else ops.node_gemm(h, agg, u1, 3 * n)
+        # tensor-core modes: the GEMM outputs that only feed an attribute-combine pass travel as fp16 rows; on a few
+        # hundred nodes (BASELINE configuration 1: 500) the persistent tcgen05 kernel is all fixed cost (8 us against
+        # ~4 us for the FFMA kernel), so small batches keep their update GEMMs on the fp32 kernel
+        tc_upd = tc and h.shape[0] >= SMALL_BATCH_NODES
+        y1 = ops.node_gemm_out16(h, agg, u1, 3 * n) if tc_upd else ops.node_gemm(h, agg, u1, 3 * n)
         g1 = ops.tp_combine(y1, node_attr, n, True, bias=u1["bias"])
         u2 = w["upd2"]
-        y2 = ops.node_gemm_out16(g1, None, u2, 2 * n) if tc else ops.node_gemm(g1, None, u2, 2 * n)
+        y2 = ops.node_gemm_out16(g1, None, u2, 2 * n) if tc_upd else ops.node_gemm(g1, None, u2, 2 * n)
         return ops.tp_combine(y2, node_attr, n, False, bias=u2["bias"], residual=h, bn_mul=w["bn_feat"][0],
                               bn_add=w["bn_feat"][1])
 
@@ -310,7 +314,8 @@ class SEGNN(nn.Module):
                 h = layer.run(lw, mode, h, pos, mass, node_attr, batch_size, num_nodes)
             per_layer.append(h)
         p1 = w["pool1"]
-        y = ops.node_gemm_out16(h, None, p1, 3 * n) if mode in _TC_MODES else ops.node_gemm(h, None, p1, 3 * n)
+        y = ops.node_gemm_out16(h, None, p1, 3 * n) if mode in _TC_MODES and h.shape[0] >= SMALL_BATCH_NODES \
+            else ops.node_gemm(h, None, p1, 3 * n)
         hp = ops.tp_combine(y, node_attr, n, True, bias=p1["bias"])
         pred = ops.head(hp, node_attr, w["head"], n)
         if return_layers:

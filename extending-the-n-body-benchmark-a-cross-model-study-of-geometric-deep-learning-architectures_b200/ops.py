@@ -379,9 +379,15 @@ GEMM_FORM_BUDGET_BYTES = 6 << 30
 GEMM_FORM_KEEP_BYTES_PER_LAYER = 4 << 30
 
 
+GEMM_FORM_MAX_GRAPH_BYTES = 48 << 30  # a chunk holds whole graphs: one graph must fit (N ~ 2800 at n = 64)
+
+
 def _use_gemm_form(batch_size: int, num_nodes: int, n: int, training: bool = False) -> bool:
     floor = GEMM_FORM_MIN_ROWS_TRAINING if training else GEMM_FORM_MIN_ROWS
-    return batch_size * num_nodes * num_nodes >= floor and n % 4 == 0 and n <= 96 and num_nodes >= 2
+    if not (batch_size * num_nodes * num_nodes >= floor and n % 4 == 0 and n <= 96 and num_nodes >= 2):
+        return False
+    # 16 n floats per edge row of ONE graph (backward): graphs too large for that stay on the fused kernels
+    return 4 * 16 * n * num_nodes * num_nodes <= GEMM_FORM_MAX_GRAPH_BYTES
 
 
 def _edge_gemm_workspace(batch_size: int, num_nodes: int, n: int, backward: bool, device):

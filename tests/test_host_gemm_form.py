@@ -43,6 +43,7 @@ def test_dispatch_thresholds(monkeypatch):
     assert ops._use_gemm_form(1, 1000, 64) and ops._use_gemm_form(1024, 100, 96)
     assert not ops._use_gemm_form(1, 1000, 25, training=True), "n = 25 (hidden 50) stays on the fused kernels"
     assert not ops._use_gemm_form(4, 1, 64, training=True)
+    assert not ops._use_gemm_form(1, 5000, 64, training=True), "one graph must fit a chunk"
     monkeypatch.setattr(ops, "GEMM_FORM_MIN_ROWS_TRAINING", 1 << 62)
     assert not ops._use_gemm_form(1, 1000, 64, training=True)
 

@@ -156,3 +156,46 @@ def test_gradients_are_bitwise_reproducible(H, B, N, edge_form, monkeypatch):
     for other in runs[1:]:
         for a, b in zip(runs[0], other):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("rows,k,n", [(5000, 146, 219), (100000, 128, 192), (777, 64, 64), (30000, 219, 73)])
+def test_gemm_pipelines_are_bitwise_reproducible(rows, k, n):
+    """Racecheck substitute for the mbarrier pipelines of the 3xTF32 GEMMs (register-prefetched loaders, bulk-copied
+    weight images, double-buffered TMEM accumulators, staged epilogue; split-K partial tiles of the TN kernel): a
+    missing barrier or a stage reused too early shows up as run-to-run differences.  30 repeats, identical bits, and
+    the first result is right."""
+    g = torch.Generator().manual_seed(rows + k + n)
+    a = torch.randn(rows, k, generator=g).cuda()
+    b = torch.randn(k, n, generator=g).cuda()
+    first = S.ops.gemm_tf32x3(a, b).clone()
+    ref = a.double() @ b.double()
+    assert float((first.double() - ref).abs().max() / ref.abs().max()) < 4e-6
+    for _ in range(30):
+        assert torch.equal(S.ops.gemm_tf32x3(a, b), first)
+    m4, n4 = (k + 3) // 4 * 4, (n + 3) // 4 * 4  # the TN kernel wants multiples of 4 floats
+    x = torch.randn(rows, m4, generator=g).cuda()
+    y = torch.randn(rows, n4, generator=g).cuda()
+    first_tn = S.ops.gemm_tn_tf32x3(x, y).clone()
+    ref_tn = x.double().t() @ y.double()
+    assert float((first_tn.double() - ref_tn).abs().max() / ref_tn.abs().max()) < 6e-6
+    for _ in range(30):
+        assert torch.equal(S.ops.gemm_tn_tf32x3(x, y), first_tn)
+
+
+def test_gemm_form_writes_inside_its_buffers(monkeypatch):
+    """Guard-band check of every buffer the GEMM-form edge layer allocates (workspace, partial rows, outputs), forward
+    and backward, with the GEMM form forced on a ragged shape (N = 37: partial 32 x 16 tiles, n = 48: one and a half
+    32-column atoms) and chunked (one graph per chunk)."""
+    monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS", 0)
+    monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS_TRAINING", 0)
+    B, N, n = 3, 37, 48
+    monkeypatch.setattr(S.ops, "GEMM_FORM_BUDGET_BYTES", int(S.ops.lib.segnn_edge_layer_gemm_workspace(1, N, n, 1, 0)))
+    om, m = _pair(96, 2, train=True)
+    assert m.n == n
+    pos, vel, mass = O.synthetic_system(B, N, seed=3)
+    y = torch.randn(B * N, 6).cuda()
+    with GuardedAllocations() as guard:
+        S.target_common_loss(m(_graph(pos, vel, mass, B, N)), y).backward()
+        n_bufs, bad = guard.check()
+    assert n_bufs > 20 and bad == 0, (n_bufs, bad)
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())

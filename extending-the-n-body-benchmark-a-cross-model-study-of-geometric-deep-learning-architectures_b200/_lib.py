@@ -33,6 +33,12 @@ PROTOTYPES = {
     "segnn_node_gemm_tc": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _int, _ptr]),
     "segnn_node_gemm_tc_out16": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr, _int, _ptr]),
     "segnn_tp_combine_y16": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_tp_combine_y16_x16": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "segnn_embed_fwd_x16": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_node_gemm_tc_x16": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _int, _int,
+                                      _ptr]),
+    "segnn_edge_layer_fwd_out16": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                          _ptr]),
     "segnn_node_gemm_tc_pair16": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _int, _ptr]),
     "segnn_pack_node_weight_tc": (_int, [_ptr, _int, _int, _int, _ptr, _ptr]),
     "segnn_tp_combine": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
@@ -71,6 +77,8 @@ PROTOTYPES = {
     "segnn_edge_layer_gemm_fwd": (_int, [_ptr, _ptr, _int, _int, _int] + [_ptr] * 13 + [_c.c_int64, _ptr]),
     "segnn_edge_layer_gemm_bwd": (_int, [_ptr, _ptr, _int, _int, _int] + [_ptr] * 25 + [_c.c_int64, _ptr, _c.c_int64,
                                                                                          _ptr]),
+    "segnn_edge_layer_gemm_bwd_phases": (_int, [_ptr, _ptr, _int, _int, _int] + [_ptr] * 25 +
+                                         [_c.c_int64, _ptr, _c.c_int64, _int, _ptr]),
     "segnn_embed_bwd": (_int, [_ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_head_bwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_generic_tp": (_int, [_ptr, _int, _ptr, _int, _c.c_int64, _ptr, _ptr, _int, _ptr, _ptr, _int, _ptr, _ptr]),

@@ -12,7 +12,7 @@ int edge_layer_tc(const float* pos, const float* mass, int B, int N, int n, cons
                   cudaStream_t stream);
 int edge_layer_h2(const float* pos, const float* mass, int B, int N, int n, const void* pp, const void* qq,
                   const float* w_edge1, const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add,
-                  float* agg, float* moments, cudaStream_t stream);
+                  float* agg, float* moments, void* agg16, cudaStream_t stream);
 int64_t pack_w2_tc(const float* ss, const float* vs, const float* sv, const float* vv, int n, int half, void* out,
                    cudaStream_t stream);
 }  // namespace segnn
@@ -45,11 +45,22 @@ int segnn_edge_layer_fwd(int mode, const float* pos, const float* mass, int B, i
     SEGNN_CHECK_ARG(w2_tc != nullptr, "tensor-core mode needs the packed weight image (segnn_pack_w2_tc, fp16)");
     SEGNN_CHECK_ARG(N >= 2, "tensor-core mode needs N >= 2");
     // the packed-half kernel also emits the train-mode BatchNorm moments (second template instance)
-    return edge_layer_h2(pos, mass, B, N, n, p, q, w_edge1, b2, w2_tc, bn_mul, bn_add, agg_out, moments,
+    return edge_layer_h2(pos, mass, B, N, n, p, q, w_edge1, b2, w2_tc, bn_mul, bn_add, agg_out, moments, nullptr,
                          (cudaStream_t)stream);
   }
   set_error("segnn_edge_layer_fwd: unknown mode %d", mode);
   return SEGNN_E_INVALID;
+}
+
+int segnn_edge_layer_fwd_out16(const float* pos, const float* mass, int B, int N, int n, const void* p, const void* q,
+                               const float* w_edge1, const float* b2, const void* w2_tc, const float* bn_mul,
+                               const float* bn_add, void* agg16_out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(B >= 0 && N >= 2 && n >= 1, "bad sizes");
+  if (B == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pos && mass && p && q && w_edge1 && b2 && w2_tc && agg16_out, "null pointer");
+  SEGNN_CHECK_ARG((bn_mul == nullptr) == (bn_add == nullptr), "bn_mul and bn_add must be given together");
+  return edge_layer_h2(pos, mass, B, N, n, p, q, w_edge1, b2, w2_tc, bn_mul, bn_add, nullptr, nullptr, agg16_out,
+                       (cudaStream_t)stream);
 }
 
 int64_t segnn_pack_w2_tc(const float* w2_ss, const float* w2_vs, const float* w2_sv, const float* w2_vv, int n,

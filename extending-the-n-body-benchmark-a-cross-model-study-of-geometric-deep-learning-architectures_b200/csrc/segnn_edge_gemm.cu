@@ -1145,14 +1145,17 @@ int segnn_edge_layer_gemm_fwd(const float* pos, const float* mass, int B, int N,
   return SEGNN_OK;
 }
 
-int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N, int n, const float* p, const float* q,
-                              const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
-                              const float* w2_vv, const float* b2, const float* w2t_ss, const float* w2t_vs,
-                              const float* w2t_sv, const float* w2t_vv, const float* bn_a, const float* bn_b,
-                              const float* bn_c, const float* dagg, float* dP, float* dQ, float* dw2_ss, float* dw2_vs,
-                              float* dw2_sv, float* dw2_vv, float* db2, float* dwe_partial, float* workspace,
-                              int64_t workspace_bytes, const float* fwd_workspace, int64_t fwd_workspace_bytes,
-                              segnn_stream_t stream) {
+int segnn_edge_layer_gemm_bwd_phases(const float* pos, const float* mass, int B, int N, int n, const float* p,
+                                     const float* q, const float* w_edge1, const float* w2_ss, const float* w2_vs,
+                                     const float* w2_sv, const float* w2_vv, const float* b2, const float* w2t_ss,
+                                     const float* w2t_vs, const float* w2t_sv, const float* w2t_vv, const float* bn_a,
+                                     const float* bn_b, const float* bn_c, const float* dagg, float* dP, float* dQ,
+                                     float* dw2_ss, float* dw2_vs, float* dw2_sv, float* dw2_vv, float* db2,
+                                     float* dwe_partial, float* workspace, int64_t workspace_bytes,
+                                     const float* fwd_workspace, int64_t fwd_workspace_bytes, int phases,
+                                     segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(phases >= 1 && phases <= 7, "phases: bit 0 rows + gate backward, bit 1 weight gradients, bit 2 data gradients");
+  const bool ph_rows = (phases & 1) != 0, ph_w = (phases & 2) != 0, ph_d = (phases & 4) != 0;
   int rc = eg::check_common(B, N, n);
   if (rc != SEGNN_OK) return rc;
   if (B == 0) return SEGNN_OK;
@@ -1165,6 +1168,7 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
   const int64_t colsum_floats = segnn_colsum_workspace((int64_t)B * N, 2 * n) / 4 + 64;
   const int64_t gpc = graphs_per_chunk(pl, colsum_floats, workspace_bytes, B);
   SEGNN_CHECK_ARG(gpc >= 1, "workspace too small for one graph (segnn_edge_layer_gemm_workspace)");
+  SEGNN_CHECK_ARG(phases == 7 || gpc >= B, "separate phases need a workspace that holds every graph in one chunk");
   cudaStream_t s = (cudaStream_t)stream;
   float* wcat = workspace + pl.o_wcat;
   float* wcat_t = workspace + pl.o_wcat_t;
@@ -1175,9 +1179,11 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
   float* ws_tn = workspace + pl.o_tn;
   float* ws_col = workspace + pl.o_colsum;
   float* chunk = ws_col + eg::align64(colsum_floats);
-  eg::build_wcat_kernel<<<(6 * n * n + 255) / 256, 256, 0, s>>>(n, w2_ss, w2_vs, w2_sv, w2t_ss, w2t_vs, w2t_sv, wcat,
-                                                              wcat_t);
-  SEGNN_CHECK_LAUNCH();
+  if (ph_rows) {
+    eg::build_wcat_kernel<<<(6 * n * n + 255) / 256, 256, 0, s>>>(n, w2_ss, w2_vs, w2_sv, w2t_ss, w2t_vs, w2t_sv, wcat,
+                                                                wcat_t);
+    SEGNN_CHECK_LAUNCH();
+  }
   const int NT = (n + 31) & ~31;
   const size_t smem_node = sizeof(float) * ((size_t)eg::kTileO * 8 + (size_t)eg::kSY * 18 * NT);
   const eg::Kernels kn = eg::kernels_for(n);
@@ -1222,7 +1228,7 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
       cxv = kxv + r0 * 3 * n;
       cyy = kyy + r0 * 3 * n;
       cdv = kdv + r0 * 3 * n;
-    } else {
+    } else if (ph_rows) {
       // recompute: message_layer_2 input rows and pre-activations
       kn.rows<<<(unsigned)blocks1, dim3(NT, 4), 0, s>>>(ra, xs, xv);
       SEGNN_CHECK_LAUNCH();
@@ -1231,21 +1237,26 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
       rc = segnn_gemm_tf32x3(xv, n, w2_vv, n, 3 * rows, n, n, dv, n, ws_g, stream);
       if (rc != SEGNN_OK) return rc;
     }
-    // gate backward: (Y, DV) -> (dY, dDV), in place when recomputed
-    kn.g2b<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, cyy, cdv, yy, dv, b2, bn_a, bn_b,
-                                                                                 bn_c, dagg, db2_rows);
-    SEGNN_CHECK_LAUNCH();
-    rc = segnn_colsum(db2_rows, nullptr, gc * N, 2 * n, 0, ws_col, db2c + (int64_t)chunk_idx * 2 * n, stream);
-    if (rc != SEGNN_OK) return rc;
-    // weight gradients: K = rows
-    rc = segnn_gemm_tn_tf32x3(cxs, 2 * n, yy, 3 * n, rows, 2 * n, 3 * n, dwcat, 3 * n, chunk_idx > 0, ws_tn, stream);
-    if (rc != SEGNN_OK) return rc;
-    // dW_vv = sum over the three components of XV_k^T dDV_k: the components sit side by side in a row
-    if ((n & 31) == 0)
-      rc = segnn_gemm_tn_grouped_tf32x3(cxv, 3 * n, dv, 3 * n, rows, n, n, 3, dwvv, n, chunk_idx > 0, ws_tn, stream);
-    else
-      rc = segnn_gemm_tn_tf32x3(cxv, n, dv, n, 3 * rows, n, n, dwvv, n, chunk_idx > 0, ws_tn, stream);
-    if (rc != SEGNN_OK) return rc;
+    if (ph_rows) {
+      // gate backward: (Y, DV) -> (dY, dDV), in place when recomputed
+      kn.g2b<<<(unsigned)(gc * N), dim3(NT, eg::kSY), smem_node, s>>>(ra, cyy, cdv, yy, dv, b2, bn_a, bn_b,
+                                                                                   bn_c, dagg, db2_rows);
+      SEGNN_CHECK_LAUNCH();
+      rc = segnn_colsum(db2_rows, nullptr, gc * N, 2 * n, 0, ws_col, db2c + (int64_t)chunk_idx * 2 * n, stream);
+      if (rc != SEGNN_OK) return rc;
+    }
+    if (ph_w) {
+      // weight gradients: K = rows
+      rc = segnn_gemm_tn_tf32x3(cxs, 2 * n, yy, 3 * n, rows, 2 * n, 3 * n, dwcat, 3 * n, chunk_idx > 0, ws_tn, stream);
+      if (rc != SEGNN_OK) return rc;
+      // dW_vv = sum over the three components of XV_k^T dDV_k: the components sit side by side in a row
+      if ((n & 31) == 0)
+        rc = segnn_gemm_tn_grouped_tf32x3(cxv, 3 * n, dv, 3 * n, rows, n, n, 3, dwvv, n, chunk_idx > 0, ws_tn, stream);
+      else
+        rc = segnn_gemm_tn_tf32x3(cxv, n, dv, n, 3 * rows, n, n, dwvv, n, chunk_idx > 0, ws_tn, stream);
+      if (rc != SEGNN_OK) return rc;
+    }
+    if (!ph_d) continue;
     // data gradients
     rc = segnn_gemm_tf32x3(yy, 3 * n, wcat_t, 2 * n, rows, 3 * n, 2 * n, dxs, 2 * n, ws_g, stream);
     if (rc != SEGNN_OK) return rc;
@@ -1270,10 +1281,25 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
                                                                               dwe_partial + node0 * 6 * n);
     SEGNN_CHECK_LAUNCH();
   }
+  if (!ph_w) return SEGNN_OK;
   eg::scatter_w2_grads_kernel<<<(6 * n * n + 255) / 256, 256, 0, s>>>(n, dwcat, dwvv, db2c, chunk_idx, dw2_ss, dw2_vs,
                                                                     dw2_sv, dw2_vv, db2);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
+}
+
+int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N, int n, const float* p, const float* q,
+                              const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
+                              const float* w2_vv, const float* b2, const float* w2t_ss, const float* w2t_vs,
+                              const float* w2t_sv, const float* w2t_vv, const float* bn_a, const float* bn_b,
+                              const float* bn_c, const float* dagg, float* dP, float* dQ, float* dw2_ss, float* dw2_vs,
+                              float* dw2_sv, float* dw2_vv, float* db2, float* dwe_partial, float* workspace,
+                              int64_t workspace_bytes, const float* fwd_workspace, int64_t fwd_workspace_bytes,
+                              segnn_stream_t stream) {
+  return segnn_edge_layer_gemm_bwd_phases(pos, mass, B, N, n, p, q, w_edge1, w2_ss, w2_vs, w2_sv, w2_vv, b2, w2t_ss,
+                                          w2t_vs, w2t_sv, w2t_vv, bn_a, bn_b, bn_c, dagg, dP, dQ, dw2_ss, dw2_vs,
+                                          dw2_sv, dw2_vv, db2, dwe_partial, workspace, workspace_bytes, fwd_workspace,
+                                          fwd_workspace_bytes, 7, stream);
 }
 
 }  // extern "C"

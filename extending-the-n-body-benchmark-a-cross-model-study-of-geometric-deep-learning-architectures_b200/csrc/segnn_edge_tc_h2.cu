@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
                          const float* __restrict__ w_edge1, const float* __restrict__ b2,
                          const uint32_t* __restrict__ w2_tc, const float* __restrict__ bn_mul,
                          const float* __restrict__ bn_add, float* __restrict__ agg, float* __restrict__ moments,
-                         int* __restrict__ err_flag) {
+                         __half* __restrict__ agg16) {
   constexpr int n = NMUL;
   constexpr int NW = n / 32;
   static_assert(NW >= 1 && NW <= 3, "warp % 4 == 3 hosts the MMA / scalar-producer warps");
@@ -133,10 +133,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (tmem != 0u) {
-    if (err_flag) atomicExch(err_flag, 2);
-    __trap();
-  }
+  if (tmem != 0u) __trap();
 
   const int recv_blocks = (N + kRecv - 1) / kRecv;
   const int send_blocks = (N + kSend - 1) / kSend;
@@ -432,11 +429,22 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         for (int rl = 0; rl < 2; ++rl) {
           const int r = 2 * rp + rl;
           if (i0 + r < N) {
-            float* o = agg + (g * N + i0 + r) * 4 * n;
-            o[w] = fmaf(acc[rl][0].x + acc[rl][0].y, sc_s, add_s);
-            o[n + w] = (acc[rl][1].x + acc[rl][1].y) * sc_v;
-            o[2 * n + w] = (acc[rl][2].x + acc[rl][2].y) * sc_v;
-            o[3 * n + w] = (acc[rl][3].x + acc[rl][3].y) * sc_v;
+            const float o0 = fmaf(acc[rl][0].x + acc[rl][0].y, sc_s, add_s);
+            const float o1 = (acc[rl][1].x + acc[rl][1].y) * sc_v, o2 = (acc[rl][2].x + acc[rl][2].y) * sc_v,
+                        o3 = (acc[rl][3].x + acc[rl][3].y) * sc_v;
+            if (agg16 != nullptr) {  // fp16 rows for segnn_node_gemm_tc_x16 (the rounding its fp32 loader applies)
+              __half* o = agg16 + (g * N + i0 + r) * 4 * n;
+              o[w] = __float2half_rn(o0);
+              o[n + w] = __float2half_rn(o1);
+              o[2 * n + w] = __float2half_rn(o2);
+              o[3 * n + w] = __float2half_rn(o3);
+            } else {
+              float* o = agg + (g * N + i0 + r) * 4 * n;
+              o[w] = o0;
+              o[n + w] = o1;
+              o[2 * n + w] = o2;
+              o[3 * n + w] = o3;
+            }
             if (MOMENTS) {  // of the raw messages (before any BatchNorm affine), like segnn_edge_fp32.cu
               float* mo = moments + (g * N + i0 + r) * 2 * n;
               mo[w] = (m2[rl][0].x + m2[rl][0].y) * (kCSilu * kCSilu);
@@ -621,7 +629,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 template <int NMUL, bool MOMENTS>
 static int launch_h2(const float* pos, const float* mass, int B, int N, const void* pp, const void* qq,
                      const float* w_edge1, const float* b2, const void* w2_tc, const float* bn_mul,
-                     const float* bn_add, float* agg, float* moments, cudaStream_t stream) {
+                     const float* bn_add, float* agg, float* moments, void* agg16, cudaStream_t stream) {
   constexpr int threads = kWarps * 32;
   const size_t smem = 1024 + (size_t)5 * NMUL * 128 + (size_t)(2 * (kSend / 2) + kRecv / 2) * 4 * 3 * NMUL * 4 +
                       (size_t)kGeoSlots * (4 * kCols * 4 + 5 * kCols * 2) + 24 * sizeof(uint64_t) + 16;
@@ -641,7 +649,7 @@ static int launch_h2(const float* pos, const float* mass, int B, int N, const vo
   }
   const unsigned grid = (unsigned)(items < sms ? items : sms);
   kern<<<grid, threads, smem, stream>>>(pos, mass, B, N, (const uint32_t*)pp, (const uint32_t*)qq, w_edge1, b2,
-                                        (const uint32_t*)w2_tc, bn_mul, bn_add, agg, moments, nullptr);
+                                        (const uint32_t*)w2_tc, bn_mul, bn_add, agg, moments, (__half*)agg16);
   err = cudaGetLastError();
   if (err != cudaSuccess) {
     set_error("edge_layer_h2: launch: %s", cudaGetErrorString(err));
@@ -654,7 +662,7 @@ static int launch_h2(const float* pos, const float* mass, int B, int N, const vo
 
 int edge_layer_h2(const float* pos, const float* mass, int B, int N, int n, const void* pp, const void* qq,
                   const float* w_edge1, const float* b2, const void* w2_tc, const float* bn_mul, const float* bn_add,
-                  float* agg, float* moments, cudaStream_t stream) {
+                  float* agg, float* moments, void* agg16, cudaStream_t stream) {
   if (N % 2 != 0) {
     set_error("edge_layer_h2: the packed-half mode needs an even graph size (sender pairs), got N=%d", N);
     return SEGNN_E_UNSUPPORTED;
@@ -662,9 +670,9 @@ int edge_layer_h2(const float* pos, const float* mass, int B, int N, int n, cons
 #define SEGNN_H2_CASE(NM)                                                                                            \
   if (n == NM)                                                                                                       \
     return moments ? tc::launch_h2<NM, true>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg,       \
-                                             moments, stream)                                                        \
+                                             moments, agg16, stream)                                                     \
                    : tc::launch_h2<NM, false>(pos, mass, B, N, pp, qq, w_edge1, b2, w2_tc, bn_mul, bn_add, agg,      \
-                                              nullptr, stream);
+                                              nullptr, agg16, stream);
   SEGNN_H2_CASE(32)
   SEGNN_H2_CASE(64)
   SEGNN_H2_CASE(96)

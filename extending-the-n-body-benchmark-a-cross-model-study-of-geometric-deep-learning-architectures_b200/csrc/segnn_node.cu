@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(const float* __restr
 
 __global__ void embed_kernel(const float* __restrict__ x_in, const float* __restrict__ node_attr,
                              const float* __restrict__ w, const float* __restrict__ bias, int nodes, int n,
-                             float* __restrict__ h) {
+                             float* __restrict__ h, __half* __restrict__ h16 = nullptr) {
   const int64_t total = (int64_t)nodes * n;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -139,11 +139,22 @@ __global__ void embed_kernel(const float* __restrict__ x_in, const float* __rest
     const float vdot = x[3] * ax + x[4] * ay + x[5] * az;
     const float s = x[6];
     float* out = h + node * 4 * n;
-    out[c] = a0 * w_s0 * s + w_p0 * pdot + w_v0 * vdot + bias[c];
+    const float o0 = a0 * w_s0 * s + w_p0 * pdot + w_v0 * vdot + bias[c];
     const float t = w_s1 * s;
-    out[1 * n + c] = ax * t + a0 * (w_p1 * x[0] + w_v1 * x[3]);
-    out[2 * n + c] = ay * t + a0 * (w_p1 * x[1] + w_v1 * x[4]);
-    out[3 * n + c] = az * t + a0 * (w_p1 * x[2] + w_v1 * x[5]);
+    const float o1 = ax * t + a0 * (w_p1 * x[0] + w_v1 * x[3]);
+    const float o2 = ay * t + a0 * (w_p1 * x[1] + w_v1 * x[4]);
+    const float o3 = az * t + a0 * (w_p1 * x[2] + w_v1 * x[5]);
+    out[c] = o0;
+    out[1 * n + c] = o1;
+    out[2 * n + c] = o2;
+    out[3 * n + c] = o3;
+    if (h16 != nullptr) {  // fp16 operand copy for the tensor-core node GEMMs (segnn_node_gemm_tc_x16)
+      __half* o16 = h16 + node * 4 * n;
+      o16[c] = __float2half_rn(o0);
+      o16[1 * n + c] = __float2half_rn(o1);
+      o16[2 * n + c] = __float2half_rn(o2);
+      o16[3 * n + c] = __float2half_rn(o3);
+    }
   }
 }
 
@@ -244,6 +255,126 @@ __global__ void __launch_bounds__(256) node_gemm_kernel(const float* __restrict_
   }
 }
 
+// Same GEMM for launches of a few hundred rows (training batches: 64 x 5 bodies = 1280 rows), where the 64 x 64 kernel is
+// a handful of CTAs whose every K step waits a full global-load latency (measured 1.1 - 2.1 us per step of 16, 12 - 39 us
+// per launch on the README training step): 32 x 64 tiles (twice the CTAs), K steps of 32 through a 4-stage cp.async
+// ring, so up to four steps of loads are in flight while one is multiplied.  Same accumulation order (k ascending, one
+// fmaf per product) as node_gemm_kernel: bit-identical results.  Needs n_in % 4 == 0 and n_out % 4 == 0 (16-byte copies).
+constexpr int kSmallGemmMaxNodes = 4096;  // above: node_gemm_kernel (fp32 mode switches to segnn_node_gemm_tf32x3 there)
+constexpr int kSmBM = 32, kSmBN = 64, kSmBK = 32, kSmStages = 4, kSmThreads = 128;
+constexpr int kSmAStride = kSmBK + 4, kSmBStride = kSmBN + 4;  // floats; rows stay 16-byte aligned
+constexpr int kSmStageFloats = kSmBM * kSmAStride + kSmBK * kSmBStride;
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int bytes = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kSmThreads) node_gemm_small_kernel(
+    const float* __restrict__ x0, const float* __restrict__ x1, int nodes, int n_in, const float* __restrict__ w_s,
+    const float* __restrict__ w_v, const float* __restrict__ bias, int n_bias, int n_out, float* __restrict__ y0,
+    float* __restrict__ y1, int split) {
+  extern __shared__ __align__(16) float sm_ring[];
+  const int cls = blockIdx.z;
+  const int64_t rows = cls == 0 ? (int64_t)nodes : (int64_t)nodes * 3;
+  const int64_t row0 = (int64_t)blockIdx.x * kSmBM;
+  if (row0 >= rows) return;
+  const int col0 = blockIdx.y * kSmBN;
+  const float* __restrict__ W = cls == 0 ? w_s : w_v;
+  const int K = x1 ? 2 * n_in : n_in;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // 16 column groups x 8 row groups, 4 x 4 outputs each
+  const int ksteps = (K + kSmBK - 1) / kSmBK;
+
+  // A copies: 32 rows x 8 chunks of 4 k = 256 chunks, two per thread; B copies: 32 k x 16 chunks of 4 columns, four
+  int64_t a_plane[2];
+  int a_row[2], a_k[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int c = tid + q * kSmThreads;
+    a_row[q] = c >> 3;
+    a_k[q] = (c & 7) * 4;
+    const int64_t r = row0 + a_row[q];
+    a_plane[q] = r < rows ? (cls == 0 ? r * 4 : (r / 3) * 4 + 1 + (r % 3)) : -1;
+  }
+  auto issue = [&](int step) {
+    if (step < ksteps) {
+      float* As = sm_ring + (step % kSmStages) * kSmStageFloats;
+      float* Bs = As + kSmBM * kSmAStride;
+      const int k0 = step * kSmBK;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int k = k0 + a_k[q];
+        const bool ok = a_plane[q] >= 0 && k < K;
+        const float* src = !ok ? x0 : (k < n_in ? x0 + a_plane[q] * n_in + k : x1 + a_plane[q] * n_in + (k - n_in));
+        cp_async16(As + a_row[q] * kSmAStride + a_k[q], src, ok);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = tid + q * kSmThreads;
+        const int bk = c >> 4, bc = (c & 15) * 4;
+        const bool ok = k0 + bk < K && col0 + bc < n_out;
+        cp_async16(Bs + bk * kSmBStride + bc, ok ? W + (int64_t)(k0 + bk) * n_out + col0 + bc : W, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, empty past the end: fixed wait depth
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int s = 0; s < kSmStages - 1; ++s) issue(s);
+  for (int step = 0; step < ksteps; ++step) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kSmStages - 2) : "memory");  // this step's group has landed
+    __syncthreads();  // ... for every thread; and every thread is done with the stage the next issue overwrites
+    issue(step + kSmStages - 1);
+    const float* As = sm_ring + (step % kSmStages) * kSmStageFloats;
+    const float* Bs = As + kSmBM * kSmAStride;
+#pragma unroll
+    for (int k4 = 0; k4 < kSmBK; k4 += 4) {
+      float4 a4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a4[i] = *reinterpret_cast<const float4*>(As + (ty * 4 + i) * kSmAStride + k4);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 b = *reinterpret_cast<const float4*>(Bs + (k4 + kk) * kSmBStride + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = kk == 0 ? a4[i].x : kk == 1 ? a4[i].y : kk == 2 ? a4[i].z : a4[i].w;
+          acc[i][0] = fmaf(a, b.x, acc[i][0]);
+          acc[i][1] = fmaf(a, b.y, acc[i][1]);
+          acc[i][2] = fmaf(a, b.z, acc[i][2]);
+          acc[i][3] = fmaf(a, b.w, acc[i][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = row0 + ty * 4 + i;
+    if (r >= rows) continue;
+    const int64_t plane = cls == 0 ? r * 4 : (r / 3) * 4 + 1 + (r % 3);
+    const int c = col0 + tx * 4;
+    if (c >= n_out) continue;  // n_out % 4 == 0: a group of four columns is inside or outside
+    float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (cls == 0 && bias != nullptr) {
+      if (c + 0 < n_bias) v.x += bias[c + 0];
+      if (c + 1 < n_bias) v.y += bias[c + 1];
+      if (c + 2 < n_bias) v.z += bias[c + 2];
+      if (c + 3 < n_bias) v.w += bias[c + 3];
+    }
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c + j < split) y0[plane * split + c + j] = vv[j];
+      else y1[plane * (n_out - split) + (c + j - split)] = vv[j];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Attribute combine + gate / residual / eval-BN epilogue of a node-level tensor product.
 // ------------------------------------------------------------------------------------------------
@@ -311,7 +442,7 @@ template <bool GATE>
 __global__ void tp_combine_y16_kernel(const __half* __restrict__ y, const float* __restrict__ node_attr, int nodes, int n,
                                       const float* __restrict__ bias, const float* __restrict__ residual,
                                       const float* __restrict__ bn_mul, const float* __restrict__ bn_add,
-                                      float* __restrict__ out) {
+                                      float* __restrict__ out, __half* __restrict__ out16) {
   const int n0 = GATE ? 2 * n : n;
   const int n_out = n0 + n;
   const int nh = n / 2;
@@ -371,10 +502,18 @@ __global__ void tp_combine_y16_kernel(const __half* __restrict__ y, const float*
       vx.x *= mv.x; vy.x *= mv.x; vz.x *= mv.x;
       vx.y *= mv.y; vy.y *= mv.y; vz.y *= mv.y;
     }
-    *reinterpret_cast<float2*>(out + o + w) = zs;
-    *reinterpret_cast<float2*>(out + o + n + w) = vx;
-    *reinterpret_cast<float2*>(out + o + 2 * n + w) = vy;
-    *reinterpret_cast<float2*>(out + o + 3 * n + w) = vz;
+    if (out != nullptr) {
+      *reinterpret_cast<float2*>(out + o + w) = zs;
+      *reinterpret_cast<float2*>(out + o + n + w) = vx;
+      *reinterpret_cast<float2*>(out + o + 2 * n + w) = vy;
+      *reinterpret_cast<float2*>(out + o + 3 * n + w) = vz;
+    }
+    if (out16 != nullptr) {  // the fp16 operand copy the next tensor-core node GEMM reads (same rounding as its loader)
+      *reinterpret_cast<__half2*>(out16 + o + w) = __float22half2_rn(zs);
+      *reinterpret_cast<__half2*>(out16 + o + n + w) = __float22half2_rn(vx);
+      *reinterpret_cast<__half2*>(out16 + o + 2 * n + w) = __float22half2_rn(vy);
+      *reinterpret_cast<__half2*>(out16 + o + 3 * n + w) = __float22half2_rn(vz);
+    }
   }
 }
 
@@ -510,6 +649,17 @@ int segnn_embed_fwd(const float* x_in, const float* node_attr, const float* w_em
   return SEGNN_OK;
 }
 
+int segnn_embed_fwd_x16(const float* x_in, const float* node_attr, const float* w_embed, const float* bias, int nodes,
+                        int n, float* h_out, void* h16_out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && n >= 1, "need nodes >= 0, n >= 1");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x_in && node_attr && w_embed && bias && h_out && h16_out, "null pointer");
+  embed_kernel<<<grid_for((int64_t)nodes * n, 256), 256, 0, (cudaStream_t)stream>>>(
+      x_in, node_attr, w_embed, bias, nodes, n, h_out, reinterpret_cast<__half*>(h16_out));
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
 int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const float* w_s, const float* w_v,
                     const float* bias, int n_bias, int n_out, float* y0, float* y1, int split,
                     segnn_stream_t stream) {
@@ -519,6 +669,22 @@ int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const
   SEGNN_CHECK_ARG(bias == nullptr || (n_bias >= 0 && n_bias <= n_out), "n_bias out of range");
   if (y1 == nullptr) split = n_out;
   SEGNN_CHECK_ARG(split > 0 && split <= n_out, "split out of range");
+  // a few hundred rows (training batches): the latency-tolerant small-tile kernel (same results bit for bit)
+  if (nodes <= kSmallGemmMaxNodes && n_in % 4 == 0 && n_out % 4 == 0 && ((uintptr_t)x0 & 15) == 0 &&
+      ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)w_s & 15) == 0 && ((uintptr_t)w_v & 15) == 0) {
+    static const cudaError_t attr = cudaFuncSetAttribute(node_gemm_small_kernel,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         kSmStages * kSmStageFloats * (int)sizeof(float));
+    if (attr != cudaSuccess) {
+      set_error("segnn_node_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr));
+      return SEGNN_E_CUDA;
+    }
+    dim3 grid_s((unsigned)(((int64_t)nodes * 3 + kSmBM - 1) / kSmBM), (n_out + kSmBN - 1) / kSmBN, 2);
+    node_gemm_small_kernel<<<grid_s, kSmThreads, kSmStages * kSmStageFloats * sizeof(float), (cudaStream_t)stream>>>(
+        x0, x1, nodes, n_in, w_s, w_v, bias, n_bias, n_out, y0, y1, split);
+    SEGNN_CHECK_LAUNCH();
+    return SEGNN_OK;
+  }
   int64_t row_tiles = ((int64_t)nodes * 3 + kGemmBM - 1) / kGemmBM;
   SEGNN_CHECK_ARG(row_tiles < (1LL << 31), "too many rows");
   dim3 grid((unsigned)row_tiles, (n_out + kGemmBN - 1) / kGemmBN, 2);
@@ -546,25 +712,26 @@ int segnn_tp_combine(const float* y, const float* node_attr, int nodes, int n, i
   return SEGNN_OK;
 }
 
-int segnn_tp_combine_y16(const void* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
-                         const float* residual, const float* bn_mul, const float* bn_add, float* out,
-                         segnn_stream_t stream) {
+static int tp_combine_y16_launch(const void* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                                 const float* residual, const float* bn_mul, const float* bn_add, float* out,
+                                 __half* out16, segnn_stream_t stream) {
   SEGNN_CHECK_ARG(nodes >= 0 && n >= 1, "bad sizes");
   if (nodes == 0) return SEGNN_OK;
-  SEGNN_CHECK_ARG(y && node_attr && out, "null pointer");
+  SEGNN_CHECK_ARG(y && node_attr && (out || out16), "null pointer");
   SEGNN_CHECK_ARG((bn_mul == nullptr) == (bn_add == nullptr), "bn_mul and bn_add must be given together");
   const __half* yh = reinterpret_cast<const __half*>(y);
   if (n % 2 == 0) {  // every row offset is then a multiple of 2 elements: half2 / float2 accesses are aligned
     int grid = grid_for((int64_t)nodes * (n / 2), 256);
     if (gate)
       tp_combine_y16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(yh, node_attr, nodes, n, bias, residual,
-                                                                         bn_mul, bn_add, out);
+                                                                         bn_mul, bn_add, out, out16);
     else
       tp_combine_y16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(yh, node_attr, nodes, n, bias, residual,
-                                                                          bn_mul, bn_add, out);
+                                                                          bn_mul, bn_add, out, out16);
     SEGNN_CHECK_LAUNCH();
     return SEGNN_OK;
   }
+  SEGNN_CHECK_ARG(out16 == nullptr && out != nullptr, "the fp16 feature copy needs an even hidden multiplicity");
   int grid = grid_for((int64_t)nodes * n, 256);
   if (gate)
     tp_combine_kernel<true, __half><<<grid, 256, 0, (cudaStream_t)stream>>>(yh, node_attr, nodes, n, bias, residual,
@@ -574,6 +741,21 @@ int segnn_tp_combine_y16(const void* y, const float* node_attr, int nodes, int n
                                                                             bn_mul, bn_add, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
+}
+
+int segnn_tp_combine_y16(const void* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                         const float* residual, const float* bn_mul, const float* bn_add, float* out,
+                         segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(out != nullptr, "null pointer");
+  return tp_combine_y16_launch(y, node_attr, nodes, n, gate, bias, residual, bn_mul, bn_add, out, nullptr, stream);
+}
+
+int segnn_tp_combine_y16_x16(const void* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                             const float* residual, const float* bn_mul, const float* bn_add, float* out,
+                             void* out16, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(out16 != nullptr, "null pointer");
+  return tp_combine_y16_launch(y, node_attr, nodes, n, gate, bias, residual, bn_mul, bn_add, out,
+                               reinterpret_cast<__half*>(out16), stream);
 }
 
 int segnn_head_fwd(const float* h, const float* node_attr, const float* w_head, int nodes, int n, float* pred,

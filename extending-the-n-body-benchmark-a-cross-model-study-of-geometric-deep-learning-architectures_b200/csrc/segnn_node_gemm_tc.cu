@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     node_gemm_tc_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int nodes, int n_in,
                         const __nv_bfloat16* __restrict__ wt_s, const __nv_bfloat16* __restrict__ wt_v,
                         const float* __restrict__ bias, int n_bias, int n_out, int nc, float* __restrict__ y0,
-                        float* __restrict__ y1, int split, int ctas_cls0, int fp16_operands, int pair16) {
+                        float* __restrict__ y1, int split, int ctas_cls0, int fp16_operands, int pair16, int in16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int K = x1 ? 2 * n_in : n_in;
@@ -169,7 +169,83 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < kLoadWarps) {
+  if (warp < kLoadWarps && in16) {
+    // ===================== loaders, 16-bit rows: x0 / x1 already hold the operand format =====================
+    // The producing kernels keep a 16-bit copy of the features next to the fp32 one (rounded exactly like the
+    // conversion below would round them), so the tile is a list of 16-byte pieces (8 consecutive k of one row) that go
+    // to their swizzled position unchanged.  A piece is 4 registers instead of 8: two batches of up to 6 pieces per
+    // thread stay in flight, the loads of batch g + 1 are issued before batch g is stored, across tile boundaries
+    // (the fp32 loader has one batch in flight and idles for a full memory latency per tile).
+    const uint16_t* __restrict__ xh0 = reinterpret_cast<const uint16_t*>(x0);
+    const uint16_t* __restrict__ xh1 = reinterpret_cast<const uint16_t*>(x1);
+    const int k8 = K / 8;                       // pieces per row
+    const int per_thread = (128 * k8) / 256;    // K % 16 == 0 -> exact
+    const int nbpt = per_thread > 6 ? 2 : 1;    // batches per tile
+    const int bs = (per_thread + nbpt - 1) / nbpt;
+    const int row_step = 256 / k8, kp_step = 256 % k8;
+    const uint32_t my_tiles = cta < tiles ? (uint32_t)((tiles - cta + cta_stride - 1) / cta_stride) : 0u;
+    const uint32_t G = my_tiles * nbpt;
+    auto issue = [&](uint32_t g, uint4 (&v)[6]) {
+      const uint32_t t = nbpt == 2 ? g >> 1 : g;
+      const int half = nbpt == 2 ? (int)(g & 1) : 0;
+      const long long tile = cta + (long long)t * cta_stride;
+      const int p0 = tid + 256 * half * bs;
+      int row = p0 / k8, kp = p0 - row * k8;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        v[j] = make_uint4(0u, 0u, 0u, 0u);
+        const long long gr = tile * 128 + row;
+        if (j < bs && half * bs + j < per_thread && gr < rows) {
+          const long long pl = four ? plane_of4(cls, gr) : plane_of(cls, gr);
+          const int k = kp * 8;
+          const uint16_t* src = k < n_in ? xh0 + pl * n_in + k : xh1 + pl * n_in + (k - n_in);
+          asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w)
+                       : "l"(src));
+        }
+        row += row_step;
+        kp += kp_step;
+        if (kp >= k8) {
+          kp -= k8;
+          ++row;
+        }
+      }
+    };
+    auto commit = [&](uint32_t g, const uint4 (&v)[6]) {
+      const uint32_t t = nbpt == 2 ? g >> 1 : g;
+      const int half = nbpt == 2 ? (int)(g & 1) : 0;
+      const int ab = t & 1;
+      if (half == 0) mbar_wait(&aempty[ab], ((t >> 1) & 1) ^ 1);
+      uint8_t* dst = sA + ab * a_bytes;
+      const int p0 = tid + 256 * half * bs;
+      int row = p0 / k8, kp = p0 - row * k8;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        if (j < bs && half * bs + j < per_thread) {
+          const int k = kp * 8;
+          *reinterpret_cast<uint4*>(dst + (k >> 6) * (128 * 128) + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4)) = v[j];
+        }
+        row += row_step;
+        kp += kp_step;
+        if (kp >= k8) {
+          kp -= k8;
+          ++row;
+        }
+      }
+      if (half == nbpt - 1) {
+        proxy_fence();
+        mbar_arrive(&afull[ab]);
+      }
+    };
+    uint4 va[6], vb[6];
+    if (G > 0) issue(0, va);
+    for (uint32_t g = 0; g < G; g += 2) {
+      if (g + 1 < G) issue(g + 1, vb);
+      commit(g, va);
+      if (g + 2 < G) issue(g + 2, va);
+      if (g + 1 < G) commit(g + 1, vb);
+    }
+  } else if (warp < kLoadWarps) {
     // ===================== loaders: fp32 rows -> bf16 swizzled A tile =====================
     // The tile is a list of 32-byte pieces (8 consecutive k of one row); piece p = tid + 256 i, so consecutive lanes
     // read consecutive sectors of a row and the memory system sees full 128-byte requests (one row per lane made every
@@ -415,7 +491,7 @@ int segnn_pack_node_weight_tc(const float* w, int K, int n_out, int operand, voi
 
 static int node_gemm_tc_launch(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
                                const float* bias, int n_bias, int n_out, float* y0, float* y1, int split, int operand,
-                               int pair16, segnn_stream_t stream) {
+                               int pair16, segnn_stream_t stream, int in16 = 0) {
   SEGNN_CHECK_ARG(nodes >= 0 && n_in >= 1 && n_out >= 1, "bad sizes");
   SEGNN_CHECK_ARG(operand == SEGNN_OPERAND_BF16 || operand == SEGNN_OPERAND_FP16, "unknown operand format");
   if (nodes == 0) return SEGNN_OK;
@@ -467,7 +543,7 @@ static int node_gemm_tc_launch(const float* x0, const float* x1, int nodes, int 
   }
   ngemm::node_gemm_tc_kernel<<<grid, ngemm::kThreads, smem, (cudaStream_t)stream>>>(
       x0, x1, nodes, n_in, (const __nv_bfloat16*)wt_s, (const __nv_bfloat16*)wt_v, bias, n_bias, n_out, nc, y0, y1,
-      split, (int)c0, operand == SEGNN_OPERAND_FP16 ? 1 : 0, pair16);
+      split, (int)c0, operand == SEGNN_OPERAND_FP16 ? 1 : 0, pair16, in16);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }
@@ -491,6 +567,14 @@ int segnn_node_gemm_tc_pair16(const float* x0, const float* x1, int nodes, int n
                               segnn_stream_t stream) {
   return node_gemm_tc_launch(x0, x1, nodes, n_in, wt_s, wt_v, bias, n_bias, n_out, (float*)y0, (float*)y1, split, operand,
                              1, stream);
+}
+
+int segnn_node_gemm_tc_x16(const void* x0, const void* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                           const float* bias, int n_bias, int n_out, void* y0, void* y1, int split, int operand,
+                           int out_mode, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(out_mode == 1 || out_mode == 2, "out_mode: 1 = fp16 node pairs (pair16), 2 = fp16 rows (out16)");
+  return node_gemm_tc_launch((const float*)x0, (const float*)x1, nodes, n_in, wt_s, wt_v, bias, n_bias, n_out,
+                             (float*)y0, (float*)y1, split, operand, out_mode, stream, 1);
 }
 
 }  // extern "C"

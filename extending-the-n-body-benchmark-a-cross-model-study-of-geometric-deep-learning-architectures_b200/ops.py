@@ -110,9 +110,23 @@ def prep(pos: torch.Tensor, vel: torch.Tensor, batch_size: int, num_nodes: int):
     return x_in, attr
 
 
-def embed(x_in, node_attr, w_embed, bias, n: int):
+# fp16 operand copies of the node features next to the fp32 ones (compute_mode 'fp16p', tensor-core node GEMMs): the
+# producers store the rounding the GEMM loader would apply, the GEMMs read half the bytes (segnn_node_gemm_tc_x16).
+# False (or SEGNN_X16_FEATURES=0): the GEMMs convert fp32 features on load; results are bit-identical either way.
+X16_FEATURES = os.environ.get("SEGNN_X16_FEATURES", "1") != "0"
+
+
+def embed(x_in, node_attr, w_embed, bias, n: int, want16: bool = False):
+    """want16: returns (h, h16) with h16 the fp16 copy of h (segnn_embed_fwd_x16)."""
     nodes = x_in.shape[0]
     h = torch.empty((nodes, 4, n), dtype=torch.float32, device=x_in.device)
+    if want16:
+        h16 = torch.empty((nodes, 4, n), dtype=torch.float16, device=x_in.device)
+        with torch.cuda.device(x_in.device):
+            check(lib.segnn_embed_fwd_x16(_p(x_in), _p(node_attr), _p(w_embed), _p(bias), nodes, n, _p(h), _p(h16),
+                                          _stream()), "segnn_embed_fwd_x16")
+        _bump()
+        return h, h16
     with torch.cuda.device(x_in.device):
         check(lib.segnn_embed_fwd(_p(x_in), _p(node_attr), _p(w_embed), _p(bias), nodes, n, _p(h), _stream()),
               "segnn_embed_fwd")
@@ -164,6 +178,14 @@ def node_gemm_out16(x0, x1, w, n_out: int):
     feed tp_combine, which reads them through segnn_tp_combine_y16."""
     nodes, _, n_in = x0.shape
     y = torch.empty((nodes, 4, n_out), dtype=torch.float16, device=x0.device)
+    if x0.dtype == torch.float16:  # fp16 feature copies: no conversion on load (segnn_node_gemm_tc_x16)
+        if int(w.get("operand", OPERAND_BF16)) != OPERAND_FP16 or (x1 is not None and x1.dtype != torch.float16):
+            raise ValueError("fp16 feature rows need fp16 operand weights and an fp16 second input")
+        with torch.cuda.device(x0.device):
+            check(lib.segnn_node_gemm_tc_x16(_p(x0), _p(x1), nodes, n_in, _p(w["wt_s"]), _p(w["wt_v"]), None, 0, n_out,
+                                             _p(y), None, n_out, OPERAND_FP16, 2, _stream()), "segnn_node_gemm_tc_x16")
+        _bump()
+        return y
     with torch.cuda.device(x0.device):
         check(lib.segnn_node_gemm_tc_out16(_p(x0), _p(x1), nodes, n_in, _p(w["wt_s"]), _p(w["wt_v"]), n_out, _p(y),
                                            int(w.get("operand", OPERAND_BF16)), _stream()), "segnn_node_gemm_tc_out16")
@@ -180,6 +202,15 @@ def node_gemm_pair16(x0, w, n_out: int, bias, n_bias: int, split: int):
         raise ValueError("pair-interleaved projections need an even node count")
     y0 = torch.empty((nodes // 2, 4, split, 2), dtype=torch.float16, device=dev)
     y1 = torch.empty((nodes // 2, 4, n_out - split, 2), dtype=torch.float16, device=dev)
+    if x0.dtype == torch.float16:  # fp16 feature copy (segnn_node_gemm_tc_x16)
+        if int(w.get("operand", OPERAND_FP16)) != OPERAND_FP16:
+            raise ValueError("fp16 feature rows need fp16 operand weights")
+        with torch.cuda.device(dev):
+            check(lib.segnn_node_gemm_tc_x16(_p(x0), None, nodes, n_in, _p(w["wt_s"]), _p(w["wt_v"]), _p(bias), n_bias,
+                                             n_out, _p(y0), _p(y1), split, OPERAND_FP16, 1, _stream()),
+                  "segnn_node_gemm_tc_x16")
+        _bump()
+        return y0, y1
     with torch.cuda.device(dev):
         check(lib.segnn_node_gemm_tc_pair16(_p(x0), None, nodes, n_in, _p(w["wt_s"]), _p(w["wt_v"]), _p(bias), n_bias,
                                             n_out, _p(y0), _p(y1), split, int(w.get("operand", OPERAND_FP16)),
@@ -200,8 +231,21 @@ def pack_node_weight_tc(w: torch.Tensor, operand: int = OPERAND_BF16) -> torch.T
 
 
 def tp_combine(y, node_attr, n: int, gate: bool, bias=None, residual=None, bn_mul=None, bn_add=None,
-               out: Optional[torch.Tensor] = None):
+               out: Optional[torch.Tensor] = None, out16: Optional[str] = None):
+    """out16 (fp16 GEMM rows only): 'both' returns (out fp32, fp16 copy), 'only' returns the fp16 copy alone
+    (segnn_tp_combine_y16_x16)."""
     nodes = y.shape[0]
+    if out16 is not None:
+        if y.dtype != torch.float16 or out16 not in ("both", "only"):
+            raise ValueError("out16 ('both' / 'only') needs fp16 GEMM rows")
+        o = None if out16 == "only" else torch.empty((nodes, 4, n), dtype=torch.float32, device=y.device)
+        o16 = torch.empty((nodes, 4, n), dtype=torch.float16, device=y.device)
+        with torch.cuda.device(y.device):
+            check(lib.segnn_tp_combine_y16_x16(_p(y), _p(node_attr), nodes, n, int(gate), _p(bias), _p(residual),
+                                               _p(bn_mul), _p(bn_add), _p(o), _p(o16), _stream()),
+                  "segnn_tp_combine_y16_x16")
+        _bump()
+        return o16 if o is None else (o, o16)
     o = out if out is not None else torch.empty((nodes, 4, n), dtype=torch.float32, device=y.device)
     fn = lib.segnn_tp_combine_y16 if y.dtype == torch.float16 else lib.segnn_tp_combine
     with torch.cuda.device(y.device):
@@ -212,9 +256,20 @@ def tp_combine(y, node_attr, n: int, gate: bool, bias=None, residual=None, bn_mu
 
 
 def edge_layer(mode: int, pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_mul=None,
-               bn_add=None, want_moments: bool = False):
-    """w2: dict with fp32 blocks 'ss','vs','sv','vv','b' and (tensor-core mode) 'tc' image."""
+               bn_add=None, want_moments: bool = False, out16: bool = False):
+    """w2: dict with fp32 blocks 'ss','vs','sv','vv','b' and (tensor-core mode) 'tc' image.  out16 (MODE_FP16_PACKED):
+    the aggregate comes back as fp16 rows (segnn_edge_layer_fwd_out16)."""
     nodes = batch_size * num_nodes
+    if out16:
+        if mode != MODE_FP16_PACKED or want_moments:
+            raise ValueError("fp16 aggregate rows are an output of the packed-half mode without moments")
+        agg16 = torch.empty((nodes, 4, n), dtype=torch.float16, device=pos.device)
+        with torch.cuda.device(pos.device):
+            check(lib.segnn_edge_layer_fwd_out16(_p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1),
+                                                 _p(w2["b"]), _p(w2.get("tc")), _p(bn_mul), _p(bn_add), _p(agg16),
+                                                 _stream()), "segnn_edge_layer_fwd_out16")
+        _bump()
+        return agg16
     if mode == MODE_FP32 and _use_gemm_form(batch_size, num_nodes, n):
         return edge_layer_gemm_fwd(pos, mass, batch_size, num_nodes, n, p, q, w_edge1, w2, bn_mul, bn_add, want_moments)
     agg = torch.empty((nodes, 4, n), dtype=torch.float32, device=pos.device)
@@ -432,9 +487,12 @@ def edge_layer_gemm_fwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q
 
 
 def edge_layer_gemm_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg,
-                        dP=None, dQ=None, gz=None, rows=None):
+                        dP=None, dQ=None, gz=None, rows=None, side=None):
     """segnn_edge_layer_gemm_bwd: same results as edge_layer_bwd (dP, dQ, message_layer_2 gradient blocks, dw_edge1).
-    rows: what edge_layer_gemm_fwd(keep_rows=True) returned for the same layer (skips the recompute)."""
+    rows: what edge_layer_gemm_fwd(keep_rows=True) returned for the same layer (skips the recompute).
+    side (an object with .run(fn), training._SideWork): when every graph fits one chunk the message_layer_2 weight
+    gradients (split-K TN GEMMs, off the critical path) are launched through it beside the data-gradient chain; the
+    returned gradient blocks are complete once the caller has joined it."""
     nodes = batch_size * num_nodes
     dev = pos.device
     f = dict(dtype=torch.float32, device=dev)
@@ -447,15 +505,21 @@ def edge_layer_gemm_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q
     w2t = {k: (w2[k + "_t"] if k + "_t" in w2 else w2[k].t().contiguous()) for k in ("ss", "vs", "sv", "vv")}
     dagg = dagg.contiguous()
     ws, nbytes = _edge_gemm_workspace(batch_size, num_nodes, n, True, dev)
-    with torch.cuda.device(dev):
-        check(lib.segnn_edge_layer_gemm_bwd(_p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1),
-                                            _p(w2["ss"]), _p(w2["vs"]), _p(w2["sv"]), _p(w2["vv"]), _p(w2["b"]),
-                                            _p(w2t["ss"]), _p(w2t["vs"]), _p(w2t["sv"]), _p(w2t["vv"]), _p(bn_a),
-                                            _p(bn_b), _p(bn_c), _p(dagg), _p(dP), _p(dQ), _p(g["ss"]), _p(g["vs"]),
-                                            _p(g["sv"]), _p(g["vv"]), _p(g["b"]), _p(dwe_partial), _p(ws), nbytes,
-                                            _p(rows[0]) if rows is not None else None,
-                                            rows[1] if rows is not None else 0, _stream()),
-              "segnn_edge_layer_gemm_bwd")
+    def launch(phases: int):
+        with torch.cuda.device(dev):
+            check(lib.segnn_edge_layer_gemm_bwd_phases(
+                _p(pos), _p(mass), batch_size, num_nodes, n, _p(p), _p(q), _p(w_edge1), _p(w2["ss"]), _p(w2["vs"]),
+                _p(w2["sv"]), _p(w2["vv"]), _p(w2["b"]), _p(w2t["ss"]), _p(w2t["vs"]), _p(w2t["sv"]), _p(w2t["vv"]),
+                _p(bn_a), _p(bn_b), _p(bn_c), _p(dagg), _p(dP), _p(dQ), _p(g["ss"]), _p(g["vs"]), _p(g["sv"]),
+                _p(g["vv"]), _p(g["b"]), _p(dwe_partial), _p(ws), nbytes, _p(rows[0]) if rows is not None else None,
+                rows[1] if rows is not None else 0, phases, _stream()), "segnn_edge_layer_gemm_bwd_phases")
+    one_chunk = nbytes >= int(lib.segnn_edge_layer_gemm_workspace(batch_size, num_nodes, n, 1, 0))
+    if side is not None and one_chunk and SIDE_STREAM_W2_GRADS:
+        launch(1)
+        side.run(lambda: launch(2))  # the closure keeps ws / rows / g alive until the caller joins the side stream
+        launch(4)
+    else:
+        launch(7)
     _bump(24 if rows is None else 18)
     return dP, dQ, g, colsum(dwe_partial)
 
@@ -526,6 +590,8 @@ def node_gemm_wgrad(x0, x1, dy0, dy1, split: int):
 
 
 _SIDE_STREAMS = {}
+# GEMM-form edge backward: message_layer_2 weight gradients on the side stream (SEGNN_SIDE_W2_GRADS=0: in line)
+SIDE_STREAM_W2_GRADS = os.environ.get("SEGNN_SIDE_W2_GRADS", "1") != "0"
 
 
 def side_stream(device, k: int = 0) -> "torch.cuda.Stream":
@@ -542,7 +608,8 @@ def side_stream(device, k: int = 0) -> "torch.cuda.Stream":
 _SPLIT_WGRAD_MAX_EDGES = 1 << 16  # below this the edge backward runs dP and the weight gradients as separate launches
 
 
-def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg):
+def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg,
+                   side=None):
     """Backward of the fused edge layer with recompute. Returns dP, dQ [nodes,4,3n], the message_layer_2 gradient
     blocks {ss, vs, sv, vv, b} and dw_edge1 [6n]."""
     nodes = batch_size * num_nodes
@@ -552,7 +619,7 @@ def edge_layer_bwd(pos, mass, batch_size: int, num_nodes: int, n: int, p, q, w_e
     gz = torch.empty(6 * n * n + 2 * n, **f)  # written by the fixed-order slab reduction (no atomics)
     if _use_gemm_form(batch_size, num_nodes, n, training=True):
         return edge_layer_gemm_bwd(pos, mass, batch_size, num_nodes, n, p, q, w_edge1, w2, bn_a, bn_b, bn_c, dagg,
-                                   dP, dQ, gz)
+                                   dP, dQ, gz, side=side)
     ws = torch.empty(max(1, int(lib.segnn_edge_layer_bwd_workspace(batch_size, num_nodes, n)) // 4), **f)
     g = dict(ss=gz[: 2 * n * n].view(n, 2 * n), vs=gz[2 * n * n: 4 * n * n].view(n, 2 * n),
              sv=gz[4 * n * n: 5 * n * n].view(n, n), vv=gz[5 * n * n: 6 * n * n].view(n, n), b=gz[6 * n * n:])

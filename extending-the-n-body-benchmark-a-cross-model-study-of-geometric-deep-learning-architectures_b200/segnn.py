@@ -120,6 +120,22 @@ class SEGNNLayer(nn.Module):
             out["bn_feat"] = _fold_bn(self.feature_norm, n, 1.0)
         return out
 
+    def run_x16(self, w, h, h16, pos, mass, node_attr, batch_size: int, num_nodes: int):
+        """`run` in the packed-half mode with fp16 operand copies of the features: every tensor-core node GEMM reads
+        16-bit rows its producer rounded (embed / combine / edge kernel), the fp32 features survive only as the
+        residual.  Bit-identical to `run` (same roundings, applied by the producer instead of the GEMM loader).
+        Returns (h_out fp32, h_out fp16)."""
+        n = self.n
+        m1, u1, u2 = w["msg1"], w["upd1"], w["upd2"]
+        p, q = ops.node_gemm_pair16(h16, dict(wt_s=m1["wt_s_h"], wt_v=m1["wt_v_h"], operand=1), 6 * n,
+                                    m1["bias_tc_h"], 3 * n, 3 * n)
+        agg16 = ops.edge_layer(ops.MODE_FP16_PACKED, pos, mass, batch_size, num_nodes, n, p, q, m1["w_edge"],
+                               w["msg2"], w["bn_msg"][0], w["bn_msg"][1], out16=True)
+        g1_16 = ops.tp_combine(ops.node_gemm_out16(h16, agg16, u1, 3 * n), node_attr, n, True, bias=u1["bias"],
+                               out16="only")
+        return ops.tp_combine(ops.node_gemm_out16(g1_16, None, u2, 2 * n), node_attr, n, False, bias=u2["bias"],
+                              residual=h, bn_mul=w["bn_feat"][0], bn_add=w["bn_feat"][1], out16="both")
+
     def run(self, w, mode: int, h, pos, mass, node_attr, batch_size: int, num_nodes: int):
         """One layer on planar features h [nodes,4,n] (eval-mode BatchNorm)."""
         n = self.n
@@ -305,17 +321,26 @@ class SEGNN(nn.Module):
                                f"(hidden_features 64/128/192); this model has n={n}")
         if x_in is None or node_attr is None:
             x_in, node_attr = ops.prep(pos, vel, batch_size, num_nodes)
-        h = ops.embed(x_in, node_attr, w["embed"]["w"], w["embed"]["bias"], n)
+        # packed-half mode on batches large enough for the tensor-core update GEMMs: fp16 operand copies of the features
+        x16 = (ops.X16_FEATURES and mode == ops.MODE_FP16_PACKED and not batch_stats_tc and num_nodes % 2 == 0
+               and n % 2 == 0 and x_in.shape[0] >= SMALL_BATCH_NODES)
+        h16 = None
+        if x16:
+            h, h16 = ops.embed(x_in, node_attr, w["embed"]["w"], w["embed"]["bias"], n, want16=True)
+        else:
+            h = ops.embed(x_in, node_attr, w["embed"]["w"], w["embed"]["bias"], n)
         per_layer = [h]
         for layer, lw in zip(self.layers, w["layers"]):
             if batch_stats_tc:  # train-mode BatchNorm without gradients: tensor-core kernels + batch statistics
                 h = layer.run_batch_statistics(lw, h, pos, mass, node_attr, batch_size, num_nodes)
+            elif x16:
+                h, h16 = layer.run_x16(lw, h, h16, pos, mass, node_attr, batch_size, num_nodes)
             else:
                 h = layer.run(lw, mode, h, pos, mass, node_attr, batch_size, num_nodes)
             per_layer.append(h)
         p1 = w["pool1"]
-        y = ops.node_gemm_out16(h, None, p1, 3 * n) if mode in _TC_MODES and h.shape[0] >= SMALL_BATCH_NODES \
-            else ops.node_gemm(h, None, p1, 3 * n)
+        y = ops.node_gemm_out16(h16 if x16 else h, None, p1, 3 * n) \
+            if mode in _TC_MODES and h.shape[0] >= SMALL_BATCH_NODES else ops.node_gemm(h, None, p1, 3 * n)
         hp = ops.tp_combine(y, node_attr, n, True, bias=p1["bias"])
         pred = ops.head(hp, node_attr, w["head"], n)
         if return_layers:

@@ -213,11 +213,12 @@ def backward_train(W: Dict, saved: Dict, dpred, backend=None):
         # fused edge layer backward (recompute) -> dP, dQ, message_layer_2 and w_edge gradients
         if rec.get("rows") is not None:  # the forward call left this layer's edge rows in HBM: no recompute
             dP, dQ, g["msg2"], dwe = _ops.edge_layer_gemm_bwd(pos, mass, B, N, n, rec["p"], rec["q"], m1["w_edge"], m2,
-                                                              bn_a, bn_b, bn_c, dagg, rows=rec["rows"])
+                                                              bn_a, bn_b, bn_c, dagg, rows=rec["rows"], side=side)
             rec["rows"] = None  # 11 n floats per edge row go back to the allocator as soon as the layer is done
         else:
+            kw = dict(side=side) if side is not None else {}  # test back ends keep the plain signature
             dP, dQ, g["msg2"], dwe = be.edge_layer_bwd(pos, mass, B, N, n, rec["p"], rec["q"], m1["w_edge"], m2, bn_a,
-                                                       bn_b, bn_c, dagg)
+                                                       bn_b, bn_c, dagg, **kw)
         # message_layer_1 projections: [P | Q] = h @ W (+ bias on P's l=0 columns)
         def msg1_weights(h_=rec["h"], dP_=dP, dQ_=dQ):
             dw_s, dw_v = be.node_gemm_wgrad(h_, None, dP_, dQ_, 3 * n)

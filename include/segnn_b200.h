@@ -83,6 +83,13 @@ int segnn_prep_fwd(const float* pos, const float* vel, int B, int N, float* x_in
 int segnn_embed_fwd(const float* x_in, const float* node_attr, const float* w_embed, const float* bias,
                     int nodes, int n, float* h_out, segnn_stream_t stream);
 
+/* Same kernel, also writing h16_out: an fp16 copy [nodes][4][n] of h_out (round to nearest even), the operand rows of
+ * segnn_node_gemm_tc_x16.  The tensor-core node GEMMs round their fp32 inputs to the operand format on load; a
+ * producer that stores the rounded copy itself halves the bytes those GEMMs read and leaves their results bit-identical
+ * (models/segnn/segnn.py:170 feeds segnn.py:264-304 of the first layer). */
+int segnn_embed_fwd_x16(const float* x_in, const float* node_attr, const float* w_embed, const float* bias,
+                        int nodes, int n, float* h_out, void* h16_out, segnn_stream_t stream);
+
 /* ---- node-level tensor products: plain GEMM + attribute combine ------------------------------------ */
 
 /* The weight contraction of an O3TensorProduct over node rows (o3_building_blocks.py:150-162) hoisted out
@@ -116,6 +123,16 @@ int segnn_node_gemm_tc_pair16(const float* x0, const float* x1, int nodes, int n
 int segnn_node_gemm_tc_out16(const float* x0, const float* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
                              int n_out, void* y, int operand, segnn_stream_t stream);
 
+/* Same GEMM reading 16-bit rows: x0, x1 planar [nodes][4][n_in] already in the `operand` format (fp16 copies written
+ * by segnn_embed_fwd_x16 / segnn_tp_combine_y16_x16 / segnn_edge_layer_fwd_out16), copied to the swizzled A tile
+ * without conversion, two batches of loads in flight per loader thread across tile boundaries.  out_mode 1: the
+ * pair-interleaved fp16 output of segnn_node_gemm_tc_pair16 (y0 / y1 / split / bias as there); out_mode 2: the fp16
+ * rows of segnn_node_gemm_tc_out16 (y1 NULL, split = n_out, bias NULL).  Results are bit-identical to the fp32-input
+ * entry points on inputs whose fp16 copy was rounded to nearest even (o3_building_blocks.py:150-162 over node rows). */
+int segnn_node_gemm_tc_x16(const void* x0, const void* x1, int nodes, int n_in, const void* wt_s, const void* wt_v,
+                           const float* bias, int n_bias, int n_out, void* y0, void* y1, int split, int operand,
+                           int out_mode, segnn_stream_t stream);
+
 /* w [K][n_out] fp32 -> wt [n_out][K] bf16 / fp16 (the B operand image of segnn_node_gemm_tc). */
 int segnn_pack_node_weight_tc(const float* w, int K, int n_out, int operand, void* wt, segnn_stream_t stream);
 
@@ -136,6 +153,13 @@ int segnn_tp_combine(const float* y, const float* node_attr, int nodes, int n, i
 int segnn_tp_combine_y16(const void* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
                          const float* residual, const float* bn_mul, const float* bn_add, float* out,
                          segnn_stream_t stream);
+
+/* Same pass, also (or only: out may be NULL) writing out16, the fp16 copy [nodes][4][n] of the result that the next
+ * tensor-core node GEMM reads through segnn_node_gemm_tc_x16 (update_layer_1 -> update_layer_2, segnn.py:286-304; the
+ * layer output -> the next layer's message_layer_1 / update_layer_1).  Needs an even n. */
+int segnn_tp_combine_y16_x16(const void* y, const float* node_attr, int nodes, int n, int gate, const float* bias,
+                             const float* residual, const float* bn_mul, const float* bn_add, float* out,
+                             void* out16, segnn_stream_t stream);
 
 /* ---- K3: fused edge layer ---------------------------------------------------------------------------- */
 
@@ -162,6 +186,13 @@ int segnn_edge_layer_fwd(int mode, const float* pos, const float* mass, int B, i
                          const float* q, const float* w_edge1, const float* w2_ss, const float* w2_vs, const float* w2_sv,
                          const float* w2_vv, const float* b2, const void* w2_tc, const float* bn_mul,
                          const float* bn_add, float* agg_out, float* moments, segnn_stream_t stream);
+
+/* SEGNN_MODE_FP16_PACKED with the aggregate written as fp16 rows agg16_out [nodes][4][n] (round to nearest even of the
+ * same fp32 values, eval-mode BatchNorm folded as above): the x1 operand of update_layer_1's tensor-core GEMM
+ * (segnn_node_gemm_tc_x16; segnn.py:205 aggregation -> segnn.py:286-299 update).  p, q, w2_tc as in that mode. */
+int segnn_edge_layer_fwd_out16(const float* pos, const float* mass, int B, int N, int n, const void* p, const void* q,
+                               const float* w_edge1, const float* b2, const void* w2_tc, const float* bn_mul,
+                               const float* bn_add, void* agg16_out, segnn_stream_t stream);
 
 /* Packs the message_layer_2 weights for SEGNN_MODE_BF16_TC / SEGNN_MODE_FP16_TC (operand = SEGNN_OPERAND_*) into the
  * [128 lanes][3n] image of 16-bit pairs the tensor-core kernel copies verbatim into TMEM (gate constants folded).
@@ -356,6 +387,22 @@ int segnn_edge_layer_gemm_bwd(const float* pos, const float* mass, int B, int N,
                               float* dw2_sv, float* dw2_vv, float* db2, float* dwe_partial, float* workspace,
                               int64_t workspace_bytes, const float* fwd_workspace, int64_t fwd_workspace_bytes,
                               segnn_stream_t stream);
+/* The same call in separately launchable phases (bit mask; 7 = segnn_edge_layer_gemm_bwd): bit 0 = rows (recompute
+ * unless fwd_workspace holds them) + gate backward + bias-gradient sums, bit 1 = the message_layer_2 weight gradients
+ * (split-K TN GEMMs over the edge rows, dw2_* / db2), bit 2 = the data gradients down to dP / dQ / dwe_partial.  Phases
+ * 1 and 2 only read what phase 0 left in `workspace`, and write disjoint parts of it, so a caller may launch the weight
+ * gradients on a second stream beside the data-gradient chain (trainer.py:309 loss.backward(): the weight gradients of
+ * a layer are off the critical path of the layers below it).  Needs a workspace that holds every graph in ONE chunk
+ * when phases != 7.  Same arguments, same results bit for bit. */
+int segnn_edge_layer_gemm_bwd_phases(const float* pos, const float* mass, int B, int N, int n, const float* p,
+                                     const float* q, const float* w_edge1, const float* w2_ss, const float* w2_vs,
+                                     const float* w2_sv, const float* w2_vv, const float* b2, const float* w2t_ss,
+                                     const float* w2t_vs, const float* w2t_sv, const float* w2t_vv, const float* bn_a,
+                                     const float* bn_b, const float* bn_c, const float* dagg, float* dP, float* dQ,
+                                     float* dw2_ss, float* dw2_vs, float* dw2_sv, float* dw2_vv, float* db2,
+                                     float* dwe_partial, float* workspace, int64_t workspace_bytes,
+                                     const float* fwd_workspace, int64_t fwd_workspace_bytes, int phases,
+                                     segnn_stream_t stream);
 
 /* lmax_h = 2 (hidden irreps n x 0e + n x 1o + n x 2e, attribute 0e + 1o, two additional scalars: BASELINE
  * configuration 3) edge layer in GEMM form, inference: the per-edge work of SEGNNLayer.message + aggregation

@@ -157,3 +157,35 @@ def test_training_step_in_gemm_form_matches_oracle(H, L, B, N, bn_train, keep, m
         worst = max(worst, err / max(scale, 1e-30)) if scale > 1e-9 else worst
         assert err <= 1e-4 * scale + 1e-5 * top, f"{k}: {err} vs scale {scale} (top {top})"
     print(f"H={H} N={N}: worst gradient rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("keep", [True, False])
+def test_side_stream_weight_gradients_are_bit_identical_to_the_inline_order(keep, monkeypatch):
+    """GEMM-form edge backward with the message_layer_2 weight gradients launched through the side stream
+    (segnn_edge_layer_gemm_bwd_phases 1 | 2 | 4) against the single in-line call (phases = 7): every gradient of a
+    README-shaped training step is bit-identical, kept rows and recomputed rows."""
+    monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS", 0)
+    monkeypatch.setattr(S.ops, "GEMM_FORM_MIN_ROWS_TRAINING", 0)
+    if not keep:
+        monkeypatch.setattr(S.ops, "GEMM_FORM_KEEP_BYTES_PER_LAYER", 0)
+    B, N, H, L = 16, 5, 192, 2
+    torch.manual_seed(3)
+    m = S.SEGNN(hidden_features=H, num_layers=L).float().cuda().train()
+    pos, vel, mass = O.synthetic_system(B, N, seed=4)
+    y = torch.randn(B * N, 6).cuda()
+    g = S.GraphBatch(pos=pos.reshape(-1, 3).float().cuda(), vel=vel.reshape(-1, 3).float().cuda(),
+                     mass=mass.reshape(-1, 1).float().cuda(), num_graphs=B, n_nodes=N)
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    grads = {}
+    for side in (False, True, True):
+        monkeypatch.setattr(S.ops, "SIDE_STREAM_W2_GRADS", side)
+        m.load_state_dict(state)  # the same running statistics before every pass
+        m.zero_grad(set_to_none=True)
+        O.target_common_loss(m(g), y).backward()
+        torch.cuda.synchronize()
+        cur = {k: p.grad.clone() for k, p in m.named_parameters()}
+        if side in grads:
+            assert all(torch.equal(cur[k], grads[side][k]) for k in cur)
+        grads[side] = cur
+    for k in grads[True]:
+        assert torch.equal(grads[True][k], grads[False][k]), k

@@ -74,3 +74,45 @@ def test_node_gemm_tf32x3_matches_the_ffma_kernel(nodes, n_in, n_out, two, split
     e_ff = float((outs[False].double() - ref).abs().max() / ref.abs().max())
     print(f"nodes={nodes} K={K} n_out={n_out}: tcgen05 3xTF32 {e_tc:.2e}, FFMA {e_ff:.2e}")
     assert e_tc < 3e-6 and e_ff < 3e-6
+
+
+@pytest.mark.parametrize("nodes,n_in,two,n_out,split", [(320, 96, False, 576, 288), (320, 96, True, 288, 288),
+                                                        (37, 96, False, 192, 192), (1000, 288, False, 192, 96),
+                                                        (500, 32, True, 96, 96), (321, 64, False, 100, 100),
+                                                        (4096, 96, True, 96, 96)])
+def test_small_batch_node_gemm_is_bit_identical_to_the_tile_kernel(nodes, n_in, two, n_out, split):
+    """segnn_node_gemm below 4096 nodes runs node_gemm_small_kernel (32 x 64 tiles, 4-stage cp.async ring); the same
+    rows inside a batch above the threshold run node_gemm_kernel (64 x 64 tiles).  Same accumulation order: the outputs
+    of the shared rows are bit-identical -- ragged row and column tiles, one and two inputs, split outputs, bias."""
+    import segnn_b200 as S
+    ops = S.ops
+    old = ops.NODE_GEMM_TF32X3
+    ops.NODE_GEMM_TF32X3 = False  # keep the large batch on the FFMA tile kernel
+    try:
+        gen = torch.Generator(device="cpu").manual_seed(nodes + n_out)
+        big = 4100 + nodes
+        K = n_in * (2 if two else 1)
+        x0 = torch.randn(big, 4, n_in, generator=gen).cuda()
+        x1 = torch.randn(big, 4, n_in, generator=gen).cuda() if two else None
+        w = dict(w_s=(torch.randn(K, n_out, generator=gen) / K ** 0.5).cuda(),
+                 w_v=(torch.randn(K, n_out, generator=gen) / K ** 0.5).cuda())
+        n_bias = min(n_out, 64)
+        bias = torch.randn(n_bias, generator=gen).cuda()
+        kw = dict(bias=bias, n_bias=n_bias)
+        if split < n_out:
+            r0, r1 = ops.node_gemm(x0, x1, w, n_out, split=split, tc=False, **kw)
+            s0, s1 = ops.node_gemm(x0[:nodes].contiguous(), None if x1 is None else x1[:nodes].contiguous(), w, n_out,
+                                   split=split, tc=False, **kw)
+            assert torch.equal(s0, r0[:nodes]) and torch.equal(s1, r1[:nodes])
+        else:
+            r = ops.node_gemm(x0, x1, w, n_out, tc=False, **kw)
+            s = ops.node_gemm(x0[:nodes].contiguous(), None if x1 is None else x1[:nodes].contiguous(), w, n_out,
+                              tc=False, **kw)
+            assert torch.equal(s, r[:nodes])
+            ref = torch.cat([x0[:nodes], x1[:nodes]], 2) if two else x0[:nodes]
+            ref = torch.stack([ref[:, 0].double() @ w["w_s"].double()] +
+                              [ref[:, c].double() @ w["w_v"].double() for c in (1, 2, 3)], 1)
+            ref[:, 0, :n_bias] += bias.double()
+            assert float((s.double() - ref).abs().max()) < 1e-4
+    finally:
+        ops.NODE_GEMM_TF32X3 = old

@@ -675,3 +675,59 @@ def test_c_abi_weight_packing_matches_python_packing(n):
     mul, add = ops.fold_batchnorm(*bn, n, 1e-5, 7.0)
     rmul, radd = P.fold_batchnorm(*bn, n, 1e-5, 7.0)
     assert torch.allclose(mul, rmul, rtol=2e-6) and torch.allclose(add, radd, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("nodes,n_in,two_inputs,n_out", [(18, 96, False, 576), (2050, 96, True, 288), (1000, 32, True, 192),
+                                                         (262, 64, False, 384), (4098, 96, False, 192),
+                                                         (3000, 48, True, 96), (700, 80, True, 160)])
+def test_node_gemm_fp16_rows_bit_identical_to_fp32_rows(nodes, n_in, two_inputs, n_out):
+    """segnn_node_gemm_tc_x16 (fp16 feature copies, no conversion on load, loads of two batches in flight across tile
+    boundaries) against the fp32-input entry points on the same values: the rounding moved from the GEMM loader to the
+    producer of the copy, so both output modes are bit-identical -- ragged last tiles, one and two inputs, every K the
+    launcher accepts in one and two batches per tile."""
+    if not S.ops.tc_available():
+        pytest.skip("tensor-core kernels not built")
+    ops = S.ops
+    gen = torch.Generator(device="cpu").manual_seed(nodes + n_out)
+    K = n_in * (2 if two_inputs else 1)
+    x0 = torch.randn(nodes, 4, n_in, generator=gen).cuda()
+    x1 = torch.randn(nodes, 4, n_in, generator=gen).cuda() if two_inputs else None
+    w = dict(w_s=(torch.randn(K, n_out, generator=gen) / K ** 0.5).cuda(),
+             w_v=(torch.randn(K, n_out, generator=gen) / K ** 0.5).cuda(), operand=1)
+    w["wt_s"], w["wt_v"] = ops.pack_node_weight_tc(w["w_s"], 1), ops.pack_node_weight_tc(w["w_v"], 1)
+    h0, h1 = x0.half(), (x1.half() if two_inputs else None)
+    ref = ops.node_gemm_out16(x0, x1, w, n_out)
+    got = ops.node_gemm_out16(h0, h1, w, n_out)
+    assert got.dtype == torch.float16 and torch.equal(got, ref)
+    if not two_inputs and n_out % 64 == 0:
+        split = n_out // 2
+        bias = torch.randn(split, generator=gen).cuda()
+        r0, r1 = ops.node_gemm_pair16(x0, w, n_out, bias, split, split)
+        g0, g1 = ops.node_gemm_pair16(h0, w, n_out, bias, split, split)
+        assert torch.equal(g0, r0) and torch.equal(g1, r1)
+
+
+@pytest.mark.parametrize("H,L,B,N", [(192, 2, 24, 100), (64, 2, 350, 6), (128, 1, 3, 700)])
+def test_fp16_feature_copies_leave_the_packed_half_forward_bit_identical(H, L, B, N):
+    """compute_mode 'fp16p' with the fp16 operand copies of the node features (embed / combine / edge kernel write them,
+    the tensor-core node GEMMs read them: SEGNNLayer.run_x16) against the same mode converting fp32 features on load:
+    every layer output and the prediction are bit-identical, so the oracle parity of the mode carries over."""
+    if not S.ops.tc_available():
+        pytest.skip("tensor-core kernels not built")
+    om, m = make_pair(H, L, seed=5)
+    m.compute_mode = "fp16p"
+    pos, vel, mass = O.synthetic_system(B, N, seed=7)
+    g = gpu_graph(pos, vel, mass, B, N)
+    old = S.ops.X16_FEATURES
+    try:
+        with torch.no_grad():
+            S.ops.X16_FEATURES = False
+            ref, ref_layers = m(g, return_layers=True)
+            S.ops.X16_FEATURES = True
+            out, layers = m(g, return_layers=True)
+    finally:
+        S.ops.X16_FEATURES = old
+    assert B * N >= 2048, "the fp16-copy path is taken from 2048 nodes on"
+    for a, b in zip(layers, ref_layers):
+        assert torch.equal(a, b)
+    assert torch.equal(out, ref)

@@ -50,6 +50,8 @@ PROTOTYPES = {
     "segnn_counter_add": (_int, [_ptr, _int, _ptr]),
     "segnn_colsum_workspace": (_c.c_int64, [_c.c_int64, _int]),
     "segnn_colsum": (_int, [_ptr, _ptr, _c.c_int64, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_colsum2": (_int, [_ptr, _ptr, _c.c_int64, _int, _int, _ptr, _ptr, _ptr, _c.c_int64, _int, _int, _ptr, _ptr,
+                             _ptr]),
     "segnn_lincomb": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c.c_int64, _int, _ptr, _ptr]),
     "segnn_bn_coeffs_fwd": (_int, [_ptr, _ptr, _int, _int, _c.c_double, _c.c_double, _ptr, _ptr, _ptr, _ptr, _c.c_double,
                                    _c.c_double, _int, _int, _ptr, _ptr, _ptr]),

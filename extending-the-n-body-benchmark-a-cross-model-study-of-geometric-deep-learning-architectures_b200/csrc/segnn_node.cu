@@ -261,9 +261,11 @@ __global__ void __launch_bounds__(256) node_gemm_kernel(const float* __restrict_
 // ring, so up to four steps of loads are in flight while one is multiplied.  Same accumulation order (k ascending, one
 // fmaf per product) as node_gemm_kernel: bit-identical results.  Needs n_in % 4 == 0 and n_out % 4 == 0 (16-byte copies).
 constexpr int kSmallGemmMaxNodes = 4096;  // above: node_gemm_kernel (fp32 mode switches to segnn_node_gemm_tf32x3 there)
-constexpr int kSmBM = 32, kSmBN = 64, kSmBK = 32, kSmStages = 4, kSmThreads = 128;
-constexpr int kSmAStride = kSmBK + 4, kSmBStride = kSmBN + 4;  // floats; rows stay 16-byte aligned
-constexpr int kSmStageFloats = kSmBM * kSmAStride + kSmBK * kSmBStride;
+// K steps of 64 from K = 256 on (message_layer_1 data gradient, K = 6n: twice the bytes in flight, half the barriers).
+constexpr int kSmBM = 32, kSmBN = 64, kSmStages = 4, kSmThreads = 128;
+constexpr int kSmBStride = kSmBN + 4;  // floats; rows stay 16-byte aligned
+template <int BK>
+__host__ __device__ constexpr int sm_stage_floats() { return kSmBM * (BK + 4) + BK * kSmBStride; }
 
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
@@ -271,11 +273,14 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool va
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
+template <int kSmBK>
 __global__ void __launch_bounds__(kSmThreads) node_gemm_small_kernel(
     const float* __restrict__ x0, const float* __restrict__ x1, int nodes, int n_in, const float* __restrict__ w_s,
     const float* __restrict__ w_v, const float* __restrict__ bias, int n_bias, int n_out, float* __restrict__ y0,
     float* __restrict__ y1, int split) {
   extern __shared__ __align__(16) float sm_ring[];
+  constexpr int kSmAStride = kSmBK + 4, kSmStageFloats = sm_stage_floats<kSmBK>();
+  constexpr int kAChunks = kSmBM * kSmBK / 4 / kSmThreads, kBChunks = kSmBK * kSmBN / 4 / kSmThreads;
   const int cls = blockIdx.z;
   const int64_t rows = cls == 0 ? (int64_t)nodes : (int64_t)nodes * 3;
   const int64_t row0 = (int64_t)blockIdx.x * kSmBM;
@@ -286,14 +291,14 @@ __global__ void __launch_bounds__(kSmThreads) node_gemm_small_kernel(
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // 16 column groups x 8 row groups, 4 x 4 outputs each
   const int ksteps = (K + kSmBK - 1) / kSmBK;
 
-  // A copies: 32 rows x 8 chunks of 4 k = 256 chunks, two per thread; B copies: 32 k x 16 chunks of 4 columns, four
-  int64_t a_plane[2];
-  int a_row[2], a_k[2];
+  // A copies: 32 rows x BK / 4 chunks of 4 k (two / four per thread); B copies: BK k x 16 chunks of 4 columns
+  int64_t a_plane[kAChunks];
+  int a_row[kAChunks], a_k[kAChunks];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < kAChunks; ++q) {
     const int c = tid + q * kSmThreads;
-    a_row[q] = c >> 3;
-    a_k[q] = (c & 7) * 4;
+    a_row[q] = c / (kSmBK / 4);
+    a_k[q] = (c % (kSmBK / 4)) * 4;
     const int64_t r = row0 + a_row[q];
     a_plane[q] = r < rows ? (cls == 0 ? r * 4 : (r / 3) * 4 + 1 + (r % 3)) : -1;
   }
@@ -303,14 +308,14 @@ __global__ void __launch_bounds__(kSmThreads) node_gemm_small_kernel(
       float* Bs = As + kSmBM * kSmAStride;
       const int k0 = step * kSmBK;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < kAChunks; ++q) {
         const int k = k0 + a_k[q];
         const bool ok = a_plane[q] >= 0 && k < K;
         const float* src = !ok ? x0 : (k < n_in ? x0 + a_plane[q] * n_in + k : x1 + a_plane[q] * n_in + (k - n_in));
         cp_async16(As + a_row[q] * kSmAStride + a_k[q], src, ok);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < kBChunks; ++q) {
         const int c = tid + q * kSmThreads;
         const int bk = c >> 4, bc = (c & 15) * 4;
         const bool ok = k0 + bk < K && col0 + bc < n_out;
@@ -672,16 +677,27 @@ int segnn_node_gemm(const float* x0, const float* x1, int nodes, int n_in, const
   // a few hundred rows (training batches): the latency-tolerant small-tile kernel (same results bit for bit)
   if (nodes <= kSmallGemmMaxNodes && n_in % 4 == 0 && n_out % 4 == 0 && ((uintptr_t)x0 & 15) == 0 &&
       ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)w_s & 15) == 0 && ((uintptr_t)w_v & 15) == 0) {
-    static const cudaError_t attr = cudaFuncSetAttribute(node_gemm_small_kernel,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         kSmStages * kSmStageFloats * (int)sizeof(float));
-    if (attr != cudaSuccess) {
-      set_error("segnn_node_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr));
+    static const cudaError_t attr32 = cudaFuncSetAttribute(node_gemm_small_kernel<32>,
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           kSmStages * sm_stage_floats<32>() * (int)sizeof(float));
+    static const cudaError_t attr64 = cudaFuncSetAttribute(node_gemm_small_kernel<64>,
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           kSmStages * sm_stage_floats<64>() * (int)sizeof(float));
+    if (attr32 != cudaSuccess || attr64 != cudaSuccess) {
+      set_error("segnn_node_gemm: cudaFuncSetAttribute: %s",
+                cudaGetErrorString(attr32 != cudaSuccess ? attr32 : attr64));
       return SEGNN_E_CUDA;
     }
     dim3 grid_s((unsigned)(((int64_t)nodes * 3 + kSmBM - 1) / kSmBM), (n_out + kSmBN - 1) / kSmBN, 2);
-    node_gemm_small_kernel<<<grid_s, kSmThreads, kSmStages * kSmStageFloats * sizeof(float), (cudaStream_t)stream>>>(
-        x0, x1, nodes, n_in, w_s, w_v, bias, n_bias, n_out, y0, y1, split);
+    const int K = x1 ? 2 * n_in : n_in;
+    if (K >= 256)
+      node_gemm_small_kernel<64><<<grid_s, kSmThreads, kSmStages * sm_stage_floats<64>() * sizeof(float),
+                                   (cudaStream_t)stream>>>(x0, x1, nodes, n_in, w_s, w_v, bias, n_bias, n_out, y0, y1,
+                                                           split);
+    else
+      node_gemm_small_kernel<32><<<grid_s, kSmThreads, kSmStages * sm_stage_floats<32>() * sizeof(float),
+                                   (cudaStream_t)stream>>>(x0, x1, nodes, n_in, w_s, w_v, bias, n_bias, n_out, y0, y1,
+                                                           split);
     SEGNN_CHECK_LAUNCH();
     return SEGNN_OK;
   }

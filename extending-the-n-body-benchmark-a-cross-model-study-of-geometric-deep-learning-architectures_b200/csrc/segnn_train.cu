@@ -68,6 +68,38 @@ __global__ void __launch_bounds__(1024) colsum_small(const float* __restrict__ x
 }
 constexpr int kColsumSmallParts = 32;  // up to 2048 rows take the single-launch path
 
+// Two independent column sums in one launch (blockIdx.y selects the job): the statistics of a train-mode BatchNorm always
+// come in pairs (sum and sum of squares, sum g and sum g * x), each pair was two launches on the critical chain.
+struct ColsumJob {
+  const float* x;
+  const float* y;
+  int64_t rows;
+  int cols, mode;
+  float* out;
+};
+__global__ void __launch_bounds__(1024) colsum_small2(ColsumJob a, ColsumJob b) {
+  __shared__ double red[32][33];
+  const ColsumJob j = blockIdx.y == 0 ? a : b;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double acc = 0.0;
+  if (c < j.cols) {  // same loop, same association as colsum_small: bit-identical sums
+#pragma unroll 4
+    for (int64_t r = ry; r < j.rows; r += 32) {
+      const double v = (double)j.x[r * j.cols + c];
+      acc += j.mode == 0 ? v : (j.mode == 1 ? v * v : v * (double)j.y[r * j.cols + c]);
+    }
+  }
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < j.cols) {
+    double s = red[0][cx];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) s += red[i][cx];
+    j.out[c] = (float)s;
+  }
+}
+
 template <typename T>
 __global__ void colsum_stage2(const T* __restrict__ partial, int nparts, int cols, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -477,6 +509,27 @@ int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mod
     colsum_stage2<double><<<(cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, (int)parts, cols, out);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
+}
+
+int segnn_colsum2(const float* xa, const float* ya, int64_t rows_a, int cols_a, int mode_a, float* out_a,
+                  const float* xb, const float* yb, int64_t rows_b, int cols_b, int mode_b, float* out_b,
+                  float* workspace, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(rows_a >= 0 && cols_a >= 1 && mode_a >= 0 && mode_a <= 2 && rows_b >= 0 && cols_b >= 1 &&
+                      mode_b >= 0 && mode_b <= 2, "bad arguments");
+  const int64_t parts_a = (rows_a + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock;
+  const int64_t parts_b = (rows_b + kColsumRowsPerBlock - 1) / kColsumRowsPerBlock;
+  if (rows_a > 0 && rows_b > 0 && parts_a <= kColsumSmallParts && parts_b <= kColsumSmallParts) {
+    SEGNN_CHECK_ARG(xa && xb && out_a && out_b && (mode_a != 2 || ya) && (mode_b != 2 || yb), "null pointer");
+    const int cmax = cols_a > cols_b ? cols_a : cols_b;
+    colsum_small2<<<dim3((cmax + 31) / 32, 2), 1024, 0, (cudaStream_t)stream>>>(
+        ColsumJob{xa, ya, rows_a, cols_a, mode_a, out_a}, ColsumJob{xb, yb, rows_b, cols_b, mode_b, out_b});
+    SEGNN_CHECK_LAUNCH();
+    return SEGNN_OK;
+  }
+  // many rows: the two-stage reductions one after the other (the workspace is reused in stream order)
+  int rc = segnn_colsum(xa, ya, rows_a, cols_a, mode_a, workspace, out_a, stream);
+  if (rc != SEGNN_OK) return rc;
+  return segnn_colsum(xb, yb, rows_b, cols_b, mode_b, workspace, out_b, stream);
 }
 
 int segnn_lincomb(const float* dy, const float* x, const float* A, const float* B, const float* C, int64_t rows,

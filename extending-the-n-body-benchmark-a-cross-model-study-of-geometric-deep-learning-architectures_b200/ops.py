@@ -542,6 +542,22 @@ def colsum(x: torch.Tensor, y: Optional[torch.Tensor] = None, mode: int = 0) -> 
     return out
 
 
+def colsum2(xa, ya, mode_a: int, xb, yb, mode_b: int):
+    """Two deterministic column reductions (see colsum) in one launch up to 2048 rows each (segnn_colsum2)."""
+    (ra, ca), (rb, cb) = xa.shape, xb.shape
+    assert xa.is_contiguous() and xb.is_contiguous() and (ya is None or ya.is_contiguous()) \
+        and (yb is None or yb.is_contiguous())
+    out_a = torch.empty(ca, dtype=torch.float32, device=xa.device)
+    out_b = torch.empty(cb, dtype=torch.float32, device=xa.device)
+    need = max(lib.segnn_colsum_workspace(ra, ca), lib.segnn_colsum_workspace(rb, cb))
+    ws = torch.empty(max(1, need // 8), dtype=torch.float64, device=xa.device)
+    with torch.cuda.device(xa.device):
+        check(lib.segnn_colsum2(_p(xa), _p(ya), ra, ca, mode_a, _p(out_a), _p(xb), _p(yb), rb, cb, mode_b, _p(out_b),
+                                _p(ws), _stream()), "segnn_colsum2")
+    _bump(1 if max(ra, rb) <= 2048 else 4)
+    return out_a, out_b
+
+
 def lincomb(dy, x, A, B=None, C=None):
     """out[r][c] = A[c]*dy[r][c] + B[c]*x[r][c] + C[c] on dense [rows, cols] views."""
     rows, cols = dy.shape

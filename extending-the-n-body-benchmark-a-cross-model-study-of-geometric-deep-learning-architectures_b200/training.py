@@ -59,6 +59,14 @@ def unflatten_packed(leaves, spec):
     return leaves[spec["t"]]
 
 
+def _colsum2_of(be):
+    """The paired column sum of a kernel namespace; test back ends that only emulate `colsum` get two calls."""
+    fn = getattr(be, "colsum2", None)
+    if fn is not None:
+        return fn
+    return lambda xa, ya, ma, xb, yb, mb: (be.colsum(xa, ya, ma), be.colsum(xb, yb, mb))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # forward (fp32 kernels), saving node-level tensors only
 # ---------------------------------------------------------------------------------------------------------------
@@ -68,6 +76,7 @@ def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: 
     follow): large graphs, whose edge layers run in GEMM form, leave their edge rows in HBM for the backward call when
     they fit ops.GEMM_FORM_KEEP_BYTES_PER_LAYER; everything else stores node-level tensors only."""
     be = backend or _ops
+    colsum2 = _colsum2_of(be)
     nodes, deg = B * N, N - 1
     E = nodes * deg
     x_in, attr = be.prep(pos, vel, B, N)
@@ -85,8 +94,7 @@ def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: 
                                          want_moments=True)
         rec = dict(h=h, p=p, q=q, agg_raw=agg_raw, rows=rows)
         if lw["bn_msg"] is not None:
-            sums = be.colsum(agg_raw.view(nodes, 4 * n))
-            sq = be.colsum(mom)
+            sums, sq = colsum2(agg_raw.view(nodes, 4 * n), None, 0, mom, None, 0)
             st = be.bn_forward_coeffs(lw["bn_msg"], n, float(E), float(deg), sums, sq, 1, bn_training,
                                       update_running_stats)
             agg = be.lincomb(agg_raw.view(nodes, 4 * n), None, st["mulcols"], None, st["addcols"]).view(nodes, 4, n)
@@ -100,8 +108,7 @@ def forward_train(W: Dict, n: int, pos, vel, mass, B: int, N: int, bn_training: 
         rec.update(agg=agg, y1=y1, g1=g1, y2=y2, pre=pre)
         if lw["bn_feat"] is not None:
             flat = pre.view(nodes, 4 * n)
-            sums = be.colsum(flat)
-            sq = be.colsum(flat, None, 1)
+            sums, sq = colsum2(flat, None, 0, flat, None, 1)
             st = be.bn_forward_coeffs(lw["bn_feat"], n, float(nodes), 1.0, sums, sq, 3, bn_training,
                                       update_running_stats)
             h = be.lincomb(flat, None, st["mulcols"], None, st["addcols"]).view(nodes, 4, n)
@@ -170,6 +177,7 @@ def _node_tp_backward(be, w, x0, x1, y, attr, n, gate, dout, split_out: Optional
 def backward_train(W: Dict, saved: Dict, dpred, backend=None):
     """Returns the gradient tree matching W (None where a leaf has no gradient, e.g. BatchNorm buffers)."""
     be = backend or _ops
+    colsum2 = _colsum2_of(be)
     n, B, N = saved["n"], saved["B"], saved["N"]
     nodes, deg = B * N, N - 1
     E = nodes * deg
@@ -188,8 +196,7 @@ def backward_train(W: Dict, saved: Dict, dpred, backend=None):
         # feature BatchNorm
         if lw["bn_feat"] is not None:
             flat_pre, flat_dh = rec["pre"].view(nodes, 4 * n), dh.view(nodes, 4 * n)
-            sum_g = be.colsum(flat_dh)
-            sum_gx = be.colsum(flat_dh, flat_pre, 2)
+            sum_g, sum_gx = colsum2(flat_dh, None, 0, flat_dh, flat_pre, 2)
             c = be.bn_backward_coeffs(lw["bn_feat"], rec["bn_feat"], n, float(nodes), 1.0, sum_g, sum_gx, bn_training)
             dpre = be.lincomb(flat_dh, flat_pre, c["A4"], c["B4"], c["C4"]).view(nodes, 4, n)
             g["bn_feat"] = dict(weight=c["dweight"], bias=c["dbias"])
@@ -202,8 +209,7 @@ def backward_train(W: Dict, saved: Dict, dpred, backend=None):
         # message BatchNorm folded through the sum over senders
         if lw["bn_msg"] is not None:
             flat_g, flat_raw = dagg.view(nodes, 4 * n), rec["agg_raw"].view(nodes, 4 * n)
-            sum_g = be.colsum(flat_g)
-            sum_gx = be.colsum(flat_g, flat_raw, 2)
+            sum_g, sum_gx = colsum2(flat_g, None, 0, flat_g, flat_raw, 2)
             c = be.bn_backward_coeffs(lw["bn_msg"], rec["bn_msg"], n, float(E), float(deg), sum_g, sum_gx, bn_training)
             g["bn_msg"] = dict(weight=c["dweight"], bias=c["dbias"])
             bn_a, bn_b, bn_c = c["bn_a"], c["bn_b"], c["bn_c"]

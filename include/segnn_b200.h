@@ -227,6 +227,13 @@ int segnn_counter_add(int* counter, int delta, segnn_stream_t stream);
 int64_t segnn_colsum_workspace(int64_t rows, int cols);
 int segnn_colsum(const float* x, const float* y, int64_t rows, int cols, int mode, float* workspace, float* out,
                  segnn_stream_t stream);
+/* Two column sums in one call: (xa, ya, mode_a) -> out_a [cols_a] and (xb, yb, mode_b) -> out_b [cols_b]; up to 2048
+ * rows each they are ONE launch (train-mode BatchNorm statistics come in pairs: sum / sum of squares in the forward,
+ * sum g / sum g*x in the backward; e3nn BatchNorm, segnn.py:233-235), otherwise two segnn_colsum calls that share
+ * `workspace` (max of the two segnn_colsum_workspace sizes).  Same sums bit for bit as segnn_colsum. */
+int segnn_colsum2(const float* xa, const float* ya, int64_t rows_a, int cols_a, int mode_a, float* out_a,
+                  const float* xb, const float* yb, int64_t rows_b, int cols_b, int mode_b, float* out_b,
+                  float* workspace, segnn_stream_t stream);
 
 /* out[r][c] = A[c]*dy[r][c] + B[c]*x[r][c] + C[c] (x/B and C may be NULL): train-mode BatchNorm forward
  * (dy := pre-norm features) and backward with the batch-statistics terms folded into per-column coefficients. */

@@ -26,7 +26,7 @@ HIDDEN, LAYERS, NBODY = 192, 6, 100
 FLOP_PER_EDGE_MSG2 = 20 * (HIDDEN // 2) ** 2       # 184,320: irreducible per-edge contraction
 FLOP_PER_EDGE_REFERENCE = 554_880                   # msg1 + msg2 in the reference's formulation
 K3_DRAM_BYTES_PER_LAUNCH = 945_620_224 + 151_324_416  # measured with ncu on this workload (1024 sims x 100 bodies)
-K3_DRAM_BYTES_PER_LAUNCH_PACKED = 473_770_752 + 140_515_840  # packed-half mode: fp16 projections
+K3_DRAM_BYTES_PER_LAUNCH_PACKED = 474_707_712 + 71_970_816  # packed-half mode: fp16 projections in, fp16 aggregate rows out
 
 
 def synthetic_system(batch, n, seed):
@@ -569,8 +569,11 @@ def main():
                          "traffic": (K3_DRAM_BYTES_PER_LAUNCH_PACKED if mode == "fp16p" else K3_DRAM_BYTES_PER_LAUNCH)
                          if (mode in ("bf16", "fp16", "fp16p") and B == 1024) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                           "(profiles/r1_v15_ncu_full_summary.json); algorithmic P + Q + agg bytes = "
-                                           + ("6.3e8 (fp16 projections)" if mode == "fp16p" else "1.10e9"),
+                                           "(" + ("profiles/r2_k3_final2_ncu_summary.json" if mode == "fp16p" else
+                                                  "profiles/r1_v15_ncu_full_summary.json")
+                                           + "); algorithmic P + Q + agg bytes = "
+                                           + ("5.5e8 (fp16 projections in, fp16 aggregate out)" if mode == "fp16p"
+                                              else "1.10e9"),
                          "peak_source": peak_src + ", bf16 dense sustained",
                          "flop_per_edge": FLOP_PER_EDGE_MSG2, "edges_per_launch": edges,
                          "avg_launch_ms": k3_ms, "launches_timed": len(k3_events),

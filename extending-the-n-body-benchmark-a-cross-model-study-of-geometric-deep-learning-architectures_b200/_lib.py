@@ -28,6 +28,8 @@ PROTOTYPES = {
     "segnn_edge_index": (_int, [_int, _int, _ptr, _ptr]),
     "segnn_edge_attr": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_prep_fwd": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_edge_attr_lmax": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr]),
+    "segnn_prep_fwd_lmax": (_int, [_ptr, _ptr, _int, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_embed_fwd": (_int, [_ptr, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr]),
     "segnn_node_gemm": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _ptr]),
     "segnn_node_gemm_tc": (_int, [_ptr, _ptr, _int, _int, _ptr, _ptr, _ptr, _int, _int, _ptr, _ptr, _int, _int, _ptr]),

@@ -9,7 +9,7 @@
 namespace segnn {
 
 constexpr int kInstrInts = 9;    // off1, mul1, dim1, off2, dim2, offo, mulo, dimo, woff
-constexpr int kCgFloats = 75;    // [5][3][5] coupling (net coefficient folded), row-major (i, j, k)
+constexpr int kCgFloats = 125;   // [5][5][5] coupling (net coefficient folded), row-major (i, j, k)
 
 // out[row][c] = bias[c] + sum_{instructions writing c} sum_u W[u][w] * sum_{i,j} C[i][j][k] x1[row][u, i] x2[row][j]
 __global__ void generic_tp_kernel(const float* __restrict__ x1, int d1, const float* __restrict__ x2, int d2,
@@ -36,7 +36,7 @@ __global__ void generic_tp_kernel(const float* __restrict__ x1, int d1, const fl
       for (int i = 0; i < 5; ++i) {
         float s = 0.f;
         if (i < dim1)
-          for (int j = 0; j < dim2; ++j) s = fmaf(C[(i * 3 + j) * 5 + k], b[off2 + j], s);
+          for (int j = 0; j < dim2; ++j) s = fmaf(C[(i * 5 + j) * 5 + k], b[off2 + j], s);
         m[i] = s;
       }
       const float* W = weights + woff + w;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256)
           for (int i = 0; i < 5; ++i) {
             float sm = 0.f;
             if (i < dim1)
-              for (int j = 0; j < dim2; ++j) sm = fmaf(C[(i * 3 + j) * 5 + k], x2s[r * d2 + off2 + j], sm);
+              for (int j = 0; j < dim2; ++j) sm = fmaf(C[(i * 5 + j) * 5 + k], x2s[r * d2 + off2 + j], sm);
             m[r][i] = sm;
           }
         const float* W = weights + woff + w;
@@ -173,7 +173,7 @@ __global__ void generic_tp_expand_kernel(const float* __restrict__ x1, int d1, c
         const float xb = xv * b[j];
 #pragma unroll
         for (int k = 0; k < 5; ++k)
-          if (k < dimo) acc[k] = fmaf(C[(i * 3 + j) * 5 + k], xb, acc[k]);
+          if (k < dimo) acc[k] = fmaf(C[(i * 5 + j) * 5 + k], xb, acc[k]);
       }
     }
 #pragma unroll
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128)
       const int* in = pairs + q * kPairInts;
       float m = 0.f;
       if (i < in[3] && k < in[2])
-        for (int j = 0; j < in[5]; ++j) m = fmaf(cg[q * kCgFloats + (i * 3 + j) * 5 + k], at[in[4] + j], m);
+        for (int j = 0; j < in[5]; ++j) m = fmaf(cg[q * kCgFloats + (i * 5 + j) * 5 + k], at[in[4] + j], m);
       M[q][i * 5 + k] = m;
     }
     for (int t = threadIdx.x; t < n_adds * 5; t += blockDim.x) {
@@ -342,6 +342,106 @@ __global__ void generic_aggregate_kernel(const float* __restrict__ m, int B, int
       s += m[e * D + c];
     }
     agg[idx] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// O3Transform for lmax_attr <= 2 (o3_building_blocks.py:230-278): e3nn 'integral' harmonics of the unit vector, degrees
+// 0..lmax in e3nn's component order; l = 2: sqrt(15) xz, sqrt(15) xy, sqrt(5) (y^2 - (x^2 + z^2) / 2), sqrt(15) yz,
+// sqrt(15) / 2 (z^2 - x^2), all over sqrt(4 pi).  The fused kernels keep lmax_attr = 1 in registers; these feed the
+// table-driven kernels above.
+// ------------------------------------------------------------------------------------------------
+constexpr float kY2a = 1.0925484305920792f;  // sqrt(15 / (4 pi))
+constexpr float kY2b = 0.6307831305050401f;  // sqrt(5 / (4 pi))
+
+__device__ __forceinline__ void harmonics_l2(float x, float y, float z, float* o) {
+  o[0] = kY2a * x * z;
+  o[1] = kY2a * x * y;
+  o[2] = kY2b * (y * y - 0.5f * (x * x + z * z));
+  o[3] = kY2a * y * z;
+  o[4] = 0.5f * kY2a * (z * z - x * x);
+}
+
+__global__ void edge_attr_lmax_kernel(const float* __restrict__ pos, const float* __restrict__ mass, int B, int N,
+                                      int lmax, float* __restrict__ edge_attr, float* __restrict__ add) {
+  const int d = (lmax + 1) * (lmax + 1);
+  const long long per = (long long)N * (N - 1);
+  const long long E = per * B;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const long long g = e / per;
+    const long long r = e - g * per;
+    const int a = (int)(r / (N - 1));
+    int b = (int)(r - (long long)a * (N - 1));
+    b += (b >= a);
+    const long long s = g * N + a, t = g * N + b;  // sender (source), receiver (target)
+    float ux, uy, uz, len;
+    unit_vec(pos[s * 3 + 0] - pos[t * 3 + 0], pos[s * 3 + 1] - pos[t * 3 + 1], pos[s * 3 + 2] - pos[t * 3 + 2], ux,
+             uy, uz, len);
+    float* o = edge_attr + e * d;
+    o[0] = kY0;
+    if (lmax >= 1) {
+      o[1] = kY1 * ux;
+      o[2] = kY1 * uy;
+      o[3] = kY1 * uz;
+    }
+    if (lmax >= 2) harmonics_l2(ux, uy, uz, o + 4);
+    add[e * 2 + 0] = len;
+    add[e * 2 + 1] = mass[s] * mass[t];
+  }
+}
+
+// node_attr = mean over the senders j of Y(r_j - r_i) + Y(v_i), l = 0 slot set to 1 (segnn.py:148); x as in K1.
+// One thread per receiver, senders read through L1 / L2 (this path is the checker-grade generic one, not tuned).
+__global__ void prep_lmax_kernel(const float* __restrict__ pos, const float* __restrict__ vel, int B, int N, int lmax,
+                                 float* __restrict__ x_in, float* __restrict__ node_attr) {
+  const int d = (lmax + 1) * (lmax + 1);
+  const long long nodes = (long long)B * N;
+  for (long long node = blockIdx.x * (long long)blockDim.x + threadIdx.x; node < nodes;
+       node += (long long)gridDim.x * blockDim.x) {
+    const long long base = (node / N) * N;
+    const int i = (int)(node - base);
+    const float px = pos[node * 3 + 0], py = pos[node * 3 + 1], pz = pos[node * 3 + 2];
+    float s1[3] = {0.f, 0.f, 0.f}, s2[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      float ux, uy, uz, len, h[5];
+      unit_vec(pos[(base + j) * 3 + 0] - px, pos[(base + j) * 3 + 1] - py, pos[(base + j) * 3 + 2] - pz, ux, uy, uz,
+               len);
+      s1[0] += ux;
+      s1[1] += uy;
+      s1[2] += uz;
+      if (lmax >= 2) {
+        harmonics_l2(ux, uy, uz, h);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s2[k] += h[k];
+      }
+    }
+    const float vx = vel[node * 3 + 0], vy = vel[node * 3 + 1], vz = vel[node * 3 + 2];
+    float ux, uy, uz, vlen;
+    unit_vec(vx, vy, vz, ux, uy, uz, vlen);
+    const float inv_deg = N > 1 ? 1.0f / (float)(N - 1) : 0.0f;
+    float* o = node_attr + node * d;
+    o[0] = 1.0f;
+    if (lmax >= 1) {
+      o[1] = kY1 * (s1[0] * inv_deg) + kY1 * ux;
+      o[2] = kY1 * (s1[1] * inv_deg) + kY1 * uy;
+      o[3] = kY1 * (s1[2] * inv_deg) + kY1 * uz;
+    }
+    if (lmax >= 2) {
+      float h[5];
+      harmonics_l2(ux, uy, uz, h);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) o[4 + k] = s2[k] * inv_deg + h[k];
+    }
+    const float m = (px + py + pz) / 3.0f;  // reference quirk: mean over xyz of the node (o3_building_blocks.py:274)
+    float* x = x_in + node * 7;
+    x[0] = px - m;
+    x[1] = py - m;
+    x[2] = pz - m;
+    x[3] = vx;
+    x[4] = vy;
+    x[5] = vz;
+    x[6] = vlen;
   }
 }
 
@@ -468,6 +568,28 @@ int segnn_generic_aggregate(const float* m, int B, int N, int D, float* agg, seg
   if (B == 0) return SEGNN_OK;
   SEGNN_CHECK_ARG(m && agg, "null pointer");
   generic_aggregate_kernel<<<generic_grid((long long)B * N * D), 256, 0, (cudaStream_t)stream>>>(m, B, N, D, agg);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_edge_attr_lmax(const float* pos, const float* mass, int B, int N, int lmax_attr, float* edge_attr, float* add,
+                         segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(B >= 0 && N >= 2 && lmax_attr >= 0 && lmax_attr <= 2, "bad sizes (lmax_attr in 0..2)");
+  if (B == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pos && mass && edge_attr && add, "null pointer");
+  edge_attr_lmax_kernel<<<generic_grid((long long)B * N * (N - 1)), 256, 0, (cudaStream_t)stream>>>(
+      pos, mass, B, N, lmax_attr, edge_attr, add);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_prep_fwd_lmax(const float* pos, const float* vel, int B, int N, int lmax_attr, float* x_in, float* node_attr,
+                        segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(B >= 0 && N >= 1 && lmax_attr >= 0 && lmax_attr <= 2, "bad sizes (lmax_attr in 0..2)");
+  if (B == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pos && vel && x_in && node_attr, "null pointer");
+  prep_lmax_kernel<<<generic_grid((long long)B * N), 256, 0, (cudaStream_t)stream>>>(pos, vel, B, N, lmax_attr, x_in,
+                                                                                    node_attr);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

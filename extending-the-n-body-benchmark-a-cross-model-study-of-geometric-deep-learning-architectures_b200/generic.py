@@ -1,6 +1,6 @@
 """Generic-irreps forward of the SEGNN modules (fp32, inference): the reference's own formulation -- gathered message
 inputs, one tensor product per call, e3nn Gate, BatchNorm (eval), scatter-sum -- on plain CUDA kernels
-(csrc/segnn_generic.cu) that accept any hidden irreps with lmax_attr = 1. It gives parity coverage for configurations
+(csrc/segnn_generic.cu) that accept any hidden irreps with l <= 2 and lmax_attr <= 2. It gives parity coverage for configurations
 the fused kernels are not specialised for (lmax_h = 2, BASELINE config 3); per-edge tensors live in HBM here, as in the
 reference. Per-edge tensor products run as expansion kernel + plain fp32 library GEMM + scatter kernel (the weight
 contraction is a plain GEMM once the coupling with the edge attribute is applied); node-level ones as one kernel.
@@ -41,14 +41,14 @@ class TensorProductPlan:
         instr, cgs = [], []
         for ins in tp.instructions:
             l1, l2, lo = ins["ls"]
-            if max(l1, lo) > 2 or l2 > 1 or ins["shape"][1] != 1:
-                raise NotImplementedError("generic tensor product: l <= 2 for features, lmax_attr = 1, attribute "
+            if max(l1, l2, lo) > 2 or ins["shape"][1] != 1:
+                raise NotImplementedError("generic tensor product: l <= 2 for features and attributes, attribute "
                                           "multiplicity 1")
             o1, m1, d1 = s1[ins["i1"]]
             o2, _, d2 = s2[ins["i2"]]
             oo, mo, do = so[ins["io"]]
             instr.append([o1, m1, d1, o2, d2, oo, mo, do, ins["offset"]])
-            c = np.zeros((5, 3, 5), dtype=np.float64)
+            c = np.zeros((5, 5, 5), dtype=np.float64)
             # net path coefficient: e3nn 'component'/'element' path weight x the reference's sqrt_k_correction
             c[:d1, :d2, :do] = math.sqrt(2 * lo + 1) * real_wigner_3j(l1, l2, lo)
             cgs.append(c)
@@ -148,12 +148,12 @@ class HoistedMessage1Plan:
         yinstr, ycg, slots, adds, cgs_add, yoff = [], [], {}, [], [], 0
         for ins in tp.instructions:
             l1, l2, lo = ins["ls"]
-            if max(l1, lo) > 2 or l2 > 1 or ins["shape"][1] != 1:
-                raise NotImplementedError("generic tensor product: l <= 2 for features, lmax_attr = 1")
+            if max(l1, l2, lo) > 2 or ins["shape"][1] != 1:
+                raise NotImplementedError("generic tensor product: l <= 2 for features and attributes")
             o1, m1, d1 = s1[ins["i1"]]
             o2, _, d2 = s2[ins["i2"]]
             oo, mo, do = so[ins["io"]]
-            c = np.zeros((5, 3, 5), dtype=np.float64)
+            c = np.zeros((5, 5, 5), dtype=np.float64)
             c[:d1, :d2, :do] = math.sqrt(2 * lo + 1) * real_wigner_3j(l1, l2, lo)
             if ins["i1"] >= 2 * nh:  # additional_message_features block (scalars)
                 if l1 != 0:
@@ -162,7 +162,7 @@ class HoistedMessage1Plan:
                 cgs_add.append(c)
                 continue
             role = ins["i1"] // nh  # 0: x_i (receiver), 1: x_j (sender)
-            ident = np.zeros((5, 3, 5), dtype=np.float64)
+            ident = np.zeros((5, 5, 5), dtype=np.float64)
             for i in range(d1):
                 ident[i, 0, i] = 1.0
             yinstr.append([o1 - role * D, m1, d1, 0, 1, yoff, mo, d1, ins["offset"]])
@@ -434,9 +434,9 @@ class GenericRunner:
         if model.training and model.norm == "batch":
             raise NotImplementedError("the generic-irreps path implements eval-mode BatchNorm only")
         D = model.hidden_irreps.dim
-        x_in, attr = ops.prep(pos, vel, B, N)
+        x_in, attr = ops.prep(pos, vel, B, N, model.lmax_attr)
         if not self.use_l2_rows:
-            ea, add = ops.edge_attr(pos, mass, B, N)
+            ea, add = ops.edge_attr(pos, mass, B, N, model.lmax_attr)
             E = ea.shape[0]
         x = self.embed.run(x_in, attr)
         per_layer = [x]

@@ -35,7 +35,8 @@ class GraphBatch:
             if name == "edge_index":
                 val = ops.edge_index(self.num_graphs, self.n_nodes, self.pos.device)
             else:
-                ea, add = ops.edge_attr(self.pos, self.mass, self.num_graphs, self.n_nodes)
+                ea, add = ops.edge_attr(self.pos, self.mass, self.num_graphs, self.n_nodes,
+                                        int(self.__dict__.get("lmax_attr", 1)))
                 self.__dict__["edge_attr"] = ea.to(self.pos.dtype)
                 self.__dict__["additional_message_features"] = add.to(self.pos.dtype)
                 return self.__dict__[name]

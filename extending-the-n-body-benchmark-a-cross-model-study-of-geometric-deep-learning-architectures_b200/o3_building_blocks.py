@@ -140,8 +140,8 @@ class O3Transform:
     implicit; they are recomputed in registers inside the fused edge kernel."""
 
     def __init__(self, lmax_attr, use_force_input=False):
-        if int(lmax_attr) != 1:
-            raise NotImplementedError("the accelerated SEGNN path is built for lmax_attr = 1")
+        if int(lmax_attr) not in (0, 1, 2):
+            raise NotImplementedError("O3Transform is built for lmax_attr <= 2")
         if use_force_input:
             raise NotImplementedError("use_force_input is never set on the configured path")
         self.attr_irreps = Irreps.spherical_harmonics(int(lmax_attr))
@@ -150,7 +150,8 @@ class O3Transform:
     def __call__(self, graph):
         b, n = infer_graph_shape(graph)
         graph.num_graphs, graph.n_nodes = b, n
-        x, attr = ops.prep(graph.pos, graph.vel, b, n)
+        graph.lmax_attr = self.attr_irreps.lmax  # degree of the lazily materialised edge attributes
+        x, attr = ops.prep(graph.pos, graph.vel, b, n, self.attr_irreps.lmax)
         graph.x = x.to(graph.pos.dtype)
         graph.node_attr = attr.to(graph.pos.dtype)
         return graph

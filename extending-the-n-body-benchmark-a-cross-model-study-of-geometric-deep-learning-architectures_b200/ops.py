@@ -85,27 +85,35 @@ def instance_norm(x: torch.Tensor, graph_ptr: torch.Tensor, blocks: torch.Tensor
     return out
 
 
-def edge_attr(pos: torch.Tensor, mass: torch.Tensor, batch_size: int, num_nodes: int):
+def edge_attr(pos: torch.Tensor, mass: torch.Tensor, batch_size: int, num_nodes: int, lmax_attr: int = 1):
     pos, mass = _f32(pos, "pos"), _f32(mass, "mass").reshape(-1)
     E = batch_size * num_nodes * (num_nodes - 1)
-    ea = torch.empty((E, 4), dtype=torch.float32, device=pos.device)
+    ea = torch.empty((E, (lmax_attr + 1) ** 2), dtype=torch.float32, device=pos.device)
     add = torch.empty((E, 2), dtype=torch.float32, device=pos.device)
     with torch.cuda.device(pos.device):
-        check(lib.segnn_edge_attr(_p(pos), _p(mass), batch_size, num_nodes, _p(ea), _p(add), _stream()),
-              "segnn_edge_attr")
+        if lmax_attr == 1:
+            check(lib.segnn_edge_attr(_p(pos), _p(mass), batch_size, num_nodes, _p(ea), _p(add), _stream()),
+                  "segnn_edge_attr")
+        else:
+            check(lib.segnn_edge_attr_lmax(_p(pos), _p(mass), batch_size, num_nodes, int(lmax_attr), _p(ea), _p(add),
+                                           _stream()), "segnn_edge_attr_lmax")
     _bump()
     return ea, add
 
 
-def prep(pos: torch.Tensor, vel: torch.Tensor, batch_size: int, num_nodes: int):
+def prep(pos: torch.Tensor, vel: torch.Tensor, batch_size: int, num_nodes: int, lmax_attr: int = 1):
     pos, vel = _f32(pos, "pos"), _f32(vel, "vel")
     nodes = batch_size * num_nodes
     assert pos.shape == (nodes, 3) and vel.shape == (nodes, 3), (pos.shape, vel.shape, nodes)
     x_in = torch.empty((nodes, 7), dtype=torch.float32, device=pos.device)
-    attr = torch.empty((nodes, 4), dtype=torch.float32, device=pos.device)
+    attr = torch.empty((nodes, (lmax_attr + 1) ** 2), dtype=torch.float32, device=pos.device)
     with torch.cuda.device(pos.device):
-        check(lib.segnn_prep_fwd(_p(pos), _p(vel), batch_size, num_nodes, _p(x_in), _p(attr), _stream()),
-              "segnn_prep_fwd")
+        if lmax_attr == 1:
+            check(lib.segnn_prep_fwd(_p(pos), _p(vel), batch_size, num_nodes, _p(x_in), _p(attr), _stream()),
+                  "segnn_prep_fwd")
+        else:
+            check(lib.segnn_prep_fwd_lmax(_p(pos), _p(vel), batch_size, num_nodes, int(lmax_attr), _p(x_in), _p(attr),
+                                          _stream()), "segnn_prep_fwd_lmax")
     _bump()
     return x_in, attr
 

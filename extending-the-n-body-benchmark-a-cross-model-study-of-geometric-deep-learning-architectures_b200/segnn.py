@@ -75,7 +75,9 @@ class SEGNNLayer(nn.Module):
             raise NotImplementedError(f"SEGNN layers take hidden -> hidden irreps with 2x0e message features; got "
                                       f"input={input_irreps}, hidden={hidden_irreps}, additional={add}")
         # the fused kernels are specialised for n x0e + n x1o (lmax_h = 1); anything else runs the generic path
-        self.fused = list(hidden_irreps) == [(hidden_irreps[0][0], 0, 1), (hidden_irreps[0][0], 1, -1)]
+        # with the steering attributes 1x0e + 1x1o (lmax_attr = 1)
+        self.fused = list(hidden_irreps) == [(hidden_irreps[0][0], 0, 1), (hidden_irreps[0][0], 1, -1)] and \
+            list(edge_attr_irreps) == [(1, 0, 1), (1, 1, -1)] and list(node_attr_irreps) == [(1, 0, 1), (1, 1, -1)]
         self.n = hidden_irreps[0][0]
 
     # -- weight packing -----------------------------------------------------------------------------------------
@@ -227,8 +229,8 @@ class SEGNN(nn.Module):
         super().__init__()
         if task != "node":
             raise NotImplementedError("only task='node' is on the N-body path")
-        if int(lmax_attr) != 1 or int(lmax_h) not in (1, 2):
-            raise NotImplementedError(f"built for lmax_attr = 1 and lmax_h in (1, 2) (got {lmax_h}, {lmax_attr})")
+        if int(lmax_attr) not in (1, 2) or int(lmax_h) not in (1, 2):
+            raise NotImplementedError(f"built for lmax_attr in (1, 2) and lmax_h in (1, 2) (got {lmax_h}, {lmax_attr})")
         if Irreps(str(input_irreps)) != Irreps("2x1o+1x0e") or Irreps(str(output_irreps)) != Irreps("2x1o"):
             raise NotImplementedError("kernels are built for the N-body irreps: input 2x1o+1x0e, output 2x1o")
         self.hidden_features, self.lmax_h, self.lmax_attr, self.num_layers = hidden_features, lmax_h, lmax_attr, num_layers
@@ -249,8 +251,9 @@ class SEGNN(nn.Module):
         self.pre_pool2 = O3TensorProduct(h, Irreps(str(output_irreps)), self.node_attr_irreps)
         self._pack_key = None
         self._packed = None
-        # lmax_h = 1 runs the fused kernels (compute_mode 'fp32' / 'bf16'); other hidden irreps (lmax_h = 2, BASELINE
-        # config 3) run the generic-irreps fp32 path (generic.py), which is also selectable with compute_mode='generic'
+        # lmax_h = 1 with lmax_attr = 1 runs the fused kernels (compute_mode 'fp32' / 'bf16'); other hidden irreps
+        # (lmax_h = 2, BASELINE config 3) and lmax_attr = 2 run the generic-irreps fp32 path (generic.py), which is also
+        # selectable with compute_mode='generic'
         self.fused = all(layer.fused for layer in self.layers)
         self._generic = None
 

@@ -75,6 +75,15 @@ int segnn_edge_attr(const float* pos, const float* mass, int B, int N, float* ed
 int segnn_prep_fwd(const float* pos, const float* vel, int B, int N, float* x_in, float* node_attr,
                    segnn_stream_t stream);
 
+/* models/segnn/o3_building_blocks.py:230-278 (O3Transform) for lmax_attr in 0..2, feeding the generic-irreps kernels
+ * (segnn_generic_*): edge_attr [E,(lmax_attr+1)^2] = Y_0..lmax(pos[src]-pos[tgt]) ('integral', normalised, e3nn
+ * component order), add [E,2] = (|r|, m_src*m_tgt); x_in [nodes,7] as segnn_prep_fwd, node_attr
+ * [nodes,(lmax_attr+1)^2] = mean_j Y(r_j - r_i) + Y(v_i) with node_attr[:,0] = 1 (models/segnn/segnn.py:148). */
+int segnn_edge_attr_lmax(const float* pos, const float* mass, int B, int N, int lmax_attr, float* edge_attr, float* add,
+                         segnn_stream_t stream);
+int segnn_prep_fwd_lmax(const float* pos, const float* vel, int B, int N, int lmax_attr, float* x_in, float* node_attr,
+                        segnn_stream_t stream);
+
 /* ---- K2: embedding tensor product ---------------------------------------------------------------- */
 
 /* models/segnn/segnn.py:170 embedding_layer = O3TensorProduct(2x1o+1x0e -> h, node_attr).

@@ -95,9 +95,9 @@ def make_wigner_fixture():
     save("ref_wigner.pt", out)
 
 
-def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True):
+def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True, lmax_attr=1):
     torch.manual_seed(seed)
-    model = SEGNN(hidden_features=H, lmax_h=lmax_h, num_layers=L).double()
+    model = SEGNN(hidden_features=H, lmax_h=lmax_h, lmax_attr=lmax_attr, num_layers=L).double()
     sd = model.state_dict()
     extra_keys = sorted(k for k in sd if "output_mask" in k or k.endswith("num_batches_tracked"))
     shapes = {k: tuple(v.shape) for k, v in sd.items() if k not in extra_keys}
@@ -114,7 +114,7 @@ def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True):
         mods = [model.embedding_layer] + list(model.layers) + [model.pre_pool1]
         for m in mods:
             hooks.append(m.register_forward_hook(lambda _m, _i, o: layers.append(o.detach().clone())))
-        g = ref_graph(pos, vel, mass, B, N)
+        g = ref_graph(pos, vel, mass, B, N, lmax_attr)
         g.y = y
         transform = {k: getattr(g, k).detach().clone() for k in ("x", "node_attr", "edge_attr",
                                                                  "additional_message_features", "edge_index")}
@@ -136,7 +136,10 @@ def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True):
     with torch.no_grad():
         ev = forward(False)
     tr = forward(True)
-    fx = {"kind": KIND, "config": dict(hidden_features=H, lmax_h=lmax_h, num_layers=L, B=B, N=N, charged=charged),
+    config = dict(hidden_features=H, lmax_h=lmax_h, num_layers=L, B=B, N=N, charged=charged)
+    if lmax_attr != 1:  # the key is absent from the lmax_attr = 1 fixtures written before the option existed
+        config["lmax_attr"] = lmax_attr
+    fx = {"kind": KIND, "config": config,
           "hidden_irreps": str(model.hidden_irreps), "num_params": sum(p.numel() for p in model.parameters()),
           "serializable": {k: v for k, v in model.get_serializable_attributes().items()},
           "state_keys": list(sd.keys()), "extra_keys": extra_keys,
@@ -340,8 +343,18 @@ def make_checkpoint_fixture():
     print("wrote", out_dir, os.listdir(out_dir))
 
 
+def make_lmax_attr2_fixtures():
+    """lmax_attr = 2 (l <= 2 steering attributes, models/segnn/segnn.py:22,36,47): the branch no BASELINE configuration
+    takes; written separately so the fixtures above stay byte-identical."""
+    run_model_case("h32_a2_n6", H=32, lmax_h=1, L=2, B=2, N=6, seed=5, lmax_attr=2)
+    run_model_case("h32_l2_a2_n5", H=32, lmax_h=2, L=2, B=2, N=5, seed=6, lmax_attr=2)
+
+
 if __name__ == "__main__":
     print("third-party provider:", KIND)
+    if sys.argv[1:] == ["lmax_attr2"]:
+        make_lmax_attr2_fixtures()
+        sys.exit(0)
     make_graph_fixture()
     make_wigner_fixture()
     make_tp_fixture()
@@ -352,3 +365,4 @@ if __name__ == "__main__":
     rollout = make_rollout_fixture(model_a)
     make_sim_and_macro_fixture(rollout)
     make_checkpoint_fixture()
+    make_lmax_attr2_fixtures()

@@ -495,6 +495,68 @@ def test_generic_irreps_path_matches_oracle(H, lmax_h, L, B, N, l2_rows, monkeyp
             assert float((fused - out).abs().max() / out.abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("B,N", [(3, 5), (2, 40), (1, 2)])
+def test_o3_transform_lmax_attr2_matches_oracle(B, N):
+    """O3Transform with lmax_attr = 2 (o3_building_blocks.py:230-278): l <= 2 'integral' harmonics of the edge vectors,
+    node attributes = mean over the senders + harmonics of the velocity (segnn_edge_attr_lmax / segnn_prep_fwd_lmax)."""
+    pos, vel, mass = O.synthetic_system(B, N, seed=11)
+    vel[0, 0] = 0.0  # a body at rest: F.normalize gives the zero vector, every l >= 1 harmonic is 0
+    ref = O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N, 2)
+    g = S.O3Transform(2)(gpu_graph(pos, vel, mass, B, N))
+    assert g.node_attr.shape == (B * N, 9) and g.edge_attr.shape == (B * N * (N - 1), 9)
+    assert torch.equal(g.edge_index.cpu(), ref.edge_index)
+    assert rel(g.x, ref.x) < 2e-6 and rel(g.edge_attr, ref.edge_attr) < 2e-6
+    assert rel(g.additional_message_features, ref.additional_message_features) < 2e-6
+    assert float((g.node_attr.double().cpu()[:, 1:] - ref.node_attr[:, 1:]).abs().max()) < 2e-6
+    assert torch.all(g.node_attr[:, 0] == 1.0) or rel(g.node_attr[:, 0], ref.node_attr[:, 0]) < 2e-6
+
+
+@pytest.mark.parametrize("H,lmax_h,L,B,N", [(32, 1, 2, 3, 5), (64, 2, 2, 2, 6), (128, 1, 2, 2, 33), (96, 2, 1, 1, 40)])
+def test_lmax_attr2_matches_oracle(H, lmax_h, L, B, N):
+    """lmax_attr = 2 (steering attributes 1x0e + 1x1o + 1x2e, models/segnn/segnn.py:22,36,47): every tensor product of the
+    model through the table-driven generic kernels with [5][5][5] couplings; per-layer parity at the fp32 tolerance."""
+    torch.manual_seed(H + lmax_h)
+    om = O.SEGNN(hidden_features=H, num_layers=L, lmax_h=lmax_h, lmax_attr=2).eval()
+    O.perturb_bn_buffers(om, seed=5)
+    m = S.SEGNN(hidden_features=H, num_layers=L, lmax_h=lmax_h, lmax_attr=2)
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().eval()
+    assert not m.fused
+    pos, vel, mass = O.synthetic_system(B, N, seed=6)
+    with torch.no_grad():
+        ref, ref_layers = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N, 2),
+                             return_layers=True)
+        out, layers = m(gpu_graph(pos, vel, mass, B, N), return_layers=True)
+        print(f"lmax_attr=2 H={H} lmax_h={lmax_h}: per-layer", [f"{rel(a, b):.2e}" for a, b in zip(layers, ref_layers)],
+              f"out {rel(out, ref):.2e}")
+        for a, b in zip(layers, ref_layers):
+            assert rel(a, b) < 1e-5
+        assert rel(out, ref) < 1e-5
+        # the reference's formulation (gathered message input) agrees with the hoisted one
+        m._generic.hoist_message_layer_1 = False
+        out2 = m(gpu_graph(pos, vel, mass, B, N))
+        assert rel(out2, ref) < 1e-5
+    with pytest.raises(NotImplementedError):  # inference only, like every generic-irreps configuration
+        m.train()(gpu_graph(pos, vel, mass, B, N))
+
+
+def test_lmax_attr2_rollout_matches_oracle():
+    torch.manual_seed(10)
+    om = O.SEGNN(hidden_features=32, num_layers=2, lmax_h=1, lmax_attr=2).eval()
+    O.perturb_bn_buffers(om, seed=3)
+    m = S.SEGNN(hidden_features=32, num_layers=2, lmax_h=1, lmax_attr=2)
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().eval()
+    B, N, steps = 3, 5, 6
+    pos, vel, mass = O.synthetic_system(B, N, seed=4)
+    ref_loc, ref_vel = O.rollout(om, pos, vel, mass, steps)
+    roll = S.SelfFeedRollout(m, B, N, "cuda", max_frames=steps + 1)
+    roll.reset(pos, vel, mass)
+    tp, tv = roll.run(steps)
+    got_loc = tp.reshape(steps + 1, B, N, 3).permute(1, 0, 2, 3)
+    assert rel(got_loc, ref_loc) < 5e-5
+
+
 def test_generic_rollout_lmax2_matches_oracle():
     torch.manual_seed(9)
     om = O.SEGNN(hidden_features=32, num_layers=2, lmax_h=2).eval()

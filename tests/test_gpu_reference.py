@@ -26,7 +26,8 @@ def rel(a, b):
 
 def cuda_model(fx, train=False):
     c = fx["config"]
-    m = S.SEGNN(hidden_features=c["hidden_features"], lmax_h=c["lmax_h"], num_layers=c["num_layers"])
+    m = S.SEGNN(hidden_features=c["hidden_features"], lmax_h=c["lmax_h"], lmax_attr=c.get("lmax_attr", 1),
+                num_layers=c["num_layers"])
     m.load_state_dict(golden_state(fx["shapes"], fx["ranges"], fx["weight_seed"]))
     return m.float().cuda().train(train)
 
@@ -38,7 +39,7 @@ def graph(fx):
 
 
 def modes_for(m, N):
-    if m.lmax_h != 1:
+    if m.lmax_h != 1 or m.lmax_attr != 1:
         return ["generic"]
     tc = S.ops.tc_available() and m.n in S.ops.TC_MULTIPLICITIES
     return ["fp32"] + (["bf16", "fp16"] if tc else []) + (["fp16p"] if tc and N % 2 == 0 else [])
@@ -54,7 +55,7 @@ def test_edge_enumeration_matches_reference_bit_exact():
         assert torch.equal(got, case["edge_index"]), (case["B"], case["N"], case["k"])
 
 
-@pytest.mark.parametrize("case", ["h64_n5", "h192_n8", "h128_n12", "h32_l2_n6"])
+@pytest.mark.parametrize("case", ["h64_n5", "h192_n8", "h128_n12", "h32_l2_n6", "h32_a2_n6", "h32_l2_a2_n5"])
 def test_segnn_eval_per_layer_matches_reference(case):
     fx = load(f"ref_segnn_{case}.pt")
     c = fx["config"]
@@ -62,7 +63,7 @@ def test_segnn_eval_per_layer_matches_reference(case):
     assert str(m.hidden_irreps).replace(" ", "") == fx["hidden_irreps"]
     assert sum(p.numel() for p in m.parameters()) == fx["num_params"]
     ref = fx["eval"]
-    g = S.O3Transform(1)(graph(fx))
+    g = S.O3Transform(c.get("lmax_attr", 1))(graph(fx))
     tr = ref["transform"]
     assert torch.equal(g.edge_index.cpu(), tr["edge_index"])
     assert rel(g.x, tr["x"]) < 2e-6 and rel(g.edge_attr, tr["edge_attr"]) < 2e-6

@@ -98,6 +98,10 @@ PROTOTYPES = {
     "segnn_generic_gate": (_int, [_ptr, _c.c_int64, _int, _int, _int, _ptr, _ptr, _ptr]),
     "segnn_generic_message_input": (_int, [_ptr, _ptr, _int, _int, _int, _int, _ptr, _ptr]),
     "segnn_generic_aggregate": (_int, [_ptr, _int, _int, _int, _ptr, _ptr]),
+    "segnn_edge_attr_list": (_int, [_ptr, _ptr, _ptr, _c.c_int64, _int, _ptr, _ptr, _ptr]),
+    "segnn_generic_message_input_list": (_int, [_ptr, _ptr, _ptr, _c.c_int64, _int, _int, _ptr, _ptr]),
+    "segnn_segment_reduce": (_int, [_ptr, _ptr, _ptr, _c.c_int64, _int, _int, _ptr, _ptr]),
+    "segnn_prep_fwd_list": (_int, [_ptr, _ptr, _ptr, _c.c_int64, _int, _ptr, _ptr, _ptr]),
     "segnn_sim_gravity": (_int, [_ptr, _ptr, _ptr, _int, _int, _c.c_double, _c.c_double, _c.c_double, _int, _int, _ptr,
                                  _ptr, _ptr, _ptr]),
     "segnn_macros_counters": (_int, [_ptr, _ptr, _int, _int, _int, _int, _c.c_float, _c.c_float, _c.c_float, _ptr, _ptr,

@@ -445,6 +445,106 @@ __global__ void prep_lmax_kernel(const float* __restrict__ pos, const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Explicit edge lists (kNN graphs, utils/build_fully_connected_graph.py:42-80; num_neighbors < N - 1): the same
+// reference formulation with gathers through edge_index (row 0 = source j, row 1 = target i) and a deterministic
+// segment reduction over the edges of a target (CSR built by the host-side plumbing from a stable sort of the targets).
+// ------------------------------------------------------------------------------------------------
+__global__ void edge_attr_list_kernel(const float* __restrict__ pos, const float* __restrict__ mass,
+                                      const long long* __restrict__ ei, long long E, int lmax,
+                                      float* __restrict__ edge_attr, float* __restrict__ add) {
+  const int d = (lmax + 1) * (lmax + 1);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const long long s = ei[e], t = ei[E + e];
+    float ux, uy, uz, len;
+    unit_vec(pos[s * 3 + 0] - pos[t * 3 + 0], pos[s * 3 + 1] - pos[t * 3 + 1], pos[s * 3 + 2] - pos[t * 3 + 2], ux,
+             uy, uz, len);
+    float* o = edge_attr + e * d;
+    o[0] = kY0;
+    if (lmax >= 1) {
+      o[1] = kY1 * ux;
+      o[2] = kY1 * uy;
+      o[3] = kY1 * uz;
+    }
+    if (lmax >= 2) harmonics_l2(ux, uy, uz, o + 4);
+    add[e * 2 + 0] = len;
+    add[e * 2 + 1] = mass[s] * mass[t];
+  }
+}
+
+// out[e] = [x[target] | x[source] | add[e]]  (segnn.py:264-279: cat(x_i, x_j, additional_message_features))
+__global__ void message_input_list_kernel(const float* __restrict__ x, const float* __restrict__ add,
+                                          const long long* __restrict__ ei, long long E, int D, int d_add,
+                                          float* __restrict__ out) {
+  const int dout = 2 * D + d_add;
+  const long long total = E * dout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx / dout;
+    const int c = (int)(idx - e * dout);
+    float v;
+    if (c < D) v = x[ei[E + e] * D + c];
+    else if (c < 2 * D) v = x[ei[e] * D + (c - D)];
+    else v = add[e * d_add + (c - 2 * D)];
+    out[idx] = v;
+  }
+}
+
+// out[node][c] = sum (or mean; 0 for an empty segment) over k in [ptr[node], ptr[node + 1]) of values[order[k]][c], in
+// that order: the scatter of segnn.py:205 / o3_building_blocks.py:257-263 without atomics, run-to-run identical
+__global__ void segment_reduce_kernel(const float* __restrict__ values, const long long* __restrict__ order,
+                                      const long long* __restrict__ ptr, long long nodes, int D, int mean,
+                                      float* __restrict__ out) {
+  const long long total = nodes * D;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long node = idx / D;
+    const int c = (int)(idx - node * D);
+    const long long k0 = ptr[node], k1 = ptr[node + 1];
+    float s = 0.f;
+    for (long long k = k0; k < k1; ++k) s += values[order[k] * D + c];
+    if (mean && k1 > k0) s /= (float)(k1 - k0);
+    out[idx] = s;
+  }
+}
+
+// node_attr = mean_attr (scatter-mean of the incoming edge attributes) + Y(v), l = 0 slot set to 1; x as in K1
+__global__ void prep_list_kernel(const float* __restrict__ pos, const float* __restrict__ vel,
+                                 const float* __restrict__ mean_attr, long long nodes, int lmax,
+                                 float* __restrict__ x_in, float* __restrict__ node_attr) {
+  const int d = (lmax + 1) * (lmax + 1);
+  for (long long node = blockIdx.x * (long long)blockDim.x + threadIdx.x; node < nodes;
+       node += (long long)gridDim.x * blockDim.x) {
+    const float px = pos[node * 3 + 0], py = pos[node * 3 + 1], pz = pos[node * 3 + 2];
+    const float vx = vel[node * 3 + 0], vy = vel[node * 3 + 1], vz = vel[node * 3 + 2];
+    float ux, uy, uz, vlen;
+    unit_vec(vx, vy, vz, ux, uy, uz, vlen);
+    const float* ma = mean_attr + node * d;
+    float* o = node_attr + node * d;
+    o[0] = 1.0f;
+    if (lmax >= 1) {
+      o[1] = ma[1] + kY1 * ux;
+      o[2] = ma[2] + kY1 * uy;
+      o[3] = ma[3] + kY1 * uz;
+    }
+    if (lmax >= 2) {
+      float h[5];
+      harmonics_l2(ux, uy, uz, h);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) o[4 + k] = ma[4 + k] + h[k];
+    }
+    const float m = (px + py + pz) / 3.0f;  // o3_building_blocks.py:274
+    float* x = x_in + node * 7;
+    x[0] = px - m;
+    x[1] = py - m;
+    x[2] = pz - m;
+    x[3] = vx;
+    x[4] = vy;
+    x[5] = vz;
+    x[6] = vlen;
+  }
+}
+
 static inline int generic_grid(long long total) {
   long long b = (total + 255) / 256;
   const long long cap = 148LL * 64;
@@ -590,6 +690,50 @@ int segnn_prep_fwd_lmax(const float* pos, const float* vel, int B, int N, int lm
   SEGNN_CHECK_ARG(pos && vel && x_in && node_attr, "null pointer");
   prep_lmax_kernel<<<generic_grid((long long)B * N), 256, 0, (cudaStream_t)stream>>>(pos, vel, B, N, lmax_attr, x_in,
                                                                                     node_attr);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_edge_attr_list(const float* pos, const float* mass, const int64_t* edge_index, int64_t E, int lmax_attr,
+                         float* edge_attr, float* add, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(E >= 0 && lmax_attr >= 0 && lmax_attr <= 2, "bad sizes (lmax_attr in 0..2)");
+  if (E == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pos && mass && edge_index && edge_attr && add, "null pointer");
+  edge_attr_list_kernel<<<generic_grid(E), 256, 0, (cudaStream_t)stream>>>(
+      pos, mass, reinterpret_cast<const long long*>(edge_index), E, lmax_attr, edge_attr, add);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_generic_message_input_list(const float* x, const float* add, const int64_t* edge_index, int64_t E, int D,
+                                     int d_add, float* out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(E >= 0 && D >= 1 && d_add >= 0, "bad sizes");
+  if (E == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(x && edge_index && out && (d_add == 0 || add), "null pointer");
+  message_input_list_kernel<<<generic_grid(E * (2 * D + d_add)), 256, 0, (cudaStream_t)stream>>>(
+      x, add, reinterpret_cast<const long long*>(edge_index), E, D, d_add, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_segment_reduce(const float* values, const int64_t* order, const int64_t* ptr, int64_t nodes, int D, int mean,
+                         float* out, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && D >= 1, "bad sizes");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(values && order && ptr && out, "null pointer");
+  segment_reduce_kernel<<<generic_grid(nodes * D), 256, 0, (cudaStream_t)stream>>>(
+      values, reinterpret_cast<const long long*>(order), reinterpret_cast<const long long*>(ptr), nodes, D, mean, out);
+  SEGNN_CHECK_LAUNCH();
+  return SEGNN_OK;
+}
+
+int segnn_prep_fwd_list(const float* pos, const float* vel, const float* mean_attr, int64_t nodes, int lmax_attr,
+                        float* x_in, float* node_attr, segnn_stream_t stream) {
+  SEGNN_CHECK_ARG(nodes >= 0 && lmax_attr >= 0 && lmax_attr <= 2, "bad sizes (lmax_attr in 0..2)");
+  if (nodes == 0) return SEGNN_OK;
+  SEGNN_CHECK_ARG(pos && vel && mean_attr && x_in && node_attr, "null pointer");
+  prep_list_kernel<<<generic_grid(nodes), 256, 0, (cudaStream_t)stream>>>(pos, vel, mean_attr, nodes, lmax_attr, x_in,
+                                                                          node_attr);
   SEGNN_CHECK_LAUNCH();
   return SEGNN_OK;
 }

@@ -429,6 +429,45 @@ class GenericRunner:
         self.pool2 = tp(model.pre_pool2)
 
     @torch.no_grad()
+    def forward_edge_list(self, pos, vel, mass, edge_index, return_layers: bool = False):
+        """SEGNN.forward (segnn.py:150-189) on an explicit edge list -- the kNN graphs build_graph_with_knn returns for
+        num_neighbors < N - 1 (utils/build_fully_connected_graph.py:42-80): gathered message input, one tensor product
+        per call, eval BatchNorm per edge, deterministic segment sum over the incoming edges of every node."""
+        model = self.model
+        if model.training and model.norm == "batch":
+            raise NotImplementedError("the generic-irreps path implements eval-mode BatchNorm only")
+        D, nodes = model.hidden_irreps.dim, pos.shape[0]
+        edge_index = edge_index.to(device=pos.device, dtype=torch.int64).contiguous()
+        E = edge_index.shape[1]
+        order, ptr = ops.edge_list_csr(edge_index, nodes)
+        ea, add = ops.edge_attr_list(pos, mass, edge_index, model.lmax_attr)
+        x_in, attr = ops.prep_list(pos, vel, ea, order, ptr, model.lmax_attr)
+        x = self.embed.run(x_in, attr)
+        per_layer = [x]
+        for layer, pl in zip(model.layers, self.layers):
+            inp = torch.empty((E, 2 * D + 2), dtype=torch.float32, device=pos.device)
+            with torch.cuda.device(pos.device):
+                check(lib.segnn_generic_message_input_list(_p(x), _p(add), _p(edge_index), E, D, 2, _p(inp),
+                                                           ops._stream()), "segnn_generic_message_input_list")
+            ops._bump()
+            m = pl["g_msg1"].run(pl["msg1"].run(inp, ea))
+            m = pl["g_msg2"].run(pl["msg2"].run(m, ea))
+            if layer.message_norm is not None:  # per edge, as the reference applies it (segnn.py:281-283)
+                mul, addc = _bn_eval_columns(layer.message_norm, layer.hidden_irreps)
+                m = ops.lincomb(m, None, mul, None, addc)
+            agg = ops.segment_reduce(m, order, ptr)
+            u = pl["g_upd1"].run(pl["upd1"].run(torch.cat([x, agg], dim=1).contiguous(), attr))
+            u = pl["upd2"].run(u, attr)
+            x = ops.add3(x, u)
+            if layer.feature_norm is not None:
+                mul, addc = _bn_eval_columns(layer.feature_norm, layer.hidden_irreps)
+                x = ops.lincomb(x, None, mul, None, addc)
+            per_layer.append(x)
+        h = self.g_pool1.run(self.pool1.run(x, attr))
+        pred = self.pool2.run(h, attr)
+        return (pred, per_layer) if return_layers else pred
+
+    @torch.no_grad()
     def forward(self, pos, vel, mass, B: int, N: int, return_layers: bool = False):
         model = self.model
         if model.training and model.norm == "batch":

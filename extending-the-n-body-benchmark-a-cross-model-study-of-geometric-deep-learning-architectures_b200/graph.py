@@ -57,8 +57,9 @@ def build_graph_with_knn(loc, batch_size, num_nodes, device, num_neighbors):
     if num_neighbors >= num_nodes:
         raise ValueError("Graph cannot have more neighbors than there are nodes in simulation - 1")
     if num_neighbors != num_nodes - 1:
-        # :42-80: k nearest neighbours per node.  Only the edge list is built here; the fused SEGNN kernels are
-        # specialised for the complete graph (the configured path, num_neighbors = N - 1) and refuse anything else.
+        # :42-80: k nearest neighbours per node.  The fused SEGNN kernels are specialised for the complete graph (the
+        # configured path, num_neighbors = N - 1); a model run on this edge list takes the generic-irreps kernels
+        # (SEGNN.forward_edge_list, inference).
         return ops.knn_edge_index(loc, int(batch_size), num_nodes, num_neighbors, device)
     return _build_fully_connected_edge_index(batch_size, num_nodes, device)
 

@@ -150,8 +150,18 @@ class O3Transform:
     def __call__(self, graph):
         b, n = infer_graph_shape(graph)
         graph.num_graphs, graph.n_nodes = b, n
-        graph.lmax_attr = self.attr_irreps.lmax  # degree of the lazily materialised edge attributes
-        x, attr = ops.prep(graph.pos, graph.vel, b, n, self.attr_irreps.lmax)
+        graph.lmax_attr = lmax = self.attr_irreps.lmax  # degree of the lazily materialised edge attributes
+        explicit = getattr(graph, "__dict__", {}).get("edge_index")
+        if torch.is_tensor(explicit) and explicit.shape[1] != b * n * (n - 1):
+            # kNN edge list (num_neighbors < N - 1): everything is materialised, as in the reference
+            ei = explicit.to(torch.int64).contiguous()
+            ea, add = ops.edge_attr_list(graph.pos, graph.mass, ei, lmax)
+            order, ptr = ops.edge_list_csr(ei, graph.pos.shape[0])
+            x, attr = ops.prep_list(graph.pos, graph.vel, ea, order, ptr, lmax)
+            graph.edge_attr = ea.to(graph.pos.dtype)
+            graph.additional_message_features = add.to(graph.pos.dtype)
+        else:
+            x, attr = ops.prep(graph.pos, graph.vel, b, n, lmax)
         graph.x = x.to(graph.pos.dtype)
         graph.node_attr = attr.to(graph.pos.dtype)
         return graph

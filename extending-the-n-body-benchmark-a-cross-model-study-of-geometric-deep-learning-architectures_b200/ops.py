@@ -73,6 +73,58 @@ def knn_edge_index(loc: torch.Tensor, batch_size: int, num_nodes: int, num_neigh
     return out
 
 
+def edge_list_csr(edge_index: torch.Tensor, nodes: int):
+    """(order, ptr) of the edges grouped by target (edge_index[1]) in their original order: index plumbing for
+    segnn_segment_reduce; stable sort + searchsorted, no host synchronisation (CUDA-graph capturable)."""
+    dst = edge_index[1].contiguous()
+    sorted_dst, order = torch.sort(dst, stable=True)
+    ptr = torch.searchsorted(sorted_dst, torch.arange(nodes + 1, dtype=torch.int64, device=dst.device))
+    return order.contiguous(), ptr.contiguous()
+
+
+def edge_attr_list(pos: torch.Tensor, mass: torch.Tensor, edge_index: torch.Tensor, lmax_attr: int = 1):
+    """O3Transform's edge part (o3_building_blocks.py:237-245,277) on an explicit edge list."""
+    pos, mass = _f32(pos, "pos"), _f32(mass, "mass").reshape(-1)
+    assert edge_index.dtype == torch.int64 and edge_index.dim() == 2 and edge_index.shape[0] == 2
+    edge_index = edge_index.contiguous()
+    E = edge_index.shape[1]
+    ea = torch.empty((E, (lmax_attr + 1) ** 2), dtype=torch.float32, device=pos.device)
+    add = torch.empty((E, 2), dtype=torch.float32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        check(lib.segnn_edge_attr_list(_p(pos), _p(mass), _p(edge_index), E, int(lmax_attr), _p(ea), _p(add), _stream()),
+              "segnn_edge_attr_list")
+    _bump()
+    return ea, add
+
+
+def segment_reduce(values: torch.Tensor, order: torch.Tensor, ptr: torch.Tensor, mean: bool = False):
+    """out[node] = sum / mean of values[order[ptr[node]:ptr[node + 1]]] in that order (deterministic scatter)."""
+    values = _f32(values, "values")
+    nodes, D = ptr.numel() - 1, values.shape[1]
+    out = torch.empty((nodes, D), dtype=torch.float32, device=values.device)
+    with torch.cuda.device(values.device):
+        check(lib.segnn_segment_reduce(_p(values), _p(order), _p(ptr), nodes, D, int(bool(mean)), _p(out), _stream()),
+              "segnn_segment_reduce")
+    _bump()
+    return out
+
+
+def prep_list(pos: torch.Tensor, vel: torch.Tensor, edge_attr: torch.Tensor, order: torch.Tensor, ptr: torch.Tensor,
+              lmax_attr: int = 1):
+    """x, node_attr of O3Transform (o3_building_blocks.py:253-276) for an explicit edge list: scatter-mean of the
+    incoming edge attributes + harmonics of the velocity, l = 0 slot 1 (segnn.py:148)."""
+    pos, vel = _f32(pos, "pos"), _f32(vel, "vel")
+    nodes = pos.shape[0]
+    mean_attr = segment_reduce(edge_attr, order, ptr, mean=True)
+    x_in = torch.empty((nodes, 7), dtype=torch.float32, device=pos.device)
+    attr = torch.empty((nodes, (lmax_attr + 1) ** 2), dtype=torch.float32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        check(lib.segnn_prep_fwd_list(_p(pos), _p(vel), _p(mean_attr), nodes, int(lmax_attr), _p(x_in), _p(attr),
+                                      _stream()), "segnn_prep_fwd_list")
+    _bump()
+    return x_in, attr
+
+
 def instance_norm(x: torch.Tensor, graph_ptr: torch.Tensor, blocks: torch.Tensor, weight, bias, eps: float):
     """models/segnn/instance_norm.py:53-129; x [rows, dim] fp32, graph_ptr int64 [graphs + 1], blocks int32 [nb, 6]."""
     x = _f32(x, "x")

@@ -29,10 +29,15 @@ class SelfFeedRollout:
     """Device-resident autoregressive rollout of a SEGNN over B independent N-body systems."""
 
     def __init__(self, model, batch_size: int, num_nodes: int, device, max_frames: int, use_cuda_graph: bool = True,
-                 target: str = "pos_dt+vel", allow_train_mode: bool = False):
+                 target: str = "pos_dt+vel", allow_train_mode: bool = False, num_neighbors: Optional[int] = None):
         if target != "pos_dt+vel":
             raise NotImplementedError("only the reference's default target 'pos_dt+vel' is built")
         self.model, self.B, self.N = model, int(batch_size), int(num_nodes)
+        # num_neighbors < N - 1: the kNN graph is rebuilt from the predicted positions every step, as
+        # infer_self_feed.py:175 does (generic-irreps kernels on the edge list); None / N - 1: the complete graph
+        self.num_neighbors = None if num_neighbors is None or int(num_neighbors) == self.N - 1 else int(num_neighbors)
+        if self.num_neighbors is not None and not 1 <= self.num_neighbors < self.N:
+            raise ValueError("Graph cannot have more neighbors than there are nodes in simulation - 1")
         self.allow_train_mode = bool(allow_train_mode)
         self.device = torch.device(device)
         self.nodes = self.B * self.N
@@ -69,7 +74,11 @@ class SelfFeedRollout:
         self.frames_written = 1
 
     def _step_eager(self):
-        pred = self.model.forward_state(self.pos, self.vel, self.mass, self.B, self.N)
+        if self.num_neighbors is not None:
+            ei = ops.knn_edge_index(self.pos, self.B, self.N, self.num_neighbors, self.device)
+            pred = self.model.forward_edge_list(self.pos, self.vel, self.mass, ei)
+        else:
+            pred = self.model.forward_state(self.pos, self.vel, self.mass, self.B, self.N)
         ops.integrate(pred, self.pos, self.vel, self.traj_pos, self.traj_vel, self.frame)
         ops.counter_add(self.frame, 1)
 
@@ -77,7 +86,7 @@ class SelfFeedRollout:
     def capture(self):
         """Warm up (packs weights, sets kernel attributes), then capture one step as a CUDA graph."""
         self._check_mode()
-        if getattr(self.model, "fused", True) and self.model.compute_mode != "generic":
+        if getattr(self.model, "fused", True) and self.model.compute_mode != "generic" and self.num_neighbors is None:
             self.model.packed(self.N - 1)
         state = (self.pos.clone(), self.vel.clone(), self.frame.clone())
         side = torch.cuda.Stream(device=self.device)
@@ -149,10 +158,8 @@ def run_inference(model_type, dataloader, model_path=None, model=None, save_dir=
     B, T, N, _ = loc_actual.shape
     if n_bodies is not None and int(n_bodies) != N:
         raise ValueError("n_bodies does not match the ground-truth trajectories")
-    if num_neighbors is not None and int(num_neighbors) != N - 1:
-        if int(num_neighbors) >= N:
-            raise ValueError("Graph cannot have more neighbors than there are nodes in simulation - 1")
-        raise NotImplementedError("kNN graphs are outside the accelerated fully-connected path")
+    if num_neighbors is not None and int(num_neighbors) >= N:
+        raise ValueError("Graph cannot have more neighbors than there are nodes in simulation - 1")
     if max_rollout_steps is not None and int(max_rollout_steps) > 0:
         T = min(T, int(max_rollout_steps))
         loc_actual, vel_actual = loc_actual[:, :T], vel_actual[:, :T]
@@ -160,7 +167,7 @@ def run_inference(model_type, dataloader, model_path=None, model=None, save_dir=
         print(f"Number of steps to generate: {T}")
     was_training = model.training
     model.eval()
-    roll = SelfFeedRollout(model, B, N, device, max_frames=T)
+    roll = SelfFeedRollout(model, B, N, device, max_frames=T, num_neighbors=num_neighbors)
     roll.reset(loc_actual[:, 0], vel_actual[:, 0], mass_actual.reshape(B, N))
     tp, tv = roll.run(T - 1)
     model.train(was_training)

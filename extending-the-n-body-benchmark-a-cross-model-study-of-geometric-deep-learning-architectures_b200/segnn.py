@@ -466,6 +466,19 @@ class SEGNN(nn.Module):
             return pred, [rec["h"] for rec in saved["layers"]] + [saved["h_last"]]
         return pred
 
+    def forward_edge_list(self, pos, vel, mass, edge_index, return_layers: bool = False):
+        """pos, vel [nodes,3], mass [nodes], edge_index int64 [2,E] (row 0 = source, row 1 = target) -> pred [nodes,6];
+        inference only (eval-mode BatchNorm, no gradients), fp32, any configuration the generic kernels cover."""
+        if (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())) or \
+                (self.training and self.norm == "batch"):
+            raise NotImplementedError("message passing on explicit edge lists (kNN graphs) is inference only: call "
+                                      "model.eval() under torch.no_grad(); training runs on the complete graph "
+                                      "(num_neighbors = N - 1)")
+        from .generic import GenericRunner
+        if self._generic is None or self._generic.embed.instr.device != pos.device:
+            self._generic = GenericRunner(self, pos.device)
+        return self._generic.forward_edge_list(pos, vel, mass.reshape(-1), edge_index, return_layers)
+
     def forward(self, graph, return_layers: bool = False):
         """SEGNN forward pass on a batched implicit graph (reference: segnn.py:150-189)."""
         b, n_nodes = infer_graph_shape(graph)
@@ -474,12 +487,15 @@ class SEGNN(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("SEGNN (B200) needs CUDA tensors: there is no CPU fallback")
         explicit = getattr(graph, "__dict__", {}).get("edge_index")
-        if torch.is_tensor(explicit) and explicit.shape[1] != b * n_nodes * (n_nodes - 1):
-            raise NotImplementedError(
-                f"the kernels are specialised for the complete graph (num_neighbors = N - 1, the configured path): "
-                f"got an explicit edge list with {explicit.shape[1]} edges for {b} graphs of {n_nodes} nodes")
         f32 = lambda t: t.to(torch.float32).contiguous()
         pos, vel, mass = f32(graph.pos), f32(graph.vel), f32(graph.mass).reshape(-1)
+        if torch.is_tensor(explicit) and explicit.shape[1] != b * n_nodes * (n_nodes - 1):
+            # an explicit edge list that is not the complete graph (kNN, num_neighbors < N - 1): generic-irreps kernels
+            # with gathers through edge_index; geometry (x, node_attr, edge_attr) is recomputed from pos / vel / mass
+            out = self.forward_edge_list(pos, vel, mass, explicit, return_layers)
+            if return_layers:
+                return out[0].to(dtype), [h.to(dtype) for h in out[1]]
+            return out.to(dtype)
         x_in = node_attr = None
         if getattr(graph, "x", None) is not None and getattr(graph, "node_attr", None) is not None:
             x_in, node_attr = f32(graph.x), f32(graph.node_attr).clone()

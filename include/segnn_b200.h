@@ -84,6 +84,22 @@ int segnn_edge_attr_lmax(const float* pos, const float* mass, int B, int N, int 
 int segnn_prep_fwd_lmax(const float* pos, const float* vel, int B, int N, int lmax_attr, float* x_in, float* node_attr,
                         segnn_stream_t stream);
 
+/* Explicit edge lists (kNN graphs of utils/build_fully_connected_graph.py:42-80, num_neighbors < N - 1), generic-irreps
+ * path, inference.  edge_index int64 [2,E]: row 0 = source j, row 1 = target i (PyG source_to_target).
+ *   segnn_edge_attr_list              o3_building_blocks.py:237-245,277 on an edge list
+ *   segnn_generic_message_input_list  segnn.py:264-279: out [E, 2D + d_add] = cat(x[target], x[source], add)
+ *   segnn_segment_reduce              segnn.py:205 (sum) / o3_building_blocks.py:257-263 (mean): out[node] = reduction of
+ *                                     values[order[k]] over k in [ptr[node], ptr[node+1]), fixed order, no atomics
+ *   segnn_prep_fwd_list               o3_building_blocks.py:253-276 + segnn.py:148 with the scatter-mean given */
+int segnn_edge_attr_list(const float* pos, const float* mass, const int64_t* edge_index, int64_t E, int lmax_attr,
+                         float* edge_attr, float* add, segnn_stream_t stream);
+int segnn_generic_message_input_list(const float* x, const float* add, const int64_t* edge_index, int64_t E, int D,
+                                     int d_add, float* out, segnn_stream_t stream);
+int segnn_segment_reduce(const float* values, const int64_t* order, const int64_t* ptr, int64_t nodes, int D, int mean,
+                         float* out, segnn_stream_t stream);
+int segnn_prep_fwd_list(const float* pos, const float* vel, const float* mean_attr, int64_t nodes, int lmax_attr,
+                        float* x_in, float* node_attr, segnn_stream_t stream);
+
 /* ---- K2: embedding tensor product ---------------------------------------------------------------- */
 
 /* models/segnn/segnn.py:170 embedding_layer = O3TensorProduct(2x1o+1x0e -> h, node_attr).

@@ -597,11 +597,12 @@ class SEGNN(nn.Module):
 # ----------------------------------------------------------------------------------------------
 
 
-def make_graph(pos, vel, mass, batch_size: int, num_nodes: int, lmax_attr: int = 1):
+def make_graph(pos, vel, mass, batch_size: int, num_nodes: int, lmax_attr: int = 1, num_neighbors=None):
     """dataloaders/segnn_n_body_dataloader.py:9-33 without PyG: attribute bag with the same field names."""
     g = SimpleNamespace(pos=pos, vel=vel, mass=mass.reshape(-1, 1), force=torch.zeros_like(pos))
     g.batch = torch.arange(batch_size).repeat_interleave(num_nodes)
-    g.edge_index = build_graph_with_knn(pos, batch_size, num_nodes, None, num_nodes - 1)
+    g.edge_index = build_graph_with_knn(pos, batch_size, num_nodes, None,
+                                        num_nodes - 1 if num_neighbors is None else num_neighbors)
     return o3_transform(g, lmax_attr)
 
 

@@ -60,10 +60,10 @@ def synthetic(B, N, seed, charged):
     return pos, vel, mass, y
 
 
-def ref_graph(pos, vel, mass, B, N, lmax_attr=1):
+def ref_graph(pos, vel, mass, B, N, lmax_attr=1, num_neighbors=None):
     g = Data(pos=pos.clone(), vel=vel.clone(), force=torch.zeros_like(pos), mass=mass.clone())
     g.batch = torch.arange(B).repeat_interleave(N)
-    g.edge_index = build_graph_with_knn(g.pos, B, N, torch.device("cpu"), N - 1)
+    g.edge_index = build_graph_with_knn(g.pos, B, N, torch.device("cpu"), N - 1 if num_neighbors is None else num_neighbors)
     return O3Transform(lmax_attr)(g)
 
 
@@ -95,7 +95,7 @@ def make_wigner_fixture():
     save("ref_wigner.pt", out)
 
 
-def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True, lmax_attr=1):
+def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True, lmax_attr=1, num_neighbors=None):
     torch.manual_seed(seed)
     model = SEGNN(hidden_features=H, lmax_h=lmax_h, lmax_attr=lmax_attr, num_layers=L).double()
     sd = model.state_dict()
@@ -114,7 +114,7 @@ def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True, lmax_attr=1):
         mods = [model.embedding_layer] + list(model.layers) + [model.pre_pool1]
         for m in mods:
             hooks.append(m.register_forward_hook(lambda _m, _i, o: layers.append(o.detach().clone())))
-        g = ref_graph(pos, vel, mass, B, N, lmax_attr)
+        g = ref_graph(pos, vel, mass, B, N, lmax_attr, num_neighbors)
         g.y = y
         transform = {k: getattr(g, k).detach().clone() for k in ("x", "node_attr", "edge_attr",
                                                                  "additional_message_features", "edge_index")}
@@ -139,6 +139,8 @@ def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True, lmax_attr=1):
     config = dict(hidden_features=H, lmax_h=lmax_h, num_layers=L, B=B, N=N, charged=charged)
     if lmax_attr != 1:  # the key is absent from the lmax_attr = 1 fixtures written before the option existed
         config["lmax_attr"] = lmax_attr
+    if num_neighbors is not None:  # kNN graph (utils/build_fully_connected_graph.py:42-80)
+        config["num_neighbors"] = num_neighbors
     fx = {"kind": KIND, "config": config,
           "hidden_irreps": str(model.hidden_irreps), "num_params": sum(p.numel() for p in model.parameters()),
           "serializable": {k: v for k, v in model.get_serializable_attributes().items()},
@@ -350,8 +352,17 @@ def make_lmax_attr2_fixtures():
     run_model_case("h32_l2_a2_n5", H=32, lmax_h=2, L=2, B=2, N=5, seed=6, lmax_attr=2)
 
 
+def make_knn_fixtures():
+    """SEGNN on kNN graphs (num_neighbors < N - 1, utils/build_fully_connected_graph.py:42-80; variable in-degree)."""
+    run_model_case("h32_knn3_n8", H=32, lmax_h=1, L=2, B=2, N=8, seed=7, num_neighbors=3)
+    run_model_case("h32_l2_knn2_n6", H=32, lmax_h=2, L=2, B=3, N=6, seed=8, num_neighbors=2)
+
+
 if __name__ == "__main__":
     print("third-party provider:", KIND)
+    if sys.argv[1:] == ["knn"]:
+        make_knn_fixtures()
+        sys.exit(0)
     if sys.argv[1:] == ["lmax_attr2"]:
         make_lmax_attr2_fixtures()
         sys.exit(0)
@@ -366,3 +377,4 @@ if __name__ == "__main__":
     make_sim_and_macro_fixture(rollout)
     make_checkpoint_fixture()
     make_lmax_attr2_fixtures()
+    make_knn_fixtures()

@@ -557,6 +557,62 @@ def test_lmax_attr2_rollout_matches_oracle():
     assert rel(got_loc, ref_loc) < 5e-5
 
 
+@pytest.mark.parametrize("H,lmax_h,lmax_attr,L,B,N,k", [(64, 1, 1, 3, 3, 10, 4), (32, 2, 1, 2, 2, 7, 1), (48, 1, 2, 2, 2, 9, 7),
+                                                       (192, 1, 1, 2, 4, 50, 6)])
+def test_knn_graph_forward_matches_oracle(H, lmax_h, lmax_attr, L, B, N, k):
+    """SEGNN on the kNN graphs of build_graph_with_knn (num_neighbors < N - 1; variable in-degree, possibly isolated
+    targets): edge list bit-exact against the oracle's, per-layer parity at the fp32 tolerance, run-to-run identical."""
+    torch.manual_seed(H + k)
+    om = O.SEGNN(hidden_features=H, num_layers=L, lmax_h=lmax_h, lmax_attr=lmax_attr).eval()
+    O.perturb_bn_buffers(om, seed=5)
+    m = S.SEGNN(hidden_features=H, num_layers=L, lmax_h=lmax_h, lmax_attr=lmax_attr)
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().eval()
+    pos, vel, mass = O.synthetic_system(B, N, seed=8)
+    og = O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N, lmax_attr, k)
+    g = gpu_graph(pos, vel, mass, B, N)
+    # the oracle's positions are float64; the edge list is built from the same values (float32 inputs would reorder ties)
+    g.edge_index = S.build_graph_with_knn(pos.reshape(-1, 3).double().cuda(), B, N, "cuda", k)
+    assert torch.equal(g.edge_index.cpu(), og.edge_index)
+    with torch.no_grad():
+        ref, ref_layers = om(og, return_layers=True)
+        out, layers = m(g, return_layers=True)
+        out2 = m(g)
+    print(f"kNN H={H} lmax_h={lmax_h} lmax_attr={lmax_attr} k={k}: per-layer",
+          [f"{rel(a, b):.2e}" for a, b in zip(layers, ref_layers)], f"out {rel(out, ref):.2e}")
+    for a, b in zip(layers, ref_layers):
+        assert rel(a, b) < 1e-5
+    assert rel(out, ref) < 1e-5
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_knn_rollout_matches_oracle(use_graph):
+    """Self-feed rollout with the kNN graph rebuilt from the predicted positions every step
+    (helper_scripts/infer_self_feed.py:175), eager and as a replayed CUDA graph."""
+    torch.manual_seed(12)
+    om = O.SEGNN(hidden_features=32, num_layers=2, lmax_h=1).eval()
+    O.perturb_bn_buffers(om, seed=3)
+    m = S.SEGNN(hidden_features=32, num_layers=2, lmax_h=1)
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().eval()
+    B, N, k, steps = 2, 7, 3, 5
+    pos, vel, mass = O.synthetic_system(B, N, seed=4)
+    loc, v = [pos.double()], [vel.double()]
+    with torch.no_grad():
+        for _ in range(steps):
+            g = O.make_graph(loc[-1].reshape(-1, 3), v[-1].reshape(-1, 3), mass.reshape(-1, 1).double(), B, N, 1, k)
+            pred = om(g).reshape(B, N, 6)
+            loc.append(loc[-1] + pred[..., :3])
+            v.append(pred[..., 3:])
+    roll = S.SelfFeedRollout(m, B, N, "cuda", max_frames=steps + 1, use_cuda_graph=use_graph, num_neighbors=k)
+    roll.reset(pos, vel, mass)
+    tp, tv = roll.run(steps)
+    got = tp.reshape(steps + 1, B, N, 3).permute(1, 0, 2, 3)
+    assert rel(got, torch.stack(loc, dim=1)) < 5e-5
+    assert rel(tv.reshape(steps + 1, B, N, 3).permute(1, 0, 2, 3), torch.stack(v, dim=1)) < 5e-5
+
+
 def test_generic_rollout_lmax2_matches_oracle():
     torch.manual_seed(9)
     om = O.SEGNN(hidden_features=32, num_layers=2, lmax_h=2).eval()
@@ -659,6 +715,19 @@ def test_device_dataloader_contract_and_training_loop(tmp_path):
     model.eval()
     d, loc, vel = S.run_inference("segnn", dl, model=model, save_dir=str(tmp_path), print_step=False)
     assert loc.shape == (2, 16, 30, 5, 3) and np.isfinite(loc).all()
+    # num_neighbors < N - 1: preprocess_batch materialises the kNN edge list, the model runs on it (generic kernels),
+    # run_inference rebuilds the neighbourhood every step; the first predicted frame equals a forward on the batch
+    args.num_neighbors = 2
+    (batch,), _ = dl.get_batch()
+    g = dl.preprocess_batch(batch, "cuda")
+    assert g.edge_index.shape == (2, 16 * 5 * 2) and g.edge_attr.shape == (160, 4) and g.node_attr.shape == (80, 4)
+    with torch.no_grad():
+        pred = model(g)
+    assert pred.shape == (80, 6) and bool(torch.isfinite(pred).all())
+    d, loc2, vel2 = S.run_inference("segnn", dl, model=model, save_dir=str(tmp_path / "knn"), print_step=False,
+                                    num_neighbors=2, max_rollout_steps=6)
+    assert loc2.shape == (2, 16, 6, 5, 3) and np.isfinite(loc2).all()
+    assert np.abs(loc2[1, :, 1] - loc[1, :, 1]).max() > 1e-6  # not the complete-graph rollout
 
 
 import numpy as np  # noqa: E402

@@ -78,6 +78,30 @@ def test_segnn_eval_per_layer_matches_reference(case):
             assert max(errs) < TOL[mode] and rel(out, ref["out"]) < TOL[mode], (mode, errs)
 
 
+@pytest.mark.parametrize("case", ["h32_knn3_n8", "h32_l2_knn2_n6"])
+def test_segnn_on_knn_graph_matches_reference(case):
+    """num_neighbors < N - 1 (utils/build_fully_connected_graph.py:42-80): the kNN edge list bit-exact, O3Transform on it,
+    per-layer outputs of the generic kernels with gathers through edge_index against the reference run."""
+    fx = load(f"ref_segnn_{case}.pt")
+    c = fx["config"]
+    m = cuda_model(fx)
+    ref, tr = fx["eval"], fx["eval"]["transform"]
+    g = graph(fx)
+    g.edge_index = S.build_graph_with_knn(g.pos, c["B"], c["N"], "cuda", c["num_neighbors"])
+    assert torch.equal(g.edge_index.cpu(), tr["edge_index"])
+    g = S.O3Transform(1)(g)
+    assert rel(g.x, tr["x"]) < 2e-6 and rel(g.edge_attr, tr["edge_attr"]) < 2e-6
+    assert rel(g.additional_message_features, tr["additional_message_features"]) < 2e-6
+    assert float((g.node_attr.double().cpu()[:, 1:] - tr["node_attr"][:, 1:]).abs().max()) < 2e-6
+    with torch.no_grad():
+        out, layers = m(g, return_layers=True)
+    errs = [rel(a, b) for a, b in zip(layers, ref["layers"])]
+    print(f"[{case}] per-layer rel err vs reference", [f"{e:.2e}" for e in errs], f"out {rel(out, ref['out']):.2e}")
+    assert max(errs) < 1e-5 and rel(out, ref["out"]) < 1e-5
+    with pytest.raises(NotImplementedError):  # inference only
+        m.train()(g)
+
+
 @pytest.mark.parametrize("case", ["h64_n5", "h192_n8", "h128_n12"])
 def test_segnn_training_step_matches_reference(case):
     """Train-mode BatchNorm forward, loss, hand-written backward and running statistics against the reference's autograd."""

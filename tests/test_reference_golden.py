@@ -158,7 +158,8 @@ def test_module_level_tensor_products_match_reference():
     assert rel(mod(inorm["x"], inorm["batch"]), inorm["y"]) < 1e-12
 
 
-CASES = ["h64_n5", "h192_n8", "h128_n12", "h32_l2_n6", "h32_a2_n6", "h32_l2_a2_n5"]  # a2: lmax_attr = 2
+CASES = ["h64_n5", "h192_n8", "h128_n12", "h32_l2_n6", "h32_a2_n6", "h32_l2_a2_n5",  # a2: lmax_attr = 2
+         "h32_knn3_n8", "h32_l2_knn2_n6"]  # knn: num_neighbors < N - 1
 
 
 def oracle_model(fx):
@@ -179,7 +180,7 @@ def test_segnn_forward_backward_matches_reference(case):
     assert sum(p.numel() for p in m.parameters()) == fx["num_params"]
     assert set(m.state_dict().keys()) == set(fx["state_keys"]) - set(fx["extra_keys"])
     # O3Transform (models/segnn/o3_building_blocks.py:230-278) + the edge order
-    g = O.make_graph(fx["pos"], fx["vel"], fx["mass"], B, N, c.get("lmax_attr", 1))
+    g = O.make_graph(fx["pos"], fx["vel"], fx["mass"], B, N, c.get("lmax_attr", 1), c.get("num_neighbors"))
     tr = fx["eval"]["transform"]
     assert torch.equal(g.edge_index, tr["edge_index"])
     for k in ("x", "edge_attr", "node_attr", "additional_message_features"):  # captured before SEGNN.forward
@@ -195,7 +196,7 @@ def test_segnn_forward_backward_matches_reference(case):
     assert rel(out, ref["out"]) < 1e-10
     # train-mode BatchNorm, loss, gradients, running statistics
     m = oracle_model(fx).train()
-    out, layers = m(O.make_graph(fx["pos"], fx["vel"], fx["mass"], B, N, c.get("lmax_attr", 1)), return_layers=True)
+    out, layers = m(O.make_graph(fx["pos"], fx["vel"], fx["mass"], B, N, c.get("lmax_attr", 1), c.get("num_neighbors")), return_layers=True)
     ref = fx["train"]
     for i, (a, b) in enumerate(zip(layers, ref["layers"])):
         assert rel(a, b) < 1e-10, (case, "train layer", i, rel(a, b))

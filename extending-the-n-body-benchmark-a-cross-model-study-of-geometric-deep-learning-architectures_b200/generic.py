@@ -258,6 +258,14 @@ def _bn_eval_columns(bn, irreps: Irreps):
     return torch.cat(mul).contiguous(), torch.cat(add).contiguous()
 
 
+def _feature_norm(layer, x, B: int, N: int):
+    """segnn.py:257-261: eval-mode BatchNorm (a per-column affine) or InstanceNorm over the N nodes of each graph."""
+    if layer.norm == "instance":
+        return layer.feature_norm.forward_equal_graphs(x, B, N)
+    mul, addc = _bn_eval_columns(layer.feature_norm, layer.hidden_irreps)
+    return ops.lincomb(x, None, mul, None, addc)
+
+
 USE_L2_ROWS = True  # False: every layer through the table-driven generic kernels (the checker of the l2 form)
 _L2_TYPES = [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0), (1, 1, 2), (2, 0, 2), (2, 1, 1)]
 
@@ -429,7 +437,7 @@ class GenericRunner:
         self.pool2 = tp(model.pre_pool2)
 
     @torch.no_grad()
-    def forward_edge_list(self, pos, vel, mass, edge_index, return_layers: bool = False):
+    def forward_edge_list(self, pos, vel, mass, edge_index, B: int, N: int, return_layers: bool = False):
         """SEGNN.forward (segnn.py:150-189) on an explicit edge list -- the kNN graphs build_graph_with_knn returns for
         num_neighbors < N - 1 (utils/build_fully_connected_graph.py:42-80): gathered message input, one tensor product
         per call, eval BatchNorm per edge, deterministic segment sum over the incoming edges of every node."""
@@ -460,8 +468,7 @@ class GenericRunner:
             u = pl["upd2"].run(u, attr)
             x = ops.add3(x, u)
             if layer.feature_norm is not None:
-                mul, addc = _bn_eval_columns(layer.feature_norm, layer.hidden_irreps)
-                x = ops.lincomb(x, None, mul, None, addc)
+                x = _feature_norm(layer, x, B, N)
             per_layer.append(x)
         h = self.g_pool1.run(self.pool1.run(x, attr))
         pred = self.pool2.run(h, attr)
@@ -486,8 +493,7 @@ class GenericRunner:
                 u = pl["upd2"].run(u, attr)
                 x = ops.add3(x, u)
                 if layer.feature_norm is not None:
-                    mul, addc = _bn_eval_columns(layer.feature_norm, layer.hidden_irreps)
-                    x = ops.lincomb(x, None, mul, None, addc)
+                    x = _feature_norm(layer, x, B, N)
                 per_layer.append(x)
                 continue
             if self.hoist_message_layer_1:
@@ -512,8 +518,7 @@ class GenericRunner:
             u = pl["upd2"].run(u, attr)
             x = ops.add3(x, u)
             if layer.feature_norm is not None:
-                mul, addc = _bn_eval_columns(layer.feature_norm, layer.hidden_irreps)
-                x = ops.lincomb(x, None, mul, None, addc)
+                x = _feature_norm(layer, x, B, N)
             per_layer.append(x)
         h = self.g_pool1.run(self.pool1.run(x, attr))
         pred = self.pool2.run(h, attr)

@@ -196,6 +196,14 @@ class InstanceNorm(nn.Module):
     def __repr__(self):
         return f"{self.__class__.__name__} ({self.irreps}, eps={self.eps})"
 
+    def forward_equal_graphs(self, input, num_graphs: int, n_nodes: int):
+        """The same normalisation for ``num_graphs`` graphs of ``n_nodes`` consecutive rows each: no host
+        synchronisation (the form SEGNN's generic path uses, CUDA-graph capturable)."""
+        ptr = torch.arange(num_graphs + 1, dtype=torch.int64, device=input.device) * n_nodes
+        w = self.weight.detach().float().contiguous() if self.affine else None
+        b = self.bias.detach().float().contiguous() if self.affine else None
+        return ops.instance_norm(input.float().contiguous(), ptr, self._blocks.to(input.device), w, b, self.eps)
+
     def forward(self, input, batch):
         if not input.is_cuda:
             raise RuntimeError("InstanceNorm (B200) needs CUDA tensors: there is no CPU fallback")

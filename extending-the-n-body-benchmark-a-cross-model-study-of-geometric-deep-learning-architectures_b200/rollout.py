@@ -76,7 +76,7 @@ class SelfFeedRollout:
     def _step_eager(self):
         if self.num_neighbors is not None:
             ei = ops.knn_edge_index(self.pos, self.B, self.N, self.num_neighbors, self.device)
-            pred = self.model.forward_edge_list(self.pos, self.vel, self.mass, ei)
+            pred = self.model.forward_edge_list(self.pos, self.vel, self.mass, ei, self.B, self.N)
         else:
             pred = self.model.forward_state(self.pos, self.vel, self.mass, self.B, self.N)
         ops.integrate(pred, self.pos, self.vel, self.traj_pos, self.traj_vel, self.frame)

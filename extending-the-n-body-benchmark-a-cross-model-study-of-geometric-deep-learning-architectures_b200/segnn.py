@@ -10,7 +10,7 @@ import torch.nn as nn
 from . import ops, packing, training
 from .graph import infer_graph_shape
 from .irreps import Irreps, weight_balanced_irreps
-from .o3_building_blocks import BatchNorm, O3TensorProduct, O3TensorProductSwishGate
+from .o3_building_blocks import BatchNorm, InstanceNorm, O3TensorProduct, O3TensorProductSwishGate
 
 def _pack_tp(kind: int, mod, n: int):
     """Operand blocks of one tensor product: from the C ABI (segnn_pack_weights) for device parameters; host-resident
@@ -56,6 +56,7 @@ class SEGNNLayer(nn.Module):
         super().__init__()
         input_irreps, hidden_irreps = Irreps(str(input_irreps)), Irreps(str(hidden_irreps))
         self.hidden_irreps = hidden_irreps
+        edge_attr_irreps, node_attr_irreps = Irreps(str(edge_attr_irreps)), Irreps(str(node_attr_irreps))
         add = Irreps(str(additional_message_irreps)) if additional_message_irreps is not None else Irreps()
         message_input_irreps = (2 * input_irreps + add).simplify()
         update_input_irreps = (input_irreps + hidden_irreps).simplify()
@@ -69,15 +70,16 @@ class SEGNNLayer(nn.Module):
         if norm == "batch":
             self.feature_norm = BatchNorm(hidden_irreps)
             self.message_norm = BatchNorm(hidden_irreps)
-        elif norm == "instance":
-            raise NotImplementedError("norm='instance' cannot be selected by the reference's create_model; not built")
+        elif norm == "instance":  # segnn.py:236-237: per-graph normalisation of the node features, no message norm
+            self.feature_norm = InstanceNorm(hidden_irreps)
         if list(add) != [(2, 0, 1)] or list(input_irreps) != list(hidden_irreps):
             raise NotImplementedError(f"SEGNN layers take hidden -> hidden irreps with 2x0e message features; got "
                                       f"input={input_irreps}, hidden={hidden_irreps}, additional={add}")
         # the fused kernels are specialised for n x0e + n x1o (lmax_h = 1); anything else runs the generic path
         # with the steering attributes 1x0e + 1x1o (lmax_attr = 1)
         self.fused = list(hidden_irreps) == [(hidden_irreps[0][0], 0, 1), (hidden_irreps[0][0], 1, -1)] and \
-            list(edge_attr_irreps) == [(1, 0, 1), (1, 1, -1)] and list(node_attr_irreps) == [(1, 0, 1), (1, 1, -1)]
+            list(edge_attr_irreps) == [(1, 0, 1), (1, 1, -1)] and list(node_attr_irreps) == [(1, 0, 1), (1, 1, -1)] \
+            and norm != "instance"  # InstanceNorm depends on the features: it cannot be folded into the kernels
         self.n = hidden_irreps[0][0]
 
     # -- weight packing -----------------------------------------------------------------------------------------
@@ -466,9 +468,11 @@ class SEGNN(nn.Module):
             return pred, [rec["h"] for rec in saved["layers"]] + [saved["h_last"]]
         return pred
 
-    def forward_edge_list(self, pos, vel, mass, edge_index, return_layers: bool = False):
-        """pos, vel [nodes,3], mass [nodes], edge_index int64 [2,E] (row 0 = source, row 1 = target) -> pred [nodes,6];
-        inference only (eval-mode BatchNorm, no gradients), fp32, any configuration the generic kernels cover."""
+    def forward_edge_list(self, pos, vel, mass, edge_index, batch_size: int, num_nodes: int,
+                          return_layers: bool = False):
+        """pos, vel [nodes,3], mass [nodes], edge_index int64 [2,E] (row 0 = source, row 1 = target), batch_size graphs
+        of num_nodes consecutive nodes -> pred [nodes,6]; inference only (eval-mode BatchNorm, no gradients), fp32, any
+        configuration the generic kernels cover."""
         if (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())) or \
                 (self.training and self.norm == "batch"):
             raise NotImplementedError("message passing on explicit edge lists (kNN graphs) is inference only: call "
@@ -477,7 +481,8 @@ class SEGNN(nn.Module):
         from .generic import GenericRunner
         if self._generic is None or self._generic.embed.instr.device != pos.device:
             self._generic = GenericRunner(self, pos.device)
-        return self._generic.forward_edge_list(pos, vel, mass.reshape(-1), edge_index, return_layers)
+        return self._generic.forward_edge_list(pos, vel, mass.reshape(-1), edge_index, int(batch_size), int(num_nodes),
+                                               return_layers)
 
     def forward(self, graph, return_layers: bool = False):
         """SEGNN forward pass on a batched implicit graph (reference: segnn.py:150-189)."""
@@ -492,7 +497,7 @@ class SEGNN(nn.Module):
         if torch.is_tensor(explicit) and explicit.shape[1] != b * n_nodes * (n_nodes - 1):
             # an explicit edge list that is not the complete graph (kNN, num_neighbors < N - 1): generic-irreps kernels
             # with gathers through edge_index; geometry (x, node_attr, edge_attr) is recomputed from pos / vel / mass
-            out = self.forward_edge_list(pos, vel, mass, explicit, return_layers)
+            out = self.forward_edge_list(pos, vel, mass, explicit, b, n_nodes, return_layers)
             if return_layers:
                 return out[0].to(dtype), [h.to(dtype) for h in out[1]]
             return out.to(dtype)

@@ -531,6 +531,8 @@ class SEGNNLayer(nn.Module):
         self.norm = norm
         self.feature_norm = BatchNorm(hidden_irreps, dtype=dtype) if norm == "batch" else None
         self.message_norm = BatchNorm(hidden_irreps, dtype=dtype) if norm == "batch" else None
+        if norm == "instance":  # segnn.py:236-237: per-graph normalisation of the node features only
+            self.feature_norm = InstanceNorm(hidden_irreps, dtype=dtype)
 
     def message(self, x_i, x_j, edge_attr, add):
         inp = torch.cat((x_i, x_j) if add is None else (x_i, x_j, add), dim=-1)
@@ -548,7 +550,7 @@ class SEGNNLayer(nn.Module):
         upd = self.update_layer_2(upd, node_attr)
         x = x + upd
         if self.feature_norm is not None:
-            x = self.feature_norm(x)
+            x = self.feature_norm(x, batch) if self.norm == "instance" else self.feature_norm(x)  # segnn.py:257-261
         return x
 
 

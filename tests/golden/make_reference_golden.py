@@ -95,9 +95,9 @@ def make_wigner_fixture():
     save("ref_wigner.pt", out)
 
 
-def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True, lmax_attr=1, num_neighbors=None):
+def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True, lmax_attr=1, num_neighbors=None, norm="batch"):
     torch.manual_seed(seed)
-    model = SEGNN(hidden_features=H, lmax_h=lmax_h, lmax_attr=lmax_attr, num_layers=L).double()
+    model = SEGNN(hidden_features=H, lmax_h=lmax_h, lmax_attr=lmax_attr, num_layers=L, norm=norm).double()
     sd = model.state_dict()
     extra_keys = sorted(k for k in sd if "output_mask" in k or k.endswith("num_batches_tracked"))
     shapes = {k: tuple(v.shape) for k, v in sd.items() if k not in extra_keys}
@@ -141,6 +141,8 @@ def run_model_case(name, H, lmax_h, L, B, N, seed, charged=True, lmax_attr=1, nu
         config["lmax_attr"] = lmax_attr
     if num_neighbors is not None:  # kNN graph (utils/build_fully_connected_graph.py:42-80)
         config["num_neighbors"] = num_neighbors
+    if norm != "batch":  # segnn.py:226-237
+        config["norm"] = norm
     fx = {"kind": KIND, "config": config,
           "hidden_irreps": str(model.hidden_irreps), "num_params": sum(p.numel() for p in model.parameters()),
           "serializable": {k: v for k, v in model.get_serializable_attributes().items()},
@@ -358,10 +360,20 @@ def make_knn_fixtures():
     run_model_case("h32_l2_knn2_n6", H=32, lmax_h=2, L=2, B=3, N=6, seed=8, num_neighbors=2)
 
 
+def make_instance_norm_fixtures():
+    """norm='instance' (models/segnn/instance_norm.py on the node features, no message norm) and norm=None."""
+    run_model_case("h32_inorm_n6", H=32, lmax_h=1, L=2, B=3, N=6, seed=9, norm="instance")
+    run_model_case("h32_l2_inorm_knn3_n7", H=32, lmax_h=2, L=2, B=2, N=7, seed=10, norm="instance", num_neighbors=3)
+    run_model_case("h32_nonorm_n5", H=32, lmax_h=1, L=2, B=2, N=5, seed=11, norm=None)
+
+
 if __name__ == "__main__":
     print("third-party provider:", KIND)
     if sys.argv[1:] == ["knn"]:
         make_knn_fixtures()
+        sys.exit(0)
+    if sys.argv[1:] == ["instance_norm"]:
+        make_instance_norm_fixtures()
         sys.exit(0)
     if sys.argv[1:] == ["lmax_attr2"]:
         make_lmax_attr2_fixtures()
@@ -378,3 +390,4 @@ if __name__ == "__main__":
     make_checkpoint_fixture()
     make_lmax_attr2_fixtures()
     make_knn_fixtures()
+    make_instance_norm_fixtures()

@@ -613,6 +613,38 @@ def test_knn_rollout_matches_oracle(use_graph):
     assert rel(tv.reshape(steps + 1, B, N, 3).permute(1, 0, 2, 3), torch.stack(v, dim=1)) < 5e-5
 
 
+@pytest.mark.parametrize("H,lmax_h,L,B,N", [(64, 1, 3, 4, 9), (48, 2, 2, 3, 6), (192, 1, 2, 2, 40)])
+def test_instance_norm_model_matches_oracle(H, lmax_h, L, B, N):
+    """norm='instance' (segnn.py:226-237, 257-261; models/segnn/instance_norm.py on the node features of every layer, no
+    message norm): per-layer parity at the fp32 tolerance, and a replayed CUDA-graph rollout step (no host sync)."""
+    torch.manual_seed(H + lmax_h)
+    om = O.SEGNN(hidden_features=H, num_layers=L, lmax_h=lmax_h, norm="instance").eval()
+    with torch.no_grad():
+        for layer in om.layers:
+            layer.feature_norm.weight.uniform_(0.5, 1.5)
+            layer.feature_norm.bias.uniform_(-0.3, 0.3)
+    m = S.SEGNN(hidden_features=H, num_layers=L, lmax_h=lmax_h, norm="instance")
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().eval()
+    assert not m.fused and m.layers[0].message_norm is None
+    pos, vel, mass = O.synthetic_system(B, N, seed=6)
+    with torch.no_grad():
+        ref, ref_layers = om(O.make_graph(pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1), B, N),
+                             return_layers=True)
+        out, layers = m(gpu_graph(pos, vel, mass, B, N), return_layers=True)
+    print(f"instance norm H={H} lmax_h={lmax_h}: per-layer", [f"{rel(a, b):.2e}" for a, b in zip(layers, ref_layers)],
+          f"out {rel(out, ref):.2e}")
+    for a, b in zip(layers, ref_layers):
+        assert rel(a, b) < 1e-5
+    assert rel(out, ref) < 1e-5
+    steps = 3
+    ref_loc, _ = O.rollout(om, pos, vel, mass, steps)
+    roll = S.SelfFeedRollout(m, B, N, "cuda", max_frames=steps + 1, use_cuda_graph=True)
+    roll.reset(pos, vel, mass)
+    tp, _ = roll.run(steps)
+    assert rel(tp.reshape(steps + 1, B, N, 3).permute(1, 0, 2, 3), ref_loc) < 5e-5
+
+
 def test_generic_rollout_lmax2_matches_oracle():
     torch.manual_seed(9)
     om = O.SEGNN(hidden_features=32, num_layers=2, lmax_h=2).eval()

@@ -27,7 +27,7 @@ def rel(a, b):
 def cuda_model(fx, train=False):
     c = fx["config"]
     m = S.SEGNN(hidden_features=c["hidden_features"], lmax_h=c["lmax_h"], lmax_attr=c.get("lmax_attr", 1),
-                num_layers=c["num_layers"])
+                num_layers=c["num_layers"], norm=c.get("norm", "batch"))
     m.load_state_dict(golden_state(fx["shapes"], fx["ranges"], fx["weight_seed"]))
     return m.float().cuda().train(train)
 
@@ -39,7 +39,7 @@ def graph(fx):
 
 
 def modes_for(m, N):
-    if m.lmax_h != 1 or m.lmax_attr != 1:
+    if not m.fused:  # lmax_h = 2, lmax_attr = 2, norm = "instance"
         return ["generic"]
     tc = S.ops.tc_available() and m.n in S.ops.TC_MULTIPLICITIES
     return ["fp32"] + (["bf16", "fp16"] if tc else []) + (["fp16p"] if tc and N % 2 == 0 else [])
@@ -55,7 +55,8 @@ def test_edge_enumeration_matches_reference_bit_exact():
         assert torch.equal(got, case["edge_index"]), (case["B"], case["N"], case["k"])
 
 
-@pytest.mark.parametrize("case", ["h64_n5", "h192_n8", "h128_n12", "h32_l2_n6", "h32_a2_n6", "h32_l2_a2_n5"])
+@pytest.mark.parametrize("case", ["h64_n5", "h192_n8", "h128_n12", "h32_l2_n6", "h32_a2_n6", "h32_l2_a2_n5",
+                                  "h32_inorm_n6", "h32_nonorm_n5"])
 def test_segnn_eval_per_layer_matches_reference(case):
     fx = load(f"ref_segnn_{case}.pt")
     c = fx["config"]
@@ -78,7 +79,7 @@ def test_segnn_eval_per_layer_matches_reference(case):
             assert max(errs) < TOL[mode] and rel(out, ref["out"]) < TOL[mode], (mode, errs)
 
 
-@pytest.mark.parametrize("case", ["h32_knn3_n8", "h32_l2_knn2_n6"])
+@pytest.mark.parametrize("case", ["h32_knn3_n8", "h32_l2_knn2_n6", "h32_l2_inorm_knn3_n7"])
 def test_segnn_on_knn_graph_matches_reference(case):
     """num_neighbors < N - 1 (utils/build_fully_connected_graph.py:42-80): the kNN edge list bit-exact, O3Transform on it,
     per-layer outputs of the generic kernels with gathers through edge_index against the reference run."""

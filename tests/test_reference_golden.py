@@ -159,13 +159,14 @@ def test_module_level_tensor_products_match_reference():
 
 
 CASES = ["h64_n5", "h192_n8", "h128_n12", "h32_l2_n6", "h32_a2_n6", "h32_l2_a2_n5",  # a2: lmax_attr = 2
-         "h32_knn3_n8", "h32_l2_knn2_n6"]  # knn: num_neighbors < N - 1
+         "h32_knn3_n8", "h32_l2_knn2_n6",  # knn: num_neighbors < N - 1
+         "h32_inorm_n6", "h32_l2_inorm_knn3_n7", "h32_nonorm_n5"]  # norm = "instance" / None
 
 
 def oracle_model(fx):
     c = fx["config"]
     m = O.SEGNN(hidden_features=c["hidden_features"], lmax_h=c["lmax_h"], lmax_attr=c.get("lmax_attr", 1),
-                num_layers=c["num_layers"])
+                num_layers=c["num_layers"], norm=c.get("norm", "batch"))
     m.load_state_dict(golden_state(fx["shapes"], fx["ranges"], fx["weight_seed"]))
     return m
 

@@ -35,6 +35,59 @@ def test_cabi_argument_errors_without_gpu():
                                     None, None, None, None, None) == 0
 
 
+def test_untaken_branch_exports_argument_errors_without_gpu():
+    """lmax_attr <= 2 geometry and the edge-list (kNN) entry points: argument checks run before any launch."""
+    lib = S._lib.lib
+    assert lib.segnn_prep_fwd_lmax(None, None, 2, 5, 3, None, None, None) == -1 and b"lmax_attr" in lib.segnn_last_error()
+    assert lib.segnn_edge_attr_lmax(None, None, 2, 5, 2, None, None, None) == -1 and b"null" in lib.segnn_last_error()
+    assert lib.segnn_edge_attr_lmax(None, None, 0, 5, 2, None, None, None) == 0
+    assert lib.segnn_edge_attr_list(None, None, None, 0, 1, None, None, None) == 0  # empty edge list is a no-op
+    assert lib.segnn_edge_attr_list(None, None, None, 4, 1, None, None, None) == -1
+    assert lib.segnn_generic_message_input_list(None, None, None, 4, 0, 2, None, None) == -1
+    assert lib.segnn_segment_reduce(None, None, None, 0, 8, 0, None, None) == 0
+    assert lib.segnn_segment_reduce(None, None, None, 3, 8, 0, None, None) == -1
+    assert lib.segnn_prep_fwd_list(None, None, None, 3, 1, None, None, None) == -1
+
+
+def test_edge_list_csr_groups_edges_by_target_in_edge_order():
+    """Index plumbing of segnn_segment_reduce: stable sort of the targets + searchsorted; isolated targets get an
+    empty segment; the order inside a segment is the edge order (what makes the sum reproducible)."""
+    ei = torch.tensor([[0, 1, 2, 3, 4, 0, 2], [3, 3, 0, 1, 3, 1, 0]])
+    order, ptr = S.ops.edge_list_csr(ei, 6)
+    assert ptr.tolist() == [0, 2, 4, 4, 7, 7, 7]  # nodes 2, 4, 5 receive nothing
+    assert order.tolist() == [2, 6, 3, 5, 0, 1, 4]
+    o2 = O.knn_edge_index(torch.randn(2 * 7, 3, dtype=torch.float64), 2, 7, 3)
+    order, ptr = S.ops.edge_list_csr(o2, 14)
+    assert int(ptr[-1]) == o2.shape[1] and torch.equal(o2[1][order], torch.sort(o2[1]).values)
+    for node in range(14):
+        seg = order[ptr[node]: ptr[node + 1]]
+        assert bool((o2[1][seg] == node).all()) and seg.tolist() == sorted(seg.tolist())
+
+
+def test_configuration_routing_of_the_untaken_branches():
+    """lmax_attr = 2, norm = 'instance' and string irreps: which configurations take the fused kernels."""
+    from segnn_b200.generic import GenericRunner
+    m = S.SEGNN(hidden_features=32, lmax_h=2, lmax_attr=2, num_layers=1)
+    om = O.SEGNN(hidden_features=32, lmax_h=2, lmax_attr=2, num_layers=1)
+    assert not m.fused and str(m.hidden_irreps).replace(" ", "") == str(om.hidden_irreps).replace(" ", "")
+    assert set(m.state_dict()) == set(om.state_dict())
+    r = GenericRunner(m, "cpu")  # plans are host-side tables
+    assert not r.use_l2_rows and r.layers[0]["msg1h"].n_pairs == 11 and r.layers[0]["msg1h"].n_adds == 3
+    assert r.embed.cg.shape[1:] == (5, 5, 5)
+    mi = S.SEGNN(hidden_features=32, num_layers=1, norm="instance")
+    assert not mi.fused and mi.layers[0].message_norm is None
+    assert set(mi.state_dict()) == set(O.SEGNN(hidden_features=32, num_layers=1, norm="instance").state_dict())
+    assert S.SEGNN(hidden_features=32, num_layers=1, norm=None).fused
+    h = "16x0e+16x1o"
+    assert S.SEGNNLayer(h, h, h, "1x0e+1x1o", "1x0e+1x1o", norm="batch", additional_message_irreps="2x0e").fused
+    assert not S.SEGNNLayer(h, h, h, "1x0e+1x1o+1x2e", "1x0e+1x1o+1x2e", norm="batch",
+                            additional_message_irreps="2x0e").fused
+    with pytest.raises(NotImplementedError):
+        S.SEGNN(hidden_features=32, lmax_attr=3)
+    with pytest.raises(ValueError):
+        S.SelfFeedRollout(S.SEGNN(hidden_features=16, num_layers=1).eval(), 1, 5, "cpu", max_frames=2, num_neighbors=5)
+
+
 def test_no_cpu_fallback():
     model = S.SEGNN(hidden_features=16, num_layers=1).eval()
     g = S.GraphBatch(pos=torch.zeros(4, 3), vel=torch.zeros(4, 3), mass=torch.ones(4, 1), num_graphs=1, n_nodes=4)

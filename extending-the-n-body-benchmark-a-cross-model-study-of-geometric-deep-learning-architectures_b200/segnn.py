@@ -204,18 +204,76 @@ class SEGNNLayer(nn.Module):
     def forward(self, x, edge_index, edge_attr, node_attr, batch, additional_message_features=None, *, pos=None,
                 mass=None, num_graphs=None, n_nodes=None, mode="fp32"):
         """Reference signature (segnn.py:239-247) on e3nn-layout features. The graph is implicit: ``edge_index`` /
-        ``edge_attr`` / ``additional_message_features`` are ignored and recomputed from ``pos`` / ``mass``."""
-        if pos is None or mass is None or num_graphs is None or n_nodes is None:
-            raise ValueError("SEGNNLayer.forward needs pos, mass, num_graphs, n_nodes (implicit complete graph)")
-        if not self.fused:
-            raise NotImplementedError("standalone SEGNNLayer.forward is built for lmax_h = 1; use SEGNN.forward")
-        if self.training:
+        ``edge_attr`` / ``additional_message_features`` are ignored and recomputed from ``pos`` / ``mass``.
+
+        Called the way the reference calls it (no ``pos`` / ``mass``: explicit ``edge_index``, ``edge_attr`` and
+        ``additional_message_features``), the layer runs the reference's own formulation on the generic-irreps kernels:
+        any hidden irreps with l <= 2, any edge list, the attributes as given (inference)."""
+        if self.training and self.norm == "batch":
             raise NotImplementedError("train-mode BatchNorm for the standalone layer: use SEGNN.forward")
+        if pos is None or mass is None or num_graphs is None or n_nodes is None:
+            if edge_index is None or edge_attr is None:
+                raise ValueError("SEGNNLayer.forward needs either pos, mass, num_graphs, n_nodes (implicit complete "
+                                 "graph) or the explicit edge_index, edge_attr (+ additional_message_features)")
+            return self._forward_edge_list(x, edge_index, edge_attr, node_attr, batch, additional_message_features)
+        if not self.fused:
+            raise NotImplementedError("the implicit-graph form of the standalone SEGNNLayer.forward is built for "
+                                      "lmax_h = 1; pass edge_index / edge_attr explicitly, or use SEGNN.forward")
         w = self.pack(n_nodes - 1, operand=1 if mode in _FP16_OPERAND_MODES else 0)
         h = packing.to_planar(x.float(), self.n)
         out = self.run(w, _MODES[mode], h, pos.float().contiguous(), mass.float().reshape(-1).contiguous(),
                        node_attr.float().contiguous(), num_graphs, n_nodes)
         return packing.from_planar(out).to(x.dtype)
+
+
+    @torch.no_grad()
+    def _forward_edge_list(self, x, edge_index, edge_attr, node_attr, batch, add):
+        """segnn.py:239-304 as written there: gather (x_i = x[target], x_j = x[source]), message_layer_1 / 2 with their
+        gates, eval BatchNorm per edge, deterministic sum over the incoming edges, update, residual, feature norm."""
+        from .generic import GatePlan, TensorProductPlan, _bn_eval_columns
+        from ._lib import check, lib
+        if not x.is_cuda:
+            raise RuntimeError("SEGNNLayer (B200) needs CUDA tensors: there is no CPU fallback")
+        dev, dtype = x.device, x.dtype
+        plans = self.__dict__.get("_plans")
+        if plans is None or plans["dev"] != dev:
+            tp = lambda m: TensorProductPlan(m, dev)
+            plans = dict(dev=dev, msg1=tp(self.message_layer_1), g_msg1=GatePlan(self.message_layer_1, dev),
+                         msg2=tp(self.message_layer_2), g_msg2=GatePlan(self.message_layer_2, dev),
+                         upd1=tp(self.update_layer_1), g_upd1=GatePlan(self.update_layer_1, dev),
+                         upd2=tp(self.update_layer_2))
+            self.__dict__["_plans"] = plans
+        f32 = lambda t: t.to(torch.float32).contiguous()
+        x, ea, attr = f32(x), f32(edge_attr), f32(node_attr)
+        ei = edge_index.to(device=dev, dtype=torch.int64).contiguous()
+        E, D = ei.shape[1], x.shape[1]
+        d_add = 0 if add is None else add.shape[1]
+        if 2 * D + d_add != self.message_layer_1.irreps_in1.dim:
+            raise ValueError(f"message input has {2 * D + d_add} columns, message_layer_1 takes "
+                             f"{self.message_layer_1.irreps_in1.dim}")
+        addf = f32(add) if add is not None else None
+        inp = torch.empty((E, 2 * D + d_add), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.segnn_generic_message_input_list(ops._p(x), ops._p(addf), ops._p(ei), E, D, d_add, ops._p(inp),
+                                                       ops._stream()), "segnn_generic_message_input_list")
+        ops._bump()
+        m = plans["g_msg1"].run(plans["msg1"].run(inp, ea))
+        m = plans["g_msg2"].run(plans["msg2"].run(m, ea))
+        if self.message_norm is not None:
+            mul, addc = _bn_eval_columns(self.message_norm, self.hidden_irreps)
+            m = ops.lincomb(m, None, mul, None, addc)
+        order, ptr = ops.edge_list_csr(ei, x.shape[0])
+        agg = ops.segment_reduce(m, order, ptr)
+        u = plans["g_upd1"].run(plans["upd1"].run(torch.cat([x, agg], dim=1).contiguous(), attr))
+        u = plans["upd2"].run(u, attr)
+        out = ops.add3(x, u)
+        if self.feature_norm is not None:
+            if self.norm == "instance":
+                out = self.feature_norm(out, batch)
+            else:
+                mul, addc = _bn_eval_columns(self.feature_norm, self.hidden_irreps)
+                out = ops.lincomb(out, None, mul, None, addc)
+        return out.to(dtype)
 
 
 class SEGNN(nn.Module):

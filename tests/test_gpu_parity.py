@@ -203,6 +203,35 @@ def test_standalone_layer_matches_oracle():
     assert rel(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("h,attr,norm", [("24x0e+24x1o", "1x0e+1x1o", "batch"), ("10x0e+10x1o+10x2e", "1x0e+1x1o", "batch"),
+                                         ("12x0e+12x1o+12x2e", "1x0e+1x1o+1x2e", "instance"),
+                                         ("16x0e+16x1o", "1x0e+1x1o+1x2e", None)])
+def test_standalone_layer_on_explicit_edge_list_matches_oracle(h, attr, norm):
+    """SEGNNLayer.forward called the reference's way (segnn.py:239-304: explicit edge_index, edge_attr, node_attr, batch,
+    additional_message_features; here a kNN edge list and ARBITRARY attribute values) runs the generic kernels."""
+    torch.manual_seed(1)
+    B, N, k = 3, 7, 3
+    ol = O.SEGNNLayer(h, h, h, attr, attr, norm=norm, additional_message_irreps="2x0e").eval()
+    if norm == "batch":
+        O.perturb_bn_buffers(ol)
+    sl = S.SEGNNLayer(h, h, h, attr, attr, norm=norm, additional_message_irreps="2x0e")
+    sl.load_state_dict(ol.state_dict())
+    sl = sl.cuda().eval()
+    D, d = O.Irreps(h).dim, O.Irreps(attr).dim
+    ei = O.knn_edge_index(torch.randn(B * N, 3, dtype=torch.float64), B, N, k)
+    E = ei.shape[1]
+    x = torch.randn(B * N, D, dtype=torch.float64)
+    ea, na = torch.randn(E, d, dtype=torch.float64), torch.randn(B * N, d, dtype=torch.float64)
+    add = torch.randn(E, 2, dtype=torch.float64)
+    batch = torch.arange(B).repeat_interleave(N)
+    with torch.no_grad():
+        ref = ol(x, ei, ea, na, batch, add)
+        out = sl(x.float().cuda(), ei.cuda(), ea.float().cuda(), na.float().cuda(), batch.cuda(), add.float().cuda())
+        out2 = sl(x.float().cuda(), ei.cuda(), ea.float().cuda(), na.float().cuda(), batch.cuda(), add.float().cuda())
+    assert out.shape == ref.shape and rel(out, ref) < 1e-5, rel(out, ref)
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_rollout_matches_oracle(use_graph):
     om, m = make_pair(64, 4, seed=3)

@@ -22,6 +22,10 @@ operator                    reference code it replaces                          
 ``edge_layer``              ``SEGNNLayer.message`` + aggregation (``segnn.py:264-284,205``)    ``segnn_edge_layer_bwd``
 ``edge_layer_tc``           same on tcgen05 (bf16 / fp16 / packed-fp16 modes), eval only       --
 ``head``                    ``pre_pool2`` on the gated features (``segnn.py:96-100``)          ``segnn_head_bwd``
+``prep_lmax``               ``O3Transform`` node part for ``lmax_attr`` in 0..2                -- (inputs only)
+``edge_attr_list``          ``O3Transform`` edge part on an explicit (kNN) edge list           -- (inputs only)
+``message_input_list``      ``cat(x_i, x_j, additional_message_features)`` (``segnn.py:264``)  -- (inference)
+``segment_reduce``          PyG ``aggr="add"`` / ``scatter(reduce="mean")`` over the targets   -- (inference)
 ==========================  ================================================================  =====================
 """
 from __future__ import annotations
@@ -34,7 +38,8 @@ from torch import Tensor
 from . import ops
 
 NS = "segnn_b200"
-__all__ = ["prep", "embed", "node_gemm", "tp_combine", "edge_layer", "edge_layer_tc", "head", "NS"]
+__all__ = ["prep", "embed", "node_gemm", "tp_combine", "edge_layer", "edge_layer_tc", "head", "prep_lmax",
+           "edge_attr_list", "message_input_list", "segment_reduce", "NS"]
 
 
 def _cuda(*ts: Optional[Tensor]) -> None:
@@ -285,3 +290,63 @@ def _head_backward(ctx, dpred):
 
 
 head.register_autograd(_head_backward, setup_context=_head_setup)
+
+
+# ---- generic-irreps path: lmax_attr <= 2 geometry and explicit edge lists (kNN graphs), inference -------------------------
+@torch.library.custom_op(f"{NS}::prep_lmax", mutates_args=())
+def prep_lmax(pos: Tensor, vel: Tensor, batch_size: int, num_nodes: int, lmax_attr: int) -> Tuple[Tensor, Tensor]:
+    """(x_in [nodes, 7], node_attr [nodes, (lmax_attr + 1)^2]) of the fully connected graphs, lmax_attr in 0..2."""
+    _cuda(pos, vel)
+    return ops.prep(pos, vel, batch_size, num_nodes, lmax_attr)
+
+
+@prep_lmax.register_fake
+def _(pos, vel, batch_size, num_nodes, lmax_attr):
+    nodes = batch_size * num_nodes
+    return (pos.new_empty((nodes, 7), dtype=torch.float32),
+            pos.new_empty((nodes, (lmax_attr + 1) ** 2), dtype=torch.float32))
+
+
+@torch.library.custom_op(f"{NS}::edge_attr_list", mutates_args=())
+def edge_attr_list(pos: Tensor, mass: Tensor, edge_index: Tensor, lmax_attr: int) -> Tuple[Tensor, Tensor]:
+    """(edge_attr [E, (lmax_attr + 1)^2], additional_message_features [E, 2]) of an int64 edge list [2, E]."""
+    _cuda(pos, mass, edge_index)
+    return ops.edge_attr_list(pos, mass, edge_index, lmax_attr)
+
+
+@edge_attr_list.register_fake
+def _(pos, mass, edge_index, lmax_attr):
+    E = edge_index.shape[1]
+    return pos.new_empty((E, (lmax_attr + 1) ** 2), dtype=torch.float32), pos.new_empty((E, 2), dtype=torch.float32)
+
+
+@torch.library.custom_op(f"{NS}::message_input_list", mutates_args=())
+def message_input_list(x: Tensor, add: Tensor, edge_index: Tensor) -> Tensor:
+    """[E, 2 D + d_add] = cat(x[target], x[source], add) for an int64 edge list [2, E] (row 0 = source)."""
+    _cuda(x, add, edge_index)
+    from ._lib import check, lib
+    x, add, edge_index = x.float().contiguous(), add.float().contiguous(), edge_index.contiguous()
+    E, D, d_add = edge_index.shape[1], x.shape[1], add.shape[1]
+    out = torch.empty((E, 2 * D + d_add), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.segnn_generic_message_input_list(ops._p(x), ops._p(add), ops._p(edge_index), E, D, d_add, ops._p(out),
+                                                   ops._stream()), "segnn_generic_message_input_list")
+    ops._bump()
+    return out
+
+
+@message_input_list.register_fake
+def _(x, add, edge_index):
+    return x.new_empty((edge_index.shape[1], 2 * x.shape[1] + add.shape[1]), dtype=torch.float32)
+
+
+@torch.library.custom_op(f"{NS}::segment_reduce", mutates_args=())
+def segment_reduce(values: Tensor, order: Tensor, ptr: Tensor, mean: bool) -> Tensor:
+    """out[node] = sum (mean) of values[order[ptr[node]:ptr[node + 1]]] in that order: deterministic scatter."""
+    _cuda(values, order, ptr)
+    return ops.segment_reduce(values, order, ptr, mean)
+
+
+@segment_reduce.register_fake
+def _(values, order, ptr, mean):
+    return values.new_empty((ptr.shape[0] - 1, values.shape[1]), dtype=torch.float32)

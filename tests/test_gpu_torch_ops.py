@@ -98,3 +98,36 @@ def test_registered_backward_matches_central_differences():
     grads2 = torch.autograd.grad(_network(d, B, N, n, w), list(w.values()))
     for a, b in zip(grads, grads2):
         assert torch.equal(a, b)
+
+
+def test_edge_list_operators_match_the_module_path():
+    """torch.ops.segnn_b200.{prep_lmax, edge_attr_list, message_input_list, segment_reduce}: opcheck + the values the
+    package's own edge-list path computes (kNN graph, lmax_attr = 2)."""
+    import segnn_b200 as S
+    torch.manual_seed(3)
+    T = torch.ops.segnn_b200
+    B, N, k, D = 2, 9, 3, 24
+    nodes = B * N
+    pos, vel = torch.randn(nodes, 3, device="cuda"), torch.randn(nodes, 3, device="cuda")
+    mass = torch.randn(nodes, device="cuda")
+    ei = S.build_graph_with_knn(pos, B, N, "cuda", k)
+    order, ptr = S.ops.edge_list_csr(ei, nodes)
+    ea, add = T.edge_attr_list(pos, mass, ei, 2)
+    ea2, add2 = S.ops.edge_attr_list(pos, mass, ei, 2)
+    assert torch.equal(ea, ea2) and torch.equal(add, add2)
+    x_in, attr = T.prep_lmax(pos, vel, B, N, 2)
+    # K1 stages the senders in tiles, the lmax kernel sums them in index order: same values to rounding
+    assert attr.shape == (nodes, 9) and float((attr[:, :4] - S.ops.prep(pos, vel, B, N)[1]).abs().max()) < 1e-6
+    x = torch.randn(nodes, D, device="cuda")
+    inp = T.message_input_list(x, add, ei)
+    assert torch.equal(inp, torch.cat([x[ei[1]], x[ei[0]], add], dim=1))
+    vals = torch.randn(ei.shape[1], D, device="cuda")
+    agg = T.segment_reduce(vals, order, ptr, False)
+    ref = torch.zeros(nodes, D, device="cuda", dtype=torch.float64).index_add_(0, ei[1], vals.double())
+    assert float((agg.double() - ref).abs().max()) < 1e-5
+    mean = T.segment_reduce(vals, order, ptr, True)
+    cnt = torch.bincount(ei[1], minlength=nodes).clamp_min(1).unsqueeze(1)
+    assert float((mean.double() - ref / cnt).abs().max()) < 1e-5
+    for op, args in ((T.edge_attr_list, (pos, mass, ei, 2)), (T.prep_lmax, (pos, vel, B, N, 2)),
+                     (T.message_input_list, (x, add, ei)), (T.segment_reduce, (vals, order, ptr, False))):
+        torch.library.opcheck(op, args, test_utils=("test_schema", "test_faketensor"))

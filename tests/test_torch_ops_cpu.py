@@ -6,7 +6,8 @@ import torch
 import segnn_b200  # noqa: F401  (registers torch.ops.segnn_b200.*)
 
 EXPECTED = ["prep", "embed", "embed_bwd", "node_gemm", "node_gemm_wgrad", "tp_combine", "tp_combine_bwd", "edge_layer",
-            "edge_layer_bwd", "edge_layer_tc", "head", "head_bwd"]
+            "edge_layer_bwd", "edge_layer_tc", "head", "head_bwd", "prep_lmax", "edge_attr_list", "message_input_list",
+            "segment_reduce"]
 
 
 def test_every_operator_is_registered_with_a_schema():
@@ -45,3 +46,24 @@ def test_fake_tensor_tracing_of_one_layer():
 def test_cpu_tensors_are_refused():
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         torch.ops.segnn_b200.prep(torch.zeros(12, 3), torch.zeros(12, 3), 2, 6)
+
+
+def test_fake_tensor_tracing_of_the_edge_list_operators():
+    """lmax_attr = 2 geometry + kNN edge list -> message input -> deterministic segment sum, shapes only."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    T = torch.ops.segnn_b200
+    B, N, k, D = 2, 9, 3, 40
+    nodes, E = B * N, B * N * 3
+    with FakeTensorMode():
+        e = lambda *s: torch.empty(*s, device="cuda")
+        pos, vel, mass = e(nodes, 3), e(nodes, 3), e(nodes)
+        ei = torch.empty(2, E, dtype=torch.int64, device="cuda")
+        x_in, attr = T.prep_lmax(pos, vel, B, N, 2)
+        ea, add = T.edge_attr_list(pos, mass, ei, 2)
+        inp = T.message_input_list(e(nodes, D), add, ei)
+        order, ptr = torch.empty(E, dtype=torch.int64, device="cuda"), torch.empty(nodes + 1, dtype=torch.int64, device="cuda")
+        agg = T.segment_reduce(e(E, D), order, ptr, False)
+        assert tuple(attr.shape) == (nodes, 9) and tuple(ea.shape) == (E, 9) and tuple(add.shape) == (E, 2)
+        assert tuple(inp.shape) == (E, 2 * D + 2) and tuple(agg.shape) == (nodes, D)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        T.segment_reduce(torch.zeros(4, 3), torch.zeros(4, dtype=torch.int64), torch.zeros(3, dtype=torch.int64), False)

@@ -437,7 +437,8 @@ class GenericRunner:
         self.pool2 = tp(model.pre_pool2)
 
     @torch.no_grad()
-    def forward_edge_list(self, pos, vel, mass, edge_index, B: int, N: int, return_layers: bool = False):
+    def forward_edge_list(self, pos, vel, mass, edge_index, B: int, N: int, return_layers: bool = False, x_in=None,
+                          node_attr=None):
         """SEGNN.forward (segnn.py:150-189) on an explicit edge list -- the kNN graphs build_graph_with_knn returns for
         num_neighbors < N - 1 (utils/build_fully_connected_graph.py:42-80): gathered message input, one tensor product
         per call, eval BatchNorm per edge, deterministic segment sum over the incoming edges of every node."""
@@ -449,7 +450,10 @@ class GenericRunner:
         E = edge_index.shape[1]
         order, ptr = ops.edge_list_csr(edge_index, nodes)
         ea, add = ops.edge_attr_list(pos, mass, edge_index, model.lmax_attr)
-        x_in, attr = ops.prep_list(pos, vel, ea, order, ptr, model.lmax_attr)
+        if x_in is None or node_attr is None:
+            x_in, attr = ops.prep_list(pos, vel, ea, order, ptr, model.lmax_attr)
+        else:  # the graph's own x / node_attr (e.g. O3Transform(use_force_input=True))
+            attr = node_attr
         x = self.embed.run(x_in, attr)
         per_layer = [x]
         for layer, pl in zip(model.layers, self.layers):
@@ -475,12 +479,15 @@ class GenericRunner:
         return (pred, per_layer) if return_layers else pred
 
     @torch.no_grad()
-    def forward(self, pos, vel, mass, B: int, N: int, return_layers: bool = False):
+    def forward(self, pos, vel, mass, B: int, N: int, return_layers: bool = False, x_in=None, node_attr=None):
         model = self.model
         if model.training and model.norm == "batch":
             raise NotImplementedError("the generic-irreps path implements eval-mode BatchNorm only")
         D = model.hidden_irreps.dim
-        x_in, attr = ops.prep(pos, vel, B, N, model.lmax_attr)
+        if x_in is None or node_attr is None:
+            x_in, attr = ops.prep(pos, vel, B, N, model.lmax_attr)
+        else:  # the graph's own x / node_attr (e.g. O3Transform(use_force_input=True))
+            attr = node_attr
         if not self.use_l2_rows:
             ea, add = ops.edge_attr(pos, mass, B, N, model.lmax_attr)
             E = ea.shape[0]

@@ -142,8 +142,6 @@ class O3Transform:
     def __init__(self, lmax_attr, use_force_input=False):
         if int(lmax_attr) not in (0, 1, 2):
             raise NotImplementedError("O3Transform is built for lmax_attr <= 2")
-        if use_force_input:
-            raise NotImplementedError("use_force_input is never set on the configured path")
         self.attr_irreps = Irreps.spherical_harmonics(int(lmax_attr))
         self.use_force_input = use_force_input
 
@@ -162,6 +160,8 @@ class O3Transform:
             graph.additional_message_features = add.to(graph.pos.dtype)
         else:
             x, attr = ops.prep(graph.pos, graph.vel, b, n, lmax)
+        if self.use_force_input:  # :267-271: node_attr += Y(force)
+            attr = ops.add_vector_harmonics(attr, graph.force, lmax)
         graph.x = x.to(graph.pos.dtype)
         graph.node_attr = attr.to(graph.pos.dtype)
         return graph

@@ -125,6 +125,21 @@ def prep_list(pos: torch.Tensor, vel: torch.Tensor, edge_attr: torch.Tensor, ord
     return x_in, attr
 
 
+def add_vector_harmonics(node_attr: torch.Tensor, vec: torch.Tensor, lmax_attr: int = 1):
+    """node_attr + Y_0..lmax(vec) with the l = 0 slot kept at 1 (o3_building_blocks.py:267-271, use_force_input: the
+    'integral' harmonics of a per-node vector added to the node attributes)."""
+    node_attr, vec = _f32(node_attr, "node_attr"), _f32(vec, "vec")
+    nodes = node_attr.shape[0]
+    assert vec.shape == (nodes, 3) and node_attr.shape[1] == (lmax_attr + 1) ** 2
+    scratch = torch.empty((nodes, 7), dtype=torch.float32, device=vec.device)
+    out = torch.empty_like(node_attr)
+    with torch.cuda.device(vec.device):
+        check(lib.segnn_prep_fwd_list(_p(vec), _p(vec), _p(node_attr), nodes, int(lmax_attr), _p(scratch), _p(out),
+                                      _stream()), "segnn_prep_fwd_list")
+    _bump()
+    return out
+
+
 def instance_norm(x: torch.Tensor, graph_ptr: torch.Tensor, blocks: torch.Tensor, weight, bias, eps: float):
     """models/segnn/instance_norm.py:53-129; x [rows, dim] fp32, graph_ptr int64 [graphs + 1], blocks int32 [nb, 6]."""
     x = _f32(x, "x")

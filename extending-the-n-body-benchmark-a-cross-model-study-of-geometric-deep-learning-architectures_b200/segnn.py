@@ -371,7 +371,7 @@ class SEGNN(nn.Module):
             from .generic import GenericRunner
             if self._generic is None or self._generic.embed.instr.device != pos.device:
                 self._generic = GenericRunner(self, pos.device)
-            return self._generic.forward(pos, vel, mass, batch_size, num_nodes, return_layers)
+            return self._generic.forward(pos, vel, mass, batch_size, num_nodes, return_layers, x_in, node_attr)
         mode = _MODES[self.compute_mode]
         batch_stats_tc = (bn_training and not needs_grad and mode == ops.MODE_FP16_PACKED and num_nodes % 2 == 0
                           and self.n in ops.TC_MULTIPLICITIES)
@@ -527,7 +527,7 @@ class SEGNN(nn.Module):
         return pred
 
     def forward_edge_list(self, pos, vel, mass, edge_index, batch_size: int, num_nodes: int,
-                          return_layers: bool = False):
+                          return_layers: bool = False, x_in=None, node_attr=None):
         """pos, vel [nodes,3], mass [nodes], edge_index int64 [2,E] (row 0 = source, row 1 = target), batch_size graphs
         of num_nodes consecutive nodes -> pred [nodes,6]; inference only (eval-mode BatchNorm, no gradients), fp32, any
         configuration the generic kernels cover."""
@@ -540,7 +540,7 @@ class SEGNN(nn.Module):
         if self._generic is None or self._generic.embed.instr.device != pos.device:
             self._generic = GenericRunner(self, pos.device)
         return self._generic.forward_edge_list(pos, vel, mass.reshape(-1), edge_index, int(batch_size), int(num_nodes),
-                                               return_layers)
+                                               return_layers, x_in, node_attr)
 
     def forward(self, graph, return_layers: bool = False):
         """SEGNN forward pass on a batched implicit graph (reference: segnn.py:150-189)."""
@@ -552,17 +552,17 @@ class SEGNN(nn.Module):
         explicit = getattr(graph, "__dict__", {}).get("edge_index")
         f32 = lambda t: t.to(torch.float32).contiguous()
         pos, vel, mass = f32(graph.pos), f32(graph.vel), f32(graph.mass).reshape(-1)
-        if torch.is_tensor(explicit) and explicit.shape[1] != b * n_nodes * (n_nodes - 1):
-            # an explicit edge list that is not the complete graph (kNN, num_neighbors < N - 1): generic-irreps kernels
-            # with gathers through edge_index; geometry (x, node_attr, edge_attr) is recomputed from pos / vel / mass
-            out = self.forward_edge_list(pos, vel, mass, explicit, b, n_nodes, return_layers)
-            if return_layers:
-                return out[0].to(dtype), [h.to(dtype) for h in out[1]]
-            return out.to(dtype)
         x_in = node_attr = None
         if getattr(graph, "x", None) is not None and getattr(graph, "node_attr", None) is not None:
             x_in, node_attr = f32(graph.x), f32(graph.node_attr).clone()
             node_attr[:, 0] = 1.0  # catch_isolated_nodes, segnn.py:148
+        if torch.is_tensor(explicit) and explicit.shape[1] != b * n_nodes * (n_nodes - 1):
+            # an explicit edge list that is not the complete graph (kNN, num_neighbors < N - 1): generic-irreps kernels
+            # with gathers through edge_index; the edge geometry is recomputed from pos / mass
+            out = self.forward_edge_list(pos, vel, mass, explicit, b, n_nodes, return_layers, x_in, node_attr)
+            if return_layers:
+                return out[0].to(dtype), [h.to(dtype) for h in out[1]]
+            return out.to(dtype)
         out = self.forward_state(pos, vel, mass, b, n_nodes, x_in, node_attr, return_layers)
         if return_layers:
             unpack = packing.from_planar if (self.fused and self.compute_mode != "generic") else (lambda h: h)

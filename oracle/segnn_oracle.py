@@ -490,7 +490,7 @@ def build_graph_with_knn(loc, batch_size, num_nodes, device=None, num_neighbors=
     return fully_connected_edge_index(batch_size, num_nodes)
 
 
-def o3_transform(graph, lmax_attr: int = 1):
+def o3_transform(graph, lmax_attr: int = 1, use_force_input: bool = False):
     """models/segnn/o3_building_blocks.py:230-278: attaches edge_attr, node_attr, x, additional_message_features."""
     pos, vel, mass = graph.pos, graph.vel, graph.mass
     src, tgt = graph.edge_index[0], graph.edge_index[1]
@@ -503,6 +503,8 @@ def o3_transform(graph, lmax_attr: int = 1):
     summed = torch.zeros(num_nodes, graph.edge_attr.shape[1], dtype=pos.dtype).index_add_(0, tgt, graph.edge_attr)
     count = torch.zeros(num_nodes, dtype=pos.dtype).index_add_(0, tgt, torch.ones_like(tgt, dtype=pos.dtype))
     graph.node_attr = summed / count.clamp_min(1).unsqueeze(1) + vel_emb
+    if use_force_input:  # :267-271
+        graph.node_attr = graph.node_attr + spherical_harmonics(lmax_attr, graph.force)
     vel_abs = vel.pow(2).sum(1, keepdim=True).sqrt()
     mean_pos = pos.mean(1, keepdim=True)  # reference quirk: mean over xyz of each node
     graph.x = torch.cat((pos - mean_pos, vel, vel_abs), 1)

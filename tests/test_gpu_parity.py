@@ -540,6 +540,38 @@ def test_o3_transform_lmax_attr2_matches_oracle(B, N):
     assert torch.all(g.node_attr[:, 0] == 1.0) or rel(g.node_attr[:, 0], ref.node_attr[:, 0]) < 2e-6
 
 
+@pytest.mark.parametrize("lmax_attr,k,mode", [(1, None, "fp32"), (1, None, "generic"), (2, None, "fp32"), (1, 3, "fp32")])
+def test_use_force_input_matches_oracle(lmax_attr, k, mode):
+    """O3Transform(use_force_input=True) (o3_building_blocks.py:267-271: node_attr += Y(force)) and a model forward on
+    the graph's own x / node_attr: fused kernels, generic kernels, lmax_attr = 2, and a kNN edge list."""
+    from types import SimpleNamespace
+    torch.manual_seed(21)
+    B, N, H, L = 3, 8, 32, 2
+    om = O.SEGNN(hidden_features=H, num_layers=L, lmax_attr=lmax_attr).eval()
+    O.perturb_bn_buffers(om, seed=5)
+    m = S.SEGNN(hidden_features=H, num_layers=L, lmax_attr=lmax_attr, compute_mode=mode)
+    m.load_state_dict(om.state_dict())
+    m = m.float().cuda().eval()
+    pos, vel, mass = O.synthetic_system(B, N, seed=6)
+    pos, vel, mass = pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1)
+    force = torch.randn(B * N, 3, dtype=torch.float64)
+    og = SimpleNamespace(pos=pos, vel=vel, mass=mass, force=force, batch=torch.arange(B).repeat_interleave(N),
+                         edge_index=O.build_graph_with_knn(pos, B, N, None, N - 1 if k is None else k))
+    og = O.o3_transform(og, lmax_attr, use_force_input=True)
+    g = gpu_graph(pos, vel, mass, B, N)
+    g.force = force.float().cuda()
+    if k is not None:
+        g.edge_index = S.build_graph_with_knn(pos.cuda(), B, N, "cuda", k)
+    g = S.O3Transform(lmax_attr, use_force_input=True)(g)
+    assert float((g.node_attr.double().cpu()[:, 1:] - og.node_attr[:, 1:]).abs().max()) < 2e-6
+    plain = S.O3Transform(lmax_attr)(gpu_graph(pos, vel, mass, B, N)).node_attr
+    assert k is not None or float((g.node_attr - plain).abs().max()) > 1e-2  # the force term is there
+    with torch.no_grad():
+        ref = om(og)
+        out = m(g)
+    assert rel(out, ref) < 1e-5, rel(out, ref)
+
+
 @pytest.mark.parametrize("H,lmax_h,L,B,N", [(32, 1, 2, 3, 5), (64, 2, 2, 2, 6), (128, 1, 2, 2, 33), (96, 2, 1, 1, 40)])
 def test_lmax_attr2_matches_oracle(H, lmax_h, L, B, N):
     """lmax_attr = 2 (steering attributes 1x0e + 1x1o + 1x2e, models/segnn/segnn.py:22,36,47): every tensor product of the

@@ -46,6 +46,21 @@ for H, lmax_h, L, B, N, seed in [(64, 1, 3, 4, 5, 0), (48, 2, 2, 2, 7, 1), (96, 
             ga = torch.autograd.grad(a.pow(2).sum(), ref.layers[0].message_layer_1.tp.weight)[0]
             gb = torch.autograd.grad(b.pow(2).sum(), om.layers[0].message_layer_1.tp.weight)[0]
             worst = max(worst, float((ga - gb).abs().max() / gb.abs().max()))
+# O3Transform(lmax_attr = 2, use_force_input = True) (o3_building_blocks.py:267-271), on a kNN graph
+from types import SimpleNamespace
+torch.manual_seed(9)
+B, N, k = 2, 7, 3
+pos, vel, mass = O.synthetic_system(B, N, seed=4)
+pos, vel, mass = pos.reshape(-1, 3), vel.reshape(-1, 3), mass.reshape(-1, 1)
+force = torch.randn_like(pos)
+g = Data(pos=pos.clone(), vel=vel.clone(), force=force.clone(), mass=mass.clone())
+g.edge_index = build_graph_with_knn(g.pos, B, N, torch.device("cpu"), k)
+g = O3Transform(2, use_force_input=True)(g)
+og = SimpleNamespace(pos=pos, vel=vel, mass=mass, force=force, edge_index=O.build_graph_with_knn(pos, B, N, None, k))
+og = O.o3_transform(og, 2, use_force_input=True)
+assert torch.equal(g.edge_index, og.edge_index)
+for key in ("node_attr", "edge_attr", "x", "additional_message_features"):
+    worst = max(worst, float((getattr(g, key) - getattr(og, key)).abs().max()))
 print("KIND", kind, "WORST", worst)
 assert worst < 1e-10, worst
 '''

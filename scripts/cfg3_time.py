@@ -3,7 +3,7 @@ sys.path.insert(0, "/root/repo")
 import torch, bench
 import segnn_b200 as S
 dev = torch.device("cuda", 0)
-for B in (4, 16):
+for B in (16, 64):
     N = 100
     torch.manual_seed(0)
     m = S.SEGNN(hidden_features=192, num_layers=6, lmax_h=2).to(dev).eval()

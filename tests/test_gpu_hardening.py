@@ -199,3 +199,40 @@ def test_gemm_form_writes_inside_its_buffers(monkeypatch):
         n_bufs, bad = guard.check()
     assert n_bufs > 20 and bad == 0, (n_bufs, bad)
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("H,lmax_h,lmax_attr,norm,B,N,k", [(32, 1, 2, "batch", 3, 7, None), (48, 2, 2, "instance", 2, 9, 4),
+                                                           (64, 1, 1, "batch", 5, 33, 6), (32, 2, 1, None, 2, 6, 1)])
+def test_generic_and_edge_list_kernels_write_inside_their_buffers(H, lmax_h, lmax_attr, norm, B, N, k):
+    """lmax_attr = 2 geometry, [5][5][5] tensor products (tiled and expand + GEMM + scatter forms), edge-list gathers,
+    segment reduction, instance norm, force harmonics: guard bands intact on ragged shapes, results run-to-run identical
+    (no atomics anywhere on these paths), standalone layer included."""
+    torch.manual_seed(H + N)
+    m = S.SEGNN(hidden_features=H, num_layers=2, lmax_h=lmax_h, lmax_attr=lmax_attr, norm=norm).float().cuda().eval()
+    pos, vel, mass = O.synthetic_system(B, N, seed=H)
+    outs = []
+    with torch.no_grad(), GuardedAllocations() as guard:
+        for _ in range(2):
+            g = _graph(pos, vel, mass, B, N)
+            g.force = torch.randn(B * N, 3).cuda() if not outs else g_force
+            g_force = g.force
+            if k is not None:
+                g.edge_index = S.build_graph_with_knn(g.pos, B, N, "cuda", k)
+            g = S.O3Transform(lmax_attr, use_force_input=True)(g)
+            out = m(g)
+            assert torch.isfinite(out).all()
+            layer = m.layers[0]
+            ei = g.edge_index if k is not None else S.build_graph_with_knn(g.pos, B, N, "cuda", N - 1)
+            ea, add = S.ops.edge_attr_list(g.pos, g.mass, ei, lmax_attr)
+            D = m.hidden_irreps.dim
+            x = torch.linspace(-1, 1, B * N * D, device="cuda").reshape(B * N, D).contiguous()
+            lo = layer(x, ei, ea, g.node_attr, g.batch if hasattr(g, "batch") else
+                       torch.arange(B, device="cuda").repeat_interleave(N), add)
+            outs.append((out.clone(), lo.clone()))
+        if k is not None:
+            roll = S.SelfFeedRollout(m, B, N, "cuda", max_frames=3, use_cuda_graph=False, num_neighbors=k)
+            roll.reset(pos, vel, mass)
+            roll.run(2)
+        n_bufs, bad = guard.check()
+    assert n_bufs > 20 and bad == 0, (n_bufs, bad)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

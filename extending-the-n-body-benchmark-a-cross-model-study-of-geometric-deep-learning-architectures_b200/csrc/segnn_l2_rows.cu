@@ -69,6 +69,7 @@ struct EdgeCtx {
   const float *yi0, *yi1, *yi2, *yj0, *yj1, *yj2, *M;
   float len, mm;
   long long row;
+  bool live;  // false: the lane has no edge in this pass (paired remainder pass of an odd edge count)
 };
 
 // CW channels of a lane at once (u = lane + 32 (c0 + c)): message_layer_1 coupling, gate, message_layer_2 coupling
@@ -83,7 +84,7 @@ __device__ __forceinline__ void edge_channels(const RowsArgs& a, const EdgeCtx& 
     bool on[CW];
 #pragma unroll
     for (int c = 0; c < CW; ++c) {
-      on[c] = lane + 32 * (c0 + c) < n;
+      on[c] = e.live && lane + 32 * (c0 + c) < n;
       uc[c] = on[c] ? lane + 32 * (c0 + c) : n - 1;
     }
     // ---- message_layer_1: 0e outputs (scalar u, gate of 1o_u, gate of 2e_u) -------------------------------------
@@ -196,9 +197,9 @@ __device__ __forceinline__ void edge_channels(const RowsArgs& a, const EdgeCtx& 
     }
 }
 
-__global__ void __launch_bounds__(kWarps * 32) l2_msg_rows_kernel(const RowsArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, 4) l2_msg_rows_kernel(const RowsArgs a) {
   __shared__ float cg_s[kTypes * 75];
-  __shared__ __align__(16) float Ms[kWarps][kTypes * 25];
+  __shared__ __align__(16) float Ms[kWarps][2][kTypes * 25];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = a.n, N = a.N;
   for (int t = threadIdx.x; t < kTypes * 75; t += blockDim.x) cg_s[t] = a.cg[t];
@@ -212,34 +213,53 @@ __global__ void __launch_bounds__(kWarps * 32) l2_msg_rows_kernel(const RowsArgs
   const float* yi2 = a.Y[2] + (base + ir) * 5 * a.ldy[2];
   const float pix = a.pos[(base + ir) * 3 + 0], piy = a.pos[(base + ir) * 3 + 1], piz = a.pos[(base + ir) * 3 + 2];
   const float mi = a.mass[base + ir];
-  float* M = Ms[warp];
-  for (int j = warp; j < N; j += kWarps) {
-    // ---- per edge: attribute, additional scalars, the seven coupling matrices ------------------------------------
-    float ux, uy, uz, len;
-    unit_vec(a.pos[(base + j) * 3 + 0] - pix, a.pos[(base + j) * 3 + 1] - piy, a.pos[(base + j) * 3 + 2] - piz, ux, uy,
-             uz, len);
-    const float at[4] = {kY0, kY1 * ux, kY1 * uy, kY1 * uz};
-    const float mm = a.mass[base + j] * mi;
+  // Two edges (senders j and j + kWarps) per iteration: the passes over full groups of 32 channels run per edge; the
+  // remainder pass (n mod 32 channels, 9 of 32 lanes for the n = 73 of BASELINE configuration 3) runs ONCE for both
+  // edges when it fits half a warp, lanes 0-15 on the first edge and 16-31 on the second.
+  const int full = n / 32, rem = n - 32 * full;
+  const bool paired = rem > 0 && rem <= 16;
+  for (int j = warp; j < N; j += 2 * kWarps) {
+    const int jb = j + kWarps;
+    const bool live_b = jb < N;
+    float len2[2], mm2[2];
     __syncwarp();
-    for (int idx = lane; idx < kTypes * 25; idx += 32) {
-      const int t = idx / 25, r = idx - t * 25, i = r / 5, k = r - i * 5;
-      const int d2 = t == 0 || t == 2 || t == 5 ? 1 : 3;   // kD2
-      const int jo = d2 == 1 ? 0 : 1;                      // offset of the attribute irrep (0e at 0, 1o at 1)
-      float m = 0.f;
-      for (int jj = 0; jj < d2; ++jj) m = fmaf(cg_s[t * 75 + (i * 3 + jj) * 5 + k], at[jo + jj], m);
-      M[idx] = m;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // ---- per edge: attribute, additional scalars, the seven coupling matrices ----------------------------------
+      const int jj = h == 0 ? j : (live_b ? jb : j);
+      float ux, uy, uz, len;
+      unit_vec(a.pos[(base + jj) * 3 + 0] - pix, a.pos[(base + jj) * 3 + 1] - piy, a.pos[(base + jj) * 3 + 2] - piz, ux,
+               uy, uz, len);
+      const float at[4] = {kY0, kY1 * ux, kY1 * uy, kY1 * uz};
+      len2[h] = len;
+      mm2[h] = a.mass[base + jj] * mi;
+      float* M = Ms[warp][h];
+      for (int idx = lane; idx < kTypes * 25; idx += 32) {
+        const int t = idx / 25, r = idx - t * 25, i = r / 5, k = r - i * 5;
+        const int d2 = t == 0 || t == 2 || t == 5 ? 1 : 3;   // kD2
+        const int jo = d2 == 1 ? 0 : 1;                      // offset of the attribute irrep (0e at 0, 1o at 1)
+        float m = 0.f;
+        for (int q = 0; q < d2; ++q) m = fmaf(cg_s[t * 75 + (i * 3 + q) * 5 + k], at[jo + q], m);
+        M[idx] = m;
+      }
     }
     __syncwarp();
-    const float* yj0 = a.Y[0] + (base + j) * a.ldy[0];
-    const float* yj1 = a.Y[1] + (base + j) * 3 * a.ldy[1];
-    const float* yj2 = a.Y[2] + (base + j) * 5 * a.ldy[2];
-    const long long row = rl * N + j;
-    {
-      EdgeCtx e{yi0, yi1, yi2, yj0, yj1, yj2, M, len, mm, row};
-      // one channel per lane and pass: two at once (edge_channels<2>, every coupling coefficient read once for both)
-      // was measured slower -- 168+ registers against 128 cost more occupancy than the shared-memory reads saved
-      for (int c0 = 0; 32 * c0 < n; ++c0) edge_channels<1>(a, e, c0, lane);
+    auto ctx = [&](int h) {
+      const int jj = (h != 0 && live_b) ? jb : j;
+      return EdgeCtx{yi0, yi1, yi2, a.Y[0] + (base + jj) * a.ldy[0], a.Y[1] + (base + jj) * 3 * a.ldy[1],
+                     a.Y[2] + (base + jj) * 5 * a.ldy[2], Ms[warp][h != 0], h != 0 ? len2[1] : len2[0],
+                     h != 0 ? mm2[1] : mm2[0], rl * N + jj, h == 0 || live_b};
+    };
+    // one channel per lane and pass: two at once (edge_channels<2>, every coupling coefficient read once for both)
+    // was measured slower -- 168+ registers against 128 cost more occupancy than the shared-memory reads saved
+    const int npass = paired ? full : full + (rem > 0 ? 1 : 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < npass; ++c0) {
+#pragma unroll 1
+      for (int h = 0; h < (live_b ? 2 : 1); ++h) edge_channels<1>(a, ctx(h), c0, lane);
     }
+    if (paired)  // lanes 0-15: first edge, 16-31: second; lanes whose channel 32 full + (lane & 15) >= n store nothing
+      edge_channels<1>(a, ctx(lane >> 4), full, lane & 15);
   }
 }
 
